@@ -1,0 +1,161 @@
+/*
+ * mega_reads_b200.h -- C ABI of the B200-native create_mega_reads / jf_aligner hot path.
+ *
+ * The reference (alekseyzimin/PacBio) has no FFI; the path lives behind three C++ class seams
+ * inside one process.  Each entry point below replaces one of those seams (cited per function,
+ * paths relative to the reference root) so that the host driver stays a transliteration of
+ * src_jf_aligner/create_mega_reads.cc:25-167.
+ *
+ * Conventions
+ *  - plain C types only; host buffers belong to the caller, all device memory to the library;
+ *  - every call returns 0 on success, a negative MR_E* code otherwise; mr_last_error() gives text;
+ *  - a context is bound to ONE GPU and is thread-compatible (one driver thread per context), the
+ *    analogue of the reference's shared-const-index + per-thread-scratch model
+ *    (coarse_aligner.hpp:126-148, overlap_graph.hpp:161-172);
+ *  - there is NO CPU fallback: without a CUDA device mr_context_create fails with MR_ENODEV.
+ */
+#ifndef MEGA_READS_B200_H
+#define MEGA_READS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_OK        0
+#define MR_EINVAL   -1   /* bad argument / unsupported option value          */
+#define MR_ENODEV   -2   /* no usable CUDA device                            */
+#define MR_ECUDA    -3   /* CUDA runtime error (text in mr_last_error)       */
+#define MR_ENOMEM   -4   /* host or device allocation failed                 */
+#define MR_ELIMIT   -5   /* input exceeds an implementation limit            */
+
+typedef struct mr_context mr_context;
+typedef struct mr_index   mr_index;
+typedef struct mr_result  mr_result;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int         mr_context_create(int device, mr_context** out);
+void        mr_context_destroy(mr_context* ctx);
+const char* mr_last_error(const mr_context* ctx);      /* ctx may be NULL: last creation error */
+int         mr_context_device(const mr_context* ctx);
+/* device seconds spent in each phase of the last mr_align_batch/mr_index_create call, for
+ * profiling; names follow the reference's global_timer phases where they exist
+ * (src_psa/mer_sa_imp.hpp:211-252, create_mega_reads.cc:130,154).  Returns number of entries. */
+int         mr_context_timers(const mr_context* ctx, const char** names, double* seconds, int cap);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t    mr_context_launches(const mr_context* ctx);
+
+/* ---- index: replaces superread_parse() -> sequence_psa (superread_parser.hpp:212-224),
+ *      i.e. sequence_psa::append_fasta (superread_parser.cc:12-46) output +
+ *      PSA::PSA -> SA::create_mt (psa.hpp:130-140, mer_sa_imp.hpp:197-267).
+ *  text2bit  : concatenated super-read bases, 2 bits each, A0 C1 G2 T3, base i at bits
+ *              2*(i%32) of word i/32 (compact_dna layout), ceil(n/32) words
+ *  sr_start  : nseq+1 offsets into the text (m_offsets[].sequence)
+ *  unitig_ids/unitig_off : CSR of each super-read's forward unitig path, (id<<1)|ori, ori 1 = 'R'
+ *              (super_read_name::u_id_ori, super_read_name.hpp:16-37); may be NULL when no -l/-u
+ *  unitig_len: length of every k-unitig (misc.cc:11-37), may be NULL
+ *  psa_min,k : --psa-min and -m.  Requires psa_min < k <= 31.                                    */
+int  mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n,
+                     const uint64_t* sr_start, uint32_t nseq,
+                     const uint32_t* unitig_ids, const uint64_t* unitig_off,
+                     const int32_t* unitig_len, uint32_t n_unitigs,
+                     uint32_t psa_min, uint32_t k, mr_index** out);
+void mr_index_destroy(mr_index* idx);
+uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min + 1 */
+/* parity taps: suffix-array values in SA order and the 4^psa_min + 1 prefix counts
+ * (mer_sa_imp.hpp:317-330), widened to 64 bit */
+int  mr_index_export_sa(mr_index* idx, uint64_t* sa_out);
+int  mr_index_export_counts(mr_index* idx, uint64_t* counts_out);
+
+/* ---- k-mer lookup: replaces PSA::search (psa.hpp:150-153 -> mer_sa_imp.hpp:369-479).
+ *  mers[i] holds a k-mer as an integer, first base most significant.  index_out/nb_out get the
+ *  rank of the first matching SA entry and the number of matches (index 0 when nb is 0).
+ *  Host-pointer version copies in and out; the _device version takes device pointers and only
+ *  enqueues the kernel on the context's stream (use mr_context_sync to wait).                  */
+int  mr_lookup_batch(mr_index* idx, const uint64_t* mers, uint64_t q, uint64_t* index_out, uint64_t* nb_out);
+int  mr_lookup_batch_device(mr_index* idx, const uint64_t* d_mers, uint64_t q, uint64_t* d_index_out, uint64_t* d_nb_out);
+int  mr_context_sync(mr_context* ctx);
+/* the CUDA stream (cudaStream_t) the context launches on, for callers that time with events */
+void* mr_context_stream(mr_context* ctx);
+
+/* ---- alignment parameters: the numeric arguments of coarse_aligner's constructor
+ *      (coarse_aligner.hpp:55-72 as called from create_mega_reads.cc:140-146) and of
+ *      overlap_graph (overlap_graph.hpp:90-95 as called from create_mega_reads.cc:155).        */
+typedef struct mr_params {
+  double   stretch_factor;     /* --stretch-factor   1.3   */
+  double   stretch_constant;   /* --stretch-constant 10    */
+  double   stretch_cap;        /* --stretch-cap      10000 */
+  uint32_t window_size;        /* --window-size      1 (only 1 is implemented)        */
+  int32_t  forward;            /* create_mega_reads: always 1; jf_aligner: -f          */
+  int32_t  max_match;          /* --max-match                                         */
+  int32_t  max_count;          /* --max-count, 0 means unlimited                      */
+  double   matching_mers;      /* -M / 100                                            */
+  double   matching_bases;     /* -B / 100                                            */
+  uint32_t unitigs_k;          /* -k (0: no unitig information, kmers_info stay empty) */
+  double   overlap_play;       /* -O 1.3   */
+  double   errors;             /* -e 3.0   */
+  int32_t  bases;              /* -b       */
+  int32_t  run_graph;          /* 0: stop after coords (jf_aligner), 1: also run the overlap graph */
+} mr_params;
+void mr_params_default(mr_params* p);
+
+/* ---- one batch of reads: replaces, for every read of the batch,
+ *      coarse_aligner::thread::align_sequence_max + coords()  (coarse_aligner.cc:42-72,81-141,
+ *      pb_aligner.cc:11-143, lis_align.hpp:139-204), the coords sort of
+ *      create_mega_reads.cc:69-77 and overlap_graph::thread::{reset,traverse}
+ *      (overlap_graph.hpp:177-196, overlap_graph.cc:7-59).
+ *  bases      : reads concatenated, one ASCII character per base, as parsed (any case, non-ACGT
+ *               breaks k-mers exactly like jf_aligner.hpp:41-52)
+ *  read_start : nreads+1 offsets into bases
+ *  The result object owns pinned host arrays, valid until mr_result_free.                       */
+int  mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p,
+                    const char* bases, const uint64_t* read_start, uint32_t nreads, mr_result** out);
+/* same, but with the batch already resident in device memory (bench.py's device-resident timing) */
+int  mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p,
+                           const char* d_bases, const uint64_t* d_read_start, const uint64_t* h_read_start,
+                           uint32_t nreads, mr_result** out);
+void mr_result_free(mr_result* r);
+
+/* Structure-of-arrays view of a result.  Coords of read r are rows
+ * [read_coords[r], read_coords[r+1]) and are ordered by (rs, re, ql, super-read index): the
+ * reference's (unstable) order of create_mega_reads.cc:74 with ties broken canonically.
+ * One row == one align_pb::coords_info (pb_aligner.hpp:103-175) and, when run_graph, one
+ * node_info (overlap_graph.hpp:9-40); node links (lstart, lprev) are row offsets inside the read. */
+typedef struct mr_result_view {
+  uint32_t nreads;
+  uint64_t ncoords;
+  const uint64_t* read_coords;      /* nreads + 1 */
+  const int32_t  *rs, *re, *qs, *qe, *nb_mers;
+  const uint32_t *pb_cons, *sr_cons, *pb_cover, *sr_cover;
+  const uint32_t *ql;               /* super-read length */
+  const uint32_t *sr;               /* super-read index (qfrag) */
+  const uint8_t  *rn;               /* reverse match */
+  const uint8_t  *use_bwd;          /* name_u == &qfrag->bwd */
+  const double   *stretch, *offset, *avg_err;
+  const uint64_t *info_off;         /* per row: start of its entries in kmers_info / bases_info */
+  const uint32_t *info_len;         /* per row: 2*#unitigs-1, or 0 when empty (no -l/-u, bad name, error path) */
+  const int32_t  *kmers_info, *bases_info;
+  /* overlap graph (NULL unless run_graph) */
+  const uint8_t  *start_node, *end_node;
+  const int32_t  *lstart, *lprev, *lpath, *lunitigs;
+  const int32_t  *component;        /* union-find root, row offset inside the read */
+  /* work counters of the batch, for roofline arithmetic */
+  uint64_t n_kmers_looked_up;       /* k-mers that reached the suffix-array lookup (x2 strands) */
+  uint64_t n_hits;                  /* hits expanded into (read, super-read) lists */
+  uint64_t n_groups;                /* (read, super-read) pairs chained */
+} mr_result_view;
+int  mr_result_get(const mr_result* r, mr_result_view* view);
+
+/* parity tap: per-(read, super-read) hit lists and chains of the last batch, in the layout of
+ * tests/oracle_lib.py (groups[g] = {read, sr, n_fwd, n_bwd, lis_fwd, lis_bwd}); only filled when
+ * mr_context_keep_taps(ctx, 1) was called before the batch. */
+int  mr_context_keep_taps(mr_context* ctx, int on);
+int  mr_result_taps(const mr_result* r, uint64_t* ngroups, const int64_t** groups,
+                    uint64_t* noffsets, const int32_t** offsets, uint64_t* nlis, const uint32_t** lis);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGA_READS_B200_H */

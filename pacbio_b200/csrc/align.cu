@@ -1,0 +1,1130 @@
+// Per-batch alignment pipeline on the device: seed selection + suffix-array lookup, per-read
+// count threshold, hit expansion, grouping by super-read (stable radix sort), chaining ("LIS"),
+// least-squares coords and filters, kmers_info, per-read ordering.  One kernel per CPU hot loop
+// of the reference; every kernel cites what it replaces.
+#include "align.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// k-mer enumeration over one tile of one read (jf_aligner.hpp:41-52,113-123 + coarse_aligner.cc:8-15,89-102)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t base_code(char c) {
+  switch(c) {
+  case 'a': case 'A': return 0;
+  case 'c': case 'C': return 1;
+  case 'g': case 'G': return 2;
+  case 't': case 'T': return 3;
+  default: return 4;
+  }
+}
+
+__device__ __forceinline__ bool is_ssr(uint64_t m, uint32_t k) {
+  const unsigned top = 2 * (k - 1);
+  const uint64_t r1 = (m >> 2) | ((m & 3) << top);
+  const uint64_t r2 = (r1 >> 2) | ((r1 & 3) << top);
+  return r1 == m || r2 == m;
+}
+
+struct tile_kmers {
+  uint64_t m[4], rm[4];
+  bool     valid[4];     // k consecutive ACGT, not a simple sequence repeat
+  bool     cand[4];      // ... and still inside the first 17 bases of its N-free run: toggles `flag`
+};
+
+// Loads the tile's bases (plus look-back / look-ahead) into shared memory as codes and enumerates
+// the 4 consecutive k-mers owned by this thread.  codes[] needs kTile + 64 bytes.
+__device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
+                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t) {
+  const int cap = k > 18 ? (int)k : 18;        // run length is only needed up to max(k, 18)
+  const int LB  = cap - (int)k;
+  const int total = LB + kTile + (int)k - 1;
+  for(int i = threadIdx.x; i < total; i += kSeedThreads) {
+    const int64_t p = (int64_t)tile_pos - LB + i;
+    codes[i] = (p >= 0 && p < (int64_t)rlen) ? base_code(bases[rstart + p]) : (uint8_t)4;
+  }
+  __syncthreads();
+  const int s0 = threadIdx.x * 4;
+  const uint64_t mask = (1ULL << (2 * k)) - 1;
+  const unsigned top = 2 * (k - 1);
+  uint64_t m = 0, rm = 0;
+  for(uint32_t j = 0; j < k; ++j) {
+    const uint64_t c = codes[LB + s0 + j] & 3;
+    m  = (m << 2) | c;
+    rm = (rm >> 2) | ((3 - c) << top);
+  }
+  int run = 0;
+  for(int j = 0; j < cap; ++j) {
+    if(codes[LB + s0 + (int)k - 1 - j] == 4) break;
+    ++run;
+  }
+#pragma unroll
+  for(int j = 0; j < 4; ++j) {
+    const bool ok = run >= (int)k && !is_ssr(m, k);
+    t.m[j] = m; t.rm[j] = rm;
+    t.valid[j] = ok;
+    t.cand[j]  = ok && run <= 17;
+    const uint8_t c = codes[LB + s0 + j + (int)k];
+    run = c == 4 ? 0 : min(run + 1, cap);
+    m  = ((m << 2) | (uint64_t)(c & 3)) & mask;
+    rm = (rm >> 2) | ((uint64_t)(3 - (c & 3)) << top);
+  }
+}
+
+// pass 0 (only when k <= 17): number of flag-toggling k-mers per tile
+__global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ read_start,
+                                                                   const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                                   uint32_t k, uint32_t* __restrict__ tile_cand) {
+  __shared__ uint8_t codes[kTile + 64];
+  __shared__ uint32_t total;
+  if(threadIdx.x == 0) total = 0;
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t rs = read_start[r];
+  tile_kmers t;
+  enumerate_tile(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes, t);
+  const uint32_t c = (uint32_t)t.cand[0] + t.cand[1] + t.cand[2] + t.cand[3];
+  if(c) atomicAdd(&total, c);
+  __syncthreads();
+  if(threadIdx.x == 0) tile_cand[blockIdx.x] = total;
+}
+
+// exclusive prefix of tile_cand inside each read (the toggle persists across N breaks, coarse_aligner.cc:89)
+__global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint32_t nreads,
+                                  const uint32_t* __restrict__ tile_cand, uint32_t* __restrict__ tile_tbase) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if(r >= nreads) return;
+  uint32_t run = 0;
+  for(uint32_t t = tile_first[r]; t < tile_first[r + 1]; ++t) { tile_tbase[t] = run; run += tile_cand[t]; }
+}
+
+// Seed kernel: for every read position decides whether its k-mer is looked up
+// (coarse_aligner.cc:93-102), looks up both strands (superread_parser.hpp:183-192 ->
+// mer_sa_imp.hpp:369-479) and applies the max-count filter (coarse_aligner.cc:108-111).
+// rec[g] = {index(m), nb(m), index(rm), nb(rm)}; size[g] = nb(m)+nb(rm) or 0 when there is no list.
+__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
+                                                                    const uint64_t* __restrict__ read_start,
+                                                                    const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                                    const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
+                                                                    uint4* __restrict__ rec, uint32_t* __restrict__ size,
+                                                                    unsigned long long* __restrict__ n_lookups) {
+  __shared__ uint8_t  codes[kTile + 64];
+  __shared__ uint64_t sw[8];
+  __shared__ uint32_t looked;
+  const uint32_t k = iv.k;
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  const uint32_t tpos = tile_pos[blockIdx.x];
+  if(threadIdx.x == 0) looked = 0;
+  tile_kmers t;
+  enumerate_tile(bases, rs, rlen, tpos, k, codes, t);
+
+  bool keep[4];
+#pragma unroll
+  for(int j = 0; j < 4; ++j) keep[j] = t.valid[j];
+  const uint32_t ncand = (uint32_t)t.cand[0] + t.cand[1] + t.cand[2] + t.cand[3];
+  if(k <= 17 && __syncthreads_or(ncand != 0)) {
+    uint64_t total;
+    uint32_t seen = tile_tbase[blockIdx.x] + (uint32_t)prim::block_exclusive_scan_256(ncand, sw, total);
+#pragma unroll
+    for(int j = 0; j < 4; ++j) {
+      if(t.cand[j]) {
+        ++seen;                              // flag starts at 1 and flips on every candidate:
+        if((seen & 1) == 0) keep[j] = false; // the 2nd, 4th, ... candidate of the read is skipped
+      }
+    }
+  }
+
+  // stage 1: prefix-table probes for all (position, strand) pairs of this thread, issued together
+  uint32_t c0[8], c1[8];
+#pragma unroll
+  for(int j = 0; j < 4; ++j) {
+    if(keep[j]) {
+      const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
+      c0[2 * j] = __ldg(iv.counts + pm);     c1[2 * j] = __ldg(iv.counts + pm + 1);
+      c0[2 * j + 1] = __ldg(iv.counts + pr); c1[2 * j + 1] = __ldg(iv.counts + pr + 1);
+    }
+  }
+  const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
+  uint32_t nlook = 0;
+  const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
+#pragma unroll
+  for(int j = 0; j < 4; ++j) {
+    uint4 out = make_uint4(0, 0, 0, 0);
+    uint32_t sz = 0;
+    if(keep[j]) {
+      ++nlook;
+      uint32_t idx[2], nb[2];
+#pragma unroll
+      for(int s = 0; s < 2; ++s) {
+        const uint64_t mer = s ? t.rm[j] : t.m[j];
+        const uint32_t a0 = c0[2 * j + s], a1 = c1[2 * j + s];
+        idx[s] = 0; nb[s] = 0;
+        if(a0 != a1) {
+          const uint32_t tt = (uint32_t)mer & tmask;
+          uint32_t lo, hi;
+          if(a1 - a0 <= 32) {
+            uint32_t less = 0, leq = 0;
+            for(uint32_t i = a0; i < a1; ++i) { const uint32_t v = __ldg(iv.tails + i); less += v < tt; leq += v <= tt; }
+            lo = a0 + less; hi = a0 + leq;
+          } else {
+            uint32_t a = a0, b = a1;
+            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) < tt) a = mid + 1; else b = mid; }
+            lo = a; b = a1;
+            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) <= tt) a = mid + 1; else b = mid; }
+            hi = a;
+          }
+          if(hi != lo && (mer & 3) == 0)
+            for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
+          nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;
+        }
+      }
+      const uint32_t total = nb[0] + nb[1];
+      if(total != 0 && !(max_count && total >= max_count)) {
+        out = make_uint4(idx[0], nb[0], idx[1], nb[1]);
+        sz = total;
+      }
+    }
+    const uint32_t pos = tpos + threadIdx.x * 4 + j;
+    if(pos < rlen) { rec[g0 + j] = out; size[g0 + j] = sz; }
+  }
+  if(nlook) atomicAdd(&looked, nlook);
+  __syncthreads();
+  if(threadIdx.x == 0 && looked) atomicAdd(n_lookups, (unsigned long long)looked);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-read count threshold (coarse_aligner.cc:117-131): smallest t with #{size <= t} > round(0.99 #lists),
+// found by a most-significant-digit-first radix select; lists above it get size 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) read_threshold_kernel(const uint64_t* __restrict__ read_start, uint32_t nbits,
+                                                              uint32_t* __restrict__ size, uint32_t* __restrict__ thr_out) {
+  __shared__ uint32_t hist[2048];
+  __shared__ uint64_t sw[8];
+  __shared__ uint32_t sh_bin, sh_before, sh_count;
+  const uint32_t r = blockIdx.x;
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  uint32_t* sz = size + rs;
+  if(threadIdx.x == 0) sh_count = 0;
+  __syncthreads();
+  uint32_t mine = 0;
+  for(uint32_t i = threadIdx.x; i < rlen; i += 256) mine += sz[i] != 0;
+  if(mine) atomicAdd(&sh_count, mine);
+  __syncthreads();
+  const uint32_t L = sh_count;
+  const double   scaled = (double)L * 0.99;
+  const uint32_t sum_thresh = (uint32_t)round(scaled);
+  if(L == 0 || sum_thresh >= L) { if(threadIdx.x == 0) thr_out[r] = 0xffffffffu; return; }
+  uint32_t kth = sum_thresh + 1, prefix = 0, remaining = nbits;
+  while(remaining > 0) {
+    const uint32_t d = remaining < 11 ? remaining : 11, shift = remaining - d;
+    for(int i = threadIdx.x; i < 2048; i += 256) hist[i] = 0;
+    __syncthreads();
+    for(uint32_t i = threadIdx.x; i < rlen; i += 256) {
+      const uint32_t v = sz[i];
+      if(v != 0 && (remaining >= 32 || (v >> remaining) == prefix)) atomicAdd(&hist[(v >> shift) & ((1u << d) - 1)], 1u);
+    }
+    __syncthreads();
+    uint32_t local[8], s = 0;
+#pragma unroll
+    for(int j = 0; j < 8; ++j) { local[j] = hist[threadIdx.x * 8 + j]; s += local[j]; }
+    uint64_t total;
+    uint32_t before = (uint32_t)prim::block_exclusive_scan_256(s, sw, total);
+    if(before < kth && kth <= before + s) {
+#pragma unroll
+      for(int j = 0; j < 8; ++j) {
+        if(kth <= before + local[j]) { sh_bin = threadIdx.x * 8 + j; sh_before = before; break; }
+        before += local[j];
+      }
+    }
+    __syncthreads();
+    kth -= sh_before;
+    prefix = (prefix << d) | sh_bin;
+    remaining = shift;
+    __syncthreads();
+  }
+  if(threadIdx.x == 0) thr_out[r] = prefix;
+  for(uint32_t i = threadIdx.x; i < rlen; i += 256) if(sz[i] > prefix) sz[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit expansion (coarse_aligner.cc:127-138 + pos_iterator, superread_parser.hpp:110-134):
+// every SA entry of a kept list becomes (key = read<<32 | super-read, payload = pb offset, signed
+// super-read offset); entries whose k-mer straddles two super-reads get super-read == nseq.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_hit(const index_view& iv, uint32_t read, uint32_t pb_off, uint32_t sa_rank, bool minus,
+                                         uint64_t slot, uint64_t* __restrict__ keys, uint64_t* __restrict__ pays,
+                                         uint32_t& n_bad) {
+  const uint32_t x = __ldg(iv.sa + sa_rank);
+  uint32_t sr, off;
+  if(index_locate(iv, x, sr, off)) {
+    const int32_t soff = minus ? -(int32_t)off : (int32_t)off;
+    keys[slot] = ((uint64_t)read << 32) | sr;
+    pays[slot] = (uint64_t)pb_off | ((uint64_t)(uint32_t)soff << 32);
+  } else {
+    keys[slot] = ((uint64_t)read << 32) | iv.nseq;
+    pays[slot] = 0;
+    ++n_bad;
+  }
+}
+
+__global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, const uint64_t* __restrict__ read_start,
+                                                               const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                               const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
+                                                               const uint64_t* __restrict__ hit_off,
+                                                               uint64_t* __restrict__ keys, uint64_t* __restrict__ pays,
+                                                               unsigned long long* __restrict__ n_invalid) {
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  const uint32_t tpos = tile_pos[blockIdx.x];
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_bad = 0;
+  for(int it = 0; it < kTile / kSeedThreads; ++it) {
+    const uint32_t pos = tpos + it * kSeedThreads + threadIdx.x;
+    uint32_t sz = 0;
+    uint4 rc = make_uint4(0, 0, 0, 0);
+    uint64_t off = 0;
+    if(pos < rlen) {
+      sz = size[rs + pos];
+      if(sz) { rc = rec[rs + pos]; off = hit_off[rs + pos]; }
+    }
+    // short lists: the owning thread writes them
+    if(sz && sz <= 8) {
+      for(uint32_t j = 0; j < rc.y; ++j) emit_hit(iv, r, pos + 1, rc.x + j, false, off + j, keys, pays, n_bad);
+      for(uint32_t j = 0; j < rc.w; ++j) emit_hit(iv, r, pos + 1, rc.z + j, true, off + rc.y + j, keys, pays, n_bad);
+    }
+    // long lists: the whole warp strides over them, coalescing the SA reads and the writes
+    unsigned big = __ballot_sync(MR_FULL_MASK, sz > 8);
+    while(big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t bx = __shfl_sync(MR_FULL_MASK, rc.x, src), by = __shfl_sync(MR_FULL_MASK, rc.y, src);
+      const uint32_t bz = __shfl_sync(MR_FULL_MASK, rc.z, src), bw = __shfl_sync(MR_FULL_MASK, rc.w, src);
+      const uint64_t boff = __shfl_sync(MR_FULL_MASK, off, src);
+      const uint32_t bpos = __shfl_sync(MR_FULL_MASK, pos, src);
+      for(uint32_t j = lane; j < by; j += 32) emit_hit(iv, r, bpos + 1, bx + j, false, boff + j, keys, pays, n_bad);
+      for(uint32_t j = lane; j < bw; j += 32) emit_hit(iv, r, bpos + 1, bz + j, true, boff + by + j, keys, pays, n_bad);
+    }
+  }
+  if(n_bad) atomicAdd(n_invalid, (unsigned long long)n_bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// group heads: one group per (read, super-read) present in the sorted hits (frags_pos_type,
+// coarse_aligner.hpp:14, as a segmented array instead of an unordered_map of vectors)
+// ------------------------------------------------------------------------------------------------
+struct head_flag {
+  const uint64_t* keys; uint32_t nseq;
+  __device__ uint64_t operator()(uint64_t i) const {
+    const uint64_t k = keys[i];
+    return ((uint32_t)k < nseq) && (i == 0 || keys[i - 1] != k);
+  }
+};
+
+__global__ void __launch_bounds__(256) group_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t nseq,
+                                                             const uint64_t* __restrict__ gpos, uint64_t* __restrict__ group_start) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = keys[i];
+    if(((uint32_t)k < nseq) && (i == 0 || keys[i - 1] != k)) group_start[gpos[i]] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chaining + coords: one warp per (read, super-read) group.
+//   chain_strand   == lis_align::compute_L_P (lis_align.hpp:139-182), window_size 1
+//   coords section == compute_coords_info + least_square_2d + canonicalize + filters
+//                     (pb_aligner.cc:11-82, least_square_2d.hpp:47-67, pb_aligner.hpp:151-174,
+//                      coarse_aligner.cc:42-60)
+// The reference's forward_list L is kept as an array in REVERSE list order (list front == array
+// end), so the usual case -- extend the chain at the front, insert at the front -- touches only
+// the last few array slots.
+// ------------------------------------------------------------------------------------------------
+struct chain_buffers {
+  int32_t*  Lpb;  int32_t* Lsr;  uint32_t* Llen;  uint32_t* Lelt;   // indexed gs + array slot
+  uint32_t* pprev; uint32_t* cstart;                                  // indexed gs + element
+};
+
+__device__ void chain_strand(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const chain_buffers& cb, uint64_t gs,
+                             double a, double b, double C, uint32_t& longest_out, uint32_t& best_out,
+                             uint32_t* tap_sub) {
+  const unsigned lane = threadIdx.x & 31;
+  int32_t*  Lpb  = cb.Lpb + gs;  int32_t* Lsr = cb.Lsr + gs;
+  uint32_t* Llen = cb.Llen + gs; uint32_t* Lelt = cb.Lelt + gs;
+  uint32_t* pprev = cb.pprev + gs; uint32_t* cstart = cb.cstart + gs;
+  uint32_t cnt = 0, longest = 0, best = 0, nsub = 0;
+  for(uint32_t base = 0; base < N; base += 32) {
+    const uint32_t il = base + lane;
+    const uint64_t pl = il < N ? pay[gs + il] : 0;
+    const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
+    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
+    while(todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t i = base + src;
+      const int32_t pb_i = __shfl_sync(MR_FULL_MASK, pb_l, src), sr_i = __shfl_sync(MR_FULL_MASK, sr_l, src);
+      if(tap_sub && lane == 0) tap_sub[gs + i] = nsub;
+      ++nsub;
+
+      int      found = -1;
+      uint32_t f_len = 0, f_elt = 0, min_len = 0xffffffffu;
+      int      prev_pos = -1;
+      for(uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t p = c0 + lane;
+        const bool in = p < cnt;
+        const uint32_t slot = cnt - 1 - p;
+        int32_t lsr = 0, lpb = 0; uint32_t llen = 0, lelt = 0;
+        if(in) { lsr = Lsr[slot]; lpb = Lpb[slot]; llen = Llen[slot]; lelt = Lelt[slot]; }
+        bool feas = false;
+        if(in && sr_i > lsr) {
+          const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
+          const double t1 = a * d2, t2 = a * d1;
+          feas = d1 <= b + t1 && d2 <= b + t2 && d1 <= C && d2 <= C;
+        }
+        const unsigned ball = __ballot_sync(MR_FULL_MASK, feas);
+        const unsigned limit = ball ? (unsigned)(__ffs(ball) - 1) : 32u;
+        // first position of the strict minimum of len among the entries walked over
+        const unsigned packed = (in && lane < limit) ? ((llen << 5) | lane) : 0xffffffffu;
+        const unsigned best_packed = __reduce_min_sync(MR_FULL_MASK, packed);
+        if(best_packed != 0xffffffffu && (best_packed >> 5) < min_len) {
+          min_len = best_packed >> 5;
+          prev_pos = (int)(c0 + (best_packed & 31));
+        }
+        if(ball) {
+          found = (int)(c0 + limit);
+          f_len = __shfl_sync(MR_FULL_MASK, llen, limit);
+          f_elt = __shfl_sync(MR_FULL_MASK, lelt, limit);
+          break;
+        }
+      }
+      const uint32_t e_len = found >= 0 ? f_len + 1 : 1;
+      const uint32_t cs = found >= 0 ? cstart[f_elt] : i;
+      if(lane == 0) { pprev[i] = found >= 0 ? f_elt : kNone; cstart[i] = cs; }
+      // insert after prev_pos: the q = prev_pos + 1 entries in front of it move up one slot
+      const uint32_t q = (uint32_t)(prev_pos + 1);
+      for(uint32_t top = cnt; top > cnt - q; ) {
+        const uint32_t lo = (top - (cnt - q)) > 32 ? top - 32 : cnt - q;
+        const uint32_t s = lo + lane;
+        const bool has = s < top;
+        int32_t v0 = 0, v1 = 0; uint32_t v2 = 0, v3 = 0;
+        if(has) { v0 = Lpb[s]; v1 = Lsr[s]; v2 = Llen[s]; v3 = Lelt[s]; }
+        __syncwarp();
+        if(has) { Lpb[s + 1] = v0; Lsr[s + 1] = v1; Llen[s + 1] = v2; Lelt[s + 1] = v3; }
+        __syncwarp();
+        top = lo;
+      }
+      if(lane == 0) { const uint32_t s = cnt - q; Lpb[s] = pb_i; Lsr[s] = sr_i; Llen[s] = e_len; Lelt[s] = i; }
+      ++cnt;
+      __syncwarp();
+      if(longest < e_len) {
+        const uint64_t pc = pay[gs + cs];
+        const double span_pb = (double)(pb_i - (int32_t)(uint32_t)pc), span_sr = (double)(sr_i - (int32_t)(uint32_t)(pc >> 32));
+        const double s1 = a * span_sr, s2 = a * span_pb;
+        if(span_pb <= s1 && span_sr <= s2) { longest = e_len; best = i; }
+      }
+    }
+  }
+  longest_out = longest;
+  best_out = best;
+}
+
+struct survivors {
+  // unsorted survivor rows (capacity cap); slot taken with atomicAdd on *count
+  int32_t  *rs, *re, *qs, *qe, *nb_mers;
+  uint32_t *pb_cons, *sr_cons, *pb_cover, *sr_cover, *ql, *sr, *read, *info_len;
+  uint8_t  *rn, *use_bwd;
+  double   *stretch, *offset, *avg_err;
+  uint64_t *chain_pos;
+  uint64_t cap;
+  unsigned long long* count;
+  unsigned long long* info_total;
+  uint32_t* read_cnt;
+};
+
+struct chain_args {
+  index_view iv;
+  const uint64_t* keys; const uint64_t* pays; const uint64_t* group_start; uint64_t ngroups;
+  const uint64_t* read_start;
+  chain_buffers cb;
+  double a, b, C, matching_mers, matching_bases;
+  int forward;
+  uint32_t unitigs_k, n_unitigs;
+  const uint32_t* unitig_ids; const uint64_t* unitig_off;
+  survivors sv;
+  uint2* tap_lens; uint32_t* tap_cf; uint32_t* tap_cb; uint32_t* tap_sub;
+};
+
+__global__ void __launch_bounds__(128) chain_coords_kernel(chain_args A) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t k = A.iv.k;
+  for(uint64_t g = warp0; g < A.ngroups; g += nwarps) {
+    const uint64_t gs = A.group_start[g];
+    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    const uint64_t key = A.keys[gs];
+    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
+    uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
+    chain_strand(A.pays, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub);
+    __syncwarp();
+    chain_strand(A.pays, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, A.tap_sub);
+    __syncwarp();
+    const bool fwd_align = len_f >= len_b;
+    const uint32_t nb = fwd_align ? len_f : len_b;
+    uint32_t* chain = A.cb.Lelt + gs;          // L is dead now: reuse as the chain, in order
+    uint32_t* pprev = A.cb.pprev + gs;
+    if(A.tap_lens) {                           // parity tap: both chains as sub-list indices
+      if(lane == 0) {
+        A.tap_lens[g] = make_uint2(len_f, len_b);
+        uint32_t cur = best_f;
+        for(uint32_t t = 0; t < len_f; ++t) { A.tap_cf[gs + len_f - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
+        cur = best_b;
+        for(uint32_t t = 0; t < len_b; ++t) { A.tap_cb[gs + len_b - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
+      }
+      __syncwarp();
+    }
+    if(nb == 0) continue;
+    if(lane == 0) {
+      uint32_t cur = fwd_align ? best_f : best_b;
+      for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
+    }
+    __syncwarp();
+
+    const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
+    const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
+    // online least squares, x = super-read offset, y = read offset, in chain order
+    double EX = 0, EY = 0, EXX = 0, EXY = 0, VX = 0, CXY = 0, NB = 0;
+    uint32_t pb_cons = 0, sr_cons = 0, pb_cover = k, sr_cover = k;
+    int32_t first_pb = 0, first_sr = 0, last_pb = 0, last_sr = 0, ppb = 0, psr = 0;
+    long n = 0;
+    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+      const uint32_t tl = t0 + lane;
+      uint64_t pl = 0;
+      if(tl < nb) pl = A.pays[gs + chain[tl]];
+      const uint32_t m = min(32u, nb - t0);
+      for(uint32_t u = 0; u < m; ++u) {
+        const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+        const int32_t pb = (int32_t)(uint32_t)p, so = (int32_t)(uint32_t)(p >> 32);
+        if(n == 0) { first_pb = pb; first_sr = so; }
+        else {
+          const uint32_t pb_diff = (uint32_t)(pb - ppb), sr_diff = (uint32_t)(so - psr);
+          pb_cons += pb_diff == 1; pb_cover += min(k, pb_diff);
+          sr_cons += sr_diff == 1; sr_cover += min(k, sr_diff);
+        }
+        ppb = pb; psr = so; last_pb = pb; last_sr = so;
+        const double x = (double)so, y = (double)pb;
+        ++n;
+        const double dn = (double)n;
+        const double dX = x - EX;  EX += dX / dn;  const double ndX = x - EX;  VX += dX * ndX;
+        const double dY = y - EY;  EY += dY / dn;  const double ndY = y - EY;
+        const double dXX = x * x - EXX;  EXX += dXX / dn;
+        const double dXY = x * y - EXY;  EXY += dXY / dn;
+        CXY += dX * ndY;
+        const double t1 = dXY * ndX, t2 = dXX * ndY;
+        NB += t1 - t2;
+      }
+    }
+    double stretch, offset, avg_err;
+    if(n == 1) { stretch = 1.0; offset = EY - EX; avg_err = 0; }
+    else {
+      stretch = CXY / VX; offset = NB / VX;
+      double e = 0;
+      for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+        const uint32_t tl = t0 + lane;
+        uint64_t pl = 0;
+        if(tl < nb) pl = A.pays[gs + chain[tl]];
+        const uint32_t m = min(32u, nb - t0);
+        for(uint32_t u = 0; u < m; ++u) {
+          const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+          const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
+          const double prod = stretch * x;
+          e += fabs(prod + offset - y);
+        }
+      }
+      avg_err = e / (double)n;
+    }
+    int32_t rs = first_pb, re = last_pb + (int32_t)k - 1, qs = first_sr, qe = last_sr;
+    bool rn = false;
+    if(qs < 0) {
+      if(A.forward) {
+        qs = (int32_t)((int64_t)ql + qs - (int64_t)k + 2);
+        qe = (int32_t)((int64_t)ql + qe + 1);
+        rn = true;
+        const double t = stretch * (double)((uint64_t)ql + 1);
+        offset -= t - (double)k;
+      } else {
+        qs = -qs + (int32_t)k - 1;
+        qe = -qe;
+        stretch = -stretch;
+        offset += (double)(k - 1);
+      }
+    } else {
+      qe += (int32_t)k - 1;
+    }
+    // filters of align_sequence_max (coarse_aligner.cc:51-54)
+    if(fabs(stretch) == 0.0) continue;
+    {
+      const double drl = (double)rl;
+      const double is = fmax(1.0, fmin(drl, stretch + offset));
+      const double tq = stretch * (double)ql;
+      const double ie = fmax(1.0, fmin(drl, tq + offset));
+      const int imp_len = (int)llabs(llrint(ie - is)) + 1;
+      if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) continue;
+      if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)pb_cover)) continue;
+    }
+    if(lane == 0) {
+      const bool use_bwd = A.forward && !fwd_align;
+      uint32_t ilen = 0;
+      if(A.unitigs_k && A.unitig_off) {
+        const uint64_t u0 = A.unitig_off[sr], u1 = A.unitig_off[sr + 1];
+        if(u1 > u0) {
+          const uint32_t first_id = (use_bwd ? A.unitig_ids[u1 - 1] : A.unitig_ids[u0]) >> 1;
+          if(first_id < A.n_unitigs) ilen = 2 * (uint32_t)(u1 - u0) - 1;
+        }
+      }
+      const unsigned long long slot = atomicAdd(A.sv.count, 1ULL);
+      if(slot < A.sv.cap) {
+        A.sv.rs[slot] = rs; A.sv.re[slot] = re; A.sv.qs[slot] = qs; A.sv.qe[slot] = qe; A.sv.nb_mers[slot] = (int32_t)nb;
+        A.sv.pb_cons[slot] = pb_cons; A.sv.sr_cons[slot] = sr_cons; A.sv.pb_cover[slot] = pb_cover; A.sv.sr_cover[slot] = sr_cover;
+        A.sv.ql[slot] = ql; A.sv.sr[slot] = sr; A.sv.read[slot] = read; A.sv.info_len[slot] = ilen;
+        A.sv.rn[slot] = rn; A.sv.use_bwd[slot] = use_bwd;
+        A.sv.stretch[slot] = stretch; A.sv.offset[slot] = offset; A.sv.avg_err[slot] = avg_err;
+        A.sv.chain_pos[slot] = gs;
+        atomicAdd(A.sv.info_total, (unsigned long long)ilen);
+        atomicAdd(A.sv.read_cnt + read, 1u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kmers_info / bases_info per surviving coords: compute_kmers_info::add_mer (pb_aligner.cc:84-143),
+// one thread per coords row walking its chain.
+// ------------------------------------------------------------------------------------------------
+struct info_args {
+  uint64_t n;
+  const uint64_t* chain_pos; const int32_t* nb_mers; const uint32_t* sr; const uint8_t* use_bwd; const uint32_t* ql;
+  const uint64_t* info_off; uint32_t* info_len;
+  const uint32_t* chain; const uint64_t* pays;
+  const uint32_t* unitig_ids; const uint64_t* unitig_off; const int32_t* unitig_len; uint32_t n_unitigs;
+  uint32_t k, unitigs_k;
+  int32_t* kinfo; int32_t* binfo;
+};
+
+__global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= A.n) return;
+  const uint32_t ilen = A.info_len[i];
+  if(ilen == 0) return;
+  int32_t* mers = A.kinfo + A.info_off[i];
+  int32_t* bases = A.binfo + A.info_off[i];
+  for(uint32_t j = 0; j < ilen; ++j) { mers[j] = 0; bases[j] = 0; }
+  const uint32_t sr = A.sr[i];
+  const bool bwd = A.use_bwd[i];
+  const uint64_t u0 = A.unitig_off[sr];
+  const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
+  const uint32_t invalid_id = 0x7fffffffu;
+  auto uid = [&](uint32_t t) -> uint32_t {
+    if(t >= nu) return invalid_id;
+    return (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
+  };
+  const int K = (int)A.k, UK = (int)A.unitigs_k;
+  const uint64_t gs = A.chain_pos[i];
+  const uint32_t nb = (uint32_t)A.nb_mers[i];
+  const bool fwd_align = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs]] >> 32) > 0;
+  const int64_t ql = A.ql[i];
+  uint32_t cunitig = 0;
+  int cend = A.unitig_len[uid(0)], prev_pos = -K;
+  bool failed = false;
+  for(uint32_t t = 0; t < nb && !failed; ++t) {
+    const int32_t so = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs + t]] >> 32);
+    const int pos = fwd_align ? so : (int)(ql + so - K + 2);
+    const int sr_pos = pos < 0 ? -pos : pos;
+    const int new_bases = min(K, sr_pos - prev_pos);
+    while(sr_pos + K > cend + 1) {
+      if(cend >= sr_pos) {
+        if(cunitig >= nu - 1) { failed = true; break; }
+        const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
+        bases[2 * cunitig] += nbb;
+        bases[2 * cunitig + 1] += nbb;
+      }
+      const uint32_t id = uid(++cunitig);
+      if(id == invalid_id || id >= A.n_unitigs) { failed = true; break; }
+      cend += A.unitig_len[id] - UK + 1;
+    }
+    if(failed) break;
+    ++mers[2 * cunitig];
+    bases[2 * cunitig] += new_bases;
+    int cendi = cend;
+    for(uint32_t u = cunitig; u < nu - 1 && sr_pos + K > cendi - UK + 1; ++u) {
+      const int full_mer = sr_pos + UK > cendi + 1;
+      mers[2 * u + 1] += full_mer;
+      mers[2 * u + 2] += full_mer;
+      const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
+      bases[2 * u + 1] += nbb;
+      bases[2 * u + 2] += nbb;
+      const uint32_t id = uid(u + 1);
+      if(id != invalid_id && id < A.n_unitigs) cendi += A.unitig_len[id] - UK + 1;
+      else { failed = true; break; }
+    }
+    prev_pos = sr_pos;
+  }
+  if(failed) A.info_len[i] = 0;      // the reference clears both vectors on error
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-read ordering of the coords rows: (rs, re, ql) as create_mega_reads.cc:69-77 /
+// pb_aligner.hpp:142-145, ties by super-read index (canonical; the reference's order there
+// depends on unordered_map iteration and an unstable sort)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bucket_rows_kernel(uint64_t n, const uint32_t* __restrict__ read, const uint64_t* __restrict__ read_coords,
+                                                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint32_t r = read[i];
+  slot[read_coords[r] + atomicAdd(cursor + r, 1u)] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
+                                                         const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
+                                                         const uint32_t* __restrict__ ql, const uint32_t* __restrict__ sr,
+                                                         uint32_t* __restrict__ order) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if(r >= nreads) return;
+  const uint64_t b = read_coords[r];
+  const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
+  for(uint32_t e = lane; e < c; e += 32) {
+    const uint32_t me = slot[b + e];
+    const int32_t a0 = rs[me], a1 = re[me]; const uint32_t a2 = ql[me], a3 = sr[me];
+    uint32_t rank = 0;
+    for(uint32_t f = 0; f < c; ++f) {
+      const uint32_t o = slot[b + f];
+      const int32_t b0 = rs[o], b1 = re[o]; const uint32_t b2 = ql[o], b3 = sr[o];
+      const bool less = b0 < a0 || (b0 == a0 && (b1 < a1 || (b1 == a1 && (b2 < a2 || (b2 == a2 && b3 < a3)))));
+      rank += less;
+    }
+    order[b + rank] = me;
+  }
+}
+
+struct gather_args {
+  uint64_t n; const uint32_t* order;
+  survivors sv; const uint64_t* sv_info_off;
+  coords_soa out;
+};
+__global__ void __launch_bounds__(256) gather_rows_kernel(gather_args A) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= A.n) return;
+  const uint32_t s = A.order[i];
+  A.out.rs[i] = A.sv.rs[s]; A.out.re[i] = A.sv.re[s]; A.out.qs[i] = A.sv.qs[s]; A.out.qe[i] = A.sv.qe[s];
+  A.out.nb_mers[i] = A.sv.nb_mers[s];
+  A.out.pb_cons[i] = A.sv.pb_cons[s]; A.out.sr_cons[i] = A.sv.sr_cons[s];
+  A.out.pb_cover[i] = A.sv.pb_cover[s]; A.out.sr_cover[i] = A.sv.sr_cover[s];
+  A.out.ql[i] = A.sv.ql[s]; A.out.sr[i] = A.sv.sr[s]; A.out.read[i] = A.sv.read[s];
+  A.out.rn[i] = A.sv.rn[s]; A.out.use_bwd[i] = A.sv.use_bwd[s];
+  A.out.stretch[i] = A.sv.stretch[s]; A.out.offset[i] = A.sv.offset[s]; A.out.avg_err[i] = A.sv.avg_err[s];
+  A.out.info_off[i] = A.sv_info_off[s]; A.out.info_len[i] = A.sv.info_len[s];
+  A.out.chain_pos[i] = A.sv.chain_pos[s];
+}
+
+// carve typed arrays out of one device buffer
+template<typename T>
+T* carve(char*& cursor, uint64_t count) {
+  T* p = reinterpret_cast<T*>(cursor);
+  cursor += ((count * sizeof(T) + 255) / 256) * 256;
+  return p;
+}
+
+} // namespace
+
+void mr_workspace_free(mr_workspace* ws) { delete ws; }
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
+                            const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads,
+                            phase_timer& timer, mr_result** out) {
+  cudaStream_t st = ctx->stream;
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  const index_view& iv = idx->view;
+  const uint32_t k = iv.k;
+  const uint64_t T = h_read_start[nreads];
+  if(T >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 bases in one batch");
+  if(nreads >= (1u << 31)) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many reads in one batch");
+
+  std::unique_ptr<mr_result> res(new mr_result);
+  res->ctx = ctx;
+  memset(&res->view, 0, sizeof(res->view));
+  res->view.nreads = nreads;
+
+  // ---- tiles (host side: O(#tiles)) ---------------------------------------------------------
+  std::vector<uint32_t> tile_first(nreads + 1), tile_read, tile_pos, read_len(nreads);
+  {
+    uint64_t nt = 0;
+    for(uint32_t r = 0; r < nreads; ++r) {
+      const uint64_t len = h_read_start[r + 1] - h_read_start[r];
+      if(len >= (1ULL << 31)) return ctx->fail(MR_ELIMIT, "mr_align_batch: read longer than 2^31 bases");
+      read_len[r] = (uint32_t)len;
+      tile_first[r] = (uint32_t)nt;
+      nt += (len + kTile - 1) / kTile;
+    }
+    tile_first[nreads] = (uint32_t)nt;
+    tile_read.resize(nt); tile_pos.resize(nt);
+    for(uint32_t r = 0; r < nreads; ++r)
+      for(uint32_t t = tile_first[r]; t < tile_first[r + 1]; ++t) { tile_read[t] = r; tile_pos[t] = (t - tile_first[r]) * kTile; }
+  }
+  const uint32_t ntiles = tile_first[nreads];
+  MR_TRY(ws.tile_first.ensure(ctx, ((size_t)nreads + 1) * 4));
+  MR_TRY(ws.read_len.ensure(ctx, ((size_t)nreads + 1) * 4));
+  MR_TRY(ws.tile_read.ensure(ctx, ((size_t)ntiles + 1) * 4));
+  MR_TRY(ws.tile_pos.ensure(ctx, ((size_t)ntiles + 1) * 4));
+  MR_TRY(ws.tile_cand.ensure(ctx, ((size_t)ntiles + 1) * 4));
+  MR_TRY(ws.tile_tbase.ensure(ctx, ((size_t)ntiles + 1) * 4));
+  MR_TRY(ws.counters.ensure(ctx, 16 * sizeof(uint64_t)));
+  MR_TRY(ws.size.ensure(ctx, (T + 4) * 4));
+  MR_TRY(ws.rec.ensure(ctx, (T + 4) * 16));
+  MR_TRY(ws.hit_off.ensure(ctx, (T + 4) * 8));
+  MR_TRY(ws.thr.ensure(ctx, ((size_t)nreads + 1) * 4));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.tile_first.p, tile_first.data(), ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.read_len.p, read_len.data(), (size_t)nreads * 4, cudaMemcpyHostToDevice, st));
+  if(ntiles) {
+    MR_CUDA(ctx, cudaMemcpyAsync(ws.tile_read.p, tile_read.data(), (size_t)ntiles * 4, cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(ws.tile_pos.p, tile_pos.data(), (size_t)ntiles * 4, cudaMemcpyHostToDevice, st));
+  }
+  MR_CUDA(ctx, cudaMemsetAsync(ws.counters.p, 0, 16 * sizeof(uint64_t), st));
+  unsigned long long* ctr = ws.counters.as<unsigned long long>();
+  // counters: 0 lookups, 1 raw hits, 2 invalid hits, 3 groups, 4 survivors, 5 info total
+  uint64_t h_ctr[16] = { 0 };
+
+  // ---- seeds + lookups ----------------------------------------------------------------------------
+  timer.begin("seed lookup");
+  if(ntiles) {
+    MR_CUDA(ctx, cudaMemsetAsync(ws.tile_tbase.p, 0, (size_t)ntiles * 4, st));
+    if(k <= 17) {
+      seed_count_kernel<<<ntiles, kSeedThreads, 0, st>>>(d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                       k, ws.tile_cand.as<uint32_t>());
+      MR_LAUNCHED(ctx);
+      tile_tbase_kernel<<<div_up(nreads, 128), 128, 0, st>>>(ws.tile_first.as<uint32_t>(), nreads, ws.tile_cand.as<uint32_t>(),
+                                                             ws.tile_tbase.as<uint32_t>());
+      MR_LAUNCHED(ctx);
+    }
+    seed_lookup_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                      ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                                      ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0);
+    MR_LAUNCHED(ctx);
+    timer.next("count threshold");
+    uint32_t nbits = 32;
+    if(p->max_count > 1) { nbits = 0; while((1u << nbits) < (uint32_t)p->max_count) ++nbits; }
+    else if(p->max_count == 1) nbits = 1;
+    read_threshold_kernel<<<nreads, 256, 0, st>>>(d_read_start, nbits, ws.size.as<uint32_t>(), ws.thr.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+  }
+  timer.next("hit expansion");
+  MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.size.as<uint32_t>() }, T, ws.hit_off.as<uint64_t>(),
+                                                           ws.scan_scratch, (uint64_t*)(ctr + 1))));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  const uint64_t H = h_ctr[1];
+  res->view.n_kmers_looked_up = h_ctr[0];
+  if(H >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 hits in one batch; use smaller batches");
+
+  uint64_t G = 0, S = 0, cap = 0;
+  const bool taps = ctx->keep_taps;
+  uint64_t *skeys = nullptr, *spays = nullptr;
+  chain_args A;
+  memset(&A, 0, sizeof(A));
+  if(H) {
+    MR_TRY(ws.key0.ensure(ctx, (H + 2) * 8)); MR_TRY(ws.key1.ensure(ctx, (H + 2) * 8));
+    MR_TRY(ws.pay0.ensure(ctx, (H + 2) * 8)); MR_TRY(ws.pay1.ensure(ctx, (H + 2) * 8));
+    expand_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                 ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ws.hit_off.as<uint64_t>(),
+                                                 ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
+    MR_LAUNCHED(ctx);
+    timer.next("group sort");
+    int sr_bits = 1;
+    while((1ULL << sr_bits) <= (uint64_t)iv.nseq) ++sr_bits;
+    bool in_first = true;
+    MR_TRY((prim::radix_sort_pairs<uint64_t, uint64_t>(ctx, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ws.key1.as<uint64_t>(),
+                                                       ws.pay1.as<uint64_t>(), H, 0, sr_bits, ws.sort, &in_first)));
+    skeys = in_first ? ws.key0.as<uint64_t>() : ws.key1.as<uint64_t>();
+    spays = in_first ? ws.pay0.as<uint64_t>() : ws.pay1.as<uint64_t>();
+    uint64_t* alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
+    uint64_t* alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
+    // group heads -> group_start
+    MR_TRY((prim::exclusive_scan<head_flag, uint64_t>(ctx, head_flag{ skeys, iv.nseq }, H, alt_key, ws.scan_scratch, (uint64_t*)(ctr + 3))));
+    MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    G = h_ctr[3];
+    const uint64_t Hvalid = H - h_ctr[2];
+    res->view.n_hits = Hvalid;
+    res->view.n_groups = G;
+    MR_TRY(ws.group_start.ensure(ctx, (G + 2) * 8));
+    group_scatter_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(skeys, H, iv.nseq, alt_key, ws.group_start.as<uint64_t>());
+    MR_LAUNCHED(ctx);
+    MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &Hvalid, 8, cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));   // Hvalid is a stack variable
+
+    // ---- chaining + coords ------------------------------------------------------------------------
+    timer.next("chain coords");
+    MR_TRY(ws.chainL.ensure(ctx, (H + 2) * 16));
+    MR_TRY(ws.read_cnt.ensure(ctx, ((size_t)nreads + 2) * 4));
+    A.iv = iv; A.keys = skeys; A.pays = spays; A.group_start = ws.group_start.as<uint64_t>(); A.ngroups = G;
+    A.read_start = d_read_start;
+    {
+      char* c = (char*)ws.chainL.p;
+      A.cb.Lpb = (int32_t*)c; A.cb.Lsr = (int32_t*)(c + (H + 2) * 4); A.cb.Llen = (uint32_t*)(c + (H + 2) * 8);
+      A.cb.Lelt = (uint32_t*)(c + (H + 2) * 12);
+      A.cb.pprev = (uint32_t*)alt_pay; A.cb.cstart = (uint32_t*)alt_pay + (H + 2);
+    }
+    A.a = p->stretch_factor; A.b = p->stretch_constant; A.C = p->stretch_cap;
+    A.matching_mers = p->matching_mers; A.matching_bases = p->matching_bases; A.forward = p->forward;
+    A.unitigs_k = idx->has_unitigs ? p->unitigs_k : 0; A.n_unitigs = idx->n_unitigs;
+    A.unitig_ids = idx->unitig_ids.as<uint32_t>(); A.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
+    if(taps) {
+      MR_TRY(ws.tap_lens.ensure(ctx, (G + 1) * 8));
+      MR_TRY(ws.tap_cf.ensure(ctx, (H + 2) * 4)); MR_TRY(ws.tap_cb.ensure(ctx, (H + 2) * 4));
+      A.tap_lens = ws.tap_lens.as<uint2>(); A.tap_cf = ws.tap_cf.as<uint32_t>(); A.tap_cb = ws.tap_cb.as<uint32_t>();
+      A.tap_sub = (uint32_t*)alt_key;       // gpos is dead once group_start exists
+    }
+    cap = std::max<uint64_t>(1 << 20, G / 4 + 1024);
+    if(cap > G) cap = G;
+    if(cap == 0) cap = 1;
+    for(int attempt = 0; attempt < 2; ++attempt) {
+      MR_TRY(ws.sv_i32.ensure(ctx, cap * 4 * 5 + 4096)); MR_TRY(ws.sv_u32.ensure(ctx, cap * 4 * 8 + 4096));
+      MR_TRY(ws.sv_f64.ensure(ctx, cap * 8 * 3 + 4096)); MR_TRY(ws.sv_u64.ensure(ctx, cap * 8 * 2 + 4096));
+      MR_TRY(ws.sv_u8.ensure(ctx, cap * 2 + 4096));
+      survivors& sv = A.sv;
+      { int32_t* b = ws.sv_i32.as<int32_t>(); sv.rs = b; sv.re = b + cap; sv.qs = b + 2 * cap; sv.qe = b + 3 * cap; sv.nb_mers = b + 4 * cap; }
+      { uint32_t* b = ws.sv_u32.as<uint32_t>(); sv.pb_cons = b; sv.sr_cons = b + cap; sv.pb_cover = b + 2 * cap; sv.sr_cover = b + 3 * cap;
+        sv.ql = b + 4 * cap; sv.sr = b + 5 * cap; sv.read = b + 6 * cap; sv.info_len = b + 7 * cap; }
+      { double* b = ws.sv_f64.as<double>(); sv.stretch = b; sv.offset = b + cap; sv.avg_err = b + 2 * cap; }
+      { uint64_t* b = ws.sv_u64.as<uint64_t>(); sv.chain_pos = b; }
+      { uint8_t* b = ws.sv_u8.as<uint8_t>(); sv.rn = b; sv.use_bwd = b + cap; }
+      sv.cap = cap; sv.count = ctr + 4; sv.info_total = ctr + 5; sv.read_cnt = ws.read_cnt.as<uint32_t>();
+      MR_CUDA(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(uint64_t), st));
+      MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
+      if(G) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 16, (G + 3) / 4);
+        chain_coords_kernel<<<grid, 128, 0, st>>>(A);
+        MR_LAUNCHED(ctx);
+      }
+      MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      MR_CUDA(ctx, cudaStreamSynchronize(st));
+      S = h_ctr[4];
+      if(S <= cap) break;
+      cap = S;                                 // rare: more survivors than provisioned, run again
+    }
+  } else {
+    MR_TRY(ws.read_cnt.ensure(ctx, ((size_t)nreads + 2) * 4));
+    MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
+  }
+  if(S >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 coords rows");
+  const uint64_t info_total = S ? h_ctr[5] : 0;
+
+  // ---- kmers_info, per-read order, final rows ---------------------------------------------------
+  timer.next("coords order");
+  MR_TRY(ws.read_coords.ensure(ctx, ((size_t)nreads + 2) * 8));
+  MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.read_cnt.as<uint32_t>() }, (uint64_t)nreads + 1,
+                                                           ws.read_coords.as<uint64_t>(), ws.scan_scratch, nullptr)));
+  coords_soa fin;
+  memset(&fin, 0, sizeof(fin));
+  const uint64_t Sc = std::max<uint64_t>(S, 1);
+  MR_TRY(ws.fin_i32.ensure(ctx, Sc * 4 * 5)); MR_TRY(ws.fin_u32.ensure(ctx, Sc * 4 * 8)); MR_TRY(ws.fin_f64.ensure(ctx, Sc * 8 * 3));
+  MR_TRY(ws.fin_u64.ensure(ctx, Sc * 8 * 3)); MR_TRY(ws.fin_u8.ensure(ctx, Sc * 2));
+  { int32_t* b = ws.fin_i32.as<int32_t>(); fin.rs = b; fin.re = b + Sc; fin.qs = b + 2 * Sc; fin.qe = b + 3 * Sc; fin.nb_mers = b + 4 * Sc; }
+  { uint32_t* b = ws.fin_u32.as<uint32_t>(); fin.pb_cons = b; fin.sr_cons = b + Sc; fin.pb_cover = b + 2 * Sc; fin.sr_cover = b + 3 * Sc;
+    fin.ql = b + 4 * Sc; fin.sr = b + 5 * Sc; fin.read = b + 6 * Sc; fin.info_len = b + 7 * Sc; }
+  { double* b = ws.fin_f64.as<double>(); fin.stretch = b; fin.offset = b + Sc; fin.avg_err = b + 2 * Sc; }
+  { uint64_t* b = ws.fin_u64.as<uint64_t>(); fin.info_off = b; fin.chain_pos = b + Sc; }
+  { uint8_t* b = ws.fin_u8.as<uint8_t>(); fin.rn = b; fin.use_bwd = b + Sc; }
+  uint64_t* sv_info_off = ws.fin_u64.as<uint64_t>() + 2 * Sc;
+  MR_TRY(ws.kinfo.ensure(ctx, (info_total + 1) * 4)); MR_TRY(ws.binfo.ensure(ctx, (info_total + 1) * 4));
+  if(S) {
+    MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ A.sv.info_len }, S, sv_info_off, ws.scan_scratch, nullptr)));
+    if(info_total) {
+      info_args I;
+      I.n = S; I.chain_pos = A.sv.chain_pos; I.nb_mers = A.sv.nb_mers; I.sr = A.sv.sr; I.use_bwd = A.sv.use_bwd; I.ql = A.sv.ql;
+      I.info_off = sv_info_off; I.info_len = A.sv.info_len; I.chain = A.cb.Lelt; I.pays = spays;
+      I.unitig_ids = idx->unitig_ids.as<uint32_t>(); I.unitig_off = idx->unitig_off.as<uint64_t>();
+      I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k; I.unitigs_k = p->unitigs_k;
+      I.kinfo = ws.kinfo.as<int32_t>(); I.binfo = ws.binfo.as<int32_t>();
+      kmers_info_kernel<<<div_up(S, 128), 128, 0, st>>>(I);
+      MR_LAUNCHED(ctx);
+    }
+    MR_TRY(ws.read_cursor.ensure(ctx, ((size_t)nreads + 1) * 4));
+    MR_TRY(ws.slot.ensure(ctx, S * 4)); MR_TRY(ws.order.ensure(ctx, S * 4));
+    MR_CUDA(ctx, cudaMemsetAsync(ws.read_cursor.p, 0, ((size_t)nreads + 1) * 4, st));
+    bucket_rows_kernel<<<div_up(S, 256), 256, 0, st>>>(S, A.sv.read, ws.read_coords.as<uint64_t>(), ws.read_cursor.as<uint32_t>(),
+                                                       ws.slot.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    rank_rows_kernel<<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+                                                                         A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, ws.order.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    gather_args Gt;
+    Gt.n = S; Gt.order = ws.order.as<uint32_t>(); Gt.sv = A.sv; Gt.sv_info_off = sv_info_off; Gt.out = fin;
+    gather_rows_kernel<<<div_up(S, 256), 256, 0, st>>>(Gt);
+    MR_LAUNCHED(ctx);
+  }
+
+  // ---- overlap graph -----------------------------------------------------------------------------
+  const bool graph = p->run_graph != 0;
+  graph_args GA;
+  memset(&GA, 0, sizeof(GA));
+  if(graph) {
+    timer.next("overlap graph");
+    MR_TRY(ws.node_i32.ensure(ctx, Sc * 4 * 7)); MR_TRY(ws.node_u8.ensure(ctx, Sc * 2)); MR_TRY(ws.node_f64.ensure(ctx, Sc * 8 * 2));
+    GA.nreads = nreads; GA.read_coords = ws.read_coords.as<uint64_t>(); GA.read_len = ws.read_len.as<uint32_t>(); GA.c = fin;
+    GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
+    GA.unitig_ids = idx->unitig_ids.as<uint32_t>(); GA.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
+    GA.unitig_len = idx->unitig_len.as<int32_t>(); GA.n_unitigs = idx->n_unitigs; GA.unitigs_k = p->unitigs_k;
+    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases;
+    { int32_t* b = ws.node_i32.as<int32_t>(); GA.lstart = b; GA.lprev = b + Sc; GA.lpath = b + 2 * Sc; GA.lunitigs = b + 3 * Sc;
+      GA.component = b + 4 * Sc; GA.uf_rank = b + 5 * Sc; GA.order = b + 6 * Sc; }
+    { uint8_t* b = ws.node_u8.as<uint8_t>(); GA.start_node = b; GA.end_node = b + Sc; }
+    { double* b = ws.node_f64.as<double>(); GA.imp_s = b; GA.imp_e = b + Sc; }
+    if(S) MR_TRY(launch_graph(ctx, GA));
+  }
+  timer.next("result download");
+
+  // ---- results to pinned host memory ----------------------------------------------------------------
+  {
+    auto rnd = [](uint64_t b) { return (b + 63) / 64 * 64; };
+    uint64_t bytes = rnd(((uint64_t)nreads + 1) * 8) + 5 * rnd(Sc * 4) + 8 * rnd(Sc * 4) + 3 * rnd(Sc * 8) + rnd(Sc * 8) + 2 * rnd(Sc)
+                     + 2 * rnd((info_total + 1) * 4) + (graph ? 2 * rnd(Sc) + 5 * rnd(Sc * 4) : 0);
+    MR_TRY(res->host.ensure(ctx, bytes + 4096));
+    char* cur = res->host.as<char>();
+    auto pull = [&](const void* dsrc, uint64_t nbytes) -> const void* {
+      void* dst = cur;
+      cur += rnd(std::max<uint64_t>(nbytes, 1));
+      if(nbytes) cudaMemcpyAsync(dst, dsrc, nbytes, cudaMemcpyDeviceToHost, st);
+      return dst;
+    };
+    mr_result_view& v = res->view;
+    v.ncoords = S;
+    v.read_coords = (const uint64_t*)pull(ws.read_coords.p, ((uint64_t)nreads + 1) * 8);
+    v.rs = (const int32_t*)pull(fin.rs, S * 4); v.re = (const int32_t*)pull(fin.re, S * 4);
+    v.qs = (const int32_t*)pull(fin.qs, S * 4); v.qe = (const int32_t*)pull(fin.qe, S * 4);
+    v.nb_mers = (const int32_t*)pull(fin.nb_mers, S * 4);
+    v.pb_cons = (const uint32_t*)pull(fin.pb_cons, S * 4); v.sr_cons = (const uint32_t*)pull(fin.sr_cons, S * 4);
+    v.pb_cover = (const uint32_t*)pull(fin.pb_cover, S * 4); v.sr_cover = (const uint32_t*)pull(fin.sr_cover, S * 4);
+    v.ql = (const uint32_t*)pull(fin.ql, S * 4); v.sr = (const uint32_t*)pull(fin.sr, S * 4);
+    v.rn = (const uint8_t*)pull(fin.rn, S); v.use_bwd = (const uint8_t*)pull(fin.use_bwd, S);
+    v.stretch = (const double*)pull(fin.stretch, S * 8); v.offset = (const double*)pull(fin.offset, S * 8);
+    v.avg_err = (const double*)pull(fin.avg_err, S * 8);
+    v.info_off = (const uint64_t*)pull(fin.info_off, S * 8); v.info_len = (const uint32_t*)pull(fin.info_len, S * 4);
+    v.kmers_info = (const int32_t*)pull(ws.kinfo.p, info_total * 4); v.bases_info = (const int32_t*)pull(ws.binfo.p, info_total * 4);
+    if(graph) {
+      v.start_node = (const uint8_t*)pull(GA.start_node, S); v.end_node = (const uint8_t*)pull(GA.end_node, S);
+      v.lstart = (const int32_t*)pull(GA.lstart, S * 4); v.lprev = (const int32_t*)pull(GA.lprev, S * 4);
+      v.lpath = (const int32_t*)pull(GA.lpath, S * 4); v.lunitigs = (const int32_t*)pull(GA.lunitigs, S * 4);
+      v.component = (const int32_t*)pull(GA.component, S * 4);
+    }
+    MR_CUDA(ctx, cudaGetLastError());
+  }
+
+  // ---- parity taps: (read, super-read) hit lists and both chains, rows sorted by (read, sr) ------
+  if(taps && G) {
+    std::vector<uint64_t> hk(H), hp(H), hg(G + 1);
+    std::vector<uint2> hl(G);
+    std::vector<uint32_t> hcf(H), hcb(H);
+    MR_CUDA(ctx, cudaMemcpyAsync(hk.data(), skeys, H * 8, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(hp.data(), spays, H * 8, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(hg.data(), ws.group_start.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(hl.data(), ws.tap_lens.p, G * 8, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(hcf.data(), ws.tap_cf.p, H * 4, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(hcb.data(), ws.tap_cb.p, H * 4, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<uint64_t> ord(G);
+    for(uint64_t g = 0; g < G; ++g) ord[g] = g;
+    std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return hk[hg[a]] < hk[hg[b]]; });
+    for(uint64_t g : ord) {
+      const uint64_t b = hg[g], e = hg[g + 1];
+      int64_t nf = 0, nbw = 0;
+      for(uint64_t i = b; i < e; ++i) ((int32_t)(uint32_t)(hp[i] >> 32) > 0 ? nf : nbw)++;
+      const int64_t row[6] = { (int64_t)(hk[b] >> 32), (int64_t)(uint32_t)hk[b], nf, nbw, hl[g].x, hl[g].y };
+      res->tap_groups.insert(res->tap_groups.end(), row, row + 6);
+      for(int pass = 0; pass < 2; ++pass)
+        for(uint64_t i = b; i < e; ++i) {
+          const int32_t so = (int32_t)(uint32_t)(hp[i] >> 32);
+          if((so > 0) == (pass == 0)) { res->tap_offsets.push_back((int32_t)(uint32_t)hp[i]); res->tap_offsets.push_back(so); }
+        }
+      for(uint32_t t = 0; t < hl[g].x; ++t) res->tap_lis.push_back(hcf[b + t]);
+      for(uint32_t t = 0; t < hl[g].y; ++t) res->tap_lis.push_back(hcb[b + t]);
+    }
+  }
+  timer.end();
+  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  *out = res.release();
+  return MR_OK;
+}
+
+extern "C" {
+
+int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
+                          const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!idx || !p || !out || !h_read_start || !d_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
+  if(idx->ctx != ctx) return ctx->fail(MR_EINVAL, "mr_align_batch: index belongs to another context");
+  if(p->window_size != 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size other than 1 is not implemented");
+  if(p->max_match) return ctx->fail(MR_EINVAL, "mr_align_batch: --max-match is not implemented yet");
+  if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
+    return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->timers.clear();
+  phase_timer timer(ctx);
+  const int rc = align_batch_impl(ctx, idx, p, d_bases, d_read_start, h_read_start, nreads, timer, out);
+  cudaStreamSynchronize(ctx->stream);
+  if(rc == MR_OK) timer.collect();
+  return rc;
+}
+
+int mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p, const char* bases, const uint64_t* read_start,
+                   uint32_t nreads, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!bases || !read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  const uint64_t T = read_start[nreads];
+  MR_TRY(ws.bases.ensure(ctx, T + 64));
+  MR_TRY(ws.read_start.ensure(ctx, ((size_t)nreads + 1) * 8));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.bases.p, bases, T, cudaMemcpyHostToDevice, ctx->stream));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.read_start.p, read_start, ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return mr_align_batch_device(ctx, idx, p, ws.bases.as<char>(), ws.read_start.as<uint64_t>(), read_start, nreads, out);
+}
+
+void mr_result_free(mr_result* r) {
+  if(!r) return;
+  cudaSetDevice(r->ctx->device);
+  delete r;
+}
+
+int mr_result_get(const mr_result* r, mr_result_view* view) {
+  if(!r || !view) return MR_EINVAL;
+  *view = r->view;
+  return MR_OK;
+}
+
+int mr_result_taps(const mr_result* r, uint64_t* ngroups, const int64_t** groups, uint64_t* noffsets, const int32_t** offsets,
+                   uint64_t* nlis, const uint32_t** lis) {
+  if(!r) return MR_EINVAL;
+  if(ngroups) *ngroups = r->tap_groups.size() / 6;
+  if(groups) *groups = r->tap_groups.data();
+  if(noffsets) *noffsets = r->tap_offsets.size() / 2;
+  if(offsets) *offsets = r->tap_offsets.data();
+  if(nlis) *nlis = r->tap_lis.size();
+  if(lis) *lis = r->tap_lis.data();
+  return MR_OK;
+}
+
+} // extern "C"

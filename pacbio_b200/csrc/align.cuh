@@ -1,0 +1,62 @@
+// Shared declarations for the per-batch alignment pipeline (align.cu, graph.cu, result.cu).
+#pragma once
+#include "index.cuh"
+#include "primitives.cuh"
+
+constexpr int      kTile        = 1024;           // read positions per CTA in the seed / expand kernels
+constexpr int      kSeedThreads = 256;
+constexpr uint32_t kNone        = 0xffffffffu;
+
+// Final per-coords arrays on the device (structure of arrays, rows sorted per read).
+struct coords_soa {
+  int32_t  *rs, *re, *qs, *qe, *nb_mers;
+  uint32_t *pb_cons, *sr_cons, *pb_cover, *sr_cover, *ql, *sr, *read;
+  uint8_t  *rn, *use_bwd;
+  double   *stretch, *offset, *avg_err;
+  uint64_t *info_off;
+  uint32_t *info_len;
+  uint64_t *chain_pos;     // start of the group's slice in the sorted hit arrays
+};
+
+// Scratch that lives in the context and is reused from batch to batch.
+struct mr_workspace {
+  dev_buf bases, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
+  dev_buf size, rec, hit_off, thr, counters;
+  dev_buf key0, key1, pay0, pay1, chainL, group_start;
+  dev_buf sv_i32, sv_u32, sv_f64, sv_u64, sv_u8;        // survivors, unsorted
+  dev_buf fin_i32, fin_u32, fin_f64, fin_u64, fin_u8;   // final rows
+  dev_buf read_cnt, read_coords, read_cursor, slot, order;
+  dev_buf kinfo, binfo;
+  dev_buf node_i32, node_u8, node_f64;
+  dev_buf tap_lens, tap_cf, tap_cb;
+  dev_buf scan_scratch;
+  prim::sort_scratch sort;
+};
+
+struct mr_result {
+  mr_context* ctx = nullptr;
+  pinned_buf  host;                 // one pinned slab holding every array of the view
+  mr_result_view view;
+  // taps
+  std::vector<int64_t>  tap_groups;
+  std::vector<int32_t>  tap_offsets;
+  std::vector<uint32_t> tap_lis;
+};
+
+// graph.cu
+struct graph_args {
+  uint32_t nreads;
+  const uint64_t* read_coords;
+  const uint32_t* read_len;
+  coords_soa c;
+  const int32_t *kinfo, *binfo;
+  const uint32_t* unitig_ids; const uint64_t* unitig_off; const int32_t* unitig_len;
+  uint32_t n_unitigs, unitigs_k;
+  double overlap_play, errors;
+  int bases;
+  // outputs / scratch, one entry per row
+  uint8_t *start_node, *end_node;
+  int32_t *lstart, *lprev, *lpath, *lunitigs, *component, *uf_rank, *order;
+  double  *imp_s, *imp_e;
+};
+int launch_graph(mr_context* ctx, const graph_args& a);

@@ -1,0 +1,92 @@
+// Host side of the B200 mega-reads tools: input parsing (super-read FASTA, k-unitig files,
+// long-read FASTA/FASTQ streams), 2-bit packing, and the per-read post-processing that turns the
+// device's coords / graph rows into the reference's text records.  Plain C++17, no CUDA; the
+// device is reached only through include/mega_reads_b200.h.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mega_reads_b200.h"
+
+namespace mrh {
+
+// ---- super-reads: sequence_psa::append_fasta (superread_parser.cc:12-46) + frag_info (frag_info.hpp:18-35)
+struct super_reads {
+  std::vector<uint64_t>    text2bit;     // compact_dna layout
+  uint64_t                 n = 0;
+  std::vector<uint64_t>    start;        // nseq + 1
+  std::vector<std::string> name;         // header line after '>'
+  std::vector<uint32_t>    unitig_ids;   // CSR of forward paths, (id << 1) | (ori == 'R')
+  std::vector<uint64_t>    unitig_off;   // nseq + 1
+  uint32_t nseq() const { return (uint32_t)name.size(); }
+  void append_fasta(const std::string& path);          // throws std::runtime_error like the reference
+  // unitig path of super-read s in the orientation a coords row uses it
+  uint32_t path_len(uint32_t s) const { return (uint32_t)(unitig_off[s + 1] - unitig_off[s]); }
+  uint32_t path_at(uint32_t s, bool bwd, uint32_t t) const {
+    const uint64_t b = unitig_off[s], e = unitig_off[s + 1];
+    return bwd ? (unitig_ids[e - 1 - t] ^ 1u) : unitig_ids[b + t];
+  }
+  std::string row_name(uint32_t s, bool bwd) const;   // fwd.name / bwd.name of frag_info
+};
+
+// ---- k-unitigs: read_unitigs_lengths / read_unitigs_sequences (misc.cc:11-37)
+struct unitigs {
+  std::vector<int32_t>     len;
+  std::vector<std::string> seq;          // only with -u
+  void load_lengths(const std::string& path);
+  void load_sequences(const std::string& path);
+};
+
+// ---- long reads: jellyfish::whole_sequence_parser as used in create_mega_reads.cc:51-58
+struct read_batch {
+  std::string              bases;        // concatenated
+  std::vector<uint64_t>    start;        // nreads + 1
+  std::vector<std::string> name;         // header up to the first white space
+  uint32_t nreads() const { return (uint32_t)name.size(); }
+  void clear() { bases.clear(); start.assign(1, 0); name.clear(); }
+};
+class read_stream {
+  std::vector<std::string> paths_;
+  size_t next_path_ = 0;
+  FILE*  f_ = nullptr;
+  std::vector<char> buf_;
+  size_t pos_ = 0, end_ = 0;
+  bool   eof_ = false;
+  std::string pending_header_;
+  bool   have_pending_ = false;
+  char   pending_kind_ = 0;
+  bool fill();
+  bool getline(std::string& line, bool append);
+  bool open_next();
+public:
+  explicit read_stream(const std::vector<std::string>& paths) : paths_(paths), buf_(1 << 22) { }
+  ~read_stream() { if(f_) fclose(f_); }
+  // appends reads until the batch holds >= max_bases bases or max_reads reads; false when exhausted
+  bool next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads);
+};
+
+// ---- options shared by the two tools (Appendix B of SURVEY.md; create_mega_reads_cmdline.yaggo)
+struct graph_options {
+  double   overlap_play = 1.3;
+  uint32_t k_len = 0;
+  double   density = 0.029, min_length = 100.0;
+  int      tiling = 1;      // 0 none, 1 greedy, 2 maximal, 3 weighted
+  int      trim = 0;        // 0 none, 1 match, 2 branch (== match)
+};
+
+// Text records of create_mega_reads for reads [r0, r1) of a result (overlap_graph.cc:61-299,
+// overlap_graph.hpp:198-262): best terminal node per component, tiling, one line per mega-read.
+void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
+                       const super_reads& sr, const unitigs& u, const graph_options& o, std::string& out);
+// same, fanned out over `threads` host threads, output in read order
+void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
+                          const graph_options& o, unsigned threads, std::string& out);
+
+// jf_aligner coords records (jf_aligner.cc:41-70)
+void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
+                   bool compact, bool zero_skip, std::string& out);
+
+} // namespace mrh

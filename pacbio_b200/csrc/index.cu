@@ -1,0 +1,284 @@
+// Suffix-array construction and batched k-mer lookup on the device.
+// Replaces the reference's PSA::PSA -> SA::create_mt (psa.hpp:130-140, mer_sa_imp.hpp:197-267:
+// histogram, partial sums, atomic scatter, 4^m std::sort calls) by one stable LSD radix sort of
+// (padded k-mer, position) pairs seeded in descending position order, and PSA::search
+// (mer_sa_imp.hpp:369-479) by a prefix-table probe plus a scan of the bucket's tails.
+#include "index.cuh"
+#include "primitives.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+// k-mer starting at `pos`, first base most significant, bases past the end of the text read as A
+__device__ __forceinline__ uint64_t text_kmer(const uint64_t* __restrict__ text, uint64_t pos, uint32_t k) {
+  const uint64_t w = pos >> 5;
+  const unsigned sh = (unsigned)(pos & 31) * 2;
+  const uint64_t w0 = text[w], w1 = text[w + 1];
+  const uint64_t raw = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0;
+  return reverse_pairs(raw) >> (64 - 2 * k);
+}
+
+__global__ void clear_text_tail_kernel(uint64_t* text, uint64_t n) {
+  const uint64_t w = n >> 5;
+  const unsigned used = (unsigned)(n & 31) * 2;
+  if(used) text[w] &= (1ULL << used) - 1; else text[w] = 0;
+  text[w + 1] = 0;
+}
+
+// entry i holds position nsa-1-i: the stable sort then leaves equal k-mers in descending position
+__global__ void __launch_bounds__(256) sa_keys_kernel(const uint64_t* __restrict__ text, uint32_t nsa, uint32_t k,
+                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsa; i += stride) {
+    const uint32_t pos = nsa - 1 - i;
+    keys[i] = text_kmer(text, pos, k);
+    vals[i] = pos;
+  }
+}
+
+// tails + prefix counts from the sorted keys: counts[v] = first rank whose m-mer is >= v.
+// Runs of empty prefixes longer than kGapInline are queued and filled by whole CTAs afterwards
+// (a tiny text leaves almost all of the 4^m prefixes empty).
+constexpr int kGapInline = 256;
+struct gap_item { uint32_t first, last, value; };
+
+__global__ void __launch_bounds__(256) sa_finish_kernel(const uint64_t* __restrict__ keys, uint32_t nsa, uint32_t tail_bits,
+                                                        uint32_t nprefix, uint32_t* __restrict__ tails,
+                                                        uint32_t* __restrict__ counts,
+                                                        gap_item* __restrict__ gaps, uint32_t* __restrict__ ngaps) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint64_t tmask = tail_bits >= 64 ? ~0ULL : ((1ULL << tail_bits) - 1);
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= nsa; i += stride) {
+    // i == nsa is the virtual end: fills counts above the last occupied prefix
+    const int64_t prev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> tail_bits);
+    const int64_t cur  = i == nsa ? (int64_t)nprefix : (int64_t)(keys[i] >> tail_bits);
+    if(i < nsa) tails[i] = (uint32_t)(keys[i] & tmask);
+    if(cur - prev <= kGapInline) {
+      for(int64_t v = prev + 1; v <= cur; ++v) counts[v] = i;
+    } else {
+      const uint32_t slot = atomicAdd(ngaps, 1u);
+      gaps[slot] = gap_item{ (uint32_t)(prev + 1), (uint32_t)cur, i };
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sa_fill_gaps_kernel(const gap_item* __restrict__ gaps, const uint32_t* __restrict__ ngaps,
+                                                           uint32_t* __restrict__ counts) {
+  const uint32_t n = *ngaps;
+  for(uint32_t g = blockIdx.x; g < n; g += gridDim.x) {
+    const gap_item it = gaps[g];
+    for(uint64_t v = (uint64_t)it.first + threadIdx.x; v <= it.last; v += blockDim.x) counts[v] = it.value;
+  }
+}
+
+__global__ void __launch_bounds__(256) blk_table_kernel(const uint32_t* __restrict__ sr_start, uint32_t nseq,
+                                                        uint32_t nblk, uint32_t* __restrict__ blk) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= nblk) return;
+  const uint64_t x = (uint64_t)b << kBlkShift;
+  uint32_t lo = 0, hi = nseq;                 // largest i in [0, nseq) with sr_start[i] <= x
+  while(hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if(sr_start[mid] <= x) lo = mid; else hi = mid; }
+  blk[b] = lo;
+}
+
+__global__ void __launch_bounds__(256) widen_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
+// one thread per query.  Every query makes two dependent, effectively random HBM accesses
+// (8 bytes of the prefix table, then the bucket's tails): the kernel is bound by random-sector
+// throughput, so all it needs is enough independent loads in flight per SM.
+__global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64_t* __restrict__ mers, uint64_t q,
+                                                     uint64_t* __restrict__ index_out, uint64_t* __restrict__ nb_out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+    uint32_t idx, nb;
+    index_lookup(iv, mers[i], idx, nb);
+    index_out[i] = idx;
+    nb_out[i]    = nb;
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
+                    const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
+                    uint32_t n_unitigs, uint32_t psa_min, uint32_t k, mr_index** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!out || !text2bit || !sr_start || nseq == 0) return ctx->fail(MR_EINVAL, "mr_index_create: null argument");
+  if(!(psa_min >= 1 && psa_min < k && k <= 31))
+    return ctx->fail(MR_EINVAL, "mr_index_create: need 1 <= psa_min < mer <= 31");
+  if(psa_min > 15) return ctx->fail(MR_ELIMIT, "mr_index_create: psa_min > 15 (prefix table over 4 GiB) not supported");
+  if(k - psa_min > (uint32_t)kMaxShort) return ctx->fail(MR_ELIMIT, "mr_index_create: mer - psa_min > 16 not supported");
+  if(n < k) return ctx->fail(MR_EINVAL, "mr_index_create: text shorter than one k-mer");
+  if(n >= 0xfffffff0ULL) return ctx->fail(MR_ELIMIT, "mr_index_create: text of 2^32 bases or more not supported");
+  if(sr_start[0] != 0 || sr_start[nseq] != n) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must span [0, n]");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->timers.clear();
+  phase_timer timer(ctx);
+
+  std::unique_ptr<mr_index> idx(new mr_index);
+  idx->ctx = ctx; idx->n = n; idx->k = k; idx->m = psa_min; idx->nseq = nseq;
+  idx->nsa = (uint32_t)(n - psa_min + 1);
+  const uint32_t nsa = idx->nsa;
+  const uint64_t nwords = (n + 31) / 32;
+  const uint32_t tail_bits = 2 * (k - psa_min);
+  const uint32_t nprefix = 1u << (2 * psa_min);
+  cudaStream_t st = ctx->stream;
+
+  timer.begin("Super read upload");
+  MR_TRY(idx->text.ensure(ctx, (nwords + 2) * sizeof(uint64_t)));
+  MR_CUDA(ctx, cudaMemsetAsync(idx->text.as<uint64_t>() + nwords, 0, 2 * sizeof(uint64_t), st));
+  MR_CUDA(ctx, cudaMemcpyAsync(idx->text.p, text2bit, nwords * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  clear_text_tail_kernel<<<1, 1, 0, st>>>(idx->text.as<uint64_t>(), n);
+  MR_LAUNCHED(ctx);
+  {
+    std::vector<uint32_t> starts32(nseq + 1);
+    for(uint32_t i = 0; i <= nseq; ++i) {
+      if(i && sr_start[i] <= sr_start[i - 1]) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must be strictly increasing");
+      starts32[i] = (uint32_t)sr_start[i];
+    }
+    MR_TRY(idx->sr_start.ensure(ctx, ((size_t)nseq + 2) * sizeof(uint32_t)));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->sr_start.p, starts32.data(), ((size_t)nseq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  const uint32_t nblk = (uint32_t)(n >> kBlkShift) + 1;
+  MR_TRY(idx->blk.ensure(ctx, ((size_t)nblk + 1) * sizeof(uint32_t)));
+  blk_table_kernel<<<div_up(nblk, 256), 256, 0, st>>>(idx->sr_start.as<uint32_t>(), nseq, nblk, idx->blk.as<uint32_t>());
+  MR_LAUNCHED(ctx);
+
+  if(unitig_ids && unitig_off && unitig_len && n_unitigs) {
+    idx->has_unitigs = true;
+    idx->n_unitigs = n_unitigs;
+    const uint64_t total = unitig_off[nseq];
+    MR_TRY(idx->unitig_ids.ensure(ctx, (total + 1) * sizeof(uint32_t)));
+    MR_TRY(idx->unitig_off.ensure(ctx, ((size_t)nseq + 1) * sizeof(uint64_t)));
+    MR_TRY(idx->unitig_len.ensure(ctx, (size_t)n_unitigs * sizeof(int32_t)));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_ids.p, unitig_ids, total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_off.p, unitig_off, ((size_t)nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_len.p, unitig_len, (size_t)n_unitigs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+
+  timer.next("sorting");
+  {
+    dev_buf k0, k1, v0, v1;
+    prim::sort_scratch scratch;
+    MR_TRY(k0.ensure(ctx, (size_t)nsa * sizeof(uint64_t)));
+    MR_TRY(k1.ensure(ctx, (size_t)nsa * sizeof(uint64_t)));
+    MR_TRY(v0.ensure(ctx, (size_t)nsa * sizeof(uint32_t)));
+    MR_TRY(v1.ensure(ctx, (size_t)nsa * sizeof(uint32_t)));
+    sa_keys_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(idx->text.as<uint64_t>(), nsa, k, k0.as<uint64_t>(), v0.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    bool in_first = true;
+    MR_TRY((prim::radix_sort_pairs<uint64_t, uint32_t>(ctx, k0.as<uint64_t>(), v0.as<uint32_t>(), k1.as<uint64_t>(),
+                                                       v1.as<uint32_t>(), nsa, 0, 2 * (int)k, scratch, &in_first)));
+    timer.next("partial sums");
+    const uint64_t* keys = in_first ? k0.as<uint64_t>() : k1.as<uint64_t>();
+    dev_buf& vres = in_first ? v0 : v1;
+    MR_TRY(idx->tails.ensure(ctx, ((size_t)nsa + 64) * sizeof(uint32_t)));
+    MR_TRY(idx->counts.ensure(ctx, ((size_t)nprefix + 2) * sizeof(uint32_t)));
+    dev_buf gaps;
+    const uint32_t max_gaps = nprefix / kGapInline + 2;
+    MR_TRY(gaps.ensure(ctx, (size_t)max_gaps * sizeof(gap_item) + 16));
+    uint32_t* ngaps = reinterpret_cast<uint32_t*>(gaps.as<gap_item>() + max_gaps);
+    MR_CUDA(ctx, cudaMemsetAsync(ngaps, 0, sizeof(uint32_t), st));
+    sa_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(keys, nsa, tail_bits, nprefix, idx->tails.as<uint32_t>(),
+                                                       idx->counts.as<uint32_t>(), gaps.as<gap_item>(), ngaps);
+    MR_LAUNCHED(ctx);
+    sa_fill_gaps_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(gaps.as<gap_item>(), ngaps, idx->counts.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    // keep the sorted positions: steal the buffer that holds them
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    std::swap(idx->sa.p, vres.p);
+    std::swap(idx->sa.cap, vres.cap);
+  }
+  timer.end();
+  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  timer.collect();
+
+  // tail-short suffixes: positions n-k+1 .. n-m, padded k-mers computed on the host from the 2-bit text
+  index_view& v = idx->view;
+  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.as<uint32_t>(); v.sa = idx->sa.as<uint32_t>();
+  v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
+  v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.tail_bits = tail_bits;
+  v.nshort = 0;
+  for(uint32_t j = 1; j <= k - psa_min; ++j) {
+    const uint64_t pos = n - k + j;
+    uint64_t key = 0;
+    for(uint32_t t = 0; t < k; ++t) {
+      const uint64_t p = pos + t;
+      const uint64_t c = p < n ? (text2bit[p >> 5] >> (2 * (p & 31))) & 3 : 0;
+      key = (key << 2) | c;
+    }
+    v.short_key[v.nshort++] = key;
+  }
+  *out = idx.release();
+  return MR_OK;
+}
+
+void mr_index_destroy(mr_index* idx) {
+  if(!idx) return;
+  cudaSetDevice(idx->ctx->device);
+  delete idx;
+}
+
+uint64_t mr_index_sa_size(const mr_index* idx) { return idx ? idx->nsa : 0; }
+
+static int export_widened(mr_index* idx, const uint32_t* d_in, uint64_t count, uint64_t* h_out) {
+  mr_context* ctx = idx->ctx;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  dev_buf tmp;
+  MR_TRY(tmp.ensure(ctx, count * sizeof(uint64_t)));
+  widen_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_in, count, tmp.as<uint64_t>());
+  MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaMemcpyAsync(h_out, tmp.p, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
+}
+
+int mr_index_export_sa(mr_index* idx, uint64_t* sa_out) {
+  if(!idx || !sa_out) return MR_EINVAL;
+  return export_widened(idx, idx->sa.as<uint32_t>(), idx->nsa, sa_out);
+}
+
+int mr_index_export_counts(mr_index* idx, uint64_t* counts_out) {
+  if(!idx || !counts_out) return MR_EINVAL;
+  return export_widened(idx, idx->counts.as<uint32_t>(), ((uint64_t)1 << (2 * idx->m)) + 1, counts_out);
+}
+
+int mr_lookup_batch_device(mr_index* idx, const uint64_t* d_mers, uint64_t q, uint64_t* d_index_out, uint64_t* d_nb_out) {
+  if(!idx) return MR_EINVAL;
+  mr_context* ctx = idx->ctx;
+  if(q == 0) return MR_OK;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, div_up(q, 256));
+  lookup_kernel<<<grid, 256, 0, ctx->stream>>>(idx->view, d_mers, q, d_index_out, d_nb_out);
+  MR_LAUNCHED(ctx);
+  return MR_OK;
+}
+
+int mr_lookup_batch(mr_index* idx, const uint64_t* mers, uint64_t q, uint64_t* index_out, uint64_t* nb_out) {
+  if(!idx || !mers || !index_out || !nb_out) return MR_EINVAL;
+  mr_context* ctx = idx->ctx;
+  if(q == 0) return MR_OK;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  dev_buf dm, di, dn;
+  MR_TRY(dm.ensure(ctx, q * sizeof(uint64_t)));
+  MR_TRY(di.ensure(ctx, q * sizeof(uint64_t)));
+  MR_TRY(dn.ensure(ctx, q * sizeof(uint64_t)));
+  MR_CUDA(ctx, cudaMemcpyAsync(dm.p, mers, q * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  MR_TRY(mr_lookup_batch_device(idx, dm.as<uint64_t>(), q, di.as<uint64_t>(), dn.as<uint64_t>()));
+  MR_CUDA(ctx, cudaMemcpyAsync(index_out, di.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MR_CUDA(ctx, cudaMemcpyAsync(nb_out, dn.p, q * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
+}
+
+} // extern "C"

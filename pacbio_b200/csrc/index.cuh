@@ -1,0 +1,82 @@
+// Device-resident super-read index: 2-bit text, suffix array, per-entry k-mer tails, prefix
+// counts and the tables that map a text position to (super-read, offset).
+//
+// Layout in HBM (n = text bases, m = psa-min, k = mer, nsa = n - m + 1):
+//   text   uint64[ceil(n/32)+2]  reference compact_dna layout (base i at bits 2(i%32)), zero padded
+//   sa     uint32[nsa]           positions ordered by (k-mer padded with A, position descending)
+//                                == the order of SA::sort_one_mer (mer_sa_imp.hpp:352-366)
+//   tails  uint32[nsa]           low 2(k-m) bits of each entry's padded k-mer: a lookup never
+//                                touches the text, one probe is one 4-byte read next to its
+//                                neighbours instead of the reference's SA read + text read
+//   counts uint32[4^m+1]         exclusive prefix of the m-mer histogram (mer_sa_imp.hpp:317-330)
+//   sr_start uint32[nseq+1], blk uint32[(n>>8)+2]: blk[b] = sequence containing base b*256
+#pragma once
+#include "common.cuh"
+
+constexpr int kBlkShift  = 8;
+constexpr int kMaxShort  = 16;    // k - m <= 16 (tails are 32 bit)
+
+struct index_view {
+  const uint32_t* __restrict__ counts;
+  const uint32_t* __restrict__ tails;
+  const uint32_t* __restrict__ sa;
+  const uint32_t* __restrict__ sr_start;
+  const uint32_t* __restrict__ blk;
+  uint64_t n;
+  uint32_t nsa, nseq, k, m, tail_bits, nshort;
+  uint64_t short_key[kMaxShort];   // padded k-mers of the tail-short suffixes (positions n-k+1 .. n-m)
+};
+
+struct mr_index {
+  mr_context* ctx = nullptr;
+  uint64_t n = 0;
+  uint32_t nsa = 0, nseq = 0, k = 0, m = 0, n_unitigs = 0;
+  bool     has_unitigs = false;
+  dev_buf  text, sa, tails, counts, sr_start, blk;
+  dev_buf  unitig_ids, unitig_off, unitig_len, sr_nunitigs;
+  index_view view;
+};
+
+// [index, nb) of SA entries whose text equals `mer` (mer_sa_imp.hpp:369-479 returns the same pair)
+__device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer, uint32_t& index, uint32_t& nb) {
+  const uint32_t pre = (uint32_t)(mer >> iv.tail_bits);
+  const uint32_t t   = (uint32_t)mer & (iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1));
+  const uint32_t c0 = __ldg(iv.counts + pre), c1 = __ldg(iv.counts + pre + 1);
+  index = 0; nb = 0;
+  if(c0 == c1) return;
+  uint32_t lo, hi;
+  if(c1 - c0 <= 32) {                       // small bucket: branch-free counting scan
+    uint32_t less = 0, leq = 0;
+    for(uint32_t i = c0; i < c1; ++i) {
+      const uint32_t v = __ldg(iv.tails + i);
+      less += v < t;
+      leq  += v <= t;
+    }
+    lo = c0 + less; hi = c0 + leq;
+  } else {
+    uint32_t a = c0, b = c1;
+    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) < t) a = mid + 1; else b = mid; }
+    lo = a; b = c1;
+    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) <= t) a = mid + 1; else b = mid; }
+    hi = a;
+  }
+  if(hi == lo) return;
+  // Suffixes shorter than k sort first inside their padded-equal range (larger position first)
+  // and never match (mer_sa_imp.hpp:399-406).  Only k-mers ending in A can collide with them.
+  if((mer & 3) == 0) {
+    for(uint32_t j = 0; j < iv.nshort; ++j) lo += iv.short_key[j] == mer;
+  }
+  nb = hi - lo;
+  index = nb ? lo : 0;
+}
+
+// SA entry x -> (super-read, 1-based offset); false when x + k crosses into the next sequence
+// (pos_iterator::operator++, superread_parser.hpp:110-134)
+__device__ __forceinline__ bool index_locate(const index_view& iv, uint32_t x, uint32_t& sr, uint32_t& off) {
+  uint32_t i = __ldg(iv.blk + (x >> kBlkShift));
+  while(__ldg(iv.sr_start + i + 1) <= x) ++i;
+  if((uint64_t)x + iv.k > __ldg(iv.sr_start + i + 1)) return false;
+  sr  = i;
+  off = x - __ldg(iv.sr_start + i) + 1;
+  return true;
+}

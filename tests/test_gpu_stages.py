@@ -1,0 +1,143 @@
+"""GPU parity tests, stage by stage, through the C ABI (ctypes) against the oracle port -- and
+against the compiled reference when oracle/_ref travelled to the box."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import gen_synth, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import pacbio_b200 as pb
+    c = pb.Context(0)
+    yield c
+    c.close()
+
+
+def _queries(k, n, seed, sr_text_codes):
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 4 ** k, size=n, dtype=np.uint64)
+    pos = rng.integers(0, len(sr_text_codes) - k, size=n // 2)
+    w = (4 ** np.arange(k - 1, -1, -1)).astype(np.uint64)
+    for i, p in enumerate(pos):
+        codes = sr_text_codes[p:p + k].astype(np.uint64)
+        if i & 1:
+            codes = 3 - codes[::-1]
+        q[i] = int((codes * w).sum())
+    return q
+
+
+CASES = [
+    dict(name="k15", genome=150000, coverage=3, read_len=4000, seed=31, repeat_frac=0.15, k=15, m=13, uk=41),
+    dict(name="k17", genome=120000, coverage=3, read_len=5000, seed=32, repeat_frac=0.0, k=17, m=13, uk=41, error=0.12),
+    dict(name="k19m10", genome=60000, coverage=4, read_len=3000, seed=33, repeat_frac=0.25, k=19, m=10, uk=31,
+         mean_unitig=200, error=0.10),
+    dict(name="k16", genome=80000, coverage=3, read_len=2500, seed=34, repeat_frac=0.1, k=16, m=12, uk=41),
+]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: c["name"])
+def case(request, tmpdir_session, ctx, port):
+    import pacbio_b200 as pb
+    c = dict(request.param)
+    gen = {k: c[k] for k in ("genome", "coverage", "read_len", "seed", "repeat_frac", "error", "mean_unitig") if k in c}
+    info = gen_synth(os.path.join(tmpdir_session, "gpu_" + c["name"]), unitig_k=c["uk"], **gen)
+    sr = pb.SuperReads(info["sr"])
+    ul = np.loadtxt(info["unitigs_len"], dtype=np.int64)[:, 1]
+    idx = ctx.index(sr, c["m"], c["k"], unitig_len=ul)
+    hp = port.index_create(info["sr"], c["m"], c["k"])
+    port.set_unitigs_lengths(hp, ul)
+    yield dict(cfg=c, info=info, sr=sr, ul=ul, idx=idx, hp=hp)
+    idx.close()
+    port.index_destroy(hp)
+
+
+def test_index_matches_oracle(case, port):
+    idx, hp, c = case["idx"], case["hp"], case["cfg"]
+    assert np.array_equal(idx.sa(), port.sa(hp))
+    assert np.array_equal(idx.counts(), port.counts(hp, c["m"]))
+
+
+def test_lookup_matches_oracle(case, port):
+    idx, hp, c, sr = case["idx"], case["hp"], case["cfg"], case["sr"]
+    _, seqs = read_fasta(case["info"]["sr"])
+    b = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    codes = ((b >> 1) ^ (b >> 2)) & 3
+    q = _queries(c["k"], 20000, 7, codes)
+    # k-mers that collide with the tail-short suffixes of the text (padded with A)
+    k, n = c["k"], len(codes)
+    extra = []
+    for j in range(1, k - c["m"] + 1):
+        v = 0
+        for t in range(k):
+            p = n - k + j + t
+            v = (v << 2) | (int(codes[p]) if p < n else 0)
+        extra.append(v)
+    q = np.concatenate([q, np.array(extra, dtype=np.uint64)])
+    gi, gn = idx.lookup(q)
+    oi, on = port.search(hp, q)
+    assert np.array_equal(gn, on)
+    assert np.array_equal(gi, oi)
+    assert int(gn.sum()) > 5000
+
+
+def _canon(cint, cdbl, info_off, kinfo, binfo):
+    rows = []
+    for j in range(len(cint)):
+        lo, hi = info_off[j], info_off[j + 1]
+        rows.append((tuple(int(x) for x in cint[j]), tuple(float(x).hex() for x in cdbl[j]),
+                     tuple(kinfo[lo:hi].tolist()), tuple(binfo[lo:hi].tolist())))
+    return rows
+
+
+@pytest.mark.parametrize("forward", [True, False])
+def test_align_stages_match_oracle(case, ctx, port, forward):
+    import pacbio_b200 as pb
+    c = case["cfg"]
+    reads = pb.Reads(case["info"]["reads"])
+    nreads = min(reads.nreads, 60)
+    sub = reads.slice(0, nreads)
+    # a read with an N run and a tiny read, to exercise the k-mer restart and the empty paths
+    names, seqs = read_fasta(case["info"]["reads"])
+    seqs = seqs[:nreads]
+    s0 = seqs[0]
+    seqs.append(s0[:700] + "NNNN" + s0[704:1500] + "n" + s0[1501:2400])
+    seqs.append("ACGT")
+    seqs.append("")
+    sub = pb.Reads(names=["r%d" % i for i in range(len(seqs))], seqs=seqs)
+    uk = c["uk"] if forward else 0
+    p = pb.default_params(unitigs_k=uk, run_graph=0, forward=int(forward))
+    ctx.keep_taps(True)
+    res = ctx.align(case["idx"], sub, p)
+    ctx.keep_taps(False)
+    ap = port.aligner_create(case["hp"], unitigs_k=uk, forward=forward)
+    total_coords = 0
+    for r, s in enumerate(seqs):
+        o = port.align_read(ap, s)
+        rows = res.tap_groups[res.tap_groups[:, 0] == r]
+        assert np.array_equal(rows[:, 1:], o["groups"]), "groups of read %d" % r
+        # offsets / lis of this read: contiguous slices in group order
+        first = int(np.flatnonzero(res.tap_groups[:, 0] == r)[0]) if len(rows) else 0
+        off0 = int(res.tap_groups[:first, 2:4].sum())
+        lis0 = int(res.tap_groups[:first, 4:6].sum())
+        noff, nlis = int(o["groups"][:, 1:3].sum()), int(o["groups"][:, 3:5].sum())
+        assert np.array_equal(res.tap_offsets[off0:off0 + noff], o["offsets"]), "hit lists of read %d" % r
+        assert np.array_equal(res.tap_lis[lis0:lis0 + nlis], o["lis"]), "chains of read %d" % r
+        rr = list(res.rows(r))
+        assert len(rr) == len(o["cint"]), "coords count of read %d" % r
+        total_coords += len(rr)
+        g_int = np.stack([res.rs[rr], res.re[rr], res.qs[rr], res.qe[rr], res.nb_mers[rr], res.pb_cons[rr],
+                          res.sr_cons[rr], res.pb_cover[rr], res.sr_cover[rr], np.full(len(rr), len(s)), res.ql[rr],
+                          res.rn[rr], res.sr[rr], res.use_bwd[rr]], axis=1).astype(np.int64) if rr else np.zeros((0, 14), np.int64)
+        g_dbl = np.stack([res.stretch[rr], res.offset[rr], res.avg_err[rr]], axis=1) if rr else np.zeros((0, 3))
+        g_off = np.concatenate([[0], np.cumsum(res.info_len[rr])]).astype(np.int64)
+        g_k = np.concatenate([res.info(i)[0] for i in rr]) if rr else np.zeros(0, np.int32)
+        g_b = np.concatenate([res.info(i)[1] for i in rr]) if rr else np.zeros(0, np.int32)
+        assert _canon(g_int, g_dbl, g_off, g_k, g_b) == _canon(o["cint"], o["cdbl"], o["info_off"], o["kinfo"], o["binfo"]), \
+            "coords of read %d" % r
+    assert total_coords > 20
+    port.aligner_destroy(ap)

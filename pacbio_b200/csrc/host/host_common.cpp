@@ -1,0 +1,498 @@
+#include "host_common.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <stdexcept>
+#include <thread>
+
+namespace mrh {
+
+// ================================================================================================
+// super-reads
+// ================================================================================================
+// "12F_7R_3F" -> (id << 1) | ori.  Mirrors super_read_name::parse (super_read_name.cc:74-90): every
+// '_'-separated piece must start with a number, the orientation is its last character ('R' or not);
+// a piece without digits invalidates the whole name (empty path).
+static bool parse_path(const std::string& name, std::vector<uint32_t>& out) {
+  out.clear();
+  if(name.empty()) return true;
+  size_t pos = 0;
+  while(true) {
+    const size_t us = name.find('_', pos);
+    const size_t end = us == std::string::npos ? name.size() : us;
+    size_t d = pos;
+    while(d < end && (name[d] == ' ' || name[d] == '\t')) ++d;     // std::stoul skips leading blanks
+    if(d < end && name[d] == '+') ++d;
+    uint64_t id = 0;
+    size_t nd = 0;
+    while(d < name.size() && name[d] >= '0' && name[d] <= '9') { id = id * 10 + (uint64_t)(name[d] - '0'); ++d; ++nd; }
+    if(nd == 0) { out.clear(); return false; }
+    const char ori = end > 0 ? name[end - 1] : 'F';
+    out.push_back((uint32_t)((id & 0x7fffffffu) << 1) | (ori == 'R' ? 1u : 0u));
+    if(us == std::string::npos) break;
+    pos = us + 1;
+  }
+  return true;
+}
+
+void super_reads::append_fasta(const std::string& path) {
+  std::ifstream is(path, std::ios::binary);
+  if(!is.good()) throw std::runtime_error("Can't open file " + path);
+  if(is.peek() != '>') throw std::runtime_error("Not in fasta format");
+  if(start.empty()) { start.push_back(0); unitig_off.push_back(0); }
+  std::string header, line;
+  std::vector<uint32_t> upath;
+  int c = is.peek();
+  while(c != EOF) {
+    std::getline(is, header);
+    const uint64_t old = n;
+    for(c = is.peek(); c != '>' && c != EOF; c = is.peek()) {
+      std::getline(is, line);
+      const uint64_t need = (n + line.size() + 31) / 32 + 1;
+      if(text2bit.size() < need) text2bit.resize(std::max<uint64_t>(need, text2bit.size() * 2), 0);
+      for(unsigned char x : line) {                                  // compact_dna.hpp:102-107 (SWAR mapping)
+        const uint64_t code = ((x >> 1) ^ (x >> 2)) & 3;
+        text2bit[n >> 5] |= code << (2 * (n & 31));
+        ++n;
+      }
+    }
+    if(n > old) {
+      name.push_back(header.substr(1));
+      parse_path(name.back(), upath);
+      unitig_ids.insert(unitig_ids.end(), upath.begin(), upath.end());
+      unitig_off.push_back(unitig_ids.size());
+      start.push_back(n);
+    }
+  }
+}
+
+std::string super_reads::row_name(uint32_t s, bool bwd) const {
+  const uint32_t u = path_len(s);
+  if(!bwd || u == 0) return name[s];
+  std::string r;
+  for(uint32_t t = 0; t < u; ++t) {
+    const uint32_t x = path_at(s, true, t);
+    if(t) r += '_';
+    r += std::to_string(x >> 1);
+    r += (x & 1) ? 'R' : 'F';
+  }
+  return r;
+}
+
+// ================================================================================================
+// k-unitigs
+// ================================================================================================
+void unitigs::load_lengths(const std::string& path) {
+  std::ifstream is(path);
+  if(!is.good()) throw std::runtime_error("Failed to open unitig lengths map file '" + path + "'");
+  std::string id;
+  unsigned int l;
+  while(is >> id >> l) len.push_back((int32_t)l);
+}
+
+void unitigs::load_sequences(const std::string& path) {
+  std::ifstream is(path, std::ios::binary);
+  if(!is.good()) throw std::runtime_error("Failed to open unitigs sequence file '" + path + "'");
+  std::string hdr, s;
+  while(std::getline(is, hdr)) {
+    if(!std::getline(is, s)) s.clear();
+    len.push_back((int32_t)s.size());
+    seq.push_back(s);
+  }
+}
+
+// ================================================================================================
+// long reads
+// ================================================================================================
+bool read_stream::open_next() {
+  if(f_) { fclose(f_); f_ = nullptr; }
+  if(next_path_ >= paths_.size()) return false;
+  const std::string& p = paths_[next_path_++];
+  f_ = fopen(p.c_str(), "rb");
+  if(!f_) throw std::runtime_error("Can't open file '" + p + "'");
+  pos_ = end_ = 0; eof_ = false;
+  return true;
+}
+
+bool read_stream::fill() {
+  if(eof_ || !f_) return false;
+  end_ = fread(buf_.data(), 1, buf_.size(), f_);
+  pos_ = 0;
+  if(end_ == 0) { eof_ = true; return false; }
+  return true;
+}
+
+// next line of the current file without its terminator; false at end of file
+bool read_stream::getline(std::string& line, bool append) {
+  if(!append) line.clear();
+  bool got = false;
+  while(true) {
+    if(pos_ == end_ && !fill()) return got;
+    got = true;
+    const char* b = buf_.data() + pos_;
+    const char* nl = (const char*)memchr(b, '\n', end_ - pos_);
+    if(nl) {
+      line.append(b, nl - b);
+      pos_ += (nl - b) + 1;
+      if(!line.empty() && line.back() == '\r') line.pop_back();
+      return true;
+    }
+    line.append(b, end_ - pos_);
+    pos_ = end_;
+  }
+}
+
+bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads) {
+  if(b.start.empty()) b.start.push_back(0);
+  std::string line;
+  bool any = false;
+  while(b.bases.size() - b.start[0] < max_bases && b.nreads() < max_reads) {
+    if(!have_pending_) {
+      // find the next header
+      bool found = false;
+      while(!found) {
+        if(!f_ && !open_next()) return any;
+        if(!getline(line, false)) { fclose(f_); f_ = nullptr; continue; }
+        if(line.empty()) continue;
+        if(line[0] == '>' || line[0] == '@') { pending_header_ = line.substr(1); pending_kind_ = line[0]; found = true; }
+        else throw std::runtime_error("Unsupported format");
+      }
+    }
+    have_pending_ = false;
+    const size_t ws = pending_header_.find_first_of(" \t\n\v\f\r");
+    b.name.push_back(pending_header_.substr(0, ws));
+    const uint64_t before = b.bases.size();
+    if(pending_kind_ == '>') {
+      while(true) {
+        if(!getline(line, false)) { fclose(f_); f_ = nullptr; break; }
+        if(!line.empty() && line[0] == '>') { pending_header_ = line.substr(1); pending_kind_ = '>'; have_pending_ = true; break; }
+        b.bases += line;
+      }
+    } else {
+      bool in_f = true;
+      while((in_f = getline(line, false))) {
+        if(!line.empty() && line[0] == '+') break;
+        b.bases += line;
+      }
+      uint64_t q = 0;
+      const uint64_t want = b.bases.size() - before;
+      while(in_f && q < want && (in_f = getline(line, false))) q += line.size();
+      if(!in_f) { fclose(f_); f_ = nullptr; }
+    }
+    b.start.push_back(b.bases.size());
+    any = true;
+  }
+  return any;
+}
+
+// ================================================================================================
+// mega-reads from the device's graph rows
+// ================================================================================================
+namespace {
+struct mega_read {
+  int    start_node, end_node, start_unitig, start_offset, end_offset, nb_unitigs;
+  double imp_s, imp_e, tiling_start, tiling_end, density;
+};
+struct span { double lo, up; };
+
+// joining interval set of [lo, up) pieces: boost::icl::interval_set<double> as used by tile_greedy
+struct joined_set {
+  std::vector<span> v;
+  bool overlaps_at_least(const span& x, double limit) const {
+    for(const span& y : v) {
+      const double lo = std::max(y.lo, x.lo), up = std::min(y.up, x.up);
+      if(lo < up && up - lo >= limit) return true;
+    }
+    return false;
+  }
+  void add(span x) {
+    if(!(x.lo < x.up)) return;
+    std::vector<span> nv;
+    bool placed = false;
+    for(const span& y : v) {
+      if(y.up < x.lo) nv.push_back(y);
+      else if(x.up < y.lo) { if(!placed) { nv.push_back(x); placed = true; } nv.push_back(y); }
+      else { x.lo = std::min(x.lo, y.lo); x.up = std::max(x.up, y.up); }
+    }
+    if(!placed) nv.push_back(x);
+    v.swap(nv);
+  }
+};
+} // namespace
+
+void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
+                       const super_reads& sr, const unitigs& u, const graph_options& o, std::string& out) {
+  const double K = o.k_len;
+  std::vector<mega_read> mrs;
+  std::vector<int> sort_tiling, tiled;
+  std::vector<uint32_t> path;
+  std::vector<double> weights;
+  char buf[256];
+  for(uint32_t r = r0; r < r1; ++r) {
+    const uint64_t b = v.read_coords[r];
+    const int n = (int)(v.read_coords[r + 1] - b);
+    if(n == 0) continue;
+    const double pb_size = (double)(batch.start[r + 1] - batch.start[r]);
+    auto row_unitig_id = [&](uint64_t row, uint32_t t) -> uint32_t {
+      const uint32_t s = v.sr[row];
+      return t < sr.path_len(s) ? (sr.path_at(s, v.use_bwd[row], t) >> 1) : 0x7fffffffu;
+    };
+
+    // mega_reads_per_comp (overlap_graph.cc:116-161): components in increasing root order
+    std::map<int, mega_read> comps;
+    for(int i = 0; i < n; ++i) {
+      const uint64_t row = b + i;
+      mega_read mr;
+      mr.start_node = v.lstart[row] == -1 ? i : v.lstart[row];
+      mr.end_node = i;
+      const uint64_t srow = b + mr.start_node;
+      mr.start_unitig = 0;
+      mr.nb_unitigs = v.lunitigs[row];
+      mr.imp_s = v.stretch[srow] + v.offset[srow];
+      { const double t = v.stretch[row] * (double)v.ql[row]; mr.imp_e = t + v.offset[row]; }
+      mr.tiling_start = v.rs[srow];
+      mr.tiling_end = v.re[row];
+      mr.start_offset = mr.end_offset = 0;
+      if(o.trim != 0) {                                   // trim_match (overlap_graph.cc:78-114)
+        const double node_imp_s = v.stretch[srow] + v.offset[srow];
+        if(node_imp_s < 1) {
+          const int32_t* ki = v.kmers_info + v.info_off[srow];
+          const int ilen = (int)v.info_len[srow];
+          int offset = 0, su = 0;
+          for(su = 0; su < ilen; su += 2) {
+            if(ki[su]) break;
+            offset += u.len[row_unitig_id(srow, su / 2)];
+          }
+          su /= 2;
+          mr.start_unitig = su;
+          mr.nb_unitigs -= su;
+          offset -= ((int)o.k_len - 1) * su;
+          mr.start_offset = offset;
+          { const double t = v.stretch[srow] * (double)(offset + 1); mr.imp_s = t + v.offset[srow]; }
+        }
+        const double node_imp_e = mr.imp_e;
+        if(node_imp_e > (double)v.ql[row]) {
+          const int32_t* ki = v.kmers_info + v.info_off[row];
+          const int ilen = (int)v.info_len[row];
+          int offset = 0, eu;
+          for(eu = ilen - 1; eu >= 0; eu -= 2) {
+            if(ki[eu]) break;
+            offset += u.len[row_unitig_id(row, eu / 2)];
+          }
+          eu /= 2;
+          const int removed = ilen / 2 - eu;
+          mr.nb_unitigs -= removed;
+          offset -= ((int)o.k_len - 1) * removed;
+          mr.end_offset = offset;
+          { const double t = v.stretch[row] * (double)((int64_t)v.ql[row] - offset); mr.imp_e = t + v.offset[row]; }
+        }
+      }
+      const double len = std::min(pb_size + 0.5, mr.tiling_end) - std::max(0.5, mr.tiling_start);
+      mr.density = (double)v.lpath[row] / len;
+      if(!v.end_node[row] || mr.density < o.density || (mr.tiling_end - mr.tiling_start) < o.min_length) continue;
+      const int root = v.component[row];
+      auto it = comps.find(root);
+      if(it == comps.end()) comps.insert(std::make_pair(root, mr));
+      else {
+        const int olpath = v.lpath[b + it->second.end_node];
+        if(v.lpath[row] > olpath || (v.lpath[row] == olpath && mr.density > it->second.density)) it->second = mr;
+      }
+    }
+    if(comps.empty()) continue;
+    mrs.clear(); sort_tiling.clear(); tiled.clear();
+    for(const auto& c : comps) { sort_tiling.push_back((int)mrs.size()); mrs.push_back(c.second); }
+    auto lpath_of = [&](int m) { return v.lpath[b + mrs[m].end_node]; };
+    auto by_pos = [&](int i, int j) {
+      return mrs[i].imp_s < mrs[j].imp_s || (mrs[i].imp_s == mrs[j].imp_s && mrs[i].imp_e < mrs[j].imp_e);
+    };
+    auto greedy = [&]() {                                  // tile_greedy (overlap_graph.cc:165-197)
+      joined_set covered;
+      std::vector<span> placed;
+      for(const int m : sort_tiling) {
+        const span pos = { mrs[m].tiling_start, mrs[m].tiling_end };
+        const double plen = pos.lo < pos.up ? pos.up - pos.lo : 0.0;
+        const double max_overlap = std::max(K * o.overlap_play, plen * (o.overlap_play - 0.9));
+        if(covered.overlaps_at_least(pos, max_overlap)) continue;
+        bool contained = false;
+        for(const span& p : placed)
+          if(!(pos.lo < pos.up) || (p.lo <= pos.lo && pos.up <= p.up)) { contained = true; break; }
+        if(contained) continue;
+        covered.add(pos);
+        placed.push_back(pos);
+        tiled.push_back(m);
+      }
+    };
+    // the std::sort calls below are the reference's own (same comparator, same input order), so
+    // even their unspecified order on ties is reproduced
+    switch(o.tiling) {
+    case 1:
+      std::sort(sort_tiling.begin(), sort_tiling.end(), [&](int i, int j) { return lpath_of(j) < lpath_of(i); });
+      greedy();
+      std::sort(tiled.begin(), tiled.end(), by_pos);
+      break;
+    case 3:
+      weights.assign(mrs.size(), 0.0);
+      for(const int i : sort_tiling) {
+        const double d2 = mrs[i].density * mrs[i].density;
+        weights[i] = d2 * (double)(v.re[b + mrs[i].end_node] - v.rs[b + mrs[i].start_node] + 1);
+      }
+      std::sort(sort_tiling.begin(), sort_tiling.end(), [&](int i, int j) { return weights[j] < weights[i]; });
+      greedy();
+      std::sort(tiled.begin(), tiled.end(), by_pos);
+      break;
+    case 2: {                                              // tile_maximal (overlap_graph.cc:212-252)
+      std::sort(sort_tiling.begin(), sort_tiling.end(), [&](int i, int j) { return mrs[i].tiling_end < mrs[j].tiling_end; });
+      struct tinfo { int score; double pos; int node, previous, length; };
+      std::vector<tinfo> info;
+      auto it = sort_tiling.begin();
+      info.push_back({ lpath_of(*it), mrs[*it].tiling_end, *it, -1, 1 });
+      for(++it; it != sort_tiling.end(); ++it) {
+        const double lstart = mrs[*it].tiling_start;
+        const double key = std::min(lstart + K * o.overlap_play, mrs[*it].tiling_end);
+        int i = (int)(std::upper_bound(info.begin(), info.end(), key, [](double x, const tinfo& y) { return x < y.pos; }) - info.begin()) - 1;
+        while(i >= 0 && mrs[info[i].node].tiling_start >= lstart) i = info[i].previous;
+        const int nscore = (i >= 0 ? info[i].score : 0) + lpath_of(*it);
+        if(nscore > info.back().score) info.push_back({ nscore, mrs[*it].tiling_end, *it, i, (i >= 0 ? info[i].length : 0) + 1 });
+      }
+      tiled.resize(info.back().length);
+      int ptr = (int)info.size() - 1;
+      for(auto rit = tiled.rbegin(); rit != tiled.rend(); ++rit) { *rit = info[ptr].node; ptr = info[ptr].previous; }
+      std::sort(tiled.begin(), tiled.end(), by_pos);
+      break;
+    }
+    default: break;
+    }
+
+    // print_mega_reads (overlap_graph.hpp:253-262, overlap_graph.cc:254-299)
+    out += '>'; out += batch.name[r]; out += '\n';
+    const std::vector<int>& final_order = tiled.empty() ? sort_tiling : tiled;
+    for(const int cmr : final_order) {
+      const mega_read& mr = mrs[cmr];
+      const uint64_t erow = b + mr.end_node, srow = b + mr.start_node;
+      path.assign((size_t)std::max(0, v.lunitigs[erow]), 0u);
+      auto prepend = [&](size_t offset, uint64_t row, size_t first, size_t last) -> size_t {
+        const uint32_t s = v.sr[row];
+        const size_t sz = sr.path_len(s);
+        if(first > last || first >= sz) return offset;
+        const size_t to_copy = std::min(last, sz - 1) - first + 1;
+        if(to_copy > offset) return offset;
+        for(size_t t = 0; t < to_copy; ++t) path[offset - to_copy + t] = sr.path_at(s, v.use_bwd[row], (uint32_t)(first + t));
+        return offset - to_copy;
+      };
+      size_t offset = prepend(path.size(), erow, 0, (size_t)sr.path_len(v.sr[erow]) - 1);
+      int node_j = mr.end_node, node_i = v.lprev[erow];
+      while(node_i >= 0) {
+        const uint64_t irow = b + node_i, jrow = b + node_j;
+        const size_t overlap = (size_t)v.lunitigs[irow] + sr.path_len(v.sr[jrow]) - (size_t)v.lunitigs[jrow];
+        const size_t end = (size_t)sr.path_len(v.sr[irow]) - 1 - overlap;
+        offset = prepend(offset, irow, 0, end);
+        node_j = node_i;
+        node_i = v.lprev[irow];
+      }
+      auto path_id = [&](int i) -> uint32_t { return (size_t)i < path.size() ? (path[i] >> 1) : 0x7fffffffu; };
+      int sr_len = 0;
+      for(int i = mr.start_unitig; i < mr.start_unitig + mr.nb_unitigs; ++i) sr_len += u.len[path_id(i)];
+      sr_len -= (mr.nb_unitigs - 1) * ((int)o.k_len - 1);
+      const uint64_t qe_out = (uint64_t)(int64_t)(sr_len + mr.end_offset) - ((uint64_t)v.ql[erow] - (uint64_t)(int64_t)v.qe[erow]);
+      snprintf(buf, sizeof(buf), "%.2f %.2f %d %d %d %llu %d %.4f ", mr.imp_s, mr.imp_e, v.rs[srow], v.re[erow],
+               v.qs[srow] - mr.start_offset, (unsigned long long)qe_out, v.lpath[erow], mr.density);
+      out += buf;
+      for(size_t t = 0; t < path.size(); ++t) {
+        if(t) out += '_';
+        snprintf(buf, sizeof(buf), "%u%c", path[t] >> 1, (path[t] & 1) ? 'R' : 'F');
+        out += buf;
+      }
+      snprintf(buf, sizeof(buf), " %d", sr_len);
+      out += buf;
+      if(!u.seq.empty()) {                                // super_read_name::print_sequence (super_read_name.cc:123-132)
+        out += ' ';
+        const size_t pb = std::min((size_t)mr.start_unitig, path.size());
+        const size_t pe = std::min((size_t)(mr.start_unitig + mr.nb_unitigs), path.size());
+        for(size_t i = pb; i < pe; ++i) {
+          const std::string& s = u.seq.at(path[i] >> 1);
+          const size_t skip = i == pb ? 0 : (size_t)o.k_len - 1;
+          if(skip >= s.size()) continue;
+          if(path[i] & 1) {
+            const size_t old = out.size();
+            out.resize(old + s.size() - skip);
+            char* w = &out[old];
+            for(size_t t = skip; t < s.size(); ++t) {
+              char ch;
+              switch(s[s.size() - 1 - t]) {
+              case 'a': case 'A': ch = 'T'; break;
+              case 'c': case 'C': ch = 'G'; break;
+              case 'g': case 'G': ch = 'C'; break;
+              case 't': case 'T': ch = 'A'; break;
+              default: ch = 'N';
+              }
+              *w++ = ch;
+            }
+          } else {
+            out.append(s, skip, std::string::npos);
+          }
+        }
+      }
+      out += '\n';
+    }
+  }
+}
+
+void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
+                          const graph_options& o, unsigned threads, std::string& out) {
+  const uint32_t nreads = v.nreads;
+  threads = std::max(1u, std::min(threads, nreads / 64 + 1));
+  if(threads == 1) { format_mega_reads(v, batch, 0, nreads, sr, u, o, out); return; }
+  std::vector<std::string> parts(threads);
+  std::vector<std::thread> th;
+  // split by coords rows so that the work is balanced
+  std::vector<uint32_t> cut(threads + 1, nreads);
+  cut[0] = 0;
+  for(unsigned t = 1; t < threads; ++t) {
+    const uint64_t want = v.ncoords * t / threads;
+    cut[t] = (uint32_t)(std::lower_bound(v.read_coords, v.read_coords + nreads + 1, want) - v.read_coords);
+    if(cut[t] > nreads) cut[t] = nreads;
+    if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  }
+  for(unsigned t = 0; t < threads; ++t)
+    th.emplace_back([&, t]() { format_mega_reads(v, batch, cut[t], cut[t + 1], sr, u, o, parts[t]); });
+  for(auto& x : th) x.join();
+  size_t total = out.size();
+  for(const auto& p : parts) total += p.size();
+  out.reserve(total);
+  for(const auto& p : parts) out += p;
+}
+
+// default ostream formatting of a double: "%g" with 6 significant digits (jf_aligner.cc:58)
+void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
+                   bool compact, bool zero_skip, std::string& out) {
+  char buf[512];
+  for(uint32_t r = r0; r < r1; ++r) {
+    const uint64_t b = v.read_coords[r], e = v.read_coords[r + 1];
+    if(b == e && zero_skip) continue;
+    const uint64_t pb_size = batch.start[r + 1] - batch.start[r];
+    if(compact) {
+      snprintf(buf, sizeof(buf), ">%llu ", (unsigned long long)(e - b));
+      out += buf; out += batch.name[r]; out += '\n';
+    }
+    for(uint64_t row = b; row < e; ++row) {
+      if(!compact) { out += batch.name[r]; out += ' '; }
+      snprintf(buf, sizeof(buf), "%d %d %d %d %d %u %u %u %u %llu %u %g %g %g ", v.rs[row], v.re[row], v.qs[row], v.qe[row],
+               v.nb_mers[row], v.pb_cons[row], v.sr_cons[row], v.pb_cover[row], v.sr_cover[row],
+               (unsigned long long)pb_size, v.ql[row], v.stretch[row], v.offset[row], v.avg_err[row]);
+      out += buf;
+      out += sr.row_name(v.sr[row], v.use_bwd[row]);
+      const int32_t* ki = v.kmers_info + v.info_off[row];
+      const int32_t* bi = v.bases_info + v.info_off[row];
+      for(uint32_t t = 0; t < v.info_len[row]; ++t) {
+        snprintf(buf, sizeof(buf), " %d:%d", ki[t], bi[t]);
+        out += buf;
+      }
+      out += '\n';
+    }
+  }
+}
+
+} // namespace mrh

@@ -1,0 +1,118 @@
+#include "pipeline.hpp"
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace mrh {
+
+std::vector<int> choose_devices() {
+  std::vector<int> d;
+  if(const char* e = getenv("MR_DEVICES")) {
+    const char* p = e;
+    while(*p) {
+      char* end;
+      const long v = strtol(p, &end, 10);
+      if(end == p) break;
+      d.push_back((int)v);
+      p = *end ? end + 1 : end;
+    }
+  } else if(const char* g = getenv("MR_GPUS")) {
+    for(int i = 0; i < atoi(g); ++i) d.push_back(i);
+  }
+  if(d.empty()) d.push_back(0);
+  return d;
+}
+
+void build_indexes(device_set& ds, const std::vector<int>& devices, const super_reads& sr, const unitigs& u,
+                   uint32_t psa_min, uint32_t mer) {
+  ds.ctx.assign(devices.size(), nullptr);
+  ds.idx.assign(devices.size(), nullptr);
+  std::vector<std::string> errors(devices.size());
+  std::vector<std::thread> th;
+  for(size_t i = 0; i < devices.size(); ++i) {
+    th.emplace_back([&, i]() {
+      int rc = mr_context_create(devices[i], &ds.ctx[i]);
+      if(rc != MR_OK) { errors[i] = std::string("mr_context_create: ") + mr_last_error(nullptr); return; }
+      rc = mr_index_create(ds.ctx[i], sr.text2bit.data(), sr.n, sr.start.data(), sr.nseq(),
+                           u.len.empty() ? nullptr : sr.unitig_ids.data(), u.len.empty() ? nullptr : sr.unitig_off.data(),
+                           u.len.empty() ? nullptr : u.len.data(), (uint32_t)u.len.size(), psa_min, mer, &ds.idx[i]);
+      if(rc != MR_OK) errors[i] = std::string("mr_index_create: ") + mr_last_error(ds.ctx[i]);
+    });
+  }
+  for(auto& t : th) t.join();
+  for(const auto& e : errors) if(!e.empty()) throw std::runtime_error(e);
+}
+
+namespace {
+struct job {
+  std::unique_ptr<read_batch> batch;
+  mr_result* result = nullptr;
+};
+}
+
+uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,
+                      const format_fn& format, FILE* out) {
+  uint64_t batch_bases = 32ULL << 20;
+  if(const char* e = getenv("MR_BATCH_BASES")) batch_bases = strtoull(e, nullptr, 0);
+  const uint32_t batch_reads = 1u << 20;
+  bounded_queue<job> to_align(2 * ds.ctx.size()), to_format(2 * ds.ctx.size());
+  std::atomic<uint64_t> total_bases(0);
+  std::string error;
+  std::mutex error_mutex;
+  auto fail = [&](const std::string& msg) { std::lock_guard<std::mutex> l(error_mutex); if(error.empty()) error = msg; };
+
+  std::thread reader([&]() {
+    try {
+      read_stream rs(read_paths);
+      while(true) {
+        job j;
+        j.batch.reset(new read_batch);
+        j.batch->clear();
+        if(!rs.next_batch(*j.batch, batch_bases, batch_reads)) break;
+        total_bases += j.batch->bases.size();
+        to_align.push(std::move(j));
+      }
+    } catch(std::exception& e) { fail(e.what()); }
+    to_align.close();
+  });
+
+  std::vector<std::thread> aligners;
+  std::atomic<int> live((int)ds.ctx.size());
+  for(size_t g = 0; g < ds.ctx.size(); ++g) {
+    aligners.emplace_back([&, g]() {
+      job j;
+      while(to_align.pop(j)) {
+        if(!error.empty()) continue;
+        const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, j.batch->bases.data(), j.batch->start.data(),
+                                      j.batch->nreads(), &j.result);
+        if(rc != MR_OK) { fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g])); continue; }
+        to_format.push(std::move(j));
+      }
+      if(--live == 0) to_format.close();
+    });
+  }
+
+  std::thread formatter([&]() {
+    job j;
+    std::string text;
+    while(to_format.pop(j)) {
+      mr_result_view v;
+      mr_result_get(j.result, &v);
+      text.clear();
+      try { format(v, *j.batch, text); } catch(std::exception& e) { fail(e.what()); }
+      if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
+      mr_result_free(j.result);
+    }
+  });
+
+  reader.join();
+  for(auto& t : aligners) t.join();
+  formatter.join();
+  fflush(out);
+  if(!error.empty()) throw std::runtime_error(error);
+  return total_bases;
+}
+
+} // namespace mrh

@@ -1,0 +1,66 @@
+// Batch pipeline shared by the two tools: a reader thread cuts the long-read stream into batches,
+// one aligner thread per GPU context pushes them through the C ABI, a formatter stage turns each
+// result into text (fanned out over -t host threads) and writes it under a lock.  Reads are
+// partitioned across GPUs batch by batch with the index replicated per GPU; there is no
+// collective on the path, only this host-side gather.
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+#include "host_common.hpp"
+
+namespace mrh {
+
+template<typename T>
+class bounded_queue {
+  std::deque<T> q_;
+  std::mutex m_;
+  std::condition_variable cv_push_, cv_pop_;
+  size_t cap_;
+  bool closed_ = false;
+public:
+  explicit bounded_queue(size_t cap) : cap_(cap) { }
+  void push(T&& x) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_push_.wait(l, [&] { return q_.size() < cap_; });
+    q_.push_back(std::move(x));
+    cv_pop_.notify_one();
+  }
+  bool pop(T& x) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_pop_.wait(l, [&] { return !q_.empty() || closed_; });
+    if(q_.empty()) return false;
+    x = std::move(q_.front());
+    q_.pop_front();
+    cv_push_.notify_one();
+    return true;
+  }
+  void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_pop_.notify_all(); }
+};
+
+struct device_set {
+  std::vector<mr_context*> ctx;
+  std::vector<mr_index*>   idx;
+  ~device_set() {
+    for(auto i : idx) mr_index_destroy(i);
+    for(auto c : ctx) mr_context_destroy(c);
+  }
+};
+
+// devices from MR_DEVICES ("0,1,2"), MR_GPUS (count) or just device 0
+std::vector<int> choose_devices();
+
+// creates one context + index per device (index build runs concurrently on all of them)
+void build_indexes(device_set& ds, const std::vector<int>& devices, const super_reads& sr, const unitigs& u,
+                   uint32_t psa_min, uint32_t mer);
+
+typedef std::function<void(const mr_result_view&, const read_batch&, std::string&)> format_fn;
+
+// runs the whole stream; returns the number of read bases processed
+uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,
+                      const format_fn& format, FILE* out);
+
+} // namespace mrh

@@ -1,0 +1,113 @@
+"""End-to-end GPU parity: the drop-in binaries (pacbio_b200/bin/{create_mega_reads,jf_aligner}),
+which reach the device only through the C ABI, against
+  * the reference's own CLI goldens (tests/golden/aligner_output),
+  * fixtures produced by the reference itself (tests/golden/synth_*), and
+  * the oracle port (and the compiled reference when present) on larger seeded inputs."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from oracle_lib import REF_CMR, gen_synth, have_ref, records
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CMR = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
+JFA = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return r
+
+
+@pytest.mark.parametrize("forward", [False, True])
+def test_reference_cli_goldens(tmp_path, forward):
+    d = os.path.join(GOLD, "aligner_output")
+    out = str(tmp_path / "coords")
+    cmd = [JFA, "-s", "10k", "-m", "17", "-r", os.path.join(d, "test_super_reads.fa"), "-p",
+           os.path.join(d, "test_pacbio.fa"), "--stretch-cap", "200", "--coords", out]
+    if forward:
+        cmd += ["-l", os.path.join(d, "test_unitigs_lengths"), "-k", "65", "-f"]
+    run(cmd)
+    got = sorted(tuple(l.split()) for l in open(out).read().splitlines()[1:] if not l.startswith(">"))
+    want = []
+    for line in open(os.path.join(d, "coords_forward_expected" if forward else "coords_normal_expected")).read().splitlines()[1:]:
+        f = line.split()
+        want.append(tuple(f[:14]) + tuple(f[15:]))     # golden is the old non-compact layout (Rname column)
+    assert got == sorted(want)
+
+
+@pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
+def test_reference_generated_fixtures(tmpdir_session, tmp_path, name):
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    cfg = meta["config"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    for key, h in meta["inputs"].items():
+        assert sha(open(info[key], "rb").read()) == h
+    common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+              "-r", info["sr"], "-p", info["reads"]]
+    out = str(tmp_path / "cmr.txt")
+    run([CMR] + common + ["-l", info["unitigs_len"], "-t", "4", "-B", "17", "--max-count", "5000", "-d", "0.029", "-o", out])
+    assert records(out) == records(os.path.join(GOLD, name + ".cmr.txt"))
+    out_u = str(tmp_path / "cmr_u.txt")
+    run([CMR] + common + ["-u", info["unitigs"], "-t", "2", "-o", out_u])
+    assert sha(open(out_u, "rb").read()) == meta["cmr_with_sequences_sha256_t1"]     # byte-identical file
+    out_c = str(tmp_path / "coords.txt")
+    run([JFA] + common + ["-l", info["unitigs_len"], "-H", "--coords", out_c])
+    assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
+
+
+@pytest.mark.parametrize("tiling,trim,bases", [("greedy", "none", False), ("maximal", "match", False),
+                                               ("weighted", "none", True), ("none", "match", False)])
+def test_larger_input_against_oracle(tmpdir_session, tmp_path, port, tiling, trim, bases):
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_big"), 1500000, coverage=4, read_len=8000, seed=77,
+                     repeat_frac=0.15, threads=4)
+    out = str(tmp_path / "gpu.txt")
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-t", "4", "-T", tiling, "--trim", trim,
+           "-r", info["sr"], "-p", info["reads"], "-o", out]
+    if bases:
+        cmd.append("-b")
+    env = dict(os.environ, MR_BATCH_BASES="2000000")          # several batches
+    run(cmd, env=env)
+    want = str(tmp_path / "oracle.txt")
+    if have_ref():
+        run([REF_CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-t", "8", "-T", tiling, "--trim", trim,
+             "-r", info["sr"], "-p", info["reads"], "-o", want] + (["-b"] if bases else []))
+    else:
+        port.run(0, info["sr"], info["reads"], info["unitigs"], want, 15, 41, threads=8, bases=bases,
+                 tiling=["none", "greedy", "maximal", "weighted"].index(tiling), trim=1 if trim == "match" else 0)
+    a, b = records(out), records(want)
+    assert len(b) > 500
+    diff = [k for k in set(a) | set(b) if a.get(k) != b.get(k)]
+    assert not diff, "%d of %d records differ, e.g. %s" % (len(diff), len(b), diff[:3])
+
+
+def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_fq"), 100000, coverage=3, read_len=3000, seed=5)
+    from oracle_lib import read_fasta
+    names, seqs = read_fasta(info["reads"])
+    half = len(names) // 2
+    fa, fq = str(tmp_path / "a.fa"), str(tmp_path / "b.fq")
+    with open(fa, "w") as f:
+        for n, s in zip(names[:half], seqs[:half]):
+            f.write(">%s some comment\n" % n)
+            for i in range(0, len(s), 61):
+                f.write(s[i:i + 61] + "\n")
+    with open(fq, "w") as f:
+        for n, s in zip(names[half:], seqs[half:]):
+            f.write("@%s\n%s\n+\n%s\n" % (n, s, "I" * len(s)))
+    out = str(tmp_path / "gpu.txt")
+    run([CMR, "-s", "1M", "-m", "15", "-k", "41", "-l", info["unitigs_len"], "-r", info["sr"], "-p", fa, "-p", fq, "-o", out])
+    want = str(tmp_path / "port.txt")
+    port.run(0, info["sr"], info["reads"], info["unitigs_len"], want, 15, 41, unitigs_is_fasta=False)
+    assert records(out) == records(want)

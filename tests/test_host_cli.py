@@ -1,0 +1,98 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the tools reject bad command lines like the reference's yaggo parsers (message + exit 1),
+and the product fails loudly -- no CPU fallback -- when there is no CUDA device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "pacbio_b200", "libmegareads_b200.so")
+CMR = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
+JFA = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
+GOLD = os.path.join(ROOT, "tests", "golden", "aligner_output")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not (os.path.exists(LIB) and os.path.exists(CMR) and os.path.exists(JFA)):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pacbio_b200", "csrc"), "all"], stdout=subprocess.DEVNULL)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mega_reads_b200.h")).read()
+    declared = set(re.findall(r"\b(mr_[a-z_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(LIB)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_a_device():
+    import pacbio_b200 as pb
+    with pytest.raises(pb.MrError, match="no CUDA device"):
+        pb.Context(0)
+    r = subprocess.run([CMR, "-s", "10k", "-m", "17", "-k", "65", "-l", os.path.join(GOLD, "test_unitigs_lengths"),
+                        "-r", os.path.join(GOLD, "test_super_reads.fa"), "-p", os.path.join(GOLD, "test_pacbio.fa")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1
+    assert b"no CUDA device" in r.stderr and r.stdout == b""
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-m", "17", "-k", "65"], b"[-s, --size=uint64] required switch"),
+    (["-s", "10k", "-k", "65"], b"[-m, --mer=uint32] required switch"),
+    (["-s", "10k", "-m", "17"], b"[-k, --k-mer=uint32] required switch"),
+    (["-s", "10k", "-m", "17", "-k", "65", "-l", "a", "-u", "b"], b"mutually exclusive"),
+    (["-s", "10x", "-m", "17", "-k", "65"], b"Invalid uint64"),
+    (["-s", "10k", "-m", "17", "-k", "65", "-T", "bogus"], b"Invalid enum"),
+    (["-s", "10k", "-m", "17", "-k", "65", "extra"], b"Requires exactly 0 argument"),
+])
+def test_create_mega_reads_rejects_bad_command_lines(args, msg):
+    r = subprocess.run([CMR] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1
+    assert msg in r.stderr
+
+
+def test_jf_aligner_needs_an_output():
+    r = subprocess.run([JFA, "-s", "10k", "-m", "17"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"No output file given" in r.stderr
+
+
+def test_missing_input_file_is_an_error():
+    r = subprocess.run([CMR, "-s", "10k", "-m", "17", "-k", "65", "-l", "/nonexistent/lengths", "-r", "x", "-p", "y"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"Failed to open unitig lengths" in r.stderr
+
+
+def test_help_exits_zero():
+    for tool in (CMR, JFA):
+        r = subprocess.run([tool, "--help"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0 and b"Usage" in r.stdout
+
+
+def test_host_parsers_match_oracle_inputs(tmp_path):
+    """numpy packer used by tests/bench == the layout the reference packs (compact_dna.hpp:109-136)."""
+    import numpy as np
+    import pacbio_b200.api as api
+    sr = api.SuperReads(os.path.join(GOLD, "test_super_reads.fa"))
+    assert sr.names == ["1R_3F", "5F_4R_2F", "7R_2F"]
+    assert sr.n == 9468 and sr.starts.tolist() == [0, 3668, 6668, 9468]
+    assert sr.paths[1] == [(5 << 1), (4 << 1) | 1, (2 << 1)]
+    assert sr.row_name(1, True) == "2R_4F_5R"
+    # base i lives at bits 2*(i%32) of word i//32
+    seq = "".join(l.strip() for l in open(os.path.join(GOLD, "test_super_reads.fa")) if not l.startswith(">"))
+    for i in (0, 1, 31, 32, 33, 5000, 9467):
+        assert (int(sr.text2bit[i // 32]) >> (2 * (i % 32))) & 3 == "ACGT".index(seq[i])
+    assert api.parse_sr_name("12F_7R") == [24, 15] and api.parse_sr_name("xF_7R") == []

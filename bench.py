@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the create_mega_reads hot path (BASELINE.json metric: PacBio bases aligned/s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic yeast-size genome (12 Mbp),
+super-reads k-unitig K=41, 50x simulated 10 kbp PacBio reads at 12 % error, production flags
+(-m 15 --psa-min 13 --stretch-cap 10000 -B 17 -d 0.029 --max-count 5000, -u unitigs).  One step ==
+one pass of the whole read set through the hot path, as a sequence of 32-Mbase batches.
+
+  value : device-timed (CUDA events on the library's stream), read batches already resident in HBM,
+          every kernel of mr_align_batch_device plus its result download
+  e2e   : the same pass through the public host path (mr_align_batch from page-locked host memory:
+          H2D + kernels + D2H, then mega-read tiling/printing on the host threads), wall clock
+  N > 1 : one process per GPU (torchrun), index replicated, every rank aligns its own read set of
+          the same size (weak scaling), no collective on the data path; barrier + max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(genome=12_000_000, coverage=50.0, read_len=10000, error=0.12, sr_cov=3.0, repeat_frac=0.0,
+                unitig_k=41, seed=43, mer=15, psa_min=13)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome", type=int, default=WORKLOAD["genome"])
+    ap.add_argument("--coverage", type=float, default=WORKLOAD["coverage"])
+    ap.add_argument("--host-threads", type=int, default=0)
+    ap.add_argument("--batch-bases", type=int, default=32 << 20)
+    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def data_files(args):
+    """Rank 0 generates the synthetic inputs once; everybody else waits for the done marker."""
+    w = dict(WORKLOAD, genome=args.genome, coverage=args.coverage)
+    tag = "g%d_c%g_s%d" % (w["genome"], w["coverage"], w["seed"])
+    d = os.path.join(os.environ.get("MR_BENCH_DIR", "/tmp/pacbio_b200_bench"), tag)
+    prefix = os.path.join(d, "synth")
+    done = prefix + ".done"
+    rank = int(os.environ.get("RANK", "0"))
+    if rank == 0 and not os.path.exists(done):
+        os.makedirs(d, exist_ok=True)
+        gen = os.path.join(ROOT, "pacbio_b200", "tools", "gen_synth")
+        if not os.path.exists(gen):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", gen + ".cc", "-o", gen])
+        out = subprocess.check_output([gen, "--genome", str(w["genome"]), "--coverage", str(w["coverage"]), "--read-len",
+                                       str(w["read_len"]), "--error", str(w["error"]), "--seed", str(w["seed"]),
+                                       "--sr-cov", str(w["sr_cov"]), "--repeat-frac", str(w["repeat_frac"]),
+                                       "--unitig-k", str(w["unitig_k"]), "--threads", str(min(16, os.cpu_count() or 1)),
+                                       "--prefix", prefix])
+        open(done, "w").write(out.decode())
+    while not os.path.exists(done):
+        time.sleep(0.5)
+    info = json.loads(open(done).read())
+    return w, dict(sr=prefix + ".superreads.fa", reads=prefix + ".reads.fa", unitigs=prefix + ".unitigs.fa",
+                   unitigs_len=prefix + ".unitigs_len.txt", info=info, prefix=prefix)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def dist_setup(n):
+    if n <= 1 or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+    return dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def max_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own create_mega_reads (oracle/_ref) or, if absent, the oracle port
+# --------------------------------------------------------------------------------------------------
+def cpu_run(w, files, nreads_sample, threads):
+    """Aligns the first nreads_sample reads on the host cores; returns (bases/s of the alignment phase, meta)."""
+    sample = files["prefix"] + ".sample%d.fa" % nreads_sample
+    nb = 0
+    with open(files["reads"]) as f, open(sample, "w") as g:
+        for i, line in enumerate(f):
+            if i >= 2 * nreads_sample:
+                break
+            g.write(line)
+            if i & 1:
+                nb += len(line) - 1
+    ref = os.path.join(ROOT, "oracle", "_ref", "create_mega_reads")
+    out = files["prefix"] + ".cpu.out"
+    if os.path.exists(ref):
+        cmd = [ref, "-s", "1M", "-m", str(w["mer"]), "--psa-min", str(w["psa_min"]), "--stretch-cap", "10000", "-k",
+               str(w["unitig_k"]), "-u", files["unitigs"], "-t", str(threads), "-B", "17", "--max-count", "5000", "-d",
+               "0.029", "-r", files["sr"], "-p", sample, "-o", out]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("reference run failed: " + r.stderr.decode()[-500:])
+        align_s = None
+        for line in r.stderr.decode().splitlines():        # -DSHOW_TIMING phase lines (global_timer.hpp:7-47)
+            if line.startswith("Starting create mega reads ..."):
+                align_s = float(line.split("...")[1])
+        if align_s is None:
+            align_s = wall
+        kind = "reference"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import Port
+        nbp, ti, align_s = Port().run(0, files["sr"], sample, files["unitigs"], out, w["mer"], w["unitig_k"], threads=threads)
+        kind = "port"
+    return nb / align_s, dict(kind=kind, cores=threads, bases=nb, seconds=align_s,
+                              sample="first %d reads (%d bases) of the workload, alignment phase only" % (nreads_sample, nb))
+
+
+def reference_arm(args, w, files):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nreads = args.cpu_sample_reads or 1500
+    vals = []
+    meta = None
+    for _ in range(args.warmup):
+        cpu_run(w, files, max(100, nreads // 10), threads)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, meta = cpu_run(w, files, nreads, threads)
+        vals.append(v)
+        t_all += meta["seconds"]
+    value = meta["bases"] * args.steps / t_all
+    line = {"impl": "reference", "metric": "pacbio_bases_aligned_per_s", "value": value, "unit": "bases/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+            "config": config_dict(args, w), "cpu_baseline": {"value": value, "unit": "bases/s", "cores": meta["cores"],
+                                                            "kind": meta["kind"], "sample": meta["sample"]},
+            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def config_dict(args, w):
+    return {"workload": "configs[1]: synthetic yeast-size genome %d bp, %gx simulated %d bp PacBio reads at %g%% error, "
+                        "k=%d, create_mega_reads production flags" % (w["genome"], w["coverage"], w["read_len"],
+                                                                      100 * w["error"], w["mer"]),
+            "genome_bp": w["genome"], "coverage": w["coverage"], "read_len": w["read_len"], "error": w["error"],
+            "mer": w["mer"], "psa_min": w["psa_min"], "unitig_k": w["unitig_k"], "batch_bases": args.batch_bases,
+            "l2": "inputs larger than L2 (step input >> 126 MB; index tables 0.5 GB)", "parallelism": "reads sharded x%d, index replicated" % args.gpus}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def ours(args, w, files):
+    import torch
+    import pacbio_b200.api as api
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = dist_setup(args.gpus)
+    torch.cuda.set_device(local_rank)
+    L = api.lib()                                   # raises if the CUDA library is missing
+    H = C.CDLL(os.path.join(ROOT, "pacbio_b200", "libmegareads_host.so"))
+    H.mrh_tool_create.restype = C.c_void_p
+    H.mrh_tool_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_char_p, C.c_size_t]
+    H.mrh_tool_load_reads.restype = C.c_int64
+    H.mrh_tool_load_reads.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
+    H.mrh_tool_run.restype = C.c_int64
+    H.mrh_tool_run.argtypes = [C.c_void_p, C.c_uint, C.c_char_p]
+    for f in ("mrh_tool_context", "mrh_tool_index", "mrh_tool_params"):
+        getattr(H, f).restype = C.c_void_p
+        getattr(H, f).argtypes = [C.c_void_p]
+    for f in ("mrh_tool_nbatches", "mrh_tool_nreads", "mrh_tool_sr_bases", "mrh_tool_sr_count"):
+        getattr(H, f).restype = C.c_uint64
+        getattr(H, f).argtypes = [C.c_void_p]
+    H.mrh_tool_batch_bases.restype = C.c_void_p
+    H.mrh_tool_batch_bases.argtypes = [C.c_void_p, C.c_uint64, api.u64p]
+    H.mrh_tool_batch_starts.restype = api.u64p
+    H.mrh_tool_batch_starts.argtypes = [C.c_void_p, C.c_uint64, api.u32p]
+    H.mrh_tool_last_stats.argtypes = [C.c_void_p, api.u64p]
+    H.mrh_tool_error.restype = C.c_char_p
+    H.mrh_tool_error.argtypes = [C.c_void_p]
+    H.mrh_tool_destroy.argtypes = [C.c_void_p]
+
+    err = C.create_string_buffer(512)
+    t0 = time.perf_counter()
+    tool = H.mrh_tool_create(files["sr"].encode(), files["unitigs"].encode(), 1, w["mer"], w["psa_min"], w["unitig_k"],
+                             local_rank, err, 512)
+    if not tool:
+        raise RuntimeError("mrh_tool_create: " + err.value.decode())
+    index_s = time.perf_counter() - t0
+    ctx, idx, params = H.mrh_tool_context(tool), H.mrh_tool_index(tool), H.mrh_tool_params(tool)
+    names = (C.c_char_p * 32)(); secs = (C.c_double * 32)()
+    nt = L.mr_context_timers(ctx, names, secs, 32)
+    index_timers = {names[i].decode(): secs[i] for i in range(nt)}
+    total_bases = H.mrh_tool_load_reads(tool, files["reads"].encode(), args.batch_bases, 0)
+    if total_bases < 0:
+        raise RuntimeError(H.mrh_tool_error(tool).decode())
+    nbatches = int(H.mrh_tool_nbatches(tool))
+    host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, args.gpus))
+
+    # ---- device-resident copies of every batch ------------------------------------------------------
+    dev = []
+    for i in range(nbatches):
+        nb, nr = C.c_uint64(), C.c_uint32()
+        pb = H.mrh_tool_batch_bases(tool, i, C.byref(nb))
+        ps = H.mrh_tool_batch_starts(tool, i, C.byref(nr))
+        hb = np.ctypeslib.as_array(C.cast(pb, api.u8p), shape=(nb.value,))
+        hs = np.ctypeslib.as_array(ps, shape=(nr.value + 1,))
+        dev.append((torch.from_numpy(hb).cuda(), torch.from_numpy(hs.astype(np.int64)).cuda(), hs.copy(), nr.value))
+    stream = torch.cuda.ExternalStream(L.mr_context_stream(ctx))
+
+    phase = {}
+    counters = dict(lookups=0, hits=0, groups=0, coords=0)
+
+    def device_step(collect):
+        for db, ds, hs, nr in dev:
+            out = C.c_void_p()
+            rc = L.mr_align_batch_device(ctx, idx, params, C.c_void_p(db.data_ptr()), C.c_void_p(ds.data_ptr()),
+                                         hs.ctypes.data_as(api.u64p), nr, C.byref(out))
+            if rc != 0:
+                raise RuntimeError(L.mr_last_error(ctx).decode())
+            if collect:
+                n = L.mr_context_timers(ctx, names, secs, 32)
+                for i in range(n):
+                    phase[names[i].decode()] = phase.get(names[i].decode(), 0.0) + secs[i]
+                v = api.ResultView()
+                L.mr_result_get(out, C.byref(v))
+                counters["lookups"] += v.n_kmers_looked_up; counters["hits"] += v.n_hits
+                counters["groups"] += v.n_groups; counters["coords"] += v.ncoords
+            L.mr_result_free(out)
+
+    for _ in range(args.warmup):
+        device_step(False)
+    torch.cuda.synchronize()
+    barrier(dist)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.mr_context_launches(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        device_step(True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier(dist)
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    launches = L.mr_context_launches(ctx) - launches0
+    dev_s_max = max_over_ranks(dist, dev_s)
+    value = args.gpus * total_bases * args.steps / dev_s_max
+
+    # ---- end to end through the host path ----------------------------------------------------------------
+    for _ in range(min(args.warmup, 1)):
+        H.mrh_tool_run(tool, host_threads, None)
+    torch.cuda.synchronize()
+    barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if H.mrh_tool_run(tool, host_threads, None) < 0:
+            raise RuntimeError(H.mrh_tool_error(tool).decode())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier(dist)
+    sampler.stop_flag = True
+    sampler.join()
+    e2e_s_max = max_over_ranks(dist, e2e_s)
+    stats = (C.c_uint64 * 8)()
+    H.mrh_tool_last_stats(tool, stats)
+    e2e_value = args.gpus * total_bases * args.steps / e2e_s_max
+
+    # ---- roofline of the dominant kernel (phase timers are CUDA events on the launching stream) ----------
+    dom = max(phase, key=phase.get) if phase else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = None
+    if dom:
+        T = total_bases * args.steps
+        # algorithmic bytes, DESIGN.md section "kernels": per read base / looked-up k-mer / hit
+        alg = {
+            "seed lookup": T * (1 + 20) + counters["lookups"] * 2 * (8 + 4 * 2.0),
+            "count threshold": T * 4 * 3,
+            "hit expansion": T * (4 + 8) * 2 + counters["hits"] * (4 + 8 + 16),
+            "group sort": counters["hits"] * (8 + 16 + 16) * 3,
+            "chain coords": counters["hits"] * (8 + 24),
+            "coords order": counters["coords"] * 120,
+            "overlap graph": counters["coords"] * 120,
+            "result download": counters["coords"] * 100,
+        }.get(dom, 0.0)
+        launches_dom = nbatches * args.steps
+        achieved = alg / phase[dom] / 1e9 if phase[dom] > 0 else 0.0
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": 1e3 * phase[dom] / launches_dom,
+                "share_of_step": phase[dom] / sum(phase.values()),
+                "phases_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()}}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            n1 = args.cpu_sample_reads or 300
+            v1, m1 = cpu_run(w, files, n1, os.cpu_count() or 1)
+            if not args.cpu_sample_reads:                       # scale the sample to ~15 s of CPU alignment work
+                n2 = int(min(H.mrh_tool_nreads(tool), max(300, 15.0 * v1 / w["read_len"])))
+                if n2 > 2 * n1:
+                    v1, m1 = cpu_run(w, files, n2, os.cpu_count() or 1)
+            cpu = {"value": v1, "unit": "bases/s", "cores": m1["cores"], "kind": m1["kind"], "sample": m1["sample"]}
+        except Exception as e:                                  # the baseline is reported, never the measured path
+            cpu = {"value": None, "unit": "bases/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    if rank == 0:
+        line = {"metric": "pacbio_bases_aligned_per_s", "value": value, "unit": "bases/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
+                "data": "synthetic", "config": config_dict(args, w),
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
+                        "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                        "host_threads": host_threads, "text_bytes_per_step": int(stats[0]),
+                        "timing": "wall clock (includes host tiling/printing), max over ranks"},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "index_build": {"seconds_total": index_s, "device_phases_s": index_timers,
+                                "superread_bases": int(H.mrh_tool_sr_bases(tool)), "superreads": int(H.mrh_tool_sr_count(tool))},
+                "work_per_step": {"read_bases": int(total_bases), "reads": int(H.mrh_tool_nreads(tool)), "batches": nbatches,
+                                  "kmers_looked_up": counters["lookups"] // max(1, args.steps),
+                                  "hits": counters["hits"] // max(1, args.steps), "groups": counters["groups"] // max(1, args.steps),
+                                  "coords": counters["coords"] // max(1, args.steps)}}
+        print(json.dumps(line))
+    H.mrh_tool_destroy(tool)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    w, files = data_files(args)
+    if args.impl == "reference":
+        reference_arm(args, w, files)
+    else:
+        ours(args, w, files)
+
+
+if __name__ == "__main__":
+    main()

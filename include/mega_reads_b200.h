@@ -47,6 +47,11 @@ int         mr_context_timers(const mr_context* ctx, const char** names, double*
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t    mr_context_launches(const mr_context* ctx);
 
+/* page-lock / unlock a caller-owned host buffer so that mr_align_batch's H2D copy runs at full PCIe
+ * speed (optional; the reference has no counterpart) */
+int         mr_host_pin(mr_context* ctx, const void* p, size_t bytes);
+int         mr_host_unpin(mr_context* ctx, const void* p);
+
 /* ---- index: replaces superread_parse() -> sequence_psa (superread_parser.hpp:212-224),
  *      i.e. sequence_psa::append_fasta (superread_parser.cc:12-46) output +
  *      PSA::PSA -> SA::create_mt (psa.hpp:130-140, mer_sa_imp.hpp:197-267).

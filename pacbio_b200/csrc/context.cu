@@ -70,6 +70,20 @@ int mr_context_timers(const mr_context* ctx, const char** names, double* seconds
   return n;
 }
 
+int mr_host_pin(mr_context* ctx, const void* p, size_t bytes) {
+  if(!ctx || !p) return MR_EINVAL;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  MR_CUDA(ctx, cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
+  return MR_OK;
+}
+
+int mr_host_unpin(mr_context* ctx, const void* p) {
+  if(!ctx || !p) return MR_EINVAL;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  MR_CUDA(ctx, cudaHostUnregister(const_cast<void*>(p)));
+  return MR_OK;
+}
+
 int mr_context_keep_taps(mr_context* ctx, int on) {
   if(!ctx) return MR_EINVAL;
   ctx->keep_taps = on != 0;

@@ -1,0 +1,126 @@
+// C ABI over the host pipeline, for bench.py and tests: load inputs once, then run whole read sets
+// through mr_align_batch (host buffers in, text out) exactly as the create_mega_reads tool does.
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+#include "pipeline.hpp"
+
+namespace {
+struct tool {
+  mrh::super_reads SR;
+  mrh::unitigs     U;
+  mrh::device_set  DS;
+  mrh::graph_options G;
+  mr_params        P;
+  std::vector<std::unique_ptr<mrh::read_batch>> batches;
+  uint64_t total_bases = 0, total_reads = 0;
+  std::string error;
+  uint64_t last_text_bytes = 0, last_d2h_bytes = 0, last_h2d_bytes = 0, last_coords = 0;
+  uint64_t last_lookups = 0, last_hits = 0, last_groups = 0;
+};
+}
+
+extern "C" {
+
+void* mrh_tool_create(const char* sr_fasta, const char* unitigs_path, int unitigs_is_fasta, unsigned mer, unsigned psa_min,
+                      unsigned unitig_k, int device, char* err, size_t err_cap) {
+  std::unique_ptr<tool> t(new tool);
+  try {
+    if(unitigs_is_fasta) t->U.load_sequences(unitigs_path); else t->U.load_lengths(unitigs_path);
+    t->SR.append_fasta(sr_fasta);
+    mrh::build_indexes(t->DS, std::vector<int>(1, device), t->SR, t->U, psa_min, mer);
+    mr_params_default(&t->P);
+    t->P.unitigs_k = unitig_k;
+    t->P.run_graph = 1;
+    t->G.k_len = unitig_k;
+    return t.release();
+  } catch(std::exception& e) {
+    if(err && err_cap) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+    return nullptr;
+  }
+}
+
+void mrh_tool_destroy(void* p) {
+  tool* t = (tool*)p;
+  if(!t) return;
+  for(auto& b : t->batches) mr_host_unpin(t->DS.ctx[0], b->bases.data());
+  delete t;
+}
+
+const char* mrh_tool_error(void* p) { return ((tool*)p)->error.c_str(); }
+mr_context* mrh_tool_context(void* p) { return ((tool*)p)->DS.ctx[0]; }
+mr_index* mrh_tool_index(void* p) { return ((tool*)p)->DS.idx[0]; }
+mr_params* mrh_tool_params(void* p) { return &((tool*)p)->P; }
+uint64_t mrh_tool_sr_bases(void* p) { return ((tool*)p)->SR.n; }
+uint64_t mrh_tool_sr_count(void* p) { return ((tool*)p)->SR.nseq(); }
+
+// loads (at most max_reads of) a read file into page-locked batches of ~batch_bases
+int64_t mrh_tool_load_reads(void* p, const char* path, uint64_t batch_bases, uint64_t max_reads) {
+  tool* t = (tool*)p;
+  try {
+    mrh::read_stream rs(std::vector<std::string>(1, path));
+    while(max_reads == 0 || t->total_reads < max_reads) {
+      std::unique_ptr<mrh::read_batch> b(new mrh::read_batch);
+      b->clear();
+      const uint64_t left = max_reads ? max_reads - t->total_reads : (1u << 20);
+      if(!rs.next_batch(*b, batch_bases, (uint32_t)std::min<uint64_t>(left, 1u << 20))) break;
+      t->total_bases += b->bases.size();
+      t->total_reads += b->nreads();
+      mr_host_pin(t->DS.ctx[0], b->bases.data(), b->bases.size());
+      t->batches.push_back(std::move(b));
+    }
+    return (int64_t)t->total_bases;
+  } catch(std::exception& e) { t->error = e.what(); return -1; }
+}
+uint64_t mrh_tool_nbatches(void* p) { return ((tool*)p)->batches.size(); }
+uint64_t mrh_tool_nreads(void* p) { return ((tool*)p)->total_reads; }
+// batch accessors, so a caller can stage the same batches on the device itself
+const char* mrh_tool_batch_bases(void* p, uint64_t i, uint64_t* nbytes) {
+  tool* t = (tool*)p; *nbytes = t->batches[i]->bases.size(); return t->batches[i]->bases.data();
+}
+const uint64_t* mrh_tool_batch_starts(void* p, uint64_t i, uint32_t* nreads) {
+  tool* t = (tool*)p; *nreads = t->batches[i]->nreads(); return t->batches[i]->start.data();
+}
+
+// One full pass over the loaded reads through the public path: mr_align_batch from host memory
+// (H2D inside), results back (D2H inside), text records formatted on `threads` host threads.
+// out_path may be null/empty (text is produced and dropped).  Returns read bases processed, <0 on error.
+int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
+  tool* t = (tool*)p;
+  FILE* out = nullptr;
+  if(out_path && *out_path) { out = fopen(out_path, "w"); if(!out) { t->error = "cannot open output"; return -1; } }
+  t->last_text_bytes = t->last_d2h_bytes = t->last_h2d_bytes = t->last_coords = 0;
+  t->last_lookups = t->last_hits = t->last_groups = 0;
+  std::string text;
+  try {
+    for(auto& b : t->batches) {
+      mr_result* r = nullptr;
+      const int rc = mr_align_batch(t->DS.ctx[0], t->DS.idx[0], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+      if(rc != MR_OK) throw std::runtime_error(mr_last_error(t->DS.ctx[0]));
+      mr_result_view v;
+      mr_result_get(r, &v);
+      text.clear();
+      mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, text);
+      if(out) fwrite(text.data(), 1, text.size(), out);
+      t->last_text_bytes += text.size();
+      t->last_h2d_bytes += b->bases.size() + (b->nreads() + 1) * 8ULL;
+      uint64_t info = 0;
+      for(uint64_t i = 0; i < v.ncoords; ++i) info += v.info_len[i];
+      t->last_d2h_bytes += (v.nreads + 1) * 8ULL + v.ncoords * (5 * 4 + 6 * 4 + 2 + 3 * 8 + 8 + 4 + 2 + 5 * 4) + info * 8;
+      t->last_coords += v.ncoords;
+      t->last_lookups += v.n_kmers_looked_up; t->last_hits += v.n_hits; t->last_groups += v.n_groups;
+      mr_result_free(r);
+    }
+  } catch(std::exception& e) { t->error = e.what(); if(out) fclose(out); return -1; }
+  if(out) fclose(out);
+  return (int64_t)t->total_bases;
+}
+void mrh_tool_last_stats(void* p, uint64_t* out8) {
+  tool* t = (tool*)p;
+  out8[0] = t->last_text_bytes; out8[1] = t->last_h2d_bytes; out8[2] = t->last_d2h_bytes; out8[3] = t->last_coords;
+  out8[4] = t->last_lookups; out8[5] = t->last_hits; out8[6] = t->last_groups; out8[7] = t->total_bases;
+}
+
+} // extern "C"

@@ -280,7 +280,7 @@ def ours(args, w, files):
     def device_step(collect):
         for db, ds, hs, nr in dev:
             out = C.c_void_p()
-            rc = L.mr_align_batch_device(ctx, idx, params, C.c_void_p(db.data_ptr()), C.c_void_p(ds.data_ptr()),
+            rc = L.mr_align_batch_device(ctx, idx, C.cast(params, C.POINTER(api.Params)), C.c_void_p(db.data_ptr()), C.c_void_p(ds.data_ptr()),
                                          hs.ctypes.data_as(api.u64p), nr, C.byref(out))
             if rc != 0:
                 raise RuntimeError(L.mr_last_error(ctx).decode())

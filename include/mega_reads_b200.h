@@ -160,6 +160,11 @@ int  mr_context_keep_taps(mr_context* ctx, int on);
 int  mr_result_taps(const mr_result* r, uint64_t* ngroups, const int64_t** groups,
                     uint64_t* noffsets, const int32_t** offsets, uint64_t* nlis, const uint32_t** lis);
 
+/* self test: the least-squares kernel divides by the running count through a shared reciprocal
+ * (3 FP64 instructions); this sweeps `samples` random operands over counts 1..max_n and reports how
+ * many quotients differ, bit for bit, from the IEEE division the reference executes (must be 0). */
+int  mr_selftest_division(mr_context* ctx, uint64_t samples, uint64_t seed, uint32_t max_n, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -338,273 +338,6 @@ __global__ void __launch_bounds__(256) group_scatter_kernel(const uint64_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// chaining + coords: one warp per (read, super-read) group.
-//   chain_strand   == lis_align::compute_L_P (lis_align.hpp:139-182), window_size 1
-//   coords section == compute_coords_info + least_square_2d + canonicalize + filters
-//                     (pb_aligner.cc:11-82, least_square_2d.hpp:47-67, pb_aligner.hpp:151-174,
-//                      coarse_aligner.cc:42-60)
-// The reference's forward_list L is kept as an array in REVERSE list order (list front == array
-// end), so the usual case -- extend the chain at the front, insert at the front -- touches only
-// the last few array slots.
-// ------------------------------------------------------------------------------------------------
-struct chain_buffers {
-  int32_t*  Lpb;  int32_t* Lsr;  uint32_t* Llen;  uint32_t* Lelt;   // indexed gs + array slot
-  uint32_t* pprev; uint32_t* cstart;                                  // indexed gs + element
-};
-
-__device__ void chain_strand(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const chain_buffers& cb, uint64_t gs,
-                             double a, double b, double C, uint32_t& longest_out, uint32_t& best_out,
-                             uint32_t* tap_sub) {
-  const unsigned lane = threadIdx.x & 31;
-  int32_t*  Lpb  = cb.Lpb + gs;  int32_t* Lsr = cb.Lsr + gs;
-  uint32_t* Llen = cb.Llen + gs; uint32_t* Lelt = cb.Lelt + gs;
-  uint32_t* pprev = cb.pprev + gs; uint32_t* cstart = cb.cstart + gs;
-  uint32_t cnt = 0, longest = 0, best = 0, nsub = 0;
-  for(uint32_t base = 0; base < N; base += 32) {
-    const uint32_t il = base + lane;
-    const uint64_t pl = il < N ? pay[gs + il] : 0;
-    const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
-    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
-    while(todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t i = base + src;
-      const int32_t pb_i = __shfl_sync(MR_FULL_MASK, pb_l, src), sr_i = __shfl_sync(MR_FULL_MASK, sr_l, src);
-      if(tap_sub && lane == 0) tap_sub[gs + i] = nsub;
-      ++nsub;
-
-      int      found = -1;
-      uint32_t f_len = 0, f_elt = 0, min_len = 0xffffffffu;
-      int      prev_pos = -1;
-      for(uint32_t c0 = 0; c0 < cnt; c0 += 32) {
-        const uint32_t p = c0 + lane;
-        const bool in = p < cnt;
-        const uint32_t slot = cnt - 1 - p;
-        int32_t lsr = 0, lpb = 0; uint32_t llen = 0, lelt = 0;
-        if(in) { lsr = Lsr[slot]; lpb = Lpb[slot]; llen = Llen[slot]; lelt = Lelt[slot]; }
-        bool feas = false;
-        if(in && sr_i > lsr) {
-          const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
-          const double t1 = a * d2, t2 = a * d1;
-          feas = d1 <= b + t1 && d2 <= b + t2 && d1 <= C && d2 <= C;
-        }
-        const unsigned ball = __ballot_sync(MR_FULL_MASK, feas);
-        const unsigned limit = ball ? (unsigned)(__ffs(ball) - 1) : 32u;
-        // first position of the strict minimum of len among the entries walked over
-        const unsigned packed = (in && lane < limit) ? ((llen << 5) | lane) : 0xffffffffu;
-        const unsigned best_packed = __reduce_min_sync(MR_FULL_MASK, packed);
-        if(best_packed != 0xffffffffu && (best_packed >> 5) < min_len) {
-          min_len = best_packed >> 5;
-          prev_pos = (int)(c0 + (best_packed & 31));
-        }
-        if(ball) {
-          found = (int)(c0 + limit);
-          f_len = __shfl_sync(MR_FULL_MASK, llen, limit);
-          f_elt = __shfl_sync(MR_FULL_MASK, lelt, limit);
-          break;
-        }
-      }
-      const uint32_t e_len = found >= 0 ? f_len + 1 : 1;
-      const uint32_t cs = found >= 0 ? cstart[f_elt] : i;
-      if(lane == 0) { pprev[i] = found >= 0 ? f_elt : kNone; cstart[i] = cs; }
-      // insert after prev_pos: the q = prev_pos + 1 entries in front of it move up one slot
-      const uint32_t q = (uint32_t)(prev_pos + 1);
-      for(uint32_t top = cnt; top > cnt - q; ) {
-        const uint32_t lo = (top - (cnt - q)) > 32 ? top - 32 : cnt - q;
-        const uint32_t s = lo + lane;
-        const bool has = s < top;
-        int32_t v0 = 0, v1 = 0; uint32_t v2 = 0, v3 = 0;
-        if(has) { v0 = Lpb[s]; v1 = Lsr[s]; v2 = Llen[s]; v3 = Lelt[s]; }
-        __syncwarp();
-        if(has) { Lpb[s + 1] = v0; Lsr[s + 1] = v1; Llen[s + 1] = v2; Lelt[s + 1] = v3; }
-        __syncwarp();
-        top = lo;
-      }
-      if(lane == 0) { const uint32_t s = cnt - q; Lpb[s] = pb_i; Lsr[s] = sr_i; Llen[s] = e_len; Lelt[s] = i; }
-      ++cnt;
-      __syncwarp();
-      if(longest < e_len) {
-        const uint64_t pc = pay[gs + cs];
-        const double span_pb = (double)(pb_i - (int32_t)(uint32_t)pc), span_sr = (double)(sr_i - (int32_t)(uint32_t)(pc >> 32));
-        const double s1 = a * span_sr, s2 = a * span_pb;
-        if(span_pb <= s1 && span_sr <= s2) { longest = e_len; best = i; }
-      }
-    }
-  }
-  longest_out = longest;
-  best_out = best;
-}
-
-struct survivors {
-  // unsorted survivor rows (capacity cap); slot taken with atomicAdd on *count
-  int32_t  *rs, *re, *qs, *qe, *nb_mers;
-  uint32_t *pb_cons, *sr_cons, *pb_cover, *sr_cover, *ql, *sr, *read, *info_len;
-  uint8_t  *rn, *use_bwd;
-  double   *stretch, *offset, *avg_err;
-  uint64_t *chain_pos;
-  uint64_t cap;
-  unsigned long long* count;
-  unsigned long long* info_total;
-  uint32_t* read_cnt;
-};
-
-struct chain_args {
-  index_view iv;
-  const uint64_t* keys; const uint64_t* pays; const uint64_t* group_start; uint64_t ngroups;
-  const uint64_t* read_start;
-  chain_buffers cb;
-  double a, b, C, matching_mers, matching_bases;
-  int forward;
-  uint32_t unitigs_k, n_unitigs;
-  const uint32_t* unitig_ids; const uint64_t* unitig_off;
-  survivors sv;
-  uint2* tap_lens; uint32_t* tap_cf; uint32_t* tap_cb; uint32_t* tap_sub;
-};
-
-__global__ void __launch_bounds__(128) chain_coords_kernel(chain_args A) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint32_t k = A.iv.k;
-  for(uint64_t g = warp0; g < A.ngroups; g += nwarps) {
-    const uint64_t gs = A.group_start[g];
-    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
-    const uint64_t key = A.keys[gs];
-    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
-    uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
-    chain_strand(A.pays, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub);
-    __syncwarp();
-    chain_strand(A.pays, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, A.tap_sub);
-    __syncwarp();
-    const bool fwd_align = len_f >= len_b;
-    const uint32_t nb = fwd_align ? len_f : len_b;
-    uint32_t* chain = A.cb.Lelt + gs;          // L is dead now: reuse as the chain, in order
-    uint32_t* pprev = A.cb.pprev + gs;
-    if(A.tap_lens) {                           // parity tap: both chains as sub-list indices
-      if(lane == 0) {
-        A.tap_lens[g] = make_uint2(len_f, len_b);
-        uint32_t cur = best_f;
-        for(uint32_t t = 0; t < len_f; ++t) { A.tap_cf[gs + len_f - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
-        cur = best_b;
-        for(uint32_t t = 0; t < len_b; ++t) { A.tap_cb[gs + len_b - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
-      }
-      __syncwarp();
-    }
-    if(nb == 0) continue;
-    if(lane == 0) {
-      uint32_t cur = fwd_align ? best_f : best_b;
-      for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
-    }
-    __syncwarp();
-
-    const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
-    const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
-    // online least squares, x = super-read offset, y = read offset, in chain order
-    double EX = 0, EY = 0, EXX = 0, EXY = 0, VX = 0, CXY = 0, NB = 0;
-    uint32_t pb_cons = 0, sr_cons = 0, pb_cover = k, sr_cover = k;
-    int32_t first_pb = 0, first_sr = 0, last_pb = 0, last_sr = 0, ppb = 0, psr = 0;
-    long n = 0;
-    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
-      const uint32_t tl = t0 + lane;
-      uint64_t pl = 0;
-      if(tl < nb) pl = A.pays[gs + chain[tl]];
-      const uint32_t m = min(32u, nb - t0);
-      for(uint32_t u = 0; u < m; ++u) {
-        const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
-        const int32_t pb = (int32_t)(uint32_t)p, so = (int32_t)(uint32_t)(p >> 32);
-        if(n == 0) { first_pb = pb; first_sr = so; }
-        else {
-          const uint32_t pb_diff = (uint32_t)(pb - ppb), sr_diff = (uint32_t)(so - psr);
-          pb_cons += pb_diff == 1; pb_cover += min(k, pb_diff);
-          sr_cons += sr_diff == 1; sr_cover += min(k, sr_diff);
-        }
-        ppb = pb; psr = so; last_pb = pb; last_sr = so;
-        const double x = (double)so, y = (double)pb;
-        ++n;
-        const double dn = (double)n;
-        const double dX = x - EX;  EX += dX / dn;  const double ndX = x - EX;  VX += dX * ndX;
-        const double dY = y - EY;  EY += dY / dn;  const double ndY = y - EY;
-        const double dXX = x * x - EXX;  EXX += dXX / dn;
-        const double dXY = x * y - EXY;  EXY += dXY / dn;
-        CXY += dX * ndY;
-        const double t1 = dXY * ndX, t2 = dXX * ndY;
-        NB += t1 - t2;
-      }
-    }
-    double stretch, offset, avg_err;
-    if(n == 1) { stretch = 1.0; offset = EY - EX; avg_err = 0; }
-    else {
-      stretch = CXY / VX; offset = NB / VX;
-      double e = 0;
-      for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
-        const uint32_t tl = t0 + lane;
-        uint64_t pl = 0;
-        if(tl < nb) pl = A.pays[gs + chain[tl]];
-        const uint32_t m = min(32u, nb - t0);
-        for(uint32_t u = 0; u < m; ++u) {
-          const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
-          const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
-          const double prod = stretch * x;
-          e += fabs(prod + offset - y);
-        }
-      }
-      avg_err = e / (double)n;
-    }
-    int32_t rs = first_pb, re = last_pb + (int32_t)k - 1, qs = first_sr, qe = last_sr;
-    bool rn = false;
-    if(qs < 0) {
-      if(A.forward) {
-        qs = (int32_t)((int64_t)ql + qs - (int64_t)k + 2);
-        qe = (int32_t)((int64_t)ql + qe + 1);
-        rn = true;
-        const double t = stretch * (double)((uint64_t)ql + 1);
-        offset -= t - (double)k;
-      } else {
-        qs = -qs + (int32_t)k - 1;
-        qe = -qe;
-        stretch = -stretch;
-        offset += (double)(k - 1);
-      }
-    } else {
-      qe += (int32_t)k - 1;
-    }
-    // filters of align_sequence_max (coarse_aligner.cc:51-54)
-    if(fabs(stretch) == 0.0) continue;
-    {
-      const double drl = (double)rl;
-      const double is = fmax(1.0, fmin(drl, stretch + offset));
-      const double tq = stretch * (double)ql;
-      const double ie = fmax(1.0, fmin(drl, tq + offset));
-      const int imp_len = (int)llabs(llrint(ie - is)) + 1;
-      if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) continue;
-      if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)pb_cover)) continue;
-    }
-    if(lane == 0) {
-      const bool use_bwd = A.forward && !fwd_align;
-      uint32_t ilen = 0;
-      if(A.unitigs_k && A.unitig_off) {
-        const uint64_t u0 = A.unitig_off[sr], u1 = A.unitig_off[sr + 1];
-        if(u1 > u0) {
-          const uint32_t first_id = (use_bwd ? A.unitig_ids[u1 - 1] : A.unitig_ids[u0]) >> 1;
-          if(first_id < A.n_unitigs) ilen = 2 * (uint32_t)(u1 - u0) - 1;
-        }
-      }
-      const unsigned long long slot = atomicAdd(A.sv.count, 1ULL);
-      if(slot < A.sv.cap) {
-        A.sv.rs[slot] = rs; A.sv.re[slot] = re; A.sv.qs[slot] = qs; A.sv.qe[slot] = qe; A.sv.nb_mers[slot] = (int32_t)nb;
-        A.sv.pb_cons[slot] = pb_cons; A.sv.sr_cons[slot] = sr_cons; A.sv.pb_cover[slot] = pb_cover; A.sv.sr_cover[slot] = sr_cover;
-        A.sv.ql[slot] = ql; A.sv.sr[slot] = sr; A.sv.read[slot] = read; A.sv.info_len[slot] = ilen;
-        A.sv.rn[slot] = rn; A.sv.use_bwd[slot] = use_bwd;
-        A.sv.stretch[slot] = stretch; A.sv.offset[slot] = offset; A.sv.avg_err[slot] = avg_err;
-        A.sv.chain_pos[slot] = gs;
-        atomicAdd(A.sv.info_total, (unsigned long long)ilen);
-        atomicAdd(A.sv.read_cnt + read, 1u);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // kmers_info / bases_info per surviving coords: compute_kmers_info::add_mer (pb_aligner.cc:84-143),
 // one thread per coords row walking its chain.
 // ------------------------------------------------------------------------------------------------
@@ -913,11 +646,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       sv.cap = cap; sv.count = ctr + 4; sv.info_total = ctr + 5; sv.read_cnt = ws.read_cnt.as<uint32_t>();
       MR_CUDA(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(uint64_t), st));
       MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
-      if(G) {
-        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 16, (G + 3) / 4);
-        chain_coords_kernel<<<grid, 128, 0, st>>>(A);
-        MR_LAUNCHED(ctx);
-      }
+      if(G) MR_TRY(launch_chain(ctx, A, ws.group_lists));
       MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       MR_CUDA(ctx, cudaStreamSynchronize(st));
       S = h_ctr[4];
@@ -1001,8 +730,10 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     auto rnd = [](uint64_t b) { return (b + 63) / 64 * 64; };
     uint64_t bytes = rnd(((uint64_t)nreads + 1) * 8) + 5 * rnd(Sc * 4) + 8 * rnd(Sc * 4) + 3 * rnd(Sc * 8) + rnd(Sc * 8) + 2 * rnd(Sc)
                      + 2 * rnd((info_total + 1) * 4) + (graph ? 2 * rnd(Sc) + 5 * rnd(Sc * 4) : 0);
-    MR_TRY(res->host.ensure(ctx, bytes + 4096));
-    char* cur = res->host.as<char>();
+    if(!ws.pinned_pool.empty()) { res->host = ws.pinned_pool.back(); ws.pinned_pool.pop_back(); }
+    else res->host = new pinned_buf;
+    MR_TRY(res->host->ensure(ctx, bytes + 4096));
+    char* cur = res->host->as<char>();
     auto pull = [&](const void* dsrc, uint64_t nbytes) -> const void* {
       void* dst = cur;
       cur += rnd(std::max<uint64_t>(nbytes, 1));
@@ -1106,6 +837,10 @@ int mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p, const cha
 void mr_result_free(mr_result* r) {
   if(!r) return;
   cudaSetDevice(r->ctx->device);
+  if(r->host) {
+    if(r->ctx->ws && r->ctx->ws->pinned_pool.size() < 4) r->ctx->ws->pinned_pool.push_back(r->host);
+    else delete r->host;
+  }
   delete r;
 }
 

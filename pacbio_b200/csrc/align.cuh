@@ -28,20 +28,56 @@ struct mr_workspace {
   dev_buf read_cnt, read_coords, read_cursor, slot, order;
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
-  dev_buf tap_lens, tap_cf, tap_cb;
+  dev_buf tap_lens, tap_cf, tap_cb, group_lists;
   dev_buf scan_scratch;
   prim::sort_scratch sort;
+  std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
+  ~mr_workspace() { for(auto p : pinned_pool) delete p; }
 };
 
 struct mr_result {
   mr_context* ctx = nullptr;
-  pinned_buf  host;                 // one pinned slab holding every array of the view
+  pinned_buf* host = nullptr;       // one pinned slab holding every array of the view (from the context's pool)
   mr_result_view view;
   // taps
   std::vector<int64_t>  tap_groups;
   std::vector<int32_t>  tap_offsets;
   std::vector<uint32_t> tap_lis;
 };
+
+
+// ---- chaining (chain.cu) ---------------------------------------------------------------------
+struct chain_buffers {
+  int32_t*  Lpb;  int32_t* Lsr;  uint32_t* Llen;  uint32_t* Lelt;   // indexed gs + array slot (global-memory tier)
+  uint32_t* pprev; uint32_t* cstart;                                  // indexed gs + element
+};
+
+struct survivors {
+  // unsorted survivor rows (capacity cap); slot taken with atomicAdd on *count
+  int32_t  *rs, *re, *qs, *qe, *nb_mers;
+  uint32_t *pb_cons, *sr_cons, *pb_cover, *sr_cover, *ql, *sr, *read, *info_len;
+  uint8_t  *rn, *use_bwd;
+  double   *stretch, *offset, *avg_err;
+  uint64_t *chain_pos;
+  uint64_t cap;
+  unsigned long long* count;
+  unsigned long long* info_total;
+  uint32_t* read_cnt;
+};
+
+struct chain_args {
+  index_view iv;
+  const uint64_t* keys; const uint64_t* pays; const uint64_t* group_start; uint64_t ngroups;
+  const uint64_t* read_start;
+  chain_buffers cb;
+  double a, b, C, matching_mers, matching_bases;
+  int forward;
+  uint32_t unitigs_k, n_unitigs;
+  const uint32_t* unitig_ids; const uint64_t* unitig_off;
+  survivors sv;
+  uint2* tap_lens; uint32_t* tap_cf; uint32_t* tap_cb; uint32_t* tap_sub;
+};
+int launch_chain(mr_context* ctx, const chain_args& A, dev_buf& lists);
 
 // graph.cu
 struct graph_args {

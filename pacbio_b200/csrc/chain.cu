@@ -1,0 +1,519 @@
+// Chaining ("LIS") + coords: one warp per (read, super-read) group.
+//   chain_*        == lis_align::compute_L_P (lis_align.hpp:139-182), window_size 1
+//   finish_group   == compute_coords_info + least_square_2d + canonicalize + the filters of
+//                     align_sequence_max (pb_aligner.cc:11-82, least_square_2d.hpp:47-67,
+//                     pb_aligner.hpp:151-174, coarse_aligner.cc:42-60)
+//
+// The reference walks a forward_list L for every new hit, stops at the first feasible extension and
+// inserts the new element after the first strict minimum of `len` seen on the way.  Here L is an
+// array kept in REVERSE list order (list front == array end): 32 entries are tested per step, a
+// ballot finds the first feasible one, a redux finds the insertion point, and the usual case --
+// extend the newest chain, insert at the front -- touches only the last array slots.
+//
+// Groups are binned by size: <= 64 hits and <= 1024 hits keep L, the chain-start coordinates and
+// the back pointers in shared memory (22 B per hit); larger groups run the same algorithm out of
+// global scratch.  The kernels are latency/issue bound, not bandwidth bound: what matters is the
+// length of the dependent chain per hit (one shared-memory round trip + ~10 FP64 ops + 3 warp
+// collectives) and the number of warps in flight.
+#include "align.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
+  const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
+  const double t1 = a * d2, t2 = a * d1;                   // mul then add, never fused (-fmad=false)
+  return d1 <= b + t1 && d2 <= b + t2 && d1 <= C && d2 <= C;
+}
+
+__device__ __forceinline__ bool accept_sequence(int32_t span_pb, int32_t span_sr, double a) {
+  const double s1 = a * (double)span_sr, s2 = a * (double)span_pb;
+  return (double)span_pb <= s1 && (double)span_sr <= s2;
+}
+
+// x / n for an integer count n given r = RN(1/n): q = RN(x*r) is within one ulp of x/n, the
+// remainder x - q*n is exact in one FMA, and q + rem*r rounds to the correctly rounded quotient
+// (Markstein's division theorem) -- bit-identical to the IEEE division the reference executes,
+// at 3 FP64 instructions instead of a ~35-instruction division sequence.  The online least
+// squares divides four values by the same n for every chain element.
+__device__ __forceinline__ double div_by_count(double x, double dn, double r) {
+  const double q = x * r;
+  const double rem = __fma_rn(-q, dn, x);
+  return __fma_rn(rem, r, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory strand: per warp arrays of CAP entries
+// ---------------------------------------------------------------------------------------------
+template<int CAP>
+struct warp_store {
+  int32_t  pb[CAP], sr[CAP], cpb[CAP], csr[CAP];
+  uint32_t meta[CAP];          // len << 16 | element index   (CAP <= 65536)
+  uint16_t pprev[CAP];         // by element index, 0xffff = none
+};
+
+template<int CAP, bool TAPS>
+__device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ pay, uint32_t N, bool neg, warp_store<CAP>& S,
+                                                  uint16_t* sub, double a, double b, double C,
+                                                  uint32_t& longest_out, uint32_t& best_out) {
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t cnt = 0, longest = 0, best = 0, nsub = 0;
+  int32_t  fr_pb = 0, fr_sr = 0, fr_cpb = 0, fr_csr = 0;    // list front (array slot cnt - 1)
+  uint32_t fr_meta = 0;
+  uint64_t next_pl = lane < N ? pay[lane] : 0;
+  for(uint32_t base = 0; base < N; base += 32) {
+    const uint32_t il = base + lane;
+    const uint64_t pl = next_pl;
+    if(base + 32 < N) next_pl = (il + 32 < N) ? pay[il + 32] : 0;      // prefetch the next 32 hits
+    const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
+    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
+    while(todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t i = base + src;
+      const int32_t pb_i = __shfl_sync(MR_FULL_MASK, pb_l, src), sr_i = __shfl_sync(MR_FULL_MASK, sr_l, src);
+      if(TAPS) { if(lane == 0) sub[i] = (uint16_t)nsub; ++nsub; }
+
+      int      found = -1, prev_pos = -1;
+      uint32_t f_meta = 0, min_len = 0xffffffffu;
+      int32_t  f_cpb = 0, f_csr = 0;
+      // Fast path: the list front (kept in registers, identical in every lane) is feasible.  Then the
+      // walk stops at position 0 without passing any entry, so the new element goes to the front.
+      if(cnt != 0 && sr_i > fr_sr && accept_mer(pb_i, sr_i, fr_pb, fr_sr, a, b, C)) {
+        found = 0; f_meta = fr_meta; f_cpb = fr_cpb; f_csr = fr_csr;
+      } else
+      for(uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t p = c0 + lane;
+        const bool in = p < cnt;
+        const uint32_t slot = cnt - 1 - p;
+        int32_t lsr = 0, lpb = 0; uint32_t meta = 0;
+        if(in) { lsr = S.sr[slot]; lpb = S.pb[slot]; meta = S.meta[slot]; }
+        const bool feas = in && sr_i > lsr && accept_mer(pb_i, sr_i, lpb, lsr, a, b, C);
+        const unsigned ball = __ballot_sync(MR_FULL_MASK, feas);
+        const unsigned limit = ball ? (unsigned)(__ffs(ball) - 1) : 32u;
+        // first position of the strict minimum of len among the entries walked over
+        const unsigned packed = (in && lane < limit) ? (((meta >> 16) << 5) | lane) : 0xffffffffu;
+        const unsigned bp = __reduce_min_sync(MR_FULL_MASK, packed);
+        if(bp != 0xffffffffu && (bp >> 5) < min_len) { min_len = bp >> 5; prev_pos = (int)(c0 + (bp & 31)); }
+        if(ball) {
+          found = (int)(c0 + limit);
+          f_meta = __shfl_sync(MR_FULL_MASK, meta, limit);
+          const uint32_t fslot = cnt - 1 - (uint32_t)found;
+          f_cpb = S.cpb[fslot]; f_csr = S.csr[fslot];           // uniform address: broadcast
+          break;
+        }
+      }
+      const uint32_t e_len = found >= 0 ? (f_meta >> 16) + 1 : 1;
+      const int32_t cpb = found >= 0 ? f_cpb : pb_i, csr = found >= 0 ? f_csr : sr_i;
+      // insert after prev_pos: the q = prev_pos + 1 entries in front of it move up one slot
+      const uint32_t q = (uint32_t)(prev_pos + 1);
+      for(uint32_t top = cnt; top > cnt - q; ) {
+        const uint32_t lo = (top - (cnt - q)) > 32 ? top - 32 : cnt - q;
+        const uint32_t s = lo + lane;
+        const bool has = s < top;
+        int32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0; uint32_t v4 = 0;
+        if(has) { v0 = S.pb[s]; v1 = S.sr[s]; v2 = S.cpb[s]; v3 = S.csr[s]; v4 = S.meta[s]; }
+        __syncwarp();
+        if(has) { S.pb[s + 1] = v0; S.sr[s + 1] = v1; S.cpb[s + 1] = v2; S.csr[s + 1] = v3; S.meta[s + 1] = v4; }
+        __syncwarp();
+        top = lo;
+      }
+      if(lane == 0) {
+        const uint32_t s = cnt - q;
+        S.pb[s] = pb_i; S.sr[s] = sr_i; S.cpb[s] = cpb; S.csr[s] = csr; S.meta[s] = (e_len << 16) | i;
+        S.pprev[i] = found >= 0 ? (uint16_t)(f_meta & 0xffff) : (uint16_t)0xffff;
+      }
+      if(q == 0) { fr_pb = pb_i; fr_sr = sr_i; fr_cpb = cpb; fr_csr = csr; fr_meta = (e_len << 16) | i; }
+      ++cnt;
+      __syncwarp();
+      if(longest < e_len && accept_sequence(pb_i - cpb, sr_i - csr, a)) { longest = e_len; best = i; }
+    }
+  }
+  longest_out = longest;
+  best_out = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// global-memory strand (groups larger than the shared-memory tiers)
+// ---------------------------------------------------------------------------------------------
+__device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const chain_buffers& cb, uint64_t gs,
+                                    double a, double b, double C, uint32_t& longest_out, uint32_t& best_out, uint32_t* tap_sub) {
+  const unsigned lane = threadIdx.x & 31;
+  int32_t*  Lpb  = cb.Lpb + gs;  int32_t* Lsr = cb.Lsr + gs;
+  uint32_t* Llen = cb.Llen + gs; uint32_t* Lelt = cb.Lelt + gs;
+  uint32_t* pprev = cb.pprev + gs; uint32_t* cstart = cb.cstart + gs;
+  uint32_t cnt = 0, longest = 0, best = 0, nsub = 0;
+  for(uint32_t base = 0; base < N; base += 32) {
+    const uint32_t il = base + lane;
+    const uint64_t pl = il < N ? pay[il] : 0;
+    const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
+    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
+    while(todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t i = base + src;
+      const int32_t pb_i = __shfl_sync(MR_FULL_MASK, pb_l, src), sr_i = __shfl_sync(MR_FULL_MASK, sr_l, src);
+      if(tap_sub && lane == 0) tap_sub[gs + i] = nsub;
+      ++nsub;
+      int      found = -1, prev_pos = -1;
+      uint32_t f_len = 0, f_elt = 0, min_len = 0xffffffffu;
+      for(uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t p = c0 + lane;
+        const bool in = p < cnt;
+        const uint32_t slot = cnt - 1 - p;
+        int32_t lsr = 0, lpb = 0; uint32_t llen = 0, lelt = 0;
+        if(in) { lsr = Lsr[slot]; lpb = Lpb[slot]; llen = Llen[slot]; lelt = Lelt[slot]; }
+        const bool feas = in && sr_i > lsr && accept_mer(pb_i, sr_i, lpb, lsr, a, b, C);
+        const unsigned ball = __ballot_sync(MR_FULL_MASK, feas);
+        const unsigned limit = ball ? (unsigned)(__ffs(ball) - 1) : 32u;
+        // len can exceed 27 bits only for groups of > 2^27 hits, which the batch limits exclude
+        const unsigned packed = (in && lane < limit) ? ((llen << 5) | lane) : 0xffffffffu;
+        const unsigned bp = __reduce_min_sync(MR_FULL_MASK, packed);
+        if(bp != 0xffffffffu && (bp >> 5) < min_len) { min_len = bp >> 5; prev_pos = (int)(c0 + (bp & 31)); }
+        if(ball) {
+          found = (int)(c0 + limit);
+          f_len = __shfl_sync(MR_FULL_MASK, llen, limit);
+          f_elt = __shfl_sync(MR_FULL_MASK, lelt, limit);
+          break;
+        }
+      }
+      const uint32_t e_len = found >= 0 ? f_len + 1 : 1;
+      const uint32_t cs = found >= 0 ? cstart[f_elt] : i;
+      if(lane == 0) { pprev[i] = found >= 0 ? f_elt : kNone; cstart[i] = cs; }
+      const uint32_t q = (uint32_t)(prev_pos + 1);
+      for(uint32_t top = cnt; top > cnt - q; ) {
+        const uint32_t lo = (top - (cnt - q)) > 32 ? top - 32 : cnt - q;
+        const uint32_t s = lo + lane;
+        const bool has = s < top;
+        int32_t v0 = 0, v1 = 0; uint32_t v2 = 0, v3 = 0;
+        if(has) { v0 = Lpb[s]; v1 = Lsr[s]; v2 = Llen[s]; v3 = Lelt[s]; }
+        __syncwarp();
+        if(has) { Lpb[s + 1] = v0; Lsr[s + 1] = v1; Llen[s + 1] = v2; Lelt[s + 1] = v3; }
+        __syncwarp();
+        top = lo;
+      }
+      if(lane == 0) { const uint32_t s = cnt - q; Lpb[s] = pb_i; Lsr[s] = sr_i; Llen[s] = e_len; Lelt[s] = i; }
+      ++cnt;
+      __syncwarp();
+      if(longest < e_len) {
+        const uint64_t pc = pay[cs];
+        if(accept_sequence(pb_i - (int32_t)(uint32_t)pc, sr_i - (int32_t)(uint32_t)(pc >> 32), a)) { longest = e_len; best = i; }
+      }
+    }
+  }
+  longest_out = longest;
+  best_out = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// coords of one group from its chain (warp-uniform; chain[t] = group-local hit index, in order)
+// ---------------------------------------------------------------------------------------------
+template<typename ChainT>
+__device__ __forceinline__ void finish_group(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                             uint32_t nb, const ChainT* chain, uint32_t* chain_global) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t k = A.iv.k;
+  const uint64_t* pay = A.pays + gs;
+  const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
+  const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
+  // online least squares, x = super-read offset, y = read offset, in chain order
+  double EX = 0, EY = 0, EXX = 0, EXY = 0, VX = 0, CXY = 0, NB = 0;
+  uint32_t pb_cons = 0, sr_cons = 0, pb_cover = k, sr_cover = k;
+  int32_t first_pb = 0, first_sr = 0, last_pb = 0, last_sr = 0, ppb = 0, psr = 0;
+  long n = 0;
+  for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+    const uint32_t tl = t0 + lane;
+    uint64_t pl = 0;
+    if(tl < nb) pl = pay[chain[tl]];
+    const uint32_t m = min(32u, nb - t0);
+    for(uint32_t u = 0; u < m; ++u) {
+      const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+      const int32_t pb = (int32_t)(uint32_t)p, so = (int32_t)(uint32_t)(p >> 32);
+      if(n == 0) { first_pb = pb; first_sr = so; }
+      else {
+        const uint32_t pb_diff = (uint32_t)(pb - ppb), sr_diff = (uint32_t)(so - psr);
+        pb_cons += pb_diff == 1; pb_cover += min(k, pb_diff);
+        sr_cons += sr_diff == 1; sr_cover += min(k, sr_diff);
+      }
+      ppb = pb; psr = so; last_pb = pb; last_sr = so;
+      const double x = (double)so, y = (double)pb;
+      ++n;
+      const double dn = (double)n;
+      const double rn_ = 1.0 / dn;                              // one true division per element
+      const double dX = x - EX;  EX += div_by_count(dX, dn, rn_);  const double ndX = x - EX;  VX += dX * ndX;
+      const double dY = y - EY;  EY += div_by_count(dY, dn, rn_);  const double ndY = y - EY;
+      const double dXX = x * x - EXX;  EXX += div_by_count(dXX, dn, rn_);
+      const double dXY = x * y - EXY;  EXY += div_by_count(dXY, dn, rn_);
+      CXY += dX * ndY;
+      const double t1 = dXY * ndX, t2 = dXX * ndY;
+      NB += t1 - t2;
+    }
+  }
+  double stretch, offset, avg_err;
+  if(n == 1) { stretch = 1.0; offset = EY - EX; avg_err = 0; }
+  else {
+    stretch = CXY / VX; offset = NB / VX;
+    double e = 0;
+    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+      const uint32_t tl = t0 + lane;
+      uint64_t pl = 0;
+      if(tl < nb) pl = pay[chain[tl]];
+      const uint32_t m = min(32u, nb - t0);
+      for(uint32_t u = 0; u < m; ++u) {
+        const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+        const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
+        const double prod = stretch * x;
+        e += fabs(prod + offset - y);
+      }
+    }
+    avg_err = e / (double)n;
+  }
+  int32_t rs = first_pb, re = last_pb + (int32_t)k - 1, qs = first_sr, qe = last_sr;
+  bool rn = false;
+  if(qs < 0) {
+    if(A.forward) {
+      qs = (int32_t)((int64_t)ql + qs - (int64_t)k + 2);
+      qe = (int32_t)((int64_t)ql + qe + 1);
+      rn = true;
+      const double t = stretch * (double)((uint64_t)ql + 1);
+      offset -= t - (double)k;
+    } else {
+      qs = -qs + (int32_t)k - 1;
+      qe = -qe;
+      stretch = -stretch;
+      offset += (double)(k - 1);
+    }
+  } else {
+    qe += (int32_t)k - 1;
+  }
+  // filters of align_sequence_max (coarse_aligner.cc:51-54)
+  if(fabs(stretch) == 0.0) return;
+  {
+    const double drl = (double)rl;
+    const double is = fmax(1.0, fmin(drl, stretch + offset));
+    const double tq = stretch * (double)ql;
+    const double ie = fmax(1.0, fmin(drl, tq + offset));
+    const int imp_len = (int)llabs(llrint(ie - is)) + 1;
+    if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) return;
+    if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)pb_cover)) return;
+  }
+  // survivor: publish its chain for the kmers_info kernel and append the row
+  if((const void*)chain != (const void*)chain_global)
+    for(uint32_t t = lane; t < nb; t += 32) chain_global[t] = chain[t];
+  if(lane == 0) {
+    const bool use_bwd = A.forward && !fwd_align;
+    uint32_t ilen = 0;
+    if(A.unitigs_k && A.unitig_off) {
+      const uint64_t u0 = A.unitig_off[sr], u1 = A.unitig_off[sr + 1];
+      if(u1 > u0) {
+        const uint32_t first_id = (use_bwd ? A.unitig_ids[u1 - 1] : A.unitig_ids[u0]) >> 1;
+        if(first_id < A.n_unitigs) ilen = 2 * (uint32_t)(u1 - u0) - 1;
+      }
+    }
+    const survivors& sv = A.sv;
+    const unsigned long long slot = atomicAdd(sv.count, 1ULL);
+    if(slot < sv.cap) {
+      sv.rs[slot] = rs; sv.re[slot] = re; sv.qs[slot] = qs; sv.qe[slot] = qe; sv.nb_mers[slot] = (int32_t)nb;
+      sv.pb_cons[slot] = pb_cons; sv.sr_cons[slot] = sr_cons; sv.pb_cover[slot] = pb_cover; sv.sr_cover[slot] = sr_cover;
+      sv.ql[slot] = ql; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = ilen;
+      sv.rn[slot] = rn; sv.use_bwd[slot] = use_bwd;
+      sv.stretch[slot] = stretch; sv.offset[slot] = offset; sv.avg_err[slot] = avg_err;
+      sv.chain_pos[slot] = gs;
+      atomicAdd(sv.info_total, (unsigned long long)ilen);
+      atomicAdd(sv.read_cnt + read, 1u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// bins groups by size; lists[c] holds the group ids of class c (0: <=64, 1: <=1024, 2: larger)
+__global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
+                                                               uint32_t* __restrict__ list0, uint32_t* __restrict__ list1,
+                                                               uint32_t* __restrict__ list2, uint32_t* __restrict__ counts) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int cls = -1;
+  if(g < ngroups) {
+    const uint64_t n = group_start[g + 1] - group_start[g];
+    cls = n <= 64 ? 0 : (n <= 1024 ? 1 : 2);
+  }
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for(int c = 0; c < 3; ++c) {
+    const unsigned m = __ballot_sync(MR_FULL_MASK, cls == c);
+    if(!m) continue;
+    unsigned base = 0;
+    if(lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counts + c, __popc(m));
+    base = __shfl_sync(MR_FULL_MASK, base, __ffs(m) - 1);
+    if(cls == c) (c == 0 ? list0 : (c == 1 ? list1 : list2))[base + __popc(m & lanemask_lt())] = (uint32_t)g;
+  }
+}
+
+template<int CAP, int WARPS, bool TAPS>
+__global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                                       const uint32_t* __restrict__ list_count,
+                                                                       uint32_t* __restrict__ cursor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  warp_store<CAP>& S = reinterpret_cast<warp_store<CAP>*>(smem_raw)[wib];
+  uint16_t* sub = TAPS ? reinterpret_cast<uint16_t*>(smem_raw + sizeof(warp_store<CAP>) * WARPS) + wib * CAP : nullptr;
+  const uint32_t total = *list_count;
+  while(true) {
+    uint32_t w = 0;
+    if(lane == 0) w = atomicAdd(cursor, 1u);              // dynamic work distribution, one group per grab
+    w = __shfl_sync(MR_FULL_MASK, w, 0);
+    if(w >= total) break;
+    const uint32_t g = list[w];
+    const uint64_t gs = A.group_start[g];
+    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    const uint64_t key = A.keys[gs];
+    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
+    uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
+    chain_strand_smem<CAP, TAPS>(A.pays + gs, N, false, S, sub, A.a, A.b, A.C, len_f, best_f);
+    __syncwarp();
+    chain_strand_smem<CAP, TAPS>(A.pays + gs, N, true, S, sub, A.a, A.b, A.C, len_b, best_b);
+    __syncwarp();
+    const bool fwd_align = len_f >= len_b;
+    const uint32_t nb = fwd_align ? len_f : len_b;
+    if(TAPS) {
+      if(lane == 0) {
+        A.tap_lens[g] = make_uint2(len_f, len_b);
+        uint32_t cur = best_f;
+        for(uint32_t t = 0; t < len_f; ++t) { A.tap_cf[gs + len_f - 1 - t] = sub[cur]; cur = S.pprev[cur]; }
+        cur = best_b;
+        for(uint32_t t = 0; t < len_b; ++t) { A.tap_cb[gs + len_b - 1 - t] = sub[cur]; cur = S.pprev[cur]; }
+      }
+      __syncwarp();
+    }
+    // L is dead: its pb[] array becomes the chain, in order
+    uint32_t* chain = reinterpret_cast<uint32_t*>(S.pb);
+    if(lane == 0) {
+      uint32_t cur = fwd_align ? best_f : best_b;
+      for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = S.pprev[cur]; }
+    }
+    __syncwarp();
+    finish_group<uint32_t>(A, gs, read, sr, fwd_align, nb, chain, A.cb.Lelt + gs);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                                   const uint32_t* __restrict__ list_count,
+                                                                   uint32_t* __restrict__ cursor) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t total = list ? *list_count : (uint32_t)A.ngroups;
+  while(true) {
+    uint32_t w = 0;
+    if(lane == 0) w = atomicAdd(cursor, 1u);
+    w = __shfl_sync(MR_FULL_MASK, w, 0);
+    if(w >= total) break;
+    const uint32_t g = list ? list[w] : w;
+    const uint64_t gs = A.group_start[g];
+    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    const uint64_t key = A.keys[gs];
+    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
+    uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
+    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub);
+    __syncwarp();
+    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, A.tap_sub);
+    __syncwarp();
+    const bool fwd_align = len_f >= len_b;
+    const uint32_t nb = fwd_align ? len_f : len_b;
+    uint32_t* chain = A.cb.Lelt + gs;          // L is dead now: reuse as the chain, in order
+    uint32_t* pprev = A.cb.pprev + gs;
+    if(A.tap_lens) {
+      if(lane == 0) {
+        A.tap_lens[g] = make_uint2(len_f, len_b);
+        uint32_t cur = best_f;
+        for(uint32_t t = 0; t < len_f; ++t) { A.tap_cf[gs + len_f - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
+        cur = best_b;
+        for(uint32_t t = 0; t < len_b; ++t) { A.tap_cb[gs + len_b - 1 - t] = A.tap_sub[gs + cur]; cur = pprev[cur]; }
+      }
+      __syncwarp();
+    }
+    if(lane == 0) {
+      uint32_t cur = fwd_align ? best_f : best_b;
+      for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
+    }
+    __syncwarp();
+    finish_group<uint32_t>(A, gs, read, sr, fwd_align, nb, chain, chain);
+    __syncwarp();
+  }
+}
+
+template<int CAP, int WARPS, bool TAPS>
+int launch_smem(mr_context* ctx, const chain_args& A, const uint32_t* list, const uint32_t* count, uint32_t* cursor, int blocks_per_sm) {
+  const size_t smem = sizeof(warp_store<CAP>) * WARPS + (TAPS ? (size_t)WARPS * CAP * sizeof(uint16_t) : 0);
+  MR_CUDA(ctx, cudaFuncSetAttribute(chain_coords_smem_kernel<CAP, WARPS, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chain_coords_smem_kernel<CAP, WARPS, TAPS><<<ctx->sm_count * blocks_per_sm, WARPS * 32, smem, ctx->stream>>>(A, list, count, cursor);
+  MR_LAUNCHED(ctx);
+  return MR_OK;
+}
+
+} // namespace
+
+// lists: 3 x ngroups uint32 + 8 uint32 counters (counts[0..2], cursors[4..6])
+int launch_chain(mr_context* ctx, const chain_args& A, dev_buf& lists) {
+  if(A.ngroups == 0) return MR_OK;
+  if(A.ngroups >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "more than 2^32 (read, super-read) groups in one batch");
+  const uint64_t G = A.ngroups;
+  MR_TRY(lists.ensure(ctx, (3 * G + 16) * sizeof(uint32_t)));
+  uint32_t* l0 = lists.as<uint32_t>(); uint32_t* l1 = l0 + G; uint32_t* l2 = l1 + G; uint32_t* ctr = l2 + G;
+  MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, l0, l1, l2, ctr);
+  MR_LAUNCHED(ctx);
+  const bool taps = A.tap_lens != nullptr;
+  // large groups first: they are the long poles, the small ones fill in behind them
+  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(A, l2, ctr + 2, ctr + 6);
+  MR_LAUNCHED(ctx);
+  if(taps) {
+    MR_TRY((launch_smem<1024, 4, true>(ctx, A, l1, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, true>(ctx, A, l0, ctr + 0, ctr + 4, 8)));
+  } else {
+    MR_TRY((launch_smem<1024, 4, false>(ctx, A, l1, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, false>(ctx, A, l0, ctr + 0, ctr + 4, 8)));
+  }
+  return MR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// self test of div_by_count against the hardware's IEEE division (exposed through the C ABI so the
+// GPU test-suite can sweep it): values shaped like the least-squares operands (differences of
+// offsets, products of offsets minus running means) over every count up to max_n.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) division_selftest_kernel(uint64_t samples, uint64_t seed, uint32_t max_n,
+                                                                 unsigned long long* mismatches) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < samples; i += stride) {
+    uint64_t z = seed + i * 0x9e3779b97f4a7c15ULL;               // splitmix64
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+    uint64_t y = z * 0xd1342543de82ef95ULL + 1;
+    y = (y ^ (y >> 29)) * 0xbf58476d1ce4e5b9ULL; y ^= y >> 32;
+    const uint32_t n = 1 + (uint32_t)(z % max_n);
+    const int e = (int)((y >> 56) % 48) - 8;                      // magnitudes 2^-8 .. 2^39
+    double x = ldexp((double)(int64_t)(y & 0xfffffffffffffULL) / 4503599627370496.0 + ((y >> 52) & 1 ? 1.0 : 0.0), e);
+    if((y >> 53) & 1) x = -x;
+    if(((y >> 54) & 3) == 0) x = (double)(int64_t)((y & 0xffffff)) - 8388608.0;   // plain integers too
+    const double dn = (double)n;
+    const double want = x / dn;
+    const double got = div_by_count(x, dn, 1.0 / dn);
+    bad += __double_as_longlong(want) != __double_as_longlong(got);
+  }
+  if(bad) atomicAdd(mismatches, bad);
+}
+}
+
+extern "C" int mr_selftest_division(mr_context* ctx, uint64_t samples, uint64_t seed, uint32_t max_n, uint64_t* mismatches) {
+  if(!ctx || !mismatches || max_n == 0) return MR_EINVAL;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  dev_buf d;
+  MR_TRY(d.ensure(ctx, sizeof(unsigned long long)));
+  MR_CUDA(ctx, cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+  division_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(samples, seed, max_n, d.as<unsigned long long>());
+  MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaMemcpyAsync(mismatches, d.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
+}

@@ -141,3 +141,14 @@ def test_align_stages_match_oracle(case, ctx, port, forward):
             "coords of read %d" % r
     assert total_coords > 20
     port.aligner_destroy(ap)
+
+
+def test_shared_reciprocal_division_is_exact(ctx):
+    """div_by_count (chain.cu) must equal IEEE x / n bit for bit: 2^30 random operands."""
+    import ctypes as C
+    L = ctx.L
+    L.mr_selftest_division.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+    for seed, max_n in ((1, 70000), (2, 1 << 20), (3, 40)):
+        bad = C.c_uint64(123)
+        ctx.check(L.mr_selftest_division(ctx.h, 1 << 28, seed, max_n, C.byref(bad)))
+        assert bad.value == 0

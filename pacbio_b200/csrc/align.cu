@@ -351,65 +351,90 @@ struct info_args {
   int32_t* kinfo; int32_t* binfo;
 };
 
+// One warp per coords row: the lanes fetch 32 chain hits at a time (two dependent global loads
+// each, all in flight together), lane 0 runs the sequential add_mer state machine out of shared
+// memory.  Counters live in shared memory while the super-read has at most kInfoSmem/2 unitigs.
+constexpr int kInfoSmem = 128;
 __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= A.n) return;
-  const uint32_t ilen = A.info_len[i];
-  if(ilen == 0) return;
-  int32_t* mers = A.kinfo + A.info_off[i];
-  int32_t* bases = A.binfo + A.info_off[i];
-  for(uint32_t j = 0; j < ilen; ++j) { mers[j] = 0; bases[j] = 0; }
-  const uint32_t sr = A.sr[i];
-  const bool bwd = A.use_bwd[i];
-  const uint64_t u0 = A.unitig_off[sr];
-  const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
-  const uint32_t invalid_id = 0x7fffffffu;
-  auto uid = [&](uint32_t t) -> uint32_t {
-    if(t >= nu) return invalid_id;
-    return (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
-  };
-  const int K = (int)A.k, UK = (int)A.unitigs_k;
-  const uint64_t gs = A.chain_pos[i];
-  const uint32_t nb = (uint32_t)A.nb_mers[i];
-  const bool fwd_align = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs]] >> 32) > 0;
-  const int64_t ql = A.ql[i];
-  uint32_t cunitig = 0;
-  int cend = A.unitig_len[uid(0)], prev_pos = -K;
-  bool failed = false;
-  for(uint32_t t = 0; t < nb && !failed; ++t) {
-    const int32_t so = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs + t]] >> 32);
-    const int pos = fwd_align ? so : (int)(ql + so - K + 2);
-    const int sr_pos = pos < 0 ? -pos : pos;
-    const int new_bases = min(K, sr_pos - prev_pos);
-    while(sr_pos + K > cend + 1) {
-      if(cend >= sr_pos) {
-        if(cunitig >= nu - 1) { failed = true; break; }
-        const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
-        bases[2 * cunitig] += nbb;
-        bases[2 * cunitig + 1] += nbb;
+  __shared__ int32_t s_off[4][32];
+  __shared__ int32_t s_mers[4][kInfoSmem], s_bases[4][kInfoSmem];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for(uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < A.n; i += nwarps) {
+    const uint32_t ilen = A.info_len[i];
+    if(ilen == 0) continue;
+    const bool in_smem = ilen <= (uint32_t)kInfoSmem;
+    int32_t* mers  = in_smem ? s_mers[wib] : A.kinfo + A.info_off[i];
+    int32_t* bases = in_smem ? s_bases[wib] : A.binfo + A.info_off[i];
+    for(uint32_t j = lane; j < ilen; j += 32) { mers[j] = 0; bases[j] = 0; }
+    const uint32_t sr = A.sr[i];
+    const bool bwd = A.use_bwd[i];
+    const uint64_t u0 = A.unitig_off[sr];
+    const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
+    const uint32_t invalid_id = 0x7fffffffu;
+    auto uid = [&](uint32_t t) -> uint32_t {
+      if(t >= nu) return invalid_id;
+      return (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
+    };
+    const int K = (int)A.k, UK = (int)A.unitigs_k;
+    const uint64_t gs = A.chain_pos[i];
+    const uint32_t nb = (uint32_t)A.nb_mers[i];
+    const int64_t ql = A.ql[i];
+    uint32_t cunitig = 0;
+    int cend = A.unitig_len[uid(0)], prev_pos = -K;
+    bool failed = false, fwd_align = true;
+    __syncwarp();
+    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+      const uint32_t tl = t0 + lane;
+      if(tl < nb) s_off[wib][lane] = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs + tl]] >> 32);
+      __syncwarp();
+      if(lane == 0 && !failed) {
+        if(t0 == 0) fwd_align = s_off[wib][0] > 0;
+        const uint32_t m = min(32u, nb - t0);
+        for(uint32_t u = 0; u < m && !failed; ++u) {
+          const int32_t so = s_off[wib][u];
+          const int pos = fwd_align ? so : (int)(ql + so - K + 2);
+          const int sr_pos = pos < 0 ? -pos : pos;
+          const int new_bases = min(K, sr_pos - prev_pos);
+          while(sr_pos + K > cend + 1) {
+            if(cend >= sr_pos) {
+              if(cunitig >= nu - 1) { failed = true; break; }
+              const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
+              bases[2 * cunitig] += nbb;
+              bases[2 * cunitig + 1] += nbb;
+            }
+            const uint32_t id = uid(++cunitig);
+            if(id == invalid_id || id >= A.n_unitigs) { failed = true; break; }
+            cend += A.unitig_len[id] - UK + 1;
+          }
+          if(failed) break;
+          ++mers[2 * cunitig];
+          bases[2 * cunitig] += new_bases;
+          int cendi = cend;
+          for(uint32_t v = cunitig; v < nu - 1 && sr_pos + K > cendi - UK + 1; ++v) {
+            const int full_mer = sr_pos + UK > cendi + 1;
+            mers[2 * v + 1] += full_mer;
+            mers[2 * v + 2] += full_mer;
+            const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
+            bases[2 * v + 1] += nbb;
+            bases[2 * v + 2] += nbb;
+            const uint32_t id = uid(v + 1);
+            if(id != invalid_id && id < A.n_unitigs) cendi += A.unitig_len[id] - UK + 1;
+            else { failed = true; break; }
+          }
+          prev_pos = sr_pos;
+        }
       }
-      const uint32_t id = uid(++cunitig);
-      if(id == invalid_id || id >= A.n_unitigs) { failed = true; break; }
-      cend += A.unitig_len[id] - UK + 1;
+      __syncwarp();
     }
-    if(failed) break;
-    ++mers[2 * cunitig];
-    bases[2 * cunitig] += new_bases;
-    int cendi = cend;
-    for(uint32_t u = cunitig; u < nu - 1 && sr_pos + K > cendi - UK + 1; ++u) {
-      const int full_mer = sr_pos + UK > cendi + 1;
-      mers[2 * u + 1] += full_mer;
-      mers[2 * u + 2] += full_mer;
-      const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
-      bases[2 * u + 1] += nbb;
-      bases[2 * u + 2] += nbb;
-      const uint32_t id = uid(u + 1);
-      if(id != invalid_id && id < A.n_unitigs) cendi += A.unitig_len[id] - UK + 1;
-      else { failed = true; break; }
+    failed = __shfl_sync(MR_FULL_MASK, (int)failed, 0) != 0;
+    if(failed) { if(lane == 0) A.info_len[i] = 0; }     // the reference clears both vectors on error
+    else if(in_smem) {
+      int32_t* gm = A.kinfo + A.info_off[i]; int32_t* gb = A.binfo + A.info_off[i];
+      for(uint32_t j = lane; j < ilen; j += 32) { gm[j] = mers[j]; gb[j] = bases[j]; }
     }
-    prev_pos = sr_pos;
+    __syncwarp();
   }
-  if(failed) A.info_len[i] = 0;      // the reference clears both vectors on error
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -687,7 +712,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       I.unitig_ids = idx->unitig_ids.as<uint32_t>(); I.unitig_off = idx->unitig_off.as<uint64_t>();
       I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k; I.unitigs_k = p->unitigs_k;
       I.kinfo = ws.kinfo.as<int32_t>(); I.binfo = ws.binfo.as<int32_t>();
-      kmers_info_kernel<<<div_up(S, 128), 128, 0, st>>>(I);
+      kmers_info_kernel<<<(unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 16, (S + 3) / 4), 128, 0, st>>>(I);
       MR_LAUNCHED(ctx);
     }
     MR_TRY(ws.read_cursor.ensure(ctx, ((size_t)nreads + 1) * 4));
@@ -730,8 +755,11 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     auto rnd = [](uint64_t b) { return (b + 63) / 64 * 64; };
     uint64_t bytes = rnd(((uint64_t)nreads + 1) * 8) + 5 * rnd(Sc * 4) + 8 * rnd(Sc * 4) + 3 * rnd(Sc * 8) + rnd(Sc * 8) + 2 * rnd(Sc)
                      + 2 * rnd((info_total + 1) * 4) + (graph ? 2 * rnd(Sc) + 5 * rnd(Sc * 4) : 0);
-    if(!ws.pinned_pool.empty()) { res->host = ws.pinned_pool.back(); ws.pinned_pool.pop_back(); }
-    else res->host = new pinned_buf;
+    {
+      std::lock_guard<std::mutex> lock(ws.pool_mutex);
+      if(!ws.pinned_pool.empty()) { res->host = ws.pinned_pool.back(); ws.pinned_pool.pop_back(); }
+    }
+    if(!res->host) res->host = new pinned_buf;
     MR_TRY(res->host->ensure(ctx, bytes + 4096));
     char* cur = res->host->as<char>();
     auto pull = [&](const void* dsrc, uint64_t nbytes) -> const void* {
@@ -838,8 +866,12 @@ void mr_result_free(mr_result* r) {
   if(!r) return;
   cudaSetDevice(r->ctx->device);
   if(r->host) {
-    if(r->ctx->ws && r->ctx->ws->pinned_pool.size() < 4) r->ctx->ws->pinned_pool.push_back(r->host);
-    else delete r->host;
+    bool kept = false;
+    if(r->ctx->ws) {
+      std::lock_guard<std::mutex> lock(r->ctx->ws->pool_mutex);
+      if(r->ctx->ws->pinned_pool.size() < 4) { r->ctx->ws->pinned_pool.push_back(r->host); kept = true; }
+    }
+    if(!kept) delete r->host;
   }
   delete r;
 }

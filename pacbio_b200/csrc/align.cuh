@@ -3,6 +3,8 @@
 #include "index.cuh"
 #include "primitives.cuh"
 
+#include <mutex>
+
 constexpr int      kTile        = 1024;           // read positions per CTA in the seed / expand kernels
 constexpr int      kSeedThreads = 256;
 constexpr uint32_t kNone        = 0xffffffffu;
@@ -32,6 +34,7 @@ struct mr_workspace {
   dev_buf scan_scratch;
   prim::sort_scratch sort;
   std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
+  std::mutex pool_mutex;                    // mr_result_free may run on another host thread than mr_align_batch
   ~mr_workspace() { for(auto p : pinned_pool) delete p; }
 };
 

@@ -56,8 +56,9 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
                                                   uint16_t* sub, double a, double b, double C,
                                                   uint32_t& longest_out, uint32_t& best_out) {
   const unsigned lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
   uint32_t cnt = 0, longest = 0, best = 0, nsub = 0;
-  int32_t  fr_pb = 0, fr_sr = 0, fr_cpb = 0, fr_csr = 0;    // list front (array slot cnt - 1)
+  int32_t  fr_pb = 0, fr_sr = 0, fr_cpb = 0, fr_csr = 0;    // list front (array slot cnt - 1), same in every lane
   uint32_t fr_meta = 0;
   uint64_t next_pl = lane < N ? pay[lane] : 0;
   for(uint32_t base = 0; base < N; base += 32) {
@@ -65,19 +66,31 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
     const uint64_t pl = next_pl;
     if(base + 32 < N) next_pl = (il + 32 < N) ? pay[il + 32] : 0;      // prefetch the next 32 hits
     const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
-    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
+    const bool mine = il < N && ((sr_l < 0) == neg);
+    const unsigned mine_mask = __ballot_sync(MR_FULL_MASK, mine);
+    if(!mine_mask) continue;
+    // 32 hits at once: does each hit extend the hit just before it (same strand)?  Whenever that
+    // earlier hit sits at the list front when its successor is processed, the reference's walk stops
+    // on it immediately, so whole runs of such hits are appended in one step below.
+    const unsigned below = mine_mask & lt;
+    const int pred_lane = below ? 31 - __clz(below) : 0;
+    const int32_t ppb = __shfl_sync(MR_FULL_MASK, pb_l, pred_lane), psr = __shfl_sync(MR_FULL_MASK, sr_l, pred_lane);
+    const bool ext = mine && below && sr_l > psr && accept_mer(pb_l, sr_l, ppb, psr, a, b, C);
+    const unsigned ext_mask = __ballot_sync(MR_FULL_MASK, ext);
+    unsigned todo = mine_mask;
     while(todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint32_t i = base + src;
       const int32_t pb_i = __shfl_sync(MR_FULL_MASK, pb_l, src), sr_i = __shfl_sync(MR_FULL_MASK, sr_l, src);
-      if(TAPS) { if(lane == 0) sub[i] = (uint16_t)nsub; ++nsub; }
+      if(TAPS) { if(lane == 0) sub[i] = (uint16_t)nsub; }
+      ++nsub;
 
       int      found = -1, prev_pos = -1;
       uint32_t f_meta = 0, min_len = 0xffffffffu;
       int32_t  f_cpb = 0, f_csr = 0;
-      // Fast path: the list front (kept in registers, identical in every lane) is feasible.  Then the
-      // walk stops at position 0 without passing any entry, so the new element goes to the front.
+      // Fast path: the list front (kept in registers) is feasible: the walk stops at position 0
+      // without passing any entry, so the new element goes to the front.
       if(cnt != 0 && sr_i > fr_sr && accept_mer(pb_i, sr_i, fr_pb, fr_sr, a, b, C)) {
         found = 0; f_meta = fr_meta; f_cpb = fr_cpb; f_csr = fr_csr;
       } else
@@ -122,10 +135,40 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
         S.pb[s] = pb_i; S.sr[s] = sr_i; S.cpb[s] = cpb; S.csr[s] = csr; S.meta[s] = (e_len << 16) | i;
         S.pprev[i] = found >= 0 ? (uint16_t)(f_meta & 0xffff) : (uint16_t)0xffff;
       }
-      if(q == 0) { fr_pb = pb_i; fr_sr = sr_i; fr_cpb = cpb; fr_csr = csr; fr_meta = (e_len << 16) | i; }
       ++cnt;
-      __syncwarp();
       if(longest < e_len && accept_sequence(pb_i - cpb, sr_i - csr, a)) { longest = e_len; best = i; }
+      if(q != 0) { __syncwarp(); continue; }        // not at the front: its successors take the normal route
+      fr_pb = pb_i; fr_sr = sr_i; fr_cpb = cpb; fr_csr = csr; fr_meta = (e_len << 16) | i;
+
+      // Run: the hits right after this one that each extend their predecessor.  They are appended
+      // together: lane t of the run gets len + 1 + t, the same chain start, its predecessor as back pointer.
+      const unsigned stop_mask = todo & ~ext_mask;
+      const unsigned run = stop_mask ? (todo & ((1u << (__ffs(stop_mask) - 1)) - 1)) : todo;
+      if(run) {
+        const uint32_t r = __popc(run);
+        const bool inrun = (run >> lane) & 1;
+        const uint32_t t = __popc(run & lt);
+        const uint32_t my_len = e_len + 1 + t;
+        if(inrun) {
+          const uint32_t s = cnt + t;
+          S.pb[s] = pb_l; S.sr[s] = sr_l; S.cpb[s] = cpb; S.csr[s] = csr; S.meta[s] = (my_len << 16) | il;
+          S.pprev[il] = (uint16_t)(base + pred_lane);
+          if(TAPS) sub[il] = (uint16_t)(nsub + t);
+        }
+        // `longest` only moves up and len grows along the run: the last accepted element wins
+        const bool acc = inrun && my_len > longest && accept_sequence(pb_l - cpb, sr_l - csr, a);
+        const unsigned accm = __ballot_sync(MR_FULL_MASK, acc);
+        if(accm) {
+          const int hl = 31 - __clz(accm);
+          longest = e_len + 1 + __popc(run & ((1u << hl) - 1));
+          best = base + hl;
+        }
+        const int last = 31 - __clz(run);
+        fr_pb = __shfl_sync(MR_FULL_MASK, pb_l, last); fr_sr = __shfl_sync(MR_FULL_MASK, sr_l, last);
+        fr_meta = ((e_len + r) << 16) | (base + last);
+        cnt += r; nsub += r; todo &= ~run;
+      }
+      __syncwarp();
     }
   }
   longest_out = longest;

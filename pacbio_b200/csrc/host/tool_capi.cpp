@@ -85,7 +85,8 @@ const uint64_t* mrh_tool_batch_starts(void* p, uint64_t i, uint32_t* nreads) {
 }
 
 // One full pass over the loaded reads through the public path: mr_align_batch from host memory
-// (H2D inside), results back (D2H inside), text records formatted on `threads` host threads.
+// (H2D inside), results back (D2H inside), text records formatted on `threads` host threads while
+// the next batch is already on the GPU (same two-stage overlap as the command line tools).
 // out_path may be null/empty (text is produced and dropped).  Returns read bases processed, <0 on error.
 int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   tool* t = (tool*)p;
@@ -93,28 +94,41 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   if(out_path && *out_path) { out = fopen(out_path, "w"); if(!out) { t->error = "cannot open output"; return -1; } }
   t->last_text_bytes = t->last_d2h_bytes = t->last_h2d_bytes = t->last_coords = 0;
   t->last_lookups = t->last_hits = t->last_groups = 0;
-  std::string text;
-  try {
-    for(auto& b : t->batches) {
-      mr_result* r = nullptr;
-      const int rc = mr_align_batch(t->DS.ctx[0], t->DS.idx[0], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
-      if(rc != MR_OK) throw std::runtime_error(mr_last_error(t->DS.ctx[0]));
+  struct item { mrh::read_batch* b; mr_result* r; };
+  mrh::bounded_queue<item> q(2);
+  std::string error;
+  std::thread formatter([&]() {
+    item it;
+    std::string text;
+    while(q.pop(it)) {
       mr_result_view v;
-      mr_result_get(r, &v);
+      mr_result_get(it.r, &v);
       text.clear();
-      mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, text);
-      if(out) fwrite(text.data(), 1, text.size(), out);
+      try {
+        mrh::format_mega_reads_mt(v, *it.b, t->SR, t->U, t->G, threads, text);
+        if(out) fwrite(text.data(), 1, text.size(), out);
+      } catch(std::exception& e) { error = e.what(); }
       t->last_text_bytes += text.size();
-      t->last_h2d_bytes += b->bases.size() + (b->nreads() + 1) * 8ULL;
+      t->last_h2d_bytes += it.b->bases.size() + (it.b->nreads() + 1) * 8ULL;
       uint64_t info = 0;
       for(uint64_t i = 0; i < v.ncoords; ++i) info += v.info_len[i];
       t->last_d2h_bytes += (v.nreads + 1) * 8ULL + v.ncoords * (5 * 4 + 6 * 4 + 2 + 3 * 8 + 8 + 4 + 2 + 5 * 4) + info * 8;
       t->last_coords += v.ncoords;
       t->last_lookups += v.n_kmers_looked_up; t->last_hits += v.n_hits; t->last_groups += v.n_groups;
-      mr_result_free(r);
+      mr_result_free(it.r);
     }
-  } catch(std::exception& e) { t->error = e.what(); if(out) fclose(out); return -1; }
+  });
+  std::string align_error;
+  for(auto& b : t->batches) {
+    mr_result* r = nullptr;
+    const int rc = mr_align_batch(t->DS.ctx[0], t->DS.idx[0], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+    if(rc != MR_OK) { align_error = mr_last_error(t->DS.ctx[0]); break; }
+    q.push(item{ b.get(), r });
+  }
+  q.close();
+  formatter.join();
   if(out) fclose(out);
+  if(!align_error.empty() || !error.empty()) { t->error = align_error.empty() ? error : align_error; return -1; }
   return (int64_t)t->total_bases;
 }
 void mrh_tool_last_stats(void* p, uint64_t* out8) {

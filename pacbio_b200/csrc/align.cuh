@@ -79,8 +79,10 @@ struct chain_args {
   const uint32_t* unitig_ids; const uint64_t* unitig_off;
   survivors sv;
   uint2* tap_lens; uint32_t* tap_cf; uint32_t* tap_cb; uint32_t* tap_sub;
+  // filled by launch_chain: per-group verdict (chain length | fwd << 31) and the list of long chains
+  uint32_t* group_nb; uint32_t* long_list; uint32_t* long_count; uint32_t* long_cursor;
 };
-int launch_chain(mr_context* ctx, const chain_args& A, dev_buf& lists);
+int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);
 
 // graph.cu
 struct graph_args {

@@ -19,6 +19,8 @@
 
 namespace {
 
+constexpr uint32_t kThreadFinishMax = 192;    // chains up to this many hits are finished by a single thread
+
 __device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
   const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
   const double t1 = a * d2, t2 = a * d1;                   // mul then add, never fused (-fmad=false)
@@ -248,69 +250,43 @@ __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N
 }
 
 // ---------------------------------------------------------------------------------------------
-// coords of one group from its chain (warp-uniform; chain[t] = group-local hit index, in order)
+// coords of one group from its chain (chain[t] = group-local hit index, in chain order)
 // ---------------------------------------------------------------------------------------------
-template<typename ChainT>
-__device__ __forceinline__ void finish_group(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
-                                             uint32_t nb, const ChainT* chain, uint32_t* chain_global) {
-  const unsigned lane = threadIdx.x & 31;
+struct coords_acc {
+  // online least squares (x = super-read offset, y = read offset) + the consecutive/cover counters
+  double EX = 0, EY = 0, EXX = 0, EXY = 0, VX = 0, CXY = 0, NB = 0;
+  uint32_t pb_cons = 0, sr_cons = 0, pb_cover, sr_cover;
+  int32_t first_pb = 0, first_sr = 0, ppb = 0, psr = 0;
+  long n = 0;
+  __device__ __forceinline__ explicit coords_acc(uint32_t k) : pb_cover(k), sr_cover(k) { }
+  __device__ __forceinline__ void add(int32_t pb, int32_t so, uint32_t k, double rcp_next) {
+    if(n == 0) { first_pb = pb; first_sr = so; }
+    else {
+      const uint32_t pb_diff = (uint32_t)(pb - ppb), sr_diff = (uint32_t)(so - psr);
+      pb_cons += pb_diff == 1; pb_cover += min(k, pb_diff);
+      sr_cons += sr_diff == 1; sr_cover += min(k, sr_diff);
+    }
+    ppb = pb; psr = so;
+    const double x = (double)so, y = (double)pb;
+    ++n;
+    const double dn = (double)n;                       // rcp_next == RN(1 / n)
+    const double dX = x - EX;  EX += div_by_count(dX, dn, rcp_next);  const double ndX = x - EX;  VX += dX * ndX;
+    const double dY = y - EY;  EY += div_by_count(dY, dn, rcp_next);  const double ndY = y - EY;
+    const double dXX = x * x - EXX;  EXX += div_by_count(dXX, dn, rcp_next);
+    const double dXY = x * y - EXY;  EXY += div_by_count(dXY, dn, rcp_next);
+    CXY += dX * ndY;
+    const double t1 = dXY * ndX, t2 = dXX * ndY;
+    NB += t1 - t2;
+  }
+};
+
+// canonicalize + filters + survivor append; call from ONE thread per group
+__device__ __forceinline__ void publish_coords(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                               uint32_t nb, const coords_acc& c, double stretch, double offset, double avg_err) {
   const uint32_t k = A.iv.k;
-  const uint64_t* pay = A.pays + gs;
   const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
   const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
-  // online least squares, x = super-read offset, y = read offset, in chain order
-  double EX = 0, EY = 0, EXX = 0, EXY = 0, VX = 0, CXY = 0, NB = 0;
-  uint32_t pb_cons = 0, sr_cons = 0, pb_cover = k, sr_cover = k;
-  int32_t first_pb = 0, first_sr = 0, last_pb = 0, last_sr = 0, ppb = 0, psr = 0;
-  long n = 0;
-  for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
-    const uint32_t tl = t0 + lane;
-    uint64_t pl = 0;
-    if(tl < nb) pl = pay[chain[tl]];
-    const uint32_t m = min(32u, nb - t0);
-    for(uint32_t u = 0; u < m; ++u) {
-      const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
-      const int32_t pb = (int32_t)(uint32_t)p, so = (int32_t)(uint32_t)(p >> 32);
-      if(n == 0) { first_pb = pb; first_sr = so; }
-      else {
-        const uint32_t pb_diff = (uint32_t)(pb - ppb), sr_diff = (uint32_t)(so - psr);
-        pb_cons += pb_diff == 1; pb_cover += min(k, pb_diff);
-        sr_cons += sr_diff == 1; sr_cover += min(k, sr_diff);
-      }
-      ppb = pb; psr = so; last_pb = pb; last_sr = so;
-      const double x = (double)so, y = (double)pb;
-      ++n;
-      const double dn = (double)n;
-      const double rn_ = 1.0 / dn;                              // one true division per element
-      const double dX = x - EX;  EX += div_by_count(dX, dn, rn_);  const double ndX = x - EX;  VX += dX * ndX;
-      const double dY = y - EY;  EY += div_by_count(dY, dn, rn_);  const double ndY = y - EY;
-      const double dXX = x * x - EXX;  EXX += div_by_count(dXX, dn, rn_);
-      const double dXY = x * y - EXY;  EXY += div_by_count(dXY, dn, rn_);
-      CXY += dX * ndY;
-      const double t1 = dXY * ndX, t2 = dXX * ndY;
-      NB += t1 - t2;
-    }
-  }
-  double stretch, offset, avg_err;
-  if(n == 1) { stretch = 1.0; offset = EY - EX; avg_err = 0; }
-  else {
-    stretch = CXY / VX; offset = NB / VX;
-    double e = 0;
-    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
-      const uint32_t tl = t0 + lane;
-      uint64_t pl = 0;
-      if(tl < nb) pl = pay[chain[tl]];
-      const uint32_t m = min(32u, nb - t0);
-      for(uint32_t u = 0; u < m; ++u) {
-        const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
-        const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
-        const double prod = stretch * x;
-        e += fabs(prod + offset - y);
-      }
-    }
-    avg_err = e / (double)n;
-  }
-  int32_t rs = first_pb, re = last_pb + (int32_t)k - 1, qs = first_sr, qe = last_sr;
+  int32_t rs = c.first_pb, re = c.ppb + (int32_t)k - 1, qs = c.first_sr, qe = c.psr;
   bool rn = false;
   if(qs < 0) {
     if(A.forward) {
@@ -337,58 +313,123 @@ __device__ __forceinline__ void finish_group(const chain_args& A, uint64_t gs, u
     const double ie = fmax(1.0, fmin(drl, tq + offset));
     const int imp_len = (int)llabs(llrint(ie - is)) + 1;
     if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) return;
-    if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)pb_cover)) return;
+    if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)c.pb_cover)) return;
   }
-  // survivor: publish its chain for the kmers_info kernel and append the row
-  if((const void*)chain != (const void*)chain_global)
-    for(uint32_t t = lane; t < nb; t += 32) chain_global[t] = chain[t];
-  if(lane == 0) {
-    const bool use_bwd = A.forward && !fwd_align;
-    uint32_t ilen = 0;
-    if(A.unitigs_k && A.unitig_off) {
-      const uint64_t u0 = A.unitig_off[sr], u1 = A.unitig_off[sr + 1];
-      if(u1 > u0) {
-        const uint32_t first_id = (use_bwd ? A.unitig_ids[u1 - 1] : A.unitig_ids[u0]) >> 1;
-        if(first_id < A.n_unitigs) ilen = 2 * (uint32_t)(u1 - u0) - 1;
+  const bool use_bwd = A.forward && !fwd_align;
+  uint32_t ilen = 0;
+  if(A.unitigs_k && A.unitig_off) {
+    const uint64_t u0 = A.unitig_off[sr], u1 = A.unitig_off[sr + 1];
+    if(u1 > u0) {
+      const uint32_t first_id = (use_bwd ? A.unitig_ids[u1 - 1] : A.unitig_ids[u0]) >> 1;
+      if(first_id < A.n_unitigs) ilen = 2 * (uint32_t)(u1 - u0) - 1;
+    }
+  }
+  const survivors& sv = A.sv;
+  const unsigned long long slot = atomicAdd(sv.count, 1ULL);
+  if(slot < sv.cap) {
+    sv.rs[slot] = rs; sv.re[slot] = re; sv.qs[slot] = qs; sv.qe[slot] = qe; sv.nb_mers[slot] = (int32_t)nb;
+    sv.pb_cons[slot] = c.pb_cons; sv.sr_cons[slot] = c.sr_cons; sv.pb_cover[slot] = c.pb_cover; sv.sr_cover[slot] = c.sr_cover;
+    sv.ql[slot] = ql; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = ilen;
+    sv.rn[slot] = rn; sv.use_bwd[slot] = use_bwd;
+    sv.stretch[slot] = stretch; sv.offset[slot] = offset; sv.avg_err[slot] = avg_err;
+    sv.chain_pos[slot] = gs;
+    atomicAdd(sv.info_total, (unsigned long long)ilen);
+    atomicAdd(sv.read_cnt + read, 1u);
+  }
+}
+
+// long chains: one warp per group, the lanes fetch 32 hits (and 32 reciprocals) at a time and every
+// lane runs the same sequential recurrence on the broadcast values
+__device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                                  uint32_t nb) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t k = A.iv.k;
+  const uint64_t* pay = A.pays + gs;
+  const uint32_t* chain = A.cb.Lelt + gs;
+  coords_acc c(k);
+  for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+    const uint32_t tl = t0 + lane;
+    uint64_t pl = 0;
+    if(tl < nb) pl = pay[chain[tl]];
+    const double rl = 1.0 / (double)(tl + 1);
+    const uint32_t m = min(32u, nb - t0);
+    for(uint32_t u = 0; u < m; ++u) {
+      const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+      c.add((int32_t)(uint32_t)p, (int32_t)(uint32_t)(p >> 32), k, __shfl_sync(MR_FULL_MASK, rl, u));
+    }
+  }
+  double stretch, offset, avg_err;
+  if(c.n == 1) { stretch = 1.0; offset = c.EY - c.EX; avg_err = 0; }
+  else {
+    stretch = c.CXY / c.VX; offset = c.NB / c.VX;
+    double e = 0;
+    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
+      const uint32_t tl = t0 + lane;
+      uint64_t pl = 0;
+      if(tl < nb) pl = pay[chain[tl]];
+      const uint32_t m = min(32u, nb - t0);
+      for(uint32_t u = 0; u < m; ++u) {
+        const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
+        const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
+        const double prod = stretch * x;
+        e += fabs(prod + offset - y);
       }
     }
-    const survivors& sv = A.sv;
-    const unsigned long long slot = atomicAdd(sv.count, 1ULL);
-    if(slot < sv.cap) {
-      sv.rs[slot] = rs; sv.re[slot] = re; sv.qs[slot] = qs; sv.qe[slot] = qe; sv.nb_mers[slot] = (int32_t)nb;
-      sv.pb_cons[slot] = pb_cons; sv.sr_cons[slot] = sr_cons; sv.pb_cover[slot] = pb_cover; sv.sr_cover[slot] = sr_cover;
-      sv.ql[slot] = ql; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = ilen;
-      sv.rn[slot] = rn; sv.use_bwd[slot] = use_bwd;
-      sv.stretch[slot] = stretch; sv.offset[slot] = offset; sv.avg_err[slot] = avg_err;
-      sv.chain_pos[slot] = gs;
-      atomicAdd(sv.info_total, (unsigned long long)ilen);
-      atomicAdd(sv.read_cnt + read, 1u);
-    }
+    avg_err = e / (double)c.n;
   }
+  if(lane == 0) publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err);
+}
+
+// short chains: one THREAD per group -- 32 independent recurrences per warp instruction
+__device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                                    uint32_t nb) {
+  const uint32_t k = A.iv.k;
+  const uint64_t* pay = A.pays + gs;
+  const uint32_t* chain = A.cb.Lelt + gs;
+  coords_acc c(k);
+  uint64_t p = pay[chain[0]];
+  for(uint32_t t = 0; t < nb; ++t) {
+    const uint64_t cur = p;
+    if(t + 1 < nb) p = pay[chain[t + 1]];              // next hit in flight while this one is folded in
+    c.add((int32_t)(uint32_t)cur, (int32_t)(uint32_t)(cur >> 32), k, 1.0 / (double)(t + 1));
+  }
+  double stretch, offset, avg_err;
+  if(c.n == 1) { stretch = 1.0; offset = c.EY - c.EX; avg_err = 0; }
+  else {
+    stretch = c.CXY / c.VX; offset = c.NB / c.VX;
+    double e = 0;
+    for(uint32_t t = 0; t < nb; ++t) {
+      const uint64_t q = pay[chain[t]];
+      const double x = (double)(int32_t)(uint32_t)(q >> 32), y = (double)(int32_t)(uint32_t)q;
+      const double prod = stretch * x;
+      e += fabs(prod + offset - y);
+    }
+    avg_err = e / (double)c.n;
+  }
+  publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err);
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// bins groups by size; lists[c] holds the group ids of class c (0: <=64, 1: <=1024, 2: larger)
+// bins groups by size; list c holds the group ids of class c (0: <=64, 1: <=1024, 2: <=4096, 3: larger)
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
-                                                               uint32_t* __restrict__ list0, uint32_t* __restrict__ list1,
-                                                               uint32_t* __restrict__ list2, uint32_t* __restrict__ counts) {
+                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1;
   if(g < ngroups) {
     const uint64_t n = group_start[g + 1] - group_start[g];
-    cls = n <= 64 ? 0 : (n <= 1024 ? 1 : 2);
+    cls = n <= 64 ? 0 : (n <= 1024 ? 1 : (n <= 4096 ? 2 : 3));
   }
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-  for(int c = 0; c < 3; ++c) {
+  for(int c = 0; c < 4; ++c) {
     const unsigned m = __ballot_sync(MR_FULL_MASK, cls == c);
     if(!m) continue;
     unsigned base = 0;
     if(lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counts + c, __popc(m));
     base = __shfl_sync(MR_FULL_MASK, base, __ffs(m) - 1);
-    if(cls == c) (c == 0 ? list0 : (c == 1 ? list1 : list2))[base + __popc(m & lanemask_lt())] = (uint32_t)g;
+    if(cls == c) lists[(uint64_t)c * ngroups + base + __popc(m & lanemask_lt())] = (uint32_t)g;
   }
 }
 
@@ -409,8 +450,6 @@ __global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_arg
     const uint32_t g = list[w];
     const uint64_t gs = A.group_start[g];
     const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
-    const uint64_t key = A.keys[gs];
-    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
     uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
     chain_strand_smem<CAP, TAPS>(A.pays + gs, N, false, S, sub, A.a, A.b, A.C, len_f, best_f);
     __syncwarp();
@@ -435,7 +474,13 @@ __global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_arg
       for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = S.pprev[cur]; }
     }
     __syncwarp();
-    finish_group<uint32_t>(A, gs, read, sr, fwd_align, nb, chain, A.cb.Lelt + gs);
+    // publish the chain (group-local hit indices, in order) and the group's verdict; the coords are
+    // computed by finish_*_kernel at full occupancy
+    for(uint32_t t = lane; t < nb; t += 32) A.cb.Lelt[gs + t] = chain[t];
+    if(lane == 0) {
+      A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
+      if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
+    }
     __syncwarp();
   }
 }
@@ -453,8 +498,6 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
     const uint32_t g = list ? list[w] : w;
     const uint64_t gs = A.group_start[g];
     const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
-    const uint64_t key = A.keys[gs];
-    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
     uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
     chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub);
     __syncwarp();
@@ -479,8 +522,40 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
       for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
     }
     __syncwarp();
-    finish_group<uint32_t>(A, gs, read, sr, fwd_align, nb, chain, chain);
+    if(lane == 0) {
+      A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
+      if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
+    }
     __syncwarp();
+  }
+}
+
+// coords of every group whose chain has at most kThreadFinishMax hits: one thread per group
+__global__ void __launch_bounds__(128) finish_thread_kernel(chain_args A) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= A.ngroups) return;
+  const uint32_t v = A.group_nb[g];
+  const uint32_t nb = v & 0x7fffffffu;
+  if(nb == 0 || nb > kThreadFinishMax) return;
+  const uint64_t gs = A.group_start[g];
+  const uint64_t key = A.keys[gs];
+  finish_group_thread(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, nb);
+}
+
+// ... and of the long chains: one warp per group
+__global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t total = *A.long_count;
+  while(true) {
+    uint32_t w = 0;
+    if(lane == 0) w = atomicAdd(A.long_cursor, 1u);
+    w = __shfl_sync(MR_FULL_MASK, w, 0);
+    if(w >= total) break;
+    const uint32_t g = A.long_list[w];
+    const uint32_t v = A.group_nb[g];
+    const uint64_t gs = A.group_start[g];
+    const uint64_t key = A.keys[gs];
+    finish_group_warp(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
   }
 }
 
@@ -495,27 +570,35 @@ int launch_smem(mr_context* ctx, const chain_args& A, const uint32_t* list, cons
 
 } // namespace
 
-// lists: 3 x ngroups uint32 + 8 uint32 counters (counts[0..2], cursors[4..6])
-int launch_chain(mr_context* ctx, const chain_args& A, dev_buf& lists) {
+// scratch `lists`: 5 x ngroups uint32 (4 size classes + long-chain list), ngroups uint32 verdicts,
+// 16 uint32 counters (class counts 0..3, class cursors 4..7, long count 8, long cursor 9)
+int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(A.ngroups == 0) return MR_OK;
   if(A.ngroups >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "more than 2^32 (read, super-read) groups in one batch");
   const uint64_t G = A.ngroups;
-  MR_TRY(lists.ensure(ctx, (3 * G + 16) * sizeof(uint32_t)));
-  uint32_t* l0 = lists.as<uint32_t>(); uint32_t* l1 = l0 + G; uint32_t* l2 = l1 + G; uint32_t* ctr = l2 + G;
+  MR_TRY(lists.ensure(ctx, (6 * G + 16) * sizeof(uint32_t)));
+  uint32_t* cls = lists.as<uint32_t>();
+  uint32_t* ctr = cls + 6 * G;
+  A.long_list = cls + 4 * G; A.group_nb = cls + 5 * G; A.long_count = ctr + 8; A.long_cursor = ctr + 9;
   MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
-  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, l0, l1, l2, ctr);
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, cls, ctr);
   MR_LAUNCHED(ctx);
   const bool taps = A.tap_lens != nullptr;
-  // large groups first: they are the long poles, the small ones fill in behind them
-  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(A, l2, ctr + 2, ctr + 6);
+  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(A, cls + 3 * G, ctr + 3, ctr + 7);
   MR_LAUNCHED(ctx);
   if(taps) {
-    MR_TRY((launch_smem<1024, 4, true>(ctx, A, l1, ctr + 1, ctr + 5, 2)));
-    MR_TRY((launch_smem<64, 8, true>(ctx, A, l0, ctr + 0, ctr + 4, 8)));
+    MR_TRY((launch_smem<4096, 2, true>(ctx, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
+    MR_TRY((launch_smem<1024, 4, true>(ctx, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, true>(ctx, A, cls, ctr + 0, ctr + 4, 8)));
   } else {
-    MR_TRY((launch_smem<1024, 4, false>(ctx, A, l1, ctr + 1, ctr + 5, 2)));
-    MR_TRY((launch_smem<64, 8, false>(ctx, A, l0, ctr + 0, ctr + 4, 8)));
+    MR_TRY((launch_smem<4096, 2, false>(ctx, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
+    MR_TRY((launch_smem<1024, 4, false>(ctx, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, false>(ctx, A, cls, ctr + 0, ctr + 4, 8)));
   }
+  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A);
+  MR_LAUNCHED(ctx);
+  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A);
+  MR_LAUNCHED(ctx);
   return MR_OK;
 }
 

@@ -19,7 +19,8 @@
 
 namespace {
 
-constexpr uint32_t kThreadFinishMax = 192;    // chains up to this many hits are finished by a single thread
+constexpr uint32_t kThreadFinishMax = 192;        // chains up to this many hits: one thread each, group order
+constexpr uint32_t kThreadFinishLongMax = 8192;   // longer chains up to this: one thread each, from the long list
 
 __device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
   const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
@@ -530,20 +531,24 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
   }
 }
 
-// coords of every group whose chain has at most kThreadFinishMax hits: one thread per group
-__global__ void __launch_bounds__(128) finish_thread_kernel(chain_args A) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(g >= A.ngroups) return;
+// coords of every group whose chain length is in (lo, hi]: one thread per group.  With list == null
+// thread i takes group i, otherwise list entry i (the long chains: warps then hold 32 chains of
+// comparable length, the recurrence of each is latency bound, 32 of them share every instruction).
+__global__ void __launch_bounds__(128) finish_thread_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                             const uint32_t* __restrict__ list_count, uint32_t lo, uint32_t hi) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= (list ? (uint64_t)*list_count : A.ngroups)) return;
+  const uint64_t g = list ? list[i] : i;
   const uint32_t v = A.group_nb[g];
   const uint32_t nb = v & 0x7fffffffu;
-  if(nb == 0 || nb > kThreadFinishMax) return;
+  if(nb <= lo || nb > hi) return;
   const uint64_t gs = A.group_start[g];
   const uint64_t key = A.keys[gs];
   finish_group_thread(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, nb);
 }
 
-// ... and of the long chains: one warp per group
-__global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A) {
+// ... and of the very long chains: one warp per group
+__global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t lo) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t total = *A.long_count;
   while(true) {
@@ -553,6 +558,7 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A) {
     if(w >= total) break;
     const uint32_t g = A.long_list[w];
     const uint32_t v = A.group_nb[g];
+    if((v & 0x7fffffffu) <= lo) continue;
     const uint64_t gs = A.group_start[g];
     const uint64_t key = A.keys[gs];
     finish_group_warp(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
@@ -595,9 +601,11 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
     MR_TRY((launch_smem<1024, 4, false>(ctx, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
     MR_TRY((launch_smem<64, 8, false>(ctx, A, cls, ctr + 0, ctr + 4, 8)));
   }
-  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A);
+  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, kThreadFinishLongMax);
   MR_LAUNCHED(ctx);
-  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A);
+  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A, A.long_list, A.long_count, kThreadFinishMax, kThreadFinishLongMax);
+  MR_LAUNCHED(ctx);
+  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A, nullptr, nullptr, 0, kThreadFinishMax);
   MR_LAUNCHED(ctx);
   return MR_OK;
 }

@@ -242,6 +242,7 @@ def ours(args, w, files):
     H.mrh_tool_batch_starts.restype = api.u64p
     H.mrh_tool_batch_starts.argtypes = [C.c_void_p, C.c_uint64, api.u32p]
     H.mrh_tool_last_stats.argtypes = [C.c_void_p, api.u64p]
+    H.mrh_tool_stage_seconds.argtypes = [C.c_void_p, api.f64p, api.f64p]
     H.mrh_tool_error.restype = C.c_char_p
     H.mrh_tool_error.argtypes = [C.c_void_p]
     H.mrh_tool_destroy.argtypes = [C.c_void_p]
@@ -331,6 +332,8 @@ def ours(args, w, files):
     stats = (C.c_uint64 * 8)()
     H.mrh_tool_last_stats(tool, stats)
     e2e_value = args.gpus * total_bases * args.steps / e2e_s_max
+    st_align, st_format = C.c_double(), C.c_double()
+    H.mrh_tool_stage_seconds(tool, C.byref(st_align), C.byref(st_format))
 
     # ---- roofline of the dominant kernel (phase timers are CUDA events on the launching stream) ----------
     dom = max(phase, key=phase.get) if phase else None
@@ -384,6 +387,7 @@ def ours(args, w, files):
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
                         "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
                         "host_threads": host_threads, "text_bytes_per_step": int(stats[0]),
+                        "stage_busy_ms_last_step": {"mr_align_batch": 1e3 * st_align.value, "host_format": 1e3 * st_format.value},
                         "timing": "wall clock (includes host tiling/printing), max over ranks"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "index_build": {"seconds_total": index_s, "device_phases_s": index_timers,

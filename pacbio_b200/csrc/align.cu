@@ -345,96 +345,82 @@ struct info_args {
   uint64_t n;
   const uint64_t* chain_pos; const int32_t* nb_mers; const uint32_t* sr; const uint8_t* use_bwd; const uint32_t* ql;
   const uint64_t* info_off; uint32_t* info_len;
-  const uint32_t* chain; const uint64_t* pays;
+  const uint64_t* chain_pay;
   const uint32_t* unitig_ids; const uint64_t* unitig_off; const int32_t* unitig_len; uint32_t n_unitigs;
   uint32_t k, unitigs_k;
   int32_t* kinfo; int32_t* binfo;
 };
 
-// One warp per coords row: the lanes fetch 32 chain hits at a time (two dependent global loads
-// each, all in flight together), lane 0 runs the sequential add_mer state machine out of shared
-// memory.  Counters live in shared memory while the super-read has at most kInfoSmem/2 unitigs.
-constexpr int kInfoSmem = 128;
+// One THREAD per coords row walking its chain (pairs stored in chain order by the chaining kernels):
+// 32 rows share every instruction.  The two counters of the current unitig are kept in registers
+// and flushed when the walk moves on to the next unitig; the overlap counters are touched only
+// near unitig boundaries.
 __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
-  __shared__ int32_t s_off[4][32];
-  __shared__ int32_t s_mers[4][kInfoSmem], s_bases[4][kInfoSmem];
-  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for(uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < A.n; i += nwarps) {
-    const uint32_t ilen = A.info_len[i];
-    if(ilen == 0) continue;
-    const bool in_smem = ilen <= (uint32_t)kInfoSmem;
-    int32_t* mers  = in_smem ? s_mers[wib] : A.kinfo + A.info_off[i];
-    int32_t* bases = in_smem ? s_bases[wib] : A.binfo + A.info_off[i];
-    for(uint32_t j = lane; j < ilen; j += 32) { mers[j] = 0; bases[j] = 0; }
-    const uint32_t sr = A.sr[i];
-    const bool bwd = A.use_bwd[i];
-    const uint64_t u0 = A.unitig_off[sr];
-    const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
-    const uint32_t invalid_id = 0x7fffffffu;
-    auto uid = [&](uint32_t t) -> uint32_t {
-      if(t >= nu) return invalid_id;
-      return (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
-    };
-    const int K = (int)A.k, UK = (int)A.unitigs_k;
-    const uint64_t gs = A.chain_pos[i];
-    const uint32_t nb = (uint32_t)A.nb_mers[i];
-    const int64_t ql = A.ql[i];
-    uint32_t cunitig = 0;
-    int cend = A.unitig_len[uid(0)], prev_pos = -K;
-    bool failed = false, fwd_align = true;
-    __syncwarp();
-    for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
-      const uint32_t tl = t0 + lane;
-      if(tl < nb) s_off[wib][lane] = (int32_t)(uint32_t)(A.pays[gs + A.chain[gs + tl]] >> 32);
-      __syncwarp();
-      if(lane == 0 && !failed) {
-        if(t0 == 0) fwd_align = s_off[wib][0] > 0;
-        const uint32_t m = min(32u, nb - t0);
-        for(uint32_t u = 0; u < m && !failed; ++u) {
-          const int32_t so = s_off[wib][u];
-          const int pos = fwd_align ? so : (int)(ql + so - K + 2);
-          const int sr_pos = pos < 0 ? -pos : pos;
-          const int new_bases = min(K, sr_pos - prev_pos);
-          while(sr_pos + K > cend + 1) {
-            if(cend >= sr_pos) {
-              if(cunitig >= nu - 1) { failed = true; break; }
-              const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
-              bases[2 * cunitig] += nbb;
-              bases[2 * cunitig + 1] += nbb;
-            }
-            const uint32_t id = uid(++cunitig);
-            if(id == invalid_id || id >= A.n_unitigs) { failed = true; break; }
-            cend += A.unitig_len[id] - UK + 1;
-          }
-          if(failed) break;
-          ++mers[2 * cunitig];
-          bases[2 * cunitig] += new_bases;
-          int cendi = cend;
-          for(uint32_t v = cunitig; v < nu - 1 && sr_pos + K > cendi - UK + 1; ++v) {
-            const int full_mer = sr_pos + UK > cendi + 1;
-            mers[2 * v + 1] += full_mer;
-            mers[2 * v + 2] += full_mer;
-            const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
-            bases[2 * v + 1] += nbb;
-            bases[2 * v + 2] += nbb;
-            const uint32_t id = uid(v + 1);
-            if(id != invalid_id && id < A.n_unitigs) cendi += A.unitig_len[id] - UK + 1;
-            else { failed = true; break; }
-          }
-          prev_pos = sr_pos;
-        }
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= A.n) return;
+  const uint32_t ilen = A.info_len[i];
+  if(ilen == 0) return;
+  int32_t* mers  = A.kinfo + A.info_off[i];
+  int32_t* bases = A.binfo + A.info_off[i];
+  for(uint32_t j = 0; j < ilen; ++j) { mers[j] = 0; bases[j] = 0; }
+  const uint32_t sr = A.sr[i];
+  const bool bwd = A.use_bwd[i];
+  const uint64_t u0 = A.unitig_off[sr];
+  const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
+  auto ulen = [&](uint32_t t) -> int {               // -1: invalid id or past the end of the path
+    if(t >= nu) return -1;
+    const uint32_t id = (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
+    return id < A.n_unitigs ? A.unitig_len[id] : -1;
+  };
+  const int K = (int)A.k, UK = (int)A.unitigs_k;
+  const uint64_t* cp = A.chain_pay + A.chain_pos[i];
+  const uint32_t nb = (uint32_t)A.nb_mers[i];
+  const int64_t ql = A.ql[i];
+  uint32_t cunitig = 0;
+  int cend = ulen(0), prev_pos = -K;
+  int cur_mers = 0, cur_bases = 0;                    // pending additions to mers/bases[2 * cunitig]
+  bool failed = false;
+  const bool fwd_align = (int32_t)(uint32_t)(cp[0] >> 32) > 0;
+  uint64_t nxt = cp[0];
+  for(uint32_t t = 0; t < nb && !failed; ++t) {
+    const uint64_t p = nxt;
+    if(t + 1 < nb) nxt = cp[t + 1];
+    const int32_t so = (int32_t)(uint32_t)(p >> 32);
+    const int pos = fwd_align ? so : (int)(ql + so - K + 2);
+    const int sr_pos = pos < 0 ? -pos : pos;
+    const int new_bases = min(K, sr_pos - prev_pos);
+    while(sr_pos + K > cend + 1) {
+      if(cend >= sr_pos) {
+        if(cunitig >= nu - 1) { failed = true; break; }
+        const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
+        cur_bases += nbb;
+        bases[2 * cunitig + 1] += nbb;
       }
-      __syncwarp();
+      mers[2 * cunitig] += cur_mers; bases[2 * cunitig] += cur_bases;
+      cur_mers = 0; cur_bases = 0;
+      const int ul = ulen(++cunitig);
+      if(ul < 0) { failed = true; break; }
+      cend += ul - UK + 1;
     }
-    failed = __shfl_sync(MR_FULL_MASK, (int)failed, 0) != 0;
-    if(failed) { if(lane == 0) A.info_len[i] = 0; }     // the reference clears both vectors on error
-    else if(in_smem) {
-      int32_t* gm = A.kinfo + A.info_off[i]; int32_t* gb = A.binfo + A.info_off[i];
-      for(uint32_t j = lane; j < ilen; j += 32) { gm[j] = mers[j]; gb[j] = bases[j]; }
+    if(failed) break;
+    ++cur_mers;
+    cur_bases += new_bases;
+    int cendi = cend;
+    for(uint32_t v = cunitig; v < nu - 1 && sr_pos + K > cendi - UK + 1; ++v) {
+      const int full_mer = sr_pos + UK > cendi + 1;
+      mers[2 * v + 1] += full_mer;
+      mers[2 * v + 2] += full_mer;
+      const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
+      bases[2 * v + 1] += nbb;
+      bases[2 * v + 2] += nbb;
+      const int ul = ulen(v + 1);
+      if(ul >= 0) cendi += ul - UK + 1;
+      else { failed = true; break; }
     }
-    __syncwarp();
+    prev_pos = sr_pos;
   }
+  if(failed) A.info_len[i] = 0;      // the reference clears both vectors on error
+  else { mers[2 * cunitig] += cur_mers; bases[2 * cunitig] += cur_bases; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -648,7 +634,10 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     A.matching_mers = p->matching_mers; A.matching_bases = p->matching_bases; A.forward = p->forward;
     A.unitigs_k = idx->has_unitigs ? p->unitigs_k : 0; A.n_unitigs = idx->n_unitigs;
     A.unitig_ids = idx->unitig_ids.as<uint32_t>(); A.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
+    A.chain_pay = alt_key;                  // gpos is dead once group_start exists
     if(taps) {
+      MR_TRY(ws.chain_pay.ensure(ctx, (H + 2) * 8));
+      A.chain_pay = ws.chain_pay.as<uint64_t>();   // with taps on, alt_key holds the sub-list indices instead
       MR_TRY(ws.tap_lens.ensure(ctx, (G + 1) * 8));
       MR_TRY(ws.tap_cf.ensure(ctx, (H + 2) * 4)); MR_TRY(ws.tap_cb.ensure(ctx, (H + 2) * 4));
       A.tap_lens = ws.tap_lens.as<uint2>(); A.tap_cf = ws.tap_cf.as<uint32_t>(); A.tap_cb = ws.tap_cb.as<uint32_t>();
@@ -708,11 +697,11 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     if(info_total) {
       info_args I;
       I.n = S; I.chain_pos = A.sv.chain_pos; I.nb_mers = A.sv.nb_mers; I.sr = A.sv.sr; I.use_bwd = A.sv.use_bwd; I.ql = A.sv.ql;
-      I.info_off = sv_info_off; I.info_len = A.sv.info_len; I.chain = A.cb.Lelt; I.pays = spays;
+      I.info_off = sv_info_off; I.info_len = A.sv.info_len; I.chain_pay = A.chain_pay;
       I.unitig_ids = idx->unitig_ids.as<uint32_t>(); I.unitig_off = idx->unitig_off.as<uint64_t>();
       I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k; I.unitigs_k = p->unitigs_k;
       I.kinfo = ws.kinfo.as<int32_t>(); I.binfo = ws.binfo.as<int32_t>();
-      kmers_info_kernel<<<(unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 16, (S + 3) / 4), 128, 0, st>>>(I);
+      kmers_info_kernel<<<div_up(S, 128), 128, 0, st>>>(I);
       MR_LAUNCHED(ctx);
     }
     MR_TRY(ws.read_cursor.ensure(ctx, ((size_t)nreads + 1) * 4));

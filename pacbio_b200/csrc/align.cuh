@@ -30,7 +30,7 @@ struct mr_workspace {
   dev_buf read_cnt, read_coords, read_cursor, slot, order;
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
-  dev_buf tap_lens, tap_cf, tap_cb, group_lists;
+  dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay;
   dev_buf scan_scratch;
   prim::sort_scratch sort;
   std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
@@ -81,6 +81,7 @@ struct chain_args {
   uint2* tap_lens; uint32_t* tap_cf; uint32_t* tap_cb; uint32_t* tap_sub;
   // filled by launch_chain: per-group verdict (chain length | fwd << 31) and the list of long chains
   uint32_t* group_nb; uint32_t* long_list; uint32_t* long_count; uint32_t* long_cursor;
+  uint64_t* chain_pay;      // per group, at its slice: the chain's (pb, sr) pairs in chain order
 };
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);
 

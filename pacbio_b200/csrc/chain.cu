@@ -345,13 +345,12 @@ __device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t 
                                                   uint32_t nb) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t k = A.iv.k;
-  const uint64_t* pay = A.pays + gs;
-  const uint32_t* chain = A.cb.Lelt + gs;
+  const uint64_t* cp = A.chain_pay + gs;          // the chain's (pb, sr) pairs, in chain order
   coords_acc c(k);
   for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
     const uint32_t tl = t0 + lane;
     uint64_t pl = 0;
-    if(tl < nb) pl = pay[chain[tl]];
+    if(tl < nb) pl = cp[tl];
     const double rl = 1.0 / (double)(tl + 1);
     const uint32_t m = min(32u, nb - t0);
     for(uint32_t u = 0; u < m; ++u) {
@@ -367,7 +366,7 @@ __device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t 
     for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
       const uint32_t tl = t0 + lane;
       uint64_t pl = 0;
-      if(tl < nb) pl = pay[chain[tl]];
+      if(tl < nb) pl = cp[tl];
       const uint32_t m = min(32u, nb - t0);
       for(uint32_t u = 0; u < m; ++u) {
         const uint64_t p = __shfl_sync(MR_FULL_MASK, pl, u);
@@ -381,18 +380,25 @@ __device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t 
   if(lane == 0) publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err);
 }
 
-// short chains: one THREAD per group -- 32 independent recurrences per warp instruction
+// one THREAD per group: 32 independent recurrences per warp instruction.  The chain's pairs are read
+// four at a time, the next four already in flight while the current ones are folded in.
 __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
                                                     uint32_t nb) {
   const uint32_t k = A.iv.k;
-  const uint64_t* pay = A.pays + gs;
-  const uint32_t* chain = A.cb.Lelt + gs;
+  const uint64_t* cp = A.chain_pay + gs;
   coords_acc c(k);
-  uint64_t p = pay[chain[0]];
-  for(uint32_t t = 0; t < nb; ++t) {
-    const uint64_t cur = p;
-    if(t + 1 < nb) p = pay[chain[t + 1]];              // next hit in flight while this one is folded in
-    c.add((int32_t)(uint32_t)cur, (int32_t)(uint32_t)(cur >> 32), k, 1.0 / (double)(t + 1));
+  uint64_t q[4];
+#pragma unroll
+  for(int j = 0; j < 4; ++j) q[j] = (uint32_t)j < nb ? cp[j] : 0;
+  for(uint32_t t0 = 0; t0 < nb; t0 += 4) {
+    uint64_t nq[4];
+#pragma unroll
+    for(int j = 0; j < 4; ++j) nq[j] = t0 + 4 + j < nb ? cp[t0 + 4 + j] : 0;
+#pragma unroll
+    for(int j = 0; j < 4; ++j)
+      if(t0 + j < nb) c.add((int32_t)(uint32_t)q[j], (int32_t)(uint32_t)(q[j] >> 32), k, 1.0 / (double)(t0 + j + 1));
+#pragma unroll
+    for(int j = 0; j < 4; ++j) q[j] = nq[j];
   }
   double stretch, offset, avg_err;
   if(c.n == 1) { stretch = 1.0; offset = c.EY - c.EX; avg_err = 0; }
@@ -400,8 +406,8 @@ __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_
     stretch = c.CXY / c.VX; offset = c.NB / c.VX;
     double e = 0;
     for(uint32_t t = 0; t < nb; ++t) {
-      const uint64_t q = pay[chain[t]];
-      const double x = (double)(int32_t)(uint32_t)(q >> 32), y = (double)(int32_t)(uint32_t)q;
+      const uint64_t p = cp[t];
+      const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
       const double prod = stretch * x;
       e += fabs(prod + offset - y);
     }
@@ -414,13 +420,24 @@ __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_
 // kernels
 // ---------------------------------------------------------------------------------------------
 // bins groups by size; list c holds the group ids of class c (0: <=64, 1: <=1024, 2: <=4096, 3: larger)
+// Single-hit groups (most groups: spurious k-mer matches) need no chaining at all: their chain is
+// hit 0, which this kernel records directly.
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
+                                                               const uint64_t* __restrict__ pays, uint64_t* __restrict__ chain_pay,
+                                                               uint32_t* __restrict__ group_nb, bool singles_here,
                                                                uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1;
   if(g < ngroups) {
-    const uint64_t n = group_start[g + 1] - group_start[g];
+    const uint64_t gs = group_start[g];
+    const uint64_t n = group_start[g + 1] - gs;
     cls = n <= 64 ? 0 : (n <= 1024 ? 1 : (n <= 4096 ? 2 : 3));
+    if(n == 1 && singles_here) {
+      cls = -1;
+      const uint64_t p = pays[gs];
+      chain_pay[gs] = p;
+      group_nb[g] = 1u | ((int32_t)(uint32_t)(p >> 32) > 0 ? 0x80000000u : 0u);
+    }
   }
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll
@@ -475,9 +492,9 @@ __global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_arg
       for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = S.pprev[cur]; }
     }
     __syncwarp();
-    // publish the chain (group-local hit indices, in order) and the group's verdict; the coords are
+    // publish the chain's (pb, sr) pairs in chain order and the group's verdict; the coords are
     // computed by finish_*_kernel at full occupancy
-    for(uint32_t t = lane; t < nb; t += 32) A.cb.Lelt[gs + t] = chain[t];
+    for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + t] = A.pays[gs + chain[t]];
     if(lane == 0) {
       A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
       if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
@@ -523,6 +540,7 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
       for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
     }
     __syncwarp();
+    for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + t] = A.pays[gs + chain[t]];
     if(lane == 0) {
       A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
       if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
@@ -587,7 +605,8 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   uint32_t* ctr = cls + 6 * G;
   A.long_list = cls + 4 * G; A.group_nb = cls + 5 * G; A.long_count = ctr + 8; A.long_cursor = ctr + 9;
   MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
-  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, cls, ctr);
+  // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr, cls, ctr);
   MR_LAUNCHED(ctx);
   const bool taps = A.tap_lens != nullptr;
   chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(A, cls + 3 * G, ctr + 3, ctr + 7);

@@ -192,6 +192,15 @@ bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_rea
 // mega-reads from the device's graph rows
 // ================================================================================================
 namespace {
+struct revcomp_table_t {
+  char t[256];
+  revcomp_table_t() {
+    for(int i = 0; i < 256; ++i) t[i] = 'N';
+    t['a'] = t['A'] = 'T'; t['c'] = t['C'] = 'G'; t['g'] = t['G'] = 'C'; t['t'] = t['T'] = 'A';
+  }
+};
+const revcomp_table_t revcomp_table;
+
 struct mega_read {
   int    start_node, end_node, start_unitig, start_offset, end_offset, nb_unitigs;
   double imp_s, imp_e, tiling_start, tiling_end, density;
@@ -419,17 +428,8 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
             const size_t old = out.size();
             out.resize(old + s.size() - skip);
             char* w = &out[old];
-            for(size_t t = skip; t < s.size(); ++t) {
-              char ch;
-              switch(s[s.size() - 1 - t]) {
-              case 'a': case 'A': ch = 'T'; break;
-              case 'c': case 'C': ch = 'G'; break;
-              case 'g': case 'G': ch = 'C'; break;
-              case 't': case 'T': ch = 'A'; break;
-              default: ch = 'N';
-              }
-              *w++ = ch;
-            }
+            const char* r = s.data() + s.size() - 1 - skip;           // rev_comp_ of super_read_name.cc:106-114
+            for(size_t t = skip; t < s.size(); ++t) *w++ = revcomp_table.t[(unsigned char)*r--];
           } else {
             out.append(s, skip, std::string::npos);
           }
@@ -441,12 +441,10 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
 }
 
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
-                          const graph_options& o, unsigned threads, std::string& out) {
+                          const graph_options& o, unsigned threads, std::vector<std::string>& parts) {
   const uint32_t nreads = v.nreads;
   threads = std::max(1u, std::min(threads, nreads / 64 + 1));
-  if(threads == 1) { format_mega_reads(v, batch, 0, nreads, sr, u, o, out); return; }
-  std::vector<std::string> parts(threads);
-  std::vector<std::thread> th;
+  parts.resize(threads);
   // split by coords rows so that the work is balanced
   std::vector<uint32_t> cut(threads + 1, nreads);
   cut[0] = 0;
@@ -456,13 +454,20 @@ void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, cons
     if(cut[t] > nreads) cut[t] = nreads;
     if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
   }
-  for(unsigned t = 0; t < threads; ++t)
-    th.emplace_back([&, t]() { format_mega_reads(v, batch, cut[t], cut[t + 1], sr, u, o, parts[t]); });
+  auto work = [&](unsigned t) {
+    std::string& out = parts[t];
+    out.clear();
+    // a mega-read line carries its sequence: about 1.3 output bytes per read base on typical data;
+    // reserving up front keeps the appends from reallocating (and copying) the growing buffer
+    const uint64_t bases = batch.start[cut[t + 1]] - batch.start[cut[t]];
+    const size_t want = u.seq.empty() ? (size_t)(bases / 16 + 4096) : (size_t)(bases + bases / 2 + 4096);
+    if(out.capacity() < want) out.reserve(want);
+    format_mega_reads(v, batch, cut[t], cut[t + 1], sr, u, o, out);
+  };
+  if(threads == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for(unsigned t = 0; t < threads; ++t) th.emplace_back(work, t);
   for(auto& x : th) x.join();
-  size_t total = out.size();
-  for(const auto& p : parts) total += p.size();
-  out.reserve(total);
-  for(const auto& p : parts) out += p;
 }
 
 // default ostream formatting of a double: "%g" with 6 significant digits (jf_aligner.cc:58)

@@ -81,9 +81,10 @@ struct graph_options {
 // overlap_graph.hpp:198-262): best terminal node per component, tiling, one line per mega-read.
 void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
                        const super_reads& sr, const unitigs& u, const graph_options& o, std::string& out);
-// same, fanned out over `threads` host threads, output in read order
+// same, fanned out over `threads` host threads; parts[0], parts[1], ... concatenated are the records
+// in read order (kept apart so that nobody has to copy hundreds of megabytes of text once more)
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
-                          const graph_options& o, unsigned threads, std::string& out);
+                          const graph_options& o, unsigned threads, std::vector<std::string>& parts);
 
 // jf_aligner coords records (jf_aligner.cc:41-70)
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,

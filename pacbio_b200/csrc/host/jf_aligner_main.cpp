@@ -106,8 +106,9 @@ int main(int argc, char* argv[]) {
       fputs(" Qname\n", out);
     }
     mrh::run_pipeline(DS, pacbio, P,
-      [&](const mr_result_view& v, const mrh::read_batch& b, std::string& text) {
-        mrh::format_coords(v, b, 0, v.nreads, SR, compact, !zero_match, text);
+      [&](const mr_result_view& v, const mrh::read_batch& b, std::vector<std::string>& parts) {
+        parts.resize(1);
+        mrh::format_coords(v, b, 0, v.nreads, SR, compact, !zero_match, parts[0]);
       }, out);
     fclose(out);
   } catch(std::exception& e) {

@@ -96,13 +96,14 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
 
   std::thread formatter([&]() {
     job j;
-    std::string text;
+    std::vector<std::string> parts;
     while(to_format.pop(j)) {
       mr_result_view v;
       mr_result_get(j.result, &v);
-      text.clear();
-      try { format(v, *j.batch, text); } catch(std::exception& e) { fail(e.what()); }
-      if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
+      for(auto& p : parts) p.clear();
+      try { format(v, *j.batch, parts); } catch(std::exception& e) { fail(e.what()); }
+      for(const auto& text : parts)
+        if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
       mr_result_free(j.result);
     }
   });

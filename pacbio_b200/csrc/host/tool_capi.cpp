@@ -19,6 +19,7 @@ struct tool {
   std::string error;
   uint64_t last_text_bytes = 0, last_d2h_bytes = 0, last_h2d_bytes = 0, last_coords = 0;
   uint64_t last_lookups = 0, last_hits = 0, last_groups = 0;
+  double   last_align_s = 0, last_format_s = 0;       // busy time of the two pipeline stages
 };
 }
 
@@ -94,21 +95,24 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   if(out_path && *out_path) { out = fopen(out_path, "w"); if(!out) { t->error = "cannot open output"; return -1; } }
   t->last_text_bytes = t->last_d2h_bytes = t->last_h2d_bytes = t->last_coords = 0;
   t->last_lookups = t->last_hits = t->last_groups = 0;
+  t->last_align_s = t->last_format_s = 0;
   struct item { mrh::read_batch* b; mr_result* r; };
   mrh::bounded_queue<item> q(2);
   std::string error;
   std::thread formatter([&]() {
     item it;
-    std::string text;
+    std::vector<std::string> parts;
     while(q.pop(it)) {
+      const auto f0 = std::chrono::steady_clock::now();
       mr_result_view v;
       mr_result_get(it.r, &v);
-      text.clear();
       try {
-        mrh::format_mega_reads_mt(v, *it.b, t->SR, t->U, t->G, threads, text);
-        if(out) fwrite(text.data(), 1, text.size(), out);
+        mrh::format_mega_reads_mt(v, *it.b, t->SR, t->U, t->G, threads, parts);
+        for(const auto& text : parts) {
+          if(out) fwrite(text.data(), 1, text.size(), out);
+          t->last_text_bytes += text.size();
+        }
       } catch(std::exception& e) { error = e.what(); }
-      t->last_text_bytes += text.size();
       t->last_h2d_bytes += it.b->bases.size() + (it.b->nreads() + 1) * 8ULL;
       uint64_t info = 0;
       for(uint64_t i = 0; i < v.ncoords; ++i) info += v.info_len[i];
@@ -116,12 +120,15 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
       t->last_coords += v.ncoords;
       t->last_lookups += v.n_kmers_looked_up; t->last_hits += v.n_hits; t->last_groups += v.n_groups;
       mr_result_free(it.r);
+      t->last_format_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
     }
   });
   std::string align_error;
   for(auto& b : t->batches) {
     mr_result* r = nullptr;
+    const auto a0 = std::chrono::steady_clock::now();
     const int rc = mr_align_batch(t->DS.ctx[0], t->DS.idx[0], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+    t->last_align_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
     if(rc != MR_OK) { align_error = mr_last_error(t->DS.ctx[0]); break; }
     q.push(item{ b.get(), r });
   }
@@ -130,6 +137,9 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   if(out) fclose(out);
   if(!align_error.empty() || !error.empty()) { t->error = align_error.empty() ? error : align_error; return -1; }
   return (int64_t)t->total_bases;
+}
+void mrh_tool_stage_seconds(void* p, double* align_s, double* format_s) {
+  tool* t = (tool*)p; *align_s = t->last_align_s; *format_s = t->last_format_s;
 }
 void mrh_tool_last_stats(void* p, uint64_t* out8) {
   tool* t = (tool*)p;

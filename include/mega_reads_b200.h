@@ -148,6 +148,7 @@ typedef struct mr_result_view {
   const int32_t  *component;        /* union-find root, row offset inside the read */
   /* work counters of the batch, for roofline arithmetic */
   uint64_t n_kmers_looked_up;       /* k-mers that reached the suffix-array lookup (x2 strands) */
+  uint64_t n_tail_entries;          /* suffix-array tail entries those lookups read (4 bytes each) */
   uint64_t n_hits;                  /* hits expanded into (read, super-read) lists */
   uint64_t n_groups;                /* (read, super-read) pairs chained */
 } mr_result_view;

@@ -45,7 +45,8 @@ class ResultView(C.Structure):
                 ("info_off", u64p), ("info_len", u32p), ("kmers_info", i32p), ("bases_info", i32p),
                 ("start_node", u8p), ("end_node", u8p),
                 ("lstart", i32p), ("lprev", i32p), ("lpath", i32p), ("lunitigs", i32p), ("component", i32p),
-                ("n_kmers_looked_up", C.c_uint64), ("n_hits", C.c_uint64), ("n_groups", C.c_uint64)]
+                ("n_kmers_looked_up", C.c_uint64), ("n_tail_entries", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_groups", C.c_uint64)]
 
 
 _lib = None

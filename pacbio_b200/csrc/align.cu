@@ -111,16 +111,17 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
                                                                     uint4* __restrict__ rec, uint32_t* __restrict__ size,
-                                                                    unsigned long long* __restrict__ n_lookups) {
+                                                                    unsigned long long* __restrict__ n_lookups,
+                                                                    unsigned long long* __restrict__ n_tails) {
   __shared__ uint8_t  codes[kTile + 64];
   __shared__ uint64_t sw[8];
-  __shared__ uint32_t looked;
+  __shared__ uint32_t looked, scanned;
   const uint32_t k = iv.k;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
-  if(threadIdx.x == 0) looked = 0;
+  if(threadIdx.x == 0) { looked = 0; scanned = 0; }
   tile_kmers t;
   enumerate_tile(bases, rs, rlen, tpos, k, codes, t);
 
@@ -146,12 +147,20 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
   for(int j = 0; j < 4; ++j) {
     if(keep[j]) {
       const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
-      c0[2 * j] = __ldg(iv.counts + pm);     c1[2 * j] = __ldg(iv.counts + pm + 1);
-      c0[2 * j + 1] = __ldg(iv.counts + pr); c1[2 * j + 1] = __ldg(iv.counts + pr + 1);
+      load_count_pair(iv.counts, pm, c0[2 * j], c1[2 * j]);
+      load_count_pair(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1]);
     }
   }
   const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
-  uint32_t nlook = 0;
+  // stage 2: the first tail of every non-empty bucket, again issued together -- most buckets hold one
+  // or two entries, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
+  uint32_t first[8];
+#pragma unroll
+  for(int q = 0; q < 8; ++q) {
+    first[q] = 0;
+    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = __ldg(iv.tails + c0[q]);
+  }
+  uint32_t nlook = 0, ntail = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
@@ -166,11 +175,13 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
         const uint32_t a0 = c0[2 * j + s], a1 = c1[2 * j + s];
         idx[s] = 0; nb[s] = 0;
         if(a0 != a1) {
+          ntail += a1 - a0 <= 32 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
           const uint32_t tt = (uint32_t)mer & tmask;
           uint32_t lo, hi;
           if(a1 - a0 <= 32) {
-            uint32_t less = 0, leq = 0;
-            for(uint32_t i = a0; i < a1; ++i) { const uint32_t v = __ldg(iv.tails + i); less += v < tt; leq += v <= tt; }
+            const uint32_t v0 = first[2 * j + s];
+            uint32_t less = v0 < tt, leq = v0 <= tt;
+            for(uint32_t i = a0 + 1; i < a1; ++i) { const uint32_t v = __ldg(iv.tails + i); less += v < tt; leq += v <= tt; }
             lo = a0 + less; hi = a0 + leq;
           } else {
             uint32_t a = a0, b = a1;
@@ -194,8 +205,9 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
     if(pos < rlen) { rec[g0 + j] = out; size[g0 + j] = sz; }
   }
   if(nlook) atomicAdd(&looked, nlook);
+  if(ntail) atomicAdd(&scanned, ntail);
   __syncthreads();
-  if(threadIdx.x == 0 && looked) atomicAdd(n_lookups, (unsigned long long)looked);
+  if(threadIdx.x == 0 && looked) { atomicAdd(n_lookups, (unsigned long long)looked); atomicAdd(n_tails, (unsigned long long)scanned); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,7 +563,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   uint64_t h_ctr[16] = { 0 };
 
   // ---- seeds + lookups ----------------------------------------------------------------------------
-  timer.begin("seed lookup");
+  timer.begin("seed prepass");
   if(ntiles) {
     MR_CUDA(ctx, cudaMemsetAsync(ws.tile_tbase.p, 0, (size_t)ntiles * 4, st));
     if(k <= 17) {
@@ -562,9 +574,10 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                              ws.tile_tbase.as<uint32_t>());
       MR_LAUNCHED(ctx);
     }
+    timer.next("seed lookup");
     seed_lookup_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                                       ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                                      ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0);
+                                                      ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
     MR_LAUNCHED(ctx);
     timer.next("count threshold");
     uint32_t nbits = 32;
@@ -576,10 +589,11 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   timer.next("hit expansion");
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.size.as<uint32_t>() }, T, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t H = h_ctr[1];
   res->view.n_kmers_looked_up = h_ctr[0];
+  res->view.n_tail_entries = h_ctr[6];
   if(H >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 hits in one batch; use smaller batches");
 
   uint64_t G = 0, S = 0, cap = 0;

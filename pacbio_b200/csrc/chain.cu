@@ -20,7 +20,7 @@
 namespace {
 
 constexpr uint32_t kThreadFinishMax = 192;        // chains up to this many hits: one thread each, group order
-constexpr uint32_t kThreadFinishLongMax = 8192;   // longer chains up to this: one thread each, from the long list
+constexpr uint32_t kThreadFinishLongMax = 1536;   // longer chains up to this: one thread each, from the long list
 
 __device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
   const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
@@ -584,10 +584,10 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t
 }
 
 template<int CAP, int WARPS, bool TAPS>
-int launch_smem(mr_context* ctx, const chain_args& A, const uint32_t* list, const uint32_t* count, uint32_t* cursor, int blocks_per_sm) {
+int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, const uint32_t* list, const uint32_t* count, uint32_t* cursor, int blocks_per_sm) {
   const size_t smem = sizeof(warp_store<CAP>) * WARPS + (TAPS ? (size_t)WARPS * CAP * sizeof(uint16_t) : 0);
   MR_CUDA(ctx, cudaFuncSetAttribute(chain_coords_smem_kernel<CAP, WARPS, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chain_coords_smem_kernel<CAP, WARPS, TAPS><<<ctx->sm_count * blocks_per_sm, WARPS * 32, smem, ctx->stream>>>(A, list, count, cursor);
+  chain_coords_smem_kernel<CAP, WARPS, TAPS><<<ctx->sm_count * blocks_per_sm, WARPS * 32, smem, st>>>(A, list, count, cursor);
   MR_LAUNCHED(ctx);
   return MR_OK;
 }
@@ -609,23 +609,38 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr, cls, ctr);
   MR_LAUNCHED(ctx);
   const bool taps = A.tap_lens != nullptr;
-  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(A, cls + 3 * G, ctr + 3, ctr + 7);
+  // The big-group tiers have few, long, latency-bound groups; they run on a side stream next to the
+  // mid/small tiers.  Likewise the three finishing kernels (independent groups) run side by side.
+  cudaStream_t s0 = ctx->stream, s1 = ctx->aux[0], s2 = ctx->aux[1];
+  MR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s0));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev[0], 0));
+  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, s1>>>(A, cls + 3 * G, ctr + 3, ctr + 7);
   MR_LAUNCHED(ctx);
   if(taps) {
-    MR_TRY((launch_smem<4096, 2, true>(ctx, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
-    MR_TRY((launch_smem<1024, 4, true>(ctx, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
-    MR_TRY((launch_smem<64, 8, true>(ctx, A, cls, ctr + 0, ctr + 4, 8)));
+    MR_TRY((launch_smem<4096, 2, true>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
+    MR_TRY((launch_smem<1024, 4, true>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, true>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
   } else {
-    MR_TRY((launch_smem<4096, 2, false>(ctx, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
-    MR_TRY((launch_smem<1024, 4, false>(ctx, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
-    MR_TRY((launch_smem<64, 8, false>(ctx, A, cls, ctr + 0, ctr + 4, 8)));
+    MR_TRY((launch_smem<4096, 2, false>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
+    MR_TRY((launch_smem<1024, 4, false>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
+    MR_TRY((launch_smem<64, 8, false>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
   }
-  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, kThreadFinishLongMax);
+  // all strands done -> finishing kernels on three streams
+  MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[1], 0));
+  MR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s0));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev[2], 0));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev[2], 0));
+  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, s1>>>(A, kThreadFinishLongMax);
   MR_LAUNCHED(ctx);
-  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A, A.long_list, A.long_count, kThreadFinishMax, kThreadFinishLongMax);
+  finish_thread_kernel<<<div_up(G, 128), 128, 0, s2>>>(A, A.long_list, A.long_count, kThreadFinishMax, kThreadFinishLongMax);
   MR_LAUNCHED(ctx);
-  finish_thread_kernel<<<div_up(G, 128), 128, 0, ctx->stream>>>(A, nullptr, nullptr, 0, kThreadFinishMax);
+  finish_thread_kernel<<<div_up(G, 128), 128, 0, s0>>>(A, nullptr, nullptr, 0, kThreadFinishMax);
   MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
+  MR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s2));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[1], 0));
+  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[3], 0));
   return MR_OK;
 }
 

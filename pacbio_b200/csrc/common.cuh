@@ -21,6 +21,8 @@ struct mr_context {
   mr_workspace* ws = nullptr;          // scratch reused across batches (align.cu)
   int          device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[2] = { nullptr, nullptr };   // side streams for kernels that may overlap (chain tiers)
+  cudaEvent_t  ev[4] = { nullptr, nullptr, nullptr, nullptr };
   std::string  err;
   uint64_t     launches = 0;
   bool         keep_taps = false;

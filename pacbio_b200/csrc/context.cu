@@ -33,6 +33,8 @@ int mr_context_create(int device, mr_context** out) {
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if(e != cudaSuccess) { g_mr_create_error = cudaGetErrorString(e); return MR_ECUDA; }
+  for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+  for(auto& v : ctx->ev) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
   *out = ctx.release();
   return MR_OK;
 }
@@ -42,6 +44,8 @@ void mr_context_destroy(mr_context* ctx) {
   cudaSetDevice(ctx->device);
   if(ctx->stream) cudaStreamSynchronize(ctx->stream);
   if(ctx->ws) mr_workspace_free(ctx->ws);
+  for(auto& a : ctx->aux) if(a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+  for(auto& v : ctx->ev) if(v) cudaEventDestroy(v);
   if(ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

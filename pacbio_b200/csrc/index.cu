@@ -183,7 +183,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     const uint64_t* keys = in_first ? k0.as<uint64_t>() : k1.as<uint64_t>();
     dev_buf& vres = in_first ? v0 : v1;
     MR_TRY(idx->tails.ensure(ctx, ((size_t)nsa + 64) * sizeof(uint32_t)));
-    MR_TRY(idx->counts.ensure(ctx, ((size_t)nprefix + 2) * sizeof(uint32_t)));
+    MR_TRY(idx->counts.ensure(ctx, ((size_t)nprefix + 8) * sizeof(uint32_t)));   // read in 16-byte blocks
     dev_buf gaps;
     const uint32_t max_gaps = nprefix / kGapInline + 2;
     MR_TRY(gaps.ensure(ctx, (size_t)max_gaps * sizeof(gap_item) + 16));

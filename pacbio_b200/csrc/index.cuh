@@ -37,11 +37,25 @@ struct mr_index {
   index_view view;
 };
 
+// counts[p], counts[p + 1] with one 16-byte load (plus a 4-byte one when p % 4 == 3): the two
+// entries almost always share a 32-byte sector, and a random sector fetched once must not be
+// requested a second time by a separate load instruction after it has left the L1.
+__device__ __forceinline__ void load_count_pair(const uint32_t* __restrict__ counts, uint32_t p, uint32_t& c0, uint32_t& c1) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(counts) + (p >> 2));
+  switch(p & 3) {
+  case 0: c0 = v.x; c1 = v.y; break;
+  case 1: c0 = v.y; c1 = v.z; break;
+  case 2: c0 = v.z; c1 = v.w; break;
+  default: c0 = v.w; c1 = __ldg(counts + p + 1);
+  }
+}
+
 // [index, nb) of SA entries whose text equals `mer` (mer_sa_imp.hpp:369-479 returns the same pair)
 __device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer, uint32_t& index, uint32_t& nb) {
   const uint32_t pre = (uint32_t)(mer >> iv.tail_bits);
   const uint32_t t   = (uint32_t)mer & (iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1));
-  const uint32_t c0 = __ldg(iv.counts + pre), c1 = __ldg(iv.counts + pre + 1);
+  uint32_t c0, c1;
+  load_count_pair(iv.counts, pre, c0, c1);
   index = 0; nb = 0;
   if(c0 == c1) return;
   uint32_t lo, hi;

@@ -105,13 +105,21 @@ class ClockSampler(threading.Thread):
 
 
 def dist_setup(n):
+    """One process per GPU under torchrun.  NCCL carries only the barrier and the max-over-ranks of
+    the timing (MR_BENCH_BACKEND=gloo runs the same plumbing on CPU for the tests)."""
     if n <= 1 or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
         return None
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group("nccl")
+    backend = os.environ.get("MR_BENCH_BACKEND", "nccl")
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend)
     return dist
+
+
+def _reduce_device(dist):
+    return "cuda" if dist.get_backend() == "nccl" else "cpu"
 
 
 def barrier(dist):
@@ -123,7 +131,7 @@ def max_over_ranks(dist, x):
     if dist is None:
         return x
     import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    t = torch.tensor([x], dtype=torch.float64, device=_reduce_device(dist))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -132,7 +140,7 @@ def sum_over_ranks(dist, x):
     if dist is None:
         return x
     import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    t = torch.tensor([x], dtype=torch.float64, device=_reduce_device(dist))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 

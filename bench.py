@@ -114,7 +114,20 @@ def dist_setup(n):
     backend = os.environ.get("MR_BENCH_BACKEND", "nccl")
     if backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group(backend)
+    # NCCL may print its version banner on stdout when the first communicator is created; stdout
+    # must carry exactly one JSON line, so the banner is sent to stderr.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group(backend)
+        dist.barrier()
+        if backend == "nccl":
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return dist
 
 

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
 #pragma unroll
   for(int q = 0; q < 8; ++q) {
     first[q] = 0;
-    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = __ldg(iv.tails + c0[q]);
+    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = load_tail(iv, c0[q]);
   }
   uint32_t nlook = 0, ntail = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
@@ -181,13 +181,13 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
           if(a1 - a0 <= 32) {
             const uint32_t v0 = first[2 * j + s];
             uint32_t less = v0 < tt, leq = v0 <= tt;
-            for(uint32_t i = a0 + 1; i < a1; ++i) { const uint32_t v = __ldg(iv.tails + i); less += v < tt; leq += v <= tt; }
+            for(uint32_t i = a0 + 1; i < a1; ++i) { const uint32_t v = load_tail(iv, i); less += v < tt; leq += v <= tt; }
             lo = a0 + less; hi = a0 + leq;
           } else {
             uint32_t a = a0, b = a1;
-            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) < tt) a = mid + 1; else b = mid; }
+            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) < tt) a = mid + 1; else b = mid; }
             lo = a; b = a1;
-            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) <= tt) a = mid + 1; else b = mid; }
+            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) <= tt) a = mid + 1; else b = mid; }
             hi = a;
           }
           if(hi != lo && (mer & 3) == 0)

@@ -45,8 +45,9 @@ __global__ void __launch_bounds__(256) sa_keys_kernel(const uint64_t* __restrict
 constexpr int kGapInline = 256;
 struct gap_item { uint32_t first, last, value; };
 
+template<typename TailT>
 __global__ void __launch_bounds__(256) sa_finish_kernel(const uint64_t* __restrict__ keys, uint32_t nsa, uint32_t tail_bits,
-                                                        uint32_t nprefix, uint32_t* __restrict__ tails,
+                                                        uint32_t nprefix, TailT* __restrict__ tails,
                                                         uint32_t* __restrict__ counts,
                                                         gap_item* __restrict__ gaps, uint32_t* __restrict__ ngaps) {
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) sa_finish_kernel(const uint64_t* __restri
     // i == nsa is the virtual end: fills counts above the last occupied prefix
     const int64_t prev = i == 0 ? -1 : (int64_t)(keys[i - 1] >> tail_bits);
     const int64_t cur  = i == nsa ? (int64_t)nprefix : (int64_t)(keys[i] >> tail_bits);
-    if(i < nsa) tails[i] = (uint32_t)(keys[i] & tmask);
+    if(i < nsa && tails) tails[i] = (TailT)(keys[i] & tmask);
     if(cur - prev <= kGapInline) {
       for(int64_t v = prev + 1; v <= cur; ++v) counts[v] = i;
     } else {
@@ -63,6 +64,14 @@ __global__ void __launch_bounds__(256) sa_finish_kernel(const uint64_t* __restri
       gaps[slot] = gap_item{ (uint32_t)(prev + 1), (uint32_t)cur, i };
     }
   }
+}
+
+// keys of the sorted entries recomputed from the text (for the parity tap that exports the
+// reference's 4^psa_min + 1 table)
+__global__ void __launch_bounds__(256) sa_rekey_kernel(const uint64_t* __restrict__ text, const uint32_t* __restrict__ sa,
+                                                       uint32_t nsa, uint32_t k, uint64_t* __restrict__ keys) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsa; i += stride) keys[i] = text_kmer(text, sa[i], k);
 }
 
 __global__ void __launch_bounds__(256) sa_fill_gaps_kernel(const gap_item* __restrict__ gaps, const uint32_t* __restrict__ ngaps,
@@ -105,6 +114,44 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
 
 } // namespace
 
+// prefix table over `mp` bases (and, when tails != null, the tails) from the sorted keys
+static int build_prefix_table(mr_context* ctx, const uint64_t* keys, uint32_t nsa, uint32_t k, uint32_t mp,
+                              void* tails, uint32_t tail_bytes, uint32_t* counts) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t tail_bits = 2 * (k - mp);
+  const uint32_t nprefix = 1u << (2 * mp);
+  dev_buf gaps;
+  const uint32_t max_gaps = nprefix / kGapInline + 2;
+  MR_TRY(gaps.ensure(ctx, (size_t)max_gaps * sizeof(gap_item) + 16));
+  uint32_t* ngaps = reinterpret_cast<uint32_t*>(gaps.as<gap_item>() + max_gaps);
+  MR_CUDA(ctx, cudaMemsetAsync(ngaps, 0, sizeof(uint32_t), st));
+  const unsigned grid = ctx->sm_count * 8;
+  if(tail_bytes == 1) sa_finish_kernel<uint8_t><<<grid, 256, 0, st>>>(keys, nsa, tail_bits, nprefix, (uint8_t*)tails, counts, gaps.as<gap_item>(), ngaps);
+  else if(tail_bytes == 2) sa_finish_kernel<uint16_t><<<grid, 256, 0, st>>>(keys, nsa, tail_bits, nprefix, (uint16_t*)tails, counts, gaps.as<gap_item>(), ngaps);
+  else sa_finish_kernel<uint32_t><<<grid, 256, 0, st>>>(keys, nsa, tail_bits, nprefix, (uint32_t*)tails, counts, gaps.as<gap_item>(), ngaps);
+  MR_LAUNCHED(ctx);
+  sa_fill_gaps_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(gaps.as<gap_item>(), ngaps, counts);
+  MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaStreamSynchronize(st));       // gaps is a local buffer
+  return MR_OK;
+}
+
+// Internal prefix length: as long as psa_min allows, small enough that prefix table + tails stay
+// L2 resident (budget 64 MB of the 126 MB), but never so small that the mean bucket exceeds ~32.
+static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k) {
+  uint32_t lo = 1;
+  while(lo < psa_min && ((uint64_t)1 << (2 * lo)) * 32 < n) ++lo;            // mean bucket <= 32
+  uint32_t best = psa_min;
+  while(best > lo) {
+    const uint32_t tb = 2 * (k - best);
+    const uint64_t bytes = (((uint64_t)1 << (2 * best)) + 1) * 4 + n * (tb <= 8 ? 1 : (tb <= 16 ? 2 : 4));
+    if(bytes <= (64ULL << 20)) break;
+    --best;
+  }
+  while(k - best > (uint32_t)kMaxShort) ++best;
+  return best;
+}
+
 extern "C" {
 
 int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
@@ -128,8 +175,11 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
   idx->nsa = (uint32_t)(n - psa_min + 1);
   const uint32_t nsa = idx->nsa;
   const uint64_t nwords = (n + 31) / 32;
-  const uint32_t tail_bits = 2 * (k - psa_min);
-  const uint32_t nprefix = 1u << (2 * psa_min);
+  const uint32_t mi = choose_internal_prefix(n, psa_min, k);
+  idx->mi = mi;
+  const uint32_t tail_bits = 2 * (k - mi);
+  const uint32_t tail_bytes = tail_bits <= 8 ? 1 : (tail_bits <= 16 ? 2 : 4);
+  const uint32_t nprefix = 1u << (2 * mi);
   cudaStream_t st = ctx->stream;
 
   timer.begin("Super read upload");
@@ -182,18 +232,9 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     timer.next("partial sums");
     const uint64_t* keys = in_first ? k0.as<uint64_t>() : k1.as<uint64_t>();
     dev_buf& vres = in_first ? v0 : v1;
-    MR_TRY(idx->tails.ensure(ctx, ((size_t)nsa + 64) * sizeof(uint32_t)));
+    MR_TRY(idx->tails.ensure(ctx, ((size_t)nsa + 64) * tail_bytes));
     MR_TRY(idx->counts.ensure(ctx, ((size_t)nprefix + 8) * sizeof(uint32_t)));   // read in 16-byte blocks
-    dev_buf gaps;
-    const uint32_t max_gaps = nprefix / kGapInline + 2;
-    MR_TRY(gaps.ensure(ctx, (size_t)max_gaps * sizeof(gap_item) + 16));
-    uint32_t* ngaps = reinterpret_cast<uint32_t*>(gaps.as<gap_item>() + max_gaps);
-    MR_CUDA(ctx, cudaMemsetAsync(ngaps, 0, sizeof(uint32_t), st));
-    sa_finish_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(keys, nsa, tail_bits, nprefix, idx->tails.as<uint32_t>(),
-                                                       idx->counts.as<uint32_t>(), gaps.as<gap_item>(), ngaps);
-    MR_LAUNCHED(ctx);
-    sa_fill_gaps_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(gaps.as<gap_item>(), ngaps, idx->counts.as<uint32_t>());
-    MR_LAUNCHED(ctx);
+    MR_TRY(build_prefix_table(ctx, keys, nsa, k, mi, idx->tails.p, tail_bytes, idx->counts.as<uint32_t>()));
     // keep the sorted positions: steal the buffer that holds them
     MR_CUDA(ctx, cudaStreamSynchronize(st));
     std::swap(idx->sa.p, vres.p);
@@ -205,9 +246,9 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
 
   // tail-short suffixes: positions n-k+1 .. n-m, padded k-mers computed on the host from the 2-bit text
   index_view& v = idx->view;
-  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.as<uint32_t>(); v.sa = idx->sa.as<uint32_t>();
+  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
-  v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.tail_bits = tail_bits;
+  v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.mi = mi; v.tail_bits = tail_bits; v.tail_bytes = tail_bytes;
   v.nshort = 0;
   for(uint32_t j = 1; j <= k - psa_min; ++j) {
     const uint64_t pos = n - k + j;
@@ -250,7 +291,25 @@ int mr_index_export_sa(mr_index* idx, uint64_t* sa_out) {
 
 int mr_index_export_counts(mr_index* idx, uint64_t* counts_out) {
   if(!idx || !counts_out) return MR_EINVAL;
-  return export_widened(idx, idx->counts.as<uint32_t>(), ((uint64_t)1 << (2 * idx->m)) + 1, counts_out);
+  mr_context* ctx = idx->ctx;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the reference's table is over psa_min bases; ours is over mi <= psa_min: rebuild it from the text
+  dev_buf keys, counts;
+  const uint32_t nprefix = 1u << (2 * idx->m);
+  MR_TRY(keys.ensure(ctx, (size_t)idx->nsa * sizeof(uint64_t)));
+  MR_TRY(counts.ensure(ctx, ((size_t)nprefix + 8) * sizeof(uint32_t)));
+  sa_rekey_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(idx->text.as<uint64_t>(), idx->sa.as<uint32_t>(), idx->nsa, idx->k,
+                                                             keys.as<uint64_t>());
+  MR_LAUNCHED(ctx);
+  MR_TRY(build_prefix_table(ctx, keys.as<uint64_t>(), idx->nsa, idx->k, idx->m, nullptr, 4, counts.as<uint32_t>()));
+  dev_buf tmp;
+  const uint64_t count = (uint64_t)nprefix + 1;
+  MR_TRY(tmp.ensure(ctx, count * sizeof(uint64_t)));
+  widen_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(counts.as<uint32_t>(), count, tmp.as<uint64_t>());
+  MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaMemcpyAsync(counts_out, tmp.p, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
 }
 
 int mr_lookup_batch_device(mr_index* idx, const uint64_t* d_mers, uint64_t q, uint64_t* d_index_out, uint64_t* d_nb_out) {

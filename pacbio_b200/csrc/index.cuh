@@ -5,10 +5,15 @@
 //   text   uint64[ceil(n/32)+2]  reference compact_dna layout (base i at bits 2(i%32)), zero padded
 //   sa     uint32[nsa]           positions ordered by (k-mer padded with A, position descending)
 //                                == the order of SA::sort_one_mer (mer_sa_imp.hpp:352-366)
-//   tails  uint32[nsa]           low 2(k-m) bits of each entry's padded k-mer: a lookup never
-//                                touches the text, one probe is one 4-byte read next to its
+//   tails  u8/u16/u32[nsa]       low 2(k-mi) bits of each entry's padded k-mer: a lookup never
+//                                touches the text, one probe is one small read next to its
 //                                neighbours instead of the reference's SA read + text read
-//   counts uint32[4^m+1]         exclusive prefix of the m-mer histogram (mer_sa_imp.hpp:317-330)
+//   counts uint32[4^mi+1]        exclusive prefix of the mi-mer histogram (mer_sa_imp.hpp:317-330).
+//                                mi <= m is an INTERNAL prefix length, chosen so that counts + tails
+//                                fit the 126 MB L2 when the index is small enough (C2: mi = 11,
+//                                17 MB + 36 MB) while buckets stay short; the (index, nb) a lookup
+//                                returns does not depend on it.  The reference's 4^m + 1 table is
+//                                recomputed on demand for the parity tap (mr_index_export_counts).
 //   sr_start uint32[nseq+1], blk uint32[(n>>8)+2]: blk[b] = sequence containing base b*256
 #pragma once
 #include "common.cuh"
@@ -18,19 +23,19 @@ constexpr int kMaxShort  = 16;    // k - m <= 16 (tails are 32 bit)
 
 struct index_view {
   const uint32_t* __restrict__ counts;
-  const uint32_t* __restrict__ tails;
+  const void*     __restrict__ tails;
   const uint32_t* __restrict__ sa;
   const uint32_t* __restrict__ sr_start;
   const uint32_t* __restrict__ blk;
   uint64_t n;
-  uint32_t nsa, nseq, k, m, tail_bits, nshort;
+  uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort;
   uint64_t short_key[kMaxShort];   // padded k-mers of the tail-short suffixes (positions n-k+1 .. n-m)
 };
 
 struct mr_index {
   mr_context* ctx = nullptr;
   uint64_t n = 0;
-  uint32_t nsa = 0, nseq = 0, k = 0, m = 0, n_unitigs = 0;
+  uint32_t nsa = 0, nseq = 0, k = 0, m = 0, mi = 0, n_unitigs = 0;
   bool     has_unitigs = false;
   dev_buf  text, sa, tails, counts, sr_start, blk;
   dev_buf  unitig_ids, unitig_off, unitig_len, sr_nunitigs;
@@ -50,6 +55,12 @@ __device__ __forceinline__ void load_count_pair(const uint32_t* __restrict__ cou
   }
 }
 
+__device__ __forceinline__ uint32_t load_tail(const index_view& iv, uint32_t i) {
+  if(iv.tail_bytes == 1) return __ldg(reinterpret_cast<const uint8_t*>(iv.tails) + i);
+  if(iv.tail_bytes == 2) return __ldg(reinterpret_cast<const uint16_t*>(iv.tails) + i);
+  return __ldg(reinterpret_cast<const uint32_t*>(iv.tails) + i);
+}
+
 // [index, nb) of SA entries whose text equals `mer` (mer_sa_imp.hpp:369-479 returns the same pair)
 __device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer, uint32_t& index, uint32_t& nb) {
   const uint32_t pre = (uint32_t)(mer >> iv.tail_bits);
@@ -62,16 +73,16 @@ __device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer,
   if(c1 - c0 <= 32) {                       // small bucket: branch-free counting scan
     uint32_t less = 0, leq = 0;
     for(uint32_t i = c0; i < c1; ++i) {
-      const uint32_t v = __ldg(iv.tails + i);
+      const uint32_t v = load_tail(iv, i);
       less += v < t;
       leq  += v <= t;
     }
     lo = c0 + less; hi = c0 + leq;
   } else {
     uint32_t a = c0, b = c1;
-    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) < t) a = mid + 1; else b = mid; }
+    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) < t) a = mid + 1; else b = mid; }
     lo = a; b = c1;
-    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(__ldg(iv.tails + mid) <= t) a = mid + 1; else b = mid; }
+    while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) <= t) a = mid + 1; else b = mid; }
     hi = a;
   }
   if(hi == lo) return;

@@ -336,7 +336,7 @@ def ours(args, w, files):
     value = args.gpus * total_bases * args.steps / dev_s_max
 
     # ---- end to end through the host path ----------------------------------------------------------------
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         H.mrh_tool_run(tool, host_threads, None)
     torch.cuda.synchronize()
     barrier(dist)

@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
     }
   }
   const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
-  // stage 2: the first tail of every non-empty bucket, again issued together -- most buckets hold one
-  // or two entries, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
+  // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
+  // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
   uint32_t first[8];
 #pragma unroll
   for(int q = 0; q < 8; ++q) {
     first[q] = 0;
-    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = load_tail(iv, c0[q]);
+    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word(iv, tail_word_of(iv, c0[q]));
   }
   uint32_t nlook = 0, ntail = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
@@ -175,21 +175,10 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
         const uint32_t a0 = c0[2 * j + s], a1 = c1[2 * j + s];
         idx[s] = 0; nb[s] = 0;
         if(a0 != a1) {
-          ntail += a1 - a0 <= 32 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
+          ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
           const uint32_t tt = (uint32_t)mer & tmask;
           uint32_t lo, hi;
-          if(a1 - a0 <= 32) {
-            const uint32_t v0 = first[2 * j + s];
-            uint32_t less = v0 < tt, leq = v0 <= tt;
-            for(uint32_t i = a0 + 1; i < a1; ++i) { const uint32_t v = load_tail(iv, i); less += v < tt; leq += v <= tt; }
-            lo = a0 + less; hi = a0 + leq;
-          } else {
-            uint32_t a = a0, b = a1;
-            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) < tt) a = mid + 1; else b = mid; }
-            lo = a; b = a1;
-            while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) <= tt) a = mid + 1; else b = mid; }
-            hi = a;
-          }
+          bucket_range(iv, a0, a1, tt, first[2 * j + s], lo, hi);
           if(hi != lo && (mer & 3) == 0)
             for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
           nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;

@@ -137,7 +137,7 @@ static int build_prefix_table(mr_context* ctx, const uint64_t* keys, uint32_t ns
 }
 
 // Internal prefix length: as long as psa_min allows, small enough that prefix table + tails stay
-// L2 resident (budget 64 MB of the 126 MB), but never so small that the mean bucket exceeds ~32.
+// L2 resident (budget 110 MB of the 126 MB), but never so small that the mean bucket exceeds ~32.
 static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k) {
   uint32_t lo = 1;
   while(lo < psa_min && ((uint64_t)1 << (2 * lo)) * 32 < n) ++lo;            // mean bucket <= 32
@@ -145,7 +145,7 @@ static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k)
   while(best > lo) {
     const uint32_t tb = 2 * (k - best);
     const uint64_t bytes = (((uint64_t)1 << (2 * best)) + 1) * 4 + n * (tb <= 8 ? 1 : (tb <= 16 ? 2 : 4));
-    if(bytes <= (64ULL << 20)) break;
+    if(bytes <= (110ULL << 20)) break;
     --best;
   }
   while(k - best > (uint32_t)kMaxShort) ++best;

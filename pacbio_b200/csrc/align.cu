@@ -353,23 +353,20 @@ struct info_args {
 };
 
 // One THREAD per coords row walking its chain (pairs stored in chain order by the chaining kernels):
-// 32 rows share every instruction.  The two counters of the current unitig are kept in registers
-// and flushed when the walk moves on to the next unitig; the overlap counters are touched only
-// near unitig boundaries.
-__global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= A.n) return;
-  const uint32_t ilen = A.info_len[i];
-  if(ilen == 0) return;
-  int32_t* mers  = A.kinfo + A.info_off[i];
-  int32_t* bases = A.binfo + A.info_off[i];
-  for(uint32_t j = 0; j < ilen; ++j) { mers[j] = 0; bases[j] = 0; }
+// 32 rows share every instruction.  Counters and unitig lengths of paths of up to kInfoLocal
+// unitigs live in thread-local arrays (L1), so the sequential walk pays ~L1 latency per hit; longer
+// paths work directly on the output slice.
+constexpr int kInfoLocal = 24;
+
+template<bool LOCAL>
+__device__ __forceinline__ bool kmers_info_walk(const info_args& A, uint64_t i, uint32_t nu, int32_t* mers, int32_t* bases,
+                                                const int32_t* ulen_tab) {
   const uint32_t sr = A.sr[i];
   const bool bwd = A.use_bwd[i];
   const uint64_t u0 = A.unitig_off[sr];
-  const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
   auto ulen = [&](uint32_t t) -> int {               // -1: invalid id or past the end of the path
     if(t >= nu) return -1;
+    if(LOCAL) return ulen_tab[t];
     const uint32_t id = (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
     return id < A.n_unitigs ? A.unitig_len[id] : -1;
   };
@@ -380,10 +377,9 @@ __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
   uint32_t cunitig = 0;
   int cend = ulen(0), prev_pos = -K;
   int cur_mers = 0, cur_bases = 0;                    // pending additions to mers/bases[2 * cunitig]
-  bool failed = false;
   const bool fwd_align = (int32_t)(uint32_t)(cp[0] >> 32) > 0;
   uint64_t nxt = cp[0];
-  for(uint32_t t = 0; t < nb && !failed; ++t) {
+  for(uint32_t t = 0; t < nb; ++t) {
     const uint64_t p = nxt;
     if(t + 1 < nb) nxt = cp[t + 1];
     const int32_t so = (int32_t)(uint32_t)(p >> 32);
@@ -392,7 +388,7 @@ __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
     const int new_bases = min(K, sr_pos - prev_pos);
     while(sr_pos + K > cend + 1) {
       if(cend >= sr_pos) {
-        if(cunitig >= nu - 1) { failed = true; break; }
+        if(cunitig >= nu - 1) return false;
         const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
         cur_bases += nbb;
         bases[2 * cunitig + 1] += nbb;
@@ -400,10 +396,9 @@ __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
       mers[2 * cunitig] += cur_mers; bases[2 * cunitig] += cur_bases;
       cur_mers = 0; cur_bases = 0;
       const int ul = ulen(++cunitig);
-      if(ul < 0) { failed = true; break; }
+      if(ul < 0) return false;
       cend += ul - UK + 1;
     }
-    if(failed) break;
     ++cur_mers;
     cur_bases += new_bases;
     int cendi = cend;
@@ -416,12 +411,40 @@ __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
       bases[2 * v + 2] += nbb;
       const int ul = ulen(v + 1);
       if(ul >= 0) cendi += ul - UK + 1;
-      else { failed = true; break; }
+      else return false;
     }
     prev_pos = sr_pos;
   }
-  if(failed) A.info_len[i] = 0;      // the reference clears both vectors on error
-  else { mers[2 * cunitig] += cur_mers; bases[2 * cunitig] += cur_bases; }
+  mers[2 * cunitig] += cur_mers; bases[2 * cunitig] += cur_bases;
+  return true;
+}
+
+__global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= A.n) return;
+  const uint32_t ilen = A.info_len[i];
+  if(ilen == 0) return;
+  int32_t* gm = A.kinfo + A.info_off[i];
+  int32_t* gb = A.binfo + A.info_off[i];
+  const uint32_t sr = A.sr[i];
+  const uint64_t u0 = A.unitig_off[sr];
+  const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
+  bool ok;
+  if(nu <= (uint32_t)kInfoLocal) {
+    int32_t lm[2 * kInfoLocal], lb[2 * kInfoLocal], ul[kInfoLocal];
+    const bool bwd = A.use_bwd[i];
+    for(uint32_t t = 0; t < nu; ++t) {
+      const uint32_t id = (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
+      ul[t] = id < A.n_unitigs ? A.unitig_len[id] : -1;
+    }
+    for(uint32_t j = 0; j < ilen; ++j) { lm[j] = 0; lb[j] = 0; }
+    ok = kmers_info_walk<true>(A, i, nu, lm, lb, ul);
+    if(ok) for(uint32_t j = 0; j < ilen; ++j) { gm[j] = lm[j]; gb[j] = lb[j]; }
+  } else {
+    for(uint32_t j = 0; j < ilen; ++j) { gm[j] = 0; gb[j] = 0; }
+    ok = kmers_info_walk<false>(A, i, nu, gm, gb, nullptr);
+  }
+  if(!ok) A.info_len[i] = 0;         // the reference clears both vectors on error
 }
 
 // ------------------------------------------------------------------------------------------------

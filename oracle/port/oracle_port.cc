@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -443,6 +444,7 @@ void align_read(const sr_index& idx, const std::string& read, const params& p,
   }
   // create_mega_reads.cc:69-77 sorts (unstably) by (rs, re, ql); ties are broken here by
   // emission order, i.e. by super-read index -- the canonical order of this project.
+  if(getenv("ORACLE_TIE_REVERSE")) std::reverse(out.begin(), out.end());   // diagnostic: break (rs, re, ql) ties the other way
   std::stable_sort(out.begin(), out.end(), [](const coords& a, const coords& b) {
     return a.rs < b.rs || (a.rs == b.rs && (a.re < b.re || (a.re == b.re && a.ql < b.ql)));
   });

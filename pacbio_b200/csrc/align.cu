@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) bucket_rows_kernel(uint64_t n, const uint
 __global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
                                                          const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
                                                          const uint32_t* __restrict__ ql, const uint32_t* __restrict__ sr,
-                                                         uint32_t* __restrict__ order) {
+                                                         const uint32_t* __restrict__ iter, uint32_t* __restrict__ order) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if(r >= nreads) return;
@@ -471,12 +471,12 @@ __global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const u
   const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
   for(uint32_t e = lane; e < c; e += 32) {
     const uint32_t me = slot[b + e];
-    const int32_t a0 = rs[me], a1 = re[me]; const uint32_t a2 = ql[me], a3 = sr[me];
+    const int32_t a0 = rs[me], a1 = re[me]; const uint32_t a2 = ql[me], a3 = sr[me], a4 = iter[me];
     uint32_t rank = 0;
     for(uint32_t f = 0; f < c; ++f) {
       const uint32_t o = slot[b + f];
-      const int32_t b0 = rs[o], b1 = re[o]; const uint32_t b2 = ql[o], b3 = sr[o];
-      const bool less = b0 < a0 || (b0 == a0 && (b1 < a1 || (b1 == a1 && (b2 < a2 || (b2 == a2 && b3 < a3)))));
+      const int32_t b0 = rs[o], b1 = re[o]; const uint32_t b2 = ql[o], b3 = sr[o], b4 = iter[o];
+      const bool less = b0 < a0 || (b0 == a0 && (b1 < a1 || (b1 == a1 && (b2 < a2 || (b2 == a2 && (b3 < a3 || (b3 == a3 && b4 < a4)))))));
       rank += less;
     }
     order[b + rank] = me;
@@ -670,16 +670,18 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       A.tap_sub = (uint32_t*)alt_key;       // gpos is dead once group_start exists
     }
     cap = std::max<uint64_t>(1 << 20, G / 4 + 1024);
-    if(cap > G) cap = G;
+    if(cap > G && !p->max_match) cap = G;
     if(cap == 0) cap = 1;
+    A.max_match = p->max_match;
+    if(p->max_match) { MR_TRY(ws.removed.ensure(ctx, H + 2)); A.removed = ws.removed.as<uint8_t>(); }
     for(int attempt = 0; attempt < 2; ++attempt) {
-      MR_TRY(ws.sv_i32.ensure(ctx, cap * 4 * 5 + 4096)); MR_TRY(ws.sv_u32.ensure(ctx, cap * 4 * 8 + 4096));
+      MR_TRY(ws.sv_i32.ensure(ctx, cap * 4 * 5 + 4096)); MR_TRY(ws.sv_u32.ensure(ctx, cap * 4 * 9 + 4096));
       MR_TRY(ws.sv_f64.ensure(ctx, cap * 8 * 3 + 4096)); MR_TRY(ws.sv_u64.ensure(ctx, cap * 8 * 2 + 4096));
       MR_TRY(ws.sv_u8.ensure(ctx, cap * 2 + 4096));
       survivors& sv = A.sv;
       { int32_t* b = ws.sv_i32.as<int32_t>(); sv.rs = b; sv.re = b + cap; sv.qs = b + 2 * cap; sv.qe = b + 3 * cap; sv.nb_mers = b + 4 * cap; }
       { uint32_t* b = ws.sv_u32.as<uint32_t>(); sv.pb_cons = b; sv.sr_cons = b + cap; sv.pb_cover = b + 2 * cap; sv.sr_cover = b + 3 * cap;
-        sv.ql = b + 4 * cap; sv.sr = b + 5 * cap; sv.read = b + 6 * cap; sv.info_len = b + 7 * cap; }
+        sv.ql = b + 4 * cap; sv.sr = b + 5 * cap; sv.read = b + 6 * cap; sv.info_len = b + 7 * cap; sv.iter = b + 8 * cap; }
       { double* b = ws.sv_f64.as<double>(); sv.stretch = b; sv.offset = b + cap; sv.avg_err = b + 2 * cap; }
       { uint64_t* b = ws.sv_u64.as<uint64_t>(); sv.chain_pos = b; }
       { uint8_t* b = ws.sv_u8.as<uint8_t>(); sv.rn = b; sv.use_bwd = b + cap; }
@@ -737,7 +739,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                        ws.slot.as<uint32_t>());
     MR_LAUNCHED(ctx);
     rank_rows_kernel<<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
-                                                                         A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, ws.order.as<uint32_t>());
+                                                                         A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, A.sv.iter, ws.order.as<uint32_t>());
     MR_LAUNCHED(ctx);
     gather_args Gt;
     Gt.n = S; Gt.order = ws.order.as<uint32_t>(); Gt.sv = A.sv; Gt.sv_info_off = sv_info_off; Gt.out = fin;
@@ -850,7 +852,7 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
   if(!idx || !p || !out || !h_read_start || !d_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
   if(idx->ctx != ctx) return ctx->fail(MR_EINVAL, "mr_align_batch: index belongs to another context");
   if(p->window_size != 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size other than 1 is not implemented");
-  if(p->max_match) return ctx->fail(MR_EINVAL, "mr_align_batch: --max-match is not implemented yet");
+  if(p->max_match && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with --max-match");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));

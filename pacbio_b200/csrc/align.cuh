@@ -30,7 +30,7 @@ struct mr_workspace {
   dev_buf read_cnt, read_coords, read_cursor, slot, order;
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
-  dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay;
+  dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay, removed;
   dev_buf scan_scratch;
   prim::sort_scratch sort;
   std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
@@ -62,6 +62,7 @@ struct survivors {
   uint8_t  *rn, *use_bwd;
   double   *stretch, *offset, *avg_err;
   uint64_t *chain_pos;
+  uint32_t *iter;           // --max-match round that produced the row (0 without it)
   uint64_t cap;
   unsigned long long* count;
   unsigned long long* info_total;
@@ -82,6 +83,7 @@ struct chain_args {
   // filled by launch_chain: per-group verdict (chain length | fwd << 31) and the list of long chains
   uint32_t* group_nb; uint32_t* long_list; uint32_t* long_count; uint32_t* long_cursor;
   uint64_t* chain_pay;      // per group, at its slice: the chain's (pb, sr) pairs in chain order
+  int max_match; uint8_t* removed;   // --max-match: hits already used by an emitted chain
 };
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);
 

@@ -182,7 +182,8 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
 // global-memory strand (groups larger than the shared-memory tiers)
 // ---------------------------------------------------------------------------------------------
 __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const chain_buffers& cb, uint64_t gs,
-                                    double a, double b, double C, uint32_t& longest_out, uint32_t& best_out, uint32_t* tap_sub) {
+                                    double a, double b, double C, uint32_t& longest_out, uint32_t& best_out, uint32_t* tap_sub,
+                                    const uint8_t* removed = nullptr) {
   const unsigned lane = threadIdx.x & 31;
   int32_t*  Lpb  = cb.Lpb + gs;  int32_t* Lsr = cb.Lsr + gs;
   uint32_t* Llen = cb.Llen + gs; uint32_t* Lelt = cb.Lelt + gs;
@@ -192,7 +193,7 @@ __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N
     const uint32_t il = base + lane;
     const uint64_t pl = il < N ? pay[il] : 0;
     const int32_t pb_l = (int32_t)(uint32_t)pl, sr_l = (int32_t)(uint32_t)(pl >> 32);
-    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg));
+    unsigned todo = __ballot_sync(MR_FULL_MASK, il < N && ((sr_l < 0) == neg) && !(removed && removed[il]));
     while(todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
@@ -282,8 +283,9 @@ struct coords_acc {
 };
 
 // canonicalize + filters + survivor append; call from ONE thread per group
-__device__ __forceinline__ void publish_coords(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
-                                               uint32_t nb, const coords_acc& c, double stretch, double offset, double avg_err) {
+__device__ __forceinline__ bool publish_coords(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                               uint32_t nb, const coords_acc& c, double stretch, double offset, double avg_err,
+                                               uint32_t iter = 0) {
   const uint32_t k = A.iv.k;
   const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
   const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
@@ -306,15 +308,15 @@ __device__ __forceinline__ void publish_coords(const chain_args& A, uint64_t gs,
     qe += (int32_t)k - 1;
   }
   // filters of align_sequence_max (coarse_aligner.cc:51-54)
-  if(fabs(stretch) == 0.0) return;
+  if(fabs(stretch) == 0.0) return false;
   {
     const double drl = (double)rl;
     const double is = fmax(1.0, fmin(drl, stretch + offset));
     const double tq = stretch * (double)ql;
     const double ie = fmax(1.0, fmin(drl, tq + offset));
     const int imp_len = (int)llabs(llrint(ie - is)) + 1;
-    if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) return;
-    if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)c.pb_cover)) return;
+    if(A.matching_mers != 0.0 && !(A.matching_mers * (double)(uint32_t)((uint32_t)imp_len - k + 1) <= (double)(int)nb)) return false;
+    if(A.matching_bases > 0.0 && !(A.matching_bases * (double)(imp_len - 2 * (int)k) <= (double)c.pb_cover)) return false;
   }
   const bool use_bwd = A.forward && !fwd_align;
   uint32_t ilen = 0;
@@ -334,15 +336,17 @@ __device__ __forceinline__ void publish_coords(const chain_args& A, uint64_t gs,
     sv.rn[slot] = rn; sv.use_bwd[slot] = use_bwd;
     sv.stretch[slot] = stretch; sv.offset[slot] = offset; sv.avg_err[slot] = avg_err;
     sv.chain_pos[slot] = gs;
+    sv.iter[slot] = iter;
     atomicAdd(sv.info_total, (unsigned long long)ilen);
     atomicAdd(sv.read_cnt + read, 1u);
   }
+  return true;
 }
 
 // long chains: one warp per group, the lanes fetch 32 hits (and 32 reciprocals) at a time and every
 // lane runs the same sequential recurrence on the broadcast values
-__device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
-                                                  uint32_t nb) {
+__device__ __forceinline__ bool finish_group_warp(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
+                                                  uint32_t nb, uint32_t iter = 0) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t k = A.iv.k;
   const uint64_t* cp = A.chain_pay + gs;          // the chain's (pb, sr) pairs, in chain order
@@ -377,7 +381,9 @@ __device__ __forceinline__ void finish_group_warp(const chain_args& A, uint64_t 
     }
     avg_err = e / (double)c.n;
   }
-  if(lane == 0) publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err);
+  bool passed = false;
+  if(lane == 0) passed = publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err, iter);
+  return __shfl_sync(MR_FULL_MASK, (int)passed, 0) != 0;
 }
 
 // one THREAD per group: 32 independent recurrences per warp instruction.  The chain's pairs are read
@@ -583,6 +589,59 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t
   }
 }
 
+// --max-match (coarse_aligner.cc:56-57, pb_aligner.hpp:47-92): after a row passes the filters the
+// chain of the strictly-longer-forward-else-backward list is removed from its list, that list is
+// chained again and the group is evaluated again, until a row fails.  One warp per group out of
+// global scratch; successive chains of a group are stored back to back in its chain_pay slice.
+__global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8_t* __restrict__ removed, uint32_t* __restrict__ cursor) {
+  const unsigned lane = threadIdx.x & 31;
+  while(true) {
+    uint32_t g = 0;
+    if(lane == 0) g = atomicAdd(cursor, 1u);
+    g = __shfl_sync(MR_FULL_MASK, g, 0);
+    if(g >= A.ngroups) break;
+    const uint64_t gs = A.group_start[g];
+    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    const uint64_t key = A.keys[gs];
+    const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
+    uint8_t* rem = removed + gs;
+    for(uint32_t t = lane; t < N; t += 32) rem[t] = 0;
+    __syncwarp();
+    uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0, used = 0;
+    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem);
+    __syncwarp();
+    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem);
+    __syncwarp();
+    uint32_t* pprev = A.cb.pprev + gs;
+    uint32_t* chain = A.cb.Lelt + gs;            // L is dead between chainings
+    for(uint32_t iter = 0; ; ++iter) {
+      const bool fwd_align = len_f >= len_b;
+      const uint32_t nb = fwd_align ? len_f : len_b;
+      if(nb == 0) break;
+      if(lane == 0) {
+        uint32_t cur = fwd_align ? best_f : best_b;
+        for(uint32_t t = 0; t < nb; ++t) { chain[nb - 1 - t] = cur; cur = pprev[cur]; }
+      }
+      __syncwarp();
+      for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + used + t] = A.pays[gs + chain[t]];
+      __syncwarp();
+      if(!finish_group_warp(A, gs + used, read, sr, fwd_align, nb, iter)) break;
+      used += nb;
+      // discard_update_LIS: the forward list only if it is STRICTLY longer, else the backward one
+      const bool drop_fwd = len_f > len_b;
+      const uint32_t dn = drop_fwd ? len_f : len_b;
+      if(lane == 0) {
+        uint32_t cur = drop_fwd ? best_f : best_b;
+        for(uint32_t t = 0; t < dn; ++t) { rem[cur] = 1; cur = pprev[cur]; }
+      }
+      __syncwarp();
+      if(drop_fwd) chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem);
+      else         chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem);
+      __syncwarp();
+    }
+  }
+}
+
 template<int CAP, int WARPS, bool TAPS>
 int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, const uint32_t* list, const uint32_t* count, uint32_t* cursor, int blocks_per_sm) {
   const size_t smem = sizeof(warp_store<CAP>) * WARPS + (TAPS ? (size_t)WARPS * CAP * sizeof(uint16_t) : 0);
@@ -606,8 +665,13 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   A.long_list = cls + 4 * G; A.group_nb = cls + 5 * G; A.long_count = ctr + 8; A.long_cursor = ctr + 9;
   MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
   // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
-  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr, cls, ctr);
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr && !A.max_match, cls, ctr);
   MR_LAUNCHED(ctx);
+  if(A.max_match) {
+    chain_maxmatch_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, A.removed, ctr + 4);
+    MR_LAUNCHED(ctx);
+    return MR_OK;
+  }
   const bool taps = A.tap_lens != nullptr;
   // The big-group tiers have few, long, latency-bound groups; they run on a side stream next to the
   // mid/small tiers.  Likewise the three finishing kernels (independent groups) run side by side.

@@ -25,7 +25,7 @@ static const char* usage_text =
   "     --window-size=uint32     (1)\n"
   " -O, --overlap-play=double    (1.3)  -e, --errors=double (3.0)\n"
   " -B, --bases-matching=double  (17.0) -M, --mers-matching=double (0.0)\n"
-  "     --max-match              Use secondary matches (not implemented)\n"
+  "     --max-match              Use secondary matches\n"
   "     --max-count=uint32       (5000) -b, --bases\n"
   " -d, --density=double         (0.029) -L, --min-length=double (100.0)\n"
   " -T, --tiling=none|greedy|maximal|weighted (greedy)   --trim=none|match|branch (none)\n"
@@ -108,7 +108,6 @@ int main(int argc, char* argv[]) {
   if(l_given && u_given) error("Switches [-u, --unitigs-sequences=path] and [-l, --unitigs-lengths=path] are mutually exclusive");
   if(argc - optind != 0) error("Requires exactly 0 argument.");
   if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
-  if(P.max_match) error("[--max-match] secondary matches are not implemented in this build");
 
   try {
     // open the output first, for early error reporting (create_mega_reads.cc:101-107)

@@ -12,7 +12,7 @@ static const char* usage_text =
   " -s, --size=uint64  -m, --mer=uint32 (required)  -F, --fine-mer (not implemented)  --psa-min=uint32 (13)\n"
   " -t, --threads=uint32 (1)  --stretch-constant=int (10)  --stretch-factor=double (1.3)  --stretch-cap=double (10000.0)\n"
   "     --window-size=uint32 (1)  -f, --forward  -B, --bases-matching=double (17.0)  -M, --mers-matching=double (0.0)\n"
-  "     --details=path (not implemented)  --coords=path (stdout)  --max-match (not implemented)\n"
+  "     --details=path (not implemented)  --coords=path (stdout)  --max-match\n"
   " -H, --no-header  -0, --zero-match  --max-count=uint32 (5000)  -l, --unitigs-lengths=path  -u, --unitigs-sequences=path\n"
   "     --compact (toggles the compact format off)  -k, --k-mer=uint32  -r, --superreads=path  -p, --pacbio=path\n";
 
@@ -79,7 +79,6 @@ int main(int argc, char* argv[]) {
   if(!details_given && !coords_given) error("No output file given. Doing nothing ungracefully.");
   if(details_given) error("[--details] the per-k-mer details output is not implemented in this build");
   if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
-  if(P.max_match) error("[--max-match] secondary matches are not implemented in this build");
   if((l_given || u_given) && !k_given)
     error("The mer length used for generating the k-unitigs (-k, --k-mer) is required if the unitig lengths (-l, --unitig-lengths or -u, --unitigs-sequences) is passed.");
 

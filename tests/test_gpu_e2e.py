@@ -116,6 +116,24 @@ def test_larger_input_against_oracle(tmpdir_session, tmp_path, port, tiling, tri
     assert not diff, "%d of %d records differ, e.g. %s" % (len(diff), len(b), diff[:3])
 
 
+def test_max_match_text_against_reference(tmpdir_session, tmp_path, port):
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_mm"), 300000, coverage=4, read_len=5000, seed=9, repeat_frac=0.25)
+    common = ["-s", "1M", "-m", "15", "-k", "41", "-l", info["unitigs_len"], "--max-match", "-r", info["sr"], "-p", info["reads"]]
+    out, outc = str(tmp_path / "gpu.txt"), str(tmp_path / "gpu.coords")
+    run([CMR] + common + ["-o", out])
+    run([JFA] + common + ["-H", "--coords", outc])
+    want, wantc = str(tmp_path / "want.txt"), str(tmp_path / "want.coords")
+    if have_ref():
+        from oracle_lib import REF_JFA
+        run([REF_CMR] + common + ["-t", "4", "-o", want])
+        run([REF_JFA] + common + ["-t", "1", "-H", "--coords", wantc])
+    else:
+        port.run(0, info["sr"], info["reads"], info["unitigs_len"], want, 15, 41, unitigs_is_fasta=False, max_match=True)
+        port.run(1, info["sr"], info["reads"], info["unitigs_len"], wantc, 15, 41, unitigs_is_fasta=False, max_match=True)
+    assert_same_records(records(outc), records(wantc), what="coords")
+    assert_same_records(records(out), records(want), reads_with_coords_ties(outc), what="mega reads")
+
+
 def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
     info = gen_synth(os.path.join(tmpdir_session, "e2e_fq"), 100000, coverage=3, read_len=3000, seed=5)
     from oracle_lib import read_fasta

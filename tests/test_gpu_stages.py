@@ -152,3 +152,38 @@ def test_shared_reciprocal_division_is_exact(ctx):
         bad = C.c_uint64(123)
         ctx.check(L.mr_selftest_division(ctx.h, 1 << 28, seed, max_n, C.byref(bad)))
         assert bad.value == 0
+
+
+def test_max_match_coords_match_oracle(case, ctx, port):
+    """--max-match: every secondary row (coarse_aligner.cc:56-57) must match the oracle, doubles bit for bit."""
+    import pacbio_b200 as pb
+    c = case["cfg"]
+    _, seqs = read_fasta(case["info"]["reads"])
+    seqs = seqs[:30]
+    # reads holding the same super-read segment twice: the second copy can only be reported as a
+    # secondary match, after the first chain has been discarded
+    _, srs = read_fasta(case["info"]["sr"])
+    for s_ in [x for x in srs if len(x) > 2500][:6]:
+        seqs.append(s_[100:1300] + "ACGTTGCA" + s_[100:1300] + s_[1300:2000])
+    n = len(seqs)
+    sub = pb.Reads(names=["r%d" % i for i in range(n)], seqs=seqs)
+    p = pb.default_params(unitigs_k=c["uk"], run_graph=0, max_match=1)
+    res = ctx.align(case["idx"], sub, p)
+    ap = port.aligner_create(case["hp"], unitigs_k=c["uk"], max_match=True)
+    extra = 0
+    for r in range(n):
+        o = port.align_read(ap, seqs[r])
+        rr = list(res.rows(r))
+        assert len(rr) == len(o["cint"]), "coords count of read %d" % r
+        g_int = np.stack([res.rs[rr], res.re[rr], res.qs[rr], res.qe[rr], res.nb_mers[rr], res.pb_cons[rr],
+                          res.sr_cons[rr], res.pb_cover[rr], res.sr_cover[rr], np.full(len(rr), len(seqs[r])), res.ql[rr],
+                          res.rn[rr], res.sr[rr], res.use_bwd[rr]], axis=1).astype(np.int64) if rr else np.zeros((0, 14), np.int64)
+        g_dbl = np.stack([res.stretch[rr], res.offset[rr], res.avg_err[rr]], axis=1) if rr else np.zeros((0, 3))
+        g_off = np.concatenate([[0], np.cumsum(res.info_len[rr])]).astype(np.int64)
+        g_k = np.concatenate([res.info(i)[0] for i in rr]) if rr else np.zeros(0, np.int32)
+        g_b = np.concatenate([res.info(i)[1] for i in rr]) if rr else np.zeros(0, np.int32)
+        assert _canon(g_int, g_dbl, g_off, g_k, g_b) == _canon(o["cint"], o["cdbl"], o["info_off"], o["kinfo"], o["binfo"]), \
+            "coords of read %d" % r
+        extra += len(rr) - len(set(res.sr[rr].tolist()))
+    assert extra > 0, "no secondary match was exercised"
+    port.aligner_destroy(ap)

@@ -45,6 +45,11 @@ def parse_args():
     ap.add_argument("--batch-bases", type=int, default=32 << 20)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mega_reads", choices=["mega_reads", "lookup"],
+                    help="lookup: BASELINE.json configs[4] microbench (k-mer queries against a random-text suffix array)")
+    ap.add_argument("--lookup-n", type=float, default=1e9)
+    ap.add_argument("--lookup-queries", type=float, default=1e9)
+    ap.add_argument("--lookup-k", type=int, default=17)
     return ap.parse_args()
 
 
@@ -428,8 +433,113 @@ def ours(args, w, files):
         dist.destroy_process_group()
 
 
+def lookup_microbench(args):
+    """configs[4]: queries/s of mr_lookup_batch_device (PSA::search replacement) on a random text of
+    --lookup-n bases, half of the queries sampled from the text (both strands), half uniform random."""
+    import torch
+    import pacbio_b200.api as api
+    n, q, k, m = int(args.lookup_n), int(args.lookup_queries), args.lookup_k, 13
+    torch.cuda.set_device(0)
+    L = api.lib()
+    rng = np.random.default_rng(46)
+    words = rng.integers(0, 2 ** 63, size=(n + 31) // 32 + 1, dtype=np.int64).astype(np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(n + 31) // 32 + 1, dtype=np.uint64)
+    ctx = api.Context(0)
+
+    class _SR:
+        pass
+    sr = _SR()
+    sr.text2bit, sr.n, sr.starts, sr.names = words, n, np.array([0, n], dtype=np.uint64), ["random"]
+    sr.unitig_ids, sr.unitig_off = np.zeros(1, np.uint32), np.zeros(2, np.uint64)
+    t0 = time.perf_counter()
+    idx = api.Index(ctx, sr, m, k)
+    build_s = time.perf_counter() - t0
+    dwords = torch.from_numpy(words.view(np.int64)).cuda()
+    mers = torch.empty(q, dtype=torch.int64, device="cuda")
+    chunk = 1 << 27
+    g = torch.Generator(device="cuda")
+    g.manual_seed(47)
+    for lo in range(0, q, chunk):
+        c = min(chunk, q - lo)
+        half = c // 2
+        pos = torch.randint(0, n - k, (half,), device="cuda", generator=g)
+        fwd = torch.zeros(half, dtype=torch.int64, device="cuda")
+        rc = torch.zeros(half, dtype=torch.int64, device="cuda")
+        for j in range(k):
+            b = pos + j
+            code = (dwords[b >> 5] >> (2 * (b & 31))) & 3
+            fwd = (fwd << 2) | code
+            rc = rc | ((3 - code) << (2 * j))
+        pick = torch.arange(half, device="cuda") & 1
+        mers[lo:lo + half] = torch.where(pick == 1, rc, fwd)
+        mers[lo + half:lo + c] = torch.randint(0, 4 ** k, (c - half,), device="cuda", generator=g)
+        del pos, fwd, rc, pick
+    out_i = torch.empty(q, dtype=torch.int64, device="cuda")
+    out_n = torch.empty(q, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream())
+
+    def step():
+        ctx.check(L.mr_lookup_batch_device(idx.h, C.c_void_p(mers.data_ptr()), q, C.c_void_p(out_i.data_ptr()),
+                                           C.c_void_p(out_n.data_ptr())))
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    dt = e0.elapsed_time(e1) * 1e-3
+    found = int((out_n > 0).sum().item())
+    # end to end: host buffers in and out through mr_lookup_batch, on a bounded slice of the queries
+    qe = min(q, 1 << 26)
+    h_m = mers[:qe].cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        idx.lookup(h_m)
+    e2e_dt = time.perf_counter() - t0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = q * (8 + 16 + 8 + 4)          # query in, (index, nb) out, prefix pair, ~one tail
+    line = {"metric": "kmer_lookups_per_s", "value": q * args.steps / dt, "unit": "queries/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "configs[4]: %g k-mer queries (half from the text, both strands; half random) against a "
+                                   "%g bp random-text suffix array, k=%d, psa-min %d" % (q, n, k, m),
+                       "l2": "index tables and query stream larger than L2"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": qe * args.steps / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": qe * 8,
+                    "d2h_bytes_per_step": qe * 16, "sample": "%d of the queries through mr_lookup_batch (host pointers)" % qe},
+            "gpu_launches": int(ctx.launches() - l0),
+            "roofline": {"kernel": "lookup_kernel", "bound": "hbm", "achieved": alg * args.steps / dt / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg * args.steps / dt / 1e9 / peak, "traffic": None,
+                         "note": "random-sector gathers; algorithmic bytes = 36 per query"},
+            "cpu_baseline": None, "index_build_s": build_s, "queries_found": found}
+    print(json.dumps(line))
+    idx.close()
+    ctx.close()
+
+
 def main():
     args = parse_args()
+    if args.workload == "lookup":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the lookup microbench has no reference arm here "
+                              "(building the reference PSA for 1 Gbp takes minutes of CPU); see cpu_baseline of the default workload"}))
+            return
+        return lookup_microbench(args)
     w, files = data_files(args)
     if args.impl == "reference":
         reference_arm(args, w, files)

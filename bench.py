@@ -533,6 +533,9 @@ def lookup_microbench(args):
 
 
 def main():
+    # watchdog: a hung run dumps every thread's Python stack on stderr and exits instead of sitting on the GPU
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MR_BENCH_WATCHDOG", "900")), exit=True)
     args = parse_args()
     if args.workload == "lookup":
         if args.impl == "reference":

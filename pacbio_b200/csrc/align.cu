@@ -6,10 +6,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
 namespace {
+
+// MR_TRACE=1: progress lines on stderr (which phase a stuck batch is in)
+static const bool g_trace = getenv("MR_TRACE") != nullptr;
+#define MR_TRACE_MSG(...) do { if(g_trace) { fprintf(stderr, "[mr] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while(0)
 
 // ------------------------------------------------------------------------------------------------
 // k-mer enumeration over one tile of one read (jf_aligner.hpp:41-52,113-123 + coarse_aligner.cc:8-15,89-102)
@@ -604,6 +609,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t H = h_ctr[1];
+  MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
   res->view.n_kmers_looked_up = h_ctr[0];
   res->view.n_tail_entries = h_ctr[6];
   if(H >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 hits in one batch; use smaller batches");
@@ -635,6 +641,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));
     G = h_ctr[3];
+    MR_TRACE_MSG("sorted; %llu groups", (unsigned long long)G);
     const uint64_t Hvalid = H - h_ctr[2];
     res->view.n_hits = Hvalid;
     res->view.n_groups = G;
@@ -692,6 +699,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       MR_CUDA(ctx, cudaStreamSynchronize(st));
       S = h_ctr[4];
+      MR_TRACE_MSG("chained; %llu rows (capacity %llu)", (unsigned long long)S, (unsigned long long)cap);
       if(S <= cap) break;
       cap = S;                                 // rare: more survivors than provisioned, run again
     }
@@ -766,6 +774,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     if(S) MR_TRY(launch_graph(ctx, GA));
   }
   timer.next("result download");
+  MR_TRACE_MSG("ordered%s; downloading", graph ? " + graph" : "");
 
   // ---- results to pinned host memory ----------------------------------------------------------------
   {
@@ -840,6 +849,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   }
   timer.end();
   MR_CUDA(ctx, cudaStreamSynchronize(st));
+  MR_TRACE_MSG("batch done");
   *out = res.release();
   return MR_OK;
 }

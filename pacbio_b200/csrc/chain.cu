@@ -17,6 +17,8 @@
 // collectives) and the number of warps in flight.
 #include "align.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr uint32_t kThreadFinishMax = 192;        // chains up to this many hits: one thread each, group order
@@ -345,6 +347,10 @@ __device__ __forceinline__ bool publish_coords(const chain_args& A, uint64_t gs,
 
 // long chains: one warp per group, the lanes fetch 32 hits (and 32 reciprocals) at a time and every
 // lane runs the same sequential recurrence on the broadcast values
+// WANT_RESULT: broadcast "the row passed the filters" to the whole warp (needed by --max-match only).
+// Without it the function ends with lane 0's publish and no warp collective: a version that always
+// ended in a __shfl_sync whose result the caller ignored hung on sm_100a (long chains, CUDA 12.9).
+template<bool WANT_RESULT>
 __device__ __forceinline__ bool finish_group_warp(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
                                                   uint32_t nb, uint32_t iter = 0) {
   const unsigned lane = threadIdx.x & 31;
@@ -381,9 +387,14 @@ __device__ __forceinline__ bool finish_group_warp(const chain_args& A, uint64_t 
     }
     avg_err = e / (double)c.n;
   }
-  bool passed = false;
-  if(lane == 0) passed = publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err, iter);
-  return __shfl_sync(MR_FULL_MASK, (int)passed, 0) != 0;
+  if(!WANT_RESULT) {
+    if(lane == 0) publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err, iter);
+    return false;
+  }
+  int passed = 0;
+  if(lane == 0) passed = publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err, iter) ? 1 : 0;
+  __syncwarp();
+  return __shfl_sync(MR_FULL_MASK, passed, 0) != 0;
 }
 
 // one THREAD per group: 32 independent recurrences per warp instruction.  The chain's pairs are read
@@ -585,7 +596,7 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t
     if((v & 0x7fffffffu) <= lo) continue;
     const uint64_t gs = A.group_start[g];
     const uint64_t key = A.keys[gs];
-    finish_group_warp(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
+    finish_group_warp<false>(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
   }
 }
 
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8
       __syncwarp();
       for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + used + t] = A.pays[gs + chain[t]];
       __syncwarp();
-      if(!finish_group_warp(A, gs + used, read, sr, fwd_align, nb, iter)) break;
+      if(!finish_group_warp<true>(A, gs + used, read, sr, fwd_align, nb, iter)) break;
       used += nb;
       // discard_update_LIS: the forward list only if it is STRICTLY longer, else the backward one
       const bool drop_fwd = len_f > len_b;
@@ -655,6 +666,11 @@ int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, const uin
 
 // scratch `lists`: 5 x ngroups uint32 (4 size classes + long-chain list), ngroups uint32 verdicts,
 // 16 uint32 counters (class counts 0..3, class cursors 4..7, long count 8, long cursor 9)
+// MR_TRACE=1: synchronise after every chain-phase kernel and name it on stderr
+static const bool g_chain_trace = getenv("MR_TRACE") != nullptr;
+#define CHAIN_TRACE(st, name) do { if(g_chain_trace) { cudaError_t e_ = cudaStreamSynchronize(st); \
+  fprintf(stderr, "[mr]   %s: %s\n", name, cudaGetErrorString(e_)); fflush(stderr); } } while(0)
+
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(A.ngroups == 0) return MR_OK;
   if(A.ngroups >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "more than 2^32 (read, super-read) groups in one batch");
@@ -667,6 +683,7 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
   classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr && !A.max_match, cls, ctr);
   MR_LAUNCHED(ctx);
+  CHAIN_TRACE(ctx->stream, "classify");
   if(A.max_match) {
     chain_maxmatch_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, A.removed, ctr + 4);
     MR_LAUNCHED(ctx);
@@ -680,14 +697,18 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   MR_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev[0], 0));
   chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, s1>>>(A, cls + 3 * G, ctr + 3, ctr + 7);
   MR_LAUNCHED(ctx);
+  CHAIN_TRACE(s1, "strands, global tier");
   if(taps) {
     MR_TRY((launch_smem<4096, 2, true>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
     MR_TRY((launch_smem<1024, 4, true>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
     MR_TRY((launch_smem<64, 8, true>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
   } else {
     MR_TRY((launch_smem<4096, 2, false>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
+    CHAIN_TRACE(s1, "strands, 4096 tier");
     MR_TRY((launch_smem<1024, 4, false>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
+    CHAIN_TRACE(s0, "strands, 1024 tier");
     MR_TRY((launch_smem<64, 8, false>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
+    CHAIN_TRACE(s0, "strands, 64 tier");
   }
   // all strands done -> finishing kernels on three streams
   MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
@@ -697,10 +718,13 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   MR_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev[2], 0));
   finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, s1>>>(A, kThreadFinishLongMax);
   MR_LAUNCHED(ctx);
+  CHAIN_TRACE(s1, "finish, warp per chain");
   finish_thread_kernel<<<div_up(G, 128), 128, 0, s2>>>(A, A.long_list, A.long_count, kThreadFinishMax, kThreadFinishLongMax);
   MR_LAUNCHED(ctx);
+  CHAIN_TRACE(s2, "finish, thread per long chain");
   finish_thread_kernel<<<div_up(G, 128), 128, 0, s0>>>(A, nullptr, nullptr, 0, kThreadFinishMax);
   MR_LAUNCHED(ctx);
+  CHAIN_TRACE(s0, "finish, thread per short chain");
   MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
   MR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s2));
   MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[1], 0));

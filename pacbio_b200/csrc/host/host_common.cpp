@@ -85,6 +85,17 @@ std::string super_reads::row_name(uint32_t s, bool bwd) const {
 // ================================================================================================
 // k-unitigs
 // ================================================================================================
+namespace {
+struct revcomp_table_t {
+  char t[256];
+  revcomp_table_t() {
+    for(int i = 0; i < 256; ++i) t[i] = 'N';
+    t['a'] = t['A'] = 'T'; t['c'] = t['C'] = 'G'; t['g'] = t['G'] = 'C'; t['t'] = t['T'] = 'A';
+  }
+};
+const revcomp_table_t revcomp_table;
+}
+
 void unitigs::load_lengths(const std::string& path) {
   std::ifstream is(path);
   if(!is.good()) throw std::runtime_error("Failed to open unitig lengths map file '" + path + "'");
@@ -102,6 +113,21 @@ void unitigs::load_sequences(const std::string& path) {
     len.push_back((int32_t)s.size());
     seq.push_back(s);
   }
+  // Printing a mega-read copies the unitigs of its path, reverse-complemented for 'R' entries;
+  // doing the complement once here turns every later append into a memcpy.
+  rc_seq.resize(seq.size());
+  const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> th;
+  for(unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&, t]() {
+      for(size_t i = t; i < seq.size(); i += nt) {
+        const std::string& f = seq[i];
+        std::string& r = rc_seq[i];
+        r.resize(f.size());
+        for(size_t j = 0; j < f.size(); ++j) r[j] = revcomp_table.t[(unsigned char)f[f.size() - 1 - j]];
+      }
+    });
+  for(auto& x : th) x.join();
 }
 
 // ================================================================================================
@@ -192,15 +218,6 @@ bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_rea
 // mega-reads from the device's graph rows
 // ================================================================================================
 namespace {
-struct revcomp_table_t {
-  char t[256];
-  revcomp_table_t() {
-    for(int i = 0; i < 256; ++i) t[i] = 'N';
-    t['a'] = t['A'] = 'T'; t['c'] = t['C'] = 'G'; t['g'] = t['G'] = 'C'; t['t'] = t['T'] = 'A';
-  }
-};
-const revcomp_table_t revcomp_table;
-
 struct mega_read {
   int    start_node, end_node, start_unitig, start_offset, end_offset, nb_unitigs;
   double imp_s, imp_e, tiling_start, tiling_end, density;
@@ -421,18 +438,9 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
         const size_t pb = std::min((size_t)mr.start_unitig, path.size());
         const size_t pe = std::min((size_t)(mr.start_unitig + mr.nb_unitigs), path.size());
         for(size_t i = pb; i < pe; ++i) {
-          const std::string& s = u.seq.at(path[i] >> 1);
+          const std::string& s = (path[i] & 1) ? u.rc_seq.at(path[i] >> 1) : u.seq.at(path[i] >> 1);
           const size_t skip = i == pb ? 0 : (size_t)o.k_len - 1;
-          if(skip >= s.size()) continue;
-          if(path[i] & 1) {
-            const size_t old = out.size();
-            out.resize(old + s.size() - skip);
-            char* w = &out[old];
-            const char* r = s.data() + s.size() - 1 - skip;           // rev_comp_ of super_read_name.cc:106-114
-            for(size_t t = skip; t < s.size(); ++t) *w++ = revcomp_table.t[(unsigned char)*r--];
-          } else {
-            out.append(s, skip, std::string::npos);
-          }
+          if(skip < s.size()) out.append(s, skip, std::string::npos);
         }
       }
       out += '\n';

@@ -36,6 +36,7 @@ struct super_reads {
 struct unitigs {
   std::vector<int32_t>     len;
   std::vector<std::string> seq;          // only with -u
+  std::vector<std::string> rc_seq;       // reverse complements (rev_comp_ of super_read_name.cc:106-114), built once at load
   void load_lengths(const std::string& path);
   void load_sequences(const std::string& path);
 };

@@ -12,7 +12,7 @@ import pytest
 
 from oracle_lib import REF_CMR, gen_synth, have_ref, records
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -25,7 +25,7 @@ def sha(b):
 
 
 def run(cmd, **kw):
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, **kw)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     return r
 

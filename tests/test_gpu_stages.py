@@ -7,7 +7,7 @@ import pytest
 
 from oracle_lib import gen_synth, read_fasta
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture(scope="module")
@@ -108,6 +108,9 @@ def test_align_stages_match_oracle(case, ctx, port, forward):
     seqs.append(s0[:700] + "NNNN" + s0[704:1500] + "n" + s0[1501:2400])
     seqs.append("ACGT")
     seqs.append("")
+    _, srs = read_fasta(case["info"]["sr"])
+    longest = max(srs, key=len)
+    seqs.append(longest[:min(len(longest), 6000)])          # one chain of thousands of hits
     sub = pb.Reads(names=["r%d" % i for i in range(len(seqs))], seqs=seqs)
     uk = c["uk"] if forward else 0
     p = pb.default_params(unitigs_k=uk, run_graph=0, forward=int(forward))
@@ -165,6 +168,10 @@ def test_max_match_coords_match_oracle(case, ctx, port):
     _, srs = read_fasta(case["info"]["sr"])
     for s_ in [x for x in srs if len(x) > 2500][:6]:
         seqs.append(s_[100:1300] + "ACGTTGCA" + s_[100:1300] + s_[1300:2000])
+    # an error-free copy of a long super-read slice: one chain of thousands of hits (the long-chain
+    # finisher; a mis-compiled variant of it once hung on exactly this)
+    longest = max(srs, key=len)
+    seqs.append(longest[:min(len(longest), 6000)])
     n = len(seqs)
     sub = pb.Reads(names=["r%d" % i for i in range(n)], seqs=seqs)
     p = pb.default_params(unitigs_k=c["uk"], run_graph=0, max_match=1)

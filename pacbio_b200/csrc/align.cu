@@ -51,7 +51,7 @@ __device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, u
   const int total = LB + kTile + (int)k - 1;
   for(int i = threadIdx.x; i < total; i += kSeedThreads) {
     const int64_t p = (int64_t)tile_pos - LB + i;
-    codes[i] = (p >= 0 && p < (int64_t)rlen) ? base_code(bases[rstart + p]) : (uint8_t)4;
+    codes[i] = (p >= 0 && p < (int64_t)rlen) ? base_code(__ldcs(bases + rstart + p)) : (uint8_t)4;
   }
   __syncthreads();
   const int s0 = threadIdx.x * 4;
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
       }
     }
     const uint32_t pos = tpos + threadIdx.x * 4 + j;
-    if(pos < rlen) { rec[g0 + j] = out; size[g0 + j] = sz; }
+    // streaming stores (evict-first): the 20 B/base of output must not push the index tables out of L2
+    if(pos < rlen) { __stcs(rec + g0 + j, out); __stcs(size + g0 + j, sz); }
   }
   if(nlook) atomicAdd(&looked, nlook);
   if(ntail) atomicAdd(&scanned, ntail);

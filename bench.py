@@ -209,7 +209,7 @@ def reference_arm(args, w, files):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nreads = args.cpu_sample_reads or 1500
+    nreads = args.cpu_sample_reads or 20000          # ~200 Mbases: a few seconds of alignment on 16 cores per step
     vals = []
     meta = None
     for _ in range(args.warmup):

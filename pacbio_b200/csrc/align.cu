@@ -613,7 +613,9 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
   res->view.n_kmers_looked_up = h_ctr[0];
   res->view.n_tail_entries = h_ctr[6];
-  if(H >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 hits in one batch; use smaller batches");
+  // MR_MAX_HITS lowers the limit (tests of the callers' batch splitting)
+  static const uint64_t hit_limit = getenv("MR_MAX_HITS") ? strtoull(getenv("MR_MAX_HITS"), nullptr, 0) : (1ULL << 32);
+  if(H >= hit_limit) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many hits in one batch; use smaller batches");
 
   uint64_t G = 0, S = 0, cap = 0;
   const bool taps = ctx->keep_taps;

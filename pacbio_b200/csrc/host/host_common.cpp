@@ -508,4 +508,41 @@ void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0
   }
 }
 
+void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, std::string& out) {
+  uint64_t ng = 0, no = 0, nl = 0;
+  const int64_t* groups = nullptr; const int32_t* offsets = nullptr; const uint32_t* lis = nullptr;
+  if(mr_result_taps(r, &ng, &groups, &no, &offsets, &nl, &lis) != MR_OK) return;
+  char buf[64];
+  uint64_t off = 0, li = 0;
+  for(uint64_t g = 0; g < ng; ++g) {
+    const int64_t* row = groups + 6 * g;
+    const uint64_t nf = row[2], nb = row[3], lf = row[4], lb = row[5];
+    const int32_t* fwd = offsets + 2 * off; const int32_t* bwd = fwd + 2 * nf;
+    const uint32_t* lis_f = lis + li; const uint32_t* lis_b = lis_f + lf;
+    out += batch.name[row[0]]; out += ' '; out += sr.name[row[1]];
+    const bool fwd_align = lf > lb;                      // strict, unlike compute_coords_info
+    const uint32_t* lit = fwd_align ? lis_f : lis_b;
+    const uint32_t* lend = lit + (fwd_align ? lf : lb);
+    uint64_t fi = 0, bi = 0;
+    while(fi < nf || bi < nb) {
+      int32_t pb = 0, so = 0; bool in_lis = false, took = false;
+      if(fi < nf && (bi == nb || fwd[2 * fi] <= bwd[2 * bi])) {
+        pb = fwd[2 * fi]; so = fwd[2 * fi + 1];
+        in_lis = fwd_align && lit < lend && *lit == fi;
+        ++fi; took = true;
+      } else if(bi < nb && (fi == nf || bwd[2 * bi] < fwd[2 * fi])) {
+        pb = bwd[2 * bi]; so = bwd[2 * bi + 1];
+        in_lis = !fwd_align && lit < lend && *lit == bi;
+        ++bi; took = true;
+      }
+      if(!took) break;
+      snprintf(buf, sizeof(buf), in_lis ? " [%d:%d]" : " %d:%d", pb, so);
+      out += buf;
+      if(in_lis) ++lit;
+    }
+    out += '\n';
+    off += nf + nb; li += lf + lb;
+  }
+}
+
 } // namespace mrh

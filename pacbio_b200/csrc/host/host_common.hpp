@@ -91,4 +91,9 @@ void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, cons
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
                    bool compact, bool zero_skip, std::string& out);
 
+// jf_aligner --details records (jf_aligner.cc:72-108): one line per (read, super-read) pair with every
+// k-mer hit "pb:sr" in read order, the hits of the reported chain in brackets.  Needs the parity
+// taps of the result (mr_context_keep_taps).
+void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, std::string& out);
+
 } // namespace mrh

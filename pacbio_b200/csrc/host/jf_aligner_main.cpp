@@ -12,7 +12,7 @@ static const char* usage_text =
   " -s, --size=uint64  -m, --mer=uint32 (required)  -F, --fine-mer (not implemented)  --psa-min=uint32 (13)\n"
   " -t, --threads=uint32 (1)  --stretch-constant=int (10)  --stretch-factor=double (1.3)  --stretch-cap=double (10000.0)\n"
   "     --window-size=uint32 (1)  -f, --forward  -B, --bases-matching=double (17.0)  -M, --mers-matching=double (0.0)\n"
-  "     --details=path (not implemented)  --coords=path (stdout)  --max-match\n"
+  "     --details=path  --coords=path (stdout)  --max-match\n"
   " -H, --no-header  -0, --zero-match  --max-count=uint32 (5000)  -l, --unitigs-lengths=path  -u, --unitigs-sequences=path\n"
   "     --compact (toggles the compact format off)  -k, --k-mer=uint32  -r, --superreads=path  -p, --pacbio=path\n";
 
@@ -21,7 +21,7 @@ int main(int argc, char* argv[]) {
   bool size_given = false, mer_given = false, k_given = false, l_given = false, u_given = false;
   bool forward = false, no_header = false, zero_match = false, compact = true, coords_given = false, details_given = false;
   uint32_t mer = 0, psa_min = 13, k_mer = 0;
-  std::string unitigs_lengths, unitigs_sequences, coords_path;
+  std::string unitigs_lengths, unitigs_sequences, coords_path, details_path;
   mr_params P;
   mr_params_default(&P);
   double bases_matching = 17.0, mers_matching = 0.0;
@@ -58,7 +58,7 @@ int main(int argc, char* argv[]) {
     case 'f': forward = true; break;
     case 'B': bases_matching = to_double(optarg, "-B, --bases-matching=double"); break;
     case 'M': mers_matching = to_double(optarg, "-M, --mers-matching=double"); break;
-    case O_DETAILS: details_given = true; break;
+    case O_DETAILS: details_given = true; details_path = optarg; break;
     case O_COORDS: coords_given = true; coords_path = optarg; break;
     case O_MAXMATCH: P.max_match = 1; break;
     case 'H': no_header = true; break;
@@ -77,14 +77,19 @@ int main(int argc, char* argv[]) {
   if(l_given && u_given) error("Switches [-u, --unitigs-sequences=path] and [-l, --unitigs-lengths=path] are mutually exclusive");
   if(argc - optind != 0) error("Requires exactly 0 argument.");
   if(!details_given && !coords_given) error("No output file given. Doing nothing ungracefully.");
-  if(details_given) error("[--details] the per-k-mer details output is not implemented in this build");
+  if(details_given && P.max_match) error("[--details] is not available together with --max-match in this build");
   if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
   if((l_given || u_given) && !k_given)
     error("The mer length used for generating the k-unitigs (-k, --k-mer) is required if the unitig lengths (-l, --unitig-lengths or -u, --unitigs-sequences) is passed.");
 
   try {
-    FILE* out = fopen(coords_path.c_str(), "w");
+    FILE* out = coords_given ? fopen(coords_path.c_str(), "w") : stdout;     // jf_aligner.cc:175-179
     if(!out) throw std::runtime_error("Failed to open file '" + coords_path + "'");
+    FILE* details = nullptr;
+    if(details_given) {
+      details = fopen(details_path.c_str(), "w");
+      if(!details) throw std::runtime_error("Failed to open file '" + details_path + "'");
+    }
     mrh::unitigs U;
     if(l_given) U.load_lengths(unitigs_lengths);
     else if(u_given) U.load_sequences(unitigs_sequences);
@@ -104,12 +109,20 @@ int main(int argc, char* argv[]) {
       if(!compact) fputs(" Rname", out);
       fputs(" Qname\n", out);
     }
+    if(details) for(auto c : DS.ctx) mr_context_keep_taps(c, 1);
+    std::string dtext;
     mrh::run_pipeline(DS, pacbio, P,
-      [&](const mr_result_view& v, const mrh::read_batch& b, std::vector<std::string>& parts) {
+      [&](const mr_result* r, const mr_result_view& v, const mrh::read_batch& b, std::vector<std::string>& parts) {
         parts.resize(1);
         mrh::format_coords(v, b, 0, v.nreads, SR, compact, !zero_match, parts[0]);
+        if(details) {                      // single formatter thread: no lock needed
+          dtext.clear();
+          mrh::format_details(r, b, SR, dtext);
+          fwrite(dtext.data(), 1, dtext.size(), details);
+        }
       }, out);
-    fclose(out);
+    if(out != stdout) fclose(out);
+    if(details) fclose(details);
   } catch(std::exception& e) {
     std::cerr << "jf_aligner: " << e.what() << std::endl;
     return 1;

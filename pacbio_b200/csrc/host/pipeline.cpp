@@ -85,10 +85,31 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       job j;
       while(to_align.pop(j)) {
         if(!error.empty()) continue;
-        const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, j.batch->bases.data(), j.batch->start.data(),
-                                      j.batch->nreads(), &j.result);
-        if(rc != MR_OK) { fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g])); continue; }
-        to_format.push(std::move(j));
+        // A batch whose hits exceed a device limit (very repeat-rich reads) or the free memory is cut
+        // in halves and retried; the halves are formatted in order, so the output does not change.
+        std::deque<std::unique_ptr<read_batch>> work;
+        work.push_back(std::move(j.batch));
+        while(!work.empty() && error.empty()) {
+          std::unique_ptr<read_batch> b = std::move(work.front());
+          work.pop_front();
+          job part;
+          const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &part.result);
+          if(rc == MR_OK) { part.batch = std::move(b); to_format.push(std::move(part)); continue; }
+          if((rc == MR_ELIMIT || rc == MR_ENOMEM) && b->nreads() > 1) {
+            const uint32_t half = b->nreads() / 2;
+            std::unique_ptr<read_batch> lo(new read_batch), hi(new read_batch);
+            lo->bases.assign(b->bases, 0, b->start[half]);
+            lo->start.assign(b->start.begin(), b->start.begin() + half + 1);
+            lo->name.assign(b->name.begin(), b->name.begin() + half);
+            hi->bases.assign(b->bases, b->start[half], std::string::npos);
+            for(uint32_t r = half; r <= b->nreads(); ++r) hi->start.push_back(b->start[r] - b->start[half]);
+            hi->name.assign(b->name.begin() + half, b->name.end());
+            work.push_front(std::move(hi));
+            work.push_front(std::move(lo));
+            continue;
+          }
+          fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g]));
+        }
       }
       if(--live == 0) to_format.close();
     });
@@ -101,7 +122,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       mr_result_view v;
       mr_result_get(j.result, &v);
       for(auto& p : parts) p.clear();
-      try { format(v, *j.batch, parts); } catch(std::exception& e) { fail(e.what()); }
+      try { format(j.result, v, *j.batch, parts); } catch(std::exception& e) { fail(e.what()); }
       for(const auto& text : parts)
         if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
       mr_result_free(j.result);

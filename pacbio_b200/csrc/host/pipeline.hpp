@@ -57,7 +57,7 @@ std::vector<int> choose_devices();
 void build_indexes(device_set& ds, const std::vector<int>& devices, const super_reads& sr, const unitigs& u,
                    uint32_t psa_min, uint32_t mer);
 
-typedef std::function<void(const mr_result_view&, const read_batch&, std::vector<std::string>&)> format_fn;
+typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<std::string>&)> format_fn;
 
 // runs the whole stream; returns the number of read bases processed
 uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,

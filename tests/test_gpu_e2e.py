@@ -58,8 +58,9 @@ def assert_same_records(got, want, tie_reads=(), what=""):
 def test_reference_cli_goldens(tmp_path, forward):
     d = os.path.join(GOLD, "aligner_output")
     out = str(tmp_path / "coords")
+    det = str(tmp_path / "details")
     cmd = [JFA, "-s", "10k", "-m", "17", "-r", os.path.join(d, "test_super_reads.fa"), "-p",
-           os.path.join(d, "test_pacbio.fa"), "--stretch-cap", "200", "--coords", out]
+           os.path.join(d, "test_pacbio.fa"), "--stretch-cap", "200", "--coords", out, "--details", det]
     if forward:
         cmd += ["-l", os.path.join(d, "test_unitigs_lengths"), "-k", "65", "-f"]
     run(cmd)
@@ -69,6 +70,9 @@ def test_reference_cli_goldens(tmp_path, forward):
         f = line.split()
         want.append(tuple(f[:14]) + tuple(f[15:]))     # golden is the old non-compact layout (Rname column)
     assert got == sorted(want)
+    # --details: the reference's golden file, line for line (the reference sorts them too: tests/wdiffn -p sort)
+    golden = os.path.join(d, "details_forward_expected" if forward else "details_normal_expected")
+    assert sorted(open(det).read().splitlines()) == sorted(open(golden).read().splitlines())
 
 
 @pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
@@ -132,6 +136,16 @@ def test_max_match_text_against_reference(tmpdir_session, tmp_path, port):
         port.run(1, info["sr"], info["reads"], info["unitigs_len"], wantc, 15, 41, unitigs_is_fasta=False, max_match=True)
     assert_same_records(records(outc), records(wantc), what="coords")
     assert_same_records(records(out), records(want), reads_with_coords_ties(outc), what="mega reads")
+
+
+def test_oversized_batches_are_split(tmpdir_session, tmp_path):
+    """A batch that exceeds a device limit is cut in halves by the host pipeline; the records do not change."""
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_split"), 200000, coverage=4, read_len=4000, seed=21)
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"]]
+    a, b = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+    run(cmd + ["-o", a])
+    run(cmd + ["-o", b], env=dict(os.environ, MR_MAX_HITS="20000"))
+    assert open(a).read() == open(b).read() and len(open(a).read()) > 1000
 
 
 def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):

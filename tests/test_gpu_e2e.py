@@ -190,3 +190,24 @@ def test_arabidopsis_size_index_against_reference(tmpdir_session, tmp_path, port
         want = str(tmp_path / "ref.txt")
         run([REF_CMR] + common + ["-u", info["unitigs"], "-t", "16", "-o", want])
         assert_same_records(got, records(want), reads_with_coords_ties(coords), what="vs reference")
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs on the box (gpurun --gpus 2)")
+def test_reads_sharded_over_two_gpus_give_the_same_records(tmpdir_session, tmp_path):
+    """MR_GPUS=2: index replicated, batches dealt to the two devices, host gather; same records."""
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_2gpu"), 400000, coverage=6, read_len=5000, seed=23)
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-t", "4", "-r", info["sr"], "-p", info["reads"]]
+    one, two = str(tmp_path / "one.txt"), str(tmp_path / "two.txt")
+    env = dict(os.environ, MR_BATCH_BASES="300000")           # many small batches so that both devices get work
+    run(cmd + ["-o", one], env=env)
+    run(cmd + ["-o", two], env=dict(env, MR_GPUS="2"))
+    a, b = records(one), records(two)
+    assert len(a) > 300 and a == b

@@ -1,4 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- NOT PART OF THE PRODUCT.  See oracle_port.hpp.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include "oracle_port.hpp"
 
 #include <algorithm>
@@ -151,9 +154,23 @@ bool sr_index::locate(uint64_t x, uint32_t& sr, int32_t& off) const {
 // ===========================================================================
 // chaining  (reference: src_lis/lis_align.hpp:139-204, window_size == 1)
 // ===========================================================================
+// ORACLE_CHAIN_STATS=1: totals of the list walk (printed at exit), used to size the device kernels
+namespace {
+struct chain_stats_t {
+  std::atomic<uint64_t> lists{0}, hits{0}, front{0}, steps{0}, none{0}, none_steps{0}, depth{0}, big_lists{0}, big_hits{0}, big_steps{0}, big_depth{0}, big_front{0};
+  bool on = getenv("ORACLE_CHAIN_STATS") != nullptr;
+  ~chain_stats_t() {
+    if(on) fprintf(stderr, "chain stats: lists %llu hits %llu front-hit %llu steps %llu no-predecessor %llu (steps %llu) insert-depth %llu | lists>512: %llu hits %llu front %llu steps %llu depth %llu\n",
+      (unsigned long long)lists, (unsigned long long)hits, (unsigned long long)front, (unsigned long long)steps, (unsigned long long)none, (unsigned long long)none_steps,
+      (unsigned long long)depth, (unsigned long long)big_lists, (unsigned long long)big_hits, (unsigned long long)big_front, (unsigned long long)big_steps, (unsigned long long)big_depth);
+  }
+} chain_stats;
+}
+
 std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, double b, double C) {
   struct elt { uint32_t idx, len; double span_pb, span_sr; };
   const uint32_t N = X.size();
+  uint64_t st_front = 0, st_steps = 0, st_none = 0, st_none_steps = 0, st_depth = 0;
   std::vector<elt>      L;       // list order of the reference's forward_list
   std::vector<uint32_t> P(N, N);
   uint32_t longest = 0, best = 0;
@@ -161,6 +178,7 @@ std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, 
   for(uint32_t i = 0; i < N; ++i) {
     elt e = { i, 1, 0.0, 0.0 };
     int prev = -1;
+    size_t walked = L.size();
     for(size_t p = 0; p < L.size(); ++p) {      // every stored len is >= 1 == e.len: the walk only ends on a hit
       const uint32_t j = L[p].idx;
       if(X[i].second > X[j].second) {
@@ -171,14 +189,26 @@ std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, 
           P[i]  = j;
           e.span_pb = L[p].span_pb + d1;
           e.span_sr = L[p].span_sr + d2;
+          walked = p;
           break;
         }
       }
       if(prev < 0 || L[p].len < L[prev].len) prev = p;
     }
+    if(chain_stats.on) {
+      if(e.len > 1 && walked == 0) ++st_front;
+      st_steps += walked;
+      if(e.len == 1) { ++st_none; st_none_steps += walked; }
+      st_depth += prev + 1;
+    }
     L.insert(L.begin() + (prev + 1), e);
     const double s1 = a * e.span_sr, s2 = a * e.span_pb;
     if(longest < e.len && e.span_pb <= s1 && e.span_sr <= s2) { longest = e.len; best = i; }
+  }
+  if(chain_stats.on) {
+    chain_stats.lists++; chain_stats.hits += N; chain_stats.front += st_front; chain_stats.steps += st_steps;
+    chain_stats.none += st_none; chain_stats.none_steps += st_none_steps; chain_stats.depth += st_depth;
+    if(N > 512) { chain_stats.big_lists++; chain_stats.big_hits += N; chain_stats.big_front += st_front; chain_stats.big_steps += st_steps; chain_stats.big_depth += st_depth; }
   }
   std::vector<uint32_t> res(longest);
   for(uint32_t t = 0, cur = best; t < longest; ++t, cur = P[cur]) res[longest - 1 - t] = cur;

@@ -84,6 +84,7 @@ struct chain_args {
   uint32_t* group_nb; uint32_t* long_list; uint32_t* long_count; uint32_t* long_cursor;
   uint64_t* chain_pay;      // per group, at its slice: the chain's (pb, sr) pairs in chain order
   int max_match; uint8_t* removed;   // --max-match: hits already used by an emitted chain
+  uint32_t* dbg_cycles;              // MR_TRACE: SM cycles spent chaining each group
 };
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);
 

@@ -17,12 +17,16 @@
 // collectives) and the number of warps in flight.
 #include "align.cuh"
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
+#include <string>
+#include <vector>
 
 namespace {
 
-constexpr uint32_t kThreadFinishMax = 192;        // chains up to this many hits: one thread each, group order
-constexpr uint32_t kThreadFinishLongMax = 1536;   // longer chains up to this: one thread each, from the long list
+constexpr uint32_t kThreadFinishLongMax = 1536;   // chains up to this many hits: one thread each; longer: one warp each
 
 __device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
   const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
@@ -46,18 +50,40 @@ __device__ __forceinline__ double div_by_count(double x, double dn, double r) {
   return __fma_rn(rem, r, q);
 }
 
+// RN(1 / n) for the chain lengths one thread handles: the count is the same in every lane, so this
+// is one broadcast read from the constant cache instead of a ~40-instruction IEEE division per element
+constexpr uint32_t kRcpMax = 2048;
+__constant__ double kRcpTable[kRcpMax + 1];
+__device__ __forceinline__ double rcp_count(uint32_t n) { return n <= kRcpMax ? kRcpTable[n] : 1.0 / (double)n; }
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory strand: per warp arrays of CAP entries
 // ---------------------------------------------------------------------------------------------
-template<int CAP>
+// One group's working set, carved out of the block's dynamic shared memory: `cap` entries per
+// array, 22 B per hit in all (cap is a multiple of 64).
 struct warp_store {
-  int32_t  pb[CAP], sr[CAP], cpb[CAP], csr[CAP];
-  uint32_t meta[CAP];          // len << 16 | element index   (CAP <= 65536)
-  uint16_t pprev[CAP];         // by element index, 0xffff = none
+  int32_t  *pb, *sr, *cpb, *csr;
+  uint32_t *meta;              // len << 16 | element index   (cap <= 65536)
+  uint16_t *pprev;             // by element index, 0xffff = none
+  __device__ __forceinline__ warp_store(unsigned char* base, uint32_t cap) {
+    pb = reinterpret_cast<int32_t*>(base); sr = pb + cap; cpb = sr + cap; csr = cpb + cap;
+    meta = reinterpret_cast<uint32_t*>(csr + cap);
+    pprev = reinterpret_cast<uint16_t*>(meta + cap);
+  }
 };
+__host__ __device__ constexpr size_t warp_store_bytes(uint32_t cap, bool taps) {
+  return (size_t)cap * 22 + (taps ? (size_t)cap * 2 : 0);
+}
 
-template<int CAP, bool TAPS>
-__device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ pay, uint32_t N, bool neg, warp_store<CAP>& S,
+template<bool TAPS>
+__device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const warp_store& S,
                                                   uint16_t* sub, double a, double b, double C,
                                                   uint32_t& longest_out, uint32_t& best_out) {
   const unsigned lane = threadIdx.x & 31;
@@ -142,20 +168,47 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
       }
       ++cnt;
       if(longest < e_len && accept_sequence(pb_i - cpb, sr_i - csr, a)) { longest = e_len; best = i; }
-      if(q != 0) { __syncwarp(); continue; }        // not at the front: its successors take the normal route
-      fr_pb = pb_i; fr_sr = sr_i; fr_cpb = cpb; fr_csr = csr; fr_meta = (e_len << 16) | i;
+      if(q == 0) { fr_pb = pb_i; fr_sr = sr_i; fr_cpb = cpb; fr_csr = csr; fr_meta = (e_len << 16) | i; }
+      else if(q > 32) { __syncwarp(); continue; }   // deep in the list: its successors take the normal route
 
-      // Run: the hits right after this one that each extend their predecessor.  They are appended
-      // together: lane t of the run gets len + 1 + t, the same chain start, its predecessor as back pointer.
+      // Run: the hits right after this one that each extend their predecessor.  When such a hit is
+      // processed its predecessor sits at list position q, so its walk passes the same q entries this
+      // one passed: if none of them is feasible for it, the walk stops on the predecessor and the first
+      // strict minimum of len over those q entries is again entry q - 1 -- the hit lands at position q
+      // too, in front of its predecessor.  The whole run is appended in one step: lane t of the run gets
+      // len + 1 + t, the same chain start, its predecessor as back pointer.  (q == 0, nothing in
+      // front, is the common case; q > 0 happens when an early stray hit with a large super-read
+      // offset stays at the list front and every hit of the real alignment files in behind it.)
       const unsigned stop_mask = todo & ~ext_mask;
-      const unsigned run = stop_mask ? (todo & ((1u << (__ffs(stop_mask) - 1)) - 1)) : todo;
+      unsigned run = stop_mask ? (todo & ((1u << (__ffs(stop_mask) - 1)) - 1)) : todo;
+      if(run && q != 0) {
+        __syncwarp();
+        bool blocked = false;
+        if((run >> lane) & 1) {
+          for(uint32_t p = 0; p < q; ++p) {
+            const uint32_t slot = cnt - 1 - p;
+            const int32_t lsr = S.sr[slot], lpb = S.pb[slot];
+            blocked |= sr_l > lsr && accept_mer(pb_l, sr_l, lpb, lsr, a, b, C);
+          }
+        }
+        const unsigned bm = __ballot_sync(MR_FULL_MASK, blocked);
+        if(bm) run &= (1u << (__ffs(bm) - 1)) - 1;
+        if(run) {                                   // the q entries in front move up by the run's length
+          const uint32_t r = __popc(run), s = cnt - q + lane;
+          const bool has = lane < q;
+          int32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0; uint32_t v4 = 0;
+          if(has) { v0 = S.pb[s]; v1 = S.sr[s]; v2 = S.cpb[s]; v3 = S.csr[s]; v4 = S.meta[s]; }
+          __syncwarp();
+          if(has) { S.pb[s + r] = v0; S.sr[s + r] = v1; S.cpb[s + r] = v2; S.csr[s + r] = v3; S.meta[s + r] = v4; }
+        }
+      }
       if(run) {
         const uint32_t r = __popc(run);
         const bool inrun = (run >> lane) & 1;
         const uint32_t t = __popc(run & lt);
         const uint32_t my_len = e_len + 1 + t;
         if(inrun) {
-          const uint32_t s = cnt + t;
+          const uint32_t s = cnt - q + t;
           S.pb[s] = pb_l; S.sr[s] = sr_l; S.cpb[s] = cpb; S.csr[s] = csr; S.meta[s] = (my_len << 16) | il;
           S.pprev[il] = (uint16_t)(base + pred_lane);
           if(TAPS) sub[il] = (uint16_t)(nsub + t);
@@ -168,9 +221,11 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
           longest = e_len + 1 + __popc(run & ((1u << hl) - 1));
           best = base + hl;
         }
-        const int last = 31 - __clz(run);
-        fr_pb = __shfl_sync(MR_FULL_MASK, pb_l, last); fr_sr = __shfl_sync(MR_FULL_MASK, sr_l, last);
-        fr_meta = ((e_len + r) << 16) | (base + last);
+        if(q == 0) {
+          const int last = 31 - __clz(run);
+          fr_pb = __shfl_sync(MR_FULL_MASK, pb_l, last); fr_sr = __shfl_sync(MR_FULL_MASK, sr_l, last);
+          fr_meta = ((e_len + r) << 16) | (base + last);
+        }
         cnt += r; nsub += r; todo &= ~run;
       }
       __syncwarp();
@@ -413,7 +468,7 @@ __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_
     for(int j = 0; j < 4; ++j) nq[j] = t0 + 4 + j < nb ? cp[t0 + 4 + j] : 0;
 #pragma unroll
     for(int j = 0; j < 4; ++j)
-      if(t0 + j < nb) c.add((int32_t)(uint32_t)q[j], (int32_t)(uint32_t)(q[j] >> 32), k, 1.0 / (double)(t0 + j + 1));
+      if(t0 + j < nb) c.add((int32_t)(uint32_t)q[j], (int32_t)(uint32_t)(q[j] >> 32), k, rcp_count(t0 + j + 1));
 #pragma unroll
     for(int j = 0; j < 4; ++j) q[j] = nq[j];
   }
@@ -436,7 +491,13 @@ __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// bins groups by size; list c holds the group ids of class c (0: <=64, 1: <=1024, 2: <=4096, 3: larger)
+// bins groups by size; list c holds the group ids of class c: class c < kSmemTiers holds the groups
+// of at most kTierCap[c] hits (and more than the tier below), the last class everything larger
+constexpr int kSmemTiers = 9;
+constexpr int kClasses = kSmemTiers + 1;
+__constant__ uint32_t kTierCap[kSmemTiers] = { 64, 256, 512, 768, 1024, 1536, 2048, 3072, 4096 };
+constexpr uint32_t kTierCapHost[kSmemTiers] = { 64, 256, 512, 768, 1024, 1536, 2048, 3072, 4096 };
+constexpr uint32_t kTierWarps[kSmemTiers]   = { 8, 8, 4, 4, 2, 1, 1, 1, 1 };       // warps (= groups in flight) per block
 // Single-hit groups (most groups: spurious k-mer matches) need no chaining at all: their chain is
 // hit 0, which this kernel records directly.
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
@@ -448,7 +509,9 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
   if(g < ngroups) {
     const uint64_t gs = group_start[g];
     const uint64_t n = group_start[g + 1] - gs;
-    cls = n <= 64 ? 0 : (n <= 1024 ? 1 : (n <= 4096 ? 2 : 3));
+    cls = kSmemTiers;
+#pragma unroll
+    for(int c = kSmemTiers - 1; c >= 0; --c) if(n <= kTierCap[c]) cls = c;
     if(n == 1 && singles_here) {
       cls = -1;
       const uint64_t p = pays[gs];
@@ -458,7 +521,7 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
   }
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-  for(int c = 0; c < 4; ++c) {
+  for(int c = 0; c < kClasses; ++c) {
     const unsigned m = __ballot_sync(MR_FULL_MASK, cls == c);
     if(!m) continue;
     unsigned base = 0;
@@ -468,14 +531,17 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
   }
 }
 
-template<int CAP, int WARPS, bool TAPS>
-__global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_args A, const uint32_t* __restrict__ list,
-                                                                       const uint32_t* __restrict__ list_count,
-                                                                       uint32_t* __restrict__ cursor) {
+// strands of the groups of one size class, out of shared memory: one warp per group, `cap` hits of
+// room per warp
+template<bool TAPS>
+__global__ void __launch_bounds__(256) chain_coords_smem_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                                const uint32_t* __restrict__ list_count,
+                                                                uint32_t* __restrict__ cursor, uint32_t cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  warp_store<CAP>& S = reinterpret_cast<warp_store<CAP>*>(smem_raw)[wib];
-  uint16_t* sub = TAPS ? reinterpret_cast<uint16_t*>(smem_raw + sizeof(warp_store<CAP>) * WARPS) + wib * CAP : nullptr;
+  unsigned char* mine_raw = smem_raw + warp_store_bytes(cap, TAPS) * wib;
+  const warp_store S(mine_raw, cap);
+  uint16_t* sub = TAPS ? reinterpret_cast<uint16_t*>(mine_raw + warp_store_bytes(cap, false)) : nullptr;
   const uint32_t total = *list_count;
   while(true) {
     uint32_t w = 0;
@@ -485,10 +551,11 @@ __global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_arg
     const uint32_t g = list[w];
     const uint64_t gs = A.group_start[g];
     const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    const long long dbg_t0 = A.dbg_cycles ? clock64() : 0;
     uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
-    chain_strand_smem<CAP, TAPS>(A.pays + gs, N, false, S, sub, A.a, A.b, A.C, len_f, best_f);
+    chain_strand_smem<TAPS>(A.pays + gs, N, false, S, sub, A.a, A.b, A.C, len_f, best_f);
     __syncwarp();
-    chain_strand_smem<CAP, TAPS>(A.pays + gs, N, true, S, sub, A.a, A.b, A.C, len_b, best_b);
+    chain_strand_smem<TAPS>(A.pays + gs, N, true, S, sub, A.a, A.b, A.C, len_b, best_b);
     __syncwarp();
     const bool fwd_align = len_f >= len_b;
     const uint32_t nb = fwd_align ? len_f : len_b;
@@ -514,7 +581,8 @@ __global__ void __launch_bounds__(WARPS * 32) chain_coords_smem_kernel(chain_arg
     for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + t] = A.pays[gs + chain[t]];
     if(lane == 0) {
       A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
-      if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
+      if(A.dbg_cycles) A.dbg_cycles[g] = (uint32_t)(clock64() - dbg_t0);
+      if(nb > kThreadFinishLongMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
     }
     __syncwarp();
   }
@@ -560,30 +628,109 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
     for(uint32_t t = lane; t < nb; t += 32) A.chain_pay[gs + t] = A.pays[gs + chain[t]];
     if(lane == 0) {
       A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
-      if(nb > kThreadFinishMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
+      if(nb > kThreadFinishLongMax) A.long_list[atomicAdd(A.long_count, 1u)] = g;
     }
     __syncwarp();
   }
 }
 
-// coords of every group whose chain length is in (lo, hi]: one thread per group.  With list == null
-// thread i takes group i, otherwise list entry i (the long chains: warps then hold 32 chains of
-// comparable length, the recurrence of each is latency bound, 32 of them share every instruction).
-__global__ void __launch_bounds__(128) finish_thread_kernel(chain_args A, const uint32_t* __restrict__ list,
-                                                             const uint32_t* __restrict__ list_count, uint32_t lo, uint32_t hi) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= (list ? (uint64_t)*list_count : A.ngroups)) return;
-  const uint64_t g = list ? list[i] : i;
-  const uint32_t v = A.group_nb[g];
-  const uint32_t nb = v & 0x7fffffffu;
-  if(nb <= lo || nb > hi) return;
+// coords, one thread per group: warps hold 32 chains, the FP64 recurrence of each is latency bound
+// and 32 of them share every instruction.
+// (1) every group of at most max_group hits, in group order (neighbouring threads read neighbouring chains)
+__global__ void __launch_bounds__(128) finish_small_groups_kernel(chain_args A, uint32_t max_group) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= A.ngroups) return;
   const uint64_t gs = A.group_start[g];
+  if(A.group_start[g + 1] - gs > max_group) return;
+  const uint32_t v = A.group_nb[g];
   const uint64_t key = A.keys[gs];
-  finish_group_thread(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, nb);
+  finish_group_thread(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
+}
+// (2) the groups of one size class, right behind the kernel that chained them (chains longer than
+// hi went to the long list).  A warp takes 32 chains, one per lane; each chain is a private stream
+// of 8-byte pairs, so the lanes do not read them themselves (32 different cache lines per load, and
+// next to the chaining kernels the L1 is a few KB): the warp copies 16 pairs of every chain into a
+// shared-memory tile with coalesced cp.async, the next tile in flight while the current one is folded in.
+constexpr int kTileE = 16;
+__global__ void __launch_bounds__(128) finish_tile_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                           const uint32_t* __restrict__ list_count, uint32_t hi) {
+  __shared__ uint64_t tile[4][2][32][kTileE + 1];      // + 1: lane j reads row j, 17 x 8 B apart -> no bank conflicts
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t total = *list_count;
+  const uint32_t k = A.iv.k;
+  const uint32_t stride = gridDim.x * 4 * 32;
+  for(uint32_t i0 = (blockIdx.x * 4 + wib) * 32; i0 < total; i0 += stride) {
+    const uint32_t i = i0 + lane;
+    uint32_t v = 0, nb = 0;
+    uint64_t gs = 0;
+    if(i < total) {
+      const uint32_t g = list[i];
+      v = A.group_nb[g]; nb = v & 0x7fffffffu;
+      if(nb > hi) nb = 0;
+      gs = A.group_start[g];
+    }
+    const uint32_t maxnb = __reduce_max_sync(MR_FULL_MASK, nb);
+    if(maxnb == 0) continue;
+    auto issue = [&](uint32_t t0, int buf) {
+#pragma unroll 4
+      for(int it = 0; it < 16; ++it) {                  // two chains per step, 16 lanes (128 B) each
+        const int jj = it * 2 + (int)(lane >> 4);
+        const uint64_t bj = __shfl_sync(MR_FULL_MASK, gs, jj);
+        const uint32_t nj = __shfl_sync(MR_FULL_MASK, nb, jj);
+        const uint32_t e = t0 + (lane & 15);
+        if(e < nj) cp_async8(&tile[wib][buf][jj][lane & 15], A.chain_pay + bj + e);
+      }
+      cp_async_commit();
+    };
+    coords_acc c(k);
+    int buf = 0;
+    issue(0, 0);
+    for(uint32_t t0 = 0; t0 < maxnb; t0 += kTileE) {
+      if(t0 + kTileE < maxnb) { issue(t0 + kTileE, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll 4
+      for(uint32_t e = 0; e < kTileE; ++e) {
+        if(t0 + e < nb) {
+          const uint64_t p = tile[wib][buf][lane][e];
+          c.add((int32_t)(uint32_t)p, (int32_t)(uint32_t)(p >> 32), k, rcp_count(t0 + e + 1));
+        }
+      }
+      __syncwarp();
+      buf ^= 1;
+    }
+    double stretch = 1.0, offset = c.EY - c.EX, avg_err = 0;
+    const bool fit = nb > 1;
+    if(fit) { stretch = c.CXY / c.VX; offset = c.NB / c.VX; }
+    if(__any_sync(MR_FULL_MASK, fit)) {
+      double err = 0;
+      buf = 0;
+      issue(0, 0);
+      for(uint32_t t0 = 0; t0 < maxnb; t0 += kTileE) {
+        if(t0 + kTileE < maxnb) { issue(t0 + kTileE, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll 4
+        for(uint32_t e = 0; e < kTileE; ++e) {
+          if(t0 + e < nb) {
+            const uint64_t p = tile[wib][buf][lane][e];
+            const double x = (double)(int32_t)(uint32_t)(p >> 32), y = (double)(int32_t)(uint32_t)p;
+            const double prod = stretch * x;
+            err += fabs(prod + offset - y);
+          }
+        }
+        __syncwarp();
+        buf ^= 1;
+      }
+      if(fit) avg_err = err / (double)c.n;
+    }
+    if(nb != 0) {
+      const uint64_t key = A.keys[gs];
+      publish_coords(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, nb, c, stretch, offset, avg_err);
+    }
+  }
 }
 
 // ... and of the very long chains: one warp per group
-__global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t lo) {
+__global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t total = *A.long_count;
   while(true) {
@@ -593,7 +740,6 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A, uint32_t
     if(w >= total) break;
     const uint32_t g = A.long_list[w];
     const uint32_t v = A.group_nb[g];
-    if((v & 0x7fffffffu) <= lo) continue;
     const uint64_t gs = A.group_start[g];
     const uint64_t key = A.keys[gs];
     finish_group_warp<false>(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
@@ -653,82 +799,153 @@ __global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8
   }
 }
 
-template<int CAP, int WARPS, bool TAPS>
-int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, const uint32_t* list, const uint32_t* count, uint32_t* cursor, int blocks_per_sm) {
-  const size_t smem = sizeof(warp_store<CAP>) * WARPS + (TAPS ? (size_t)WARPS * CAP * sizeof(uint16_t) : 0);
-  MR_CUDA(ctx, cudaFuncSetAttribute(chain_coords_smem_kernel<CAP, WARPS, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chain_coords_smem_kernel<CAP, WARPS, TAPS><<<ctx->sm_count * blocks_per_sm, WARPS * 32, smem, st>>>(A, list, count, cursor);
+template<bool TAPS>
+int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, int tier, const uint32_t* list, const uint32_t* count, uint32_t* cursor) {
+  const uint32_t cap = kTierCapHost[tier], warps = kTierWarps[tier];
+  const size_t smem = warp_store_bytes(cap, TAPS) * warps;
+  MR_CUDA(ctx, cudaFuncSetAttribute(chain_coords_smem_kernel<TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_store_bytes(4096, TAPS)));
+  // as many blocks as one SM can hold at a time (shared memory, 64 warps, 32 blocks), on every SM
+  const size_t per_sm = 227 * 1024;
+  const uint32_t fit = (uint32_t)std::min<size_t>(std::min<size_t>(per_sm / (smem + 1024), 64 / warps), 32);
+  chain_coords_smem_kernel<TAPS><<<ctx->sm_count * std::max(fit, 1u), warps * 32, smem, st>>>(A, list, count, cursor, cap);
   MR_LAUNCHED(ctx);
   return MR_OK;
 }
 
 } // namespace
 
-// scratch `lists`: 5 x ngroups uint32 (4 size classes + long-chain list), ngroups uint32 verdicts,
-// 16 uint32 counters (class counts 0..3, class cursors 4..7, long count 8, long cursor 9)
+// scratch `lists`: (kClasses + 2) x ngroups uint32 (size classes, long-chain list, verdicts) + 32 uint32
+// counters (class counts 0..9, class cursors 16..25, long count 28, long cursor 29, max-match cursor 30)
 // MR_TRACE=1: synchronise after every chain-phase kernel and name it on stderr
 static const bool g_chain_trace = getenv("MR_TRACE") != nullptr;
-#define CHAIN_TRACE(st, name) do { if(g_chain_trace) { cudaError_t e_ = cudaStreamSynchronize(st); \
-  fprintf(stderr, "[mr]   %s: %s\n", name, cudaGetErrorString(e_)); fflush(stderr); } } while(0)
+static double trace_now() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static double g_trace_t0 = 0;
+#define CHAIN_TRACE(st, name) do { if(g_chain_trace) { cudaError_t e_ = cudaStreamSynchronize(st); const double n_ = trace_now(); \
+  fprintf(stderr, "[mr]   %-34s %8.3f ms  %s\n", name, 1e3 * (n_ - g_trace_t0), cudaGetErrorString(e_)); fflush(stderr); g_trace_t0 = trace_now(); } } while(0)
+
+// MR_TRACE_TIMELINE=1: timing events around every chain-phase kernel, no extra synchronisation; the
+// start / end of each kernel relative to the start of the phase is printed once the phase is over
+static const bool g_chain_timeline = getenv("MR_TRACE_TIMELINE") != nullptr;
+struct timeline_t {
+  struct item { std::string name; cudaEvent_t b, e; };
+  std::vector<item> items;
+  cudaEvent_t origin = nullptr;
+  void begin(cudaStream_t st) { if(!g_chain_timeline) return; cudaEventCreate(&origin); cudaEventRecord(origin, st); }
+  void open(const char* name, cudaStream_t st) { if(!g_chain_timeline) return; item it; it.name = name; cudaEventCreate(&it.b); cudaEventCreate(&it.e); cudaEventRecord(it.b, st); items.push_back(it); }
+  void close(cudaStream_t st) { if(!g_chain_timeline) return; cudaEventRecord(items.back().e, st); }
+  void report() {
+    if(!g_chain_timeline) return;
+    cudaDeviceSynchronize();
+    for(auto& it : items) {
+      float b = 0, e = 0;
+      cudaEventElapsedTime(&b, origin, it.b); cudaEventElapsedTime(&e, origin, it.e);
+      fprintf(stderr, "[mr]   timeline %-28s %8.3f -> %8.3f ms\n", it.name.c_str(), b, e);
+      cudaEventDestroy(it.b); cudaEventDestroy(it.e);
+    }
+    cudaEventDestroy(origin); items.clear();
+  }
+};
 
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(A.ngroups == 0) return MR_OK;
   if(A.ngroups >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "more than 2^32 (read, super-read) groups in one batch");
   const uint64_t G = A.ngroups;
-  MR_TRY(lists.ensure(ctx, (6 * G + 16) * sizeof(uint32_t)));
+  MR_TRY(lists.ensure(ctx, ((kClasses + 2) * G + 32) * sizeof(uint32_t)));
   uint32_t* cls = lists.as<uint32_t>();
-  uint32_t* ctr = cls + 6 * G;
-  A.long_list = cls + 4 * G; A.group_nb = cls + 5 * G; A.long_count = ctr + 8; A.long_cursor = ctr + 9;
-  MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 16 * sizeof(uint32_t), ctx->stream));
+  uint32_t* ctr = cls + (kClasses + 2) * G;
+  A.long_list = cls + kClasses * G; A.group_nb = cls + (kClasses + 1) * G; A.long_count = ctr + 28; A.long_cursor = ctr + 29;
+  MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 32 * sizeof(uint32_t), ctx->stream));
+  if(!ctx->chain_tables) {
+    std::vector<double> rcp(kRcpMax + 1, 0.0);
+    for(uint32_t n = 1; n <= kRcpMax; ++n) rcp[n] = 1.0 / (double)n;
+    MR_CUDA(ctx, cudaMemcpyToSymbol(kRcpTable, rcp.data(), rcp.size() * sizeof(double)));
+    ctx->chain_tables = true;
+  }
+  static dev_buf dbg;
+  if(g_chain_trace && getenv("MR_TRACE_CYCLES")) { MR_TRY(dbg.ensure(ctx, G * 4)); cudaMemset(dbg.p, 0, G * 4); A.dbg_cycles = dbg.as<uint32_t>(); }
+  if(g_chain_trace) { cudaStreamSynchronize(ctx->stream); g_trace_t0 = trace_now(); }
   // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
-  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb, A.tap_lens == nullptr && !A.max_match, cls, ctr);
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb,
+                                                                  A.tap_lens == nullptr && !A.max_match, cls, ctr);
   MR_LAUNCHED(ctx);
   CHAIN_TRACE(ctx->stream, "classify");
   if(A.max_match) {
-    chain_maxmatch_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, A.removed, ctr + 4);
+    chain_maxmatch_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(A, A.removed, ctr + 30);
     MR_LAUNCHED(ctx);
     return MR_OK;
   }
   const bool taps = A.tap_lens != nullptr;
-  // The big-group tiers have few, long, latency-bound groups; they run on a side stream next to the
-  // mid/small tiers.  Likewise the three finishing kernels (independent groups) run side by side.
-  cudaStream_t s0 = ctx->stream, s1 = ctx->aux[0], s2 = ctx->aux[1];
+  // Every size class is latency bound (a group is a sequential walk) and limited by the shared
+  // memory its tier needs; the tiers run on separate streams, largest groups first, so that together
+  // they fill the SMs, and each is followed on its stream by the kernel that turns its chains into coords.
+  cudaStream_t s0 = ctx->stream;
   MR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s0));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev[0], 0));
-  chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, s1>>>(A, cls + 3 * G, ctr + 3, ctr + 7);
-  MR_LAUNCHED(ctx);
-  CHAIN_TRACE(s1, "strands, global tier");
-  if(taps) {
-    MR_TRY((launch_smem<4096, 2, true>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
-    MR_TRY((launch_smem<1024, 4, true>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
-    MR_TRY((launch_smem<64, 8, true>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
-  } else {
-    MR_TRY((launch_smem<4096, 2, false>(ctx, s1, A, cls + 2 * G, ctr + 2, ctr + 6, 1)));
-    CHAIN_TRACE(s1, "strands, 4096 tier");
-    MR_TRY((launch_smem<1024, 4, false>(ctx, s0, A, cls + 1 * G, ctr + 1, ctr + 5, 2)));
-    CHAIN_TRACE(s0, "strands, 1024 tier");
-    MR_TRY((launch_smem<64, 8, false>(ctx, s0, A, cls, ctr + 0, ctr + 4, 8)));
-    CHAIN_TRACE(s0, "strands, 64 tier");
+  char label[64];
+  timeline_t tl;
+  tl.begin(s0);
+  for(int c = kClasses - 1; c >= 0; --c) {
+    cudaStream_t st = c == 0 ? s0 : ctx->aux[c - 1];
+    if(c != 0) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[0], 0));
+    const uint32_t* list = cls + (uint64_t)c * G;
+    snprintf(label, sizeof label, "strands %d", c); tl.open(label, st);
+    if(c == kSmemTiers) {
+      chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, ctr + 16 + c);
+      MR_LAUNCHED(ctx);
+    } else if(taps) { MR_TRY(launch_smem<true>(ctx, st, A, c, list, ctr + c, ctr + 16 + c)); }
+    else            { MR_TRY(launch_smem<false>(ctx, st, A, c, list, ctr + c, ctr + 16 + c)); }
+    tl.close(st);
+    if(g_chain_trace) { snprintf(label, sizeof label, "strands, tier %d (<= %u hits)", c, c < kSmemTiers ? kTierCapHost[c] : 0u); CHAIN_TRACE(st, label); }
+    snprintf(label, sizeof label, "finish %d", c); tl.open(label, st);
+    if(c != 0) {
+      finish_tile_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, kThreadFinishLongMax);
+      MR_LAUNCHED(ctx);
+      tl.close(st);
+      if(g_chain_trace) { snprintf(label, sizeof label, "finish, tier %d", c); CHAIN_TRACE(st, label); }
+      MR_CUDA(ctx, cudaEventRecord(ctx->ev[c], st));
+    } else {
+      finish_small_groups_kernel<<<div_up(G, 128), 128, 0, st>>>(A, kTierCapHost[0]);
+      MR_LAUNCHED(ctx);
+      tl.close(st);
+      CHAIN_TRACE(st, "finish, small groups");
+    }
   }
-  // all strands done -> finishing kernels on three streams
-  MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[1], 0));
-  MR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s0));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->ev[2], 0));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev[2], 0));
-  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, s1>>>(A, kThreadFinishLongMax);
+  for(int c = 1; c < kClasses; ++c) MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[c], 0));
+  tl.open("finish warp", s0);
+  finish_warp_kernel<<<ctx->sm_count * 8, 128, 0, s0>>>(A);      // chains too long for one thread
   MR_LAUNCHED(ctx);
-  CHAIN_TRACE(s1, "finish, warp per chain");
-  finish_thread_kernel<<<div_up(G, 128), 128, 0, s2>>>(A, A.long_list, A.long_count, kThreadFinishMax, kThreadFinishLongMax);
-  MR_LAUNCHED(ctx);
-  CHAIN_TRACE(s2, "finish, thread per long chain");
-  finish_thread_kernel<<<div_up(G, 128), 128, 0, s0>>>(A, nullptr, nullptr, 0, kThreadFinishMax);
-  MR_LAUNCHED(ctx);
-  CHAIN_TRACE(s0, "finish, thread per short chain");
-  MR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s1));
-  MR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s2));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[1], 0));
-  MR_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev[3], 0));
+  tl.close(s0);
+  tl.report();
+  CHAIN_TRACE(s0, "finish, warp per chain");
+  if(g_chain_trace && A.dbg_cycles) {
+    cudaDeviceSynchronize();
+    std::vector<uint32_t> cyc(G), nbv(G); std::vector<uint64_t> gs(G + 1);
+    cudaMemcpy(cyc.data(), A.dbg_cycles, G * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(nbv.data(), A.group_nb, G * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(gs.data(), A.group_start, (G + 1) * 8, cudaMemcpyDeviceToHost);
+    std::vector<uint32_t> order(G);
+    for(uint64_t i = 0; i < G; ++i) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cyc[x] > cyc[y]; });
+    double tot = 0; for(uint64_t i = 0; i < G; ++i) tot += cyc[i];
+    fprintf(stderr, "[mr]   chaining cycles: total %.3g; slowest groups (cycles, hits, chain):", tot);
+    for(int i = 0; i < 12 && i < (int)G; ++i) { const uint32_t g = order[i]; fprintf(stderr, " (%u, %llu, %u)", cyc[g], (unsigned long long)(gs[g + 1] - gs[g]), nbv[g] & 0x7fffffffu); }
+    fprintf(stderr, "\n");
+    for(int w = 0; w < 2 && w < (int)G; ++w) {
+      const uint32_t g = order[w];
+      const uint64_t n = gs[g + 1] - gs[g];
+      std::vector<uint64_t> pv(n);
+      cudaMemcpy(pv.data(), A.pays + gs[g], n * 8, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[mr]   slow group %u:", g);
+      for(uint64_t t = 0; t < n && t < 120; ++t) fprintf(stderr, " %d:%d", (int32_t)(uint32_t)pv[t], (int32_t)(uint32_t)(pv[t] >> 32));
+      fprintf(stderr, "\n");
+    }
+  }
+  if(g_chain_trace) {
+    uint32_t h[32];
+    cudaMemcpy(h, ctr, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[mr]   groups per class:");
+    for(int c = 0; c < kClasses; ++c) fprintf(stderr, " %u", h[c]);
+    fprintf(stderr, "  very long chains: %u\n", h[28]);
+  }
   return MR_OK;
 }
 

@@ -21,11 +21,12 @@ struct mr_context {
   mr_workspace* ws = nullptr;          // scratch reused across batches (align.cu)
   int          device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t aux[2] = { nullptr, nullptr };   // side streams for kernels that may overlap (chain tiers)
-  cudaEvent_t  ev[4] = { nullptr, nullptr, nullptr, nullptr };
+  cudaStream_t aux[9] = { };   // side streams for kernels that may overlap (chain tiers)
+  cudaEvent_t  ev[10] = { };
   std::string  err;
   uint64_t     launches = 0;
   bool         keep_taps = false;
+  bool         chain_tables = false;   // constant tables of chain.cu uploaded to this device
   std::vector<std::pair<std::string, double>> timers;
   int          sm_count = kNumSMs;
 

@@ -498,12 +498,16 @@ constexpr int kClasses = kSmemTiers + 1;
 __constant__ uint32_t kTierCap[kSmemTiers] = { 64, 256, 512, 768, 1024, 1536, 2048, 3072, 4096 };
 constexpr uint32_t kTierCapHost[kSmemTiers] = { 64, 256, 512, 768, 1024, 1536, 2048, 3072, 4096 };
 constexpr uint32_t kTierWarps[kSmemTiers]   = { 8, 8, 4, 4, 2, 1, 1, 1, 1 };       // warps (= groups in flight) per block
+// groups of 2 .. kTinyMax hits (chance matches of a 16- or 17-mer: most groups that are not single
+// hits) get one THREAD each, list kClasses; a warp per two-hit group would waste 30 lanes on ~800 instructions
+constexpr uint32_t kTinyMax = 8;
 // Single-hit groups (most groups: spurious k-mer matches) need no chaining at all: their chain is
 // hit 0, which this kernel records directly.
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
                                                                const uint64_t* __restrict__ pays, uint64_t* __restrict__ chain_pay,
                                                                uint32_t* __restrict__ group_nb, bool singles_here,
                                                                uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
+  // (singles_here is false with parity taps or --max-match on: then every group goes to the strand kernels)
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1;
   if(g < ngroups) {
@@ -517,17 +521,62 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
       const uint64_t p = pays[gs];
       chain_pay[gs] = p;
       group_nb[g] = 1u | ((int32_t)(uint32_t)(p >> 32) > 0 ? 0x80000000u : 0u);
-    }
+    } else if(n <= kTinyMax && singles_here) cls = kClasses;
   }
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-  for(int c = 0; c < kClasses; ++c) {
+  for(int c = 0; c <= kClasses; ++c) {
     const unsigned m = __ballot_sync(MR_FULL_MASK, cls == c);
     if(!m) continue;
     unsigned base = 0;
     if(lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counts + c, __popc(m));
     base = __shfl_sync(MR_FULL_MASK, base, __ffs(m) - 1);
     if(cls == c) lists[(uint64_t)c * ngroups + base + __popc(m & lanemask_lt())] = (uint32_t)g;
+  }
+}
+
+// chains of the tiny groups: one thread per group runs compute_L_P as written (lis_align.hpp:139-182)
+// on arrays of kTinyMax entries
+__global__ void __launch_bounds__(128) chain_tiny_kernel(chain_args A, const uint32_t* __restrict__ list,
+                                                          const uint32_t* __restrict__ list_count) {
+  const uint32_t total = *list_count;
+  for(uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const uint32_t g = list[w];
+    const uint64_t gs = A.group_start[g];
+    const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
+    int32_t pb[kTinyMax], sr[kTinyMax];
+    uint8_t len[kTinyMax], cstart[kTinyMax], pprev[kTinyMax], L[kTinyMax];
+    for(uint32_t i = 0; i < N; ++i) { const uint64_t p = A.pays[gs + i]; pb[i] = (int32_t)(uint32_t)p; sr[i] = (int32_t)(uint32_t)(p >> 32); }
+    uint32_t longest[2] = { 0, 0 }, best[2] = { 0, 0 };
+    for(int s = 0; s < 2; ++s) {
+      uint32_t cnt = 0;
+      for(uint32_t i = 0; i < N; ++i) {
+        if((sr[i] < 0) != (s == 1)) continue;
+        int found = -1, prev = -1;
+        uint32_t min_len = 0xffffffffu;
+        for(uint32_t p = 0; p < cnt; ++p) {                 // list order, front first
+          const uint32_t j = L[p];
+          if(sr[i] > sr[j] && accept_mer(pb[i], sr[i], pb[j], sr[j], A.a, A.b, A.C)) { found = (int)p; break; }
+          if(len[j] < min_len) { min_len = len[j]; prev = (int)p; }
+        }
+        const uint32_t fj = found >= 0 ? L[found] : 0;
+        const uint32_t e_len = found >= 0 ? len[fj] + 1u : 1u;
+        const uint32_t cs = found >= 0 ? cstart[fj] : i;
+        len[i] = (uint8_t)e_len; cstart[i] = (uint8_t)cs; pprev[i] = found >= 0 ? (uint8_t)fj : (uint8_t)0xff;
+        for(int p = (int)cnt; p > prev + 1; --p) L[p] = L[p - 1];
+        L[prev + 1] = (uint8_t)i;
+        ++cnt;
+        if(longest[s] < e_len && accept_sequence(pb[i] - pb[cs], sr[i] - sr[cs], A.a)) { longest[s] = e_len; best[s] = i; }
+      }
+    }
+    const bool fwd_align = longest[0] >= longest[1];
+    const uint32_t nb = fwd_align ? longest[0] : longest[1];
+    uint32_t cur = fwd_align ? best[0] : best[1];
+    for(uint32_t t = 0; t < nb; ++t) {
+      A.chain_pay[gs + nb - 1 - t] = (uint64_t)(uint32_t)pb[cur] | ((uint64_t)(uint32_t)sr[cur] << 32);
+      cur = pprev[cur];
+    }
+    A.group_nb[g] = nb | (fwd_align ? 0x80000000u : 0u);
   }
 }
 
@@ -814,8 +863,9 @@ int launch_smem(mr_context* ctx, cudaStream_t st, const chain_args& A, int tier,
 
 } // namespace
 
-// scratch `lists`: (kClasses + 2) x ngroups uint32 (size classes, long-chain list, verdicts) + 32 uint32
-// counters (class counts 0..9, class cursors 16..25, long count 28, long cursor 29, max-match cursor 30)
+// scratch `lists`: (kClasses + 3) x ngroups uint32 (size classes, tiny groups, long-chain list, verdicts)
+// + 32 uint32 counters (class counts 0..9, tiny count 10, class cursors 16..25, long count 28, long
+// cursor 29, max-match cursor 30)
 // MR_TRACE=1: synchronise after every chain-phase kernel and name it on stderr
 static const bool g_chain_trace = getenv("MR_TRACE") != nullptr;
 static double trace_now() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
@@ -850,10 +900,10 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(A.ngroups == 0) return MR_OK;
   if(A.ngroups >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "more than 2^32 (read, super-read) groups in one batch");
   const uint64_t G = A.ngroups;
-  MR_TRY(lists.ensure(ctx, ((kClasses + 2) * G + 32) * sizeof(uint32_t)));
+  MR_TRY(lists.ensure(ctx, ((kClasses + 3) * G + 32) * sizeof(uint32_t)));
   uint32_t* cls = lists.as<uint32_t>();
-  uint32_t* ctr = cls + (kClasses + 2) * G;
-  A.long_list = cls + kClasses * G; A.group_nb = cls + (kClasses + 1) * G; A.long_count = ctr + 28; A.long_cursor = ctr + 29;
+  uint32_t* ctr = cls + (kClasses + 3) * G;
+  A.long_list = cls + (kClasses + 1) * G; A.group_nb = cls + (kClasses + 2) * G; A.long_count = ctr + 28; A.long_cursor = ctr + 29;
   MR_CUDA(ctx, cudaMemsetAsync(ctr, 0, 32 * sizeof(uint32_t), ctx->stream));
   if(!ctx->chain_tables) {
     std::vector<double> rcp(kRcpMax + 1, 0.0);
@@ -887,6 +937,13 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
     cudaStream_t st = c == 0 ? s0 : ctx->aux[c - 1];
     if(c != 0) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[0], 0));
     const uint32_t* list = cls + (uint64_t)c * G;
+    if(c == 0 && !taps) {
+      tl.open("tiny groups", st);
+      chain_tiny_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(A, cls + (uint64_t)kClasses * G, ctr + kClasses);
+      MR_LAUNCHED(ctx);
+      tl.close(st);
+      CHAIN_TRACE(st, "tiny groups");
+    }
     snprintf(label, sizeof label, "strands %d", c); tl.open(label, st);
     if(c == kSmemTiers) {
       chain_coords_global_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, ctr + 16 + c);
@@ -926,6 +983,14 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
     for(uint64_t i = 0; i < G; ++i) order[i] = (uint32_t)i;
     std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cyc[x] > cyc[y]; });
     double tot = 0; for(uint64_t i = 0; i < G; ++i) tot += cyc[i];
+    {
+      const uint32_t edges[] = { 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 128, 256, 512, 1024, 1536, 4096, 0xffffffffu };
+      uint64_t cntb[19] = { }, hitb[19] = { };
+      for(uint64_t i = 0; i < G; ++i) { const uint64_t n = gs[i + 1] - gs[i]; int b = 0; while(n > edges[b]) ++b; cntb[b]++; hitb[b] += n; }
+      fprintf(stderr, "[mr]   group sizes (<= edge: groups / hits):");
+      for(int b = 0; b < 19; ++b) if(cntb[b]) fprintf(stderr, " %u: %llu / %llu;", edges[b], (unsigned long long)cntb[b], (unsigned long long)hitb[b]);
+      fprintf(stderr, "\n");
+    }
     fprintf(stderr, "[mr]   chaining cycles: total %.3g; slowest groups (cycles, hits, chain):", tot);
     for(int i = 0; i < 12 && i < (int)G; ++i) { const uint32_t g = order[i]; fprintf(stderr, " (%u, %llu, %u)", cyc[g], (unsigned long long)(gs[g + 1] - gs[g]), nbv[g] & 0x7fffffffu); }
     fprintf(stderr, "\n");

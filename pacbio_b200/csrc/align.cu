@@ -281,44 +281,69 @@ __device__ __forceinline__ void emit_hit(const index_view& iv, uint32_t read, ui
   }
 }
 
-__global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, const uint64_t* __restrict__ read_start,
-                                                               const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
-                                                               const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
-                                                               const uint64_t* __restrict__ hit_off,
-                                                               uint64_t* __restrict__ keys, uint64_t* __restrict__ pays,
-                                                               unsigned long long* __restrict__ n_invalid) {
+// hits per tile (lists that survived the count threshold); their exclusive scan gives every tile its
+// slice of the hit arrays, and expand_kernel redoes the scan inside the tile: no per-position
+// offset array (8 B x read bases written and read back) is needed
+__global__ void __launch_bounds__(kSeedThreads) tile_hits_kernel(const uint64_t* __restrict__ read_start,
+                                                                  const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                                  const uint32_t* __restrict__ size, uint32_t* __restrict__ tile_hits) {
+  __shared__ uint64_t sw[8];
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
-  const unsigned lane = threadIdx.x & 31;
+  uint32_t s = 0;
+#pragma unroll
+  for(int it = 0; it < kTile / kSeedThreads; ++it) {
+    const uint32_t pos = tpos + it * kSeedThreads + threadIdx.x;
+    if(pos < rlen) s += __ldcs(size + rs + pos);
+  }
+  uint64_t total;
+  (void)prim::block_exclusive_scan_256(s, sw, total);
+  if(threadIdx.x == 0) tile_hits[blockIdx.x] = (uint32_t)total;
+}
+
+__global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, const uint64_t* __restrict__ read_start,
+                                                               const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                               const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
+                                                               const uint64_t* __restrict__ tile_off,
+                                                               uint64_t* __restrict__ keys, uint64_t* __restrict__ pays,
+                                                               unsigned long long* __restrict__ n_invalid) {
+  __shared__ uint64_t sw[8];
+  __shared__ uint32_t s_off[kSeedThreads];
+  __shared__ uint4    s_rec[kSeedThreads];
+  uint64_t run = tile_off[blockIdx.x];
+  if(tile_off[blockIdx.x + 1] == run) return;          // nothing in this tile
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  const uint32_t tpos = tile_pos[blockIdx.x];
   uint32_t n_bad = 0;
   for(int it = 0; it < kTile / kSeedThreads; ++it) {
     const uint32_t pos = tpos + it * kSeedThreads + threadIdx.x;
     uint32_t sz = 0;
     uint4 rc = make_uint4(0, 0, 0, 0);
-    uint64_t off = 0;
     if(pos < rlen) {
-      sz = size[rs + pos];
-      if(sz) { rc = rec[rs + pos]; off = hit_off[rs + pos]; }
+      sz = __ldcs(size + rs + pos);
+      if(sz) rc = __ldcs(rec + rs + pos);
     }
-    // short lists: the owning thread writes them
-    if(sz && sz <= 8) {
-      for(uint32_t j = 0; j < rc.y; ++j) emit_hit(iv, r, pos + 1, rc.x + j, false, off + j, keys, pays, n_bad);
-      for(uint32_t j = 0; j < rc.w; ++j) emit_hit(iv, r, pos + 1, rc.z + j, true, off + rc.y + j, keys, pays, n_bad);
+    uint64_t in_iter;
+    s_off[threadIdx.x] = (uint32_t)prim::block_exclusive_scan_256(sz, sw, in_iter);   // 256 lists below max-count: fits 32 bits
+    s_rec[threadIdx.x] = rc;
+    __syncthreads();
+    // one thread per HIT, not per list: thread h finds the position whose list holds hit h (the last
+    // position whose offset is <= h; empty lists share their offset with the next one), so the loads
+    // of different hits are independent and the stores of a warp are 32 consecutive slots
+    for(uint32_t h = threadIdx.x; h < (uint32_t)in_iter; h += kSeedThreads) {
+      uint32_t lo = 0, hi = kSeedThreads;
+      while(hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if(s_off[mid] <= h) lo = mid; else hi = mid; }
+      const uint4 c = s_rec[lo];
+      const uint32_t j = h - s_off[lo];
+      const bool minus = j >= c.y;
+      emit_hit(iv, r, tpos + it * kSeedThreads + lo + 1, minus ? c.z + (j - c.y) : c.x + j, minus, run + h, keys, pays, n_bad);
     }
-    // long lists: the whole warp strides over them, coalescing the SA reads and the writes
-    unsigned big = __ballot_sync(MR_FULL_MASK, sz > 8);
-    while(big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      const uint32_t bx = __shfl_sync(MR_FULL_MASK, rc.x, src), by = __shfl_sync(MR_FULL_MASK, rc.y, src);
-      const uint32_t bz = __shfl_sync(MR_FULL_MASK, rc.z, src), bw = __shfl_sync(MR_FULL_MASK, rc.w, src);
-      const uint64_t boff = __shfl_sync(MR_FULL_MASK, off, src);
-      const uint32_t bpos = __shfl_sync(MR_FULL_MASK, pos, src);
-      for(uint32_t j = lane; j < by; j += 32) emit_hit(iv, r, bpos + 1, bx + j, false, boff + j, keys, pays, n_bad);
-      for(uint32_t j = lane; j < bw; j += 32) emit_hit(iv, r, bpos + 1, bz + j, true, boff + by + j, keys, pays, n_bad);
-    }
+    run += in_iter;
+    __syncthreads();
   }
   if(n_bad) atomicAdd(n_invalid, (unsigned long long)n_bad);
 }
@@ -567,7 +592,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY(ws.counters.ensure(ctx, 16 * sizeof(uint64_t)));
   MR_TRY(ws.size.ensure(ctx, (T + 4) * 4));
   MR_TRY(ws.rec.ensure(ctx, (T + 4) * 16));
-  MR_TRY(ws.hit_off.ensure(ctx, (T + 4) * 8));
+  MR_TRY(ws.hit_off.ensure(ctx, ((size_t)ntiles + 4) * 8));
   MR_TRY(ws.thr.ensure(ctx, ((size_t)nreads + 1) * 4));
   MR_CUDA(ctx, cudaMemcpyAsync(ws.tile_first.p, tile_first.data(), ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, st));
   MR_CUDA(ctx, cudaMemcpyAsync(ws.read_len.p, read_len.data(), (size_t)nreads * 4, cudaMemcpyHostToDevice, st));
@@ -605,8 +630,15 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_LAUNCHED(ctx);
   }
   timer.next("hit expansion");
-  MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.size.as<uint32_t>() }, T, ws.hit_off.as<uint64_t>(),
+  if(ntiles) {
+    tile_hits_kernel<<<ntiles, kSeedThreads, 0, st>>>(d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                     ws.size.as<uint32_t>(), ws.tile_cand.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+  }
+  // tile_off[t] = first hit slot of tile t, tile_off[ntiles] = number of hits (also in counter 1)
+  MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
+  if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
   MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t H = h_ctr[1];

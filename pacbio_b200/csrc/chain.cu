@@ -56,13 +56,6 @@ constexpr uint32_t kRcpMax = 2048;
 __constant__ double kRcpTable[kRcpMax + 1];
 __device__ __forceinline__ double rcp_count(uint32_t n) { return n <= kRcpMax ? kRcpTable[n] : 1.0 / (double)n; }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
 // ---------------------------------------------------------------------------------------------
 // shared-memory strand: per warp arrays of CAP entries
 // ---------------------------------------------------------------------------------------------

@@ -151,3 +151,13 @@ __device__ __forceinline__ uint64_t reverse_pairs(uint64_t x) {
   x = __brevll(x);
   return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);
 }
+
+// ---- cp.async (LDGSTS): 8-byte copies global -> shared that do not pass through registers ----------
+#ifdef __CUDACC__
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif

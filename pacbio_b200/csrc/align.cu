@@ -895,7 +895,8 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
                           const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
   if(!ctx) return MR_EINVAL;
   if(!idx || !p || !out || !h_read_start || !d_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
-  if(idx->ctx != ctx) return ctx->fail(MR_EINVAL, "mr_align_batch: index belongs to another context");
+  // an index is read-only once built: any context of its device may align against it
+  if(idx->ctx->device != ctx->device) return ctx->fail(MR_EINVAL, "mr_align_batch: index lives on another device");
   if(p->window_size != 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size other than 1 is not implemented");
   if(p->max_match && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with --max-match");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))

@@ -130,6 +130,7 @@ int main(int argc, char* argv[]) {
     std::cerr << "compute_psa " << SR.nseq() << ' ' << SR.n << '\n';
     mrh::device_set DS;
     mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(22u, psa_min), mer);
+    mrh::add_streams(DS, mrh::streams_per_device());
     const auto t1 = std::chrono::steady_clock::now();
     if(show_timing) std::cerr << "Starting Super read parse ... " << std::chrono::duration<double>(t1 - t0).count() << '\n';
 

@@ -99,6 +99,7 @@ int main(int argc, char* argv[]) {
     std::cerr << "compute_psa " << SR.nseq() << ' ' << SR.n << '\n';
     mrh::device_set DS;
     mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(22u, psa_min), mer);
+    mrh::add_streams(DS, mrh::streams_per_device());
     P.matching_mers = mers_matching / 100.0;
     P.matching_bases = bases_matching / 100.0;
     P.unitigs_k = U.len.empty() ? 0 : k_mer;

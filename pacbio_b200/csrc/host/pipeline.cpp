@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 
 namespace mrh {
@@ -29,6 +30,7 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
                    uint32_t psa_min, uint32_t mer) {
   ds.ctx.assign(devices.size(), nullptr);
   ds.idx.assign(devices.size(), nullptr);
+  ds.owns_idx.assign(devices.size(), true);
   std::vector<std::string> errors(devices.size());
   std::vector<std::thread> th;
   for(size_t i = 0; i < devices.size(); ++i) {
@@ -45,10 +47,33 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
   for(const auto& e : errors) if(!e.empty()) throw std::runtime_error(e);
 }
 
+unsigned streams_per_device() {
+  if(const char* e = getenv("MR_STREAMS")) { const int v = atoi(e); return v < 1 ? 1u : (v > 8 ? 8u : (unsigned)v); }
+  return 1;
+}
+
+void add_streams(device_set& ds, unsigned per_device) {
+  const size_t ndev = ds.ctx.size();
+  for(unsigned s = 1; s < per_device; ++s) {
+    for(size_t d = 0; d < ndev; ++d) {
+      mr_context* c = nullptr;
+      if(mr_context_create(mr_context_device(ds.ctx[d]), &c) != MR_OK) throw std::runtime_error(std::string("mr_context_create: ") + mr_last_error(nullptr));
+      ds.ctx.push_back(c);
+      ds.idx.push_back(ds.idx[d]);
+      ds.owns_idx.push_back(false);
+    }
+  }
+}
+
 namespace {
-struct job {
+struct part {
   std::unique_ptr<read_batch> batch;
   mr_result* result = nullptr;
+};
+struct job {
+  uint64_t seq = 0;                  // position in the input stream
+  std::unique_ptr<read_batch> batch;
+  std::vector<part> parts;           // aligned: one part, or several when the batch had to be split
 };
 }
 
@@ -66,8 +91,9 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   std::thread reader([&]() {
     try {
       read_stream rs(read_paths);
-      while(true) {
+      for(uint64_t seq = 0; ; ++seq) {
         job j;
+        j.seq = seq;
         j.batch.reset(new read_batch);
         j.batch->clear();
         if(!rs.next_batch(*j.batch, batch_bases, batch_reads)) break;
@@ -92,9 +118,9 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
         while(!work.empty() && error.empty()) {
           std::unique_ptr<read_batch> b = std::move(work.front());
           work.pop_front();
-          job part;
-          const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &part.result);
-          if(rc == MR_OK) { part.batch = std::move(b); to_format.push(std::move(part)); continue; }
+          part pt;
+          const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &pt.result);
+          if(rc == MR_OK) { pt.batch = std::move(b); j.parts.push_back(std::move(pt)); continue; }
           if((rc == MR_ELIMIT || rc == MR_ENOMEM) && b->nreads() > 1) {
             const uint32_t half = b->nreads() / 2;
             std::unique_ptr<read_batch> lo(new read_batch), hi(new read_batch);
@@ -110,6 +136,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           }
           fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g]));
         }
+        to_format.push(std::move(j));
       }
       if(--live == 0) to_format.close();
     });
@@ -118,15 +145,24 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   std::thread formatter([&]() {
     job j;
     std::vector<std::string> parts;
+    std::map<uint64_t, job> waiting;           // aligned out of turn (several aligner threads)
+    uint64_t next_seq = 0;
     while(to_format.pop(j)) {
-      mr_result_view v;
-      mr_result_get(j.result, &v);
-      for(auto& p : parts) p.clear();
-      try { format(j.result, v, *j.batch, parts); } catch(std::exception& e) { fail(e.what()); }
-      for(const auto& text : parts)
-        if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
-      mr_result_free(j.result);
+      waiting.emplace(j.seq, std::move(j));
+      for(auto it = waiting.find(next_seq); it != waiting.end(); it = waiting.find(++next_seq)) {
+        for(auto& pt : it->second.parts) {
+          mr_result_view v;
+          mr_result_get(pt.result, &v);
+          for(auto& p : parts) p.clear();
+          try { format(pt.result, v, *pt.batch, parts); } catch(std::exception& e) { fail(e.what()); }
+          for(const auto& text : parts)
+            if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
+          mr_result_free(pt.result);
+        }
+        waiting.erase(it);
+      }
     }
+    for(auto& w : waiting) for(auto& pt : w.second.parts) mr_result_free(pt.result);   // only after an error
   });
 
   reader.join();

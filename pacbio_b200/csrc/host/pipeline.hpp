@@ -1,6 +1,6 @@
 // Batch pipeline shared by the two tools: a reader thread cuts the long-read stream into batches,
 // one aligner thread per GPU context pushes them through the C ABI, a formatter stage turns each
-// result into text (fanned out over -t host threads) and writes it under a lock.  Reads are
+// result into text (fanned out over -t host threads) and writes the records in input order.  Reads are
 // partitioned across GPUs batch by batch with the index replicated per GPU; there is no
 // collective on the path, only this host-side gather.
 #pragma once
@@ -41,11 +41,14 @@ public:
   void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_pop_.notify_all(); }
 };
 
+// one entry per aligner thread: a context (stream + scratch) and the index it reads.  Several
+// contexts of one device share that device's index (owns_idx false for all but the first).
 struct device_set {
   std::vector<mr_context*> ctx;
   std::vector<mr_index*>   idx;
+  std::vector<bool>        owns_idx;
   ~device_set() {
-    for(auto i : idx) mr_index_destroy(i);
+    for(size_t i = 0; i < idx.size(); ++i) if(i >= owns_idx.size() || owns_idx[i]) mr_index_destroy(idx[i]);
     for(auto c : ctx) mr_context_destroy(c);
   }
 };
@@ -56,6 +59,15 @@ std::vector<int> choose_devices();
 // creates one context + index per device (index build runs concurrently on all of them)
 void build_indexes(device_set& ds, const std::vector<int>& devices, const super_reads& sr, const unitigs& u,
                    uint32_t psa_min, uint32_t mer);
+
+// batches in flight per device: MR_STREAMS (default 1).  The kernels of one batch are a mix of
+// bandwidth-bound (seed lookups, sort) and latency-bound (chaining, coords) work with host round
+// trips in between; a second batch on its own stream fills some of those gaps (measured on B200,
+// configs[1]: +4 % device throughput with 2, +11 % with 3, but the aligner threads then compete
+// with the formatter threads for host cores and the end-to-end rate drops, hence the default).
+unsigned streams_per_device();
+// adds per_device - 1 more contexts for every device of ds, sharing the device's index
+void add_streams(device_set& ds, unsigned per_device);
 
 typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<std::string>&)> format_fn;
 

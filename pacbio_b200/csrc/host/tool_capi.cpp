@@ -1,5 +1,6 @@
 // C ABI over the host pipeline, for bench.py and tests: load inputs once, then run whole read sets
 // through mr_align_batch (host buffers in, text out) exactly as the create_mega_reads tool does.
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -33,6 +34,7 @@ void* mrh_tool_create(const char* sr_fasta, const char* unitigs_path, int unitig
     if(unitigs_is_fasta) t->U.load_sequences(unitigs_path); else t->U.load_lengths(unitigs_path);
     t->SR.append_fasta(sr_fasta);
     mrh::build_indexes(t->DS, std::vector<int>(1, device), t->SR, t->U, psa_min, mer);
+    mrh::add_streams(t->DS, mrh::streams_per_device());
     mr_params_default(&t->P);
     t->P.unitigs_k = unitig_k;
     t->P.run_graph = 1;
@@ -53,6 +55,9 @@ void mrh_tool_destroy(void* p) {
 
 const char* mrh_tool_error(void* p) { return ((tool*)p)->error.c_str(); }
 mr_context* mrh_tool_context(void* p) { return ((tool*)p)->DS.ctx[0]; }
+// the tool keeps MR_STREAMS contexts on its device (batches in flight); all of them read the one index
+unsigned mrh_tool_nstreams(void* p) { return (unsigned)((tool*)p)->DS.ctx.size(); }
+mr_context* mrh_tool_stream_context(void* p, unsigned s) { return ((tool*)p)->DS.ctx[s]; }
 mr_index* mrh_tool_index(void* p) { return ((tool*)p)->DS.idx[0]; }
 mr_params* mrh_tool_params(void* p) { return &((tool*)p)->P; }
 uint64_t mrh_tool_sr_bases(void* p) { return ((tool*)p)->SR.n; }
@@ -97,44 +102,77 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   t->last_text_bytes = t->last_d2h_bytes = t->last_h2d_bytes = t->last_coords = 0;
   t->last_lookups = t->last_hits = t->last_groups = 0;
   t->last_align_s = t->last_format_s = 0;
-  struct item { mrh::read_batch* b; mr_result* r; };
-  mrh::bounded_queue<item> q(2);
-  std::string error;
+  // one aligner thread per context takes the next batch; results are formatted in batch order
+  const size_t nb = t->batches.size();
+  std::vector<mr_result*> done(nb, nullptr);
+  std::vector<char> ready(nb, 0);
+  std::mutex m;
+  std::condition_variable cv;
+  size_t formatted = 0;                       // batches the formatter is done with (guarded by m)
+  bool   stop = false;
+  std::string error, align_error;
   std::thread formatter([&]() {
-    item it;
     std::vector<std::string>& parts = t->parts;
-    while(q.pop(it)) {
+    for(size_t i = 0; i < nb; ++i) {
+      mr_result* r = nullptr;
+      {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return ready[i] || stop; });
+        if(!ready[i]) return;
+        r = done[i];
+      }
       const auto f0 = std::chrono::steady_clock::now();
+      mrh::read_batch* b = t->batches[i].get();
       mr_result_view v;
-      mr_result_get(it.r, &v);
+      mr_result_get(r, &v);
       try {
-        mrh::format_mega_reads_mt(v, *it.b, t->SR, t->U, t->G, threads, parts);
+        mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, parts);
         for(const auto& text : parts) {
           if(out) fwrite(text.data(), 1, text.size(), out);
           t->last_text_bytes += text.size();
         }
       } catch(std::exception& e) { error = e.what(); }
-      t->last_h2d_bytes += it.b->bases.size() + (it.b->nreads() + 1) * 8ULL;
+      t->last_h2d_bytes += b->bases.size() + (b->nreads() + 1) * 8ULL;
       uint64_t info = 0;
-      for(uint64_t i = 0; i < v.ncoords; ++i) info += v.info_len[i];
+      for(uint64_t c = 0; c < v.ncoords; ++c) info += v.info_len[c];
       t->last_d2h_bytes += (v.nreads + 1) * 8ULL + v.ncoords * (5 * 4 + 6 * 4 + 2 + 3 * 8 + 8 + 4 + 2 + 5 * 4) + info * 8;
       t->last_coords += v.ncoords;
       t->last_lookups += v.n_kmers_looked_up; t->last_hits += v.n_hits; t->last_groups += v.n_groups;
-      mr_result_free(it.r);
+      mr_result_free(r);
       t->last_format_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - f0).count();
+      { std::lock_guard<std::mutex> l(m); formatted = i + 1; }
+      cv.notify_all();
     }
   });
-  std::string align_error;
-  for(auto& b : t->batches) {
-    mr_result* r = nullptr;
-    const auto a0 = std::chrono::steady_clock::now();
-    const int rc = mr_align_batch(t->DS.ctx[0], t->DS.idx[0], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
-    t->last_align_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
-    if(rc != MR_OK) { align_error = mr_last_error(t->DS.ctx[0]); break; }
-    q.push(item{ b.get(), r });
+  std::atomic<size_t> next(0);
+  std::vector<double> busy(t->DS.ctx.size(), 0.0);
+  std::vector<std::thread> aligners;
+  for(size_t s = 0; s < t->DS.ctx.size(); ++s) {
+    aligners.emplace_back([&, s]() {
+      while(true) {
+        const size_t i = next++;
+        if(i >= nb) break;
+        {   // stay at most a few batches ahead of the formatter (bounds the pinned result memory)
+          std::unique_lock<std::mutex> l(m);
+          cv.wait(l, [&] { return i < formatted + 2 + t->DS.ctx.size() || stop; });
+          if(stop) break;
+        }
+        mrh::read_batch* b = t->batches[i].get();
+        mr_result* r = nullptr;
+        const auto a0 = std::chrono::steady_clock::now();
+        const int rc = mr_align_batch(t->DS.ctx[s], t->DS.idx[s], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+        busy[s] += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
+        std::lock_guard<std::mutex> l(m);
+        if(rc != MR_OK) { if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]); stop = true; cv.notify_all(); break; }
+        done[i] = r; ready[i] = 1;
+        cv.notify_all();
+      }
+    });
   }
-  q.close();
+  for(auto& th : aligners) th.join();
   formatter.join();
+  for(double b : busy) t->last_align_s = std::max(t->last_align_s, b);
+  for(size_t i = 0; i < nb; ++i) if(ready[i] && i >= formatted) mr_result_free(done[i]);   // only after an error
   if(out) fclose(out);
   if(!align_error.empty() || !error.empty()) { t->error = align_error.empty() ? error : align_error; return -1; }
   return (int64_t)t->total_bases;

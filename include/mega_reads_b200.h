@@ -74,6 +74,20 @@ uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min +
 int  mr_index_export_sa(mr_index* idx, uint64_t* sa_out);
 int  mr_index_export_counts(mr_index* idx, uint64_t* counts_out);
 
+/* ---- index files.  The reference rebuilds the suffix array in every process
+ *  (superread_parser.hpp:212-224 is called from main, create_mega_reads.cc:131), while the pipeline
+ *  runs the tool many times over the same super-reads (array jobs,
+ *  mega_reads_assemble_cluster2.sh:358-448).  mr_index_save writes a built index to one file,
+ *  mr_index_load brings it back on any device without sorting.  mr_inputs_checksum hashes the
+ *  arguments of mr_index_create on the host; mr_index_checksum returns the hash an index was built
+ *  from (also after a load), so a caller can tell whether a file matches the inputs it parsed.    */
+int      mr_index_save(mr_index* idx, const char* path);
+int      mr_index_load(mr_context* ctx, const char* path, mr_index** out);
+uint64_t mr_index_checksum(const mr_index* idx);
+uint64_t mr_inputs_checksum(const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
+                            const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
+                            uint32_t n_unitigs, uint32_t psa_min, uint32_t k);
+
 /* ---- k-mer lookup: replaces PSA::search (psa.hpp:150-153 -> mer_sa_imp.hpp:369-479).
  *  mers[i] holds a k-mer as an integer, first base most significant.  index_out/nb_out get the
  *  rank of the first matching SA entry and the number of matches (index 0 when nb is 0).

@@ -75,6 +75,12 @@ def lib():
     L.mr_index_create.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, C.c_uint32, u32p, u64p, i32p, C.c_uint32,
                                   C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.mr_index_destroy.argtypes = [C.c_void_p]
+    L.mr_index_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.mr_index_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.mr_index_checksum.restype = C.c_uint64
+    L.mr_index_checksum.argtypes = [C.c_void_p]
+    L.mr_inputs_checksum.restype = C.c_uint64
+    L.mr_inputs_checksum.argtypes = [u64p, C.c_uint64, u64p, C.c_uint32, u32p, u64p, i32p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.mr_index_sa_size.restype = C.c_uint64
     L.mr_index_sa_size.argtypes = [C.c_void_p]
     L.mr_index_export_sa.argtypes = [C.c_void_p, u64p]
@@ -261,9 +267,14 @@ def default_params(**kw):
 
 
 class Index:
-    def __init__(self, ctx, sr, psa_min, k, unitig_len=None):
+    def __init__(self, ctx, sr, psa_min, k, unitig_len=None, load_from=None):
+        """Builds the index of `sr` (a SuperReads) or, with load_from, reads a file written by save()."""
         self.ctx, self.sr, self.m, self.k = ctx, sr, psa_min, k
         h = C.c_void_p()
+        if load_from is not None:
+            ctx.check(ctx.L.mr_index_load(ctx.h, os.fsencode(load_from), C.byref(h)))
+            self.h = h
+            return
         if unitig_len is not None:
             ul = np.ascontiguousarray(unitig_len, dtype=np.int32)
             ids = np.ascontiguousarray(sr.unitig_ids, dtype=np.uint32)
@@ -280,6 +291,12 @@ class Index:
         if self.h:
             self.ctx.L.mr_index_destroy(self.h)
             self.h = None
+
+    def save(self, path):
+        self.ctx.check(self.ctx.L.mr_index_save(self.h, os.fsencode(path)))
+
+    def checksum(self):
+        return int(self.ctx.L.mr_index_checksum(self.h))
 
     def sa(self):
         out = np.empty(self.ctx.L.mr_index_sa_size(self.h), dtype=np.uint64)

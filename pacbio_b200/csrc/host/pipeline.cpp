@@ -1,6 +1,7 @@
 #include "pipeline.hpp"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -32,19 +33,43 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
   ds.idx.assign(devices.size(), nullptr);
   ds.owns_idx.assign(devices.size(), true);
   std::vector<std::string> errors(devices.size());
+  std::vector<char> loaded(devices.size(), 0);
+  // MR_INDEX_CACHE=<file>: reuse a saved index when it was built from these very inputs, else build
+  // and save (the reference builds its suffix array again in every process)
+  const char* cache = getenv("MR_INDEX_CACHE");
+  const bool with_unitigs = !u.len.empty();
+  const uint32_t* uid = with_unitigs ? sr.unitig_ids.data() : nullptr;
+  const uint64_t* uoff = with_unitigs ? sr.unitig_off.data() : nullptr;
+  const int32_t*  ulen = with_unitigs ? u.len.data() : nullptr;
+  const uint64_t want = cache && *cache ? mr_inputs_checksum(sr.text2bit.data(), sr.n, sr.start.data(), sr.nseq(), uid, uoff, ulen,
+                                                             (uint32_t)u.len.size(), psa_min, mer) : 0;
   std::vector<std::thread> th;
   for(size_t i = 0; i < devices.size(); ++i) {
     th.emplace_back([&, i]() {
       int rc = mr_context_create(devices[i], &ds.ctx[i]);
       if(rc != MR_OK) { errors[i] = std::string("mr_context_create: ") + mr_last_error(nullptr); return; }
-      rc = mr_index_create(ds.ctx[i], sr.text2bit.data(), sr.n, sr.start.data(), sr.nseq(),
-                           u.len.empty() ? nullptr : sr.unitig_ids.data(), u.len.empty() ? nullptr : sr.unitig_off.data(),
-                           u.len.empty() ? nullptr : u.len.data(), (uint32_t)u.len.size(), psa_min, mer, &ds.idx[i]);
+      if(cache && *cache) {
+        mr_index* got = nullptr;
+        if(mr_index_load(ds.ctx[i], cache, &got) == MR_OK) {
+          if(mr_index_checksum(got) == want) { ds.idx[i] = got; loaded[i] = 1; return; }
+          mr_index_destroy(got);               // a file for other super-reads / options: ignore it
+        }
+      }
+      rc = mr_index_create(ds.ctx[i], sr.text2bit.data(), sr.n, sr.start.data(), sr.nseq(), uid, uoff, ulen,
+                           (uint32_t)u.len.size(), psa_min, mer, &ds.idx[i]);
       if(rc != MR_OK) errors[i] = std::string("mr_index_create: ") + mr_last_error(ds.ctx[i]);
     });
   }
   for(auto& t : th) t.join();
   for(const auto& e : errors) if(!e.empty()) throw std::runtime_error(e);
+  if(cache && *cache) {
+    if(loaded[0]) fprintf(stderr, "index: loaded from %s\n", cache);
+    else {
+      const std::string tmp = std::string(cache) + ".tmp";
+      if(mr_index_save(ds.idx[0], tmp.c_str()) == MR_OK && rename(tmp.c_str(), cache) == 0) fprintf(stderr, "index: built and saved to %s\n", cache);
+      else { remove(tmp.c_str()); fprintf(stderr, "index: built; could not save to %s\n", cache); }
+    }
+  }
 }
 
 unsigned streams_per_device() {

@@ -207,6 +207,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     idx->has_unitigs = true;
     idx->n_unitigs = n_unitigs;
     const uint64_t total = unitig_off[nseq];
+    idx->unitig_total = total;
     MR_TRY(idx->unitig_ids.ensure(ctx, (total + 1) * sizeof(uint32_t)));
     MR_TRY(idx->unitig_off.ensure(ctx, ((size_t)nseq + 1) * sizeof(uint64_t)));
     MR_TRY(idx->unitig_len.ensure(ctx, (size_t)n_unitigs * sizeof(int32_t)));
@@ -260,6 +261,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     }
     v.short_key[v.nshort++] = key;
   }
+  idx->inputs_checksum = mr_inputs_checksum(text2bit, n, sr_start, nseq, unitig_ids, unitig_off, unitig_len, n_unitigs, psa_min, k);
   *out = idx.release();
   return MR_OK;
 }

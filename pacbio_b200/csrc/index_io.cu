@@ -1,0 +1,173 @@
+// Index serialisation: the reference rebuilds its suffix array in every process, and the
+// pipeline runs create_mega_reads several times over the same super-reads
+// (mega_reads_assemble_cluster2.sh:358-448 array jobs; passes over the same -r in
+// mega_reads_assemble_nomatch.sh:217-261).  A built index is a handful of flat device arrays, so it
+// is written to / read from one file: a fixed header, then the arrays back to back.  The header
+// carries a checksum of the INPUTS (text, super-read starts, unitig tables, psa-min, mer) so that a
+// caller can tell whether a file on disk belongs to the inputs it has just parsed.
+#include "index.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+constexpr char     kMagic[8] = { 'M', 'R', 'B', '2', 'I', 'D', 'X', '1' };
+constexpr uint32_t kSections = 9;     // text sa tails counts sr_start blk unitig_ids unitig_off unitig_len
+
+struct file_header {
+  char     magic[8];
+  uint64_t n;
+  uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort, n_unitigs, has_unitigs;
+  uint64_t short_key[kMaxShort];
+  uint64_t bytes[kSections];
+  uint64_t inputs_checksum;
+  uint64_t reserved[4];
+};
+
+inline uint64_t mix(uint64_t h, uint64_t v) {      // splitmix64 finaliser over a running value
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ULL;
+  h ^= h >> 27; h *= 0x94d049bb133111ebULL;
+  h ^= h >> 31;
+  return h;
+}
+
+struct section { dev_buf* buf; uint64_t bytes; };
+
+void sections_of(mr_index* idx, section* s) {
+  const uint64_t nwords = (idx->n + 31) / 32;
+  const uint32_t nprefix = 1u << (2 * idx->mi);
+  const uint32_t nblk = (uint32_t)(idx->n >> kBlkShift) + 1;
+  s[0] = { &idx->text,     (nwords + 2) * sizeof(uint64_t) };
+  s[1] = { &idx->sa,       (uint64_t)idx->nsa * sizeof(uint32_t) };
+  s[2] = { &idx->tails,    ((uint64_t)idx->nsa + 64) * idx->view.tail_bytes };
+  s[3] = { &idx->counts,   ((uint64_t)nprefix + 8) * sizeof(uint32_t) };
+  s[4] = { &idx->sr_start, ((uint64_t)idx->nseq + 2) * sizeof(uint32_t) };
+  s[5] = { &idx->blk,      ((uint64_t)nblk + 1) * sizeof(uint32_t) };
+  s[6] = { &idx->unitig_ids, 0 }; s[7] = { &idx->unitig_off, 0 }; s[8] = { &idx->unitig_len, 0 };
+  if(idx->has_unitigs) {
+    s[6].bytes = idx->unitig_total * sizeof(uint32_t);
+    s[7].bytes = ((uint64_t)idx->nseq + 1) * sizeof(uint64_t);
+    s[8].bytes = (uint64_t)idx->n_unitigs * sizeof(int32_t);
+  }
+}
+
+struct file_closer { void operator()(FILE* f) const { if(f) fclose(f); } };
+constexpr size_t kChunk = 64u << 20;
+
+} // namespace
+
+extern "C" {
+
+uint64_t mr_inputs_checksum(const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
+                            const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
+                            uint32_t n_unitigs, uint32_t psa_min, uint32_t k) {
+  uint64_t h = mix(mix(mix(mix(0x6d72623230306964ULL, n), nseq), psa_min), k);
+  if(text2bit) {
+    const uint64_t nwords = n / 32;
+    for(uint64_t i = 0; i < nwords; ++i) h = mix(h, text2bit[i]);
+    if(n & 31) h = mix(h, text2bit[nwords] & ((1ULL << (2 * (n & 31))) - 1));   // bits past the last base are not part of the input
+  }
+  if(sr_start) for(uint32_t i = 0; i <= nseq; ++i) h = mix(h, sr_start[i]);
+  if(unitig_ids && unitig_off && unitig_len && n_unitigs) {
+    h = mix(h, n_unitigs);
+    for(uint32_t i = 0; i <= nseq; ++i) h = mix(h, unitig_off[i]);
+    for(uint64_t i = 0; i < unitig_off[nseq]; ++i) h = mix(h, unitig_ids[i]);
+    for(uint32_t i = 0; i < n_unitigs; ++i) h = mix(h, (uint64_t)(uint32_t)unitig_len[i]);
+  }
+  return h;
+}
+
+uint64_t mr_index_checksum(const mr_index* idx) { return idx ? idx->inputs_checksum : 0; }
+
+int mr_index_save(mr_index* idx, const char* path) {
+  if(!idx || !path) return MR_EINVAL;
+  mr_context* ctx = idx->ctx;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<FILE, file_closer> f(fopen(path, "wb"));
+  if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_save: cannot open ") + path);
+  file_header h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kMagic, 8);
+  h.n = idx->n; h.nsa = idx->nsa; h.nseq = idx->nseq; h.k = idx->k; h.m = idx->m; h.mi = idx->mi;
+  h.tail_bits = idx->view.tail_bits; h.tail_bytes = idx->view.tail_bytes; h.nshort = idx->view.nshort;
+  h.n_unitigs = idx->n_unitigs; h.has_unitigs = idx->has_unitigs;
+  memcpy(h.short_key, idx->view.short_key, sizeof h.short_key);
+  h.inputs_checksum = idx->inputs_checksum;
+  section s[kSections];
+  sections_of(idx, s);
+  for(uint32_t i = 0; i < kSections; ++i) h.bytes[i] = s[i].bytes;
+  if(fwrite(&h, sizeof h, 1, f.get()) != 1) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+  pinned_buf stage;
+  MR_TRY(stage.ensure(ctx, kChunk));
+  for(uint32_t i = 0; i < kSections; ++i) {
+    for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
+      const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
+      MR_CUDA(ctx, cudaMemcpyAsync(stage.p, (const char*)s[i].buf->p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+      MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if(fwrite(stage.p, 1, len, f.get()) != len) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+    }
+  }
+  if(fflush(f.get()) != 0) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+  return MR_OK;
+}
+
+int mr_index_load(mr_context* ctx, const char* path, mr_index** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!path || !out) return ctx->fail(MR_EINVAL, "mr_index_load: null argument");
+  *out = nullptr;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<FILE, file_closer> f(fopen(path, "rb"));
+  if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_load: cannot open ") + path);
+  file_header h;
+  if(fread(&h, sizeof h, 1, f.get()) != 1 || memcmp(h.magic, kMagic, 8) != 0)
+    return ctx->fail(MR_EINVAL, "mr_index_load: not an index file of this library version");
+  if(!(h.m >= 1 && h.m < h.k && h.k <= 31 && h.mi >= 1 && h.mi <= h.m && h.n >= h.k && h.n < 0xfffffff0ULL && h.nseq >= 1 &&
+       h.nsa == (uint32_t)(h.n - h.m + 1) && h.tail_bits == 2 * (h.k - h.mi) && h.nshort <= (uint32_t)kMaxShort &&
+       (h.tail_bytes == 1 || h.tail_bytes == 2 || h.tail_bytes == 4)))
+    return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
+  ctx->timers.clear();
+  phase_timer timer(ctx);
+  timer.begin("index load");
+  std::unique_ptr<mr_index> idx(new mr_index);
+  idx->ctx = ctx; idx->n = h.n; idx->nsa = h.nsa; idx->nseq = h.nseq; idx->k = h.k; idx->m = h.m; idx->mi = h.mi;
+  idx->n_unitigs = h.n_unitigs; idx->has_unitigs = h.has_unitigs != 0;
+  idx->inputs_checksum = h.inputs_checksum;
+  idx->view.tail_bytes = h.tail_bytes;
+  if(idx->has_unitigs) idx->unitig_total = h.bytes[6] / sizeof(uint32_t);
+  section s[kSections];
+  sections_of(idx.get(), s);
+  for(uint32_t i = 0; i < kSections; ++i)
+    if(s[i].bytes != h.bytes[i]) return ctx->fail(MR_EINVAL, "mr_index_load: section sizes do not match the header");
+  pinned_buf stage[2];
+  MR_TRY(stage[0].ensure(ctx, kChunk)); MR_TRY(stage[1].ensure(ctx, kChunk));
+  int which = 0;
+  for(uint32_t i = 0; i < kSections; ++i) {
+    if(s[i].bytes == 0) continue;
+    MR_TRY(s[i].buf->ensure(ctx, s[i].bytes));
+    for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
+      const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
+      // two staging buffers: the file read of one chunk overlaps the upload of the previous one
+      MR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which]));
+      if(fread(stage[which].p, 1, len, f.get()) != len) return ctx->fail(MR_EINVAL, "mr_index_load: file is truncated");
+      MR_CUDA(ctx, cudaMemcpyAsync((char*)s[i].buf->p + off, stage[which].p, len, cudaMemcpyHostToDevice, ctx->stream));
+      MR_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->stream));
+      which ^= 1;
+    }
+  }
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  timer.end();
+  timer.collect();
+  index_view& v = idx->view;
+  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
+  v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
+  v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
+  v.nshort = h.nshort;
+  memcpy(v.short_key, h.short_key, sizeof h.short_key);
+  *out = idx.release();
+  return MR_OK;
+}
+
+} // extern "C"

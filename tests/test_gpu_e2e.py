@@ -148,6 +148,36 @@ def test_oversized_batches_are_split(tmpdir_session, tmp_path):
     assert open(a).read() == open(b).read() and len(open(a).read()) > 1000
 
 
+def test_several_batches_in_flight_keep_the_record_order(tmpdir_session, tmp_path):
+    """MR_STREAMS contexts per GPU share one index; the formatter puts the batches back in input order."""
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_streams"), 200000, coverage=6, read_len=4000, seed=23)
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"]]
+    a, b = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+    run(cmd + ["-o", a], env=dict(os.environ, MR_STREAMS="1"))
+    run(cmd + ["-o", b], env=dict(os.environ, MR_STREAMS="3", MR_BATCH_BASES="60000"))
+    assert open(a).read() == open(b).read() and len(open(a).read()) > 1000
+
+
+def test_index_cache_is_used_and_checked(tmpdir_session, tmp_path):
+    """MR_INDEX_CACHE: the first run builds and saves, the second loads; a cache made from other super-reads is rebuilt."""
+    a = gen_synth(os.path.join(tmpdir_session, "e2e_cache_a"), 150000, coverage=3, read_len=3000, seed=41)
+    b = gen_synth(os.path.join(tmpdir_session, "e2e_cache_b"), 150000, coverage=3, read_len=3000, seed=42)
+    cache = str(tmp_path / "index.cache")
+    env = dict(os.environ, MR_INDEX_CACHE=cache)
+
+    def go(info, out, env_):
+        cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-r", info["sr"], "-p", info["reads"], "-o", out]
+        return subprocess.run(cmd, env=env_, stderr=subprocess.PIPE, check=True).stderr.decode()
+
+    plain, first, second, other = (str(tmp_path / n) for n in ("plain.txt", "first.txt", "second.txt", "other.txt"))
+    go(a, plain, os.environ)
+    assert "built and saved" in go(a, first, env) and os.path.getsize(cache) > 100000
+    assert "loaded from" in go(a, second, env)
+    assert open(plain).read() == open(first).read() == open(second).read() and len(open(plain).read()) > 1000
+    assert "built and saved" in go(b, other, env)            # checksum mismatch: not used, replaced
+    assert "loaded from" in go(b, other, env)
+
+
 def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
     info = gen_synth(os.path.join(tmpdir_session, "e2e_fq"), 100000, coverage=3, read_len=3000, seed=5)
     from oracle_lib import read_fasta

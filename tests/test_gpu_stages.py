@@ -62,6 +62,53 @@ def test_index_matches_oracle(case, port):
     assert np.array_equal(idx.counts(), port.counts(hp, c["m"]))
 
 
+def test_saved_index_loads_identically(case, ctx, port, tmp_path):
+    """mr_index_save / mr_index_load: the loaded index is the built one (SA, counts, lookups, checksum)."""
+    import pacbio_b200 as pb
+    idx, c, sr = case["idx"], case["cfg"], case["sr"]
+    path = str(tmp_path / "index.bin")
+    idx.save(path)
+    ctx2 = pb.Context(0)
+    try:
+        back = pb.Index(ctx2, sr, c["m"], c["k"], load_from=path)
+        assert back.checksum() == idx.checksum() != 0
+        assert np.array_equal(back.sa(), idx.sa())
+        assert np.array_equal(back.counts(), idx.counts())
+        rng = np.random.default_rng(5)
+        q = rng.integers(0, 4 ** c["k"], size=5000, dtype=np.uint64)
+        q[:2500] = [int(x) for x in _text_kmers(case, 2500, c["k"])]
+        a, b = idx.lookup(q), back.lookup(q)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and int(a[1].sum()) >= 2500
+        back.close()
+        # a truncated file and a file that is not an index are refused
+        raw = open(path, "rb").read()
+        open(path, "wb").write(raw[:len(raw) // 2])
+        with pytest.raises(pb.MrError):
+            pb.Index(ctx2, sr, c["m"], c["k"], load_from=path)
+        open(path, "wb").write(b"not an index" * 100)
+        with pytest.raises(pb.MrError):
+            pb.Index(ctx2, sr, c["m"], c["k"], load_from=path)
+    finally:
+        ctx2.close()
+
+
+def _text_kmers(case, n, k):
+    _, seqs = read_fasta(case["info"]["sr"])
+    b = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    codes = (((b >> 1) ^ (b >> 2)) & 3).astype(np.uint64)
+    rng = np.random.default_rng(9)
+    w = (4 ** np.arange(k - 1, -1, -1)).astype(np.uint64)
+    starts = np.cumsum([0] + [len(s) for s in seqs])
+    out = []
+    while len(out) < n:
+        s = int(rng.integers(0, len(seqs)))
+        if len(seqs[s]) < k:
+            continue
+        p = int(starts[s] + rng.integers(0, len(seqs[s]) - k + 1))
+        out.append(int((codes[p:p + k] * w).sum()))
+    return out
+
+
 def test_lookup_matches_oracle(case, port):
     idx, hp, c, sr = case["idx"], case["hp"], case["cfg"], case["sr"]
     _, seqs = read_fasta(case["info"]["sr"])

@@ -30,6 +30,39 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_inputs_checksum_tracks_every_input():
+    """mr_inputs_checksum (host code, no device): what decides whether a saved index may be reused."""
+    import numpy as np
+    import pacbio_b200.api as api
+    L = api.lib()
+    rng = np.random.default_rng(3)
+    n, nseq = 1000, 4
+    text = rng.integers(0, 2 ** 63, size=(n + 31) // 32, dtype=np.uint64)
+    starts = np.array([0, 200, 500, 800, n], dtype=np.uint64)
+    ids = np.arange(9, dtype=np.uint32)
+    off = np.array([0, 2, 4, 7, 9], dtype=np.uint64)
+    ulen = np.array([60, 70, 80, 90, 100, 110, 120, 130, 140], dtype=np.int32)
+
+    def h(text=text, n=n, starts=starts, ids=ids, off=off, ulen=ulen, m=13, k=15, with_unitigs=True):
+        p = lambda a, t: a.ctypes.data_as(t)
+        if with_unitigs:
+            return L.mr_inputs_checksum(p(text, api.u64p), n, p(starts, api.u64p), nseq, p(ids, api.u32p), p(off, api.u64p),
+                                        p(ulen, api.i32p), len(ulen), m, k)
+        return L.mr_inputs_checksum(p(text, api.u64p), n, p(starts, api.u64p), nseq, None, None, None, 0, m, k)
+
+    base = h()
+    assert base == h() and base != 0
+    t2 = text.copy(); t2[5] ^= 1 << 20
+    s2 = starts.copy(); s2[2] += 1
+    i2 = ids.copy(); i2[3] ^= 1
+    u2 = ulen.copy(); u2[0] += 1
+    others = [h(text=t2), h(starts=s2), h(ids=i2), h(ulen=u2), h(m=12), h(k=16), h(with_unitigs=False)]
+    assert len(set(others + [base])) == len(others) + 1
+    # bits of the last word past base n are padding, not input (n = 1000: 8 bases, 16 bits, in the last word)
+    t3 = text.copy(); t3[-1] ^= np.uint64(1) << np.uint64(40)
+    assert h(text=t3) == base
+
+
 def _has_gpu():
     try:
         import torch

@@ -168,6 +168,17 @@ typedef struct mr_result_view {
 } mr_result_view;
 int  mr_result_get(const mr_result* r, mr_result_view* view);
 
+/* ---- overlap graph over rows the caller already has: replaces overlap_graph::thread::reset +
+ *  traverse (overlap_graph.hpp:177-198, overlap_graph.cc:7-59) as longest_path_overlap_graph2.cc:46-49
+ *  calls them on the rows of a coords file.  `rows` is an mr_result_view in HOST memory whose
+ *  coords columns and kmers_info / bases_info are filled (graph pointers ignored); rows->sr[i]
+ *  indexes the caller's table of unitig paths (path_ids[path_off[s] .. path_off[s + 1]) as
+ *  id << 1 | (orientation == 'R'), rows->use_bwd[i] reads it reversed and flipped).  Rows keep
+ *  their order; the result echoes them and adds the node arrays.                                   */
+int  mr_graph_batch(mr_context* ctx, const mr_params* params, const mr_result_view* rows, const uint32_t* read_len,
+                    const uint32_t* path_ids, const uint64_t* path_off, uint32_t npaths,
+                    const int32_t* unitig_len, uint32_t n_unitigs, mr_result** out);
+
 /* parity tap: per-(read, super-read) hit lists and chains of the last batch, in the layout of
  * tests/oracle_lib.py (groups[g] = {read, sr, n_fwd, n_bwd, lis_fwd, lis_bwd}); only filled when
  * mr_context_keep_taps(ctx, 1) was called before the batch. */

@@ -13,6 +13,77 @@
 namespace {
 
 // MR_TRACE=1: progress lines on stderr (which phase a stuck batch is in)
+// ------------------------------------------------------------------------------------------------
+// final rows, graph node arrays and the copy of both to one pinned slab: shared by mr_align_batch
+// and mr_graph_batch
+// ------------------------------------------------------------------------------------------------
+static int setup_final_rows(mr_context* ctx, mr_workspace& ws, uint64_t Sc, coords_soa& fin) {
+  memset(&fin, 0, sizeof(fin));
+  MR_TRY(ws.fin_i32.ensure(ctx, Sc * 4 * 5)); MR_TRY(ws.fin_u32.ensure(ctx, Sc * 4 * 8)); MR_TRY(ws.fin_f64.ensure(ctx, Sc * 8 * 3));
+  MR_TRY(ws.fin_u64.ensure(ctx, Sc * 8 * 3)); MR_TRY(ws.fin_u8.ensure(ctx, Sc * 2));
+  { int32_t* b = ws.fin_i32.as<int32_t>(); fin.rs = b; fin.re = b + Sc; fin.qs = b + 2 * Sc; fin.qe = b + 3 * Sc; fin.nb_mers = b + 4 * Sc; }
+  { uint32_t* b = ws.fin_u32.as<uint32_t>(); fin.pb_cons = b; fin.sr_cons = b + Sc; fin.pb_cover = b + 2 * Sc; fin.sr_cover = b + 3 * Sc;
+    fin.ql = b + 4 * Sc; fin.sr = b + 5 * Sc; fin.read = b + 6 * Sc; fin.info_len = b + 7 * Sc; }
+  { double* b = ws.fin_f64.as<double>(); fin.stretch = b; fin.offset = b + Sc; fin.avg_err = b + 2 * Sc; }
+  { uint64_t* b = ws.fin_u64.as<uint64_t>(); fin.info_off = b; fin.chain_pos = b + Sc; }
+  { uint8_t* b = ws.fin_u8.as<uint8_t>(); fin.rn = b; fin.use_bwd = b + Sc; }
+  return MR_OK;
+}
+
+static int setup_graph_nodes(mr_context* ctx, mr_workspace& ws, uint64_t Sc, graph_args& GA) {
+  MR_TRY(ws.node_i32.ensure(ctx, Sc * 4 * 7)); MR_TRY(ws.node_u8.ensure(ctx, Sc * 2)); MR_TRY(ws.node_f64.ensure(ctx, Sc * 8 * 2));
+  { int32_t* b = ws.node_i32.as<int32_t>(); GA.lstart = b; GA.lprev = b + Sc; GA.lpath = b + 2 * Sc; GA.lunitigs = b + 3 * Sc;
+    GA.component = b + 4 * Sc; GA.uf_rank = b + 5 * Sc; GA.order = b + 6 * Sc; }
+  { uint8_t* b = ws.node_u8.as<uint8_t>(); GA.start_node = b; GA.end_node = b + Sc; }
+  { double* b = ws.node_f64.as<double>(); GA.imp_s = b; GA.imp_e = b + Sc; }
+  return MR_OK;
+}
+
+static int download_rows(mr_context* ctx, mr_workspace& ws, mr_result* res, const coords_soa& fin, uint32_t nreads, uint64_t S,
+                         uint64_t info_total, const graph_args* GA) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t Sc = std::max<uint64_t>(S, 1);
+  auto rnd = [](uint64_t b) { return (b + 63) / 64 * 64; };
+  uint64_t bytes = rnd(((uint64_t)nreads + 1) * 8) + 5 * rnd(Sc * 4) + 8 * rnd(Sc * 4) + 3 * rnd(Sc * 8) + rnd(Sc * 8) + 2 * rnd(Sc)
+                   + 2 * rnd((info_total + 1) * 4) + (GA ? 2 * rnd(Sc) + 5 * rnd(Sc * 4) : 0);
+  {
+    std::lock_guard<std::mutex> lock(ws.pool_mutex);
+    if(!ws.pinned_pool.empty()) { res->host = ws.pinned_pool.back(); ws.pinned_pool.pop_back(); }
+  }
+  if(!res->host) res->host = new pinned_buf;
+  MR_TRY(res->host->ensure(ctx, bytes + 4096));
+  char* cur = res->host->as<char>();
+  auto pull = [&](const void* dsrc, uint64_t nbytes) -> const void* {
+    void* dst = cur;
+    cur += rnd(std::max<uint64_t>(nbytes, 1));
+    if(nbytes) cudaMemcpyAsync(dst, dsrc, nbytes, cudaMemcpyDeviceToHost, st);
+    return dst;
+  };
+  mr_result_view& v = res->view;
+  v.ncoords = S;
+  v.read_coords = (const uint64_t*)pull(ws.read_coords.p, ((uint64_t)nreads + 1) * 8);
+  v.rs = (const int32_t*)pull(fin.rs, S * 4); v.re = (const int32_t*)pull(fin.re, S * 4);
+  v.qs = (const int32_t*)pull(fin.qs, S * 4); v.qe = (const int32_t*)pull(fin.qe, S * 4);
+  v.nb_mers = (const int32_t*)pull(fin.nb_mers, S * 4);
+  v.pb_cons = (const uint32_t*)pull(fin.pb_cons, S * 4); v.sr_cons = (const uint32_t*)pull(fin.sr_cons, S * 4);
+  v.pb_cover = (const uint32_t*)pull(fin.pb_cover, S * 4); v.sr_cover = (const uint32_t*)pull(fin.sr_cover, S * 4);
+  v.ql = (const uint32_t*)pull(fin.ql, S * 4); v.sr = (const uint32_t*)pull(fin.sr, S * 4);
+  v.rn = (const uint8_t*)pull(fin.rn, S); v.use_bwd = (const uint8_t*)pull(fin.use_bwd, S);
+  v.stretch = (const double*)pull(fin.stretch, S * 8); v.offset = (const double*)pull(fin.offset, S * 8);
+  v.avg_err = (const double*)pull(fin.avg_err, S * 8);
+  v.info_off = (const uint64_t*)pull(fin.info_off, S * 8); v.info_len = (const uint32_t*)pull(fin.info_len, S * 4);
+  v.kmers_info = (const int32_t*)pull(ws.kinfo.p, info_total * 4); v.bases_info = (const int32_t*)pull(ws.binfo.p, info_total * 4);
+  if(GA) {
+    v.start_node = (const uint8_t*)pull(GA->start_node, S); v.end_node = (const uint8_t*)pull(GA->end_node, S);
+    v.lstart = (const int32_t*)pull(GA->lstart, S * 4); v.lprev = (const int32_t*)pull(GA->lprev, S * 4);
+    v.lpath = (const int32_t*)pull(GA->lpath, S * 4); v.lunitigs = (const int32_t*)pull(GA->lunitigs, S * 4);
+    v.component = (const int32_t*)pull(GA->component, S * 4);
+  }
+  MR_CUDA(ctx, cudaGetLastError());
+  return MR_OK;
+}
+
+
 static const bool g_trace = getenv("MR_TRACE") != nullptr;
 #define MR_TRACE_MSG(...) do { if(g_trace) { fprintf(stderr, "[mr] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while(0)
 
@@ -751,16 +822,8 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.read_cnt.as<uint32_t>() }, (uint64_t)nreads + 1,
                                                            ws.read_coords.as<uint64_t>(), ws.scan_scratch, nullptr)));
   coords_soa fin;
-  memset(&fin, 0, sizeof(fin));
   const uint64_t Sc = std::max<uint64_t>(S, 1);
-  MR_TRY(ws.fin_i32.ensure(ctx, Sc * 4 * 5)); MR_TRY(ws.fin_u32.ensure(ctx, Sc * 4 * 8)); MR_TRY(ws.fin_f64.ensure(ctx, Sc * 8 * 3));
-  MR_TRY(ws.fin_u64.ensure(ctx, Sc * 8 * 3)); MR_TRY(ws.fin_u8.ensure(ctx, Sc * 2));
-  { int32_t* b = ws.fin_i32.as<int32_t>(); fin.rs = b; fin.re = b + Sc; fin.qs = b + 2 * Sc; fin.qe = b + 3 * Sc; fin.nb_mers = b + 4 * Sc; }
-  { uint32_t* b = ws.fin_u32.as<uint32_t>(); fin.pb_cons = b; fin.sr_cons = b + Sc; fin.pb_cover = b + 2 * Sc; fin.sr_cover = b + 3 * Sc;
-    fin.ql = b + 4 * Sc; fin.sr = b + 5 * Sc; fin.read = b + 6 * Sc; fin.info_len = b + 7 * Sc; }
-  { double* b = ws.fin_f64.as<double>(); fin.stretch = b; fin.offset = b + Sc; fin.avg_err = b + 2 * Sc; }
-  { uint64_t* b = ws.fin_u64.as<uint64_t>(); fin.info_off = b; fin.chain_pos = b + Sc; }
-  { uint8_t* b = ws.fin_u8.as<uint8_t>(); fin.rn = b; fin.use_bwd = b + Sc; }
+  MR_TRY(setup_final_rows(ctx, ws, Sc, fin));
   uint64_t* sv_info_off = ws.fin_u64.as<uint64_t>() + 2 * Sc;
   MR_TRY(ws.kinfo.ensure(ctx, (info_total + 1) * 4)); MR_TRY(ws.binfo.ensure(ctx, (info_total + 1) * 4));
   if(S) {
@@ -796,61 +859,19 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   memset(&GA, 0, sizeof(GA));
   if(graph) {
     timer.next("overlap graph");
-    MR_TRY(ws.node_i32.ensure(ctx, Sc * 4 * 7)); MR_TRY(ws.node_u8.ensure(ctx, Sc * 2)); MR_TRY(ws.node_f64.ensure(ctx, Sc * 8 * 2));
     GA.nreads = nreads; GA.read_coords = ws.read_coords.as<uint64_t>(); GA.read_len = ws.read_len.as<uint32_t>(); GA.c = fin;
     GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
     GA.unitig_ids = idx->unitig_ids.as<uint32_t>(); GA.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
     GA.unitig_len = idx->unitig_len.as<int32_t>(); GA.n_unitigs = idx->n_unitigs; GA.unitigs_k = p->unitigs_k;
     GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases;
-    { int32_t* b = ws.node_i32.as<int32_t>(); GA.lstart = b; GA.lprev = b + Sc; GA.lpath = b + 2 * Sc; GA.lunitigs = b + 3 * Sc;
-      GA.component = b + 4 * Sc; GA.uf_rank = b + 5 * Sc; GA.order = b + 6 * Sc; }
-    { uint8_t* b = ws.node_u8.as<uint8_t>(); GA.start_node = b; GA.end_node = b + Sc; }
-    { double* b = ws.node_f64.as<double>(); GA.imp_s = b; GA.imp_e = b + Sc; }
+    MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
     if(S) MR_TRY(launch_graph(ctx, GA));
   }
   timer.next("result download");
   MR_TRACE_MSG("ordered%s; downloading", graph ? " + graph" : "");
 
   // ---- results to pinned host memory ----------------------------------------------------------------
-  {
-    auto rnd = [](uint64_t b) { return (b + 63) / 64 * 64; };
-    uint64_t bytes = rnd(((uint64_t)nreads + 1) * 8) + 5 * rnd(Sc * 4) + 8 * rnd(Sc * 4) + 3 * rnd(Sc * 8) + rnd(Sc * 8) + 2 * rnd(Sc)
-                     + 2 * rnd((info_total + 1) * 4) + (graph ? 2 * rnd(Sc) + 5 * rnd(Sc * 4) : 0);
-    {
-      std::lock_guard<std::mutex> lock(ws.pool_mutex);
-      if(!ws.pinned_pool.empty()) { res->host = ws.pinned_pool.back(); ws.pinned_pool.pop_back(); }
-    }
-    if(!res->host) res->host = new pinned_buf;
-    MR_TRY(res->host->ensure(ctx, bytes + 4096));
-    char* cur = res->host->as<char>();
-    auto pull = [&](const void* dsrc, uint64_t nbytes) -> const void* {
-      void* dst = cur;
-      cur += rnd(std::max<uint64_t>(nbytes, 1));
-      if(nbytes) cudaMemcpyAsync(dst, dsrc, nbytes, cudaMemcpyDeviceToHost, st);
-      return dst;
-    };
-    mr_result_view& v = res->view;
-    v.ncoords = S;
-    v.read_coords = (const uint64_t*)pull(ws.read_coords.p, ((uint64_t)nreads + 1) * 8);
-    v.rs = (const int32_t*)pull(fin.rs, S * 4); v.re = (const int32_t*)pull(fin.re, S * 4);
-    v.qs = (const int32_t*)pull(fin.qs, S * 4); v.qe = (const int32_t*)pull(fin.qe, S * 4);
-    v.nb_mers = (const int32_t*)pull(fin.nb_mers, S * 4);
-    v.pb_cons = (const uint32_t*)pull(fin.pb_cons, S * 4); v.sr_cons = (const uint32_t*)pull(fin.sr_cons, S * 4);
-    v.pb_cover = (const uint32_t*)pull(fin.pb_cover, S * 4); v.sr_cover = (const uint32_t*)pull(fin.sr_cover, S * 4);
-    v.ql = (const uint32_t*)pull(fin.ql, S * 4); v.sr = (const uint32_t*)pull(fin.sr, S * 4);
-    v.rn = (const uint8_t*)pull(fin.rn, S); v.use_bwd = (const uint8_t*)pull(fin.use_bwd, S);
-    v.stretch = (const double*)pull(fin.stretch, S * 8); v.offset = (const double*)pull(fin.offset, S * 8);
-    v.avg_err = (const double*)pull(fin.avg_err, S * 8);
-    v.info_off = (const uint64_t*)pull(fin.info_off, S * 8); v.info_len = (const uint32_t*)pull(fin.info_len, S * 4);
-    v.kmers_info = (const int32_t*)pull(ws.kinfo.p, info_total * 4); v.bases_info = (const int32_t*)pull(ws.binfo.p, info_total * 4);
-    if(graph) {
-      v.start_node = (const uint8_t*)pull(GA.start_node, S); v.end_node = (const uint8_t*)pull(GA.end_node, S);
-      v.lstart = (const int32_t*)pull(GA.lstart, S * 4); v.lprev = (const int32_t*)pull(GA.lprev, S * 4);
-      v.lpath = (const int32_t*)pull(GA.lpath, S * 4); v.lunitigs = (const int32_t*)pull(GA.lunitigs, S * 4);
-      v.component = (const int32_t*)pull(GA.component, S * 4);
-    }
-    MR_CUDA(ctx, cudaGetLastError());
-  }
+  MR_TRY(download_rows(ctx, ws, res.get(), fin, nreads, S, info_total, graph ? &GA : nullptr));
 
   // ---- parity taps: (read, super-read) hit lists and both chains, rows sorted by (read, sr) ------
   if(taps && G) {
@@ -923,6 +944,78 @@ int mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p, const cha
   MR_CUDA(ctx, cudaMemcpyAsync(ws.bases.p, bases, T, cudaMemcpyHostToDevice, ctx->stream));
   MR_CUDA(ctx, cudaMemcpyAsync(ws.read_start.p, read_start, ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   return mr_align_batch_device(ctx, idx, p, ws.bases.as<char>(), ws.read_start.as<uint64_t>(), read_start, nreads, out);
+}
+
+// Overlap graph of coords rows that come from the caller (host memory) instead of from the aligner:
+// replaces overlap_graph::thread::reset + traverse (overlap_graph.hpp:177-198, overlap_graph.cc:7-59)
+// as longest_path_overlap_graph2.cc:46-49 calls them on the rows of a coords file.
+int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* rows, const uint32_t* read_len,
+                   const uint32_t* path_ids, const uint64_t* path_off, uint32_t npaths,
+                   const int32_t* unitig_len, uint32_t n_unitigs, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!p || !rows || !out || !read_len || !path_ids || !path_off || !unitig_len)
+    return ctx->fail(MR_EINVAL, "mr_graph_batch: null argument");
+  if(!p->unitigs_k || !n_unitigs) return ctx->fail(MR_EINVAL, "mr_graph_batch: the overlap graph needs unitig lengths and -k");
+  *out = nullptr;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  cudaStream_t st = ctx->stream;
+  const uint32_t nreads = rows->nreads;
+  const uint64_t S = rows->ncoords, Sc = std::max<uint64_t>(S, 1);
+  if(S >= (1ULL << 31)) return ctx->fail(MR_ELIMIT, "mr_graph_batch: too many rows in one batch");
+  if(rows->read_coords[0] != 0 || rows->read_coords[nreads] != S) return ctx->fail(MR_EINVAL, "mr_graph_batch: read_coords must span [0, ncoords]");
+  uint64_t info_total = 0;
+  for(uint64_t i = 0; i < S; ++i) {
+    if(rows->sr[i] >= npaths) return ctx->fail(MR_EINVAL, "mr_graph_batch: row refers to a path that was not given");
+    if(rows->info_len[i]) info_total = std::max<uint64_t>(info_total, rows->info_off[i] + rows->info_len[i]);
+  }
+  ctx->timers.clear();
+  phase_timer timer(ctx);
+  timer.begin("rows upload");
+  std::unique_ptr<mr_result> res(new mr_result);
+  res->ctx = ctx;
+  memset(&res->view, 0, sizeof(res->view));
+  res->view.nreads = nreads;
+  coords_soa fin;
+  MR_TRY(setup_final_rows(ctx, ws, Sc, fin));
+  MR_TRY(ws.read_coords.ensure(ctx, ((size_t)nreads + 2) * 8));
+  MR_TRY(ws.read_len.ensure(ctx, ((size_t)nreads + 1) * 4));
+  MR_TRY(ws.kinfo.ensure(ctx, (info_total + 1) * 4)); MR_TRY(ws.binfo.ensure(ctx, (info_total + 1) * 4));
+  MR_TRY(ws.path_ids.ensure(ctx, (path_off[npaths] + 1) * 4)); MR_TRY(ws.path_off.ensure(ctx, ((size_t)npaths + 1) * 8));
+  MR_TRY(ws.path_ulen.ensure(ctx, (size_t)n_unitigs * 4));
+  auto push = [&](void* dst, const void* src, uint64_t bytes) { if(bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); };
+  push(ws.read_coords.p, rows->read_coords, ((uint64_t)nreads + 1) * 8);
+  push(ws.read_len.p, read_len, (uint64_t)nreads * 4);
+  push(fin.rs, rows->rs, S * 4); push(fin.re, rows->re, S * 4); push(fin.qs, rows->qs, S * 4); push(fin.qe, rows->qe, S * 4);
+  push(fin.nb_mers, rows->nb_mers, S * 4);
+  push(fin.pb_cons, rows->pb_cons, S * 4); push(fin.sr_cons, rows->sr_cons, S * 4);
+  push(fin.pb_cover, rows->pb_cover, S * 4); push(fin.sr_cover, rows->sr_cover, S * 4);
+  push(fin.ql, rows->ql, S * 4); push(fin.sr, rows->sr, S * 4);
+  push(fin.rn, rows->rn, S); push(fin.use_bwd, rows->use_bwd, S);
+  push(fin.stretch, rows->stretch, S * 8); push(fin.offset, rows->offset, S * 8); push(fin.avg_err, rows->avg_err, S * 8);
+  push(fin.info_off, rows->info_off, S * 8); push(fin.info_len, rows->info_len, S * 4);
+  push(ws.kinfo.p, rows->kmers_info, info_total * 4); push(ws.binfo.p, rows->bases_info, info_total * 4);
+  push(ws.path_ids.p, path_ids, path_off[npaths] * 4); push(ws.path_off.p, path_off, ((uint64_t)npaths + 1) * 8);
+  push(ws.path_ulen.p, unitig_len, (uint64_t)n_unitigs * 4);
+  MR_CUDA(ctx, cudaGetLastError());
+  timer.next("overlap graph");
+  graph_args GA;
+  memset(&GA, 0, sizeof(GA));
+  GA.nreads = nreads; GA.read_coords = ws.read_coords.as<uint64_t>(); GA.read_len = ws.read_len.as<uint32_t>(); GA.c = fin;
+  GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
+  GA.unitig_ids = ws.path_ids.as<uint32_t>(); GA.unitig_off = ws.path_off.as<uint64_t>();
+  GA.unitig_len = ws.path_ulen.as<int32_t>(); GA.n_unitigs = n_unitigs; GA.unitigs_k = p->unitigs_k;
+  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases;
+  MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
+  if(S) MR_TRY(launch_graph(ctx, GA));
+  timer.next("result download");
+  MR_TRY(download_rows(ctx, ws, res.get(), fin, nreads, S, info_total, &GA));
+  timer.end();
+  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  timer.collect();
+  *out = res.release();
+  return MR_OK;
 }
 
 void mr_result_free(mr_result* r) {

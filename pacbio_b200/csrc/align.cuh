@@ -24,6 +24,7 @@ struct coords_soa {
 struct mr_workspace {
   dev_buf bases, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
   dev_buf size, rec, hit_off, thr, counters;
+  dev_buf path_ids, path_off, path_ulen;               // mr_graph_batch: the caller's unitig paths
   dev_buf key0, key1, pay0, pay1, chainL, group_start;
   dev_buf sv_i32, sv_u32, sv_f64, sv_u64, sv_u8;        // survivors, unsorted
   dev_buf fin_i32, fin_u32, fin_f64, fin_u64, fin_u8;   // final rows

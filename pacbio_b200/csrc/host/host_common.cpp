@@ -1,3 +1,5 @@
+#include <cerrno>
+#include <cstring>
 #include "host_common.hpp"
 
 #include <algorithm>
@@ -543,6 +545,111 @@ void format_details(const mr_result* r, const read_batch& batch, const super_rea
     out += '\n';
     off += nf + nb; li += lf + lb;
   }
+}
+
+// ================================================================================================
+// compact coords files
+// ================================================================================================
+void coords_batch::clear() {
+  reads.clear(); read_len.clear();
+  paths = super_reads();
+  paths.unitig_off.push_back(0);
+  read_coords.assign(1, 0); info_off.clear();
+  rs.clear(); re.clear(); qs.clear(); qe.clear(); nb_mers.clear(); kmers_info.clear(); bases_info.clear();
+  pb_cons.clear(); sr_cons.clear(); pb_cover.clear(); sr_cover.clear(); ql.clear(); sr.clear(); info_len.clear();
+  rn.clear(); use_bwd.clear(); stretch.clear(); offset.clear(); avg_err.clear();
+}
+
+mr_result_view coords_batch::view() const {
+  mr_result_view v;
+  memset(&v, 0, sizeof v);
+  v.nreads = reads.nreads(); v.ncoords = rs.size(); v.read_coords = read_coords.data();
+  v.rs = rs.data(); v.re = re.data(); v.qs = qs.data(); v.qe = qe.data(); v.nb_mers = nb_mers.data();
+  v.pb_cons = pb_cons.data(); v.sr_cons = sr_cons.data(); v.pb_cover = pb_cover.data(); v.sr_cover = sr_cover.data();
+  v.ql = ql.data(); v.sr = sr.data(); v.rn = rn.data(); v.use_bwd = use_bwd.data();
+  v.stretch = stretch.data(); v.offset = offset.data(); v.avg_err = avg_err.data();
+  v.info_off = info_off.data(); v.info_len = info_len.data();
+  v.kmers_info = kmers_info.data(); v.bases_info = bases_info.data();
+  return v;
+}
+
+coords_file::coords_file(const std::string& path) : f_(fopen(path.c_str(), "r")) {
+  if(!f_) throw std::runtime_error("Failed to open coords file '" + path + "'");
+}
+
+bool coords_file::getline() {
+  line_.clear();
+  char buf[1 << 16];
+  bool any = false;
+  while(fgets(buf, sizeof buf, f_)) {
+    any = true;
+    const size_t len = strlen(buf);
+    if(len && buf[len - 1] == '\n') { line_.append(buf, len - 1); return true; }
+    line_.append(buf, len);
+  }
+  return any;
+}
+
+bool coords_file::next_batch(coords_batch& b, uint64_t max_rows) {
+  b.clear();
+  if(!started_) {                              // skip the column header: everything before the first '>' line
+    started_ = true;
+    while((pending_ = getline()) && (line_.empty() || line_[0] != '>')) { }
+  }
+  std::vector<uint32_t> upath;
+  while(pending_ && b.rs.size() < max_rows) {
+    if(line_.empty() || line_[0] != '>') throw std::runtime_error("Invalid input file. Line expected to match /^>/ but got: " + line_);
+    char* end = nullptr;
+    errno = 0;
+    const long nb_lines = strtol(line_.c_str() + 1, &end, 10);
+    if(nb_lines <= 0 || errno == ERANGE) throw std::runtime_error("Invalid input file. Expected number of lines but got: " + line_.substr(1));
+    b.reads.name.push_back(*end ? std::string(end + 1) : std::string());
+    uint32_t rl_first = 0;
+    for(long j = 0; j < nb_lines; ++j) {
+      if(!getline()) throw std::runtime_error("Invalid input file. File truncated");
+      const char* p = line_.c_str();
+      char* q = nullptr;
+      auto integer = [&]() -> long { const long v = strtol(p, &q, 10); p = q; return v; };
+      auto real = [&]() -> double { const double v = strtod(p, &q); p = q; return v; };
+      b.rs.push_back((int32_t)integer()); b.re.push_back((int32_t)integer());
+      b.qs.push_back((int32_t)integer()); b.qe.push_back((int32_t)integer());
+      b.nb_mers.push_back((int32_t)integer());
+      b.pb_cons.push_back((uint32_t)integer()); b.sr_cons.push_back((uint32_t)integer());
+      b.pb_cover.push_back((uint32_t)integer()); b.sr_cover.push_back((uint32_t)integer());
+      const uint32_t rl = (uint32_t)integer();
+      if(j == 0) rl_first = rl;
+      b.ql.push_back((uint32_t)integer());
+      b.stretch.push_back(real()); b.offset.push_back(real()); b.avg_err.push_back(real());
+      while(*p == ' ' || *p == '\t') ++p;
+      const char* ne = p;
+      while(*ne && *ne != ' ' && *ne != '\t') ++ne;
+      b.paths.name.emplace_back(p, ne);
+      parse_path(b.paths.name.back(), upath);
+      b.paths.unitig_ids.insert(b.paths.unitig_ids.end(), upath.begin(), upath.end());
+      b.paths.unitig_off.push_back(b.paths.unitig_ids.size());
+      b.sr.push_back((uint32_t)(b.paths.name.size() - 1));
+      b.rn.push_back(0); b.use_bwd.push_back(0);
+      p = ne;
+      b.info_off.push_back(b.kmers_info.size());
+      uint32_t ninfo = 0;
+      while(true) {                            // "mers:bases" pairs until something else
+        const long m = strtol(p, &q, 10);
+        if(q == p || *q != ':') break;
+        const char* p2 = q + 1;
+        const long bs = strtol(p2, &q, 10);
+        if(q == p2) break;
+        b.kmers_info.push_back((int32_t)m); b.bases_info.push_back((int32_t)bs);
+        ++ninfo;
+        p = q;
+      }
+      b.info_len.push_back(ninfo);
+    }
+    b.read_len.push_back(rl_first);
+    b.reads.start.push_back(b.reads.start.back() + rl_first);
+    b.read_coords.push_back(b.rs.size());
+    pending_ = getline();
+  }
+  return b.reads.nreads() != 0;
 }
 
 } // namespace mrh

@@ -96,4 +96,33 @@ void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0
 // taps of the result (mr_context_keep_taps).
 void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, std::string& out);
 
+// ---- compact coords files (jf_aligner --coords, format of print_coords, jf_aligner.cc:41-70),
+// read back the way longest_path_overlap_graph2 does (coords_parsing.cc:7-64): records
+// ">N read-name" + N rows; a row = 14 numbers, the super-read name (a unitig path), then one
+// "mers:bases" pair per kmers_info entry.  One batch holds the rows of whole reads as the columns
+// of an mr_result_view over its own vectors, ready for mr_graph_batch.
+struct coords_batch {
+  read_batch  reads;                    // names; start[] is the running sum of Rlen (no bases)
+  std::vector<uint32_t> read_len;
+  super_reads paths;                    // entry i: name and unitig path of row i
+  std::vector<uint64_t> read_coords, info_off;
+  std::vector<int32_t>  rs, re, qs, qe, nb_mers, kmers_info, bases_info;
+  std::vector<uint32_t> pb_cons, sr_cons, pb_cover, sr_cover, ql, sr, info_len;
+  std::vector<uint8_t>  rn, use_bwd;
+  std::vector<double>   stretch, offset, avg_err;
+  mr_result_view view() const;
+  void clear();
+};
+class coords_file {
+  FILE* f_ = nullptr;
+  std::string line_;
+  bool started_ = false, pending_ = false;
+  bool getline();
+public:
+  explicit coords_file(const std::string& path);
+  ~coords_file() { if(f_) fclose(f_); }
+  // appends whole reads until the batch holds >= max_rows rows; false when the file is exhausted
+  bool next_batch(coords_batch& b, uint64_t max_rows);
+};
+
 } // namespace mrh

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/synth_*.{json,cmr.txt,coords.txt} by running the REFERENCE ITSELF
+"""Regenerates tests/golden/synth_*.{json,cmr.txt,coords.txt,lp.txt,lp_maximal.txt} by running the REFERENCE ITSELF
 (oracle/_ref, compiled from /root/reference by oracle/Makefile) on seeded synthetic inputs made by
 pacbio_b200/tools/gen_synth.  Run in the build container only (needs oracle/_ref):
 
@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle_lib import REF_CMR, REF_JFA, Ref, gen_synth  # noqa: E402
+from oracle_lib import REF_CMR, REF_JFA, REF_LP, Ref, gen_synth  # noqa: E402
 
 CONFIGS = {
     "synth_g1": dict(gen=dict(genome=120000, coverage=3, read_len=4000, error=0.15, seed=11, repeat_frac=0.1),
@@ -61,7 +61,23 @@ def text_codes_of(sr_fasta):
     return ((b >> 1) ^ (b >> 2)) & 3
 
 
+LP_VARIANTS = {"lp": [], "lp_maximal": ["-T", "maximal", "--trim", "match", "-b", "-O", "1.5", "-d", "0.01"]}
+
+
+def longest_path_goldens():
+    """synth_*.lp*.txt: the reference's longest_path_overlap_graph2 on the committed coords files."""
+    for name, cfg in CONFIGS.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            info = gen_synth(os.path.join(tmp, name), **cfg["gen"])
+            for tag, extra in LP_VARIANTS.items():
+                subprocess.check_call([REF_LP, "-k", str(cfg["unitig_k"]), "-l", info["unitigs_len"], "-t", "1"] + extra +
+                                      ["-o", os.path.join(HERE, "%s.%s.txt" % (name, tag)), os.path.join(HERE, name + ".coords.txt")])
+            print(name, "longest path goldens written")
+
+
 def main():
+    if "--only-longest-path" in sys.argv:
+        return longest_path_goldens()
     ref = Ref()
     for name, cfg in CONFIGS.items():
         with tempfile.TemporaryDirectory() as tmp:
@@ -110,3 +126,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if "--only-longest-path" not in sys.argv:
+        longest_path_goldens()

@@ -19,6 +19,7 @@ PORT_SO = os.path.join(ORACLE_DIR, "liboracle_port.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref_tap.so")
 REF_CMR = os.path.join(ORACLE_DIR, "_ref", "create_mega_reads")
 REF_JFA = os.path.join(ORACLE_DIR, "_ref", "jf_aligner")
+REF_LP = os.path.join(ORACLE_DIR, "_ref", "longest_path_overlap_graph2")
 GEN = os.path.join(ROOT, "pacbio_b200", "tools", "gen_synth")
 
 

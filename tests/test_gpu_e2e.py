@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 CMR = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
 JFA = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
+LPG = os.path.join(ROOT, "pacbio_b200", "bin", "longest_path_overlap_graph2")
 
 
 def sha(b):
@@ -93,6 +94,51 @@ def test_reference_generated_fixtures(tmpdir_session, tmp_path, name):
     out_c = str(tmp_path / "coords.txt")
     run([JFA] + common + ["-l", info["unitigs_len"], "-H", "--coords", out_c])
     assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
+
+
+LP_VARIANTS = {"lp": [], "lp_maximal": ["-T", "maximal", "--trim", "match", "-b", "-O", "1.5", "-d", "0.01"]}   # as in make_golden.py
+
+
+@pytest.mark.parametrize("variant", sorted(LP_VARIANTS))
+@pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
+def test_longest_path_matches_reference_fixture(tmpdir_session, tmp_path, name, variant):
+    """longest_path_overlap_graph2 (coords file -> overlap graph on the GPU -> mega-reads) against the
+    reference binary's output on the same committed coords file, byte for byte."""
+    cfg = json.load(open(os.path.join(GOLD, name + ".json")))["config"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    out = str(tmp_path / "lp.txt")
+    run([LPG, "-k", str(cfg["unitig_k"]), "-l", info["unitigs_len"], "-t", "3"] + LP_VARIANTS[variant] +
+        ["-o", out, os.path.join(GOLD, name + ".coords.txt")])
+    assert open(out).read() == open(os.path.join(GOLD, "%s.%s.txt" % (name, variant))).read()
+    # small batches (several mr_graph_batch calls) give the same file
+    out2 = str(tmp_path / "lp2.txt")
+    run([LPG, "-k", str(cfg["unitig_k"]), "-l", info["unitigs_len"]] + LP_VARIANTS[variant] +
+        ["-o", out2, os.path.join(GOLD, name + ".coords.txt")], env=dict(os.environ, MR_BATCH_ROWS="37"))
+    assert open(out2).read() == open(out).read()
+
+
+def test_longest_path_agrees_with_create_mega_reads(tmpdir_session, tmp_path):
+    """jf_aligner --coords | longest_path_overlap_graph2 is the same pipeline as create_mega_reads cut in two at a text
+    file; apart from the decimals lost in that file the two give the same mega-reads (same reads, same super-read paths)."""
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_lp_pipe"), 200000, coverage=4, read_len=4000, seed=29)
+    common = ["-s", "1M", "-m", "15", "-k", "41", "-r", info["sr"], "-p", info["reads"]]
+    coords, lp, cmr = (str(tmp_path / n) for n in ("coords.txt", "lp.txt", "cmr.txt"))
+    run([JFA] + common + ["-l", info["unitigs_len"], "--coords", coords])
+    run([LPG, "-k", "41", "-l", info["unitigs_len"], "-o", lp, coords])
+    run([CMR] + common + ["-l", info["unitigs_len"], "-o", cmr])
+
+    def paths(path):
+        out, cur = {}, None
+        for line in open(path):
+            if line.startswith(">"):
+                cur = out.setdefault(line.strip(), [])
+            else:
+                cur.append(line.split()[8])
+        return out
+    a, b = paths(lp), paths(cmr)
+    assert len(b) > 100
+    same = sum(1 for k in b if a.get(k) == b[k])
+    assert same >= 0.98 * len(b), (same, len(b))
 
 
 @pytest.mark.parametrize("tiling,trim,bases", [("greedy", "none", False), ("maximal", "match", False),

@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pacbio_b200", "libmegareads_b200.so")
 CMR = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
 JFA = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
+LPG = os.path.join(ROOT, "pacbio_b200", "bin", "longest_path_overlap_graph2")
 GOLD = os.path.join(ROOT, "tests", "golden", "aligner_output")
 
 
@@ -96,6 +97,19 @@ def test_create_mega_reads_rejects_bad_command_lines(args, msg):
     r = subprocess.run([CMR] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1
     assert msg in r.stderr
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["coords.txt"], b"[-k, --k-mer=uint32] required switch"),
+    (["-k", "41"], b"Requires exactly 1 argument"),
+    (["-k", "41", "coords.txt"], b"One of --unitigs-lengths or --unitigs-sequences is required"),
+    (["-k", "41", "-l", "a", "-u", "b", "coords.txt"], b"mutually exclusive"),
+    (["-k", "41", "-l", "a", "-T", "weighted", "coords.txt"], b"Invalid enum"),
+])
+def test_longest_path_rejects_bad_command_lines(args, msg):
+    """longest_path_overlap_graph2_cmdline.yaggo + longest_path_overlap_graph2.cc:71-72"""
+    r = subprocess.run([LPG] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and msg in r.stderr and r.stdout == b""
 
 
 def test_jf_aligner_needs_an_output():

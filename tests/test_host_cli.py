@@ -13,12 +13,14 @@ LIB = os.path.join(ROOT, "pacbio_b200", "libmegareads_b200.so")
 CMR = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
 JFA = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
 LPG = os.path.join(ROOT, "pacbio_b200", "bin", "longest_path_overlap_graph2")
+MRG = os.path.join(ROOT, "pacbio_b200", "bin", "merge_coords")
+REF_MRG = os.path.join(ROOT, "oracle", "_ref", "merge_coords")
 GOLD = os.path.join(ROOT, "tests", "golden", "aligner_output")
 
 
 @pytest.fixture(scope="module", autouse=True)
 def built():
-    if not (os.path.exists(LIB) and os.path.exists(CMR) and os.path.exists(JFA)):
+    if not all(os.path.exists(p) for p in (LIB, CMR, JFA, LPG, MRG)):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "pacbio_b200", "csrc"), "all"], stdout=subprocess.DEVNULL)
 
 
@@ -110,6 +112,49 @@ def test_longest_path_rejects_bad_command_lines(args, msg):
     """longest_path_overlap_graph2_cmdline.yaggo + longest_path_overlap_graph2.cc:71-72"""
     r = subprocess.run([LPG] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and msg in r.stderr and r.stdout == b""
+
+
+def test_merge_coords(tmp_path):
+    """merge_coords.cc:11-84: per read, the rows of every input in input order; same reads in the same order required."""
+    g = os.path.join(ROOT, "tests", "golden")
+    a = os.path.join(g, "synth_g1.coords.txt")
+    # a second file over the same reads: every other row of the first, reads without rows kept as ">0 name"
+    b = str(tmp_path / "b.txt")
+    with open(b, "w") as f:
+        rec = []
+        for line in open(a).read().splitlines() + [">"]:
+            if line.startswith(">"):
+                if rec:
+                    keep = rec[1::2]
+                    f.write(">%d %s\n" % (len(keep), rec[0].split(" ", 1)[1]))
+                    f.write("".join(l + "\n" for l in keep))
+                rec = [line]
+            else:
+                rec.append(line)
+    out = subprocess.run([MRG, a, b, a], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    na = {l.split(" ", 1)[1]: int(l[1:].split()[0]) for l in open(a) if l.startswith(">")}
+    nb = {l.split(" ", 1)[1].strip(): int(l[1:].split()[0]) for l in open(b) if l.startswith(">")}
+    heads = [l for l in out if l.startswith(">")]
+    assert len(heads) == len(na)
+    for h in heads:
+        name = h.split(" ", 1)[1]
+        assert int(h[1:].split()[0]) == 2 * na[name + "\n"] + nb[name]
+    assert len(out) == len(heads) + 2 * sum(na.values()) + sum(nb.values())
+    if os.path.exists(REF_MRG):                     # the compiled reference, when it is there
+        want = subprocess.run([REF_MRG, a, b, a], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+        assert out == want
+    # one input: copied; none: empty; -o writes the file
+    assert subprocess.run([MRG, a], stdout=subprocess.PIPE, check=True).stdout == open(a, "rb").read()
+    assert subprocess.run([MRG], stdout=subprocess.PIPE, check=True).stdout == b""
+    o = str(tmp_path / "o.txt")
+    subprocess.run([MRG, "-o", o, a, b], check=True)
+    assert open(o).read().count(">") == len(na)
+    # different reads / different order: error, exit 1
+    other = os.path.join(g, "synth_g2.coords.txt")
+    r = subprocess.run([MRG, a, other], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and (b"Invalid order of query sequence" in r.stderr or b"prematurely" in r.stderr)
+    r = subprocess.run([MRG, a, str(tmp_path / "missing")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"Error opening coords file" in r.stderr
 
 
 def test_jf_aligner_needs_an_output():

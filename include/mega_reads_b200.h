@@ -117,6 +117,7 @@ typedef struct mr_params {
   double   errors;             /* -e 3.0   */
   int32_t  bases;              /* -b       */
   int32_t  run_graph;          /* 0: stop after coords (jf_aligner), 1: also run the overlap graph */
+  uint32_t fine_mer;           /* -F: mer length of the fine pass (fine_aligner.cc:38-51), 0 = none; < -m    */
 } mr_params;
 void mr_params_default(mr_params* p);
 

@@ -1,4 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- NOT PART OF THE PRODUCT.  See oracle_port.hpp.
+#include <limits>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -143,6 +144,30 @@ void sr_index::search(uint64_t mer, uint64_t& index_out, uint64_t& nb_out) const
   index_out = nb_out ? f : 0;
 }
 
+void sr_index::search_k(uint64_t mer, unsigned kk, uint64_t& index_out, uint64_t& nb_out) const {
+  // mer_sa_imp.hpp:369-381 (pattern not longer than psa-min: the counts table alone) and :382-479
+  // (longer: search on the first kk bases); both return the SA entries whose text starts with the
+  // pattern, entries with fewer than kk bases left never match.
+  const uint64_t N = text.size();
+  uint64_t a = 0, b = sa.size();
+  while(a < b) { const uint64_t mid = (a + b) / 2; if(kmer_at(sa[mid], kk) < mer) a = mid + 1; else b = mid; }
+  const uint64_t first = a;
+  b = sa.size();
+  while(a < b) { const uint64_t mid = (a + b) / 2; if(kmer_at(sa[mid], kk) <= mer) a = mid + 1; else b = mid; }
+  uint64_t last = a, f = first;
+  while(f < last && sa[f] + kk > N) ++f;
+  nb_out    = last - f;
+  index_out = nb_out ? f : 0;
+}
+
+bool sr_index::locate_k(uint64_t x, unsigned kk, uint32_t& sr, int32_t& off) const {
+  const size_t i = std::upper_bound(starts.begin(), starts.end(), x) - starts.begin() - 1;
+  if(x + kk > starts[i + 1]) return false;
+  sr  = i;
+  off = (int32_t)(x - starts[i] + 1);
+  return true;
+}
+
 bool sr_index::locate(uint64_t x, uint32_t& sr, int32_t& off) const {
   const size_t i = std::upper_bound(starts.begin(), starts.end(), x) - starts.begin() - 1;
   if(x + k > starts[i + 1]) return false;
@@ -209,6 +234,30 @@ std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, 
     chain_stats.lists++; chain_stats.hits += N; chain_stats.front += st_front; chain_stats.steps += st_steps;
     chain_stats.none += st_none; chain_stats.none_steps += st_none_steps; chain_stats.depth += st_depth;
     if(N > 512) { chain_stats.big_lists++; chain_stats.big_hits += N; chain_stats.big_front += st_front; chain_stats.big_steps += st_steps; chain_stats.big_depth += st_depth; }
+  }
+  std::vector<uint32_t> res(longest);
+  for(uint32_t t = 0, cur = best; t < longest; ++t, cur = P[cur]) res[longest - 1 - t] = cur;
+  return res;
+}
+
+// lis_align::accept_all for both predicates (fine_aligner.cc:43-46): only the strict increase of the
+// super-read offset decides whether an element extends a list entry
+static std::vector<uint32_t> chain_accept_all(const std::vector<std::pair<int,int>>& X) {
+  struct elt { uint32_t idx, len; };
+  const uint32_t N = X.size();
+  std::vector<elt>      L;
+  std::vector<uint32_t> P(N, N);
+  uint32_t longest = 0, best = 0;
+  L.reserve(N);
+  for(uint32_t i = 0; i < N; ++i) {
+    elt e = { i, 1 };
+    int prev = -1;
+    for(size_t p = 0; p < L.size(); ++p) {
+      if(X[i].second > X[L[p].idx].second) { e.len = L[p].len + 1; P[i] = L[p].idx; break; }
+      if(prev < 0 || L[p].len < L[prev].len) prev = p;
+    }
+    L.insert(L.begin() + (prev + 1), e);
+    if(longest < e.len) { longest = e.len; best = i; }
   }
   std::vector<uint32_t> res(longest);
   for(uint32_t t = 0, cur = best; t < longest; ++t, cur = P[cur]) res[longest - 1 - t] = cur;
@@ -356,7 +405,13 @@ void kmers_info_state::add_mer(int pos) {
 
 coords compute_coords_info(const sr_index& idx, const mer_lists& ml, uint64_t pb_size, const params& p,
                            const std::vector<int>* unitigs_lengths) {
-  const unsigned k = idx.k;
+  return compute_coords_info_k(idx, ml, pb_size, p, unitigs_lengths, idx.k, p.forward);
+}
+
+coords compute_coords_info_k(const sr_index& idx, const mer_lists& ml, uint64_t pb_size, const params& p0,
+                             const std::vector<int>* unitigs_lengths, unsigned k, bool forward) {
+  params p = p0;
+  p.forward = forward;
   const size_t nf = ml.fwd.lis.size(), nb = ml.bwd.lis.size();
   const bool fwd_align = nf >= nb;
   coords c;
@@ -475,6 +530,78 @@ void align_read(const sr_index& idx, const std::string& read, const params& p,
   // create_mega_reads.cc:69-77 sorts (unstably) by (rs, re, ql); ties are broken here by
   // emission order, i.e. by super-read index -- the canonical order of this project.
   if(getenv("ORACLE_TIE_REVERSE")) std::reverse(out.begin(), out.end());   // diagnostic: break (rs, re, ql) ties the other way
+  std::stable_sort(out.begin(), out.end(), [](const coords& a, const coords& b) {
+    return a.rs < b.rs || (a.rs == b.rs && (a.re < b.re || (a.re == b.re && a.ql < b.ql)));
+  });
+}
+
+// ===========================================================================
+// fine pass (reference: fine_aligner.hpp:49-58, fine_aligner.cc:7-51)
+// ===========================================================================
+void fine_align_read(const sr_index& idx, const std::string& read, const params& p, unsigned fine_k,
+                     const std::vector<int>* unitigs_lengths, const std::vector<coords>& coarse, std::vector<coords>& out) {
+  struct window { double begin, end; mer_lists ml; };
+  // the reference keys this map by the address of the super-read's name (iteration order =
+  // allocation order of the frag_info objects); only the order of exact (rs, re, ql) ties depends on it
+  std::map<uint32_t, std::vector<window>> wins;
+  for(const coords& c : coarse) {                          // prime_frags_pos, fine_aligner.hpp:49-58
+    window w;
+    const double s1 = c.stretch + c.offset;
+    w.begin = std::max(0.0, s1 - c.avg_err);
+    const double t = c.stretch * (double)c.ql;
+    const double e1 = t + c.offset;
+    const double e2 = e1 + c.avg_err;
+    w.end = std::min((double)c.rl, e2 - (double)fine_k);
+    w.ml.sr = c.sr;
+    wins[c.sr].push_back(std::move(w));
+  }
+  // fetch_local_super_reads, fine_aligner.cc:7-36; the mer stream is parser_base::next (jf_aligner.hpp:113-123)
+  const uint64_t mask = fine_k < 32 ? (1ULL << (2 * fine_k)) - 1 : ~0ULL;
+  uint64_t m = 0, rm = 0;
+  unsigned len = 0;
+  for(size_t i = 0; i < read.size(); ++i) {
+    int code;
+    switch(read[i]) {
+    case 'a': case 'A': code = 0; break;
+    case 'c': case 'C': code = 1; break;
+    case 'g': case 'G': code = 2; break;
+    case 't': case 'T': code = 3; break;
+    default: code = -1;
+    }
+    if(code < 0) { len = 0; continue; }
+    ++len;
+    m  = ((m << 2) | (uint64_t)code) & mask;
+    rm = (rm >> 2) | ((uint64_t)(3 - code) << (2 * (fine_k - 1)));
+    if(len < fine_k) continue;
+    const bool canonical = m < rm;
+    const int pb_off = (int)(i + 1) - (int)fine_k + 1;
+    uint64_t ri[2], rn[2];
+    idx.search_k(canonical ? m : rm, fine_k, ri[0], rn[0]);
+    idx.search_k(canonical ? rm : m, fine_k, ri[1], rn[1]);
+    for(int pass = 0; pass < 2; ++pass) {
+      for(uint64_t r = ri[pass]; r < ri[pass] + rn[pass]; ++r) {
+        uint32_t sr; int32_t off;
+        if(!idx.locate_k(idx.sa[r], fine_k, sr, off)) continue;
+        if(pass) off = -off;
+        if(!canonical) off = -off;
+        auto it = wins.find(sr);
+        if(it == wins.end()) continue;
+        for(window& w : it->second)
+          if((double)pb_off >= w.begin && (double)pb_off <= w.end)
+            (off > 0 ? w.ml.fwd : w.ml.bwd).offsets.push_back(std::make_pair(pb_off, off));
+      }
+    }
+  }
+  out.clear();
+  const double inf = std::numeric_limits<double>::infinity();
+  (void)inf;
+  for(auto& it : wins) {
+    for(window& w : it.second) {                           // fine_aligner.cc:43-50: accept-all LIS, every window gives a row
+      w.ml.fwd.lis = chain_accept_all(w.ml.fwd.offsets);
+      w.ml.bwd.lis = chain_accept_all(w.ml.bwd.offsets);
+      out.push_back(compute_coords_info_k(idx, w.ml, read.size(), p, unitigs_lengths, fine_k, true));
+    }
+  }
   std::stable_sort(out.begin(), out.end(), [](const coords& a, const coords& b) {
     return a.rs < b.rs || (a.rs == b.rs && (a.re < b.re || (a.re == b.re && a.ql < b.ql)));
   });

@@ -43,6 +43,9 @@ struct sr_index {
   void build(unsigned m_, unsigned k_);        // mer_sa_imp.hpp:197-253,352-366
   uint64_t kmer_at(uint64_t pos, unsigned len) const;   // padded with A past the end
   void search(uint64_t mer, uint64_t& index_out, uint64_t& nb_out) const; // mer_sa_imp.hpp:369-479
+  // the same search with a pattern of kk <= k bases (the fine pass looks up shorter mers in the same SA)
+  void search_k(uint64_t mer, unsigned kk, uint64_t& index_out, uint64_t& nb_out) const;
+  bool locate_k(uint64_t x, unsigned kk, uint32_t& sr, int32_t& off) const;
   // SA entry -> (super-read, 1-based offset); false if the k-mer straddles two sequences
   bool locate(uint64_t x, uint32_t& sr, int32_t& off) const;  // superread_parser.hpp:110-134
 };
@@ -98,6 +101,16 @@ void fetch_super_reads(const sr_index& idx, const std::string& read, int max_cou
 // pb_aligner.cc:11-82
 coords compute_coords_info(const sr_index& idx, const mer_lists& ml, uint64_t pb_size, const params& p,
                            const std::vector<int>* unitigs_lengths);
+
+// same with the mer length given (the fine pass: align_k = --fine-mer, forward = true)
+coords compute_coords_info_k(const sr_index& idx, const mer_lists& ml, uint64_t pb_size, const params& p,
+                             const std::vector<int>* unitigs_lengths, unsigned k, bool forward);
+
+// fine_aligner.hpp:49-58 + fine_aligner.cc:7-51: one window per coarse row, all hits of the shorter
+// mer that fall on the row's super-read inside the window, accept-all chaining, coords with
+// align_k = fine_k.  Output sorted like align_read's (ties: super-read index, then coarse order).
+void fine_align_read(const sr_index& idx, const std::string& read, const params& p, unsigned fine_k,
+                     const std::vector<int>* unitigs_lengths, const std::vector<coords>& coarse, std::vector<coords>& out);
 
 // coarse_aligner.cc:42-60; output sorted by (rs, re, ql, sr) (create_mega_reads.cc:69-77 + tie rule)
 void align_read(const sr_index& idx, const std::string& read, const params& p,

@@ -84,6 +84,10 @@ void op_index_counts(void* p, uint64_t* out) { auto& v = ((op_index*)p)->idx.cou
 void op_index_seq_starts(void* p, uint64_t* out) { auto& v = ((op_index*)p)->idx.starts; memcpy(out, v.data(), v.size() * 8); }
 // text as one code (0..3) per byte
 void op_index_text_codes(void* p, uint8_t* out) { auto& v = ((op_index*)p)->idx.text; memcpy(out, v.data(), v.size()); }
+void op_index_search_k(void* p, const uint64_t* mers, uint64_t q, unsigned kk, uint64_t* index_out, uint64_t* nb_out) {
+  op_index* oi = (op_index*)p;
+  for(uint64_t i = 0; i < q; ++i) oi->idx.search_k(mers[i], kk, index_out[i], nb_out[i]);
+}
 void op_index_search(void* p, const uint64_t* mers, uint64_t q, uint64_t* index_out, uint64_t* nb_out) {
   const sr_index& idx = ((op_index*)p)->idx;
   for(uint64_t i = 0; i < q; ++i) idx.search(mers[i], index_out[i], nb_out[i]);
@@ -189,6 +193,10 @@ int op_sr_overlap(const char* a, const char* b) { return sr_overlap(parse_sr_nam
 // (jf_aligner.cc:161-233, compact format, no header).  `unitigs_is_fasta` selects -u vs -l.
 // Returns the number of read bases processed (< 0 on error); *align_seconds gets the time of the
 // per-read phase only (the reference's "create mega reads" timer).
+// --fine-mer for the next op_run calls (0 = no fine pass); kept out of op_run's long argument list
+static unsigned g_fine_mer = 0;
+void op_set_fine_mer(unsigned k) { g_fine_mer = k; }
+
 int64_t op_run(int mode, const char* sr_fasta, const char* reads_path, const char* unitigs_path, int unitigs_is_fasta,
                const char* out_path, unsigned mer, unsigned psa_min, unsigned threads, uint64_t max_reads,
                double stretch_factor, double stretch_constant, double stretch_cap, int forward, int max_match,
@@ -200,7 +208,8 @@ int64_t op_run(int mode, const char* sr_fasta, const char* reads_path, const cha
     const auto t0 = std::chrono::steady_clock::now();
     oi.idx.append_fasta(sr_fasta);
     std::cerr << "compute_psa " << oi.idx.srs.size() << ' ' << oi.idx.n() << '\n';
-    oi.idx.build(psa_min, mer);
+    // create_mega_reads.cc:131-132: the suffix array keeps suffixes down to min(fine mer, psa-min) bases
+    oi.idx.build(g_fine_mer ? std::min(g_fine_mer, psa_min) : psa_min, mer);
     const auto t1 = std::chrono::steady_clock::now();
     if(unitigs_path && *unitigs_path) {
       std::ifstream is(unitigs_path);
@@ -236,7 +245,7 @@ int64_t op_run(int mode, const char* sr_fasta, const char* reads_path, const cha
     auto worker = [&]() {
       std::vector<read_rec> job(100);
       std::string out;
-      std::vector<mer_lists> groups; std::vector<coords> cs;
+      std::vector<mer_lists> groups; std::vector<coords> cs, fine;
       while(true) {
         size_t filled = 0;
         {
@@ -247,6 +256,10 @@ int64_t op_run(int mode, const char* sr_fasta, const char* reads_path, const cha
         for(size_t i = 0; i < filled; ++i) {
           try {
             align_read(oi.idx, job[i].seq, p, p.unitigs_k ? &oi.unitigs_lengths : nullptr, groups, cs);
+            if(g_fine_mer) {                                    // create_mega_reads.cc:64-68, jf_aligner.cc:144-148
+              fine_align_read(oi.idx, job[i].seq, p, g_fine_mer, p.unitigs_k ? &oi.unitigs_lengths : nullptr, cs, fine);
+              cs.swap(fine);
+            }
             if(mode == 0)
               mega_reads_for_read(oi.idx, cs, job[i].name, job[i].seq.size(), p, oi.unitigs_lengths,
                                   oi.unitigs_sequences.empty() ? nullptr : &oi.unitigs_sequences, out);

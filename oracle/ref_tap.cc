@@ -12,6 +12,8 @@
 #include <src_jf_aligner/superread_parser.hpp>
 #include <src_jf_aligner/coarse_aligner.hpp>
 #include <src_lis/lis_align.hpp>
+#include <src_jf_aligner/jf_aligner.hpp>
+#include <src_jf_aligner/fine_aligner.hpp>
 #include <sstream>
 
 using align_pb::coarse_aligner;
@@ -92,6 +94,21 @@ void ref_index_search(void* p, const uint64_t* mers, uint64_t q, uint64_t* index
   }
 }
 
+// the same search with a pattern of kk bases, as the fine pass issues it (fine_aligner.cc:13-15 ->
+// superread_parser.hpp:183-192): mer type short_mer_type, Psize = kk
+void ref_index_search_k(void* p, const uint64_t* mers, uint64_t q, unsigned int kk, uint64_t* index_out, uint64_t* nb_out) {
+  ref_index* r = (ref_index*)p;
+  short_mer_type::k(kk);
+  for(uint64_t i = 0; i < q; ++i) {
+    short_mer_type m;
+    for(unsigned int j = 0; j < kk; ++j)
+      m.shift_left((int)((mers[i] >> (2 * (kk - 1 - j))) & 3));
+    auto res = r->psa.m_sa->search(mer_dna_ptr<short_mer_type>(m), kk);
+    nb_out[i]    = res.first;
+    index_out[i] = res.first ? res.second : 0;
+  }
+}
+
 // chaining on (pb, sr) int pairs; returns chain length, indices into out (size >= n)
 uint32_t ref_lis(const int32_t* pairs, uint32_t n, double a, double b, double C, uint32_t window, uint32_t* out) {
   std::vector<std::pair<int,int> > X(n);
@@ -127,6 +144,26 @@ void* ref_aligner_create(void* p, double stretch_factor, double stretch_constant
   return a;
 }
 void ref_aligner_destroy(void* p) { delete (ref_aligner*)p; }
+
+// diagnostic: run the fine pass on the read last given to ref_align_read and print, for every window
+// of super-read `sr`, its bounds and first hits (fine_aligner.hpp:49-58, fine_aligner.cc:7-36)
+void ref_fine_dump(void* p, const char* seq, uint64_t len, unsigned int fine_k, int64_t sr) {
+  ref_aligner* a = (ref_aligner*)p;
+  const std::string s(seq, len);
+  short_mer_type::k(fine_k);
+  align_pb::fine_aligner fa(a->idx->psa, fine_k, a->aligner->unitigs_lengths_, a->aligner->unitigs_k_);
+  align_pb::fine_aligner::thread th(fa);
+  short_parse_sequence parser(s);
+  th.align_sequence(parser, s.size(), a->th->coords());
+  const frag_lists::frag_info* base = a->idx->psa.m_headers.data();
+  for(const auto& it : th.frags_pos_)
+    for(const auto& w : it.second) {
+      if(w.ml.frag - base != sr) continue;
+      std::cerr << "ref window sr " << sr << " begin " << w.begin << " end " << w.end << " fwd " << w.ml.fwd.offsets.size() << " bwd " << w.ml.bwd.offsets.size() << " first bwd:";
+      for(size_t i = 0; i < w.ml.bwd.offsets.size() && i < 6; ++i) std::cerr << ' ' << w.ml.bwd.offsets[i].first << ':' << w.ml.bwd.offsets[i].second;
+      std::cerr << " lis bwd " << w.ml.bwd.lis.size() << std::endl;
+    }
+}
 
 // align one read; groups are emitted sorted by super-read index
 int ref_align_read(void* p, const char* seq, uint64_t len) {

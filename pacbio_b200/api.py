@@ -33,7 +33,7 @@ class Params(C.Structure):
                 ("window_size", C.c_uint32), ("forward", C.c_int32), ("max_match", C.c_int32),
                 ("max_count", C.c_int32), ("matching_mers", C.c_double), ("matching_bases", C.c_double),
                 ("unitigs_k", C.c_uint32), ("overlap_play", C.c_double), ("errors", C.c_double),
-                ("bases", C.c_int32), ("run_graph", C.c_int32)]
+                ("bases", C.c_int32), ("run_graph", C.c_int32), ("fine_mer", C.c_uint32)]
 
 
 class ResultView(C.Structure):

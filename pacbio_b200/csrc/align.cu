@@ -116,7 +116,7 @@ struct tile_kmers {
 // Loads the tile's bases (plus look-back / look-ahead) into shared memory as codes and enumerates
 // the 4 consecutive k-mers owned by this thread.  codes[] needs kTile + 64 bytes.
 __device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
-                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t) {
+                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t, bool every_mer = false) {
   const int cap = k > 18 ? (int)k : 18;        // run length is only needed up to max(k, 18)
   const int LB  = cap - (int)k;
   const int total = LB + kTile + (int)k - 1;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, u
   }
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
-    const bool ok = run >= (int)k && !is_ssr(m, k);
+    const bool ok = run >= (int)k && (every_mer || !is_ssr(m, k));    // the fine pass takes every mer (jf_aligner.hpp:113-123)
     t.m[j] = m; t.rm[j] = rm;
     t.valid[j] = ok;
     t.cand[j]  = ok && run <= 17;
@@ -417,6 +417,148 @@ __global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, con
     __syncthreads();
   }
   if(n_bad) atomicAdd(n_invalid, (unsigned long long)n_bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fine pass (-F, fine_aligner.hpp:49-58 + fine_aligner.cc:7-51): every coarse row opens a window on
+// its read; all hits of the shorter mer that land on the row's super-read inside the window are
+// chained with accept-all predicates and give the row's new coords.
+// ------------------------------------------------------------------------------------------------
+// windows (prime_frags_pos) + the (read, super-read) -> row table, unsorted
+__global__ void __launch_bounds__(256) fine_windows_kernel(uint64_t S, survivors sv, const uint64_t* __restrict__ read_start, uint32_t kk,
+                                                            uint64_t* __restrict__ wkey, uint32_t* __restrict__ wrow,
+                                                            double* __restrict__ wbegin, double* __restrict__ wend,
+                                                            uint32_t* __restrict__ gread, uint32_t* __restrict__ gsr, uint32_t* __restrict__ giter) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= S) return;
+  const uint32_t read = sv.read[i], sr = sv.sr[i];
+  const double stretch = sv.stretch[i], offset = sv.offset[i], err = sv.avg_err[i];
+  const double rl = (double)(read_start[read + 1] - read_start[read]);
+  const double s1 = stretch + offset;
+  wbegin[i] = fmax(0.0, s1 - err);
+  const double t = stretch * (double)sv.ql[i];
+  const double e1 = t + offset;
+  const double e2 = e1 + err;
+  wend[i] = fmin(rl, e2 - (double)kk);
+  wkey[i] = ((uint64_t)read << 32) | sr;
+  wrow[i] = (uint32_t)i;
+  gread[i] = read; gsr[i] = sr; giter[i] = sv.iter[i];
+}
+
+// lookups of every kk-mer of the reads: rec = {index(m), nb(m), index(rm), nb(rm)}, size = nb(m) + nb(rm)
+__global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, uint32_t kk, const char* __restrict__ bases,
+                                                                  const uint64_t* __restrict__ read_start,
+                                                                  const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                                  const uint64_t* __restrict__ table_off,
+                                                                  uint4* __restrict__ rec, uint32_t* __restrict__ size) {
+  __shared__ uint8_t codes[kTile + 64];
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  const uint32_t tpos = tile_pos[blockIdx.x];
+  const bool has_rows = table_off[r + 1] != table_off[r];        // a read without coarse rows has no window
+  tile_kmers t;
+  enumerate_tile(bases, rs, rlen, tpos, kk, codes, t, true);
+  const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
+#pragma unroll
+  for(int j = 0; j < 4; ++j) {
+    const uint32_t pos = tpos + threadIdx.x * 4 + j;
+    if(pos >= rlen) continue;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if(has_rows && t.valid[j]) {
+      index_lookup_prefix(iv, t.m[j], kk, out.x, out.y);
+      index_lookup_prefix(iv, t.rm[j], kk, out.z, out.w);
+    }
+    __stcs(rec + g0 + j, out);
+    __stcs(size + g0 + j, out.y + out.w);
+  }
+}
+
+// EMIT = false: counts, per tile and per row, the hits that fall into a window; EMIT = true: writes
+// them (key = row, payload = pb offset | signed super-read offset << 32) in emission order
+// (read position, forward range before reverse range, suffix-array order).
+template<bool EMIT>
+__global__ void __launch_bounds__(kSeedThreads) fine_expand_kernel(index_view iv, uint32_t kk, const uint64_t* __restrict__ read_start,
+                                                                    const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
+                                                                    const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
+                                                                    const uint64_t* __restrict__ table_off, const uint64_t* __restrict__ tkey,
+                                                                    const uint32_t* __restrict__ trow,
+                                                                    const double* __restrict__ wbegin, const double* __restrict__ wend,
+                                                                    uint32_t* __restrict__ tile_cnt, const uint64_t* __restrict__ tile_off,
+                                                                    uint32_t* __restrict__ row_cnt,
+                                                                    uint64_t* __restrict__ keys, uint64_t* __restrict__ pays) {
+  __shared__ uint64_t sw[8];
+  __shared__ uint32_t s_off[kSeedThreads];
+  __shared__ uint4    s_rec[kSeedThreads];
+  const uint32_t r = tile_read[blockIdx.x];
+  const uint64_t t0 = table_off[r], t1 = table_off[r + 1];
+  if(t0 == t1) { if(!EMIT && threadIdx.x == 0) tile_cnt[blockIdx.x] = 0; return; }
+  if(EMIT && tile_off[blockIdx.x + 1] == tile_off[blockIdx.x]) return;
+  const uint64_t rs = read_start[r];
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
+  const uint32_t tpos = tile_pos[blockIdx.x];
+  uint64_t run = EMIT ? tile_off[blockIdx.x] : 0;
+  for(int it = 0; it < kTile / kSeedThreads; ++it) {
+    const uint32_t pos = tpos + it * kSeedThreads + threadIdx.x;
+    uint32_t sz = 0;
+    uint4 rc = make_uint4(0, 0, 0, 0);
+    if(pos < rlen) {
+      sz = __ldcs(size + rs + pos);
+      if(sz) rc = __ldcs(rec + rs + pos);
+    }
+    uint64_t raw_total;
+    s_off[threadIdx.x] = (uint32_t)prim::block_exclusive_scan_256(sz, sw, raw_total);
+    s_rec[threadIdx.x] = rc;
+    __syncthreads();
+    for(uint32_t base = 0; base < (uint32_t)raw_total; base += kSeedThreads) {
+      const uint32_t h = base + threadIdx.x;
+      uint32_t nmatch = 0, first = 0, sr = 0, off = 0, pb_off = 0;
+      bool minus = false;
+      if(h < (uint32_t)raw_total) {
+        uint32_t lo = 0, hi = kSeedThreads;
+        while(hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if(s_off[mid] <= h) lo = mid; else hi = mid; }
+        const uint4 c = s_rec[lo];
+        const uint32_t j = h - s_off[lo];
+        minus = j >= c.y;
+        pb_off = tpos + it * kSeedThreads + lo + 1;
+        const uint32_t x = __ldg(iv.sa + (minus ? c.z + (j - c.y) : c.x + j));
+        if(index_locate_k(iv, x, kk, sr, off)) {
+          // rows of (read, sr) in the table: equal keys are contiguous
+          const uint64_t want = ((uint64_t)r << 32) | sr;
+          uint64_t a = t0, b = t1;
+          while(a < b) { const uint64_t mid = (a + b) >> 1; if(tkey[mid] < want) a = mid + 1; else b = mid; }
+          first = (uint32_t)a;
+          for(uint64_t q = a; q < t1 && tkey[q] == want; ++q) {
+            const uint32_t row = trow[q];
+            const double p = (double)pb_off;
+            if(p >= wbegin[row] && p <= wend[row]) {
+              ++nmatch;
+              if(!EMIT) atomicAdd(row_cnt + row, 1u);
+            }
+          }
+        }
+      }
+      uint64_t chunk_total;
+      const uint64_t mine = prim::block_exclusive_scan_256(nmatch, sw, chunk_total);
+      if(EMIT && nmatch) {
+        const uint64_t want = ((uint64_t)r << 32) | sr;
+        const int32_t soff = minus ? -(int32_t)off : (int32_t)off;
+        uint64_t slot = run + mine;
+        for(uint64_t q = first; q < t1 && tkey[q] == want; ++q) {
+          const uint32_t row = trow[q];
+          const double p = (double)pb_off;
+          if(p >= wbegin[row] && p <= wend[row]) {
+            keys[slot] = row;
+            pays[slot] = (uint64_t)pb_off | ((uint64_t)(uint32_t)soff << 32);
+            ++slot;
+          }
+        }
+      }
+      run += chunk_total;
+    }
+    __syncthreads();
+  }
+  if(!EMIT && threadIdx.x == 0) tile_cnt[blockIdx.x] = (uint32_t)run;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -814,6 +956,99 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
   }
   if(S >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: more than 2^32 coords rows");
+  uint32_t k_coords = k;                                 // mer length of the rows that go on (kmers_info)
+
+  // ---- fine pass (-F): the coarse rows become windows, their coords are recomputed from shorter mers -----
+  if(p->fine_mer && S) {
+    timer.next("fine pass");
+    const uint32_t kk = p->fine_mer;
+    fine_buffers& fb = ws.fine;
+    MR_TRY(fb.wkey0.ensure(ctx, S * 8)); MR_TRY(fb.wkey1.ensure(ctx, S * 8)); MR_TRY(fb.wrow0.ensure(ctx, S * 4)); MR_TRY(fb.wrow1.ensure(ctx, S * 4));
+    MR_TRY(fb.wbegin.ensure(ctx, S * 8)); MR_TRY(fb.wend.ensure(ctx, S * 8));
+    MR_TRY(fb.gread.ensure(ctx, S * 4)); MR_TRY(fb.gsr.ensure(ctx, S * 4)); MR_TRY(fb.giter.ensure(ctx, S * 4));
+    MR_TRY(fb.table_off.ensure(ctx, ((size_t)nreads + 2) * 8));
+    MR_TRY(fb.row_cnt.ensure(ctx, (S + 2) * 4)); MR_TRY(fb.group_start.ensure(ctx, (S + 2) * 8));
+    // rows of read r in the (read, super-read)-sorted table: [table_off[r], table_off[r + 1])
+    MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.read_cnt.as<uint32_t>() }, (uint64_t)nreads + 1,
+                                                             fb.table_off.as<uint64_t>(), ws.scan_scratch, nullptr)));
+    fine_windows_kernel<<<div_up(S, 256), 256, 0, st>>>(S, A.sv, d_read_start, kk, fb.wkey0.as<uint64_t>(), fb.wrow0.as<uint32_t>(),
+                                                        fb.wbegin.as<double>(), fb.wend.as<double>(), fb.gread.as<uint32_t>(),
+                                                        fb.gsr.as<uint32_t>(), fb.giter.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    int sr_bits = 1, read_bits = 1;
+    while((1ULL << sr_bits) <= (uint64_t)iv.nseq) ++sr_bits;
+    while((1ULL << read_bits) <= (uint64_t)nreads) ++read_bits;
+    bool first = true;
+    MR_TRY((prim::radix_sort_pairs<uint64_t, uint32_t>(ctx, fb.wkey0.as<uint64_t>(), fb.wrow0.as<uint32_t>(), fb.wkey1.as<uint64_t>(),
+                                                       fb.wrow1.as<uint32_t>(), S, 0, sr_bits, fb.sort, &first)));
+    uint64_t *wk_a = first ? fb.wkey0.as<uint64_t>() : fb.wkey1.as<uint64_t>(), *wk_b = first ? fb.wkey1.as<uint64_t>() : fb.wkey0.as<uint64_t>();
+    uint32_t *wr_a = first ? fb.wrow0.as<uint32_t>() : fb.wrow1.as<uint32_t>(), *wr_b = first ? fb.wrow1.as<uint32_t>() : fb.wrow0.as<uint32_t>();
+    MR_TRY((prim::radix_sort_pairs<uint64_t, uint32_t>(ctx, wk_a, wr_a, wk_b, wr_b, S, 32, 32 + read_bits, fb.sort, &first)));
+    const uint64_t* tkey = first ? wk_a : wk_b;
+    const uint32_t* trow = first ? wr_a : wr_b;
+    if(ntiles) {
+      fine_seed_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                        fb.table_off.as<uint64_t>(), ws.rec.as<uint4>(), ws.size.as<uint32_t>());
+      MR_LAUNCHED(ctx);
+    }
+    MR_CUDA(ctx, cudaMemsetAsync(fb.row_cnt.p, 0, (S + 2) * 4, st));
+    fine_expand_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                             ws.rec.as<uint4>(), ws.size.as<uint32_t>(), fb.table_off.as<uint64_t>(), tkey, trow,
+                                                             fb.wbegin.as<double>(), fb.wend.as<double>(), ws.tile_cand.as<uint32_t>(), nullptr,
+                                                             fb.row_cnt.as<uint32_t>(), nullptr, nullptr);
+    MR_LAUNCHED(ctx);
+    MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
+                                                             ws.scan_scratch, (uint64_t*)(ctr + 7))));
+    MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 7, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(h_ctr + 7, ctr + 7, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t Hf = h_ctr[7];
+    MR_TRACE_MSG("fine pass: %llu windows, %llu hits inside them", (unsigned long long)S, (unsigned long long)Hf);
+    if(Hf >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many fine-pass hits in one batch; use smaller batches");
+    MR_TRY(ws.key0.ensure(ctx, (Hf + 2) * 8)); MR_TRY(ws.key1.ensure(ctx, (Hf + 2) * 8));
+    MR_TRY(ws.pay0.ensure(ctx, (Hf + 2) * 8)); MR_TRY(ws.pay1.ensure(ctx, (Hf + 2) * 8));
+    MR_TRY(ws.chainL.ensure(ctx, (Hf + 2) * 16));
+    if(Hf) {
+      fine_expand_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                              ws.rec.as<uint4>(), ws.size.as<uint32_t>(), fb.table_off.as<uint64_t>(), tkey, trow,
+                                                              fb.wbegin.as<double>(), fb.wend.as<double>(), nullptr, ws.hit_off.as<uint64_t>(),
+                                                              nullptr, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>());
+      MR_LAUNCHED(ctx);
+    }
+    int row_bits = 1;
+    while((1ULL << row_bits) < S) ++row_bits;
+    bool in_first = true;
+    MR_TRY((prim::radix_sort_pairs<uint64_t, uint64_t>(ctx, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ws.key1.as<uint64_t>(),
+                                                       ws.pay1.as<uint64_t>(), Hf, 0, row_bits, ws.sort, &in_first)));
+    MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ fb.row_cnt.as<uint32_t>() }, S + 1,
+                                                             fb.group_start.as<uint64_t>(), ws.scan_scratch, nullptr)));
+    chain_args F = A;
+    F.keys = in_first ? ws.key0.as<uint64_t>() : ws.key1.as<uint64_t>();
+    F.pays = in_first ? ws.pay0.as<uint64_t>() : ws.pay1.as<uint64_t>();
+    uint64_t* f_alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
+    uint64_t* f_alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
+    F.group_start = fb.group_start.as<uint64_t>(); F.ngroups = S;
+    {
+      char* cb = (char*)ws.chainL.p;
+      F.cb.Lpb = (int32_t*)cb; F.cb.Lsr = (int32_t*)(cb + (Hf + 2) * 4); F.cb.Llen = (uint32_t*)(cb + (Hf + 2) * 8);
+      F.cb.Lelt = (uint32_t*)(cb + (Hf + 2) * 12);
+      F.cb.pprev = (uint32_t*)f_alt_pay; F.cb.cstart = (uint32_t*)f_alt_pay + (Hf + 2);
+    }
+    F.chain_pay = f_alt_key;
+    F.a = -1.0; F.b = 0.0; F.C = -1.0;                    // lis_align::accept_all
+    F.matching_mers = 0.0; F.matching_bases = 0.0; F.forward = 1; F.no_filter = 1; F.align_k = kk;
+    F.group_read = fb.gread.as<uint32_t>(); F.group_sr = fb.gsr.as<uint32_t>(); F.group_iter = fb.giter.as<uint32_t>();
+    F.max_match = 0; F.removed = nullptr;
+    F.tap_lens = nullptr; F.tap_cf = nullptr; F.tap_cb = nullptr; F.tap_sub = nullptr;
+    MR_CUDA(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(uint64_t), st));
+    MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
+    MR_TRY(launch_chain(ctx, F, ws.group_lists));
+    MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    if(h_ctr[4] != S) return ctx->fail(MR_ECUDA, "mr_align_batch: internal error, the fine pass lost rows");
+    A = F;
+    k_coords = kk;
+  }
   const uint64_t info_total = S ? h_ctr[5] : 0;
 
   // ---- kmers_info, per-read order, final rows ---------------------------------------------------
@@ -833,7 +1068,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       I.n = S; I.chain_pos = A.sv.chain_pos; I.nb_mers = A.sv.nb_mers; I.sr = A.sv.sr; I.use_bwd = A.sv.use_bwd; I.ql = A.sv.ql;
       I.info_off = sv_info_off; I.info_len = A.sv.info_len; I.chain_pay = A.chain_pay;
       I.unitig_ids = idx->unitig_ids.as<uint32_t>(); I.unitig_off = idx->unitig_off.as<uint64_t>();
-      I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k; I.unitigs_k = p->unitigs_k;
+      I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k_coords; I.unitigs_k = p->unitigs_k;
       I.kinfo = ws.kinfo.as<int32_t>(); I.binfo = ws.binfo.as<int32_t>();
       kmers_info_kernel<<<div_up(S, 128), 128, 0, st>>>(I);
       MR_LAUNCHED(ctx);
@@ -920,6 +1155,10 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
   if(idx->ctx->device != ctx->device) return ctx->fail(MR_EINVAL, "mr_align_batch: index lives on another device");
   if(p->window_size != 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size other than 1 is not implemented");
   if(p->max_match && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with --max-match");
+  if(p->fine_mer && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with a fine pass");
+  if(p->fine_mer && (p->fine_mer < idx->m || p->fine_mer > idx->k))
+    return ctx->fail(MR_EINVAL, "mr_align_batch: the fine mer must lie between the psa_min and the mer length the index was built with "
+                                "(the reference builds its suffix array with min(fine mer, psa-min), create_mega_reads.cc:131-132)");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -20,10 +20,17 @@ struct coords_soa {
   uint64_t *chain_pos;     // start of the group's slice in the sorted hit arrays
 };
 
+// scratch of the fine pass
+struct fine_buffers {
+  dev_buf wkey0, wkey1, wrow0, wrow1, wbegin, wend, gread, gsr, giter, table_off, row_cnt, group_start;
+  prim::sort_scratch sort;
+};
+
 // Scratch that lives in the context and is reused from batch to batch.
 struct mr_workspace {
   dev_buf bases, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
   dev_buf size, rec, hit_off, thr, counters;
+  fine_buffers fine;
   dev_buf path_ids, path_off, path_ulen;               // mr_graph_batch: the caller's unitig paths
   dev_buf key0, key1, pay0, pay1, chainL, group_start;
   dev_buf sv_i32, sv_u32, sv_f64, sv_u64, sv_u8;        // survivors, unsorted
@@ -85,6 +92,10 @@ struct chain_args {
   uint32_t* group_nb; uint32_t* long_list; uint32_t* long_count; uint32_t* long_cursor;
   uint64_t* chain_pay;      // per group, at its slice: the chain's (pb, sr) pairs in chain order
   int max_match; uint8_t* removed;   // --max-match: hits already used by an emitted chain
+  // fine pass (fine_aligner.cc:38-51): groups are the windows of the coarse rows, possibly empty
+  uint32_t align_k;                  // mer length the coords are computed with (0: the index's k)
+  int no_filter;                     // every group yields a row
+  const uint32_t *group_read, *group_sr, *group_iter;   // identity of group g when not taken from keys[]
   uint32_t* dbg_cycles;              // MR_TRACE: SM cycles spent chaining each group
 };
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);

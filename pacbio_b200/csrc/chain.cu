@@ -28,13 +28,16 @@ namespace {
 
 constexpr uint32_t kThreadFinishLongMax = 1536;   // chains up to this many hits: one thread each; longer: one warp each
 
+// (C < 0 / a < 0: lis_align::accept_all, the predicates of the fine pass, fine_aligner.cc:43-46)
 __device__ __forceinline__ bool accept_mer(int32_t pb_i, int32_t sr_i, int32_t lpb, int32_t lsr, double a, double b, double C) {
+  if(C < 0.0) return true;
   const double d1 = (double)(pb_i - lpb), d2 = (double)(sr_i - lsr);
   const double t1 = a * d2, t2 = a * d1;                   // mul then add, never fused (-fmad=false)
   return d1 <= b + t1 && d2 <= b + t2 && d1 <= C && d2 <= C;
 }
 
 __device__ __forceinline__ bool accept_sequence(int32_t span_pb, int32_t span_sr, double a) {
+  if(a < 0.0) return true;
   const double s1 = a * (double)span_sr, s2 = a * (double)span_pb;
   return (double)span_pb <= s1 && (double)span_sr <= s2;
 }
@@ -332,11 +335,19 @@ struct coords_acc {
   }
 };
 
+// (read, super-read) of a group: the key of its first hit, or -- when groups are rows given by the
+// caller (fine pass: a group may be empty) -- the caller's per-group arrays
+__device__ __forceinline__ void group_identity(const chain_args& A, uint64_t g, uint64_t gs, uint32_t& read, uint32_t& sr) {
+  if(A.group_read) { read = A.group_read[g]; sr = A.group_sr[g]; return; }
+  const uint64_t key = A.keys[gs];
+  read = (uint32_t)(key >> 32); sr = (uint32_t)key;
+}
+
 // canonicalize + filters + survivor append; call from ONE thread per group
 __device__ __forceinline__ bool publish_coords(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
                                                uint32_t nb, const coords_acc& c, double stretch, double offset, double avg_err,
                                                uint32_t iter = 0) {
-  const uint32_t k = A.iv.k;
+  const uint32_t k = A.align_k ? A.align_k : A.iv.k;
   const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
   const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
   int32_t rs = c.first_pb, re = c.ppb + (int32_t)k - 1, qs = c.first_sr, qe = c.psr;
@@ -357,9 +368,9 @@ __device__ __forceinline__ bool publish_coords(const chain_args& A, uint64_t gs,
   } else {
     qe += (int32_t)k - 1;
   }
-  // filters of align_sequence_max (coarse_aligner.cc:51-54)
-  if(fabs(stretch) == 0.0) return false;
-  {
+  // filters of align_sequence_max (coarse_aligner.cc:51-54); the fine pass keeps every row (fine_aligner.cc:47-49)
+  if(!A.no_filter && fabs(stretch) == 0.0) return false;
+  if(!A.no_filter) {
     const double drl = (double)rl;
     const double is = fmax(1.0, fmin(drl, stretch + offset));
     const double tq = stretch * (double)ql;
@@ -402,7 +413,7 @@ template<bool WANT_RESULT>
 __device__ __forceinline__ bool finish_group_warp(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
                                                   uint32_t nb, uint32_t iter = 0) {
   const unsigned lane = threadIdx.x & 31;
-  const uint32_t k = A.iv.k;
+  const uint32_t k = A.align_k ? A.align_k : A.iv.k;
   const uint64_t* cp = A.chain_pay + gs;          // the chain's (pb, sr) pairs, in chain order
   coords_acc c(k);
   for(uint32_t t0 = 0; t0 < nb; t0 += 32) {
@@ -448,8 +459,8 @@ __device__ __forceinline__ bool finish_group_warp(const chain_args& A, uint64_t 
 // one THREAD per group: 32 independent recurrences per warp instruction.  The chain's pairs are read
 // four at a time, the next four already in flight while the current ones are folded in.
 __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, bool fwd_align,
-                                                    uint32_t nb) {
-  const uint32_t k = A.iv.k;
+                                                    uint32_t nb, uint32_t iter = 0) {
+  const uint32_t k = A.align_k ? A.align_k : A.iv.k;
   const uint64_t* cp = A.chain_pay + gs;
   coords_acc c(k);
   uint64_t q[4];
@@ -478,7 +489,25 @@ __device__ __forceinline__ void finish_group_thread(const chain_args& A, uint64_
     }
     avg_err = e / (double)c.n;
   }
-  publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err);
+  publish_coords(A, gs, read, sr, fwd_align, nb, c, stretch, offset, avg_err, iter);
+}
+
+// a window of the fine pass without any hit: compute_coords_info returns right after the constructor
+// (pb_aligner.cc:25-28).  The reference leaves rs, re, qs, qe uninitialised there; they are 0 here.
+__device__ __forceinline__ void publish_empty(const chain_args& A, uint64_t gs, uint32_t read, uint32_t sr, uint32_t iter) {
+  const uint32_t k = A.align_k ? A.align_k : A.iv.k;
+  const survivors& sv = A.sv;
+  const unsigned long long slot = atomicAdd(sv.count, 1ULL);
+  if(slot < sv.cap) {
+    sv.rs[slot] = 0; sv.re[slot] = 0; sv.qs[slot] = 0; sv.qe[slot] = 0; sv.nb_mers[slot] = 0;
+    sv.pb_cons[slot] = 0; sv.sr_cons[slot] = 0; sv.pb_cover[slot] = k; sv.sr_cover[slot] = k;
+    sv.ql[slot] = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr]; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = 0;
+    sv.rn[slot] = 0; sv.use_bwd[slot] = 0;
+    sv.stretch[slot] = 0; sv.offset[slot] = 0; sv.avg_err[slot] = 0;
+    sv.chain_pos[slot] = gs;
+    sv.iter[slot] = iter;
+    atomicAdd(sv.read_cnt + read, 1u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,7 +538,10 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
     cls = kSmemTiers;
 #pragma unroll
     for(int c = kSmemTiers - 1; c >= 0; --c) if(n <= kTierCap[c]) cls = c;
-    if(n == 1 && singles_here) {
+    if(n == 0) {                                 // a fine-pass window without hits: no chain, a default row
+      cls = -1;
+      group_nb[g] = 0x80000000u;
+    } else if(n == 1 && singles_here) {
       cls = -1;
       const uint64_t p = pays[gs];
       chain_pay[gs] = p;
@@ -685,8 +717,11 @@ __global__ void __launch_bounds__(128) finish_small_groups_kernel(chain_args A, 
   const uint64_t gs = A.group_start[g];
   if(A.group_start[g + 1] - gs > max_group) return;
   const uint32_t v = A.group_nb[g];
-  const uint64_t key = A.keys[gs];
-  finish_group_thread(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
+  uint32_t read, sr;
+  group_identity(A, g, gs, read, sr);
+  const uint32_t iter = A.group_iter ? A.group_iter[g] : 0;
+  if((v & 0x7fffffffu) == 0) { publish_empty(A, gs, read, sr, iter); return; }
+  finish_group_thread(A, gs, read, sr, (v >> 31) != 0, v & 0x7fffffffu, iter);
 }
 // (2) the groups of one size class, right behind the kernel that chained them (chains longer than
 // hi went to the long list).  A warp takes 32 chains, one per lane; each chain is a private stream
@@ -699,14 +734,14 @@ __global__ void __launch_bounds__(128) finish_tile_kernel(chain_args A, const ui
   __shared__ uint64_t tile[4][2][32][kTileE + 1];      // + 1: lane j reads row j, 17 x 8 B apart -> no bank conflicts
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t total = *list_count;
-  const uint32_t k = A.iv.k;
+  const uint32_t k = A.align_k ? A.align_k : A.iv.k;
   const uint32_t stride = gridDim.x * 4 * 32;
   for(uint32_t i0 = (blockIdx.x * 4 + wib) * 32; i0 < total; i0 += stride) {
     const uint32_t i = i0 + lane;
-    uint32_t v = 0, nb = 0;
+    uint32_t v = 0, nb = 0, g = 0;
     uint64_t gs = 0;
     if(i < total) {
-      const uint32_t g = list[i];
+      g = list[i];
       v = A.group_nb[g]; nb = v & 0x7fffffffu;
       if(nb > hi) nb = 0;
       gs = A.group_start[g];
@@ -765,8 +800,9 @@ __global__ void __launch_bounds__(128) finish_tile_kernel(chain_args A, const ui
       if(fit) avg_err = err / (double)c.n;
     }
     if(nb != 0) {
-      const uint64_t key = A.keys[gs];
-      publish_coords(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, nb, c, stretch, offset, avg_err);
+      uint32_t read, sr;
+      group_identity(A, g, gs, read, sr);
+      publish_coords(A, gs, read, sr, (v >> 31) != 0, nb, c, stretch, offset, avg_err, A.group_iter ? A.group_iter[g] : 0);
     }
   }
 }
@@ -783,8 +819,9 @@ __global__ void __launch_bounds__(128) finish_warp_kernel(chain_args A) {
     const uint32_t g = A.long_list[w];
     const uint32_t v = A.group_nb[g];
     const uint64_t gs = A.group_start[g];
-    const uint64_t key = A.keys[gs];
-    finish_group_warp<false>(A, gs, (uint32_t)(key >> 32), (uint32_t)key, (v >> 31) != 0, v & 0x7fffffffu);
+    uint32_t read, sr;
+    group_identity(A, g, gs, read, sr);
+    finish_group_warp<false>(A, gs, read, sr, (v >> 31) != 0, v & 0x7fffffffu, A.group_iter ? A.group_iter[g] : 0);
   }
 }
 

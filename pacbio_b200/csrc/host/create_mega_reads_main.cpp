@@ -13,7 +13,7 @@ static const char* usage_text =
   "Align PacBio reads and SuperReads, and create mega reads\n\n"
   " -s, --size=uint64            Number of k-mers in SuperReads (required, unused)\n"
   " -m, --mer=uint32             Mer size (required)\n"
-  " -F, --fine-mer=uint32        Mer size for fine alignment (not implemented)\n"
+  " -F, --fine-mer=uint32        Mer size for fine alignment\n"
   "     --psa-min=uint32         Min suffix length in SA (13)\n"
   " -l, --unitigs-lengths=path   Length of k-unitigs\n"
   " -u, --unitigs-sequences=path Fasta file containing the sequence of the k-unitigs\n"
@@ -67,7 +67,7 @@ int main(int argc, char* argv[]) {
     case 'V': puts("b200-mega-reads 0.1"); return 0;
     case 's': size_given = true; (void)to_uint64(optarg, "-s, --size=uint64", true); break;
     case 'm': mer_given = true; mer = to_uint32(optarg, "-m, --mer=uint32"); break;
-    case 'F': error("[-F, --fine-mer] the fine alignment pass is not implemented in this build");
+    case 'F': P.fine_mer = to_uint32(optarg, "-F, --fine-mer=uint32"); break;
     case O_PSA_MIN: psa_min = to_uint32(optarg, "--psa-min=uint32"); break;
     case 'l': l_given = true; unitigs_lengths = optarg; break;
     case 'u': u_given = true; unitigs_sequences = optarg; break;
@@ -129,7 +129,8 @@ int main(int argc, char* argv[]) {
     if(SR.nseq() == 0) throw std::runtime_error("no super-read sequence");
     std::cerr << "compute_psa " << SR.nseq() << ' ' << SR.n << '\n';
     mrh::device_set DS;
-    mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(22u, psa_min), mer);
+    // the suffix array keeps suffixes down to min(fine mer, psa-min) bases (create_mega_reads.cc:131-132, jf_aligner.cc:202-203)
+    mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(P.fine_mer ? P.fine_mer : 22u, psa_min), mer);
     mrh::add_streams(DS, mrh::streams_per_device());
     const auto t1 = std::chrono::steady_clock::now();
     if(show_timing) std::cerr << "Starting Super read parse ... " << std::chrono::duration<double>(t1 - t0).count() << '\n';

@@ -9,7 +9,7 @@
 static const char* usage_text =
   "Usage: jf_aligner [options]\n"
   "Align PacBio reads and SuperReads\n\n"
-  " -s, --size=uint64  -m, --mer=uint32 (required)  -F, --fine-mer (not implemented)  --psa-min=uint32 (13)\n"
+  " -s, --size=uint64  -m, --mer=uint32 (required)  -F, --fine-mer=uint32  --psa-min=uint32 (13)\n"
   " -t, --threads=uint32 (1)  --stretch-constant=int (10)  --stretch-factor=double (1.3)  --stretch-cap=double (10000.0)\n"
   "     --window-size=uint32 (1)  -f, --forward  -B, --bases-matching=double (17.0)  -M, --mers-matching=double (0.0)\n"
   "     --details=path  --coords=path (stdout)  --max-match\n"
@@ -48,7 +48,7 @@ int main(int argc, char* argv[]) {
     case 'V': puts("b200-mega-reads 0.1"); return 0;
     case 's': size_given = true; (void)to_uint64(optarg, "-s, --size=uint64", true); break;
     case 'm': mer_given = true; mer = to_uint32(optarg, "-m, --mer=uint32"); break;
-    case 'F': error("[-F, --fine-mer] the fine alignment pass is not implemented in this build");
+    case 'F': P.fine_mer = to_uint32(optarg, "-F, --fine-mer=uint32"); break;
     case O_PSA_MIN: psa_min = to_uint32(optarg, "--psa-min=uint32"); break;
     case 't': (void)to_uint32(optarg, "-t, --threads=uint32"); break;
     case O_SC: P.stretch_constant = (double)to_int(optarg, "--stretch-constant=int"); break;
@@ -78,6 +78,7 @@ int main(int argc, char* argv[]) {
   if(argc - optind != 0) error("Requires exactly 0 argument.");
   if(!details_given && !coords_given) error("No output file given. Doing nothing ungracefully.");
   if(details_given && P.max_match) error("[--details] is not available together with --max-match in this build");
+  if(details_given && P.fine_mer) error("[--details] is not available together with -F in this build");
   if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
   if((l_given || u_given) && !k_given)
     error("The mer length used for generating the k-unitigs (-k, --k-mer) is required if the unitig lengths (-l, --unitig-lengths or -u, --unitigs-sequences) is passed.");
@@ -98,7 +99,8 @@ int main(int argc, char* argv[]) {
     if(SR.nseq() == 0) throw std::runtime_error("no super-read sequence");
     std::cerr << "compute_psa " << SR.nseq() << ' ' << SR.n << '\n';
     mrh::device_set DS;
-    mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(22u, psa_min), mer);
+    // the suffix array keeps suffixes down to min(fine mer, psa-min) bases (create_mega_reads.cc:131-132, jf_aligner.cc:202-203)
+    mrh::build_indexes(DS, mrh::choose_devices(), SR, U, std::min<uint32_t>(P.fine_mer ? P.fine_mer : 22u, psa_min), mer);
     mrh::add_streams(DS, mrh::streams_per_device());
     P.matching_mers = mers_matching / 100.0;
     P.matching_bases = bases_matching / 100.0;

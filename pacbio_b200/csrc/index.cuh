@@ -136,6 +136,60 @@ __device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer,
   index = nb ? lo : 0;
 }
 
+// The same for a pattern of kk <= k bases (the fine pass looks shorter mers up in the same suffix
+// array; mer_sa_imp.hpp:376-381 when kk <= psa-min, :382-479 otherwise): the entries whose text
+// STARTS with the pattern.  They are the padded k-mers in [mer << s, ((mer + 1) << s) - 1],
+// s = 2 (k - kk); suffixes with fewer than kk bases left carry the smallest key of that range
+// (their missing bases are padded with A) and never match.
+__device__ __forceinline__ void index_lookup_prefix(const index_view& iv, uint64_t mer, uint32_t kk, uint32_t& index, uint32_t& nb) {
+  const uint32_t s = 2 * (iv.k - kk);
+  uint32_t lo, hi;
+  if(kk <= iv.mi) {
+    const uint32_t sh = 2 * (iv.mi - kk);
+    lo = __ldg(iv.counts + (uint32_t)(mer << sh));
+    hi = __ldg(iv.counts + (uint32_t)((mer + 1) << sh));
+  } else {
+    const uint32_t rb = 2 * (kk - iv.mi);                       // pattern bits below the table prefix
+    const uint32_t pre = (uint32_t)(mer >> rb);
+    const uint32_t t_lo = (uint32_t)((mer & ((1ULL << rb) - 1)) << s);
+    const uint32_t t_hi = t_lo | (s ? ((1u << s) - 1) : 0u);
+    uint32_t c0, c1;
+    load_count_pair(iv.counts, pre, c0, c1);
+    lo = hi = c0;
+    if(c0 != c1) {
+      if(c1 - c0 <= 64) {
+        const uint32_t w0 = tail_word(iv, tail_word_of(iv, c0));
+        uint32_t less, leq, dummy;
+        bucket_count(iv, c0, c1, t_lo, w0, less, dummy);
+        bucket_count(iv, c0, c1, t_hi, w0, dummy, leq);
+        lo = c0 + less; hi = c0 + leq;
+      } else {
+        uint32_t a = c0, b = c1;
+        while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) < t_lo) a = mid + 1; else b = mid; }
+        lo = a; b = c1;
+        while(a < b) { const uint32_t mid = a + ((b - a) >> 1); if(load_tail(iv, mid) <= t_hi) a = mid + 1; else b = mid; }
+        hi = a;
+      }
+    }
+  }
+  if(hi != lo) {
+    for(uint32_t j = 0; j < iv.nshort; ++j)                     // short_key[j]: the suffix with k - 1 - j bases
+      lo += (iv.k - 1 - j < kk) && (iv.short_key[j] >> s) == mer;
+  }
+  nb = hi - lo;
+  index = nb ? lo : 0;
+}
+
+// SA entry x -> (super-read, 1-based offset) for a mer of kk bases; false when it crosses into the next sequence
+__device__ __forceinline__ bool index_locate_k(const index_view& iv, uint32_t x, uint32_t kk, uint32_t& sr, uint32_t& off) {
+  uint32_t i = __ldg(iv.blk + (x >> kBlkShift));
+  while(__ldg(iv.sr_start + i + 1) <= x) ++i;
+  if((uint64_t)x + kk > __ldg(iv.sr_start + i + 1)) return false;
+  sr  = i;
+  off = x - __ldg(iv.sr_start + i) + 1;
+  return true;
+}
+
 // SA entry x -> (super-read, 1-based offset); false when x + k crosses into the next sequence
 // (pos_iterator::operator++, superread_parser.hpp:110-134)
 __device__ __forceinline__ bool index_locate(const index_view& iv, uint32_t x, uint32_t& sr, uint32_t& off) {

@@ -75,9 +75,32 @@ def longest_path_goldens():
             print(name, "longest path goldens written")
 
 
+# -F (fine pass): which fine mers are pinned for which fixture, and whether the jf_aligner coords are kept too
+FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}
+
+
+def fine_goldens():
+    """synth_*.fine<F>.{cmr,coords}.txt: the reference's create_mega_reads / jf_aligner with -F."""
+    for name, cfg in CONFIGS.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            info = gen_synth(os.path.join(tmp, name), **cfg["gen"])
+            common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+                      "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"]]
+            for fine, with_coords in FINE[name]:
+                cmr = os.path.join(HERE, "%s.fine%d.cmr.txt" % (name, fine))
+                subprocess.check_call([REF_CMR] + common + ["-F", str(fine), "-t", "1", "-o", cmr], stderr=subprocess.DEVNULL)
+                if with_coords:
+                    subprocess.check_call([REF_JFA] + common + ["-F", str(fine), "-t", "1", "-H", "--coords",
+                                                                os.path.join(HERE, "%s.fine%d.coords.txt" % (name, fine))],
+                                          stderr=subprocess.DEVNULL)
+            print(name, "fine pass goldens written")
+
+
 def main():
     if "--only-longest-path" in sys.argv:
         return longest_path_goldens()
+    if "--only-fine" in sys.argv:
+        return fine_goldens()
     ref = Ref()
     for name, cfg in CONFIGS.items():
         with tempfile.TemporaryDirectory() as tmp:
@@ -126,5 +149,6 @@ def main():
 
 if __name__ == "__main__":
     main()
-    if "--only-longest-path" not in sys.argv:
+    if "--only-longest-path" not in sys.argv and "--only-fine" not in sys.argv:
         longest_path_goldens()
+        fine_goldens()

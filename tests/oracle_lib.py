@@ -116,6 +116,16 @@ class _Taps:
         self.f("index_search")(h, _ptr(mers, u64p), len(mers), _ptr(idx, u64p), _ptr(nb, u64p))
         return idx, nb
 
+    def search_k(self, h, mers, kk):
+        """The fine pass's lookup: patterns of kk <= k bases in the same suffix array."""
+        mers = np.ascontiguousarray(mers, dtype=np.uint64)
+        idx = np.empty(len(mers), np.uint64)
+        nb = np.empty(len(mers), np.uint64)
+        f = self.f("index_search_k")
+        f.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_uint, u64p, u64p]
+        f(h, _ptr(mers, u64p), len(mers), kk, _ptr(idx, u64p), _ptr(nb, u64p))
+        return idx, nb
+
     def lis(self, pairs, a=1.3, b=10.0, cap=10000.0, window=1):
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         out = np.empty(max(1, len(pairs)), dtype=np.uint32)
@@ -187,8 +197,10 @@ class Port(_Taps):
     def run(self, mode, sr, reads, unitigs, out, mer, k_unitig, unitigs_is_fasta=True, psa_min=13, threads=1,
             max_reads=0, stretch_factor=1.3, stretch_constant=10.0, stretch_cap=10000.0, forward=True,
             max_match=False, max_count=5000, mers_matching=0.0, bases_matching=17.0, overlap_play=1.3, errors=3.0,
-            density=0.029, min_length=100.0, bases=False, tiling=1, trim=0):
+            density=0.029, min_length=100.0, bases=False, tiling=1, trim=0, fine_mer=0):
         ti, ta = C.c_double(0), C.c_double(0)
+        self.lib.op_set_fine_mer.argtypes = [C.c_uint]
+        self.lib.op_set_fine_mer(fine_mer)
         nb = self.lib.op_run(mode, sr.encode(), reads.encode(), (unitigs or "").encode(), int(unitigs_is_fasta),
                              out.encode(), mer, psa_min, threads, max_reads, stretch_factor, stretch_constant,
                              stretch_cap, int(forward), int(max_match), max_count, mers_matching, bases_matching,

@@ -96,6 +96,40 @@ def test_reference_generated_fixtures(tmpdir_session, tmp_path, name):
     assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
 
 
+FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}   # as in make_golden.py
+
+
+@pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
+def test_fine_pass_matches_reference_fixture(tmpdir_session, tmp_path, name):
+    """-F (fine_aligner.cc): windows from the coarse rows, shorter mers looked up in the same suffix array (fine mer
+    below, at and above --psa-min), accept-all chaining -- against the reference's own records."""
+    cfg = json.load(open(os.path.join(GOLD, name + ".json")))["config"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+              "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"]]
+    for fine, with_coords in FINE[name]:
+        out = str(tmp_path / "cmr.txt")
+        run([CMR] + common + ["-F", str(fine), "-t", "2", "-o", out])
+        assert open(out).read() == open(os.path.join(GOLD, "%s.fine%d.cmr.txt" % (name, fine))).read()
+        if with_coords:
+            out = str(tmp_path / "coords.txt")
+            run([JFA] + common + ["-F", str(fine), "-H", "--coords", out])
+            assert records(out) == records(os.path.join(GOLD, "%s.fine%d.coords.txt" % (name, fine)))
+
+
+def test_fine_pass_larger_input_against_oracle(tmpdir_session, tmp_path, port):
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_fine_big"), 400000, coverage=4, read_len=5000, seed=37, repeat_frac=0.1)
+    for fine, extra in ((12, []), (10, ["--max-match"])):
+        out, want = str(tmp_path / "gpu.txt"), str(tmp_path / "port.txt")
+        run([CMR, "-s", "1M", "-m", "15", "-k", "41", "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"],
+             "-F", str(fine), "-o", out] + extra, env=dict(os.environ, MR_BATCH_BASES="300000"))
+        port.run(0, info["sr"], info["reads"], info["unitigs_len"], want, 15, 41, unitigs_is_fasta=False, threads=8,
+                 fine_mer=fine, max_match=bool(extra))
+        got, exp = records(out), records(want)
+        diff = [k for k in set(got) | set(exp) if got.get(k) != exp.get(k)]
+        assert len(exp) > 200 and len(diff) <= max(2, len(exp) // 100), (len(diff), len(exp), diff[:3])
+
+
 LP_VARIANTS = {"lp": [], "lp_maximal": ["-T", "maximal", "--trim", "match", "-b", "-O", "1.5", "-d", "0.01"]}   # as in make_golden.py
 
 

@@ -114,6 +114,26 @@ def test_port_text_matches_reference_fixture(port, golden_case, tmp_path):
     assert sha(open(out, "rb").read()) == meta["cmr_with_sequences_sha256_t1"]
 
 
+FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}   # as in make_golden.py
+
+
+def test_port_fine_pass_matches_reference_fixture(port, golden_case, tmp_path):
+    """-F: the port's restatement of fine_aligner.cc against the reference's own output (fine mer below,
+    at and above --psa-min)."""
+    name, meta, info = golden_case
+    cfg = meta["config"]
+    for fine, with_coords in FINE[name]:
+        out = str(tmp_path / "cmr.txt")
+        port.run(0, info["sr"], info["reads"], info["unitigs_len"], out, cfg["mer"], cfg["unitig_k"],
+                 unitigs_is_fasta=False, psa_min=cfg["psa_min"], threads=2, fine_mer=fine)
+        assert records(out) == records(os.path.join(GOLD, "%s.fine%d.cmr.txt" % (name, fine)))
+        if with_coords:
+            out = str(tmp_path / "coords.txt")
+            port.run(1, info["sr"], info["reads"], info["unitigs_len"], out, cfg["mer"], cfg["unitig_k"],
+                     unitigs_is_fasta=False, psa_min=cfg["psa_min"], threads=2, fine_mer=fine)
+            assert records(out) == records(os.path.join(GOLD, "%s.fine%d.coords.txt" % (name, fine)))
+
+
 # ---- live comparison against the compiled reference -------------------------------------------------
 def _canon_coords(r):
     rows = []

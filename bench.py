@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="mega_reads", choices=["mega_reads", "lookup"],
                     help="lookup: BASELINE.json configs[4] microbench (k-mer queries against a random-text suffix array)")
+    ap.add_argument("--fine-mer", type=int, default=0,
+                    help="also run the -F fine pass with this mer (not part of the BASELINE metric: off by default)")
     ap.add_argument("--lookup-n", type=float, default=1e9)
     ap.add_argument("--lookup-queries", type=float, default=1e9)
     ap.add_argument("--lookup-k", type=int, default=17)
@@ -275,12 +277,15 @@ def ours(args, w, files):
 
     err = C.create_string_buffer(512)
     t0 = time.perf_counter()
-    tool = H.mrh_tool_create(files["sr"].encode(), files["unitigs"].encode(), 1, w["mer"], w["psa_min"], w["unitig_k"],
+    psa_min = min(args.fine_mer, w["psa_min"]) if args.fine_mer else w["psa_min"]      # create_mega_reads.cc:131-132
+    tool = H.mrh_tool_create(files["sr"].encode(), files["unitigs"].encode(), 1, w["mer"], psa_min, w["unitig_k"],
                              local_rank, err, 512)
     if not tool:
         raise RuntimeError("mrh_tool_create: " + err.value.decode())
     index_s = time.perf_counter() - t0
     ctx, idx, params = H.mrh_tool_context(tool), H.mrh_tool_index(tool), H.mrh_tool_params(tool)
+    if args.fine_mer:
+        C.cast(params, C.POINTER(api.Params)).contents.fine_mer = args.fine_mer
     H.mrh_tool_nstreams.restype = C.c_uint
     H.mrh_tool_nstreams.argtypes = [C.c_void_p]
     H.mrh_tool_stream_context.restype = C.c_void_p
@@ -467,7 +472,7 @@ def ours(args, w, files):
         line = {"metric": "pacbio_bases_aligned_per_s", "value": value, "unit": "bases/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-                "data": "synthetic", "config": dict(config_dict(args, w), streams_per_gpu=nstreams),
+                "data": "synthetic", "config": dict(config_dict(args, w), streams_per_gpu=nstreams, fine_mer=args.fine_mer),
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
                         "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,

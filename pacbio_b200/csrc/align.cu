@@ -602,9 +602,14 @@ struct info_args {
 // paths work directly on the output slice.
 constexpr int kInfoLocal = 24;
 
+// Elements [t_begin, t_end) of the chain.  A segment that does not start at 0 first puts itself in the
+// state the sequential walk has after element t_begin - 1: previous position = that element's, current
+// unitig = the first one the element's mer ends in (the walk only moves forward and the ends of the
+// unitigs increase along the path -- the caller checks that -- so this is where the walk stands).
+// The pending counters start at 0: sums are what is stored, every segment adds its share.
 template<bool LOCAL>
 __device__ __forceinline__ bool kmers_info_walk(const info_args& A, uint64_t i, uint32_t nu, int32_t* mers, int32_t* bases,
-                                                const int32_t* ulen_tab) {
+                                                const int32_t* ulen_tab, uint32_t t_begin = 0, uint32_t t_end = 0xffffffffu) {
   const uint32_t sr = A.sr[i];
   const bool bwd = A.use_bwd[i];
   const uint64_t u0 = A.unitig_off[sr];
@@ -622,10 +627,21 @@ __device__ __forceinline__ bool kmers_info_walk(const info_args& A, uint64_t i, 
   int cend = ulen(0), prev_pos = -K;
   int cur_mers = 0, cur_bases = 0;                    // pending additions to mers/bases[2 * cunitig]
   const bool fwd_align = (int32_t)(uint32_t)(cp[0] >> 32) > 0;
-  uint64_t nxt = cp[0];
-  for(uint32_t t = 0; t < nb; ++t) {
+  if(t_end > nb) t_end = nb;
+  if(t_begin != 0) {
+    const int32_t so = (int32_t)(uint32_t)(cp[t_begin - 1] >> 32);
+    const int pos = fwd_align ? so : (int)(ql + so - K + 2);
+    prev_pos = pos < 0 ? -pos : pos;
+    while(prev_pos + K > cend + 1) {
+      const int ul = ulen(++cunitig);
+      if(ul < 0) return true;                      // the segment that owns that element reports the error
+      cend += ul - UK + 1;
+    }
+  }
+  uint64_t nxt = cp[t_begin];
+  for(uint32_t t = t_begin; t < t_end; ++t) {
     const uint64_t p = nxt;
-    if(t + 1 < nb) nxt = cp[t + 1];
+    if(t + 1 < t_end) nxt = cp[t + 1];
     const int32_t so = (int32_t)(uint32_t)(p >> 32);
     const int pos = fwd_align ? so : (int)(ql + so - K + 2);
     const int sr_pos = pos < 0 ? -pos : pos;
@@ -663,8 +679,17 @@ __device__ __forceinline__ bool kmers_info_walk(const info_args& A, uint64_t i, 
   return true;
 }
 
+// One WARP per coords row.  The chain is cut into pieces of kInfoPiece hits; lane l of the warp takes
+// piece l of every run of 32 pieces, so the warp reads 32 x kInfoPiece consecutive pairs at once
+// (coalesced, all loads in flight together) instead of 32 threads each following a private stream one
+// dependent load at a time.  Every piece starts in the state the sequential walk has there (see
+// kmers_info_walk) and adds its counts to the row's counters in shared memory.
+constexpr int kInfoPiece = 8;
+
 __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int32_t s_ul[4][kInfoLocal], s_m[4][2 * kInfoLocal], s_b[4][2 * kInfoLocal];
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t i = (uint64_t)blockIdx.x * 4 + wib;
   if(i >= A.n) return;
   const uint32_t ilen = A.info_len[i];
   if(ilen == 0) return;
@@ -673,22 +698,111 @@ __global__ void __launch_bounds__(128) kmers_info_kernel(info_args A) {
   const uint32_t sr = A.sr[i];
   const uint64_t u0 = A.unitig_off[sr];
   const uint32_t nu = (uint32_t)(A.unitig_off[sr + 1] - u0);
-  bool ok;
-  if(nu <= (uint32_t)kInfoLocal) {
-    int32_t lm[2 * kInfoLocal], lb[2 * kInfoLocal], ul[kInfoLocal];
-    const bool bwd = A.use_bwd[i];
-    for(uint32_t t = 0; t < nu; ++t) {
-      const uint32_t id = (bwd ? A.unitig_ids[u0 + nu - 1 - t] : A.unitig_ids[u0 + t]) >> 1;
-      ul[t] = id < A.n_unitigs ? A.unitig_len[id] : -1;
+  if(nu > (uint32_t)kInfoLocal) {                  // long unitig paths: one thread, counters in the output slice itself
+    if(lane == 0) {
+      for(uint32_t j = 0; j < ilen; ++j) { gm[j] = 0; gb[j] = 0; }
+      if(!kmers_info_walk<false>(A, i, nu, gm, gb, nullptr)) A.info_len[i] = 0;
     }
-    for(uint32_t j = 0; j < ilen; ++j) { lm[j] = 0; lb[j] = 0; }
-    ok = kmers_info_walk<true>(A, i, nu, lm, lb, ul);
-    if(ok) for(uint32_t j = 0; j < ilen; ++j) { gm[j] = lm[j]; gb[j] = lb[j]; }
-  } else {
-    for(uint32_t j = 0; j < ilen; ++j) { gm[j] = 0; gb[j] = 0; }
-    ok = kmers_info_walk<false>(A, i, nu, gm, gb, nullptr);
+    return;
   }
-  if(!ok) A.info_len[i] = 0;         // the reference clears both vectors on error
+  int32_t *ul = s_ul[wib], *sm = s_m[wib], *sb = s_b[wib];
+  const int K = (int)A.k, UK = (int)A.unitigs_k;
+  const bool bwd = A.use_bwd[i];
+  bool bad_step = false;
+  if(lane < nu) {
+    const uint32_t id = (bwd ? A.unitig_ids[u0 + nu - 1 - lane] : A.unitig_ids[u0 + lane]) >> 1;
+    const int len = id < A.n_unitigs ? A.unitig_len[id] : -1;
+    ul[lane] = len;
+    bad_step = lane != 0 && len >= 0 && len - UK + 1 < 0;
+  }
+  for(uint32_t j = lane; j < ilen; j += 32) { sm[j] = 0; sb[j] = 0; }
+  const bool increasing = !__any_sync(MR_FULL_MASK, bad_step);   // unitig ends increase along the path (always, for real k-unitigs)
+  __syncwarp();
+  if(!increasing) {                                // odd unitig lengths: the plain sequential walk
+    bool ok = true;
+    if(lane == 0) ok = kmers_info_walk<true>(A, i, nu, sm, sb, ul);
+    ok = __shfl_sync(MR_FULL_MASK, (int)ok, 0) != 0;
+    __syncwarp();
+    if(ok) { for(uint32_t j = lane; j < ilen; j += 32) { gm[j] = sm[j]; gb[j] = sb[j]; } }
+    else if(lane == 0) A.info_len[i] = 0;
+    return;
+  }
+  const uint64_t* cp = A.chain_pay + A.chain_pos[i];
+  const uint32_t nb = (uint32_t)A.nb_mers[i];
+  const int64_t ql = A.ql[i];
+  const bool fwd_align = (int32_t)(uint32_t)(cp[0] >> 32) > 0;
+  auto position = [&](uint64_t p) -> int {
+    const int32_t so = (int32_t)(uint32_t)(p >> 32);
+    const int pos = fwd_align ? so : (int)(ql + so - K + 2);
+    return pos < 0 ? -pos : pos;
+  };
+  auto ulen = [&](uint32_t t) -> int { return t < nu ? ul[t] : -1; };
+  bool failed = false;
+  for(uint32_t base = 0; base < nb; base += 32 * kInfoPiece) {
+    const uint32_t t0 = base + lane * kInfoPiece;
+    uint64_t q[kInfoPiece], before = 0;
+#pragma unroll
+    for(int j = 0; j < kInfoPiece; ++j) q[j] = t0 + j < nb ? cp[t0 + j] : 0;
+    if(t0 != 0 && t0 < nb) before = cp[t0 - 1];
+    if(t0 < nb && !failed) {
+      uint32_t cunitig = 0;
+      int cend = ulen(0), prev_pos = -K, cur_mers = 0, cur_bases = 0;
+      bool ok = true;
+      if(t0 != 0) {
+        prev_pos = position(before);
+        while(prev_pos + K > cend + 1) {
+          const int len = ulen(++cunitig);
+          if(len < 0) break;                       // the piece that owns that hit reports the error
+          cend += len - UK + 1;
+        }
+        ok = cunitig < nu;
+      }
+#pragma unroll
+      for(int j = 0; j < kInfoPiece; ++j) {
+        if(!ok || t0 + j >= nb) break;
+        const int sr_pos = position(q[j]);
+        const int new_bases = min(K, sr_pos - prev_pos);
+        while(sr_pos + K > cend + 1) {
+          if(cend >= sr_pos) {
+            if(cunitig >= nu - 1) { failed = true; break; }
+            const int nbb = cend - max(sr_pos, prev_pos + K) + 1;
+            cur_bases += nbb;
+            if(nbb) atomicAdd(sb + 2 * cunitig + 1, nbb);
+          }
+          if(cur_mers) atomicAdd(sm + 2 * cunitig, cur_mers);
+          if(cur_bases) atomicAdd(sb + 2 * cunitig, cur_bases);
+          cur_mers = 0; cur_bases = 0;
+          const int len = ulen(++cunitig);
+          if(len < 0) { failed = true; break; }
+          cend += len - UK + 1;
+        }
+        if(failed) break;
+        ++cur_mers;
+        cur_bases += new_bases;
+        int cendi = cend;
+        for(uint32_t v = cunitig; v < nu - 1 && sr_pos + K > cendi - UK + 1; ++v) {
+          const int full_mer = sr_pos + UK > cendi + 1;
+          if(full_mer) { atomicAdd(sm + 2 * v + 1, 1); atomicAdd(sm + 2 * v + 2, 1); }
+          const int nbb = min(new_bases, sr_pos + K - cendi + UK - 2);
+          if(nbb) { atomicAdd(sb + 2 * v + 1, nbb); atomicAdd(sb + 2 * v + 2, nbb); }
+          const int len = ulen(v + 1);
+          if(len >= 0) cendi += len - UK + 1;
+          else { failed = true; break; }
+        }
+        if(failed) break;
+        prev_pos = sr_pos;
+      }
+      if(!failed && ok) {
+        if(cur_mers) atomicAdd(sm + 2 * cunitig, cur_mers);
+        if(cur_bases) atomicAdd(sb + 2 * cunitig, cur_bases);
+      }
+    }
+    failed = __any_sync(MR_FULL_MASK, failed);
+    if(failed) break;
+  }
+  __syncwarp();
+  if(!failed) { for(uint32_t j = lane; j < ilen; j += 32) { gm[j] = sm[j]; gb[j] = sb[j]; } }
+  else if(lane == 0) A.info_len[i] = 0;      // the reference clears both vectors on error
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1070,7 +1184,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       I.unitig_ids = idx->unitig_ids.as<uint32_t>(); I.unitig_off = idx->unitig_off.as<uint64_t>();
       I.unitig_len = idx->unitig_len.as<int32_t>(); I.n_unitigs = idx->n_unitigs; I.k = k_coords; I.unitigs_k = p->unitigs_k;
       I.kinfo = ws.kinfo.as<int32_t>(); I.binfo = ws.binfo.as<int32_t>();
-      kmers_info_kernel<<<div_up(S, 128), 128, 0, st>>>(I);
+      kmers_info_kernel<<<div_up(S, 4), 128, 0, st>>>(I);
       MR_LAUNCHED(ctx);
     }
     MR_TRY(ws.read_cursor.ensure(ctx, ((size_t)nreads + 1) * 4));

@@ -3,6 +3,7 @@
 // histogram, partial sums, atomic scatter, 4^m std::sort calls) by one stable LSD radix sort of
 // (padded k-mer, position) pairs seeded in descending position order, and PSA::search
 // (mer_sa_imp.hpp:369-479) by a prefix-table probe plus a scan of the bucket's tails.
+#include <cstdlib>
 #include "index.cuh"
 #include "primitives.cuh"
 
@@ -147,6 +148,10 @@ static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k)
     const uint64_t bytes = (((uint64_t)1 << (2 * best)) + 1) * 4 + n * (tb <= 8 ? 1 : (tb <= 16 ? 2 : 4));
     if(bytes <= (110ULL << 20)) break;
     --best;
+  }
+  if(const char* e = getenv("MR_INDEX_PREFIX")) {           // tuning knob: force the internal prefix length
+    const uint32_t v = (uint32_t)atoi(e);
+    if(v >= 1 && v <= psa_min) best = v;
   }
   while(k - best > (uint32_t)kMaxShort) ++best;
   return best;

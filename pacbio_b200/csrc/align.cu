@@ -573,14 +573,6 @@ struct head_flag {
   }
 };
 
-__global__ void __launch_bounds__(256) group_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t nseq,
-                                                             const uint64_t* __restrict__ gpos, uint64_t* __restrict__ group_start) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint64_t k = keys[i];
-    if(((uint32_t)k < nseq) && (i == 0 || keys[i - 1] != k)) group_start[gpos[i]] = i;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // kmers_info / bases_info per surviving coords: compute_kmers_info::add_mer (pb_aligner.cc:84-143),
@@ -999,7 +991,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     uint64_t* alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
     uint64_t* alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
     // group heads -> group_start
-    MR_TRY((prim::exclusive_scan<head_flag, uint64_t>(ctx, head_flag{ skeys, iv.nseq }, H, alt_key, ws.scan_scratch, (uint64_t*)(ctr + 3))));
+    MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));
     G = h_ctr[3];
@@ -1008,8 +1000,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     res->view.n_hits = Hvalid;
     res->view.n_groups = G;
     MR_TRY(ws.group_start.ensure(ctx, (G + 2) * 8));
-    group_scatter_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(skeys, H, iv.nseq, alt_key, ws.group_start.as<uint64_t>());
-    MR_LAUNCHED(ctx);
+    MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
     MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &Hvalid, 8, cudaMemcpyHostToDevice, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));   // Hvalid is a stack variable
 

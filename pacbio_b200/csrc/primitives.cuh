@@ -107,6 +107,53 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(In in, uint64_
   }
 }
 
+// positions of the set flags: out[k] = index of the k-th i with in(i) != 0 (in() yields 0 / 1).
+// Same tile walk as scan_apply_kernel, but only the flagged positions are written.
+template<typename In>
+__global__ void __launch_bounds__(kScanThreads) flag_positions_kernel(In in, uint64_t n, const uint64_t* __restrict__ block_sums,
+                                                                       uint64_t* __restrict__ out) {
+  __shared__ uint64_t sw[8];
+  __shared__ uint8_t stage[kScanTile];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+#pragma unroll
+  for(int i = 0; i < kScanItems; ++i) {
+    const uint32_t t = i * kScanThreads + threadIdx.x;
+    const uint64_t idx = base + t;
+    stage[t] = idx < n ? (uint8_t)in(idx) : 0;
+  }
+  __syncthreads();
+  uint32_t flags = 0, s = 0;
+#pragma unroll
+  for(int i = 0; i < kScanItems; ++i) { const uint32_t f = stage[threadIdx.x * kScanItems + i]; flags |= f << i; s += f; }
+  uint64_t total;
+  uint64_t run = block_exclusive_scan_256(s, sw, total) + block_sums[blockIdx.x];
+#pragma unroll
+  for(int i = 0; i < kScanItems; ++i)
+    if((flags >> i) & 1) out[run++] = base + (uint64_t)threadIdx.x * kScanItems + i;
+}
+
+// out[] as above; *d_total (device) and block_sums scratch as in exclusive_scan.  Two launches +
+// the single-CTA scan of the tile sums; the caller reads *d_total before sizing `out`, so the
+// positions are written by a separate call.
+template<typename In>
+int flag_count(mr_context* ctx, In in, uint64_t n, dev_buf& scratch, uint64_t* d_total) {
+  const uint32_t nblocks = div_up(n, kScanTile);
+  if(n == 0) { MR_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream)); return MR_OK; }
+  MR_TRY(scratch.ensure(ctx, ((size_t)nblocks + 1) * sizeof(uint64_t)));
+  scan_reduce_kernel<In><<<nblocks, kScanThreads, 0, ctx->stream>>>(in, n, scratch.as<uint64_t>());
+  MR_LAUNCHED(ctx);
+  scan_blocksums_kernel<<<1, 1024, 0, ctx->stream>>>(scratch.as<uint64_t>(), nblocks, d_total);
+  MR_LAUNCHED(ctx);
+  return MR_OK;
+}
+template<typename In>
+int flag_positions(mr_context* ctx, In in, uint64_t n, dev_buf& scratch, uint64_t* out) {
+  if(n == 0) return MR_OK;
+  flag_positions_kernel<In><<<div_up(n, kScanTile), kScanThreads, 0, ctx->stream>>>(in, n, scratch.as<uint64_t>(), out);
+  MR_LAUNCHED(ctx);
+  return MR_OK;
+}
+
 struct ptr_in_u32 { const uint32_t* p; __device__ uint64_t operator()(uint64_t i) const { return p[i]; } };
 struct ptr_in_u64 { const uint64_t* p; __device__ uint64_t operator()(uint64_t i) const { return p[i]; } };
 

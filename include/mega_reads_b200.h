@@ -169,6 +169,18 @@ typedef struct mr_result_view {
 } mr_result_view;
 int  mr_result_get(const mr_result* r, mr_result_view* view);
 
+/* ---- staged batches: mr_align_batch copies its input and only then starts the kernels.  A caller
+ *  that knows the next batch can have it copied while the current one is aligned: mr_stage_batch
+ *  starts the copy on the context's copy stream and returns (at once when the buffers are pinned,
+ *  mr_host_pin; it may be called from another host thread than the aligning one),
+ *  mr_align_staged waits for the copy on the device, aligns, and releases the staged batch
+ *  (mr_staged_free does that for a batch that is never aligned).  `bases` must stay valid until
+ *  mr_align_staged / mr_staged_free returns.                                                     */
+typedef struct mr_staged mr_staged;
+int  mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_start, uint32_t nreads, mr_staged** out);
+int  mr_align_staged(mr_context* ctx, mr_index* idx, const mr_params* p, mr_staged* staged, mr_result** out);
+void mr_staged_free(mr_staged* staged);
+
 /* ---- overlap graph over rows the caller already has: replaces overlap_graph::thread::reset +
  *  traverse (overlap_graph.hpp:177-198, overlap_graph.cc:7-59) as longest_path_overlap_graph2.cc:46-49
  *  calls them on the rows of a coords file.  `rows` is an mr_result_view in HOST memory whose

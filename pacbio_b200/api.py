@@ -92,6 +92,9 @@ def lib():
                                  C.POINTER(C.c_void_p)]
     L.mr_align_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, u64p,
                                         C.c_uint32, C.POINTER(C.c_void_p)]
+    L.mr_stage_batch.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.mr_align_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mr_staged_free.argtypes = [C.c_void_p]
     L.mr_result_free.argtypes = [C.c_void_p]
     L.mr_result_get.argtypes = [C.c_void_p, C.POINTER(ResultView)]
     L.mr_result_taps.argtypes = [C.c_void_p, u64p, C.POINTER(i64p), u64p, C.POINTER(i32p), u64p, C.POINTER(u32p)]
@@ -248,6 +251,18 @@ class Context:
         starts = np.ascontiguousarray(reads.starts, dtype=np.uint64)
         self.check(self.L.mr_align_batch(self.h, index.h, C.byref(params), reads.bases.ctypes.data_as(C.c_void_p),
                                          _p(starts, u64p), reads.nreads, C.byref(out)))
+        return Result(self, out)
+
+    def stage(self, reads):
+        """Starts the host -> device copy of a batch (mr_stage_batch); pass the handle to align_staged."""
+        h = C.c_void_p()
+        starts = np.ascontiguousarray(reads.starts, dtype=np.uint64)
+        self.check(self.L.mr_stage_batch(self.h, reads.bases.ctypes.data_as(C.c_void_p), _p(starts, u64p), reads.nreads, C.byref(h)))
+        return h
+
+    def align_staged(self, index, staged, params):
+        out = C.c_void_p()
+        self.check(self.L.mr_align_staged(self.h, index.h, C.byref(params), staged, C.byref(out)))
         return Result(self, out)
 
     def align_device(self, index, d_bases_ptr, d_starts_ptr, h_starts, nreads, params):

@@ -182,7 +182,7 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // (coarse_aligner.cc:93-102), looks up both strands (superread_parser.hpp:183-192 ->
 // mer_sa_imp.hpp:369-479) and applies the max-count filter (coarse_aligner.cc:108-111).
 // rec[g] = {index(m), nb(m), index(rm), nb(rm)}; size[g] = nb(m)+nb(rm) or 0 when there is no list.
-__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kSeedThreads, 6) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
@@ -1360,6 +1360,60 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   timer.collect();
   *out = res.release();
   return MR_OK;
+}
+
+// Staged batches: the host -> device copy of batch i + 1 runs on its own stream while the kernels
+// of batch i run.  mr_stage_batch may be called from another host thread than the one that aligns
+// (a pageable source makes the copy call block; a pinned one, mr_host_pin, returns at once).
+int mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_start, uint32_t nreads, mr_staged** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!bases || !read_start || !out) return ctx->fail(MR_EINVAL, "mr_stage_batch: null argument");
+  *out = nullptr;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  std::unique_ptr<mr_staged> s;
+  {
+    std::lock_guard<std::mutex> lock(ws.pool_mutex);
+    if(!ws.staged_pool.empty()) { s.reset(ws.staged_pool.back()); ws.staged_pool.pop_back(); }
+  }
+  if(!s) {
+    s.reset(new mr_staged);
+    s->ctx = ctx;
+    MR_CUDA(ctx, cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+  }
+  const uint64_t T = read_start[nreads];
+  MR_TRY(s->bases.ensure(ctx, T + 64));
+  MR_TRY(s->read_start.ensure(ctx, ((size_t)nreads + 1) * 8));
+  s->h_read_start.assign(read_start, read_start + nreads + 1);
+  s->nreads = nreads;
+  MR_CUDA(ctx, cudaMemcpyAsync(s->bases.p, bases, T, cudaMemcpyHostToDevice, ctx->copy_stream));
+  MR_CUDA(ctx, cudaMemcpyAsync(s->read_start.p, s->h_read_start.data(), ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+  MR_CUDA(ctx, cudaEventRecord(s->ready, ctx->copy_stream));
+  *out = s.release();
+  return MR_OK;
+}
+
+void mr_staged_free(mr_staged* s) {
+  if(!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaEventSynchronize(s->ready);
+  mr_workspace* ws = s->ctx->ws;
+  if(ws) {
+    std::lock_guard<std::mutex> lock(ws->pool_mutex);
+    if(ws->staged_pool.size() < 4) { ws->staged_pool.push_back(s); return; }
+  }
+  delete s;
+}
+
+int mr_align_staged(mr_context* ctx, mr_index* idx, const mr_params* p, mr_staged* s, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!s || s->ctx != ctx) return ctx->fail(MR_EINVAL, "mr_align_staged: the batch was staged on another context");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ready, 0));
+  const int rc = mr_align_batch_device(ctx, idx, p, s->bases.as<char>(), s->read_start.as<uint64_t>(), s->h_read_start.data(), s->nreads, out);
+  mr_staged_free(s);
+  return rc;
 }
 
 void mr_result_free(mr_result* r) {

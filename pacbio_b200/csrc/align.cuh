@@ -26,6 +26,16 @@ struct fine_buffers {
   prim::sort_scratch sort;
 };
 
+// a batch of reads already copied (or on its way) to the device, see mr_stage_batch
+struct mr_staged {
+  mr_context* ctx = nullptr;
+  dev_buf bases, read_start;
+  std::vector<uint64_t> h_read_start;
+  uint32_t nreads = 0;
+  cudaEvent_t ready = nullptr;
+  ~mr_staged() { if(ready) cudaEventDestroy(ready); }
+};
+
 // Scratch that lives in the context and is reused from batch to batch.
 struct mr_workspace {
   dev_buf bases, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
@@ -43,7 +53,8 @@ struct mr_workspace {
   prim::sort_scratch sort;
   std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
   std::mutex pool_mutex;                    // mr_result_free may run on another host thread than mr_align_batch
-  ~mr_workspace() { for(auto p : pinned_pool) delete p; }
+  std::vector<mr_staged*> staged_pool;      // device input buffers of staged batches, recycled (cudaMalloc synchronises the device)
+  ~mr_workspace() { for(auto p : pinned_pool) delete p; for(auto s : staged_pool) delete s; }
 };
 
 struct mr_result {

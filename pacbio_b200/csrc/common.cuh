@@ -21,6 +21,7 @@ struct mr_context {
   mr_workspace* ws = nullptr;          // scratch reused across batches (align.cu)
   int          device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host -> device copies of staged batches (mr_stage_batch)
   cudaStream_t aux[9] = { };   // side streams for kernels that may overlap (chain tiers)
   cudaEvent_t  ev[10] = { };
   std::string  err;

@@ -34,6 +34,7 @@ int mr_context_create(int device, mr_context** out) {
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if(e != cudaSuccess) { g_mr_create_error = cudaGetErrorString(e); return MR_ECUDA; }
   for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for(auto& v : ctx->ev) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
   *out = ctx.release();
   return MR_OK;
@@ -45,6 +46,7 @@ void mr_context_destroy(mr_context* ctx) {
   if(ctx->stream) cudaStreamSynchronize(ctx->stream);
   if(ctx->ws) mr_workspace_free(ctx->ws);
   for(auto& a : ctx->aux) if(a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+  if(ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for(auto& v : ctx->ev) if(v) cudaEventDestroy(v);
   if(ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

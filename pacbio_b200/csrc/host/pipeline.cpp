@@ -129,13 +129,31 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
     to_align.close();
   });
 
-  std::vector<std::thread> aligners;
+  // per context: an uploader thread stages the next batch (host -> device copy on the context's copy
+  // stream, mr_stage_batch) while the aligner thread runs the kernels of the current one
+  struct staged_job { job j; mr_staged* staged; };
+  std::vector<std::unique_ptr<bounded_queue<staged_job>>> staged;
+  for(size_t g = 0; g < ds.ctx.size(); ++g) staged.emplace_back(new bounded_queue<staged_job>(1));
+  std::vector<std::thread> aligners, uploaders;
   std::atomic<int> live((int)ds.ctx.size());
   for(size_t g = 0; g < ds.ctx.size(); ++g) {
-    aligners.emplace_back([&, g]() {
+    uploaders.emplace_back([&, g]() {
       job j;
       while(to_align.pop(j)) {
-        if(!error.empty()) continue;
+        staged_job sj;
+        sj.staged = nullptr;
+        if(error.empty() && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
+          sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
+        sj.j = std::move(j);
+        staged[g]->push(std::move(sj));
+      }
+      staged[g]->close();
+    });
+    aligners.emplace_back([&, g]() {
+      staged_job sj;
+      while(staged[g]->pop(sj)) {
+        job j = std::move(sj.j);
+        if(!error.empty()) { if(sj.staged) mr_staged_free(sj.staged); continue; }
         // A batch whose hits exceed a device limit (very repeat-rich reads) or the free memory is cut
         // in halves and retried; the halves are formatted in order, so the output does not change.
         std::deque<std::unique_ptr<read_batch>> work;
@@ -144,7 +162,9 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           std::unique_ptr<read_batch> b = std::move(work.front());
           work.pop_front();
           part pt;
-          const int rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &pt.result);
+          int rc;
+          if(sj.staged) { rc = mr_align_staged(ds.ctx[g], ds.idx[g], &params, sj.staged, &pt.result); sj.staged = nullptr; }
+          else rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &pt.result);
           if(rc == MR_OK) { pt.batch = std::move(b); j.parts.push_back(std::move(pt)); continue; }
           if((rc == MR_ELIMIT || rc == MR_ENOMEM) && b->nreads() > 1) {
             const uint32_t half = b->nreads() / 2;
@@ -191,6 +211,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   });
 
   reader.join();
+  for(auto& t : uploaders) t.join();
   for(auto& t : aligners) t.join();
   formatter.join();
   fflush(out);

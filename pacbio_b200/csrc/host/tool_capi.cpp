@@ -146,29 +146,48 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   });
   std::atomic<size_t> next(0);
   std::vector<double> busy(t->DS.ctx.size(), 0.0);
-  std::vector<std::thread> aligners;
+  std::vector<std::thread> aligners, uploaders;
+  struct staged_item { size_t i; mr_staged* s; };
+  std::vector<std::unique_ptr<mrh::bounded_queue<staged_item>>> staged;
+  for(size_t s = 0; s < t->DS.ctx.size(); ++s) staged.emplace_back(new mrh::bounded_queue<staged_item>(1));
   for(size_t s = 0; s < t->DS.ctx.size(); ++s) {
-    aligners.emplace_back([&, s]() {
+    // the copy of a context's next batch runs (on its copy stream) while its current batch is aligned
+    uploaders.emplace_back([&, s]() {
       while(true) {
         const size_t i = next++;
         if(i >= nb) break;
         {   // stay at most a few batches ahead of the formatter (bounds the pinned result memory)
           std::unique_lock<std::mutex> l(m);
-          cv.wait(l, [&] { return i < formatted + 2 + t->DS.ctx.size() || stop; });
+          cv.wait(l, [&] { return i < formatted + 3 + t->DS.ctx.size() || stop; });
           if(stop) break;
         }
         mrh::read_batch* b = t->batches[i].get();
+        mr_staged* st = nullptr;
+        if(mr_stage_batch(t->DS.ctx[s], b->bases.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
+          std::lock_guard<std::mutex> l(m);
+          if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]);
+          stop = true; cv.notify_all();
+          break;
+        }
+        staged[s]->push(staged_item{ i, st });
+      }
+      staged[s]->close();
+    });
+    aligners.emplace_back([&, s]() {
+      staged_item it;
+      while(staged[s]->pop(it)) {
         mr_result* r = nullptr;
         const auto a0 = std::chrono::steady_clock::now();
-        const int rc = mr_align_batch(t->DS.ctx[s], t->DS.idx[s], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+        const int rc = mr_align_staged(t->DS.ctx[s], t->DS.idx[s], &t->P, it.s, &r);
         busy[s] += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
         std::lock_guard<std::mutex> l(m);
-        if(rc != MR_OK) { if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]); stop = true; cv.notify_all(); break; }
-        done[i] = r; ready[i] = 1;
+        if(rc != MR_OK) { if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]); stop = true; cv.notify_all(); continue; }
+        done[it.i] = r; ready[it.i] = 1;
         cv.notify_all();
       }
     });
   }
+  for(auto& th : uploaders) th.join();
   for(auto& th : aligners) th.join();
   formatter.join();
   for(double b : busy) t->last_align_s = std::max(t->last_align_s, b);

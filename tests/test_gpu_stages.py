@@ -193,6 +193,25 @@ def test_align_stages_match_oracle(case, ctx, port, forward):
     port.aligner_destroy(ap)
 
 
+def test_staged_batches_give_the_same_rows(case, ctx):
+    """mr_stage_batch + mr_align_staged (copy of the next batch under the kernels of the current one) == mr_align_batch."""
+    import pacbio_b200 as pb
+    c = case["cfg"]
+    reads = pb.Reads(case["info"]["reads"])
+    p = pb.default_params(unitigs_k=c["uk"], run_graph=1)
+    want = ctx.align(case["idx"], reads, p)
+    s1 = ctx.stage(reads)
+    s2 = ctx.stage(reads)                      # two batches in flight on the copy stream
+    got1 = ctx.align_staged(case["idx"], s1, p)
+    got2 = ctx.align_staged(case["idx"], s2, p)
+    for got in (got1, got2):
+        assert got.ncoords == want.ncoords and got.ncoords > 0
+        for f in ("rs", "re", "qs", "qe", "nb_mers", "sr", "stretch", "offset", "avg_err", "lpath", "lprev", "component"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    s3 = ctx.stage(reads)                      # a staged batch that is never aligned can be dropped
+    ctx.L.mr_staged_free(s3)
+
+
 def test_shared_reciprocal_division_is_exact(ctx):
     """div_by_count (chain.cu) must equal IEEE x / n bit for bit: 2^30 random operands."""
     import ctypes as C

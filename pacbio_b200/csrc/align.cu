@@ -182,7 +182,7 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // (coarse_aligner.cc:93-102), looks up both strands (superread_parser.hpp:183-192 ->
 // mer_sa_imp.hpp:369-479) and applies the max-count filter (coarse_aligner.cc:108-111).
 // rec[g] = {index(m), nb(m), index(rm), nb(rm)}; size[g] = nb(m)+nb(rm) or 0 when there is no list.
-__global__ void __launch_bounds__(kSeedThreads, 6) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,

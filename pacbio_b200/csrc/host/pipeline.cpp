@@ -77,6 +77,11 @@ unsigned streams_per_device() {
   return 1;
 }
 
+bool stage_batches() {
+  const char* e = getenv("MR_STAGE");
+  return e && *e && *e != '0';
+}
+
 void add_streams(device_set& ds, unsigned per_device) {
   const size_t ndev = ds.ctx.size();
   for(unsigned s = 1; s < per_device; ++s) {
@@ -142,7 +147,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       while(to_align.pop(j)) {
         staged_job sj;
         sj.staged = nullptr;
-        if(error.empty() && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
+        if(stage_batches() && error.empty() && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
         sj.j = std::move(j);
         staged[g]->push(std::move(sj));

@@ -66,6 +66,9 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
 // configs[1]: +4 % device throughput with 2, +11 % with 3, but the aligner threads then compete
 // with the formatter threads for host cores and the end-to-end rate drops, hence the default).
 unsigned streams_per_device();
+// MR_STAGE=1: copy the next batch to the device while the current one is aligned (mr_stage_batch /
+// mr_align_staged); off by default until it has run on the target box
+bool stage_batches();
 // adds per_device - 1 more contexts for every device of ds, sharing the device's index
 void add_streams(device_set& ds, unsigned per_device);
 

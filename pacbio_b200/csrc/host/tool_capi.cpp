@@ -163,7 +163,7 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
         }
         mrh::read_batch* b = t->batches[i].get();
         mr_staged* st = nullptr;
-        if(mr_stage_batch(t->DS.ctx[s], b->bases.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
+        if(mrh::stage_batches() && mr_stage_batch(t->DS.ctx[s], b->bases.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
           std::lock_guard<std::mutex> l(m);
           if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]);
           stop = true; cv.notify_all();
@@ -178,7 +178,9 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
       while(staged[s]->pop(it)) {
         mr_result* r = nullptr;
         const auto a0 = std::chrono::steady_clock::now();
-        const int rc = mr_align_staged(t->DS.ctx[s], t->DS.idx[s], &t->P, it.s, &r);
+        mrh::read_batch* b = t->batches[it.i].get();
+        const int rc = it.s ? mr_align_staged(t->DS.ctx[s], t->DS.idx[s], &t->P, it.s, &r)
+                            : mr_align_batch(t->DS.ctx[s], t->DS.idx[s], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
         busy[s] += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
         std::lock_guard<std::mutex> l(m);
         if(rc != MR_OK) { if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]); stop = true; cv.notify_all(); continue; }

@@ -81,24 +81,51 @@ def data_files(args):
                    unitigs_len=prefix + ".unitigs_len.txt", info=info, prefix=prefix)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe):
+    ONE `nvidia-smi -lms 200` process per rank, started before the timed region and killed after it.
+    (A new nvidia-smi per sample re-initialises NVML over every GPU of the box and forks a process
+    that holds gigabytes of page-locked memory, five times a second per rank: at N > 1 that showed
+    up as slower host-synchronising phases of the device-timed step.)"""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc, self.path = index, [], None, None
 
-    def run(self):
+    def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        if os.environ.get("MR_BENCH_NO_CLOCKS"):          # A/B switch: does the sampling itself cost anything?
+            return
+        try:
+            import tempfile
+            fd, self.path = tempfile.mkstemp(prefix="mr_clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.rows.append([x.strip() for x in out.split(",")])
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+            self.proc = None
+        if self.path:
+            try:
+                for line in open(self.path):
+                    r = [x.strip() for x in line.strip().split(",")]
+                    if len(r) >= 6:
+                        self.rows.append(r)
+                os.remove(self.path)
             except Exception:
                 pass
-            time.sleep(0.2)
+            self.path = None
 
     def summary(self):
         if not self.rows:
@@ -410,8 +437,7 @@ def ours(args, w, files):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier(dist)
-    sampler.stop_flag = True
-    sampler.join()
+    sampler.stop()
     e2e_s_max = max_over_ranks(dist, e2e_s)
     stats = (C.c_uint64 * 8)()
     H.mrh_tool_last_stats(tool, stats)
@@ -476,7 +502,7 @@ def ours(args, w, files):
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
                         "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                        "host_threads": host_threads, "text_bytes_per_step": int(stats[0]),
+                        "host_threads": host_threads, "host_cores": os.cpu_count(), "text_bytes_per_step": int(stats[0]),
                         "stage_busy_ms_last_step": {"mr_align_batch": 1e3 * st_align.value, "host_format": 1e3 * st_format.value},
                         "timing": "wall clock (includes host tiling/printing), max over ranks"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
@@ -554,8 +580,7 @@ def lookup_microbench(args):
     e1.record(stream)
     ctx.sync()
     torch.cuda.synchronize()
-    sampler.stop_flag = True
-    sampler.join()
+    sampler.stop()
     dt = e0.elapsed_time(e1) * 1e-3
     found = int((out_n > 0).sum().item())
     # end to end: host buffers in and out through mr_lookup_batch, on a bounded slice of the queries

@@ -157,22 +157,12 @@ static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k)
   return best;
 }
 
-extern "C" {
-
-int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
-                    const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
-                    uint32_t n_unitigs, uint32_t psa_min, uint32_t k, mr_index** out) {
-  if(!ctx) return MR_EINVAL;
-  if(!out || !text2bit || !sr_start || nseq == 0) return ctx->fail(MR_EINVAL, "mr_index_create: null argument");
-  if(!(psa_min >= 1 && psa_min < k && k <= 31))
-    return ctx->fail(MR_EINVAL, "mr_index_create: need 1 <= psa_min < mer <= 31");
-  if(psa_min > 15) return ctx->fail(MR_ELIMIT, "mr_index_create: psa_min > 15 (prefix table over 4 GiB) not supported");
-  if(k - psa_min > (uint32_t)kMaxShort) return ctx->fail(MR_ELIMIT, "mr_index_create: mer - psa_min > 16 not supported");
-  if(n < k) return ctx->fail(MR_EINVAL, "mr_index_create: text shorter than one k-mer");
-  if(n >= 0xfffffff0ULL) return ctx->fail(MR_ELIMIT, "mr_index_create: text of 2^32 bases or more not supported");
-  if(sr_start[0] != 0 || sr_start[nseq] != n) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must span [0, n]");
-  MR_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->timers.clear();
+// One part: a complete index over `n` bases of text.  sr_start[0 .. nseq] are the part's own
+// super-read starts (sr_start[nseq] = its own bases <= n; the rest of the text, if any, is the
+// extension described in index.cuh).
+static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
+                      uint32_t psa_min, uint32_t k, mr_index** out) {
+  if(n >= 0xfffffff0ULL) return ctx->fail(MR_ELIMIT, "mr_index_create: index part of 2^32 bases or more");
   phase_timer timer(ctx);
 
   std::unique_ptr<mr_index> idx(new mr_index);
@@ -195,10 +185,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
   MR_LAUNCHED(ctx);
   {
     std::vector<uint32_t> starts32(nseq + 1);
-    for(uint32_t i = 0; i <= nseq; ++i) {
-      if(i && sr_start[i] <= sr_start[i - 1]) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must be strictly increasing");
-      starts32[i] = (uint32_t)sr_start[i];
-    }
+    for(uint32_t i = 0; i <= nseq; ++i) starts32[i] = (uint32_t)sr_start[i];
     MR_TRY(idx->sr_start.ensure(ctx, ((size_t)nseq + 2) * sizeof(uint32_t)));
     MR_CUDA(ctx, cudaMemcpyAsync(idx->sr_start.p, starts32.data(), ((size_t)nseq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));
@@ -207,20 +194,6 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
   MR_TRY(idx->blk.ensure(ctx, ((size_t)nblk + 1) * sizeof(uint32_t)));
   blk_table_kernel<<<div_up(nblk, 256), 256, 0, st>>>(idx->sr_start.as<uint32_t>(), nseq, nblk, idx->blk.as<uint32_t>());
   MR_LAUNCHED(ctx);
-
-  if(unitig_ids && unitig_off && unitig_len && n_unitigs) {
-    idx->has_unitigs = true;
-    idx->n_unitigs = n_unitigs;
-    const uint64_t total = unitig_off[nseq];
-    idx->unitig_total = total;
-    MR_TRY(idx->unitig_ids.ensure(ctx, (total + 1) * sizeof(uint32_t)));
-    MR_TRY(idx->unitig_off.ensure(ctx, ((size_t)nseq + 1) * sizeof(uint64_t)));
-    MR_TRY(idx->unitig_len.ensure(ctx, (size_t)n_unitigs * sizeof(int32_t)));
-    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_ids.p, unitig_ids, total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_off.p, unitig_off, ((size_t)nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_len.p, unitig_len, (size_t)n_unitigs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));
-  }
 
   timer.next("sorting");
   {
@@ -255,6 +228,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
   v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
   v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.mi = mi; v.tail_bits = tail_bits; v.tail_bytes = tail_bytes;
+  v.sr_base = 0; v.nseq_all = nseq;
   v.nshort = 0;
   for(uint32_t j = 1; j <= k - psa_min; ++j) {
     const uint64_t pos = n - k + j;
@@ -265,6 +239,122 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
       key = (key << 2) | c;
     }
     v.short_key[v.nshort++] = key;
+  }
+  idx->n_all = sr_start[nseq]; idx->nseq_all = nseq;
+  *out = idx.release();
+  return MR_OK;
+}
+
+// whole-index tables of a freshly built or loaded one-part index: the super-read lengths
+int finish_single_part(mr_index* idx, const std::vector<uint32_t>& sr_len) {
+  mr_context* ctx = idx->ctx;
+  MR_TRY(idx->sr_len.ensure(ctx, (sr_len.size() + 1) * sizeof(uint32_t)));
+  MR_CUDA(ctx, cudaMemcpyAsync(idx->sr_len.p, sr_len.data(), sr_len.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
+}
+
+// bases [from, from + len) of a 2-bit text as a text of its own (base 0 at bit 0 of word 0)
+static void slice_text(const uint64_t* text, uint64_t from, uint64_t len, std::vector<uint64_t>& out) {
+  const uint64_t nwords = (len + 31) / 32, last = (from + len - 1) >> 5;
+  out.assign(nwords + 2, 0);
+  const uint64_t w0 = from >> 5;
+  const unsigned sh = (unsigned)(from & 31) * 2;
+  for(uint64_t i = 0; i < nwords; ++i) {
+    const uint64_t lo = text[w0 + i];
+    const uint64_t hi = (sh && w0 + i + 1 <= last) ? text[w0 + i + 1] : 0;
+    out[i] = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+  }
+  if(len & 31) out[nwords - 1] &= (1ULL << (2 * (len & 31))) - 1;
+}
+
+extern "C" {
+
+int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
+                    const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
+                    uint32_t n_unitigs, uint32_t psa_min, uint32_t k, mr_index** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!out || !text2bit || !sr_start || nseq == 0) return ctx->fail(MR_EINVAL, "mr_index_create: null argument");
+  if(!(psa_min >= 1 && psa_min < k && k <= 31))
+    return ctx->fail(MR_EINVAL, "mr_index_create: need 1 <= psa_min < mer <= 31");
+  if(psa_min > 15) return ctx->fail(MR_ELIMIT, "mr_index_create: psa_min > 15 (prefix table over 4 GiB) not supported");
+  if(k - psa_min > (uint32_t)kMaxShort) return ctx->fail(MR_ELIMIT, "mr_index_create: mer - psa_min > 16 not supported");
+  if(n < k) return ctx->fail(MR_EINVAL, "mr_index_create: text shorter than one k-mer");
+  if(sr_start[0] != 0 || sr_start[nseq] != n) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must span [0, n]");
+  if(nseq >= 0xfffffff0u) return ctx->fail(MR_ELIMIT, "mr_index_create: 2^32 super-reads or more not supported");
+  std::vector<uint32_t> sr_len(nseq);
+  for(uint32_t i = 0; i < nseq; ++i) {
+    if(sr_start[i + 1] <= sr_start[i]) return ctx->fail(MR_EINVAL, "mr_index_create: sr_start must be strictly increasing");
+    if(sr_start[i + 1] - sr_start[i] >= (1ULL << 31)) return ctx->fail(MR_ELIMIT, "mr_index_create: super-read of 2^31 bases or more");
+    sr_len[i] = (uint32_t)(sr_start[i + 1] - sr_start[i]);
+  }
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->timers.clear();
+  cudaStream_t st = ctx->stream;
+
+  // ---- parts (index.cuh): one unless the text has 2^32 bases or more ------------------------------
+  // MR_INDEX_PART_BASES lowers the limit (the tests force several parts on small inputs)
+  uint64_t part_limit = 0xfffffff0ULL - 64;
+  if(const char* e = getenv("MR_INDEX_PART_BASES")) { const uint64_t v = strtoull(e, nullptr, 0); if(v >= 1024 && v < part_limit) part_limit = v; }
+  const uint64_t ext_max = k - 1;
+  std::vector<uint32_t> cut;            // part p = super-reads [cut[p], cut[p + 1])
+  cut.push_back(0);
+  if(n + 0 > part_limit) {
+    const uint64_t nparts = (n + part_limit - ext_max - 1) / (part_limit - ext_max);
+    if(nparts > (uint64_t)kMaxParts) return ctx->fail(MR_ELIMIT, "mr_index_create: text too long (more than 4 index parts)");
+    for(uint64_t p = 1; p < nparts; ++p) {
+      const uint64_t target = n / nparts * p;
+      uint32_t i = (uint32_t)(std::lower_bound(sr_start, sr_start + nseq, target) - sr_start);
+      if(i <= cut.back()) i = cut.back() + 1;
+      if(i >= nseq) break;
+      cut.push_back(i);
+    }
+  }
+  cut.push_back(nseq);
+  const uint32_t P = (uint32_t)cut.size() - 1;
+
+  std::unique_ptr<mr_index> idx;
+  for(uint32_t p = 0; p < P; ++p) {
+    const uint64_t from = sr_start[cut[p]], own = sr_start[cut[p + 1]] - from;
+    const uint64_t ext = std::min<uint64_t>(ext_max, n - (from + own));
+    if(own + ext >= 0xfffffff0ULL || own + ext > part_limit + ext_max + (1ULL << 31))
+      return ctx->fail(MR_ELIMIT, "mr_index_create: cannot cut the super-reads into parts of fewer than 2^32 bases");
+    const uint32_t pseq = cut[p + 1] - cut[p];
+    mr_index* part = nullptr;
+    if(P == 1) {
+      MR_TRY(build_part(ctx, text2bit, n, sr_start, nseq, psa_min, k, &part));
+    } else {
+      std::vector<uint64_t> ptext, pstart(pseq + 1);
+      slice_text(text2bit, from, own + ext, ptext);
+      for(uint32_t i = 0; i <= pseq; ++i) pstart[i] = sr_start[cut[p] + i] - from;
+      MR_TRY(build_part(ctx, ptext.data(), own + ext, pstart.data(), pseq, psa_min, k, &part));
+    }
+    part->view.sr_base = cut[p];
+    part->view.nseq_all = nseq;
+    if(p == 0) idx.reset(part); else idx->more.push_back(part);
+  }
+  idx->n_all = n; idx->nseq_all = nseq;
+  MR_TRY(finish_single_part(idx.get(), sr_len));
+  if(P > 1) {
+    std::vector<index_view> views(P - 1);
+    for(uint32_t p = 1; p < P; ++p) views[p - 1] = idx->more[p - 1]->view;
+    MR_TRY(idx->more_views.ensure(ctx, views.size() * sizeof(index_view)));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->more_views.p, views.data(), views.size() * sizeof(index_view), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+
+  if(unitig_ids && unitig_off && unitig_len && n_unitigs) {
+    idx->has_unitigs = true;
+    idx->n_unitigs = n_unitigs;
+    const uint64_t total = unitig_off[nseq];
+    idx->unitig_total = total;
+    MR_TRY(idx->unitig_ids.ensure(ctx, (total + 1) * sizeof(uint32_t)));
+    MR_TRY(idx->unitig_off.ensure(ctx, ((size_t)nseq + 1) * sizeof(uint64_t)));
+    MR_TRY(idx->unitig_len.ensure(ctx, (size_t)n_unitigs * sizeof(int32_t)));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_ids.p, unitig_ids, total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_off.p, unitig_off, ((size_t)nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaMemcpyAsync(idx->unitig_len.p, unitig_len, (size_t)n_unitigs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MR_CUDA(ctx, cudaStreamSynchronize(st));
   }
   idx->inputs_checksum = mr_inputs_checksum(text2bit, n, sr_start, nseq, unitig_ids, unitig_off, unitig_len, n_unitigs, psa_min, k);
   *out = idx.release();

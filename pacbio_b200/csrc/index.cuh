@@ -15,11 +15,28 @@
 //                                returns does not depend on it.  The reference's 4^m + 1 table is
 //                                recomputed on demand for the parity tap (mr_index_export_counts).
 //   sr_start uint32[nseq+1], blk uint32[(n>>8)+2]: blk[b] = sequence containing base b*256
+//
+// Texts of 2^32 bases or more (BASELINE configs[3], human-size): the super-reads are cut, at
+// super-read boundaries, into up to kMaxParts PARTS of fewer than 2^32 bases; every part is a
+// complete index of the kind above over its own text (positions, ranks and counts stay 32 bit, the
+// lookup kernels are the same) and a k-mer's list is the concatenation of its per-part lists.
+// What makes that identical to one suffix array over the whole text:
+//   * a super-read lies in exactly one part and the order of a part's suffix array restricted to
+//     one super-read is the order of the global one (same keys, positions shifted by a constant),
+//     so every (read, super-read, strand) hit list comes out in the reference's order;
+//   * the list size the count filters see (coarse_aligner.cc:108-125) is the sum over the parts.
+//     The global suffix array also matches k-mers that straddle two consecutive super-reads (they
+//     count, and are dropped later by pos_iterator): a part's text is therefore extended by the
+//     first k-1 bases of the next part, so these positions keep their k-mer; the extension's own
+//     positions are suffixes shorter than k inside the part, which never match, and are counted by
+//     the next part, where they are ordinary positions.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 constexpr int kBlkShift  = 8;
 constexpr int kMaxShort  = 16;    // k - m <= 16 (tails are 32 bit)
+constexpr int kMaxParts  = 4;     // parts of one index (texts up to ~2^34 bases)
 
 struct index_view {
   const uint32_t* __restrict__ counts;
@@ -29,6 +46,8 @@ struct index_view {
   const uint32_t* __restrict__ blk;
   uint64_t n;
   uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort;
+  uint32_t sr_base;                // global index of this part's first super-read (0 for a one-part index)
+  uint32_t nseq_all;               // super-reads of the whole index (== nseq for a one-part index)
   uint64_t short_key[kMaxShort];   // padded k-mers of the tail-short suffixes (positions n-k+1 .. n-m)
 };
 
@@ -42,6 +61,15 @@ struct mr_index {
   dev_buf  text, sa, tails, counts, sr_start, blk;
   dev_buf  unitig_ids, unitig_off, unitig_len, sr_nunitigs;
   index_view view;
+  // whole-index tables (a one-part index: the part is the index itself)
+  uint64_t n_all = 0;                // bases of all super-reads
+  uint32_t nseq_all = 0;             // number of super-reads
+  dev_buf  sr_len;                   // uint32[nseq_all]: length of every super-read, by global index
+  std::vector<mr_index*> more;       // parts 1 .. P-1 (owned); part 0 is this object
+  dev_buf  more_views;               // index_view[P-1] on the device, for the kernels that walk the parts
+  uint32_t nparts() const { return 1 + (uint32_t)more.size(); }
+  const index_view& part_view(uint32_t p) const { return p == 0 ? view : more[p - 1]->view; }
+  ~mr_index() { for(mr_index* m_ : more) delete m_; }
 };
 
 // counts[p], counts[p + 1] with one 16-byte load (plus a 4-byte one when p % 4 == 3): the two

@@ -73,7 +73,9 @@ def data_files(args):
                                        "--sr-cov", str(w["sr_cov"]), "--repeat-frac", str(w["repeat_frac"]),
                                        "--unitig-k", str(w["unitig_k"]), "--threads", str(min(16, os.cpu_count() or 1)),
                                        "--prefix", prefix])
-        open(done, "w").write(out.decode())
+        with open(done + ".tmp", "w") as f:                 # atomically: the other ranks poll for this file
+            f.write(out.decode())
+        os.replace(done + ".tmp", done)
     while not os.path.exists(done):
         time.sleep(0.5)
     info = json.loads(open(done).read())

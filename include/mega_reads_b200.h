@@ -68,7 +68,14 @@ int  mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n,
                      const int32_t* unitig_len, uint32_t n_unitigs,
                      uint32_t psa_min, uint32_t k, mr_index** out);
 void mr_index_destroy(mr_index* idx);
-uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min + 1 */
+uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min + 1 (of the first part) */
+/* A text of 2^32 bases or more (the reference switches to its 48-bit suffix array there,
+ * src_psa/48bit_index.hpp) is indexed as several PARTS of fewer than 2^32 bases, cut at super-read
+ * boundaries; mr_align_batch gives the same rows either way.  The calls that speak in ranks of one
+ * suffix array (mr_index_export_*, mr_lookup_batch*, mr_index_save) return MR_ELIMIT for an index
+ * of several parts, and so does the fine pass (mr_params.fine_mer != 0).
+ * Environment: MR_INDEX_PART_BASES=<n> lowers the part limit (tests). */
+uint32_t mr_index_parts(const mr_index* idx);
 /* parity taps: suffix-array values in SA order and the 4^psa_min + 1 prefix counts
  * (mer_sa_imp.hpp:317-330), widened to 64 bit */
 int  mr_index_export_sa(mr_index* idx, uint64_t* sa_out);

@@ -81,6 +81,8 @@ def lib():
     L.mr_index_checksum.argtypes = [C.c_void_p]
     L.mr_inputs_checksum.restype = C.c_uint64
     L.mr_inputs_checksum.argtypes = [u64p, C.c_uint64, u64p, C.c_uint32, u32p, u64p, i32p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.mr_index_parts.restype = C.c_uint32
+    L.mr_index_parts.argtypes = [C.c_void_p]
     L.mr_index_sa_size.restype = C.c_uint64
     L.mr_index_sa_size.argtypes = [C.c_void_p]
     L.mr_index_export_sa.argtypes = [C.c_void_p, u64p]
@@ -312,6 +314,9 @@ class Index:
 
     def checksum(self):
         return int(self.ctx.L.mr_index_checksum(self.h))
+
+    def parts(self):
+        return int(self.ctx.L.mr_index_parts(self.h))
 
     def sa(self):
         out = np.empty(self.ctx.L.mr_index_sa_size(self.h), dtype=np.uint64)

@@ -182,7 +182,11 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // (coarse_aligner.cc:93-102), looks up both strands (superread_parser.hpp:183-192 ->
 // mer_sa_imp.hpp:369-479) and applies the max-count filter (coarse_aligner.cc:108-111).
 // rec[g] = {index(m), nb(m), index(rm), nb(rm)}; size[g] = nb(m)+nb(rm) or 0 when there is no list.
-__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, const char* __restrict__ bases,
+// kMulti (index of several parts, index.cuh): one launch per part, each with its own rec array;
+// size[g] accumulates the per-part list sizes over the launches (part_flags bit 0: first part,
+// bit 1: last part) and the max-count filter is applied to the sum by the last one.
+template<bool kMulti>
+__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, uint32_t part_flags, const char* __restrict__ bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
@@ -261,15 +265,25 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
         }
       }
       const uint32_t total = nb[0] + nb[1];
-      if(total != 0 && !(max_count && total >= max_count)) {
+      if(kMulti) {
+        out = make_uint4(idx[0], nb[0], idx[1], nb[1]);
+        sz = total;
+      } else if(total != 0 && !(max_count && total >= max_count)) {
         out = make_uint4(idx[0], nb[0], idx[1], nb[1]);
         sz = total;
       }
     }
     const uint32_t pos = tpos + threadIdx.x * 4 + j;
     // streaming stores (evict-first): the 20 B/base of output must not push the index tables out of L2
-    if(pos < rlen) { __stcs(rec + g0 + j, out); __stcs(size + g0 + j, sz); }
+    if(pos < rlen) {
+      if(kMulti) {
+        if(!(part_flags & 1)) sz += size[g0 + j];
+        if((part_flags & 2) && max_count && sz >= max_count) sz = 0;
+      }
+      __stcs(rec + g0 + j, out); __stcs(size + g0 + j, sz);
+    }
   }
+  if(kMulti && !(part_flags & 1)) nlook = 0;          // a k-mer is counted once, not once per part
   if(nlook) atomicAdd(&looked, nlook);
   if(ntail) atomicAdd(&scanned, ntail);
   __syncthreads();
@@ -343,10 +357,10 @@ __device__ __forceinline__ void emit_hit(const index_view& iv, uint32_t read, ui
   uint32_t sr, off;
   if(index_locate(iv, x, sr, off)) {
     const int32_t soff = minus ? -(int32_t)off : (int32_t)off;
-    keys[slot] = ((uint64_t)read << 32) | sr;
+    keys[slot] = ((uint64_t)read << 32) | (iv.sr_base + sr);
     pays[slot] = (uint64_t)pb_off | ((uint64_t)(uint32_t)soff << 32);
   } else {
-    keys[slot] = ((uint64_t)read << 32) | iv.nseq;
+    keys[slot] = ((uint64_t)read << 32) | iv.nseq_all;
     pays[slot] = 0;
     ++n_bad;
   }
@@ -374,7 +388,12 @@ __global__ void __launch_bounds__(kSeedThreads) tile_hits_kernel(const uint64_t*
   if(threadIdx.x == 0) tile_hits[blockIdx.x] = (uint32_t)total;
 }
 
-__global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, const uint64_t* __restrict__ read_start,
+// kMulti: rec holds one array per part, rec_stride entries apart; a list is the concatenation of its
+// per-part lists (forward then backward entries of part 0, of part 1, ...), more_views[p - 1] is
+// the view of part p.
+template<bool kMulti>
+__global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, const index_view* __restrict__ more_views, uint32_t nparts,
+                                                               uint64_t rec_stride, const uint64_t* __restrict__ read_start,
                                                                const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
                                                                const uint64_t* __restrict__ tile_off,
@@ -408,8 +427,20 @@ __global__ void __launch_bounds__(kSeedThreads) expand_kernel(index_view iv, con
     for(uint32_t h = threadIdx.x; h < (uint32_t)in_iter; h += kSeedThreads) {
       uint32_t lo = 0, hi = kSeedThreads;
       while(hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if(s_off[mid] <= h) lo = mid; else hi = mid; }
-      const uint4 c = s_rec[lo];
-      const uint32_t j = h - s_off[lo];
+      uint4 c = s_rec[lo];
+      uint32_t j = h - s_off[lo];
+      if(kMulti) {
+        uint32_t part = 0;
+        while(j >= c.y + c.w && part + 1 < nparts) {       // the list continues in the next part
+          j -= c.y + c.w;
+          ++part;
+          c = __ldg(rec + part * rec_stride + rs + tpos + it * kSeedThreads + lo);
+        }
+        const bool minus = j >= c.y;
+        emit_hit(part ? more_views[part - 1] : iv, r, tpos + it * kSeedThreads + lo + 1, minus ? c.z + (j - c.y) : c.x + j, minus,
+                 run + h, keys, pays, n_bad);
+        continue;
+      }
       const bool minus = j >= c.y;
       emit_hit(iv, r, tpos + it * kSeedThreads + lo + 1, minus ? c.z + (j - c.y) : c.x + j, minus, run + h, keys, pays, n_bad);
     }
@@ -910,7 +941,9 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY(ws.tile_tbase.ensure(ctx, ((size_t)ntiles + 1) * 4));
   MR_TRY(ws.counters.ensure(ctx, 16 * sizeof(uint64_t)));
   MR_TRY(ws.size.ensure(ctx, (T + 4) * 4));
-  MR_TRY(ws.rec.ensure(ctx, (T + 4) * 16));
+  const uint32_t nparts = idx->nparts();
+  const uint64_t rec_stride = T + 4;
+  MR_TRY(ws.rec.ensure(ctx, rec_stride * 16 * nparts));
   MR_TRY(ws.hit_off.ensure(ctx, ((size_t)ntiles + 4) * 8));
   MR_TRY(ws.thr.ensure(ctx, ((size_t)nreads + 1) * 4));
   MR_CUDA(ctx, cudaMemcpyAsync(ws.tile_first.p, tile_first.data(), ((size_t)nreads + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -937,10 +970,20 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       MR_LAUNCHED(ctx);
     }
     timer.next("seed lookup");
-    seed_lookup_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                      ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                                      ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
-    MR_LAUNCHED(ctx);
+    if(nparts == 1) {
+      seed_lookup_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                               ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                                               ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
+      MR_LAUNCHED(ctx);
+    } else {
+      for(uint32_t part = 0; part < nparts; ++part) {
+        seed_lookup_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(idx->part_view(part), (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
+                                                                d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                                ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                                                ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
+        MR_LAUNCHED(ctx);
+      }
+    }
     timer.next("count threshold");
     uint32_t nbits = 32;
     if(p->max_count > 1) { nbits = 0; while((1u << nbits) < (uint32_t)p->max_count) ++nbits; }
@@ -976,13 +1019,19 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   if(H) {
     MR_TRY(ws.key0.ensure(ctx, (H + 2) * 8)); MR_TRY(ws.key1.ensure(ctx, (H + 2) * 8));
     MR_TRY(ws.pay0.ensure(ctx, (H + 2) * 8)); MR_TRY(ws.pay1.ensure(ctx, (H + 2) * 8));
-    expand_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                 ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ws.hit_off.as<uint64_t>(),
-                                                 ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
+    if(nparts == 1)
+      expand_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, nullptr, 1, 0, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ws.hit_off.as<uint64_t>(),
+                                                          ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
+    else
+      expand_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(iv, idx->more_views.as<index_view>(), nparts, rec_stride, d_read_start,
+                                                         ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                         ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ws.hit_off.as<uint64_t>(),
+                                                         ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
     MR_LAUNCHED(ctx);
     timer.next("group sort");
     int sr_bits = 1;
-    while((1ULL << sr_bits) <= (uint64_t)iv.nseq) ++sr_bits;
+    while((1ULL << sr_bits) <= (uint64_t)iv.nseq_all) ++sr_bits;
     bool in_first = true;
     MR_TRY((prim::radix_sort_pairs<uint64_t, uint64_t>(ctx, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ws.key1.as<uint64_t>(),
                                                        ws.pay1.as<uint64_t>(), H, 0, sr_bits, ws.sort, &in_first)));
@@ -991,7 +1040,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     uint64_t* alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
     uint64_t* alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
     // group heads -> group_start
-    MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
+    MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));
     G = h_ctr[3];
@@ -1000,7 +1049,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     res->view.n_hits = Hvalid;
     res->view.n_groups = G;
     MR_TRY(ws.group_start.ensure(ctx, (G + 2) * 8));
-    MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
+    MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
     MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &Hvalid, 8, cudaMemcpyHostToDevice, st));
     MR_CUDA(ctx, cudaStreamSynchronize(st));   // Hvalid is a stack variable
 
@@ -1008,7 +1057,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     timer.next("chain coords");
     MR_TRY(ws.chainL.ensure(ctx, (H + 2) * 16));
     MR_TRY(ws.read_cnt.ensure(ctx, ((size_t)nreads + 2) * 4));
-    A.iv = iv; A.keys = skeys; A.pays = spays; A.group_start = ws.group_start.as<uint64_t>(); A.ngroups = G;
+    A.iv = iv; A.sr_len = idx->sr_len.as<uint32_t>(); A.keys = skeys; A.pays = spays; A.group_start = ws.group_start.as<uint64_t>(); A.ngroups = G;
     A.read_start = d_read_start;
     {
       char* c = (char*)ws.chainL.p;
@@ -1081,7 +1130,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                         fb.gsr.as<uint32_t>(), fb.giter.as<uint32_t>());
     MR_LAUNCHED(ctx);
     int sr_bits = 1, read_bits = 1;
-    while((1ULL << sr_bits) <= (uint64_t)iv.nseq) ++sr_bits;
+    while((1ULL << sr_bits) <= (uint64_t)iv.nseq_all) ++sr_bits;
     while((1ULL << read_bits) <= (uint64_t)nreads) ++read_bits;
     bool first = true;
     MR_TRY((prim::radix_sort_pairs<uint64_t, uint32_t>(ctx, fb.wkey0.as<uint64_t>(), fb.wrow0.as<uint32_t>(), fb.wkey1.as<uint64_t>(),
@@ -1264,6 +1313,8 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
   if(p->fine_mer && (p->fine_mer < idx->m || p->fine_mer > idx->k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the fine mer must lie between the psa_min and the mer length the index was built with "
                                 "(the reference builds its suffix array with min(fine mer, psa-min), create_mega_reads.cc:131-132)");
+  if(p->fine_mer && idx->nparts() > 1)
+    return ctx->fail(MR_ELIMIT, "mr_align_batch: the fine pass is not implemented for an index of several parts (text of 2^32 bases or more)");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -90,6 +90,7 @@ struct survivors {
 
 struct chain_args {
   index_view iv;
+  const uint32_t* sr_len;            // length of every super-read, by global index (all parts)
   const uint64_t* keys; const uint64_t* pays; const uint64_t* group_start; uint64_t ngroups;
   const uint64_t* read_start;
   chain_buffers cb;

@@ -348,7 +348,7 @@ __device__ __forceinline__ bool publish_coords(const chain_args& A, uint64_t gs,
                                                uint32_t nb, const coords_acc& c, double stretch, double offset, double avg_err,
                                                uint32_t iter = 0) {
   const uint32_t k = A.align_k ? A.align_k : A.iv.k;
-  const uint32_t ql = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr];
+  const uint32_t ql = A.sr_len[sr];
   const uint32_t rl = (uint32_t)(A.read_start[read + 1] - A.read_start[read]);
   int32_t rs = c.first_pb, re = c.ppb + (int32_t)k - 1, qs = c.first_sr, qe = c.psr;
   bool rn = false;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void publish_empty(const chain_args& A, uint64_t gs, 
   if(slot < sv.cap) {
     sv.rs[slot] = 0; sv.re[slot] = 0; sv.qs[slot] = 0; sv.qe[slot] = 0; sv.nb_mers[slot] = 0;
     sv.pb_cons[slot] = 0; sv.sr_cons[slot] = 0; sv.pb_cover[slot] = k; sv.sr_cover[slot] = k;
-    sv.ql[slot] = A.iv.sr_start[sr + 1] - A.iv.sr_start[sr]; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = 0;
+    sv.ql[slot] = A.sr_len[sr]; sv.sr[slot] = sr; sv.read[slot] = read; sv.info_len[slot] = 0;
     sv.rn[slot] = 0; sv.use_bwd[slot] = 0;
     sv.stretch[slot] = 0; sv.offset[slot] = 0; sv.avg_err[slot] = 0;
     sv.chain_pos[slot] = gs;

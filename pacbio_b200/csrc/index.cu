@@ -3,6 +3,7 @@
 // histogram, partial sums, atomic scatter, 4^m std::sort calls) by one stable LSD radix sort of
 // (padded k-mer, position) pairs seeded in descending position order, and PSA::search
 // (mer_sa_imp.hpp:369-479) by a prefix-table probe plus a scan of the bucket's tails.
+#include <cstdio>
 #include <cstdlib>
 #include "index.cuh"
 #include "primitives.cuh"
@@ -334,6 +335,11 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     if(p == 0) idx.reset(part); else idx->more.push_back(part);
   }
   idx->n_all = n; idx->nseq_all = nseq;
+  if(getenv("MR_TRACE")) {
+    fprintf(stderr, "[mr] index parts: %u (", P);
+    for(uint32_t p = 0; p < P; ++p) fprintf(stderr, "%s%llu", p ? " + " : "", (unsigned long long)(sr_start[cut[p + 1]] - sr_start[cut[p]]));
+    fprintf(stderr, " bases)\n");
+  }
   MR_TRY(finish_single_part(idx.get(), sr_len));
   if(P > 1) {
     std::vector<index_view> views(P - 1);
@@ -368,6 +374,7 @@ void mr_index_destroy(mr_index* idx) {
 }
 
 uint64_t mr_index_sa_size(const mr_index* idx) { return idx ? idx->nsa : 0; }
+uint32_t mr_index_parts(const mr_index* idx) { return idx ? idx->nparts() : 0; }
 
 static int export_widened(mr_index* idx, const uint32_t* d_in, uint64_t count, uint64_t* h_out) {
   mr_context* ctx = idx->ctx;
@@ -381,13 +388,19 @@ static int export_widened(mr_index* idx, const uint32_t* d_in, uint64_t count, u
   return MR_OK;
 }
 
+// The taps and PSA::search below speak in ranks of ONE suffix array: they are defined for a
+// one-part index (every text below 2^32 bases).
+#define MR_ONE_PART(idx, what) do { if((idx)->nparts() > 1) return (idx)->ctx->fail(MR_ELIMIT, what ": not defined for an index of several parts (text of 2^32 bases or more)"); } while(0)
+
 int mr_index_export_sa(mr_index* idx, uint64_t* sa_out) {
   if(!idx || !sa_out) return MR_EINVAL;
+  MR_ONE_PART(idx, "mr_index_export_sa");
   return export_widened(idx, idx->sa.as<uint32_t>(), idx->nsa, sa_out);
 }
 
 int mr_index_export_counts(mr_index* idx, uint64_t* counts_out) {
   if(!idx || !counts_out) return MR_EINVAL;
+  MR_ONE_PART(idx, "mr_index_export_counts");
   mr_context* ctx = idx->ctx;
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   // the reference's table is over psa_min bases; ours is over mi <= psa_min: rebuild it from the text
@@ -411,6 +424,7 @@ int mr_index_export_counts(mr_index* idx, uint64_t* counts_out) {
 
 int mr_lookup_batch_device(mr_index* idx, const uint64_t* d_mers, uint64_t q, uint64_t* d_index_out, uint64_t* d_nb_out) {
   if(!idx) return MR_EINVAL;
+  MR_ONE_PART(idx, "mr_lookup_batch");
   mr_context* ctx = idx->ctx;
   if(q == 0) return MR_OK;
   MR_CUDA(ctx, cudaSetDevice(ctx->device));

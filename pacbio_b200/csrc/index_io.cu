@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <vector>
+
+int finish_single_part(mr_index* idx, const std::vector<uint32_t>& sr_len);   // index.cu
 
 namespace {
 
@@ -85,6 +88,7 @@ uint64_t mr_index_checksum(const mr_index* idx) { return idx ? idx->inputs_check
 int mr_index_save(mr_index* idx, const char* path) {
   if(!idx || !path) return MR_EINVAL;
   mr_context* ctx = idx->ctx;
+  if(idx->nparts() > 1) return ctx->fail(MR_ELIMIT, "mr_index_save: an index of several parts (text of 2^32 bases or more) has no file format yet");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   std::unique_ptr<FILE, file_closer> f(fopen(path, "wb"));
   if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_save: cannot open ") + path);
@@ -165,7 +169,15 @@ int mr_index_load(mr_context* ctx, const char* path, mr_index** out) {
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
   v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
   v.nshort = h.nshort;
+  v.sr_base = 0; v.nseq_all = h.nseq;
   memcpy(v.short_key, h.short_key, sizeof h.short_key);
+  idx->n_all = h.n; idx->nseq_all = h.nseq;
+  {                                            // super-read lengths from the starts just loaded
+    std::vector<uint32_t> st(h.nseq + 1), len(h.nseq);
+    MR_CUDA(ctx, cudaMemcpy(st.data(), idx->sr_start.p, ((size_t)h.nseq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for(uint32_t i = 0; i < h.nseq; ++i) len[i] = st[i + 1] - st[i];
+    MR_TRY(finish_single_part(idx.get(), len));
+  }
   *out = idx.release();
   return MR_OK;
 }

@@ -96,6 +96,26 @@ def test_reference_generated_fixtures(tmpdir_session, tmp_path, name):
     assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
 
 
+@pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
+def test_index_of_several_parts_reproduces_the_reference_fixtures(tmpdir_session, tmp_path, name):
+    """The route for super-read sets of 2^32 bases or more (several index parts), forced on the
+    fixture inputs: same bytes as the reference's file."""
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    cfg = meta["config"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    nbases = sum(len(l) - 1 for l in open(info["sr"]) if not l.startswith(">"))
+    env = dict(os.environ, MR_INDEX_PART_BASES=str(max(1024, nbases // 3 + 1000)), MR_TRACE="1")
+    common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+              "-r", info["sr"], "-p", info["reads"]]
+    out_u = str(tmp_path / "cmr_u.txt")
+    r = run([CMR] + common + ["-u", info["unitigs"], "-t", "2", "-o", out_u], env=env)
+    assert b"index parts: 3" in r.stderr or b"index parts: 4" in r.stderr, r.stderr.decode()[-500:]
+    assert sha(open(out_u, "rb").read()) == meta["cmr_with_sequences_sha256_t1"]
+    out_c = str(tmp_path / "coords.txt")
+    run([JFA] + common + ["-l", info["unitigs_len"], "-H", "--coords", out_c], env={k_: v_ for k_, v_ in env.items() if k_ != "MR_TRACE"})
+    assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
+
+
 FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}   # as in make_golden.py
 
 

@@ -212,6 +212,51 @@ def test_staged_batches_give_the_same_rows(case, ctx):
     ctx.L.mr_staged_free(s3)
 
 
+@pytest.mark.parametrize("max_count", [5000, 3])
+def test_index_of_several_parts_gives_the_same_lists_and_rows(case, ctx, max_count):
+    """A text of 2^32 bases or more is indexed as several parts (index.cuh); MR_INDEX_PART_BASES forces
+    that on a small input.  Hit lists, chains, rows and graph must not depend on the cut -- including
+    the list sizes the count filters see (k-mers straddling two super-reads at a cut, max-count on the
+    sum over the parts)."""
+    import pacbio_b200 as pb
+    c = case["cfg"]
+    sr = case["sr"]
+    assert case["idx"].parts() == 1
+    os.environ["MR_INDEX_PART_BASES"] = str(max(1024, int(sr.n / 3.3)))
+    try:
+        idx = ctx.index(sr, c["m"], c["k"], unitig_len=case["ul"])
+    finally:
+        del os.environ["MR_INDEX_PART_BASES"]
+    try:
+        assert idx.parts() in (3, 4)
+        reads = pb.Reads(case["info"]["reads"])
+        names, seqs = read_fasta(case["info"]["reads"])
+        _, srs = read_fasta(case["info"]["sr"])
+        # reads that are super-read junctions: their k-mers straddle two consecutive super-reads
+        seqs = seqs[:80] + [srs[i][-200:] + srs[i + 1][:200] for i in range(0, len(srs) - 1, max(1, len(srs) // 40))]
+        sub = pb.Reads(names=["r%d" % i for i in range(len(seqs))], seqs=seqs)
+        p = pb.default_params(unitigs_k=c["uk"], run_graph=1)
+        p.max_count = max_count
+        out = []
+        for ix in (case["idx"], idx):
+            ctx.keep_taps(True)
+            out.append(ctx.align(ix, sub, p))
+            ctx.keep_taps(False)
+        want, got = out
+        assert want.ncoords > 20 or max_count < 10
+        for f in ("tap_groups", "tap_offsets", "tap_lis"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), f
+        assert got.ncoords == want.ncoords
+        for f in ("rs", "re", "qs", "qe", "nb_mers", "pb_cons", "sr_cons", "pb_cover", "sr_cover", "ql", "rn", "sr", "use_bwd",
+                  "stretch", "offset", "avg_err", "info_len", "lpath", "lprev", "lstart", "lunitigs", "component"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), f
+        # what is defined for one suffix array only says so
+        with pytest.raises(Exception):
+            idx.sa()
+    finally:
+        idx.close()
+
+
 def test_shared_reciprocal_division_is_exact(ctx):
     """div_by_count (chain.cu) must equal IEEE x / n bit for bit: 2^30 random operands."""
     import ctypes as C

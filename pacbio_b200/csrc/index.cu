@@ -163,7 +163,7 @@ static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k)
 // extension described in index.cuh).
 static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
                       uint32_t psa_min, uint32_t k, mr_index** out) {
-  if(n >= 0xfffffff0ULL) return ctx->fail(MR_ELIMIT, "mr_index_create: index part of 2^32 bases or more");
+  if(n > 0xff000000ULL + 64) return ctx->fail(MR_ELIMIT, "mr_index_create: index part of 2^32 bases or more");
   phase_timer timer(ctx);
 
   std::unique_ptr<mr_index> idx(new mr_index);
@@ -295,7 +295,8 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
 
   // ---- parts (index.cuh): one unless the text has 2^32 bases or more ------------------------------
   // MR_INDEX_PART_BASES lowers the limit (the tests force several parts on small inputs)
-  uint64_t part_limit = 0xfffffff0ULL - 64;
+  // 2^32 - 2^24: grid-stride loops over 32-bit ranks must not wrap
+  uint64_t part_limit = 0xff000000ULL;
   if(const char* e = getenv("MR_INDEX_PART_BASES")) { const uint64_t v = strtoull(e, nullptr, 0); if(v >= 1024 && v < part_limit) part_limit = v; }
   const uint64_t ext_max = k - 1;
   std::vector<uint32_t> cut;            // part p = super-reads [cut[p], cut[p + 1])
@@ -318,7 +319,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
   for(uint32_t p = 0; p < P; ++p) {
     const uint64_t from = sr_start[cut[p]], own = sr_start[cut[p + 1]] - from;
     const uint64_t ext = std::min<uint64_t>(ext_max, n - (from + own));
-    if(own + ext >= 0xfffffff0ULL || own + ext > part_limit + ext_max + (1ULL << 31))
+    if(own + ext > 0xff000000ULL + 64)
       return ctx->fail(MR_ELIMIT, "mr_index_create: cannot cut the super-reads into parts of fewer than 2^32 bases");
     const uint32_t pseq = cut[p + 1] - cut[p];
     mr_index* part = nullptr;
@@ -335,7 +336,7 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     if(p == 0) idx.reset(part); else idx->more.push_back(part);
   }
   idx->n_all = n; idx->nseq_all = nseq;
-  if(getenv("MR_TRACE")) {
+  if(getenv("MR_TRACE") || (P > 1 && getenv("MR_SHOW_TIMING"))) {
     fprintf(stderr, "[mr] index parts: %u (", P);
     for(uint32_t p = 0; p < P; ++p) fprintf(stderr, "%s%llu", p ? " + " : "", (unsigned long long)(sr_start[cut[p + 1]] - sr_start[cut[p]]));
     fprintf(stderr, " bases)\n");

@@ -473,10 +473,28 @@ def ours(args, w, files):
                 traffic = prof["dram_bytes_per_launch"]
         except Exception:
             pass
+        # the ceiling this kernel lives under: random 32-byte sectors per second, measured
+        # here with a pointer-chase-free gather (mr_selftest_random_gather) over a table far larger than
+        # the L2 and over one of the size of this index's lookup tables
+        rnd = None
+        try:
+            g1, g2 = C.c_double(), C.c_double()
+            tbl = int((4 ** 12 + 1) * 4 + H.mrh_tool_sr_bases(tool))       # prefix table + 8-bit tails of this index
+            if L.mr_selftest_random_gather(ctx, 1 << 30, 1 << 28, C.byref(g1)) == 0 and \
+               L.mr_selftest_random_gather(ctx, tbl, 1 << 28, C.byref(g2)) == 0:
+                rnd = {"hbm_table_1GiB": g1.value, "index_sized_table": g2.value, "index_sized_table_bytes": tbl, "unit": "GB/s",
+                       "how": "2^28 independent 16-byte loads at random 16-byte-aligned places, 8 in flight per thread, "
+                              "sectors x 32 B / best of 3 launches (mr_selftest_random_gather)"}
+        except Exception:
+            pass
         roof = {"kernel": "seed_lookup_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg / launches_k, "avg_launch_ms": 1e3 * phase[kern] / launches_k,
                 "share_of_step": phase[kern] / sum(phase.values()),
+                "random_sector_peak": rnd,
+                "dram_gbs_from_traffic": (traffic / (phase[kern] / launches_k) / 1e9) if traffic else None,
+                "frac_of_random_sector_peak": (traffic / (phase[kern] / launches_k) / 1e9 / rnd["hbm_table_1GiB"])
+                if traffic and rnd and rnd["hbm_table_1GiB"] > 0 else None,
                 "note": "random 32-byte-sector gathers into a 268 MB prefix table and the tail array: bounded by "
                         "random-access sector throughput, not by streaming bandwidth; with streams_per_gpu > 1 the launch runs next to "
                         "the other stream's kernels, so avg_launch_ms is its duration while sharing the GPU; the chaining kernels "

@@ -211,6 +211,13 @@ int  mr_result_taps(const mr_result* r, uint64_t* ngroups, const int64_t** group
  * many quotients differ, bit for bit, from the IEEE division the reference executes (must be 0). */
 int  mr_selftest_division(mr_context* ctx, uint64_t samples, uint64_t seed, uint32_t max_n, uint64_t* mismatches);
 
+/* measurement aid: the random 32-byte-sector ceiling of this GPU, the denominator the
+ * k-mer lookup is judged against.  `loads` independent 16-byte loads (8 in flight per thread, no
+ * pointer chasing) at uniformly random 16-byte-aligned places of a table of table_bytes; reports
+ * sectors x 32 B per second of the best of three launches, in GB/s.  A table much larger than the
+ * 126 MB L2 gives the HBM figure, a table of the index's size what the L2 adds. */
+int  mr_selftest_random_gather(mr_context* ctx, uint64_t table_bytes, uint64_t loads, double* sector_gbs);
+
 #ifdef __cplusplus
 }
 #endif

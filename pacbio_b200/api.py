@@ -81,6 +81,8 @@ def lib():
     L.mr_index_checksum.argtypes = [C.c_void_p]
     L.mr_inputs_checksum.restype = C.c_uint64
     L.mr_inputs_checksum.argtypes = [u64p, C.c_uint64, u64p, C.c_uint32, u32p, u64p, i32p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.mr_selftest_random_gather.restype = C.c_int
+    L.mr_selftest_random_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
     L.mr_index_parts.restype = C.c_uint32
     L.mr_index_parts.argtypes = [C.c_void_p]
     L.mr_index_sa_size.restype = C.c_uint64

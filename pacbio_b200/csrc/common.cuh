@@ -30,6 +30,8 @@ struct mr_context {
   bool         chain_tables = false;   // constant tables of chain.cu uploaded to this device
   std::vector<std::pair<std::string, double>> timers;
   int          sm_count = kNumSMs;
+  // L2 persistence (context.cu): bytes of L2 set aside for persisting lines, largest access-policy window
+  size_t       l2_persist_bytes = 0, l2_window_max = 0;
 
   int fail(int code, const std::string& msg) { err = msg; return code; }
 };
@@ -63,13 +65,14 @@ extern thread_local std::string g_mr_create_error;
 struct dev_buf {
   void*  p = nullptr;
   size_t cap = 0;
-  ~dev_buf() { if(p) cudaFree(p); }
+  bool   owned = true;          // false: p points into another buffer (alias), never freed here
+  ~dev_buf() { if(p && owned) cudaFree(p); }
   dev_buf() = default;
   dev_buf(const dev_buf&) = delete;
   dev_buf& operator=(const dev_buf&) = delete;
   int ensure(mr_context* ctx, size_t bytes) {
     if(bytes <= cap) return MR_OK;
-    if(p) { cudaFree(p); p = nullptr; cap = 0; }
+    release();
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if(e != cudaSuccess) {
@@ -87,7 +90,8 @@ struct dev_buf {
     cap = want;
     return MR_OK;
   }
-  void release() { if(p) { cudaFree(p); p = nullptr; cap = 0; } }
+  void release() { if(p && owned) cudaFree(p); p = nullptr; cap = 0; owned = true; }
+  void alias(void* q, size_t bytes) { release(); p = q; cap = bytes; owned = false; }
   template<typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

@@ -1,6 +1,7 @@
 // Context management for the C ABI: one context == one GPU == one stream.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -31,6 +32,17 @@ int mr_context_create(int device, mr_context** out) {
   std::unique_ptr<mr_context> ctx(new mr_context);
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  // L2 persistence for the lookup tables of an index (align.cu, seed lookup): the largest set-aside
+  // the device allows.  MR_L2_PERSIST=0 switches it off (A/B measurements).
+  {
+    const char* env = getenv("MR_L2_PERSIST");
+    if(!(env && atoi(env) == 0) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      if(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+        ctx->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+        ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      } else cudaGetLastError();
+    }
+  }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if(e != cudaSuccess) { g_mr_create_error = cudaGetErrorString(e); return MR_ECUDA; }
   for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);

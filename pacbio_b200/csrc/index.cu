@@ -114,6 +114,28 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
   }
 }
 
+// random-sector ceiling: every thread issues 8 independent 16-byte loads per round at hashed places
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256) random_gather_kernel(const uint4* __restrict__ table, uint64_t nelem, uint32_t rounds,
+                                                            uint32_t salt, uint32_t* __restrict__ sink) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc = 0;
+  for(uint32_t r = 0; r < rounds; ++r) {
+    uint4 v[8];
+#pragma unroll
+    for(int j = 0; j < 8; ++j) {
+      const uint64_t h = ((uint64_t)mix32((tid * 8u + j + salt) ^ mix32(r + 0x9e3779b9u)) << 32) | mix32((r + 1) * 0x9e3779b9u ^ (tid + j * 0x85ebca6bu));
+      v[j] = __ldg(table + (uint64_t)(((unsigned __int128)h * nelem) >> 64));
+    }
+#pragma unroll
+    for(int j = 0; j < 8; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+  }
+  if(acc == 0x12345678u) sink[0] = acc;          // keeps the loads alive
+}
+
 } // namespace
 
 // prefix table over `mp` bases (and, when tails != null, the tails) from the sorted keys
@@ -212,8 +234,8 @@ static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, con
     timer.next("partial sums");
     const uint64_t* keys = in_first ? k0.as<uint64_t>() : k1.as<uint64_t>();
     dev_buf& vres = in_first ? v0 : v1;
-    MR_TRY(idx->tails.ensure(ctx, ((size_t)nsa + 64) * tail_bytes));
-    MR_TRY(idx->counts.ensure(ctx, ((size_t)nprefix + 8) * sizeof(uint32_t)));   // read in 16-byte blocks
+    MR_TRY(idx->alloc_lut(ctx, ((size_t)nprefix + 8) * sizeof(uint32_t),       // counts are read in 16-byte blocks
+                          ((size_t)nsa + 64) * tail_bytes));
     MR_TRY(build_prefix_table(ctx, keys, nsa, k, mi, idx->tails.p, tail_bytes, idx->counts.as<uint32_t>()));
     // keep the sorted positions: steal the buffer that holds them
     MR_CUDA(ctx, cudaStreamSynchronize(st));
@@ -420,6 +442,36 @@ int mr_index_export_counts(mr_index* idx, uint64_t* counts_out) {
   MR_LAUNCHED(ctx);
   MR_CUDA(ctx, cudaMemcpyAsync(counts_out, tmp.p, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MR_OK;
+}
+
+int mr_selftest_random_gather(mr_context* ctx, uint64_t table_bytes, uint64_t loads, double* sector_gbs) {
+  if(!ctx) return MR_EINVAL;
+  if(!sector_gbs || table_bytes < 4096 || loads == 0) return ctx->fail(MR_EINVAL, "mr_selftest_random_gather: bad argument");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  dev_buf table, sink;
+  MR_TRY(table.ensure(ctx, table_bytes));
+  MR_TRY(sink.ensure(ctx, 64));
+  MR_CUDA(ctx, cudaMemsetAsync(table.p, 0x5a, table_bytes, ctx->stream));
+  const unsigned grid = ctx->sm_count * 8;
+  const uint64_t per_round = (uint64_t)grid * 256 * 8;
+  const uint32_t rounds = (uint32_t)std::max<uint64_t>(1, (loads + per_round - 1) / per_round);
+  cudaEvent_t a, b;
+  MR_CUDA(ctx, cudaEventCreate(&a)); MR_CUDA(ctx, cudaEventCreate(&b));
+  double best = 0.0;
+  for(int rep = 0; rep < 4; ++rep) {              // the first launch warms up
+    cudaEventRecord(a, ctx->stream);
+    random_gather_kernel<<<grid, 256, 0, ctx->stream>>>(table.as<uint4>(), table_bytes / 16, rounds, 977u * rep, sink.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    cudaEventRecord(b, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(b);
+    if(e != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); return ctx->fail(MR_ECUDA, cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if(rep && ms > 0) best = std::max(best, (double)rounds * per_round * 32.0 / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *sector_gbs = best;
   return MR_OK;
 }
 

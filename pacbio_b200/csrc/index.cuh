@@ -59,6 +59,18 @@ struct mr_index {
   uint64_t unitig_total = 0;         // entries of unitig_ids
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;
+  dev_buf  lut;                      // counts and tails live side by side in this one allocation, so that
+                                     // a single L2 access-policy window covers what a lookup reads
+  int alloc_lut(mr_context* c, size_t counts_bytes, size_t tails_bytes) {
+    const size_t off = (counts_bytes + 255) & ~(size_t)255;
+    const int rc = lut.ensure(c, off + tails_bytes);
+    if(rc != MR_OK) return rc;
+    counts.alias(lut.p, counts_bytes);
+    tails.alias((char*)lut.p + off, tails_bytes);
+    lut_bytes = off + tails_bytes;
+    return MR_OK;
+  }
+  size_t   lut_bytes = 0;
   dev_buf  unitig_ids, unitig_off, unitig_len, sr_nunitigs;
   index_view view;
   // whole-index tables (a one-part index: the part is the index itself)

@@ -148,6 +148,7 @@ int mr_index_load(mr_context* ctx, const char* path, mr_index** out) {
   pinned_buf stage[2];
   MR_TRY(stage[0].ensure(ctx, kChunk)); MR_TRY(stage[1].ensure(ctx, kChunk));
   int which = 0;
+  MR_TRY(idx->alloc_lut(ctx, s[3].bytes, s[2].bytes));
   for(uint32_t i = 0; i < kSections; ++i) {
     if(s[i].bytes == 0) continue;
     MR_TRY(s[i].buf->ensure(ctx, s[i].bytes));

@@ -257,6 +257,14 @@ def test_index_of_several_parts_gives_the_same_lists_and_rows(case, ctx, max_cou
         idx.close()
 
 
+def test_random_sector_ceiling_microkernel(ctx):
+    """mr_selftest_random_gather (bench.py's roofline denominator) runs and reports a plausible figure."""
+    import ctypes as C
+    g = C.c_double()
+    ctx.check(ctx.L.mr_selftest_random_gather(ctx.h, 256 << 20, 1 << 24, C.byref(g)))
+    assert 50.0 < g.value < 20000.0, g.value
+
+
 def test_shared_reciprocal_division_is_exact(ctx):
     """div_by_count (chain.cu) must equal IEEE x / n bit for bit: 2^30 random operands."""
     import ctypes as C

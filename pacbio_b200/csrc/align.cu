@@ -85,6 +85,8 @@ static int download_rows(mr_context* ctx, mr_workspace& ws, mr_result* res, cons
 
 
 static const bool g_trace = getenv("MR_TRACE") != nullptr;
+// MR_L2_HINT=1: table loads of the seed kernel carry the L2 evict_last hint (A/B switch)
+static const bool g_l2_hint = getenv("MR_L2_HINT") && atoi(getenv("MR_L2_HINT")) != 0;
 #define MR_TRACE_MSG(...) do { if(g_trace) { fprintf(stderr, "[mr] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while(0)
 
 // ------------------------------------------------------------------------------------------------
@@ -185,8 +187,9 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // kMulti (index of several parts, index.cuh): one launch per part, each with its own rec array;
 // size[g] accumulates the per-part list sizes over the launches (part_flags bit 0: first part,
 // bit 1: last part) and the max-count filter is applied to the sum by the last one.
-template<bool kMulti>
-__global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv, uint32_t part_flags, const char* __restrict__ bases,
+// kHint: the table loads carry the L2 evict_last hint (index.cuh).
+template<bool kMulti, bool kHint>
+__global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, const char* __restrict__ bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
@@ -222,13 +225,14 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
   }
 
   // stage 1: prefix-table probes for all (position, strand) pairs of this thread, issued together
+  const uint64_t pol = kHint ? l2_evict_last_policy() : 0;
   uint32_t c0[8], c1[8];
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
     if(keep[j]) {
       const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
-      load_count_pair(iv.counts, pm, c0[2 * j], c1[2 * j]);
-      load_count_pair(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1]);
+      load_count_pair<kHint>(iv.counts, pm, c0[2 * j], c1[2 * j], pol);
+      load_count_pair<kHint>(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
     }
   }
   const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
 #pragma unroll
   for(int q = 0; q < 8; ++q) {
     first[q] = 0;
-    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word(iv, tail_word_of(iv, c0[q]));
+    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
   }
   uint32_t nlook = 0, ntail = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
           ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
           const uint32_t tt = (uint32_t)mer & tmask;
           uint32_t lo, hi;
-          bucket_range(iv, a0, a1, tt, first[2 * j + s], lo, hi);
+          bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
           if(hi != lo && (mer & 3) == 0)
             for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
           nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;
@@ -280,7 +284,10 @@ __global__ void __launch_bounds__(kSeedThreads) seed_lookup_kernel(index_view iv
         if(!(part_flags & 1)) sz += size[g0 + j];
         if((part_flags & 2) && max_count && sz >= max_count) sz = 0;
       }
-      __stcs(rec + g0 + j, out); __stcs(size + g0 + j, sz);
+      // expand_kernel reads rec only where size != 0 (a one-part index): positions without a list
+      // (most of them) write 4 bytes instead of 20
+      if(kMulti || sz) __stcs(rec + g0 + j, out);
+      __stcs(size + g0 + j, sz);
     }
   }
   if(kMulti && !(part_flags & 1)) nlook = 0;          // a k-mer is counted once, not once per part
@@ -991,14 +998,15 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     timer.next("seed lookup");
     if(nparts == 1) {
       l2_window(ctx, st, idx, true);
-      seed_lookup_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                               ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                                               ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
+      auto kern = g_l2_hint ? seed_lookup_kernel<false, true> : seed_lookup_kernel<false, false>;
+      kern<<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                          ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
       MR_LAUNCHED(ctx);
     } else {
       for(uint32_t part = 0; part < nparts; ++part) {
         l2_window(ctx, st, part ? idx->more[part - 1] : idx, true);
-        seed_lookup_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(idx->part_view(part), (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
+        seed_lookup_kernel<true, false><<<ntiles, kSeedThreads, 0, st>>>(idx->part_view(part), (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
                                                                 d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                                                 ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
                                                                 ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6);

@@ -361,7 +361,7 @@ def ours(args, w, files):
     stream = torch.cuda.ExternalStream(L.mr_context_stream(ctx))
 
     phase = {}
-    counters = dict(lookups=0, tails=0, hits=0, groups=0, coords=0)
+    counters = dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0)
 
     import threading
 
@@ -369,7 +369,7 @@ def ours(args, w, files):
         # one thread per context: batches lane, lane + nstreams, ... (the C call releases the GIL)
         c = ctxs[lane]
         lnames = (C.c_char_p * 32)(); lsecs = (C.c_double * 32)()
-        ph, cn = {}, dict(lookups=0, tails=0, hits=0, groups=0, coords=0)
+        ph, cn = {}, dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0)
         try:
             for db, ds, hs, nr in dev[lane::nstreams]:
                 out = C.c_void_p()
@@ -384,7 +384,7 @@ def ours(args, w, files):
                     v = api.ResultView()
                     L.mr_result_get(out, C.byref(v))
                     cn["lookups"] += v.n_kmers_looked_up; cn["tails"] += v.n_tail_entries; cn["hits"] += v.n_hits
-                    cn["groups"] += v.n_groups; cn["coords"] += v.ncoords
+                    cn["groups"] += v.n_groups; cn["coords"] += v.ncoords; cn["lists"] += v.n_lists
                 L.mr_result_free(out)
         except Exception as e:                       # noqa: BLE001
             errors.append(e)
@@ -450,8 +450,9 @@ def ours(args, w, files):
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     # Phase timers are CUDA events recorded on the library's own stream around each phase; the
     # "seed lookup" phase is exactly one launch of seed_lookup_kernel per batch.  Algorithmic bytes
-    # (kernel table): per read base 1 B read (ASCII) + 20 B written (lookup record + list
-    # size); per looked-up k-mer 2 strands x 8 B of the prefix table; 4 B per suffix-array tail read.
+    # (kernel table): per read base 1 B read (ASCII) + 4 B written (list size); per position
+    # that keeps a list 16 B written (lookup record); per looked-up k-mer 2 strands x 8 B (slot: bucket
+    # start, size and the tails of a small bucket); 1 B per tail entry scanned in the tail array.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -463,7 +464,7 @@ def ours(args, w, files):
     if phase:
         T = total_bases * args.steps
         kern = "seed lookup"
-        alg = T * 21 + counters["lookups"] * 16 + counters["tails"] * 4
+        alg = T * 5 + counters["lists"] * 16 + counters["lookups"] * 16 + counters["tails"] * 1
         launches_k = nbatches * args.steps
         achieved = alg / phase[kern] / 1e9 if phase.get(kern, 0) > 0 else 0.0
         traffic = None
@@ -479,7 +480,7 @@ def ours(args, w, files):
         rnd = None
         try:
             g1, g2 = C.c_double(), C.c_double()
-            tbl = int((4 ** 12 + 1) * 4 + H.mrh_tool_sr_bases(tool))       # prefix table + 8-bit tails of this index
+            tbl = int(4 ** 12 * 8 + H.mrh_tool_sr_bases(tool))             # slot table + 8-bit tails of this index
             if L.mr_selftest_random_gather(ctx, 1 << 30, 1 << 28, C.byref(g1)) == 0 and \
                L.mr_selftest_random_gather(ctx, tbl, 1 << 28, C.byref(g2)) == 0:
                 rnd = {"hbm_table_1GiB": g1.value, "index_sized_table": g2.value, "index_sized_table_bytes": tbl, "unit": "GB/s",
@@ -495,7 +496,7 @@ def ours(args, w, files):
                 "dram_gbs_from_traffic": (traffic / (phase[kern] / launches_k) / 1e9) if traffic else None,
                 "frac_of_random_sector_peak": (traffic / (phase[kern] / launches_k) / 1e9 / rnd["hbm_table_1GiB"])
                 if traffic and rnd and rnd["hbm_table_1GiB"] > 0 else None,
-                "note": "random 32-byte-sector gathers into a 268 MB prefix table and the tail array: bounded by "
+                "note": "random 32-byte-sector gathers into a 134 MB slot table (and the tail array for buckets not held inline): bounded by "
                         "random-access sector throughput, not by streaming bandwidth; with streams_per_gpu > 1 the launch runs next to "
                         "the other stream's kernels, so avg_launch_ms is its duration while sharing the GPU; the chaining kernels "
                         "(phase 'chain coords') are latency/issue bound, see profiles/",
@@ -530,6 +531,8 @@ def ours(args, w, files):
                                 "superread_bases": int(H.mrh_tool_sr_bases(tool)), "superreads": int(H.mrh_tool_sr_count(tool))},
                 "work_per_step": {"read_bases": int(total_bases), "reads": int(H.mrh_tool_nreads(tool)), "batches": nbatches,
                                   "kmers_looked_up": counters["lookups"] // max(1, args.steps),
+                                  "positions_with_list": counters["lists"] // max(1, args.steps),
+                                  "tail_entries_scanned": counters["tails"] // max(1, args.steps),
                                   "hits": counters["hits"] // max(1, args.steps), "groups": counters["groups"] // max(1, args.steps),
                                   "coords": counters["coords"] // max(1, args.steps)}}
         print(json.dumps(line))

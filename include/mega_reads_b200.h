@@ -170,9 +170,10 @@ typedef struct mr_result_view {
   const int32_t  *component;        /* union-find root, row offset inside the read */
   /* work counters of the batch, for roofline arithmetic */
   uint64_t n_kmers_looked_up;       /* k-mers that reached the suffix-array lookup (x2 strands) */
-  uint64_t n_tail_entries;          /* suffix-array tail entries those lookups read (4 bytes each) */
+  uint64_t n_tail_entries;          /* entries of the tail array those lookups scanned (buckets not held inline in their slot) */
   uint64_t n_hits;                  /* hits expanded into (read, super-read) lists */
   uint64_t n_groups;                /* (read, super-read) pairs chained */
+  uint64_t n_lists;                 /* read positions whose k-mer kept a non-empty list after --max-count */
 } mr_result_view;
 int  mr_result_get(const mr_result* r, mr_result_view* view);
 

@@ -187,24 +187,26 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // kMulti (index of several parts, index.cuh): one launch per part, each with its own rec array;
 // size[g] accumulates the per-part list sizes over the launches (part_flags bit 0: first part,
 // bit 1: last part) and the max-count filter is applied to the sum by the last one.
-// kHint: the table loads carry the L2 evict_last hint (index.cuh).
-template<bool kMulti, bool kHint>
+// kHint: the table loads carry the L2 evict_last hint (index.cuh).  kSlots: lookups start from the
+// slot table (index_view::slots) instead of the counts table.
+template<bool kMulti, bool kHint, bool kSlots>
 __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, const char* __restrict__ bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
                                                                     uint4* __restrict__ rec, uint32_t* __restrict__ size,
                                                                     unsigned long long* __restrict__ n_lookups,
-                                                                    unsigned long long* __restrict__ n_tails) {
+                                                                    unsigned long long* __restrict__ n_tails,
+                                                                    unsigned long long* __restrict__ n_lists) {
   __shared__ uint8_t  codes[kTile + 64];
   __shared__ uint64_t sw[8];
-  __shared__ uint32_t looked, scanned;
+  __shared__ uint32_t looked, scanned, listed;
   const uint32_t k = iv.k;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
-  if(threadIdx.x == 0) { looked = 0; scanned = 0; }
+  if(threadIdx.x == 0) { looked = 0; scanned = 0; listed = 0; }
   tile_kmers t;
   enumerate_tile(bases, rs, rlen, tpos, k, codes, t);
 
@@ -224,27 +226,53 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
     }
   }
 
-  // stage 1: prefix-table probes for all (position, strand) pairs of this thread, issued together
   const uint64_t pol = kHint ? l2_evict_last_policy() : 0;
-  uint32_t c0[8], c1[8];
+  const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
+  uint32_t c0[8], c1[8], first[8];
+  uint32_t inl[8];                        // kSlots: the bucket's tails when it is held inline in its slot
+  if(kSlots) {
+    // stage 1: ONE 8-byte read per (position, strand): bucket start, size and -- for a bucket of at
+    // most slot_cap entries -- its tails
+    uint2 sl[8];
 #pragma unroll
-  for(int j = 0; j < 4; ++j) {
-    if(keep[j]) {
-      const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
-      load_count_pair<kHint>(iv.counts, pm, c0[2 * j], c1[2 * j], pol);
-      load_count_pair<kHint>(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
+    for(int j = 0; j < 4; ++j) {
+      if(keep[j]) {
+        sl[2 * j]     = __ldg(iv.slots + (uint32_t)(t.m[j] >> iv.tail_bits));
+        sl[2 * j + 1] = __ldg(iv.slots + (uint32_t)(t.rm[j] >> iv.tail_bits));
+      }
+    }
+    // stage 2: larger buckets go to the tail array (size 255 = "255 or more": the exact end is in counts)
+#pragma unroll
+    for(int q = 0; q < 8; ++q) {
+      c0[q] = c1[q] = 0; first[q] = 0; inl[q] = 0;
+      if(keep[q >> 1]) {
+        const uint32_t n = sl[q].y & 255u;
+        c0[q] = sl[q].x; c1[q] = sl[q].x + n; inl[q] = sl[q].y >> 8;
+        if(n > iv.slot_cap) {
+          if(n == 255u) c1[q] = __ldg(iv.counts + (uint32_t)((q & 1 ? t.rm[q >> 1] : t.m[q >> 1]) >> iv.tail_bits) + 1);
+          first[q] = tail_word<false>(iv, tail_word_of(iv, c0[q]), 0);
+        }
+      }
+    }
+  } else {
+    // stage 1: prefix-table probes for all (position, strand) pairs of this thread, issued together
+#pragma unroll
+    for(int j = 0; j < 4; ++j) {
+      if(keep[j]) {
+        const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
+        load_count_pair<kHint>(iv.counts, pm, c0[2 * j], c1[2 * j], pol);
+        load_count_pair<kHint>(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
+      }
+    }
+    // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
+    // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
+#pragma unroll
+    for(int q = 0; q < 8; ++q) {
+      first[q] = 0;
+      if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
     }
   }
-  const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
-  // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
-  // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
-  uint32_t first[8];
-#pragma unroll
-  for(int q = 0; q < 8; ++q) {
-    first[q] = 0;
-    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
-  }
-  uint32_t nlook = 0, ntail = 0;
+  uint32_t nlook = 0, ntail = 0, nlist = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
@@ -259,10 +287,16 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
         const uint32_t a0 = c0[2 * j + s], a1 = c1[2 * j + s];
         idx[s] = 0; nb[s] = 0;
         if(a0 != a1) {
-          ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
           const uint32_t tt = (uint32_t)mer & tmask;
           uint32_t lo, hi;
-          bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
+          if(kSlots && a1 - a0 <= iv.slot_cap) {
+            uint32_t less = 0, leq = 0, pk = inl[2 * j + s];
+            for(uint32_t i = a0; i < a1; ++i, pk >>= iv.tail_bits) { const uint32_t v = pk & tmask; less += v < tt; leq += v <= tt; }
+            lo = a0 + less; hi = a0 + leq;
+          } else {
+            ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
+            bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
+          }
           if(hi != lo && (mer & 3) == 0)
             for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
           nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;
@@ -278,7 +312,7 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
       }
     }
     const uint32_t pos = tpos + threadIdx.x * 4 + j;
-    // streaming stores (evict-first): the 20 B/base of output must not push the index tables out of L2
+    // streaming stores (evict-first): the output must not push the index tables out of L2
     if(pos < rlen) {
       if(kMulti) {
         if(!(part_flags & 1)) sz += size[g0 + j];
@@ -288,13 +322,19 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
       // (most of them) write 4 bytes instead of 20
       if(kMulti || sz) __stcs(rec + g0 + j, out);
       __stcs(size + g0 + j, sz);
+      if((!kMulti || (part_flags & 2)) && sz) ++nlist;
     }
   }
   if(kMulti && !(part_flags & 1)) nlook = 0;          // a k-mer is counted once, not once per part
   if(nlook) atomicAdd(&looked, nlook);
   if(ntail) atomicAdd(&scanned, ntail);
+  if(nlist) atomicAdd(&listed, nlist);
   __syncthreads();
-  if(threadIdx.x == 0 && looked) { atomicAdd(n_lookups, (unsigned long long)looked); atomicAdd(n_tails, (unsigned long long)scanned); }
+  if(threadIdx.x == 0) {
+    if(looked) atomicAdd(n_lookups, (unsigned long long)looked);
+    if(scanned) atomicAdd(n_tails, (unsigned long long)scanned);
+    if(listed) atomicAdd(n_lists, (unsigned long long)listed);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -998,18 +1038,21 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     timer.next("seed lookup");
     if(nparts == 1) {
       l2_window(ctx, st, idx, true);
-      auto kern = g_l2_hint ? seed_lookup_kernel<false, true> : seed_lookup_kernel<false, false>;
+      auto kern = iv.slots ? seed_lookup_kernel<false, false, true>
+                           : (g_l2_hint ? seed_lookup_kernel<false, true, false> : seed_lookup_kernel<false, false, false>);
       kern<<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                           ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
+                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9);
       MR_LAUNCHED(ctx);
     } else {
       for(uint32_t part = 0; part < nparts; ++part) {
         l2_window(ctx, st, part ? idx->more[part - 1] : idx, true);
-        seed_lookup_kernel<true, false><<<ntiles, kSeedThreads, 0, st>>>(idx->part_view(part), (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
-                                                                d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                                ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                                                ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6);
+        const index_view& pv = idx->part_view(part);
+        auto kern = pv.slots ? seed_lookup_kernel<true, false, true> : seed_lookup_kernel<true, false, false>;
+        kern<<<ntiles, kSeedThreads, 0, st>>>(pv, (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
+                                            d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                            ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                            ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9);
         MR_LAUNCHED(ctx);
       }
     }
@@ -1031,12 +1074,13 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t H = h_ctr[1];
   MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
   res->view.n_kmers_looked_up = h_ctr[0];
   res->view.n_tail_entries = h_ctr[6];
+  res->view.n_lists = h_ctr[9];
   // MR_MAX_HITS lowers the limit (tests of the callers' batch splitting)
   static const uint64_t hit_limit = getenv("MR_MAX_HITS") ? strtoull(getenv("MR_MAX_HITS"), nullptr, 0) : (1ULL << 32);
   if(H >= hit_limit) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many hits in one batch; use smaller batches");

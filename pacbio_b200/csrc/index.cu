@@ -12,6 +12,8 @@
 #include <cstring>
 #include <memory>
 
+int build_slots(mr_index* idx);
+
 namespace {
 
 // k-mer starting at `pos`, first base most significant, bases past the end of the text read as A
@@ -111,6 +113,19 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
     index_lookup(iv, mers[i], idx, nb);
     index_out[i] = idx;
     nb_out[i]    = nb;
+  }
+}
+
+// slots (index_view::slots) from counts + 8-bit tails
+__global__ void __launch_bounds__(256) slots_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ tails,
+                                                    uint32_t nprefix, uint32_t tail_bits, uint32_t cap, uint2* __restrict__ slots) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nprefix; p += stride) {
+    const uint32_t a0 = counts[p], n = counts[p + 1] - a0;
+    uint32_t pack = 0;
+    if(n <= cap)
+      for(uint32_t i = 0; i < n; ++i) pack |= (uint32_t)tails[a0 + i] << (tail_bits * i);
+    slots[p] = make_uint2(a0, min(n, 255u) | (pack << 8));
   }
 }
 
@@ -252,6 +267,7 @@ static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, con
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
   v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.mi = mi; v.tail_bits = tail_bits; v.tail_bytes = tail_bytes;
   v.sr_base = 0; v.nseq_all = nseq;
+  MR_TRY(build_slots(idx.get()));
   v.nshort = 0;
   for(uint32_t j = 1; j <= k - psa_min; ++j) {
     const uint64_t pos = n - k + j;
@@ -265,6 +281,24 @@ static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, con
   }
   idx->n_all = sr_start[nseq]; idx->nseq_all = nseq;
   *out = idx.release();
+  return MR_OK;
+}
+
+// slot table of a part whose counts and tails are in place (after a build or a load)
+int build_slots(mr_index* idx) {
+  mr_context* ctx = idx->ctx;
+  index_view& v = idx->view;
+  v.slots = nullptr; v.slot_cap = 0;
+  if(v.tail_bytes != 1 || v.tail_bits == 0 || getenv("MR_NO_SLOTS")) return MR_OK;
+  const uint32_t nprefix = 1u << (2 * v.mi);
+  if((uint64_t)v.nsa > (uint64_t)nprefix * (24 / v.tail_bits)) return MR_OK;      // mean bucket above the inline capacity: no gain
+  MR_TRY(idx->slots.ensure(ctx, (size_t)nprefix * sizeof(uint2)));
+  const uint32_t cap = 24 / v.tail_bits;
+  slots_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(idx->counts.as<uint32_t>(), idx->tails.as<uint8_t>(), nprefix, v.tail_bits, cap,
+                                                         idx->slots.as<uint2>());
+  MR_LAUNCHED(ctx);
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  v.slots = idx->slots.as<uint2>(); v.slot_cap = cap;
   return MR_OK;
 }
 

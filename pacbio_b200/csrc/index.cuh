@@ -46,6 +46,12 @@ struct index_view {
   const uint32_t* __restrict__ blk;
   uint64_t n;
   uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort;
+  // slots[p] = { counts[p], min(bucket size, 255) | tails of the bucket << 8 } for buckets of at most
+  // slot_cap = 24 / tail_bits entries: ONE 8-byte random read answers a lookup whose bucket is small
+  // (93 % of them at a mean bucket of 2) instead of a counts read plus a tails read.  Built when the
+  // tails have at most 8 bits (slot_cap >= 3); null otherwise.
+  const uint2*    __restrict__ slots;
+  uint32_t slot_cap;
   uint32_t sr_base;                // global index of this part's first super-read (0 for a one-part index)
   uint32_t nseq_all;               // super-reads of the whole index (== nseq for a one-part index)
   uint64_t short_key[kMaxShort];   // padded k-mers of the tail-short suffixes (positions n-k+1 .. n-m)
@@ -59,6 +65,7 @@ struct mr_index {
   uint64_t unitig_total = 0;         // entries of unitig_ids
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;
+  dev_buf  slots;                    // uint2[4^mi]: see index_view::slots
   dev_buf  lut;                      // counts and tails live side by side in this one allocation, so that
                                      // a single L2 access-policy window covers what a lookup reads
   int alloc_lut(mr_context* c, size_t counts_bytes, size_t tails_bytes) {

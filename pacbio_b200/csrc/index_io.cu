@@ -13,6 +13,7 @@
 #include <vector>
 
 int finish_single_part(mr_index* idx, const std::vector<uint32_t>& sr_len);   // index.cu
+int build_slots(mr_index* idx);                                                 // index.cu
 
 namespace {
 
@@ -171,6 +172,7 @@ int mr_index_load(mr_context* ctx, const char* path, mr_index** out) {
   v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
   v.nshort = h.nshort;
   v.sr_base = 0; v.nseq_all = h.nseq;
+  MR_TRY(build_slots(idx.get()));               // derived from counts + tails: not part of the file
   memcpy(v.short_key, h.short_key, sizeof h.short_key);
   idx->n_all = h.n; idx->nseq_all = h.nseq;
   {                                            // super-read lengths from the starts just loaded

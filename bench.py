@@ -361,7 +361,7 @@ def ours(args, w, files):
     stream = torch.cuda.ExternalStream(L.mr_context_stream(ctx))
 
     phase = {}
-    counters = dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0)
+    counters = dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0, buckets=0)
 
     import threading
 
@@ -369,7 +369,7 @@ def ours(args, w, files):
         # one thread per context: batches lane, lane + nstreams, ... (the C call releases the GIL)
         c = ctxs[lane]
         lnames = (C.c_char_p * 32)(); lsecs = (C.c_double * 32)()
-        ph, cn = {}, dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0)
+        ph, cn = {}, dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0, buckets=0)
         try:
             for db, ds, hs, nr in dev[lane::nstreams]:
                 out = C.c_void_p()
@@ -384,7 +384,7 @@ def ours(args, w, files):
                     v = api.ResultView()
                     L.mr_result_get(out, C.byref(v))
                     cn["lookups"] += v.n_kmers_looked_up; cn["tails"] += v.n_tail_entries; cn["hits"] += v.n_hits
-                    cn["groups"] += v.n_groups; cn["coords"] += v.ncoords; cn["lists"] += v.n_lists
+                    cn["groups"] += v.n_groups; cn["coords"] += v.ncoords; cn["lists"] += v.n_lists; cn["buckets"] += v.n_buckets
                 L.mr_result_free(out)
         except Exception as e:                       # noqa: BLE001
             errors.append(e)
@@ -451,8 +451,8 @@ def ours(args, w, files):
     # Phase timers are CUDA events recorded on the library's own stream around each phase; the
     # "seed lookup" phase is exactly one launch of seed_lookup_kernel per batch.  Algorithmic bytes
     # (kernel table): per read base 1 B read (ASCII) + 4 B written (list size); per position
-    # that keeps a list 16 B written (lookup record); per looked-up k-mer 2 strands x 8 B (slot: bucket
-    # start, size and the tails of a small bucket); 1 B per tail entry scanned in the tail array.
+    # that keeps a list 16 B written (lookup record); per looked-up k-mer 2 strands x 8 B (the bucket's
+    # two bounds in the prefix table); 1 B per tail entry scanned in the tail array.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -474,29 +474,41 @@ def ours(args, w, files):
                 traffic = prof["dram_bytes_per_launch"]
         except Exception:
             pass
-        # the ceiling this kernel lives under: random 32-byte sectors per second, measured
-        # here with a pointer-chase-free gather (mr_selftest_random_gather) over a table far larger than
-        # the L2 and over one of the size of this index's lookup tables
+        # The ceiling this kernel lives under is the rate of random DRAM accesses, not bytes:
+        # mr_selftest_random_gather (pointer-chase-free 16-byte loads at random places of a 1 GiB table)
+        # tops out at ~50 G loads/s on B200 whether a miss fetches 64 or 128 bytes (profiles/
+        # r01_gather_probe.txt).  A lookup makes one random access per strand into the prefix table and one
+        # more per non-empty bucket into the tail array.
         rnd = None
         try:
             g1, g2 = C.c_double(), C.c_double()
-            tbl = int(4 ** 12 * 8 + H.mrh_tool_sr_bases(tool))             # slot table + 8-bit tails of this index
+            tbl = int((4 ** 12 + 1) * 4 + H.mrh_tool_sr_bases(tool))       # prefix table + 8-bit tails of this index
             if L.mr_selftest_random_gather(ctx, 1 << 30, 1 << 28, C.byref(g1)) == 0 and \
                L.mr_selftest_random_gather(ctx, tbl, 1 << 28, C.byref(g2)) == 0:
-                rnd = {"hbm_table_1GiB": g1.value, "index_sized_table": g2.value, "index_sized_table_bytes": tbl, "unit": "GB/s",
-                       "how": "2^28 independent 16-byte loads at random 16-byte-aligned places, 8 in flight per thread, "
-                              "sectors x 32 B / best of 3 launches (mr_selftest_random_gather)"}
+                acc = (2 * counters["lookups"] + counters["buckets"]) / phase[kern] / 1e9
+                hit = None
+                try:
+                    hit = json.load(open(os.path.join(ROOT, "profiles", "r01_seed_lookup_summary.json")))["l2_sector_hit_rate_pct"] / 100.0
+                except Exception:
+                    pass
+                rnd = {"peak_G_accesses_per_s": g1.value / 32.0, "peak_table": "1 GiB (HBM)",
+                       "peak_G_accesses_per_s_index_sized_table": g2.value / 32.0, "index_sized_table_bytes": tbl,
+                       "achieved_G_accesses_per_s": acc, "frac": acc / (g1.value / 32.0),
+                       "l2_hit_rate_ncu": hit,
+                       "achieved_G_dram_accesses_per_s": acc * (1.0 - hit) if hit is not None else None,
+                       "frac_dram": acc * (1.0 - hit) / (g1.value / 32.0) if hit is not None else None,
+                       "how": "accesses = 2 x looked-up k-mers + non-empty buckets scanned (kernel counters) / CUDA-event time of the "
+                              "launches; peak = 2^28 independent random 16-byte loads, 8 in flight per thread, best of 3 launches; "
+                              "frac > 1 means L2 hits: frac_dram discounts them with the hit rate of the committed ncu capture"}
         except Exception:
             pass
         roof = {"kernel": "seed_lookup_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg / launches_k, "avg_launch_ms": 1e3 * phase[kern] / launches_k,
                 "share_of_step": phase[kern] / sum(phase.values()),
-                "random_sector_peak": rnd,
+                "random_access": rnd,
                 "dram_gbs_from_traffic": (traffic / (phase[kern] / launches_k) / 1e9) if traffic else None,
-                "frac_of_random_sector_peak": (traffic / (phase[kern] / launches_k) / 1e9 / rnd["hbm_table_1GiB"])
-                if traffic and rnd and rnd["hbm_table_1GiB"] > 0 else None,
-                "note": "random 32-byte-sector gathers into a 134 MB slot table (and the tail array for buckets not held inline): bounded by "
+                "note": "random gathers into a 67 MB prefix table and a 36 MB tail array: bounded by "
                         "random-access sector throughput, not by streaming bandwidth; with streams_per_gpu > 1 the launch runs next to "
                         "the other stream's kernels, so avg_launch_ms is its duration while sharing the GPU; the chaining kernels "
                         "(phase 'chain coords') are latency/issue bound, see profiles/",
@@ -533,6 +545,7 @@ def ours(args, w, files):
                                   "kmers_looked_up": counters["lookups"] // max(1, args.steps),
                                   "positions_with_list": counters["lists"] // max(1, args.steps),
                                   "tail_entries_scanned": counters["tails"] // max(1, args.steps),
+                                  "buckets_scanned": counters["buckets"] // max(1, args.steps),
                                   "hits": counters["hits"] // max(1, args.steps), "groups": counters["groups"] // max(1, args.steps),
                                   "coords": counters["coords"] // max(1, args.steps)}}
         print(json.dumps(line))

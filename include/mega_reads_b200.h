@@ -174,6 +174,7 @@ typedef struct mr_result_view {
   uint64_t n_hits;                  /* hits expanded into (read, super-read) lists */
   uint64_t n_groups;                /* (read, super-read) pairs chained */
   uint64_t n_lists;                 /* read positions whose k-mer kept a non-empty list after --max-count */
+  uint64_t n_buckets;               /* non-empty prefix buckets those lookups went on to scan (second random access) */
 } mr_result_view;
 int  mr_result_get(const mr_result* r, mr_result_view* view);
 

@@ -46,7 +46,7 @@ class ResultView(C.Structure):
                 ("start_node", u8p), ("end_node", u8p),
                 ("lstart", i32p), ("lprev", i32p), ("lpath", i32p), ("lunitigs", i32p), ("component", i32p),
                 ("n_kmers_looked_up", C.c_uint64), ("n_tail_entries", C.c_uint64), ("n_hits", C.c_uint64),
-                ("n_groups", C.c_uint64), ("n_lists", C.c_uint64)]
+                ("n_groups", C.c_uint64), ("n_lists", C.c_uint64), ("n_buckets", C.c_uint64)]
 
 
 _lib = None

@@ -197,16 +197,17 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
                                                                     uint4* __restrict__ rec, uint32_t* __restrict__ size,
                                                                     unsigned long long* __restrict__ n_lookups,
                                                                     unsigned long long* __restrict__ n_tails,
-                                                                    unsigned long long* __restrict__ n_lists) {
+                                                                    unsigned long long* __restrict__ n_lists,
+                                                                    unsigned long long* __restrict__ n_buckets) {
   __shared__ uint8_t  codes[kTile + 64];
   __shared__ uint64_t sw[8];
-  __shared__ uint32_t looked, scanned, listed;
+  __shared__ uint32_t looked, scanned, listed, buckets;
   const uint32_t k = iv.k;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
-  if(threadIdx.x == 0) { looked = 0; scanned = 0; listed = 0; }
+  if(threadIdx.x == 0) { looked = 0; scanned = 0; listed = 0; buckets = 0; }
   tile_kmers t;
   enumerate_tile(bases, rs, rlen, tpos, k, codes, t);
 
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
       if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
     }
   }
-  uint32_t nlook = 0, ntail = 0, nlist = 0;
+  uint32_t nlook = 0, ntail = 0, nlist = 0, nbucket = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
             lo = a0 + less; hi = a0 + leq;
           } else {
             ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
+            ++nbucket;
             bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
           }
           if(hi != lo && (mer & 3) == 0)
@@ -329,11 +331,13 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
   if(nlook) atomicAdd(&looked, nlook);
   if(ntail) atomicAdd(&scanned, ntail);
   if(nlist) atomicAdd(&listed, nlist);
+  if(nbucket) atomicAdd(&buckets, nbucket);
   __syncthreads();
   if(threadIdx.x == 0) {
     if(looked) atomicAdd(n_lookups, (unsigned long long)looked);
     if(scanned) atomicAdd(n_tails, (unsigned long long)scanned);
     if(listed) atomicAdd(n_lists, (unsigned long long)listed);
+    if(buckets) atomicAdd(n_buckets, (unsigned long long)buckets);
   }
 }
 
@@ -1042,7 +1046,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                            : (g_l2_hint ? seed_lookup_kernel<false, true, false> : seed_lookup_kernel<false, false, false>);
       kern<<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                           ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9);
+                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
       MR_LAUNCHED(ctx);
     } else {
       for(uint32_t part = 0; part < nparts; ++part) {
@@ -1052,7 +1056,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
         kern<<<ntiles, kSeedThreads, 0, st>>>(pv, (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
                                             d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                             ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                            ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9);
+                                            ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
         MR_LAUNCHED(ctx);
       }
     }
@@ -1074,13 +1078,14 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 11 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
   const uint64_t H = h_ctr[1];
   MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
   res->view.n_kmers_looked_up = h_ctr[0];
   res->view.n_tail_entries = h_ctr[6];
   res->view.n_lists = h_ctr[9];
+  res->view.n_buckets = h_ctr[10];
   // MR_MAX_HITS lowers the limit (tests of the callers' batch splitting)
   static const uint64_t hit_limit = getenv("MR_MAX_HITS") ? strtoull(getenv("MR_MAX_HITS"), nullptr, 0) : (1ULL << 32);
   if(H >= hit_limit) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many hits in one batch; use smaller batches");

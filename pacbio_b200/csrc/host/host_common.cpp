@@ -428,10 +428,14 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       snprintf(buf, sizeof(buf), "%.2f %.2f %d %d %d %llu %d %.4f ", mr.imp_s, mr.imp_e, v.rs[srow], v.re[erow],
                v.qs[srow] - mr.start_offset, (unsigned long long)qe_out, v.lpath[erow], mr.density);
       out += buf;
-      for(size_t t = 0; t < path.size(); ++t) {
-        if(t) out += '_';
-        snprintf(buf, sizeof(buf), "%u%c", path[t] >> 1, (path[t] & 1) ? 'R' : 'F');
-        out += buf;
+      for(size_t t = 0; t < path.size(); ++t) {             // "<id><F|R>" joined by '_': no printf per unitig
+        char nb[16];
+        int len = 0;
+        uint32_t id = path[t] >> 1;
+        nb[15 - len++] = (path[t] & 1) ? 'R' : 'F';
+        do { nb[15 - len++] = (char)('0' + id % 10); id /= 10; } while(id);
+        if(t) nb[15 - len++] = '_';
+        out.append(nb + 16 - len, (size_t)len);
       }
       snprintf(buf, sizeof(buf), " %d", sr_len);
       out += buf;

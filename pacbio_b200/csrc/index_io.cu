@@ -53,7 +53,7 @@ void sections_of(mr_index* idx, section* s) {
   s[6] = { &idx->unitig_ids, 0 }; s[7] = { &idx->unitig_off, 0 }; s[8] = { &idx->unitig_len, 0 };
   if(idx->has_unitigs) {
     s[6].bytes = idx->unitig_total * sizeof(uint32_t);
-    s[7].bytes = ((uint64_t)idx->nseq + 1) * sizeof(uint64_t);
+    s[7].bytes = ((uint64_t)(idx->nseq_all ? idx->nseq_all : idx->nseq) + 1) * sizeof(uint64_t);   // spans all parts
     s[8].bytes = (uint64_t)idx->n_unitigs * sizeof(int32_t);
   }
 }
@@ -86,13 +86,13 @@ uint64_t mr_inputs_checksum(const uint64_t* text2bit, uint64_t n, const uint64_t
 
 uint64_t mr_index_checksum(const mr_index* idx) { return idx ? idx->inputs_checksum : 0; }
 
-int mr_index_save(mr_index* idx, const char* path) {
-  if(!idx || !path) return MR_EINVAL;
-  mr_context* ctx = idx->ctx;
-  if(idx->nparts() > 1) return ctx->fail(MR_ELIMIT, "mr_index_save: an index of several parts (text of 2^32 bases or more) has no file format yet");
-  MR_CUDA(ctx, cudaSetDevice(ctx->device));
-  std::unique_ptr<FILE, file_closer> f(fopen(path, "wb"));
-  if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_save: cannot open ") + path);
+} // extern "C"
+
+namespace {
+
+// one part: header + its sections.  Whole-index fields of the header: reserved[0] = number of parts
+// (written in the first header only; 0 in files of the one-part era), reserved[1] = sr_base of the part.
+int save_part(mr_context* ctx, mr_index* idx, FILE* f, pinned_buf& stage, uint32_t nparts) {
   file_header h;
   memset(&h, 0, sizeof h);
   memcpy(h.magic, kMagic, 8);
@@ -101,20 +101,85 @@ int mr_index_save(mr_index* idx, const char* path) {
   h.n_unitigs = idx->n_unitigs; h.has_unitigs = idx->has_unitigs;
   memcpy(h.short_key, idx->view.short_key, sizeof h.short_key);
   h.inputs_checksum = idx->inputs_checksum;
+  h.reserved[0] = nparts; h.reserved[1] = idx->view.sr_base;
   section s[kSections];
   sections_of(idx, s);
   for(uint32_t i = 0; i < kSections; ++i) h.bytes[i] = s[i].bytes;
-  if(fwrite(&h, sizeof h, 1, f.get()) != 1) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
-  pinned_buf stage;
-  MR_TRY(stage.ensure(ctx, kChunk));
+  if(fwrite(&h, sizeof h, 1, f) != 1) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
   for(uint32_t i = 0; i < kSections; ++i) {
     for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
       const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
       MR_CUDA(ctx, cudaMemcpyAsync(stage.p, (const char*)s[i].buf->p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
       MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if(fwrite(stage.p, 1, len, f.get()) != len) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+      if(fwrite(stage.p, 1, len, f) != len) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
     }
   }
+  return MR_OK;
+}
+
+int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index* idx, file_header& h, std::vector<uint32_t>& sr_len) {
+  if(fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0)
+    return ctx->fail(MR_EINVAL, "mr_index_load: not an index file of this library version");
+  if(!(h.m >= 1 && h.m < h.k && h.k <= 31 && h.mi >= 1 && h.mi <= h.m && h.n >= h.k && h.n < 0xfffffff0ULL && h.nseq >= 1 &&
+       h.nsa == (uint32_t)(h.n - h.m + 1) && h.tail_bits == 2 * (h.k - h.mi) && h.nshort <= (uint32_t)kMaxShort &&
+       (h.tail_bytes == 1 || h.tail_bytes == 2 || h.tail_bytes == 4)))
+    return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
+  idx->ctx = ctx; idx->n = h.n; idx->nsa = h.nsa; idx->nseq = h.nseq; idx->k = h.k; idx->m = h.m; idx->mi = h.mi;
+  idx->n_unitigs = h.n_unitigs; idx->has_unitigs = h.has_unitigs != 0;
+  idx->inputs_checksum = h.inputs_checksum;
+  idx->view.tail_bytes = h.tail_bytes;
+  if(idx->has_unitigs) idx->unitig_total = h.bytes[6] / sizeof(uint32_t);
+  section s[kSections];
+  sections_of(idx, s);
+  if(idx->has_unitigs) s[7].bytes = h.bytes[7];      // unitig_off spans the super-reads of ALL parts
+  for(uint32_t i = 0; i < kSections; ++i)
+    if(s[i].bytes != h.bytes[i]) return ctx->fail(MR_EINVAL, "mr_index_load: section sizes do not match the header");
+  MR_TRY(idx->alloc_lut(ctx, s[3].bytes, s[2].bytes));
+  for(uint32_t i = 0; i < kSections; ++i) {
+    if(s[i].bytes == 0) continue;
+    MR_TRY(s[i].buf->ensure(ctx, s[i].bytes));
+    for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
+      const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
+      // two staging buffers: the file read of one chunk overlaps the upload of the previous one
+      MR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which]));
+      if(fread(stage[which].p, 1, len, f) != len) return ctx->fail(MR_EINVAL, "mr_index_load: file is truncated");
+      MR_CUDA(ctx, cudaMemcpyAsync((char*)s[i].buf->p + off, stage[which].p, len, cudaMemcpyHostToDevice, ctx->stream));
+      MR_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->stream));
+      which ^= 1;
+    }
+  }
+  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  index_view& v = idx->view;
+  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
+  v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
+  v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
+  v.nshort = h.nshort;
+  v.sr_base = (uint32_t)h.reserved[1]; v.nseq_all = h.nseq;
+  MR_TRY(build_slots(idx));                      // derived from counts + tails: not part of the file
+  memcpy(v.short_key, h.short_key, sizeof h.short_key);
+  idx->n_all = h.n; idx->nseq_all = h.nseq;
+  {                                              // super-read lengths from the starts just loaded
+    std::vector<uint32_t> st(h.nseq + 1);
+    MR_CUDA(ctx, cudaMemcpy(st.data(), idx->sr_start.p, ((size_t)h.nseq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for(uint32_t i = 0; i < h.nseq; ++i) sr_len.push_back(st[i + 1] - st[i]);
+  }
+  return MR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int mr_index_save(mr_index* idx, const char* path) {
+  if(!idx || !path) return MR_EINVAL;
+  mr_context* ctx = idx->ctx;
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<FILE, file_closer> f(fopen(path, "wb"));
+  if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_save: cannot open ") + path);
+  pinned_buf stage;
+  MR_TRY(stage.ensure(ctx, kChunk));
+  MR_TRY(save_part(ctx, idx, f.get(), stage, idx->nparts()));
+  for(mr_index* part : idx->more) MR_TRY(save_part(ctx, part, f.get(), stage, 0));
   if(fflush(f.get()) != 0) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
   return MR_OK;
 }
@@ -126,61 +191,45 @@ int mr_index_load(mr_context* ctx, const char* path, mr_index** out) {
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   std::unique_ptr<FILE, file_closer> f(fopen(path, "rb"));
   if(!f) return ctx->fail(MR_EINVAL, std::string("mr_index_load: cannot open ") + path);
-  file_header h;
-  if(fread(&h, sizeof h, 1, f.get()) != 1 || memcmp(h.magic, kMagic, 8) != 0)
-    return ctx->fail(MR_EINVAL, "mr_index_load: not an index file of this library version");
-  if(!(h.m >= 1 && h.m < h.k && h.k <= 31 && h.mi >= 1 && h.mi <= h.m && h.n >= h.k && h.n < 0xfffffff0ULL && h.nseq >= 1 &&
-       h.nsa == (uint32_t)(h.n - h.m + 1) && h.tail_bits == 2 * (h.k - h.mi) && h.nshort <= (uint32_t)kMaxShort &&
-       (h.tail_bytes == 1 || h.tail_bytes == 2 || h.tail_bytes == 4)))
-    return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
   ctx->timers.clear();
   phase_timer timer(ctx);
   timer.begin("index load");
-  std::unique_ptr<mr_index> idx(new mr_index);
-  idx->ctx = ctx; idx->n = h.n; idx->nsa = h.nsa; idx->nseq = h.nseq; idx->k = h.k; idx->m = h.m; idx->mi = h.mi;
-  idx->n_unitigs = h.n_unitigs; idx->has_unitigs = h.has_unitigs != 0;
-  idx->inputs_checksum = h.inputs_checksum;
-  idx->view.tail_bytes = h.tail_bytes;
-  if(idx->has_unitigs) idx->unitig_total = h.bytes[6] / sizeof(uint32_t);
-  section s[kSections];
-  sections_of(idx.get(), s);
-  for(uint32_t i = 0; i < kSections; ++i)
-    if(s[i].bytes != h.bytes[i]) return ctx->fail(MR_EINVAL, "mr_index_load: section sizes do not match the header");
   pinned_buf stage[2];
   MR_TRY(stage[0].ensure(ctx, kChunk)); MR_TRY(stage[1].ensure(ctx, kChunk));
   int which = 0;
-  MR_TRY(idx->alloc_lut(ctx, s[3].bytes, s[2].bytes));
-  for(uint32_t i = 0; i < kSections; ++i) {
-    if(s[i].bytes == 0) continue;
-    MR_TRY(s[i].buf->ensure(ctx, s[i].bytes));
-    for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
-      const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
-      // two staging buffers: the file read of one chunk overlaps the upload of the previous one
-      MR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which]));
-      if(fread(stage[which].p, 1, len, f.get()) != len) return ctx->fail(MR_EINVAL, "mr_index_load: file is truncated");
-      MR_CUDA(ctx, cudaMemcpyAsync((char*)s[i].buf->p + off, stage[which].p, len, cudaMemcpyHostToDevice, ctx->stream));
-      MR_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->stream));
-      which ^= 1;
-    }
+  std::unique_ptr<mr_index> idx(new mr_index);
+  std::vector<uint32_t> sr_len;
+  file_header h;
+  MR_TRY(load_part(ctx, f.get(), stage, which, idx.get(), h, sr_len));
+  const uint32_t nparts = h.reserved[0] ? (uint32_t)h.reserved[0] : 1u;
+  if(nparts > (uint32_t)kMaxParts) return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
+  uint64_t n_all = h.n;
+  for(uint32_t p = 1; p < nparts; ++p) {
+    std::unique_ptr<mr_index> part(new mr_index);
+    file_header hp;
+    MR_TRY(load_part(ctx, f.get(), stage, which, part.get(), hp, sr_len));
+    if(hp.k != h.k || hp.m != h.m || part->view.sr_base != sr_len.size() - hp.nseq)
+      return ctx->fail(MR_EINVAL, "mr_index_load: parts do not fit together");
+    n_all += hp.n;
+    idx->more.push_back(part.release());
   }
-  MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   timer.end();
   timer.collect();
-  index_view& v = idx->view;
-  v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
-  v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
-  v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
-  v.nshort = h.nshort;
-  v.sr_base = 0; v.nseq_all = h.nseq;
-  MR_TRY(build_slots(idx.get()));               // derived from counts + tails: not part of the file
-  memcpy(v.short_key, h.short_key, sizeof h.short_key);
-  idx->n_all = h.n; idx->nseq_all = h.nseq;
-  {                                            // super-read lengths from the starts just loaded
-    std::vector<uint32_t> st(h.nseq + 1), len(h.nseq);
-    MR_CUDA(ctx, cudaMemcpy(st.data(), idx->sr_start.p, ((size_t)h.nseq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    for(uint32_t i = 0; i < h.nseq; ++i) len[i] = st[i + 1] - st[i];
-    MR_TRY(finish_single_part(idx.get(), len));
+  const uint32_t nseq_all = (uint32_t)sr_len.size();
+  idx->nseq_all = nseq_all;
+  idx->view.nseq_all = nseq_all;
+  for(mr_index* part : idx->more) { part->nseq_all = nseq_all; part->view.nseq_all = nseq_all; }
+  if(nparts > 1) {
+    // a part's text carries the first k-1 bases of the next part (index.cuh): they are not its own
+    n_all = 0;
+    for(uint32_t i = 0; i < nseq_all; ++i) n_all += sr_len[i];
+    std::vector<index_view> views(nparts - 1);
+    for(uint32_t p = 1; p < nparts; ++p) views[p - 1] = idx->more[p - 1]->view;
+    MR_TRY(idx->more_views.ensure(ctx, views.size() * sizeof(index_view)));
+    MR_CUDA(ctx, cudaMemcpy(idx->more_views.p, views.data(), views.size() * sizeof(index_view), cudaMemcpyHostToDevice));
   }
+  idx->n_all = n_all;
+  MR_TRY(finish_single_part(idx.get(), sr_len));
   *out = idx.release();
   return MR_OK;
 }

@@ -213,7 +213,7 @@ def test_staged_batches_give_the_same_rows(case, ctx):
 
 
 @pytest.mark.parametrize("max_count", [5000, 3])
-def test_index_of_several_parts_gives_the_same_lists_and_rows(case, ctx, max_count):
+def test_index_of_several_parts_gives_the_same_lists_and_rows(case, ctx, max_count, tmp_path):
     """A text of 2^32 bases or more is indexed as several parts (index.cuh); MR_INDEX_PART_BASES forces
     that on a small input.  Hit lists, chains, rows and graph must not depend on the cut -- including
     the list sizes the count filters see (k-mers straddling two super-reads at a cut, max-count on the
@@ -253,6 +253,18 @@ def test_index_of_several_parts_gives_the_same_lists_and_rows(case, ctx, max_cou
         # what is defined for one suffix array only says so
         with pytest.raises(Exception):
             idx.sa()
+        # an index of several parts goes through a file like any other
+        path = str(tmp_path / "parts.bin")
+        idx.save(path)
+        back = pb.Index(ctx, sr, c["m"], c["k"], load_from=path)
+        try:
+            assert back.parts() == idx.parts() and back.checksum() == idx.checksum() != 0
+            again = ctx.align(back, sub, p)
+            assert again.ncoords == want.ncoords
+            for f in ("rs", "re", "qs", "qe", "nb_mers", "ql", "sr", "stretch", "offset", "avg_err", "info_len", "lpath", "lprev", "component"):
+                assert np.array_equal(getattr(again, f), getattr(want, f)), f
+        finally:
+            back.close()
     finally:
         idx.close()
 

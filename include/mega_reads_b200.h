@@ -73,7 +73,7 @@ uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min +
  * src_psa/48bit_index.hpp) is indexed as several PARTS of fewer than 2^32 bases, cut at super-read
  * boundaries; mr_align_batch gives the same rows either way.  The calls that speak in ranks of one
  * suffix array (mr_index_export_*, mr_lookup_batch*) return MR_ELIMIT for an index of several
- * parts, and so does the fine pass (mr_params.fine_mer != 0).
+ * parts.
  * Environment: MR_INDEX_PART_BASES=<n> lowers the part limit (tests). */
 uint32_t mr_index_parts(const mr_index* idx);
 /* parity taps: suffix-array values in SA order and the 4^psa_min + 1 prefix counts

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) fine_windows_kernel(uint64_t S, survivors
 }
 
 // lookups of every kk-mer of the reads: rec = {index(m), nb(m), index(rm), nb(rm)}, size = nb(m) + nb(rm)
-__global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, uint32_t kk, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, bool first_part, uint32_t kk, const char* __restrict__ bases,
                                                                   const uint64_t* __restrict__ read_start,
                                                                   const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                   const uint64_t* __restrict__ table_off,
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, 
       index_lookup_prefix(iv, t.rm[j], kk, out.z, out.w);
     }
     __stcs(rec + g0 + j, out);
-    __stcs(size + g0 + j, out.y + out.w);
+    __stcs(size + g0 + j, (first_part ? 0u : size[g0 + j]) + out.y + out.w);      // one launch per index part
   }
 }
 
@@ -560,7 +560,8 @@ __global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, 
 // them (key = row, payload = pb offset | signed super-read offset << 32) in emission order
 // (read position, forward range before reverse range, suffix-array order).
 template<bool EMIT>
-__global__ void __launch_bounds__(kSeedThreads) fine_expand_kernel(index_view iv, uint32_t kk, const uint64_t* __restrict__ read_start,
+__global__ void __launch_bounds__(kSeedThreads) fine_expand_kernel(index_view iv, const index_view* __restrict__ more_views, uint32_t nparts,
+                                                                    uint64_t rec_stride, uint32_t kk, const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint4* __restrict__ rec, const uint32_t* __restrict__ size,
                                                                     const uint64_t* __restrict__ table_off, const uint64_t* __restrict__ tkey,
@@ -599,12 +600,20 @@ __global__ void __launch_bounds__(kSeedThreads) fine_expand_kernel(index_view iv
       if(h < (uint32_t)raw_total) {
         uint32_t lo = 0, hi = kSeedThreads;
         while(hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if(s_off[mid] <= h) lo = mid; else hi = mid; }
-        const uint4 c = s_rec[lo];
-        const uint32_t j = h - s_off[lo];
+        uint4 c = s_rec[lo];
+        uint32_t j = h - s_off[lo];
+        uint32_t part = 0;
+        while(j >= c.y + c.w && part + 1 < nparts) {        // the list continues in the next index part
+          j -= c.y + c.w;
+          ++part;
+          c = __ldg(rec + part * rec_stride + rs + tpos + it * kSeedThreads + lo);
+        }
+        const index_view& pv = part ? more_views[part - 1] : iv;
         minus = j >= c.y;
         pb_off = tpos + it * kSeedThreads + lo + 1;
-        const uint32_t x = __ldg(iv.sa + (minus ? c.z + (j - c.y) : c.x + j));
-        if(index_locate_k(iv, x, kk, sr, off)) {
+        const uint32_t x = __ldg(pv.sa + (minus ? c.z + (j - c.y) : c.x + j));
+        if(index_locate_k(pv, x, kk, sr, off)) {
+          sr += pv.sr_base;
           // rows of (read, sr) in the table: equal keys are contiguous
           const uint64_t want = ((uint64_t)r << 32) | sr;
           uint64_t a = t0, b = t1;
@@ -1220,12 +1229,15 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     const uint64_t* tkey = first ? wk_a : wk_b;
     const uint32_t* trow = first ? wr_a : wr_b;
     if(ntiles) {
-      fine_seed_kernel<<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                        fb.table_off.as<uint64_t>(), ws.rec.as<uint4>(), ws.size.as<uint32_t>());
-      MR_LAUNCHED(ctx);
+      for(uint32_t part = 0; part < nparts; ++part) {
+        fine_seed_kernel<<<ntiles, kSeedThreads, 0, st>>>(idx->part_view(part), part == 0, kk, d_bases, d_read_start, ws.tile_read.as<uint32_t>(),
+                                                          ws.tile_pos.as<uint32_t>(), fb.table_off.as<uint64_t>(),
+                                                          ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>());
+        MR_LAUNCHED(ctx);
+      }
     }
     MR_CUDA(ctx, cudaMemsetAsync(fb.row_cnt.p, 0, (S + 2) * 4, st));
-    fine_expand_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+    fine_expand_kernel<false><<<ntiles, kSeedThreads, 0, st>>>(iv, idx->more_views.as<index_view>(), nparts, rec_stride, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                                              ws.rec.as<uint4>(), ws.size.as<uint32_t>(), fb.table_off.as<uint64_t>(), tkey, trow,
                                                              fb.wbegin.as<double>(), fb.wend.as<double>(), ws.tile_cand.as<uint32_t>(), nullptr,
                                                              fb.row_cnt.as<uint32_t>(), nullptr, nullptr);
@@ -1242,7 +1254,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_TRY(ws.pay0.ensure(ctx, (Hf + 2) * 8)); MR_TRY(ws.pay1.ensure(ctx, (Hf + 2) * 8));
     MR_TRY(ws.chainL.ensure(ctx, (Hf + 2) * 16));
     if(Hf) {
-      fine_expand_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(iv, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+      fine_expand_kernel<true><<<ntiles, kSeedThreads, 0, st>>>(iv, idx->more_views.as<index_view>(), nparts, rec_stride, kk, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                                               ws.rec.as<uint4>(), ws.size.as<uint32_t>(), fb.table_off.as<uint64_t>(), tkey, trow,
                                                               fb.wbegin.as<double>(), fb.wend.as<double>(), nullptr, ws.hit_off.as<uint64_t>(),
                                                               nullptr, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>());
@@ -1392,8 +1404,6 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
   if(p->fine_mer && (p->fine_mer < idx->m || p->fine_mer > idx->k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the fine mer must lie between the psa_min and the mer length the index was built with "
                                 "(the reference builds its suffix array with min(fine mer, psa-min), create_mega_reads.cc:131-132)");
-  if(p->fine_mer && idx->nparts() > 1)
-    return ctx->fail(MR_ELIMIT, "mr_align_batch: the fine pass is not implemented for an index of several parts (text of 2^32 bases or more)");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -266,7 +266,7 @@ static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, con
   v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
   v.n = n; v.nsa = nsa; v.nseq = nseq; v.k = k; v.m = psa_min; v.mi = mi; v.tail_bits = tail_bits; v.tail_bytes = tail_bytes;
-  v.sr_base = 0; v.nseq_all = nseq;
+  v.sr_base = 0; v.nseq_all = nseq; v.own = (uint32_t)sr_start[nseq];
   MR_TRY(build_slots(idx.get()));
   v.nshort = 0;
   for(uint32_t j = 1; j <= k - psa_min; ++j) {

@@ -52,6 +52,7 @@ struct index_view {
   // tails have at most 8 bits (slot_cap >= 3); null otherwise.
   const uint2*    __restrict__ slots;
   uint32_t slot_cap;
+  uint32_t own;                    // bases of the part's own super-reads (sr_start[nseq]); n - own = extension (index.cuh header)
   uint32_t sr_base;                // global index of this part's first super-read (0 for a one-part index)
   uint32_t nseq_all;               // super-reads of the whole index (== nseq for a one-part index)
   uint64_t short_key[kMaxShort];   // padded k-mers of the tail-short suffixes (positions n-k+1 .. n-m)
@@ -264,6 +265,7 @@ __device__ __forceinline__ void index_lookup_prefix(const index_view& iv, uint64
 
 // SA entry x -> (super-read, 1-based offset) for a mer of kk bases; false when it crosses into the next sequence
 __device__ __forceinline__ bool index_locate_k(const index_view& iv, uint32_t x, uint32_t kk, uint32_t& sr, uint32_t& off) {
+  if(x >= iv.own) return false;              // a position of the extension: it belongs to the next part
   uint32_t i = __ldg(iv.blk + (x >> kBlkShift));
   while(__ldg(iv.sr_start + i + 1) <= x) ++i;
   if((uint64_t)x + kk > __ldg(iv.sr_start + i + 1)) return false;

@@ -91,7 +91,7 @@ uint64_t mr_index_checksum(const mr_index* idx) { return idx ? idx->inputs_check
 namespace {
 
 // one part: header + its sections.  Whole-index fields of the header: reserved[0] = number of parts
-// (written in the first header only; 0 in files of the one-part era), reserved[1] = sr_base of the part.
+// (written in the first header only), reserved[1] = sr_base of the part.
 int save_part(mr_context* ctx, mr_index* idx, FILE* f, pinned_buf& stage, uint32_t nparts) {
   file_header h;
   memset(&h, 0, sizeof h);
@@ -155,6 +155,7 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
   v.n = h.n; v.nsa = h.nsa; v.nseq = h.nseq; v.k = h.k; v.m = h.m; v.mi = h.mi; v.tail_bits = h.tail_bits; v.tail_bytes = h.tail_bytes;
   v.nshort = h.nshort;
   v.sr_base = (uint32_t)h.reserved[1]; v.nseq_all = h.nseq;
+  v.own = 0;                                     // set below from the loaded starts
   MR_TRY(build_slots(idx));                      // derived from counts + tails: not part of the file
   memcpy(v.short_key, h.short_key, sizeof h.short_key);
   idx->n_all = h.n; idx->nseq_all = h.nseq;
@@ -162,6 +163,7 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
     std::vector<uint32_t> st(h.nseq + 1);
     MR_CUDA(ctx, cudaMemcpy(st.data(), idx->sr_start.p, ((size_t)h.nseq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for(uint32_t i = 0; i < h.nseq; ++i) sr_len.push_back(st[i + 1] - st[i]);
+    v.own = st[h.nseq];
   }
   return MR_OK;
 }

@@ -119,21 +119,27 @@ def test_index_of_several_parts_reproduces_the_reference_fixtures(tmpdir_session
 FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}   # as in make_golden.py
 
 
+@pytest.mark.parametrize("parts", [False, True], ids=["one_part", "several_parts"])
 @pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
-def test_fine_pass_matches_reference_fixture(tmpdir_session, tmp_path, name):
+def test_fine_pass_matches_reference_fixture(tmpdir_session, tmp_path, name, parts):
     """-F (fine_aligner.cc): windows from the coarse rows, shorter mers looked up in the same suffix array (fine mer
-    below, at and above --psa-min), accept-all chaining -- against the reference's own records."""
+    below, at and above --psa-min), accept-all chaining -- against the reference's own records; also with the
+    super-reads cut into several index parts (the layout of a text of 2^32 bases or more)."""
     cfg = json.load(open(os.path.join(GOLD, name + ".json")))["config"]
     info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    env = dict(os.environ)
+    if parts:
+        nbases = sum(len(l) - 1 for l in open(info["sr"]) if not l.startswith(">"))
+        env["MR_INDEX_PART_BASES"] = str(max(1024, nbases // 3 + 1000))
     common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
               "-l", info["unitigs_len"], "-r", info["sr"], "-p", info["reads"]]
     for fine, with_coords in FINE[name]:
         out = str(tmp_path / "cmr.txt")
-        run([CMR] + common + ["-F", str(fine), "-t", "2", "-o", out])
+        run([CMR] + common + ["-F", str(fine), "-t", "2", "-o", out], env=env)
         assert open(out).read() == open(os.path.join(GOLD, "%s.fine%d.cmr.txt" % (name, fine))).read()
         if with_coords:
             out = str(tmp_path / "coords.txt")
-            run([JFA] + common + ["-F", str(fine), "-H", "--coords", out])
+            run([JFA] + common + ["-F", str(fine), "-H", "--coords", out], env=env)
             assert records(out) == records(os.path.join(GOLD, "%s.fine%d.coords.txt" % (name, fine)))
 
 

@@ -10,9 +10,9 @@
 //                                neighbours instead of the reference's SA read + text read
 //   counts uint32[4^mi+1]        exclusive prefix of the mi-mer histogram (mer_sa_imp.hpp:317-330).
 //                                mi <= m is an INTERNAL prefix length, chosen so that counts + tails
-//                                fit the 126 MB L2 when the index is small enough (C2: mi = 11,
-//                                17 MB + 36 MB) while buckets stay short; the (index, nb) a lookup
-//                                returns does not depend on it.  The reference's 4^m + 1 table is
+//                                are of the order of the 126 MB L2 when the index is small enough
+//                                (C2: mi = 12, 67 MB + 36 MB) while buckets stay short; the
+//                                (index, nb) a lookup returns does not depend on it.  The reference's 4^m + 1 table is
 //                                recomputed on demand for the parity tap (mr_index_export_counts).
 //   sr_start uint32[nseq+1], blk uint32[(n>>8)+2]: blk[b] = sequence containing base b*256
 //

@@ -115,18 +115,29 @@ struct tile_kmers {
   bool     cand[4];      // ... and still inside the first 17 bases of its N-free run: toggles `flag`
 };
 
-// Loads the tile's bases (plus look-back / look-ahead) into shared memory as codes and enumerates
-// the 4 consecutive k-mers owned by this thread.  codes[] needs kTile + 64 bytes.
-__device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
-                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t, bool every_mer = false) {
+// Loads the tile's bases (plus look-back / look-ahead) into shared memory as codes; codes[] needs
+// kTile + 64 bytes.  Returns whether this thread loaded a non-ACGT code (positions outside the read
+// count as such).  Ends with a barrier.
+__device__ __forceinline__ bool load_tile_codes(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
+                                                uint32_t tile_pos, uint32_t k, uint8_t* codes) {
   const int cap = k > 18 ? (int)k : 18;        // run length is only needed up to max(k, 18)
   const int LB  = cap - (int)k;
   const int total = LB + kTile + (int)k - 1;
+  bool broke = false;
   for(int i = threadIdx.x; i < total; i += kSeedThreads) {
     const int64_t p = (int64_t)tile_pos - LB + i;
-    codes[i] = (p >= 0 && p < (int64_t)rlen) ? base_code(__ldcs(bases + rstart + p)) : (uint8_t)4;
+    const uint8_t c = (p >= 0 && p < (int64_t)rlen) ? base_code(__ldcs(bases + rstart + p)) : (uint8_t)4;
+    codes[i] = c;
+    broke |= c == 4;
   }
   __syncthreads();
+  return broke;
+}
+
+// Enumerates the 4 consecutive k-mers owned by this thread from the codes of load_tile_codes.
+__device__ __forceinline__ void tile_kmers_from_codes(uint32_t k, const uint8_t* codes, tile_kmers& t, bool every_mer = false) {
+  const int cap = k > 18 ? (int)k : 18;
+  const int LB  = cap - (int)k;
   const int s0 = threadIdx.x * 4;
   const uint64_t mask = (1ULL << (2 * k)) - 1;
   const unsigned top = 2 * (k - 1);
@@ -154,6 +165,12 @@ __device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, u
   }
 }
 
+__device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
+                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t, bool every_mer = false) {
+  (void)load_tile_codes(bases, rstart, rlen, tile_pos, k, codes);
+  tile_kmers_from_codes(k, codes, t, every_mer);
+}
+
 // pass 0 (only when k <= 17): number of flag-toggling k-mers per tile
 __global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ read_start,
                                                                    const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
@@ -163,8 +180,12 @@ __global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(const char* __
   if(threadIdx.x == 0) total = 0;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
+  // A k-mer toggles the flag only inside the first 17 bases of an N-free run (run <= 17): a tile whose
+  // window holds no run start -- almost every tile -- has none, and skips the k-mer arithmetic.
+  const bool broke = load_tile_codes(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes);
+  if(!__syncthreads_or(broke)) { if(threadIdx.x == 0) tile_cand[blockIdx.x] = 0; return; }
   tile_kmers t;
-  enumerate_tile(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes, t);
+  tile_kmers_from_codes(k, codes, t);
   const uint32_t c = (uint32_t)t.cand[0] + t.cand[1] + t.cand[2] + t.cand[3];
   if(c) atomicAdd(&total, c);
   __syncthreads();

@@ -97,6 +97,14 @@ __global__ void __launch_bounds__(256) blk_table_kernel(const uint32_t* __restri
   blk[b] = lo;
 }
 
+__global__ void __launch_bounds__(256) blkx_kernel(const uint32_t* __restrict__ blk, const uint32_t* __restrict__ sr_start, uint32_t nblk,
+                                                   uint4* __restrict__ blkx) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= nblk) return;
+  const uint32_t i = blk[b];
+  blkx[b] = make_uint4(i, sr_start[i], sr_start[i + 1], 0u);
+}
+
 __global__ void __launch_bounds__(256) widen_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
@@ -284,10 +292,18 @@ static int build_part(mr_context* ctx, const uint64_t* text2bit, uint64_t n, con
   return MR_OK;
 }
 
-// slot table of a part whose counts and tails are in place (after a build or a load)
+// derived tables of a part whose arrays are in place (after a build or a load): blkx, and the slot table
 int build_slots(mr_index* idx) {
   mr_context* ctx = idx->ctx;
   index_view& v = idx->view;
+  {
+    const uint32_t nblk = (uint32_t)(idx->n >> kBlkShift) + 1;
+    MR_TRY(idx->blkx.ensure(ctx, (size_t)nblk * sizeof(uint4)));
+    blkx_kernel<<<div_up(nblk, 256), 256, 0, ctx->stream>>>(idx->blk.as<uint32_t>(), idx->sr_start.as<uint32_t>(), nblk, idx->blkx.as<uint4>());
+    MR_LAUNCHED(ctx);
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    v.blkx = idx->blkx.as<uint4>();
+  }
   v.slots = nullptr; v.slot_cap = 0;
   // Off unless MR_SLOTS=1.  Measured on the bench workload (mi = 12, 134 MB of slots instead of 67 MB of
   // counts): seed lookup 30.2 -> 35.2 ms per step although only half as many tail entries are

@@ -44,6 +44,7 @@ struct index_view {
   const uint32_t* __restrict__ sa;
   const uint32_t* __restrict__ sr_start;
   const uint32_t* __restrict__ blk;
+  const uint4*    __restrict__ blkx;   // blkx[b] = { blk[b], sr_start[blk[b]], sr_start[blk[b] + 1], 0 }: one load locates a hit
   uint64_t n;
   uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort;
   // slots[p] = { counts[p], min(bucket size, 255) | tails of the bucket << 8 } for buckets of at most
@@ -67,6 +68,7 @@ struct mr_index {
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;
   dev_buf  slots;                    // uint2[4^mi]: see index_view::slots
+  dev_buf  blkx;                     // uint4[(n>>8)+1]: see index_view::blkx (derived; not in index files)
   dev_buf  lut;                      // counts and tails live side by side in this one allocation, so that
                                      // a single L2 access-policy window covers what a lookup reads
   int alloc_lut(mr_context* c, size_t counts_bytes, size_t tails_bytes) {
@@ -266,21 +268,23 @@ __device__ __forceinline__ void index_lookup_prefix(const index_view& iv, uint64
 // SA entry x -> (super-read, 1-based offset) for a mer of kk bases; false when it crosses into the next sequence
 __device__ __forceinline__ bool index_locate_k(const index_view& iv, uint32_t x, uint32_t kk, uint32_t& sr, uint32_t& off) {
   if(x >= iv.own) return false;              // a position of the extension: it belongs to the next part
-  uint32_t i = __ldg(iv.blk + (x >> kBlkShift));
-  while(__ldg(iv.sr_start + i + 1) <= x) ++i;
-  if((uint64_t)x + kk > __ldg(iv.sr_start + i + 1)) return false;
+  const uint4 b = __ldg(iv.blkx + (x >> kBlkShift));
+  uint32_t i = b.x, s0 = b.y, s1 = b.z;
+  while(s1 <= x) { ++i; s0 = s1; s1 = __ldg(iv.sr_start + i + 1); }
+  if((uint64_t)x + kk > s1) return false;
   sr  = i;
-  off = x - __ldg(iv.sr_start + i) + 1;
+  off = x - s0 + 1;
   return true;
 }
 
 // SA entry x -> (super-read, 1-based offset); false when x + k crosses into the next sequence
 // (pos_iterator::operator++, superread_parser.hpp:110-134)
 __device__ __forceinline__ bool index_locate(const index_view& iv, uint32_t x, uint32_t& sr, uint32_t& off) {
-  uint32_t i = __ldg(iv.blk + (x >> kBlkShift));
-  while(__ldg(iv.sr_start + i + 1) <= x) ++i;
-  if((uint64_t)x + iv.k > __ldg(iv.sr_start + i + 1)) return false;
+  const uint4 b = __ldg(iv.blkx + (x >> kBlkShift));     // sequence of the block's first base and its bounds
+  uint32_t i = b.x, s0 = b.y, s1 = b.z;
+  while(s1 <= x) { ++i; s0 = s1; s1 = __ldg(iv.sr_start + i + 1); }
+  if((uint64_t)x + iv.k > s1) return false;
   sr  = i;
-  off = x - __ldg(iv.sr_start + i) + 1;
+  off = x - s0 + 1;
   return true;
 }

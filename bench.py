@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=int, default=WORKLOAD["genome"])
     ap.add_argument("--coverage", type=float, default=WORKLOAD["coverage"])
+    ap.add_argument("--config", default="yeast", choices=["yeast", "human"],
+                    help="yeast: BASELINE.json configs[1] (the metric's configuration, default); human: the shape of configs[3] on "
+                         "the GPUs given -- 3.1 Gbp genome with 20 %% repeats, > 2^32 super-read bases (an index of several parts), "
+                         "15 kbp reads at 15 %% error, a 0.2x slice of reads per GPU unless --coverage is given")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--batch-bases", type=int, default=32 << 20)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0: auto)")
@@ -58,7 +62,11 @@ def parse_args():
 def data_files(args):
     """Rank 0 generates the synthetic inputs once; everybody else waits for the done marker."""
     w = dict(WORKLOAD, genome=args.genome, coverage=args.coverage)
-    tag = "g%d_c%g_s%d" % (w["genome"], w["coverage"], w["seed"])
+    if args.config == "human":
+        w.update(genome=3_100_000_000 if args.genome == WORKLOAD["genome"] else args.genome,
+                 coverage=0.2 if args.coverage == WORKLOAD["coverage"] else args.coverage,
+                 read_len=15000, error=0.15, sr_cov=1.4, repeat_frac=0.2, seed=45)
+    tag = "g%d_c%g_s%d_r%g_l%d" % (w["genome"], w["coverage"], w["seed"], w["repeat_frac"], w["read_len"])
     d = os.path.join(os.environ.get("MR_BENCH_DIR", "/tmp/pacbio_b200_bench"), tag)
     prefix = os.path.join(d, "synth")
     done = prefix + ".done"
@@ -262,8 +270,10 @@ def reference_arm(args, w, files):
 
 
 def config_dict(args, w):
-    return {"workload": "configs[1]: synthetic yeast-size genome %d bp, %gx simulated %d bp PacBio reads at %g%% error, "
-                        "k=%d, create_mega_reads production flags" % (w["genome"], w["coverage"], w["read_len"],
+    name = "configs[1]: synthetic yeast-size genome" if args.config == "yeast" else \
+        "configs[3] shape: synthetic human-size genome (%g%% repeats, %gx super-reads)," % (100 * w["repeat_frac"], w["sr_cov"])
+    return {"workload": "%s %d bp, %gx simulated %d bp PacBio reads at %g%% error, "
+                        "k=%d, create_mega_reads production flags" % (name, w["genome"], w["coverage"], w["read_len"],
                                                                       100 * w["error"], w["mer"]),
             "genome_bp": w["genome"], "coverage": w["coverage"], "read_len": w["read_len"], "error": w["error"],
             "mer": w["mer"], "psa_min": w["psa_min"], "unitig_k": w["unitig_k"], "batch_bases": args.batch_bases,
@@ -327,6 +337,8 @@ def ours(args, w, files):
     # index file round trip: what a second process pays instead of the build
     index_io = None
     try:
+        if H.mrh_tool_sr_bases(tool) > 500_000_000:
+            raise RuntimeError("skipped: index of more than 0.5 G super-read bases (tens of GB on disk)")
         path = os.path.join(os.path.dirname(files["sr"]), "index.rank%d.bin" % rank).encode()
         t1 = time.perf_counter()
         if L.mr_index_save(idx, path) != 0:
@@ -464,8 +476,9 @@ def ours(args, w, files):
     if phase:
         T = total_bases * args.steps
         kern = "seed lookup"
-        alg = T * 5 + counters["lists"] * 16 + counters["lookups"] * 16 + counters["tails"] * 1
-        launches_k = nbatches * args.steps
+        nparts = int(L.mr_index_parts(idx))           # an index of several parts: every part is probed for every k-mer
+        alg = T * 5 + counters["lists"] * 16 + counters["lookups"] * 16 * nparts + counters["tails"] * 1
+        launches_k = nbatches * args.steps * nparts
         achieved = alg / phase[kern] / 1e9 if phase.get(kern, 0) > 0 else 0.0
         traffic = None
         try:                                     # dram bytes per launch from the committed ncu --set full capture
@@ -485,7 +498,7 @@ def ours(args, w, files):
             tbl = int((4 ** 12 + 1) * 4 + H.mrh_tool_sr_bases(tool))       # prefix table + 8-bit tails of this index
             if L.mr_selftest_random_gather(ctx, 1 << 30, 1 << 28, C.byref(g1)) == 0 and \
                L.mr_selftest_random_gather(ctx, tbl, 1 << 28, C.byref(g2)) == 0:
-                acc = (2 * counters["lookups"] + counters["buckets"]) / phase[kern] / 1e9
+                acc = (2 * counters["lookups"] * nparts + counters["buckets"]) / phase[kern] / 1e9
                 hit = None
                 try:
                     hit = json.load(open(os.path.join(ROOT, "profiles", "r01_seed_lookup_summary.json")))["l2_sector_hit_rate_pct"] / 100.0
@@ -539,7 +552,7 @@ def ours(args, w, files):
                         "stage_busy_ms_last_step": {"mr_align_batch": 1e3 * st_align.value, "host_format": 1e3 * st_format.value},
                         "timing": "wall clock (includes host tiling/printing), max over ranks"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "index_build": {"file_round_trip": index_io, "seconds_total": index_s, "device_phases_s": index_timers,
+                "index_build": {"file_round_trip": index_io, "seconds_total": index_s, "parts": int(L.mr_index_parts(idx)), "device_phases_s": index_timers,
                                 "superread_bases": int(H.mrh_tool_sr_bases(tool)), "superreads": int(H.mrh_tool_sr_count(tool))},
                 "work_per_step": {"read_bases": int(total_bases), "reads": int(H.mrh_tool_nreads(tool)), "batches": nbatches,
                                   "kmers_looked_up": counters["lookups"] // max(1, args.steps),

@@ -62,7 +62,7 @@ def parse_args():
 def data_files(args):
     """Rank 0 generates the synthetic inputs once; everybody else waits for the done marker."""
     w = dict(WORKLOAD, genome=args.genome, coverage=args.coverage)
-    if args.config == "human":
+    if getattr(args, "config", "yeast") == "human":
         w.update(genome=3_100_000_000 if args.genome == WORKLOAD["genome"] else args.genome,
                  coverage=0.2 if args.coverage == WORKLOAD["coverage"] else args.coverage,
                  read_len=15000, error=0.15, sr_cov=1.4, repeat_frac=0.2, seed=45)
@@ -270,7 +270,7 @@ def reference_arm(args, w, files):
 
 
 def config_dict(args, w):
-    name = "configs[1]: synthetic yeast-size genome" if args.config == "yeast" else \
+    name = "configs[1]: synthetic yeast-size genome" if getattr(args, "config", "yeast") == "yeast" else \
         "configs[3] shape: synthetic human-size genome (%g%% repeats, %gx super-reads)," % (100 * w["repeat_frac"], w["sr_cov"])
     return {"workload": "%s %d bp, %gx simulated %d bp PacBio reads at %g%% error, "
                         "k=%d, create_mega_reads production flags" % (name, w["genome"], w["coverage"], w["read_len"],

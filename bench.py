@@ -65,7 +65,8 @@ def data_files(args):
     if getattr(args, "config", "yeast") == "human":
         w.update(genome=3_100_000_000 if args.genome == WORKLOAD["genome"] else args.genome,
                  coverage=0.2 if args.coverage == WORKLOAD["coverage"] else args.coverage,
-                 read_len=15000, error=0.15, sr_cov=1.4, repeat_frac=0.2, seed=45)
+                 read_len=15000, error=0.15, sr_cov=1.4, repeat_frac=0.2, seed=45,
+                 mer=17)                       # mega_reads_assemble.sh:10 (MER=17): at 15 a random mer has ~8 chance matches in 8.7 G bases
     tag = "g%d_c%g_s%d_r%g_l%d" % (w["genome"], w["coverage"], w["seed"], w["repeat_frac"], w["read_len"])
     d = os.path.join(os.environ.get("MR_BENCH_DIR", "/tmp/pacbio_b200_bench"), tag)
     prefix = os.path.join(d, "synth")

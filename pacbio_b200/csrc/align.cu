@@ -922,26 +922,47 @@ __global__ void __launch_bounds__(256) bucket_rows_kernel(uint64_t n, const uint
   slot[read_coords[r] + atomicAdd(cursor + r, 1u)] = (uint32_t)i;
 }
 
+// Order of a read's rows by (rs, re, ql, super-read, iteration) -- create_mega_reads.cc:69-77 plus the
+// canonical tie rule -- by counting, for every row, the rows that come before it.  The five keys of a
+// row are first gathered next to each other in slot order (row_keys_kernel), so that the quadratic
+// loop reads one contiguous, warp-uniform stream; a read with many rows (repeats: thousands) gets a
+// whole CTA, the usual read (a dozen rows) one warp.
+struct row_key { int32_t rs, re; uint32_t ql, sr, iter; };
+__device__ __forceinline__ bool row_key_less(const row_key& b, const row_key& a) {
+  return b.rs < a.rs || (b.rs == a.rs && (b.re < a.re || (b.re == a.re && (b.ql < a.ql || (b.ql == a.ql && (b.sr < a.sr || (b.sr == a.sr && b.iter < a.iter)))))));
+}
+__global__ void __launch_bounds__(256) row_keys_kernel(uint64_t S, const uint32_t* __restrict__ slot,
+                                                       const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
+                                                       const uint32_t* __restrict__ ql, const uint32_t* __restrict__ sr,
+                                                       const uint32_t* __restrict__ iter, int4* __restrict__ k4, uint32_t* __restrict__ k5) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= S) return;
+  const uint32_t me = slot[i];
+  k4[i] = make_int4(rs[me], re[me], (int)ql[me], (int)sr[me]);
+  k5[i] = iter[me];
+}
+constexpr uint32_t kRankWarpMax = 96;     // rows of a read ranked by one warp; more: by a CTA of its own
+template<bool kBig>
 __global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
-                                                         const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
-                                                         const uint32_t* __restrict__ ql, const uint32_t* __restrict__ sr,
-                                                         const uint32_t* __restrict__ iter, uint32_t* __restrict__ order) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                         const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
+                                                         uint32_t* __restrict__ order) {
+  uint32_t r, first, step;
+  if(kBig) { r = blockIdx.x; first = threadIdx.x; step = blockDim.x; }
+  else     { r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; first = threadIdx.x & 31; step = 32; }
   if(r >= nreads) return;
   const uint64_t b = read_coords[r];
   const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
-  for(uint32_t e = lane; e < c; e += 32) {
-    const uint32_t me = slot[b + e];
-    const int32_t a0 = rs[me], a1 = re[me]; const uint32_t a2 = ql[me], a3 = sr[me], a4 = iter[me];
+  if(kBig ? c <= kRankWarpMax : c > kRankWarpMax) return;
+  for(uint32_t e = first; e < c; e += step) {
+    const int4 a4 = k4[b + e];
+    const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, k5[b + e] };
     uint32_t rank = 0;
     for(uint32_t f = 0; f < c; ++f) {
-      const uint32_t o = slot[b + f];
-      const int32_t b0 = rs[o], b1 = re[o]; const uint32_t b2 = ql[o], b3 = sr[o], b4 = iter[o];
-      const bool less = b0 < a0 || (b0 == a0 && (b1 < a1 || (b1 == a1 && (b2 < a2 || (b2 == a2 && (b3 < a3 || (b3 == a3 && b4 < a4)))))));
-      rank += less;
+      const int4 o4 = __ldg(k4 + b + f);
+      const row_key o = { o4.x, o4.y, (uint32_t)o4.z, (uint32_t)o4.w, __ldg(k5 + b + f) };
+      rank += row_key_less(o, a);
     }
-    order[b + rank] = me;
+    order[b + rank] = slot[b + e];
   }
 }
 
@@ -1345,9 +1366,18 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     bucket_rows_kernel<<<div_up(S, 256), 256, 0, st>>>(S, A.sv.read, ws.read_coords.as<uint64_t>(), ws.read_cursor.as<uint32_t>(),
                                                        ws.slot.as<uint32_t>());
     MR_LAUNCHED(ctx);
-    rank_rows_kernel<<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
-                                                                         A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, A.sv.iter, ws.order.as<uint32_t>());
+    MR_TRY(ws.rowkey4.ensure(ctx, S * sizeof(int4))); MR_TRY(ws.rowkey5.ensure(ctx, S * sizeof(uint32_t)));
+    row_keys_kernel<<<div_up(S, 256), 256, 0, st>>>(S, ws.slot.as<uint32_t>(), A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, A.sv.iter,
+                                                    ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>());
     MR_LAUNCHED(ctx);
+    rank_rows_kernel<false><<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+                                                                                ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), ws.order.as<uint32_t>());
+    MR_LAUNCHED(ctx);
+    if(S > kRankWarpMax) {                         // some read may have that many rows
+      rank_rows_kernel<true><<<nreads, 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), ws.order.as<uint32_t>());
+      MR_LAUNCHED(ctx);
+    }
     gather_args Gt;
     Gt.n = S; Gt.order = ws.order.as<uint32_t>(); Gt.sv = A.sv; Gt.sv_info_off = sv_info_off; Gt.out = fin;
     gather_rows_kernel<<<div_up(S, 256), 256, 0, st>>>(Gt);

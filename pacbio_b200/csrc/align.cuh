@@ -45,7 +45,7 @@ struct mr_workspace {
   dev_buf key0, key1, pay0, pay1, chainL, group_start;
   dev_buf sv_i32, sv_u32, sv_f64, sv_u64, sv_u8;        // survivors, unsorted
   dev_buf fin_i32, fin_u32, fin_f64, fin_u64, fin_u8;   // final rows
-  dev_buf read_cnt, read_coords, read_cursor, slot, order;
+  dev_buf read_cnt, read_coords, read_cursor, slot, order, rowkey4, rowkey5;
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
   dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay, removed;

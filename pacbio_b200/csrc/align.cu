@@ -941,18 +941,17 @@ __global__ void __launch_bounds__(256) row_keys_kernel(uint64_t S, const uint32_
   k4[i] = make_int4(rs[me], re[me], (int)ql[me], (int)sr[me]);
   k5[i] = iter[me];
 }
-constexpr uint32_t kRankWarpMax = 96;     // rows of a read ranked by one warp; more: by a CTA of its own
 template<bool kBig>
 __global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
                                                          const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
-                                                         uint32_t* __restrict__ order) {
+                                                         uint32_t warp_max, uint32_t* __restrict__ order) {
   uint32_t r, first, step;
   if(kBig) { r = blockIdx.x; first = threadIdx.x; step = blockDim.x; }
   else     { r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; first = threadIdx.x & 31; step = 32; }
   if(r >= nreads) return;
   const uint64_t b = read_coords[r];
   const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
-  if(kBig ? c <= kRankWarpMax : c > kRankWarpMax) return;
+  if(kBig ? c <= warp_max : c > warp_max) return;
   for(uint32_t e = first; e < c; e += step) {
     const int4 a4 = k4[b + e];
     const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, k5[b + e] };
@@ -1371,11 +1370,12 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>());
     MR_LAUNCHED(ctx);
     rank_rows_kernel<false><<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
-                                                                                ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), ws.order.as<uint32_t>());
+                                                                                ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(), ws.order.as<uint32_t>());
     MR_LAUNCHED(ctx);
-    if(S > kRankWarpMax) {                         // some read may have that many rows
+    if(S > (uint64_t)big_rows_threshold()) {                         // some read may have that many rows
       rank_rows_kernel<true><<<nreads, 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
-                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), ws.order.as<uint32_t>());
+                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(),
+                                                     ws.order.as<uint32_t>());
       MR_LAUNCHED(ctx);
     }
     gather_args Gt;
@@ -1394,7 +1394,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
     GA.unitig_ids = idx->unitig_ids.as<uint32_t>(); GA.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
     GA.unitig_len = idx->unitig_len.as<int32_t>(); GA.n_unitigs = idx->n_unitigs; GA.unitigs_k = p->unitigs_k;
-    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases;
+    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
     MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
     if(S) MR_TRY(launch_graph(ctx, GA));
   }
@@ -1541,7 +1541,7 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
   GA.unitig_ids = ws.path_ids.as<uint32_t>(); GA.unitig_off = ws.path_off.as<uint64_t>();
   GA.unitig_len = ws.path_ulen.as<int32_t>(); GA.n_unitigs = n_unitigs; GA.unitigs_k = p->unitigs_k;
-  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases;
+  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
   MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
   if(S) MR_TRY(launch_graph(ctx, GA));
   timer.next("result download");

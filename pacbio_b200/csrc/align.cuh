@@ -1,5 +1,6 @@
 // Shared declarations for the per-batch alignment pipeline (align.cu, graph.cu, result.cu).
 #pragma once
+#include <cstdlib>
 #include "index.cuh"
 #include "primitives.cuh"
 
@@ -123,9 +124,16 @@ struct graph_args {
   uint32_t n_unitigs, unitigs_k;
   double overlap_play, errors;
   int bases;
+  int warp_max_rows;       // reads with more rows than this get a CTA instead of a warp (big_rows_threshold())
   // outputs / scratch, one entry per row
   uint8_t *start_node, *end_node;
   int32_t *lstart, *lprev, *lpath, *lunitigs, *component, *uf_rank, *order;
   double  *imp_s, *imp_e;
 };
 int launch_graph(mr_context* ctx, const graph_args& a);
+// rows per read above which the per-read kernels (coords order, overlap graph) use a CTA instead of a
+// warp; MR_BIG_ROWS lowers it so that the tests drive the small fixtures through the CTA kernels
+inline int big_rows_threshold() {
+  static const int v = [] { const char* e = getenv("MR_BIG_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 96; }();
+  return v;
+}

@@ -116,6 +116,28 @@ def test_index_of_several_parts_reproduces_the_reference_fixtures(tmpdir_session
     assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
 
 
+@pytest.mark.parametrize("name", ["synth_g1", "synth_g2", "synth_g3"])
+def test_many_row_kernels_reproduce_the_reference_fixtures(tmpdir_session, tmp_path, name):
+    """Reads with many coords rows (repeats) get a CTA instead of a warp in the coords-order and
+    overlap-graph kernels; MR_BIG_ROWS=3 sends nearly every read of the fixtures down that path."""
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    cfg = meta["config"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
+    env = dict(os.environ, MR_BIG_ROWS="3")
+    common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+              "-r", info["sr"], "-p", info["reads"]]
+    out_u = str(tmp_path / "cmr_u.txt")
+    run([CMR] + common + ["-u", info["unitigs"], "-t", "2", "-o", out_u], env=env)
+    assert sha(open(out_u, "rb").read()) == meta["cmr_with_sequences_sha256_t1"]
+    out_c = str(tmp_path / "coords.txt")
+    run([JFA] + common + ["-l", info["unitigs_len"], "-H", "--coords", out_c], env=env)
+    assert records(out_c) == records(os.path.join(GOLD, name + ".coords.txt"))
+    # the graph stage from a coords file (longest_path_overlap_graph2) through the same kernels
+    out_lp = str(tmp_path / "lp.txt")
+    run([LPG, "-k", str(cfg["unitig_k"]), "-l", info["unitigs_len"], "-o", out_lp, os.path.join(GOLD, name + ".coords.txt")], env=env)
+    assert open(out_lp).read() == open(os.path.join(GOLD, name + ".lp.txt")).read()
+
+
 FINE = {"synth_g1": [(11, True), (14, False)], "synth_g2": [(13, False)], "synth_g3": [(12, True)]}   # as in make_golden.py
 
 
@@ -212,6 +234,8 @@ def test_larger_input_against_oracle(tmpdir_session, tmp_path, port, tiling, tri
     if bases:
         cmd.append("-b")
     env = dict(os.environ, MR_BATCH_BASES="2000000")          # several batches
+    if tiling == "maximal":
+        env["MR_BIG_ROWS"] = "8"                              # reads with more than 8 rows through the CTA kernels
     run(cmd, env=env)
     want = str(tmp_path / "oracle.txt")
     if have_ref():

@@ -1,8 +1,8 @@
 // Overlap graph between the super-reads aligned to one read: nodes ordered by implied start,
 // O(n^2) edge test (position overlap vs unitig-path dovetail overlap), longest-path DP and
-// union-find components.  One warp per read; the outer node loop is sequential as in the
-// reference, the inner loop over candidate successors runs 32 wide with a ballot for the
-// reference's `break`.  Replaces overlap_graph::thread::reset + overlap_graph::traverse
+// union-find components.  One warp per read (graph_kernel) or, for a read with many rows, one CTA
+// (graph_big_kernel); the outer node loop is sequential as in the reference, the inner loop over
+// candidate successors runs 32 (256) wide with a ballot for the reference's `break`.  Replaces overlap_graph::thread::reset + overlap_graph::traverse
 // (overlap_graph.hpp:24-34,177-196, overlap_graph.cc:7-59, union_find.cc:6-24,
 // super_read_name.cc:49-72).
 #include "align.cuh"

@@ -31,11 +31,11 @@ static int setup_final_rows(mr_context* ctx, mr_workspace& ws, uint64_t Sc, coor
 }
 
 static int setup_graph_nodes(mr_context* ctx, mr_workspace& ws, uint64_t Sc, graph_args& GA) {
-  MR_TRY(ws.node_i32.ensure(ctx, Sc * 4 * 7)); MR_TRY(ws.node_u8.ensure(ctx, Sc * 2)); MR_TRY(ws.node_f64.ensure(ctx, Sc * 8 * 2));
+  MR_TRY(ws.node_i32.ensure(ctx, Sc * 4 * 7)); MR_TRY(ws.node_u8.ensure(ctx, Sc * 2)); MR_TRY(ws.node_f64.ensure(ctx, Sc * 8 * 5));
   { int32_t* b = ws.node_i32.as<int32_t>(); GA.lstart = b; GA.lprev = b + Sc; GA.lpath = b + 2 * Sc; GA.lunitigs = b + 3 * Sc;
     GA.component = b + 4 * Sc; GA.uf_rank = b + 5 * Sc; GA.order = b + 6 * Sc; }
   { uint8_t* b = ws.node_u8.as<uint8_t>(); GA.start_node = b; GA.end_node = b + Sc; }
-  { double* b = ws.node_f64.as<double>(); GA.imp_s = b; GA.imp_e = b + Sc; }
+  { double* b = ws.node_f64.as<double>(); GA.imp_s = b; GA.imp_e = b + Sc; GA.ord_s = b + 2 * Sc; GA.ord_e = b + 3 * Sc; GA.ord_err = b + 4 * Sc; }
   return MR_OK;
 }
 
@@ -1394,7 +1394,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
     GA.unitig_ids = idx->unitig_ids.as<uint32_t>(); GA.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
     GA.unitig_len = idx->unitig_len.as<int32_t>(); GA.n_unitigs = idx->n_unitigs; GA.unitigs_k = p->unitigs_k;
-    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
+    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold(); GA.cta_max_rows = std::max(big_rows_threshold(), huge_rows_threshold());
     MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
     if(S) MR_TRY(launch_graph(ctx, GA));
   }
@@ -1541,7 +1541,7 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
   GA.unitig_ids = ws.path_ids.as<uint32_t>(); GA.unitig_off = ws.path_off.as<uint64_t>();
   GA.unitig_len = ws.path_ulen.as<int32_t>(); GA.n_unitigs = n_unitigs; GA.unitigs_k = p->unitigs_k;
-  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
+  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold(); GA.cta_max_rows = std::max(big_rows_threshold(), huge_rows_threshold());
   MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
   if(S) MR_TRY(launch_graph(ctx, GA));
   timer.next("result download");

@@ -125,6 +125,8 @@ struct graph_args {
   double overlap_play, errors;
   int bases;
   int warp_max_rows;       // reads with more rows than this get a CTA instead of a warp (big_rows_threshold())
+  int cta_max_rows;        // ... and above this a CTA of 1024 threads instead of 256 (huge_rows_threshold())
+  double *ord_s, *ord_e, *ord_err;   // scratch of the CTA kernels: imp_s, imp_e, avg_err in node order
   // outputs / scratch, one entry per row
   uint8_t *start_node, *end_node;
   int32_t *lstart, *lprev, *lpath, *lunitigs, *component, *uf_rank, *order;
@@ -133,6 +135,10 @@ struct graph_args {
 int launch_graph(mr_context* ctx, const graph_args& a);
 // rows per read above which the per-read kernels (coords order, overlap graph) use a CTA instead of a
 // warp; MR_BIG_ROWS lowers it so that the tests drive the small fixtures through the CTA kernels
+inline int huge_rows_threshold() {
+  static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 2048; }();
+  return v;
+}
 inline int big_rows_threshold() {
   static const int v = [] { const char* e = getenv("MR_BIG_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 96; }();
   return v;

@@ -188,12 +188,13 @@ __global__ void __launch_bounds__(128) graph_kernel(graph_args A) {
   }
 }
 
-// The same for a read with many rows (repeats: hundreds to thousands): one CTA per read.  The outer
+// The same for a read with many rows (repeats: hundreds to thousands): one CTA per read, of 256 threads
+// up to cta_max_rows rows and of 1024 above (the scan of a node's successors takes rows / threads rounds).  The outer
 // node loop stays sequential; the candidate successors are tested kBigThreads at a time, the
 // reference's `break` becomes the first flagged thread of the block, and the unions of a round are
 // still done by one thread in successor order.
-constexpr int kBigThreads = 256;
-__global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A) {
+template<int kBigThreads>
+__global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A, int min_rows, int max_rows) {
   __shared__ int32_t  edge_j[kBigThreads];
   __shared__ unsigned s_brk[kBigThreads / 32], s_edge[kBigThreads / 32];
   const int tid = (int)threadIdx.x;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A) {
   if(r >= A.nreads) return;
   const uint64_t b = A.read_coords[r];
   const int n = (int)(A.read_coords[r + 1] - b);
-  if(n <= A.warp_max_rows) return;
+  if(n <= min_rows || n > max_rows) return;
   const double rl = (double)A.read_len[r];
   const double K = (double)A.unitigs_k;
   int32_t* parent = A.component + b;
@@ -211,6 +212,10 @@ __global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A) {
   int32_t* order  = A.order + b;
   double*  imp_s  = A.imp_s + b;
   double*  imp_e  = A.imp_e + b;
+  // the same three values per node in node ORDER: the successor scan reads them without going through order[]
+  double*  ord_s   = A.ord_s + b;
+  double*  ord_e   = A.ord_e + b;
+  double*  ord_err = A.ord_err + b;
 
   for(int i = tid; i < n; i += kBigThreads) {
     const uint64_t row = b + i;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A) {
       rk += (sj < s || (sj == s && ej < e)) || (sj == s && ej == e && j < i);
     }
     order[rk] = i;
+    ord_s[rk] = s; ord_e[rk] = e; ord_err[rk] = A.c.avg_err[b + i];
   }
   __syncthreads();
 
@@ -251,10 +257,10 @@ __global__ void __launch_bounds__(kBigThreads) graph_big_kernel(graph_args A) {
       const bool in = bb < n;
       const int jj = in ? order[bb] : 0;
       const uint64_t row_j = b + jj;
-      const double is_j = imp_s[jj], ie_j = imp_e[jj];
+      const double is_j = in ? ord_s[bb] : 0.0, ie_j = in ? ord_e[bb] : 0.0;
       const bool skip = !in || is_j <= 1 || ie_i > ie_j + 31;
       const double position_len = ie_i - is_j;
-      const double error1 = err_i + A.c.avg_err[row_j];
+      const double error1 = err_i + (in ? ord_err[bb] : 0.0);
       const double error  = A.errors * error1;
       const double ppl = position_len * A.overlap_play;
       const bool brk = !skip && (ppl + error < K);
@@ -341,7 +347,10 @@ int launch_graph(mr_context* ctx, const graph_args& a) {
   if(a.nreads == 0) return MR_OK;
   graph_kernel<<<div_up((uint64_t)a.nreads * 32, 128), 128, 0, ctx->stream>>>(a);
   MR_LAUNCHED(ctx);
-  graph_big_kernel<<<a.nreads, kBigThreads, 0, ctx->stream>>>(a);      // returns at once for the usual read
+  // reads with many rows: a CTA each (the kernels return at once for every other read)
+  graph_big_kernel<256><<<a.nreads, 256, 0, ctx->stream>>>(a, a.warp_max_rows, a.cta_max_rows);
+  MR_LAUNCHED(ctx);
+  graph_big_kernel<1024><<<a.nreads, 1024, 0, ctx->stream>>>(a, a.cta_max_rows, 0x7fffffff);
   MR_LAUNCHED(ctx);
   return MR_OK;
 }

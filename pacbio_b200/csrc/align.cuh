@@ -136,7 +136,7 @@ int launch_graph(mr_context* ctx, const graph_args& a);
 // rows per read above which the per-read kernels (coords order, overlap graph) use a CTA instead of a
 // warp; MR_BIG_ROWS lowers it so that the tests drive the small fixtures through the CTA kernels
 inline int huge_rows_threshold() {
-  static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 2048; }();
+  static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 0x7fffffff; }();      // off by default: measured slower
   return v;
 }
 inline int big_rows_threshold() {

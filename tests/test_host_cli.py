@@ -188,3 +188,24 @@ def test_host_parsers_match_oracle_inputs(tmp_path):
     for i in (0, 1, 31, 32, 33, 5000, 9467):
         assert (int(sr.text2bit[i // 32]) >> (2 * (i % 32))) & 3 == "ACGT".index(seq[i])
     assert api.parse_sr_name("12F_7R") == [24, 15] and api.parse_sr_name("xF_7R") == []
+
+
+def test_bench_workload_shapes(tmp_path, monkeypatch):
+    """bench.py's two workload shapes (configs[1] by default, --config human for configs[3]) generate their
+    inputs with the parameters they name; scaled down here through --genome / --coverage."""
+    import argparse
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setenv("MR_BENCH_DIR", str(tmp_path))
+    monkeypatch.delenv("RANK", raising=False)
+    a = argparse.Namespace(gpus=1, genome=60000, coverage=1.0, config="human", batch_bases=1 << 20)
+    w, files = bench.data_files(a)
+    assert (w["mer"], w["read_len"], w["repeat_frac"], w["sr_cov"]) == (17, 15000, 0.2, 1.4)
+    assert all(os.path.exists(files[k]) for k in ("sr", "reads", "unitigs", "unitigs_len"))
+    assert files["info"]["superread_bases"] > 60000 and files["info"]["reads"] >= 3
+    assert "configs[3]" in bench.config_dict(a, w)["workload"]
+    b = argparse.Namespace(gpus=1, genome=60000, coverage=1.0, config="yeast", batch_bases=1 << 20)
+    w2, files2 = bench.data_files(b)
+    assert (w2["mer"], w2["read_len"]) == (15, 10000) and files2["prefix"] != files["prefix"]
+    assert "configs[1]" in bench.config_dict(b, w2)["workload"]

@@ -20,6 +20,8 @@ t = 1.0 + rank                                  # pretend rank r needed 1 + r se
 t_max = bench.max_over_ranks(dist, t)
 total = bench.sum_over_ranks(dist, float(reads))
 value = args.gpus * reads / t_max               # whole-job throughput = all ranks' units / slowest rank
-print(json.dumps({"rank": rank, "reads": reads, "t_max": t_max, "total": total, "value": value,
-                  "files_exist": all(os.path.exists(files[k]) for k in ("sr", "reads", "unitigs"))}))
+# one write per line: the two ranks share the launcher's stdout pipe
+sys.stdout.write(json.dumps({"rank": rank, "reads": reads, "t_max": t_max, "total": total, "value": value,
+                             "files_exist": all(os.path.exists(files[k]) for k in ("sr", "reads", "unitigs"))}) + "\n")
+sys.stdout.flush()
 dist.destroy_process_group()

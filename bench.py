@@ -14,6 +14,13 @@ one pass of the whole read set through the hot path, as a sequence of 32-Mbase b
           H2D + kernels + D2H, then mega-read tiling/printing on the host threads), wall clock
   N > 1 : one process per GPU (torchrun), index replicated, every rank aligns its own read set of
           the same size (weak scaling), no collective on the data path; barrier + max over ranks.
+  roofline : seed_lookup_kernel (the largest kernel of the step).  Besides the contract's byte figures
+          it carries `random_access`: the rate of random DRAM accesses is what bounds a k-mer lookup, and
+          its ceiling is measured in the same run (mr_selftest_random_gather).
+  --config human : the shape of BASELINE.json configs[3] on the GPUs given (3.1 Gbp genome with repeats,
+          more than 2^32 super-read bases = an index of several parts, 15 kbp reads, k = 17); not the
+          metric's configuration, reported in DESIGN.md.
+  --workload lookup : configs[4], k-mer queries against a 1 Gbp suffix array.
 """
 import argparse
 import ctypes as C

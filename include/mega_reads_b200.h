@@ -91,6 +91,10 @@ int  mr_index_export_counts(mr_index* idx, uint64_t* counts_out);
 int      mr_index_save(mr_index* idx, const char* path);
 int      mr_index_load(mr_context* ctx, const char* path, mr_index** out);
 uint64_t mr_index_checksum(const mr_index* idx);
+/* reads only the header of an index file: the checksum of the inputs it was built from, so that a
+ * caller can skip a file made for other inputs without uploading gigabytes first.  mr_index_load
+ * itself verifies a hash of the arrays against the header and fails on a corrupt or stale body. */
+int      mr_index_peek_checksum(const char* path, uint64_t* checksum);
 uint64_t mr_inputs_checksum(const uint64_t* text2bit, uint64_t n, const uint64_t* sr_start, uint32_t nseq,
                             const uint32_t* unitig_ids, const uint64_t* unitig_off, const int32_t* unitig_len,
                             uint32_t n_unitigs, uint32_t psa_min, uint32_t k);

@@ -443,7 +443,8 @@ __device__ __forceinline__ void emit_hit(const index_view& iv, uint32_t read, ui
 // offset array (8 B x read bases written and read back) is needed
 __global__ void __launch_bounds__(kSeedThreads) tile_hits_kernel(const uint64_t* __restrict__ read_start,
                                                                   const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
-                                                                  const uint32_t* __restrict__ size, uint32_t* __restrict__ tile_hits) {
+                                                                  const uint32_t* __restrict__ size, uint32_t* __restrict__ tile_hits,
+                                                                  unsigned long long* __restrict__ overflow) {
   __shared__ uint64_t sw[8];
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
@@ -457,7 +458,12 @@ __global__ void __launch_bounds__(kSeedThreads) tile_hits_kernel(const uint64_t*
   }
   uint64_t total;
   (void)prim::block_exclusive_scan_256(s, sw, total);
-  if(threadIdx.x == 0) tile_hits[blockIdx.x] = (uint32_t)total;
+  // a tile total of 2^32 or more (only without --max-count, on a degenerate text) must not wrap: the
+  // batch is refused (MR_ELIMIT) and the caller halves it
+  if(threadIdx.x == 0) {
+    tile_hits[blockIdx.x] = total > 0xffffffffULL ? 0xffffffffu : (uint32_t)total;
+    if(total > 0xffffffffULL) atomicAdd(overflow, 1ULL);
+  }
 }
 
 // kMulti: rec holds one array per part, rec_stride entries apart; a list is the concatenation of its
@@ -1074,7 +1080,8 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   }
   MR_CUDA(ctx, cudaMemsetAsync(ws.counters.p, 0, 16 * sizeof(uint64_t), st));
   unsigned long long* ctr = ws.counters.as<unsigned long long>();
-  // counters: 0 lookups, 1 raw hits, 2 invalid hits, 3 groups, 4 survivors, 5 info total
+  // counters: 0 lookups, 1 raw hits, 2 invalid hits, 3 groups, 4 survivors, 5 info total, 6 tails, 7 fine hits,
+  // 9 lists, 10 buckets, 11 tile overflow
   uint64_t h_ctr[16] = { 0 };
 
   // ---- seeds + lookups ----------------------------------------------------------------------------
@@ -1121,15 +1128,16 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   timer.next("hit expansion");
   if(ntiles) {
     tile_hits_kernel<<<ntiles, kSeedThreads, 0, st>>>(d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                                     ws.size.as<uint32_t>(), ws.tile_cand.as<uint32_t>());
+                                                     ws.size.as<uint32_t>(), ws.tile_cand.as<uint32_t>(), ctr + 11);
     MR_LAUNCHED(ctx);
   }
   // tile_off[t] = first hit slot of tile t, tile_off[ntiles] = number of hits (also in counter 1)
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 11 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, cudaStreamSynchronize(st));
+  if(h_ctr[11]) return ctx->fail(MR_ELIMIT, "mr_align_batch: 2^32 or more hits in one 1024-base tile; use --max-count");
   const uint64_t H = h_ctr[1];
   MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
   res->view.n_kmers_looked_up = h_ctr[0];
@@ -1457,12 +1465,20 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
                                 "(the reference builds its suffix array with min(fine mer, psa-min), create_mega_reads.cc:131-132)");
   if(p->run_graph && !(idx->has_unitigs && p->unitigs_k))
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
+  if(p->run_graph && !idx->unitig_ids_ok)
+    return ctx->fail(MR_EINVAL, "mr_align_batch: a super-read name refers to a k-unitig that the unitig table (-l/-u) does not have");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->timers.clear();
   phase_timer timer(ctx);
   const int rc = align_batch_impl(ctx, idx, p, d_bases, d_read_start, h_read_start, nreads, timer, out);
   cudaStreamSynchronize(ctx->stream);
   if(rc == MR_OK) timer.collect();
+  else {
+    // a failed batch may have left kernels of the chain tiers running on the side streams: the caller
+    // retries with a smaller batch, which re-sizes the very buffers they use
+    for(cudaStream_t s : ctx->aux) if(s) cudaStreamSynchronize(s);
+    cudaGetLastError();
+  }
   return rc;
 }
 
@@ -1501,6 +1517,9 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   if(S >= (1ULL << 31)) return ctx->fail(MR_ELIMIT, "mr_graph_batch: too many rows in one batch");
   if(rows->read_coords[0] != 0 || rows->read_coords[nreads] != S) return ctx->fail(MR_EINVAL, "mr_graph_batch: read_coords must span [0, ncoords]");
   uint64_t info_total = 0;
+  for(uint64_t i = 0; i < path_off[npaths]; ++i)
+    if((path_ids[i] >> 1) >= n_unitigs)
+      return ctx->fail(MR_EINVAL, "mr_graph_batch: a path refers to a k-unitig that the unitig table does not have");
   for(uint64_t i = 0; i < S; ++i) {
     if(rows->sr[i] >= npaths) return ctx->fail(MR_EINVAL, "mr_graph_batch: row refers to a path that was not given");
     if(rows->info_len[i]) info_total = std::max<uint64_t>(info_total, rows->info_off[i] + rows->info_len[i]);

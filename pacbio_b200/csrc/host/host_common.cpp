@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <map>
 #include <stdexcept>
@@ -259,6 +260,10 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
   std::vector<uint32_t> path;
   std::vector<double> weights;
   char buf[256];
+  // ids come from super-read names, lengths from the -l/-u table: the libraries refuse a table that
+  // does not cover the names (mr_align_batch, mr_graph_batch), this keeps a stray id from reading
+  // past the table all the same
+  auto ulen_of = [&](uint32_t id) -> int { return id < u.len.size() ? u.len[id] : 0; };
   for(uint32_t r = r0; r < r1; ++r) {
     const uint64_t b = v.read_coords[r];
     const int n = (int)(v.read_coords[r + 1] - b);
@@ -292,7 +297,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
           int offset = 0, su = 0;
           for(su = 0; su < ilen; su += 2) {
             if(ki[su]) break;
-            offset += u.len[row_unitig_id(srow, su / 2)];
+            offset += ulen_of(row_unitig_id(srow, su / 2));
           }
           su /= 2;
           mr.start_unitig = su;
@@ -308,7 +313,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
           int offset = 0, eu;
           for(eu = ilen - 1; eu >= 0; eu -= 2) {
             if(ki[eu]) break;
-            offset += u.len[row_unitig_id(row, eu / 2)];
+            offset += ulen_of(row_unitig_id(row, eu / 2));
           }
           eu /= 2;
           const int removed = ilen / 2 - eu;
@@ -422,7 +427,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       }
       auto path_id = [&](int i) -> uint32_t { return (size_t)i < path.size() ? (path[i] >> 1) : 0x7fffffffu; };
       int sr_len = 0;
-      for(int i = mr.start_unitig; i < mr.start_unitig + mr.nb_unitigs; ++i) sr_len += u.len[path_id(i)];
+      for(int i = mr.start_unitig; i < mr.start_unitig + mr.nb_unitigs; ++i) sr_len += ulen_of(path_id(i));
       sr_len -= (mr.nb_unitigs - 1) * ((int)o.k_len - 1);
       const uint64_t qe_out = (uint64_t)(int64_t)(sr_len + mr.end_offset) - ((uint64_t)v.ql[erow] - (uint64_t)(int64_t)v.qe[erow]);
       snprintf(buf, sizeof(buf), "%.2f %.2f %d %d %d %llu %d %.4f ", mr.imp_s, mr.imp_e, v.rs[srow], v.re[erow],
@@ -479,9 +484,13 @@ void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, cons
     format_mega_reads(v, batch, cut[t], cut[t + 1], sr, u, o, out);
   };
   if(threads == 1) { work(0); return; }
+  // an exception in a worker must reach the caller's catch, not std::terminate
+  std::vector<std::exception_ptr> errors(threads);
   std::vector<std::thread> th;
-  for(unsigned t = 0; t < threads; ++t) th.emplace_back(work, t);
+  for(unsigned t = 0; t < threads; ++t)
+    th.emplace_back([&, t]() { try { work(t); } catch(...) { errors[t] = std::current_exception(); } });
   for(auto& x : th) x.join();
+  for(auto& e : errors) if(e) std::rethrow_exception(e);
 }
 
 // default ostream formatting of a double: "%g" with 6 significant digits (jf_aligner.cc:58)

@@ -48,7 +48,8 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
     th.emplace_back([&, i]() {
       int rc = mr_context_create(devices[i], &ds.ctx[i]);
       if(rc != MR_OK) { errors[i] = std::string("mr_context_create: ") + mr_last_error(nullptr); return; }
-      if(cache && *cache) {
+      uint64_t on_disk = 0;
+      if(cache && *cache && mr_index_peek_checksum(cache, &on_disk) == MR_OK && on_disk == want) {   // header first: no upload of a file for other inputs
         mr_index* got = nullptr;
         if(mr_index_load(ds.ctx[i], cache, &got) == MR_OK) {
           if(mr_index_checksum(got) == want) { ds.idx[i] = got; loaded[i] = 1; return; }
@@ -116,7 +117,8 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   std::atomic<uint64_t> total_bases(0);
   std::string error;
   std::mutex error_mutex;
-  auto fail = [&](const std::string& msg) { std::lock_guard<std::mutex> l(error_mutex); if(error.empty()) error = msg; };
+  std::atomic<bool> failed(false);       // what the worker threads test; the text stays under the mutex
+  auto fail = [&](const std::string& msg) { std::lock_guard<std::mutex> l(error_mutex); if(error.empty()) error = msg; failed = true; };
 
   std::thread reader([&]() {
     try {
@@ -147,7 +149,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       while(to_align.pop(j)) {
         staged_job sj;
         sj.staged = nullptr;
-        if(stage_batches() && error.empty() && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
+        if(stage_batches() && !failed && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
         sj.j = std::move(j);
         staged[g]->push(std::move(sj));
@@ -158,12 +160,12 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       staged_job sj;
       while(staged[g]->pop(sj)) {
         job j = std::move(sj.j);
-        if(!error.empty()) { if(sj.staged) mr_staged_free(sj.staged); continue; }
+        if(failed) { if(sj.staged) mr_staged_free(sj.staged); continue; }
         // A batch whose hits exceed a device limit (very repeat-rich reads) or the free memory is cut
         // in halves and retried; the halves are formatted in order, so the output does not change.
         std::deque<std::unique_ptr<read_batch>> work;
         work.push_back(std::move(j.batch));
-        while(!work.empty() && error.empty()) {
+        while(!work.empty() && !failed) {
           std::unique_ptr<read_batch> b = std::move(work.front());
           work.pop_front();
           part pt;

@@ -434,6 +434,15 @@ int mr_index_create(mr_context* ctx, const uint64_t* text2bit, uint64_t n, const
     idx->n_unitigs = n_unitigs;
     const uint64_t total = unitig_off[nseq];
     idx->unitig_total = total;
+    for(uint32_t i = 0; i < nseq; ++i)
+      if(unitig_off[i + 1] < unitig_off[i]) return ctx->fail(MR_EINVAL, "mr_index_create: unitig_off must be non-decreasing");
+    // A path may name a k-unitig the -l/-u table does not have (a stray super-read name): coords and
+    // kmers_info handle that like the reference (pb_aligner.cc:103-143 clears the row's vectors), but the
+    // overlap graph indexes the length table with these ids unchecked -- mr_align_batch refuses to run
+    // it on such an index instead of reading out of bounds.
+    uint32_t max_uid = 0;
+    for(uint64_t i = 0; i < total; ++i) max_uid = std::max(max_uid, unitig_ids[i] >> 1);
+    idx->unitig_ids_ok = total == 0 || max_uid < n_unitigs;
     MR_TRY(idx->unitig_ids.ensure(ctx, (total + 1) * sizeof(uint32_t)));
     MR_TRY(idx->unitig_off.ensure(ctx, ((size_t)nseq + 1) * sizeof(uint64_t)));
     MR_TRY(idx->unitig_len.ensure(ctx, (size_t)n_unitigs * sizeof(int32_t)));

@@ -64,6 +64,8 @@ struct mr_index {
   uint64_t n = 0;
   uint32_t nsa = 0, nseq = 0, k = 0, m = 0, mi = 0, n_unitigs = 0;
   bool     has_unitigs = false;
+  bool     unitig_ids_ok = true;     // every id of the unitig paths is below n_unitigs (the overlap graph and the
+                                     // printing index unitig_len with them unchecked, as the reference does)
   uint64_t unitig_total = 0;         // entries of unitig_ids
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;

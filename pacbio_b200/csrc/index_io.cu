@@ -7,6 +7,7 @@
 // caller can tell whether a file on disk belongs to the inputs it has just parsed.
 #include "index.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -17,7 +18,9 @@ int build_slots(mr_index* idx);                                                 
 
 namespace {
 
-constexpr char     kMagic[8] = { 'M', 'R', 'B', '2', 'I', 'D', 'X', '1' };
+// version 2: reserved[2] = hash of the part's section bytes (verified by mr_index_load), reserved[3] = layout
+// tag derived from the parameters the arrays depend on (mi, tail width, block shift)
+constexpr char     kMagic[8] = { 'M', 'R', 'B', '2', 'I', 'D', 'X', '2' };
 constexpr uint32_t kSections = 9;     // text sa tails counts sr_start blk unitig_ids unitig_off unitig_len
 
 struct file_header {
@@ -36,6 +39,25 @@ inline uint64_t mix(uint64_t h, uint64_t v) {      // splitmix64 finaliser over 
   h ^= h >> 27; h *= 0x94d049bb133111ebULL;
   h ^= h >> 31;
   return h;
+}
+
+// running hash of the section bytes as they pass through the staging buffer (8 bytes per step, a
+// multiply and a rotate: several GB/s, far above the file read)
+inline uint64_t body_hash(uint64_t h, const void* p, size_t len) {
+  const unsigned char* b = (const unsigned char*)p;
+  size_t i = 0;
+  for(; i + 8 <= len; i += 8) {
+    uint64_t w;
+    memcpy(&w, b + i, 8);
+    h = (h ^ w) * 0x9e3779b97f4a7c15ULL;
+    h = (h << 29) | (h >> 35);
+  }
+  uint64_t w = 0;
+  if(i < len) { memcpy(&w, b + i, len - i); h = (h ^ w) * 0x9e3779b97f4a7c15ULL; h = (h << 29) | (h >> 35); }
+  return mix(h, len);
+}
+inline uint64_t layout_tag(uint32_t mi, uint32_t tail_bits, uint32_t tail_bytes) {
+  return mix(mix(mix(mix(0x6c61796f757432ULL, mi), tail_bits), tail_bytes), (uint64_t)kBlkShift);
 }
 
 struct section { dev_buf* buf; uint64_t bytes; };
@@ -105,15 +127,24 @@ int save_part(mr_context* ctx, mr_index* idx, FILE* f, pinned_buf& stage, uint32
   section s[kSections];
   sections_of(idx, s);
   for(uint32_t i = 0; i < kSections; ++i) h.bytes[i] = s[i].bytes;
-  if(fwrite(&h, sizeof h, 1, f) != 1) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+  h.reserved[3] = layout_tag(idx->mi, idx->view.tail_bits, idx->view.tail_bytes);
+  const long header_at = ftell(f);
+  if(header_at < 0 || fwrite(&h, sizeof h, 1, f) != 1) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+  uint64_t bh = 0x6d72626f6479ULL;
   for(uint32_t i = 0; i < kSections; ++i) {
     for(uint64_t off = 0; off < s[i].bytes; off += kChunk) {
       const size_t len = (size_t)std::min<uint64_t>(kChunk, s[i].bytes - off);
       MR_CUDA(ctx, cudaMemcpyAsync(stage.p, (const char*)s[i].buf->p + off, len, cudaMemcpyDeviceToHost, ctx->stream));
       MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      bh = body_hash(bh, stage.p, len);
       if(fwrite(stage.p, 1, len, f) != len) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
     }
   }
+  // the hash of the body is only known now: rewrite the header in place
+  h.reserved[2] = bh;
+  const long end_at = ftell(f);
+  if(end_at < 0 || fseek(f, header_at, SEEK_SET) != 0 || fwrite(&h, sizeof h, 1, f) != 1 || fseek(f, end_at, SEEK_SET) != 0)
+    return ctx->fail(MR_EINVAL, "mr_index_save: write error");
   return MR_OK;
 }
 
@@ -124,6 +155,15 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
        h.nsa == (uint32_t)(h.n - h.m + 1) && h.tail_bits == 2 * (h.k - h.mi) && h.nshort <= (uint32_t)kMaxShort &&
        (h.tail_bytes == 1 || h.tail_bytes == 2 || h.tail_bytes == 4)))
     return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
+  if(h.reserved[3] != layout_tag(h.mi, h.tail_bits, h.tail_bytes))
+    return ctx->fail(MR_EINVAL, "mr_index_load: the file was written with another array layout");
+  // the unitig sections are the only ones whose size is not implied by the fields above: bound them
+  // (a path entry per super-read base at most; unitig_off spans the super-reads of all parts, each of
+  // which has at least one base of a text of fewer than 2^34)
+  if(h.has_unitigs && (h.bytes[6] % sizeof(uint32_t) != 0 || h.bytes[6] > (1ULL << 36) || h.bytes[7] % sizeof(uint64_t) != 0 ||
+                       h.bytes[7] < ((uint64_t)h.nseq + 1) * sizeof(uint64_t) || h.bytes[7] > ((1ULL << 34) + 1) * sizeof(uint64_t) ||
+                       h.n_unitigs == 0))
+    return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header (unitig sections)");
   idx->ctx = ctx; idx->n = h.n; idx->nsa = h.nsa; idx->nseq = h.nseq; idx->k = h.k; idx->m = h.m; idx->mi = h.mi;
   idx->n_unitigs = h.n_unitigs; idx->has_unitigs = h.has_unitigs != 0;
   idx->inputs_checksum = h.inputs_checksum;
@@ -135,6 +175,8 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
   for(uint32_t i = 0; i < kSections; ++i)
     if(s[i].bytes != h.bytes[i]) return ctx->fail(MR_EINVAL, "mr_index_load: section sizes do not match the header");
   MR_TRY(idx->alloc_lut(ctx, s[3].bytes, s[2].bytes));
+  uint64_t bh = 0x6d72626f6479ULL;
+  uint32_t max_uid = 0;
   for(uint32_t i = 0; i < kSections; ++i) {
     if(s[i].bytes == 0) continue;
     MR_TRY(s[i].buf->ensure(ctx, s[i].bytes));
@@ -143,12 +185,19 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
       // two staging buffers: the file read of one chunk overlaps the upload of the previous one
       MR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which]));
       if(fread(stage[which].p, 1, len, f) != len) return ctx->fail(MR_EINVAL, "mr_index_load: file is truncated");
+      bh = body_hash(bh, stage[which].p, len);
+      if(i == 6) {                               // largest unitig id of the paths: see mr_index::unitig_ids_ok
+        const uint32_t* ids = (const uint32_t*)stage[which].p;
+        for(size_t q = 0; q < len / sizeof(uint32_t); ++q) max_uid = std::max(max_uid, ids[q] >> 1);
+      }
       MR_CUDA(ctx, cudaMemcpyAsync((char*)s[i].buf->p + off, stage[which].p, len, cudaMemcpyHostToDevice, ctx->stream));
       MR_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->stream));
       which ^= 1;
     }
   }
   MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if(bh != h.reserved[2]) return ctx->fail(MR_EINVAL, "mr_index_load: the arrays do not match the hash in the header (corrupt or stale file)");
+  idx->unitig_ids_ok = !idx->has_unitigs || idx->unitig_total == 0 || max_uid < idx->n_unitigs;
   index_view& v = idx->view;
   v.counts = idx->counts.as<uint32_t>(); v.tails = idx->tails.p; v.sa = idx->sa.as<uint32_t>();
   v.sr_start = idx->sr_start.as<uint32_t>(); v.blk = idx->blk.as<uint32_t>();
@@ -183,6 +232,15 @@ int mr_index_save(mr_index* idx, const char* path) {
   MR_TRY(save_part(ctx, idx, f.get(), stage, idx->nparts()));
   for(mr_index* part : idx->more) MR_TRY(save_part(ctx, part, f.get(), stage, 0));
   if(fflush(f.get()) != 0) return ctx->fail(MR_EINVAL, "mr_index_save: write error");
+  return MR_OK;
+}
+
+int mr_index_peek_checksum(const char* path, uint64_t* checksum) {
+  if(!path || !checksum) return MR_EINVAL;
+  std::unique_ptr<FILE, file_closer> f(fopen(path, "rb"));
+  file_header h;
+  if(!f || fread(&h, sizeof h, 1, f.get()) != 1 || memcmp(h.magic, kMagic, 8) != 0) return MR_EINVAL;
+  *checksum = h.inputs_checksum;
   return MR_OK;
 }
 

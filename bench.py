@@ -12,8 +12,14 @@ one pass of the whole read set through the hot path, as a sequence of 32-Mbase b
           every kernel of mr_align_batch_device plus its result download
   e2e   : the same pass through the public host path (mr_align_batch from page-locked host memory:
           H2D + kernels + D2H, then mega-read tiling/printing on the host threads), wall clock
-  N > 1 : one process per GPU (torchrun), index replicated, every rank aligns its own read set of
-          the same size (weak scaling), no collective on the data path; barrier + max over ranks.
+  N > 1 : one process per GPU (torchrun), index replicated, rank r aligns ITS OWN shard of the reads
+          (shard r of an N x read set drawn from the same genome: disjoint reads, same size -- weak
+          scaling), no collective on the data path; barrier + max over ranks.
+  parity : before the line is printed, the records of the reads the CPU reference was run on are
+          written by the GPU path and compared with the reference's file (per read, lines sorted;
+          reads whose coords hold an exact (rs, re, ql) tie are the reference's own coin flip,
+          SURVEY.md 0.7, and counted apart).  A difference on any other read makes the run fail.
+  cli   : wall time of the drop-in binary itself (FASTA in -> record file out), next to e2e.
   roofline : seed_lookup_kernel (the largest kernel of the step).  Besides the contract's byte figures
           it carries `random_access`: the rate of random DRAM accesses is what bounds a k-mer lookup, and
           its ceiling is measured in the same run (mr_selftest_random_gather).
@@ -35,6 +41,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# the committed r01 ncu capture of seed_lookup_kernel describes the kernel as it was in round 1: it is
+# only quoted (traffic, L2 hit rate) while the kernel is unchanged
+SEED_KERNEL_CHANGED = False
 
 WORKLOAD = dict(genome=12_000_000, coverage=50.0, read_len=10000, error=0.12, sr_cov=3.0, repeat_frac=0.0,
                 unitig_k=41, seed=43, mer=15, psa_min=13)
@@ -79,24 +89,36 @@ def data_files(args):
     prefix = os.path.join(d, "synth")
     done = prefix + ".done"
     rank = int(os.environ.get("RANK", "0"))
-    if rank == 0 and not os.path.exists(done):
-        os.makedirs(d, exist_ok=True)
+    world = int(os.environ.get("WORLD_SIZE", "1")) if getattr(args, "gpus", 1) > 1 else 1
+    shards = world if getattr(args, "impl", "ours") == "ours" else 1   # rank r aligns shard r; the CPU arm runs on shard 0
+    shard_done = lambda i: done if i == 0 else prefix + ".shard%d.done" % i
+
+    def generate(first_shard, nshards):
         gen = os.path.join(ROOT, "pacbio_b200", "tools", "gen_synth")
         if not os.path.exists(gen):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", gen + ".cc", "-o", gen])
         out = subprocess.check_output([gen, "--genome", str(w["genome"]), "--coverage", str(w["coverage"]), "--read-len",
                                        str(w["read_len"]), "--error", str(w["error"]), "--seed", str(w["seed"]),
                                        "--sr-cov", str(w["sr_cov"]), "--repeat-frac", str(w["repeat_frac"]),
-                                       "--unitig-k", str(w["unitig_k"]), "--threads", str(min(16, os.cpu_count() or 1)),
-                                       "--prefix", prefix])
-        with open(done + ".tmp", "w") as f:                 # atomically: the other ranks poll for this file
-            f.write(out.decode())
-        os.replace(done + ".tmp", done)
-    while not os.path.exists(done):
+                                       "--unitig-k", str(w["unitig_k"]), "--threads", str(min(32, os.cpu_count() or 1)),
+                                       "--shards", str(nshards), "--first-shard", str(first_shard), "--prefix", prefix])
+        for i in range(first_shard, nshards):           # atomically: the other ranks poll for these files
+            with open(shard_done(i) + ".tmp", "w") as f:
+                f.write(out.decode())
+            os.replace(shard_done(i) + ".tmp", shard_done(i))
+
+    if rank == 0:
+        os.makedirs(d, exist_ok=True)
+        missing = [i for i in range(shards) if not os.path.exists(shard_done(i))]
+        if missing:
+            generate(min(missing), shards)
+    mine = rank if shards > 1 else 0
+    while not (os.path.exists(done) and os.path.exists(shard_done(mine))):
         time.sleep(0.5)
     info = json.loads(open(done).read())
-    return w, dict(sr=prefix + ".superreads.fa", reads=prefix + ".reads.fa", unitigs=prefix + ".unitigs.fa",
-                   unitigs_len=prefix + ".unitigs_len.txt", info=info, prefix=prefix)
+    reads = prefix + ".reads.fa" if mine == 0 else prefix + ".reads.shard%d.fa" % mine
+    return w, dict(sr=prefix + ".superreads.fa", reads=reads, reads0=prefix + ".reads.fa", unitigs=prefix + ".unitigs.fa",
+                   unitigs_len=prefix + ".unitigs_len.txt", info=info, prefix=prefix, shard=mine)
 
 
 class ClockSampler:
@@ -213,23 +235,37 @@ def sum_over_ranks(dist, x):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own create_mega_reads (oracle/_ref) or, if absent, the oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_run(w, files, nreads_sample, threads):
-    """Aligns the first nreads_sample reads on the host cores; returns (bases/s of the alignment phase, meta)."""
+def write_sample(files, nreads_sample):
+    """First nreads_sample records of shard 0 (any FASTA line layout) -> (path, bases, read names)."""
     sample = files["prefix"] + ".sample%d.fa" % nreads_sample
-    nb = 0
-    with open(files["reads"]) as f, open(sample, "w") as g:
-        for i, line in enumerate(f):
-            if i >= 2 * nreads_sample:
-                break
+    nb, names = 0, []
+    with open(files["reads0"]) as f, open(sample, "w") as g:
+        for line in f:
+            if line.startswith(">"):
+                if len(names) >= nreads_sample:
+                    break
+                names.append(line[1:].split()[0] if line[1:].split() else "")
+            else:
+                nb += len(line.rstrip("\r\n"))
             g.write(line)
-            if i & 1:
-                nb += len(line) - 1
+    return sample, nb, names
+
+
+def production_flags(w, files, threads):
+    """mega_reads_assemble.sh:175-177 with the defaults of mega_reads_assemble_cluster.sh:13-15"""
+    return ["-s", "1M", "-m", str(w["mer"]), "--psa-min", str(w["psa_min"]), "--stretch-cap", "10000", "-k",
+            str(w["unitig_k"]), "-u", files["unitigs"], "-t", str(threads), "-B", "17", "--max-count", "5000", "-d",
+            "0.029", "-r", files["sr"]]
+
+
+def cpu_run(w, files, nreads_sample, threads):
+    """Aligns the first nreads_sample reads of shard 0 on the host cores; returns (bases/s of the
+    alignment phase, meta).  The records stay in meta["out"] for the parity gate."""
+    sample, nb, names = write_sample(files, nreads_sample)
     ref = os.path.join(ROOT, "oracle", "_ref", "create_mega_reads")
     out = files["prefix"] + ".cpu.out"
     if os.path.exists(ref):
-        cmd = [ref, "-s", "1M", "-m", str(w["mer"]), "--psa-min", str(w["psa_min"]), "--stretch-cap", "10000", "-k",
-               str(w["unitig_k"]), "-u", files["unitigs"], "-t", str(threads), "-B", "17", "--max-count", "5000", "-d",
-               "0.029", "-r", files["sr"], "-p", sample, "-o", out]
+        cmd = [ref] + production_flags(w, files, threads) + ["-p", sample, "-o", out]
         t0 = time.perf_counter()
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         wall = time.perf_counter() - t0
@@ -247,8 +283,8 @@ def cpu_run(w, files, nreads_sample, threads):
         from oracle_lib import Port
         nbp, ti, align_s = Port().run(0, files["sr"], sample, files["unitigs"], out, w["mer"], w["unitig_k"], threads=threads)
         kind = "port"
-    return nb / align_s, dict(kind=kind, cores=threads, bases=nb, seconds=align_s,
-                              sample="first %d reads (%d bases) of the workload, alignment phase only" % (nreads_sample, nb))
+    return nb / align_s, dict(kind=kind, cores=threads, bases=nb, seconds=align_s, out=out, sample_path=sample, names=names,
+                              sample="first %d reads (%d bases) of the workload, alignment phase only" % (len(names), nb))
 
 
 def reference_arm(args, w, files):
@@ -256,10 +292,14 @@ def reference_arm(args, w, files):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nreads = args.cpu_sample_reads or 20000          # ~200 Mbases: a few seconds of alignment on 16 cores per step
+    total_reads = int(files["info"]["reads"])
+    v0, m0 = cpu_run(w, files, min(total_reads, 2000), threads)      # sizes the steps (and warms the page cache)
+    # the whole read set when a step stays under a minute, else a bounded prefix (~30 s of alignment)
+    nreads = args.cpu_sample_reads or (total_reads if files["info"]["read_bases"] / v0 <= 60.0
+                                       else int(max(300, min(total_reads, 30.0 * v0 / w["read_len"]))))
     vals = []
     meta = None
-    for _ in range(args.warmup):
+    for _ in range(max(0, args.warmup - 1)):
         cpu_run(w, files, max(100, nreads // 10), threads)
     t_all = 0.0
     for _ in range(args.steps):
@@ -285,7 +325,148 @@ def config_dict(args, w):
                                                                       100 * w["error"], w["mer"]),
             "genome_bp": w["genome"], "coverage": w["coverage"], "read_len": w["read_len"], "error": w["error"],
             "mer": w["mer"], "psa_min": w["psa_min"], "unitig_k": w["unitig_k"], "batch_bases": args.batch_bases,
-            "l2": "inputs larger than L2 (step input >> 126 MB; index tables 0.5 GB)", "parallelism": "reads sharded x%d, index replicated" % args.gpus}
+            "l2": "inputs larger than L2: a step streams about %d MB of reads per GPU through batches of %d MB (L2: 126 MB)"
+                  % (w["genome"] * w["coverage"] / 1e6, args.batch_bases >> 20),
+            "parallelism": "reads sharded x%d (rank r aligns shard r of an %dx read set), index replicated" % (args.gpus, args.gpus)}
+
+
+def parse_records(path):
+    """create_mega_reads output -> {read name: sorted tuple of its lines} (record order is free)"""
+    recs, cur = {}, None
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                cur = line[1:]
+                recs[cur] = []
+            elif cur is not None:
+                recs[cur].append(line)
+    return {k: tuple(sorted(v)) for k, v in recs.items()}
+
+
+def reads_with_coords_ties(coords_path):
+    """Reads whose coords hold an exact (rs, re, ql) tie: the reference orders those by unordered_map pointer
+    hash + an unstable sort (create_mega_reads.cc:69-77), so its own record for such a read is a coin flip."""
+    ties, cur, seen = set(), None, None
+    with open(coords_path) as f:
+        for line in f:
+            if line.startswith(">"):
+                cur, seen = line.split()[1], set()
+            else:
+                x = line.split()
+                key = (x[0], x[1], x[10])
+                if key in seen:
+                    ties.add(cur)
+                seen.add(key)
+    return ties
+
+
+def parity_gate(H, L, tool, host_threads, w, files, meta):
+    """GPU records of the reads the CPU arm aligned vs the CPU arm's file."""
+    names = meta["names"]
+    want = parse_records(meta["out"])
+    # the batches that hold the first len(names) reads of shard 0 (rank 0 loaded shard 0)
+    need, nb, have = len(names), int(H.mrh_tool_nbatches(tool)), 0
+    import pacbio_b200.api as api
+    count = 0
+    while count < nb and have < need:
+        nr = C.c_uint32()
+        H.mrh_tool_batch_starts(tool, count, C.byref(nr))
+        have += nr.value
+        count += 1
+    out = files["prefix"] + ".gpu.sample.out"
+    if H.mrh_tool_run_range(tool, host_threads, out.encode(), 0, count) < 0:
+        raise RuntimeError(H.mrh_tool_error(tool).decode())
+    sample = set(names)
+    got = {k: v for k, v in parse_records(out).items() if k in sample}
+    diff = sorted(k for k in set(got) | set(want) if got.get(k) != want.get(k))
+    ties = set()
+    if diff:                                   # which of them are coords ties: our own jf_aligner on the same sample
+        jfa = os.path.join(ROOT, "pacbio_b200", "bin", "jf_aligner")
+        coords = files["prefix"] + ".gpu.sample.coords"
+        cmd = [jfa, "-s", "1M", "-m", str(w["mer"]), "--psa-min", str(w["psa_min"]), "--stretch-cap", "10000", "-k", str(w["unitig_k"]),
+               "-l", files["unitigs_len"], "-B", "17", "--max-count", "5000", "-H", "--coords", coords, "-r", files["sr"],
+               "-p", meta["sample_path"]]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode == 0:
+            ties = reads_with_coords_ties(coords)
+    hard = [k for k in diff if k not in ties]
+    return {"records": len(want), "records_gpu": len(got), "sample_reads": len(names), "differ": len(diff), "differ_non_tie": len(hard),
+            "against": meta["kind"], "examples": hard[:3],
+            "how": "records of the first %d reads of shard 0, GPU path (mr_align_batch + host tiling/printing, written to a file) vs "
+                   "the CPU arm's file, per read with lines sorted; `differ` counts reads whose coords hold an exact (rs, re, ql) tie, "
+                   "where the reference's own record depends on unordered_map order" % len(names)}
+
+
+def file_sha256(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 24), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def cli_run(w, files, total_bases, host_threads, gpus=1):
+    """The drop-in binary itself: FASTA in -> record file out, whole process wall clock plus its own phase
+    timers (the same stderr lines the reference prints with -DSHOW_TIMING)."""
+    exe = os.path.join(ROOT, "pacbio_b200", "bin", "create_mega_reads")
+    out = files["prefix"] + ".cli.out"
+    cmd = [exe] + production_flags(w, files, host_threads) + ["-p", files["reads"], "-o", out]
+    env = dict(os.environ, MR_SHOW_TIMING="1", MR_DEVICES=os.environ.get("LOCAL_RANK", "0"))
+    best = None
+    for _ in range(2):                           # second run: page cache warm, as for the reference arm
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("create_mega_reads failed: " + r.stderr.decode()[-300:])
+        ph = {}
+        for line in r.stderr.decode().splitlines():
+            if line.startswith("Starting ") and "..." in line:
+                try:
+                    ph[line[9:line.index("...")].strip()] = float(line.split("...")[1].split()[0])
+                except ValueError:
+                    pass
+        cur = {"wall_s": wall, "phases_s": ph, "out_bytes": os.path.getsize(out)}
+        if best is None or wall < best["wall_s"]:
+            best = cur
+    align_s = best["phases_s"].get("create mega reads")
+    best["value"] = total_bases / align_s if align_s else None
+    best["unit"] = "bases/s"
+    best["what"] = ("bin/create_mega_reads <production flags> -p reads.fa -o out, best of 2 runs; value = read bases / its "
+                    "'create mega reads' phase (read parsing + alignment + tiling + writing the record file), the phase "
+                    "the reference arm times; wall_s is the whole process including super-read parsing and index build")
+    if gpus > 1:
+        # the product's own sharding (MR_GPUS: one context + index per device, batches dealt to whichever device is
+        # free, ordered host gather) on the same file: the record file must not depend on the number of devices
+        out_n = files["prefix"] + ".cli.n%d.out" % gpus
+        cmd_n = [exe] + production_flags(w, files, os.cpu_count() or host_threads) + ["-p", files["reads"], "-o", out_n]
+        env_n = {k: v for k, v in env.items() if k != "MR_DEVICES"}
+        env_n["MR_GPUS"] = str(gpus)
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd_n, env=env_n, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            best["multi_gpu"] = {"gpus": gpus, "error": r.stderr.decode()[-300:]}
+        else:
+            a_s = None
+            for line in r.stderr.decode().splitlines():
+                if line.startswith("Starting create mega reads ..."):
+                    a_s = float(line.split("...")[1].split()[0])
+            best["multi_gpu"] = {"gpus": gpus, "wall_s": wall, "value": total_bases / a_s if a_s else None,
+                                 "records_equal_to_one_device": file_sha256(out) == file_sha256(out_n),
+                                 "what": "MR_GPUS=%d bin/create_mega_reads on the same reads file (one process, reads dealt to "
+                                         "the devices, ordered gather), record file compared byte for byte with the 1-device run" % gpus}
+        try:
+            os.remove(out_n)
+        except OSError:
+            pass
+    try:
+        os.remove(out)
+    except OSError:
+        pass
+    return best
 
 
 # --------------------------------------------------------------------------------------------------
@@ -306,6 +487,8 @@ def ours(args, w, files):
     H.mrh_tool_load_reads.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
     H.mrh_tool_run.restype = C.c_int64
     H.mrh_tool_run.argtypes = [C.c_void_p, C.c_uint, C.c_char_p]
+    H.mrh_tool_run_range.restype = C.c_int64
+    H.mrh_tool_run_range.argtypes = [C.c_void_p, C.c_uint, C.c_char_p, C.c_uint64, C.c_uint64]
     for f in ("mrh_tool_context", "mrh_tool_index", "mrh_tool_params"):
         getattr(H, f).restype = C.c_void_p
         getattr(H, f).argtypes = [C.c_void_p]
@@ -445,7 +628,8 @@ def ours(args, w, files):
     dev_s = e0.elapsed_time(e1) * 1e-3
     launches = sum(L.mr_context_launches(c_) for c_ in ctxs) - launches0
     dev_s_max = max_over_ranks(dist, dev_s)
-    value = args.gpus * total_bases * args.steps / dev_s_max
+    job_bases = sum_over_ranks(dist, float(total_bases))        # every rank aligned its own shard
+    value = job_bases * args.steps / dev_s_max
 
     # ---- end to end through the host path ----------------------------------------------------------------
     for _ in range(args.warmup):
@@ -463,7 +647,7 @@ def ours(args, w, files):
     e2e_s_max = max_over_ranks(dist, e2e_s)
     stats = (C.c_uint64 * 8)()
     H.mrh_tool_last_stats(tool, stats)
-    e2e_value = args.gpus * total_bases * args.steps / e2e_s_max
+    e2e_value = job_bases * args.steps / e2e_s_max
     st_align, st_format = C.c_double(), C.c_double()
     H.mrh_tool_stage_seconds(tool, C.byref(st_align), C.byref(st_format))
 
@@ -488,13 +672,17 @@ def ours(args, w, files):
         alg = T * 5 + counters["lists"] * 16 + counters["lookups"] * 16 * nparts + counters["tails"] * 1
         launches_k = nbatches * args.steps * nparts
         achieved = alg / phase[kern] / 1e9 if phase.get(kern, 0) > 0 else 0.0
-        traffic = None
-        try:                                     # dram bytes per launch from the committed ncu --set full capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_seed_lookup_summary.json")))
-            if prof.get("batch_bases") == args.batch_bases and prof.get("genome") == w["genome"]:
-                traffic = prof["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        traffic, hit = None, None
+        for name in ("r02_seed_lookup_summary.json", "r01_seed_lookup_summary.json"):
+            try:                                 # per launch, from the committed ncu --set full capture of THIS configuration
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if prof.get("batch_bases") == args.batch_bases and prof.get("genome") == w["genome"] and \
+                   prof.get("kernel", "seed_lookup_kernel") == "seed_lookup_kernel" and (name.startswith("r02") or not SEED_KERNEL_CHANGED):
+                    traffic = prof["dram_bytes_per_launch"]
+                    hit = prof["l2_sector_hit_rate_pct"] / 100.0
+                    break
+            except Exception:
+                pass
         # The ceiling this kernel lives under is the rate of random DRAM accesses, not bytes:
         # mr_selftest_random_gather (pointer-chase-free 16-byte loads at random places of a 1 GiB table)
         # tops out at ~50 G loads/s on B200 whether a miss fetches 64 or 128 bytes (profiles/
@@ -503,24 +691,19 @@ def ours(args, w, files):
         rnd = None
         try:
             g1, g2 = C.c_double(), C.c_double()
-            tbl = int((4 ** 12 + 1) * 4 + H.mrh_tool_sr_bases(tool))       # prefix table + 8-bit tails of this index
+            tbl = int(L.mr_index_table_bytes(idx)) // max(1, nparts)       # prefix table + tails one launch reads at random
             if L.mr_selftest_random_gather(ctx, 1 << 30, 1 << 28, C.byref(g1)) == 0 and \
                L.mr_selftest_random_gather(ctx, tbl, 1 << 28, C.byref(g2)) == 0:
                 acc = (2 * counters["lookups"] * nparts + counters["buckets"]) / phase[kern] / 1e9
-                hit = None
-                try:
-                    hit = json.load(open(os.path.join(ROOT, "profiles", "r01_seed_lookup_summary.json")))["l2_sector_hit_rate_pct"] / 100.0
-                except Exception:
-                    pass
-                rnd = {"peak_G_accesses_per_s": g1.value / 32.0, "peak_table": "1 GiB (HBM)",
-                       "peak_G_accesses_per_s_index_sized_table": g2.value / 32.0, "index_sized_table_bytes": tbl,
-                       "achieved_G_accesses_per_s": acc, "frac": acc / (g1.value / 32.0),
+                rnd = {"peak_G_accesses_per_s": g2.value / 32.0, "peak_table_bytes": tbl,
+                       "peak_table": "a table of this index's own size (%d MB; the L2 holds 126 MB)" % (tbl >> 20),
+                       "peak_G_accesses_per_s_1GiB_table": g1.value / 32.0,
+                       "achieved_G_accesses_per_s": acc, "frac": acc / (g2.value / 32.0),
                        "l2_hit_rate_ncu": hit,
-                       "achieved_G_dram_accesses_per_s": acc * (1.0 - hit) if hit is not None else None,
-                       "frac_dram": acc * (1.0 - hit) / (g1.value / 32.0) if hit is not None else None,
                        "how": "accesses = 2 x looked-up k-mers + non-empty buckets scanned (kernel counters) / CUDA-event time of the "
-                              "launches; peak = 2^28 independent random 16-byte loads, 8 in flight per thread, best of 3 launches; "
-                              "frac > 1 means L2 hits: frac_dram discounts them with the hit rate of the committed ncu capture"}
+                              "launches; peak = 2^28 independent random 16-byte loads into a table as large as the index's lookup "
+                              "tables, 8 in flight per thread, best of 3 launches, measured in this run; l2_hit_rate_ncu only "
+                              "when profiles/ holds a capture of this very configuration"}
         except Exception:
             pass
         roof = {"kernel": "seed_lookup_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -529,14 +712,18 @@ def ours(args, w, files):
                 "share_of_step": phase[kern] / sum(phase.values()),
                 "random_access": rnd,
                 "dram_gbs_from_traffic": (traffic / (phase[kern] / launches_k) / 1e9) if traffic else None,
-                "note": "random gathers into a 67 MB prefix table and a 36 MB tail array: bounded by "
-                        "random-access sector throughput, not by streaming bandwidth; with streams_per_gpu > 1 the launch runs next to "
-                        "the other stream's kernels, so avg_launch_ms is its duration while sharing the GPU; the chaining kernels "
-                        "(phase 'chain coords') are latency/issue bound, see profiles/",
+                "lookup_table_bytes": int(L.mr_index_table_bytes(idx)), "index_parts": nparts,
+                "note": "random gathers into the prefix table and the tail array of the index (lookup_table_bytes over index_parts "
+                        "parts): bounded by random-access throughput (random_access), not by streaming bandwidth; with "
+                        "streams_per_gpu > 1 the launch runs next to the other stream's kernels, so avg_launch_ms is its duration "
+                        "while sharing the GPU; the chaining kernels (phase 'chain coords') are latency/issue bound, see profiles/",
                 "phases_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()}}
 
-    cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity gate (rank 0; every N) ----------------------------------------------------
+    # The reference binary aligns a bounded prefix of shard 0 on the host cores; the GPU path then writes the
+    # records of the very same reads (the batches that hold them) and the two files are compared per read.
+    cpu, parity, cli = None, None, None
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             n1 = args.cpu_sample_reads or 300
             v1, m1 = cpu_run(w, files, n1, os.cpu_count() or 1)
@@ -545,21 +732,28 @@ def ours(args, w, files):
                 if n2 > 2 * n1:
                     v1, m1 = cpu_run(w, files, n2, os.cpu_count() or 1)
             cpu = {"value": v1, "unit": "bases/s", "cores": m1["cores"], "kind": m1["kind"], "sample": m1["sample"]}
+            parity = parity_gate(H, L, tool, host_threads, w, files, m1)
         except Exception as e:                                  # the baseline is reported, never the measured path
             cpu = {"value": None, "unit": "bases/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+    if rank == 0 and not os.environ.get("MR_BENCH_NO_CLI"):
+        try:
+            cli = cli_run(w, files, total_bases, host_threads, args.gpus)
+        except Exception as e:                                  # noqa: BLE001
+            cli = {"error": str(e)[:300]}
 
     if rank == 0:
         line = {"metric": "pacbio_bases_aligned_per_s", "value": value, "unit": "bases/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-                "data": "synthetic", "config": dict(config_dict(args, w), streams_per_gpu=nstreams, fine_mer=args.fine_mer),
+                "data": "synthetic", "config": config_dict(args, w),
+                "run": {"streams_per_gpu": nstreams, "fine_mer": args.fine_mer, "shard_of_rank0": files["shard"]},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
                         "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
                         "host_threads": host_threads, "host_cores": os.cpu_count(), "text_bytes_per_step": int(stats[0]),
                         "stage_busy_ms_last_step": {"mr_align_batch": 1e3 * st_align.value, "host_format": 1e3 * st_format.value},
-                        "timing": "wall clock (includes host tiling/printing), max over ranks"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                        "timing": "wall clock (includes host tiling/printing), max over ranks", "cli": cli},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "index_build": {"file_round_trip": index_io, "seconds_total": index_s, "parts": int(L.mr_index_parts(idx)), "device_phases_s": index_timers,
                                 "superread_bases": int(H.mrh_tool_sr_bases(tool)), "superreads": int(H.mrh_tool_sr_count(tool))},
                 "work_per_step": {"read_bases": int(total_bases), "reads": int(H.mrh_tool_nreads(tool)), "batches": nbatches,
@@ -570,9 +764,14 @@ def ours(args, w, files):
                                   "hits": counters["hits"] // max(1, args.steps), "groups": counters["groups"] // max(1, args.steps),
                                   "coords": counters["coords"] // max(1, args.steps)}}
         print(json.dumps(line))
+        sys.stdout.flush()
     H.mrh_tool_destroy(tool)
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and parity and parity.get("differ_non_tie", 0) > 0:
+        sys.stderr.write("bench.py: PARITY FAILURE: %d records differ from the reference on reads without a coords tie\n"
+                         % parity["differ_non_tie"])
+        sys.exit(3)
 
 
 def lookup_microbench(args):
@@ -684,6 +883,8 @@ def main():
                               "(building the reference PSA for 1 Gbp takes minutes of CPU); see cpu_baseline of the default workload"}))
             return
         return lookup_microbench(args)
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return                                   # rank 0 alone runs the CPU arm
     w, files = data_files(args)
     if args.impl == "reference":
         reference_arm(args, w, files)

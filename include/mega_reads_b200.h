@@ -76,6 +76,9 @@ uint64_t mr_index_sa_size(const mr_index* idx);                 /* n - psa_min +
  * parts.
  * Environment: MR_INDEX_PART_BASES=<n> lowers the part limit (tests). */
 uint32_t mr_index_parts(const mr_index* idx);
+/* bytes of the tables a k-mer lookup reads at random (prefix counts + tails, all parts): what has to
+ * stay in the L2 for lookups to hit there; bench.py sizes its random-access ceiling probe with it */
+uint64_t mr_index_table_bytes(const mr_index* idx);
 /* parity taps: suffix-array values in SA order and the 4^psa_min + 1 prefix counts
  * (mer_sa_imp.hpp:317-330), widened to 64 bit */
 int  mr_index_export_sa(mr_index* idx, uint64_t* sa_out);

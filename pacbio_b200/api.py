@@ -85,6 +85,9 @@ def lib():
     L.mr_selftest_random_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
     L.mr_index_parts.restype = C.c_uint32
     L.mr_index_parts.argtypes = [C.c_void_p]
+    L.mr_index_table_bytes.restype = C.c_uint64
+    L.mr_index_table_bytes.argtypes = [C.c_void_p]
+    L.mr_index_peek_checksum.argtypes = [C.c_char_p, u64p]
     L.mr_index_sa_size.restype = C.c_uint64
     L.mr_index_sa_size.argtypes = [C.c_void_p]
     L.mr_index_export_sa.argtypes = [C.c_void_p, u64p]

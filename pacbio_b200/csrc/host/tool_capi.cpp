@@ -95,16 +95,21 @@ const uint64_t* mrh_tool_batch_starts(void* p, uint64_t i, uint32_t* nreads) {
 // (H2D inside), results back (D2H inside), text records formatted on `threads` host threads while
 // the next batch is already on the GPU (same two-stage overlap as the command line tools).
 // out_path may be null/empty (text is produced and dropped).  Returns read bases processed, <0 on error.
-int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
+// mrh_tool_run_range: the same over batches [first, first + count) only (bench.py's parity gate writes
+// the records of the reads the CPU reference was run on).
+int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint64_t first, uint64_t count) {
   tool* t = (tool*)p;
+  if(first > t->batches.size()) first = t->batches.size();
+  count = std::min<uint64_t>(count, t->batches.size() - first);
   FILE* out = nullptr;
   if(out_path && *out_path) { out = fopen(out_path, "w"); if(!out) { t->error = "cannot open output"; return -1; } }
   t->last_text_bytes = t->last_d2h_bytes = t->last_h2d_bytes = t->last_coords = 0;
   t->last_lookups = t->last_hits = t->last_groups = 0;
   t->last_align_s = t->last_format_s = 0;
   // one aligner thread per context takes the next batch; results are formatted in batch order
-  const size_t nb = t->batches.size();
+  const size_t nb = (size_t)count;
   std::vector<mr_result*> done(nb, nullptr);
+  uint64_t bases_done = 0;
   std::vector<char> ready(nb, 0);
   std::mutex m;
   std::condition_variable cv;
@@ -122,7 +127,8 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
         r = done[i];
       }
       const auto f0 = std::chrono::steady_clock::now();
-      mrh::read_batch* b = t->batches[i].get();
+      mrh::read_batch* b = t->batches[first + i].get();
+      bases_done += b->bases.size();
       mr_result_view v;
       mr_result_get(r, &v);
       try {
@@ -161,7 +167,7 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
           cv.wait(l, [&] { return i < formatted + 3 + t->DS.ctx.size() || stop; });
           if(stop) break;
         }
-        mrh::read_batch* b = t->batches[i].get();
+        mrh::read_batch* b = t->batches[first + i].get();
         mr_staged* st = nullptr;
         if(mrh::stage_batches() && mr_stage_batch(t->DS.ctx[s], b->bases.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
           std::lock_guard<std::mutex> l(m);
@@ -178,7 +184,7 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
       while(staged[s]->pop(it)) {
         mr_result* r = nullptr;
         const auto a0 = std::chrono::steady_clock::now();
-        mrh::read_batch* b = t->batches[it.i].get();
+        mrh::read_batch* b = t->batches[first + it.i].get();
         const int rc = it.s ? mr_align_staged(t->DS.ctx[s], t->DS.idx[s], &t->P, it.s, &r)
                             : mr_align_batch(t->DS.ctx[s], t->DS.idx[s], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
         busy[s] += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
@@ -196,7 +202,10 @@ int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   for(size_t i = 0; i < nb; ++i) if(ready[i] && i >= formatted) mr_result_free(done[i]);   // only after an error
   if(out) fclose(out);
   if(!align_error.empty() || !error.empty()) { t->error = align_error.empty() ? error : align_error; return -1; }
-  return (int64_t)t->total_bases;
+  return (int64_t)bases_done;
+}
+int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
+  return mrh_tool_run_range(p, threads, out_path, 0, ~0ULL);
 }
 void mrh_tool_stage_seconds(void* p, double* align_s, double* format_s) {
   tool* t = (tool*)p; *align_s = t->last_align_s; *format_s = t->last_format_s;

@@ -464,6 +464,12 @@ void mr_index_destroy(mr_index* idx) {
 
 uint64_t mr_index_sa_size(const mr_index* idx) { return idx ? idx->nsa : 0; }
 uint32_t mr_index_parts(const mr_index* idx) { return idx ? idx->nparts() : 0; }
+uint64_t mr_index_table_bytes(const mr_index* idx) {
+  if(!idx) return 0;
+  uint64_t b = idx->lut_bytes;
+  for(const mr_index* p : idx->more) b += p->lut_bytes;
+  return b;
+}
 
 static int export_widened(mr_index* idx, const uint32_t* d_in, uint64_t count, uint64_t* h_out) {
   mr_context* ctx = idx->ctx;

@@ -48,6 +48,8 @@ struct options {
   uint64_t genome = 1000000, seed = 42;
   double   coverage = 20, error = 0.15, sr_cov = 2.0, repeat_frac = 0.0, single_frac = 0.1;
   uint32_t read_len = 10000, unitig_k = 41, mean_unitig = 500, threads = 8, line = 80;
+  uint32_t shards = 1;     // > 1: also <prefix>.reads.shard<i>.fa, i = 1 .. shards-1, each as many NEW reads as reads.fa
+  uint32_t first_shard = 0; // > 0: write only the read shards first_shard .. shards-1 (the other files exist already)
   std::string prefix = "synth";
 };
 
@@ -67,6 +69,8 @@ int main(int argc, char** argv) {
     else if(a == "--unitig-k") o.unitig_k = atoi(v);
     else if(a == "--mean-unitig") o.mean_unitig = atoi(v);
     else if(a == "--threads") o.threads = atoi(v);
+    else if(a == "--shards") o.shards = std::max(1, atoi(v));
+    else if(a == "--first-shard") o.first_shard = std::max(0, atoi(v));
     else if(a == "--prefix") o.prefix = v;
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
@@ -116,6 +120,9 @@ int main(int argc, char** argv) {
     std::sort(copies.begin(), copies.end(), [](const rep_copy& a, const rep_copy& b) { return a.pos < b.pos; });
   }
 
+  size_t n_unitigs_out = 0, nseg_out = 0;
+  uint64_t sr_bases = 0, nsr = 0;
+  if(o.first_shard == 0) {
   // ---- unitigs: segment i = genome[cut[i], cut[i+1] + K - 1) --------------
   std::vector<uint64_t> cut;
   std::vector<int64_t>  seg_family;   // family id if the segment is an exact repeat interior, else -1
@@ -176,8 +183,8 @@ int main(int argc, char** argv) {
     fclose(fa); fclose(fl);
   }
 
+  n_unitigs_out = uid_seg.size(); nseg_out = nseg;
   // ---- super-reads ---------------------------------------------------------
-  uint64_t sr_bases = 0, nsr = 0;
   {
     FILE* f = fopen((o.prefix + ".superreads.fa").c_str(), "w");
     if(!f) { perror("open"); return 1; }
@@ -218,23 +225,27 @@ int main(int argc, char** argv) {
     }
     fclose(f);
   }
+  }   // first_shard == 0
 
   // ---- reads ---------------------------------------------------------------
   const uint64_t nreads = std::max<uint64_t>(1, (uint64_t)(o.coverage * G / o.read_len));
   uint64_t read_bases = 0;
-  {
-    FILE* f = fopen((o.prefix + ".reads.fa").c_str(), "w");
+  // shard s holds reads [s * nreads, (s + 1) * nreads): disjoint draws from the same genome (a read's
+  // random stream depends on its index only), so shard 0 is the file a run without --shards writes
+  for(uint32_t shard = o.first_shard; shard < o.shards; ++shard) {
+    FILE* f = fopen((o.prefix + (shard ? ".reads.shard" + std::to_string(shard) + ".fa" : std::string(".reads.fa"))).c_str(), "w");
     if(!f) { perror("open"); return 1; }
     const uint64_t chunk = 4096;
     std::vector<std::string> bufs(o.threads);
     std::vector<uint64_t> nb(o.threads);
-    for(uint64_t base = 0; base < nreads; base += chunk * o.threads) {
+    const uint64_t first_read = (uint64_t)shard * nreads, end_read = first_read + nreads;
+    for(uint64_t base = first_read; base < end_read; base += chunk * o.threads) {
       std::vector<std::thread> th;
       for(uint32_t t = 0; t < o.threads; ++t) {
         th.emplace_back([&, t]() {
           std::string& out = bufs[t];
           out.clear(); nb[t] = 0;
-          const uint64_t lo = base + t * chunk, hi = std::min(nreads, lo + chunk);
+          const uint64_t lo = base + t * chunk, hi = std::min(end_read, lo + chunk);
           for(uint64_t r = lo; r < hi; ++r) {
             rng_t g(o.seed * 0x100000001b3ULL + r + 1);
             uint64_t len = (uint64_t)(o.read_len * (0.8 + 0.4 * g.unit()));
@@ -265,13 +276,13 @@ int main(int argc, char** argv) {
         });
       }
       for(auto& x : th) x.join();
-      for(uint32_t t = 0; t < o.threads; ++t) { fwrite(bufs[t].data(), 1, bufs[t].size(), f); read_bases += nb[t]; }
+      for(uint32_t t = 0; t < o.threads; ++t) { fwrite(bufs[t].data(), 1, bufs[t].size(), f); if(shard == o.first_shard) read_bases += nb[t]; }
     }
     fclose(f);
   }
   printf("{\"genome\": %llu, \"unitigs\": %zu, \"segments\": %zu, \"superreads\": %llu, \"superread_bases\": %llu, "
          "\"reads\": %llu, \"read_bases\": %llu, \"unitig_k\": %u}\n",
-         (unsigned long long)G, uid_seg.size(), nseg, (unsigned long long)nsr, (unsigned long long)sr_bases,
+         (unsigned long long)G, n_unitigs_out, nseg_out, (unsigned long long)nsr, (unsigned long long)sr_bases,
          (unsigned long long)nreads, (unsigned long long)read_bases, K);
   return 0;
 }

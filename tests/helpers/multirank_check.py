@@ -15,13 +15,15 @@ w, files = bench.data_files(args)
 dist = bench.dist_setup(args.gpus)
 rank = int(os.environ["RANK"])
 bench.barrier(dist)
-reads = sum(1 for line in open(files["reads"]) if line.startswith(">"))
+names = [line[1:].split()[0] for line in open(files["reads"]) if line.startswith(">")]
+reads = len(names)
 t = 1.0 + rank                                  # pretend rank r needed 1 + r seconds
 t_max = bench.max_over_ranks(dist, t)
 total = bench.sum_over_ranks(dist, float(reads))
 value = args.gpus * reads / t_max               # whole-job throughput = all ranks' units / slowest rank
 # one write per line: the two ranks share the launcher's stdout pipe
-sys.stdout.write(json.dumps({"rank": rank, "reads": reads, "t_max": t_max, "total": total, "value": value,
+sys.stdout.write(json.dumps({"rank": rank, "reads": reads, "shard": files["shard"], "reads_file": files["reads"],
+                             "first_read": names[0], "last_read": names[-1], "t_max": t_max, "total": total, "value": value,
                              "files_exist": all(os.path.exists(files[k]) for k in ("sr", "reads", "unitigs"))}) + "\n")
 sys.stdout.flush()
 dist.destroy_process_group()

@@ -330,7 +330,7 @@ def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
     assert records(out) == records(want)
 
 
-@pytest.mark.skipif(not os.environ.get("MR_BIG_TESTS"), reason="set MR_BIG_TESTS=1: 135 Mbp genome, ~1 minute of reference CPU time")
+@pytest.mark.skipif(bool(os.environ.get("MR_SKIP_BIG_TESTS")), reason="MR_SKIP_BIG_TESTS set (135 Mbp genome, ~1 minute of reference CPU time)")
 def test_arabidopsis_size_index_against_reference(tmpdir_session, tmp_path, port):
     """BASELINE.json configs[2] index scale (135 Mbp genome, 270 M super-read bases, repeat-rich) on a
     subsample of reads.  The text of the GPU tool must equal the oracle port's (same canonical tie

@@ -132,6 +132,52 @@ def test_lookup_matches_oracle(case, port):
     assert int(gn.sum()) > 5000
 
 
+@pytest.mark.parametrize("k", [15, 17, 19])
+def test_lookup_at_scale_matches_reference_psa_search(ctx, port, tmpdir_session, k):
+    """BASELINE.json configs[4] parity: mr_lookup_batch == PSA::search (mer_sa_imp.hpp:369-479, through the
+    compiled reference's libref_tap.so when it travelled to the box, else the oracle port) on a 64 Mbp random
+    text x 1e6 queries -- half sampled from the text (both strands), half uniform random -- at k = 15 / 17 / 19."""
+    import pacbio_b200 as pb
+    from oracle_lib import Ref, have_ref
+    n, nq, m = 64_000_000, 1_000_000, 13
+    fa = os.path.join(tmpdir_session, "lookup_scale.fa")
+    rng = np.random.default_rng(4600)
+    if not os.path.exists(fa):
+        codes = rng.integers(0, 4, size=n, dtype=np.uint8)
+        with open(fa, "wb") as f:                       # 16 sequences of 4 Mbp, one line each
+            for i in range(16):
+                f.write(b">%d\n" % i)
+                f.write(np.frombuffer(b"ACGT", dtype=np.uint8)[codes[i * (n // 16):(i + 1) * (n // 16)]].tobytes())
+                f.write(b"\n")
+    sr = pb.SuperReads(fa)
+    assert sr.n == n
+    words = sr.text2bit
+    qr = np.random.default_rng(4700 + k)
+    pos = qr.integers(0, n - k, size=nq // 2).astype(np.int64)
+    fwd = np.zeros(nq // 2, dtype=np.uint64)
+    rc = np.zeros(nq // 2, dtype=np.uint64)
+    for j in range(k):
+        b = pos + j
+        code = (words[b >> 5] >> (2 * (b & 31)).astype(np.uint64)) & np.uint64(3)
+        fwd = (fwd << np.uint64(2)) | code
+        rc = rc | ((np.uint64(3) - code) << np.uint64(2 * j))
+    q = np.concatenate([np.where(np.arange(nq // 2) & 1, rc, fwd), qr.integers(0, 4 ** k, size=nq - nq // 2, dtype=np.uint64)])
+    idx = ctx.index(sr, m, k)
+    try:
+        gi, gn = idx.lookup(q)
+    finally:
+        idx.close()
+    checker = Ref() if have_ref() else port
+    h = checker.index_create(fa, m, k, 16)
+    try:
+        oi, on = checker.search(h, q)
+    finally:
+        checker.index_destroy(h)
+    assert np.array_equal(gn, on)
+    assert np.array_equal(gi, oi)
+    assert int((gn > 0).sum()) >= nq // 4           # every k-mer sampled on the text's own strand is found (the search is strand specific)
+
+
 def _canon(cint, cdbl, info_off, kinfo, binfo):
     rows = []
     for j in range(len(cint)):

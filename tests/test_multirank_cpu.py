@@ -20,6 +20,10 @@ def test_two_ranks_gloo(tmp_path):
     assert sorted(x["rank"] for x in rows) == [0, 1]
     assert all(x["files_exist"] for x in rows)
     assert rows[0]["reads"] == rows[1]["reads"] > 0
+    # rank r aligns shard r: disjoint reads of the same genome, numbered on from the previous shard
+    rows.sort(key=lambda x: x["rank"])
+    assert [x["shard"] for x in rows] == [0, 1] and rows[0]["reads_file"] != rows[1]["reads_file"]
+    assert rows[0]["first_read"].startswith("read0/") and rows[1]["first_read"].startswith("read%d/" % rows[0]["reads"])
     for x in rows:
         assert x["t_max"] == 2.0                       # slowest rank
         assert x["total"] == 2 * x["reads"]
@@ -32,7 +36,7 @@ def test_reference_arm_other_ranks_do_no_work(tmp_path):
     # rank 1 would wait for rank 0's data: create the done marker by running rank 0's generation first
     env0 = dict(env, RANK="0", LOCAL_RANK="0")
     code = ("import sys; sys.path.insert(0, %r); import bench, argparse; "
-            "bench.data_files(argparse.Namespace(genome=40000, coverage=2.0))" % ROOT)
+            "bench.data_files(argparse.Namespace(genome=40000, coverage=2.0, gpus=2, impl='reference'))" % ROOT)
     subprocess.check_call([sys.executable, "-c", code], env=env0)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--genome", "40000", "--coverage", "2", "--steps", "1", "--warmup", "0"],

@@ -493,6 +493,72 @@ void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, cons
   for(auto& e : errors) if(e) std::rethrow_exception(e);
 }
 
+// ---- result dumps (profiling aid) -------------------------------------------------------------------
+namespace {
+template<typename T> bool put(FILE* f, const T* p, uint64_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
+template<typename T> bool get(FILE* f, std::vector<T>& v, uint64_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+}
+bool dump_result(const std::string& path, const mr_result_view& v, const read_batch& batch) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if(!f) return false;
+  uint64_t info_total = 0;
+  for(uint64_t i = 0; i < v.ncoords; ++i) if(v.info_len[i]) info_total = std::max<uint64_t>(info_total, v.info_off[i] + v.info_len[i]);
+  const uint64_t head[4] = { 0x3150554d5544524dULL, v.nreads, v.ncoords, info_total };
+  const uint64_t S = v.ncoords;
+  bool ok = put(f, head, 4) && put(f, v.read_coords, (uint64_t)v.nreads + 1) && put(f, v.info_off, S);
+  const int32_t* i32[10] = { v.rs, v.re, v.qs, v.qe, v.nb_mers, v.lstart, v.lprev, v.lpath, v.lunitigs, v.component };
+  for(auto p : i32) ok = ok && put(f, p, S);
+  ok = ok && put(f, v.kmers_info, info_total) && put(f, v.bases_info, info_total);
+  const uint32_t* u32[7] = { v.pb_cons, v.sr_cons, v.pb_cover, v.sr_cover, v.ql, v.sr, v.info_len };
+  for(auto p : u32) ok = ok && put(f, p, S);
+  const uint8_t* u8[4] = { v.rn, v.use_bwd, v.start_node, v.end_node };
+  for(auto p : u8) ok = ok && put(f, p, S);
+  const double* f64[3] = { v.stretch, v.offset, v.avg_err };
+  for(auto p : f64) ok = ok && put(f, p, S);
+  ok = ok && put(f, batch.start.data(), (uint64_t)v.nreads + 1);
+  for(uint32_t r = 0; r < v.nreads && ok; ++r) {
+    const uint32_t len = (uint32_t)batch.name[r].size();
+    ok = put(f, &len, 1) && put(f, batch.name[r].data(), len);
+  }
+  return fclose(f) == 0 && ok;
+}
+bool load_result(const std::string& path, result_dump& d) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if(!f) return false;
+  uint64_t head[4];
+  bool ok = fread(head, 8, 4, f) == 4 && head[0] == 0x3150554d5544524dULL;
+  if(!ok) { fclose(f); return false; }
+  const uint64_t nreads = head[1], S = head[2], info_total = head[3];
+  ok = get(f, d.u64[0], nreads + 1) && get(f, d.u64[1], S);
+  for(int i = 0; i < 10; ++i) ok = ok && get(f, d.i32[i], S);
+  ok = ok && get(f, d.i32[10], info_total) && get(f, d.i32[11], info_total);
+  for(int i = 0; i < 7; ++i) ok = ok && get(f, d.u32[i], S);
+  for(int i = 0; i < 4; ++i) ok = ok && get(f, d.u8[i], S);
+  for(int i = 0; i < 3; ++i) ok = ok && get(f, d.f64[i], S);
+  d.batch.clear();
+  ok = ok && get(f, d.batch.start, nreads + 1);
+  for(uint64_t r = 0; r < nreads && ok; ++r) {
+    uint32_t len = 0;
+    ok = fread(&len, 4, 1, f) == 1 && len < (1u << 20);
+    std::string nm(len, ' ');
+    ok = ok && (len == 0 || fread(&nm[0], 1, len, f) == len);
+    d.batch.name.push_back(nm);
+  }
+  fclose(f);
+  if(!ok) return false;
+  mr_result_view& v = d.view;
+  memset(&v, 0, sizeof v);
+  v.nreads = (uint32_t)nreads; v.ncoords = S; v.read_coords = d.u64[0].data(); v.info_off = d.u64[1].data();
+  v.rs = d.i32[0].data(); v.re = d.i32[1].data(); v.qs = d.i32[2].data(); v.qe = d.i32[3].data(); v.nb_mers = d.i32[4].data();
+  v.lstart = d.i32[5].data(); v.lprev = d.i32[6].data(); v.lpath = d.i32[7].data(); v.lunitigs = d.i32[8].data(); v.component = d.i32[9].data();
+  v.kmers_info = d.i32[10].data(); v.bases_info = d.i32[11].data();
+  v.pb_cons = d.u32[0].data(); v.sr_cons = d.u32[1].data(); v.pb_cover = d.u32[2].data(); v.sr_cover = d.u32[3].data();
+  v.ql = d.u32[4].data(); v.sr = d.u32[5].data(); v.info_len = d.u32[6].data();
+  v.rn = d.u8[0].data(); v.use_bwd = d.u8[1].data(); v.start_node = d.u8[2].data(); v.end_node = d.u8[3].data();
+  v.stretch = d.f64[0].data(); v.offset = d.f64[1].data(); v.avg_err = d.f64[2].data();
+  return true;
+}
+
 // default ostream formatting of a double: "%g" with 6 significant digits (jf_aligner.cc:58)
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
                    bool compact, bool zero_skip, std::string& out) {

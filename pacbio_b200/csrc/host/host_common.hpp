@@ -87,6 +87,21 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
                           const graph_options& o, unsigned threads, std::vector<std::string>& parts);
 
+// Debug / profiling aid: one batch's result rows + read names on disk (MR_DUMP_BATCH=<file> in the bench's
+// host path writes the first batch), read back by pacbio_b200/tools/format_replay to time the
+// formatting stage on any host without a GPU.
+struct result_dump {
+  mr_result_view view;                  // points into the vectors below
+  read_batch     batch;                 // names and starts only (no bases)
+  std::vector<uint64_t> u64[2];         // read_coords, info_off
+  std::vector<int32_t>  i32[12];        // rs re qs qe nb_mers lstart lprev lpath lunitigs component kmers_info bases_info
+  std::vector<uint32_t> u32[7];         // pb_cons sr_cons pb_cover sr_cover ql sr info_len
+  std::vector<uint8_t>  u8[4];          // rn use_bwd start_node end_node
+  std::vector<double>   f64[3];         // stretch offset avg_err
+};
+bool dump_result(const std::string& path, const mr_result_view& v, const read_batch& batch);
+bool load_result(const std::string& path, result_dump& d);
+
 // jf_aligner coords records (jf_aligner.cc:41-70)
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
                    bool compact, bool zero_skip, std::string& out);

@@ -131,6 +131,10 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
       bases_done += b->bases.size();
       mr_result_view v;
       mr_result_get(r, &v);
+      if(const char* dump = getenv("MR_DUMP_BATCH")) {       // profiling aid: the first batch's rows on disk, once
+        static std::atomic<bool> dumped(false);
+        if(*dump && !dumped.exchange(true) && !mrh::dump_result(dump, v, *b)) fprintf(stderr, "MR_DUMP_BATCH: cannot write %s\n", dump);
+      }
       try {
         mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, parts);
         for(const auto& text : parts) {

@@ -1,0 +1,40 @@
+// Times the host formatting stage (mega_reads_per_comp + tiling + printing, host_common.cpp) on a result
+// dumped by MR_DUMP_BATCH=<file> -- no GPU needed, so the stage can be profiled and tuned on any host.
+//   format_replay <dump> <superreads.fa> <unitigs.fa> <unitig_k> <threads> [reps] [out.txt]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "../csrc/host/host_common.hpp"
+
+int main(int argc, char** argv) {
+  if(argc < 6) { fprintf(stderr, "usage: %s dump superreads.fa unitigs.fa unitig_k threads [reps] [out]\n", argv[0]); return 1; }
+  try {
+    mrh::result_dump d;
+    if(!mrh::load_result(argv[1], d)) throw std::runtime_error("cannot read the dump");
+    mrh::super_reads SR;
+    SR.append_fasta(argv[2]);
+    mrh::unitigs U;
+    U.load_sequences(argv[3]);
+    mrh::graph_options G;
+    G.k_len = (uint32_t)atoi(argv[4]);
+    const unsigned threads = (unsigned)atoi(argv[5]);
+    const int reps = argc > 6 ? atoi(argv[6]) : 5;
+    std::vector<std::string> parts;
+    double best = 1e30;
+    uint64_t bytes = 0;
+    for(int i = 0; i < reps; ++i) {
+      const auto t0 = std::chrono::steady_clock::now();
+      mrh::format_mega_reads_mt(d.view, d.batch, SR, U, G, threads, parts);
+      const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      best = std::min(best, s);
+      bytes = 0;
+      for(auto& p : parts) bytes += p.size();
+    }
+    printf("{\"reads\": %u, \"rows\": %llu, \"text_bytes\": %llu, \"threads\": %u, \"best_s\": %.6f, \"thread_seconds\": %.6f}\n",
+           d.view.nreads, (unsigned long long)d.view.ncoords, (unsigned long long)bytes, threads, best, best * threads);
+    if(argc > 7) { FILE* f = fopen(argv[7], "w"); for(auto& p : parts) fwrite(p.data(), 1, p.size(), f); fclose(f); }
+  } catch(std::exception& e) { fprintf(stderr, "format_replay: %s\n", e.what()); return 1; }
+  return 0;
+}

@@ -971,6 +971,15 @@ __global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const u
   }
 }
 
+// largest number of coords rows any read of the batch has: the host picks the overlap-graph and
+// row-ordering kernels with it
+__global__ void __launch_bounds__(256) max_rows_kernel(const uint32_t* __restrict__ read_cnt, uint32_t nreads, unsigned long long* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = r < nreads ? read_cnt[r] : 0u;
+  v = __reduce_max_sync(MR_FULL_MASK, v);
+  if((threadIdx.x & 31) == 0 && v) atomicMax(out, (unsigned long long)v);
+}
+
 struct gather_args {
   uint64_t n; const uint32_t* order;
   survivors sv; const uint64_t* sv_info_off;
@@ -1187,8 +1196,8 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     res->view.n_groups = G;
     MR_TRY(ws.group_start.ensure(ctx, (G + 2) * 8));
     MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
-    MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &Hvalid, 8, cudaMemcpyHostToDevice, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));   // Hvalid is a stack variable
+    // end of the last group; the source lives in the result object (a copy from pageable memory is staged before the call returns)
+    MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &res->view.n_hits, 8, cudaMemcpyHostToDevice, st));
 
     // ---- chaining + coords ------------------------------------------------------------------------
     timer.next("chain coords");
@@ -1235,7 +1244,9 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       MR_CUDA(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(uint64_t), st));
       MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
       if(G) MR_TRY(launch_chain(ctx, A, ws.group_lists));
-      MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      max_rows_kernel<<<div_up(nreads, 256), 256, 0, st>>>(ws.read_cnt.as<uint32_t>(), nreads, ctr + 12);
+      MR_LAUNCHED(ctx);
+      MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 13 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       MR_CUDA(ctx, cudaStreamSynchronize(st));
       S = h_ctr[4];
       MR_TRACE_MSG("chained; %llu rows (capacity %llu)", (unsigned long long)S, (unsigned long long)cap);
@@ -1344,6 +1355,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     k_coords = kk;
   }
   const uint64_t info_total = S ? h_ctr[5] : 0;
+  const int max_rows = S ? (int)std::min<uint64_t>(h_ctr[12], 0x7fffffff) : 0;      // rows of the read that has most
 
   // ---- kmers_info, per-read order, final rows ---------------------------------------------------
   timer.next("coords order");
@@ -1380,7 +1392,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     rank_rows_kernel<false><<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
                                                                                 ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(), ws.order.as<uint32_t>());
     MR_LAUNCHED(ctx);
-    if(S > (uint64_t)big_rows_threshold()) {                         // some read may have that many rows
+    if(max_rows > big_rows_threshold()) {                            // some read has that many rows
       rank_rows_kernel<true><<<nreads, 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
                                                      ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(),
                                                      ws.order.as<uint32_t>());
@@ -1402,9 +1414,9 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
     GA.unitig_ids = idx->unitig_ids.as<uint32_t>(); GA.unitig_off = idx->has_unitigs ? idx->unitig_off.as<uint64_t>() : nullptr;
     GA.unitig_len = idx->unitig_len.as<int32_t>(); GA.n_unitigs = idx->n_unitigs; GA.unitigs_k = p->unitigs_k;
-    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold(); GA.cta_max_rows = std::max(big_rows_threshold(), huge_rows_threshold());
+    GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
     MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
-    if(S) MR_TRY(launch_graph(ctx, GA));
+    if(S) MR_TRY(launch_graph(ctx, ws, GA, S, max_rows));
   }
   timer.next("result download");
   MR_TRACE_MSG("ordered%s; downloading", graph ? " + graph" : "");
@@ -1524,6 +1536,13 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
     if(rows->sr[i] >= npaths) return ctx->fail(MR_EINVAL, "mr_graph_batch: row refers to a path that was not given");
     if(rows->info_len[i]) info_total = std::max<uint64_t>(info_total, rows->info_off[i] + rows->info_len[i]);
   }
+  std::vector<uint32_t> row_read(Sc, 0);
+  int max_rows = 0;
+  for(uint32_t r = 0; r < nreads; ++r) {
+    if(rows->read_coords[r + 1] < rows->read_coords[r] || rows->read_coords[r + 1] > S) return ctx->fail(MR_EINVAL, "mr_graph_batch: read_coords must be non-decreasing");
+    max_rows = (int)std::max<uint64_t>(max_rows, std::min<uint64_t>(rows->read_coords[r + 1] - rows->read_coords[r], 0x7fffffff));
+    for(uint64_t i = rows->read_coords[r]; i < rows->read_coords[r + 1]; ++i) row_read[i] = r;
+  }
   ctx->timers.clear();
   phase_timer timer(ctx);
   timer.begin("rows upload");
@@ -1545,7 +1564,7 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   push(fin.nb_mers, rows->nb_mers, S * 4);
   push(fin.pb_cons, rows->pb_cons, S * 4); push(fin.sr_cons, rows->sr_cons, S * 4);
   push(fin.pb_cover, rows->pb_cover, S * 4); push(fin.sr_cover, rows->sr_cover, S * 4);
-  push(fin.ql, rows->ql, S * 4); push(fin.sr, rows->sr, S * 4);
+  push(fin.ql, rows->ql, S * 4); push(fin.sr, rows->sr, S * 4); push(fin.read, row_read.data(), S * 4);
   push(fin.rn, rows->rn, S); push(fin.use_bwd, rows->use_bwd, S);
   push(fin.stretch, rows->stretch, S * 8); push(fin.offset, rows->offset, S * 8); push(fin.avg_err, rows->avg_err, S * 8);
   push(fin.info_off, rows->info_off, S * 8); push(fin.info_len, rows->info_len, S * 4);
@@ -1560,9 +1579,9 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   GA.kinfo = ws.kinfo.as<int32_t>(); GA.binfo = ws.binfo.as<int32_t>();
   GA.unitig_ids = ws.path_ids.as<uint32_t>(); GA.unitig_off = ws.path_off.as<uint64_t>();
   GA.unitig_len = ws.path_ulen.as<int32_t>(); GA.n_unitigs = n_unitigs; GA.unitigs_k = p->unitigs_k;
-  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold(); GA.cta_max_rows = std::max(big_rows_threshold(), huge_rows_threshold());
+  GA.overlap_play = p->overlap_play; GA.errors = p->errors; GA.bases = p->bases; GA.warp_max_rows = big_rows_threshold();
   MR_TRY(setup_graph_nodes(ctx, ws, Sc, GA));
-  if(S) MR_TRY(launch_graph(ctx, GA));
+  if(S) MR_TRY(launch_graph(ctx, ws, GA, S, max_rows));
   timer.next("result download");
   MR_TRY(download_rows(ctx, ws, res.get(), fin, nreads, S, info_total, &GA));
   timer.end();

@@ -1,5 +1,6 @@
 // Shared declarations for the per-batch alignment pipeline (align.cu, graph.cu, result.cu).
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "index.cuh"
 #include "primitives.cuh"
@@ -49,6 +50,7 @@ struct mr_workspace {
   dev_buf read_cnt, read_coords, read_cursor, slot, order, rowkey4, rowkey5;
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
+  dev_buf node_path, edge_cnt, edge_off, edges, path_i32, path_f64, path_u8;   // overlap graph of reads with many rows (graph.cu)
   dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay, removed;
   dev_buf scan_scratch;
   prim::sort_scratch sort;
@@ -124,19 +126,25 @@ struct graph_args {
   uint32_t n_unitigs, unitigs_k;
   double overlap_play, errors;
   int bases;
-  int warp_max_rows;       // reads with more rows than this get a CTA instead of a warp (big_rows_threshold())
-  int cta_max_rows;        // ... and above this a CTA of 1024 threads instead of 256 (huge_rows_threshold())
-  double *ord_s, *ord_e, *ord_err;   // scratch of the CTA kernels: imp_s, imp_e, avg_err in node order
+  int warp_max_rows;       // reads with more rows than this take the edge-list kernels instead of one warp (big_rows_threshold())
+  double *ord_s, *ord_e, *ord_err;   // reads with many rows: imp_s, imp_e, avg_err in node order
+  ulonglong2* ord_path;              // ... and the node's unitig path: x = offset into unitig_ids, y = length | reversed << 32
+  uint32_t*   edge_cnt;              // out-edges of the node at every order position (0 for the rows of other reads)
+  uint64_t*   edge_off;              // exclusive scan of edge_cnt: a node's slice of `edges`
+  int4*       edges;                 // { successor's order position, weight - common, unitigs added, 0 }
   // outputs / scratch, one entry per row
   uint8_t *start_node, *end_node;
   int32_t *lstart, *lprev, *lpath, *lunitigs, *component, *uf_rank, *order;
   double  *imp_s, *imp_e;
 };
-int launch_graph(mr_context* ctx, const graph_args& a);
+struct mr_workspace;
+int launch_graph(mr_context* ctx, mr_workspace& ws, graph_args a, uint64_t S, int max_rows);
 // rows per read above which the per-read kernels (coords order, overlap graph) use a CTA instead of a
 // warp; MR_BIG_ROWS lowers it so that the tests drive the small fixtures through the CTA kernels
-inline int huge_rows_threshold() {
-  static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 0x7fffffff; }();      // off by default: measured slower
+// rows of a read whose sequential graph state (33 bytes per row) still goes to shared memory: 6144 rows = 198 KB
+// of the 227 KB a CTA may have on B200; larger reads use global scratch.  MR_HUGE_ROWS lowers it (tests).
+inline int path_smem_rows_limit() {
+  static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? std::min(x, 6144) : 6144; }();
   return v;
 }
 inline int big_rows_threshold() {

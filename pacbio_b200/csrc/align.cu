@@ -1145,7 +1145,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
   MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  MR_CUDA(ctx, ctx->wait(st));
   if(h_ctr[11]) return ctx->fail(MR_ELIMIT, "mr_align_batch: 2^32 or more hits in one 1024-base tile; use --max-count");
   const uint64_t H = h_ctr[1];
   MR_TRACE_MSG("batch: %u reads, %llu bases, %llu lookups, %llu raw hits", nreads, (unsigned long long)T, (unsigned long long)h_ctr[0], (unsigned long long)H);
@@ -1188,7 +1188,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     // group heads -> group_start
     MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    MR_CUDA(ctx, ctx->wait(st));
     G = h_ctr[3];
     MR_TRACE_MSG("sorted; %llu groups", (unsigned long long)G);
     const uint64_t Hvalid = H - h_ctr[2];
@@ -1247,7 +1247,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       max_rows_kernel<<<div_up(nreads, 256), 256, 0, st>>>(ws.read_cnt.as<uint32_t>(), nreads, ctr + 12);
       MR_LAUNCHED(ctx);
       MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 13 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      MR_CUDA(ctx, cudaStreamSynchronize(st));
+      MR_CUDA(ctx, ctx->wait(st));
       S = h_ctr[4];
       MR_TRACE_MSG("chained; %llu rows (capacity %llu)", (unsigned long long)S, (unsigned long long)cap);
       if(S <= cap) break;
@@ -1306,7 +1306,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                              ws.scan_scratch, (uint64_t*)(ctr + 7))));
     MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 7, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr + 7, ctr + 7, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    MR_CUDA(ctx, ctx->wait(st));
     const uint64_t Hf = h_ctr[7];
     MR_TRACE_MSG("fine pass: %llu windows, %llu hits inside them", (unsigned long long)S, (unsigned long long)Hf);
     if(Hf >= (1ULL << 32)) return ctx->fail(MR_ELIMIT, "mr_align_batch: too many fine-pass hits in one batch; use smaller batches");
@@ -1349,7 +1349,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
     MR_TRY(launch_chain(ctx, F, ws.group_lists));
     MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    MR_CUDA(ctx, ctx->wait(st));
     if(h_ctr[4] != S) return ctx->fail(MR_ECUDA, "mr_align_batch: internal error, the fine pass lost rows");
     A = F;
     k_coords = kk;
@@ -1435,7 +1435,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     MR_CUDA(ctx, cudaMemcpyAsync(hl.data(), ws.tap_lens.p, G * 8, cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaMemcpyAsync(hcf.data(), ws.tap_cf.p, H * 4, cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, cudaMemcpyAsync(hcb.data(), ws.tap_cb.p, H * 4, cudaMemcpyDeviceToHost, st));
-    MR_CUDA(ctx, cudaStreamSynchronize(st));
+    MR_CUDA(ctx, ctx->wait(st));
     std::vector<uint64_t> ord(G);
     for(uint64_t g = 0; g < G; ++g) ord[g] = g;
     std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return hk[hg[a]] < hk[hg[b]]; });
@@ -1455,7 +1455,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     }
   }
   timer.end();
-  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  MR_CUDA(ctx, ctx->wait(st));
   MR_TRACE_MSG("batch done");
   *out = res.release();
   return MR_OK;
@@ -1585,7 +1585,7 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
   timer.next("result download");
   MR_TRY(download_rows(ctx, ws, res.get(), fin, nreads, S, info_total, &GA));
   timer.end();
-  MR_CUDA(ctx, cudaStreamSynchronize(st));
+  MR_CUDA(ctx, ctx->wait(st));
   timer.collect();
   *out = res.release();
   return MR_OK;

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 thread_local std::string g_mr_create_error;
 
@@ -49,6 +50,12 @@ int mr_context_create(int device, mr_context** out) {
   for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for(auto& v : ctx->ev) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+  {
+    const char* env = getenv("MR_BLOCKING_SYNC");
+    const unsigned cores = std::thread::hardware_concurrency();
+    ctx->blocking_sync = env && *env ? atoi(env) != 0 : (cores != 0 && cores / (unsigned)count < 8);
+    cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventDisableTiming | cudaEventBlockingSync);
+  }
   *out = ctx.release();
   return MR_OK;
 }
@@ -61,6 +68,7 @@ void mr_context_destroy(mr_context* ctx) {
   for(auto& a : ctx->aux) if(a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
   if(ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for(auto& v : ctx->ev) if(v) cudaEventDestroy(v);
+  if(ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if(ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -143,7 +143,7 @@ int main(int argc, char* argv[]) {
     G.k_len = k_mer;
     const unsigned fthreads = std::max(1u, threads);
     const uint64_t nb = mrh::run_pipeline(DS, pacbio, P,
-      [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<std::string>& parts) {
+      [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<mrh::text_buf>& parts) {
         mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts);
       }, out);
     const auto t2 = std::chrono::steady_clock::now();

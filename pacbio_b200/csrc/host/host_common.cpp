@@ -1,4 +1,5 @@
 #include <cerrno>
+#include <new>
 #include <cstring>
 #include "host_common.hpp"
 
@@ -12,6 +13,26 @@
 #include <thread>
 
 namespace mrh {
+
+// ================================================================================================
+// output text
+// ================================================================================================
+void text_buf::release() { free(p_); p_ = nullptr; size_ = cap_ = 0; }
+void text_buf::grow(size_t need) {
+  size_t cap = std::max<size_t>(need + need / 4, 1 << 16);
+  cap = (cap + 4095) & ~(size_t)4095;
+  char* q = (char*)aligned_alloc(4096, cap);
+  if(!q) throw std::bad_alloc();
+  if(size_) memcpy(q, p_, size_);
+  free(p_);
+  p_ = q; cap_ = cap;
+}
+void text_buf::flush() { }
+void text_buf::append(const char* s, size_t n) {
+  if(size_ + n > cap_) grow(size_ + n);
+  memcpy(p_ + size_, s, n);
+  size_ += n;
+}
 
 // ================================================================================================
 // super-reads
@@ -111,23 +132,25 @@ void unitigs::load_sequences(const std::string& path) {
   std::ifstream is(path, std::ios::binary);
   if(!is.good()) throw std::runtime_error("Failed to open unitigs sequence file '" + path + "'");
   std::string hdr, s;
+  off.assign(1, 0);
   while(std::getline(is, hdr)) {
     if(!std::getline(is, s)) s.clear();
     len.push_back((int32_t)s.size());
-    seq.push_back(s);
+    fwd += s;
+    off.push_back(fwd.size());
   }
   // Printing a mega-read copies the unitigs of its path, reverse-complemented for 'R' entries;
   // doing the complement once here turns every later append into a memcpy.
-  rc_seq.resize(seq.size());
+  rc.resize(fwd.size());
   const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::vector<std::thread> th;
   for(unsigned t = 0; t < nt; ++t)
     th.emplace_back([&, t]() {
-      for(size_t i = t; i < seq.size(); i += nt) {
-        const std::string& f = seq[i];
-        std::string& r = rc_seq[i];
-        r.resize(f.size());
-        for(size_t j = 0; j < f.size(); ++j) r[j] = revcomp_table.t[(unsigned char)f[f.size() - 1 - j]];
+      for(size_t i = t; i + 1 < off.size(); i += nt) {
+        const char* f = fwd.data() + off[i];
+        char* r = &rc[off[i]];
+        const size_t n = off[i + 1] - off[i];
+        for(size_t j = 0; j < n; ++j) r[j] = revcomp_table.t[(unsigned char)f[n - 1 - j]];
       }
     });
   for(auto& x : th) x.join();
@@ -221,6 +244,45 @@ bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_rea
 // mega-reads from the device's graph rows
 // ================================================================================================
 namespace {
+// ---- number formatting.  A mega-read line holds three "%.2f" / "%.4f" doubles (overlap_graph.cc:285-290);
+// glibc's printf spends ~0.4 us on each (multi-precision), a quarter of the whole formatting stage.
+inline int fmt_uint(char* p, uint64_t v) {
+  char t[24];
+  int n = 0;
+  do { t[n++] = (char)('0' + v % 10); v /= 10; } while(v);
+  for(int i = 0; i < n; ++i) p[i] = t[n - 1 - i];
+  return n;
+}
+inline int fmt_int(char* p, int64_t v) {
+  if(v < 0) { *p = '-'; return 1 + fmt_uint(p + 1, (uint64_t)0 - (uint64_t)v); }
+  return fmt_uint(p, (uint64_t)v);
+}
+// Exactly what printf("%.<d>f", x) prints, d = 2 or 4, round-to-nearest with ties to even ON THE EXACT VALUE:
+// x * 10^d = r + e with r the rounded product and e = fma(x, 10^d, -r) its exact error, so the position of
+// the exact value relative to the half-way point is known without any wide arithmetic (r < 2^52: r - floor(r)
+// and its distance to 0.5 are exact, and |e| is below half of their granularity).  Checked against glibc
+// on 4e7 operands including decimal and binary ties (tests/test_host_cli.py).
+inline int fmt_fixed(char* p, double x, int d) {
+  const double ax = std::fabs(x);
+  if(!(ax < 1e11)) return snprintf(p, 64, "%.*f", d, x);      // huge, inf, nan: the library's way
+  const double scale = d == 2 ? 100.0 : 10000.0;
+  const uint64_t iscale = d == 2 ? 100 : 10000;
+  const double r = ax * scale;
+  const double e = std::fma(ax, scale, -r);
+  const double fl = std::floor(r);
+  const double diff = (r - fl) - 0.5;
+  uint64_t n = (uint64_t)fl;
+  if(diff > 0 || (diff == 0 && e > 0)) ++n;
+  else if(diff == 0 && e == 0) n += n & 1;
+  char* q = p;
+  if(std::signbit(x)) *q++ = '-';
+  q += fmt_uint(q, n / iscale);
+  *q++ = '.';
+  uint64_t f = n % iscale;
+  for(int i = d - 1; i >= 0; --i) { q[i] = (char)('0' + f % 10); f /= 10; }
+  return (int)(q + d - p);
+}
+
 struct mega_read {
   int    start_node, end_node, start_unitig, start_offset, end_offset, nb_unitigs;
   double imp_s, imp_e, tiling_start, tiling_end, density;
@@ -252,14 +314,47 @@ struct joined_set {
 };
 } // namespace
 
+uint64_t selftest_fixed_format(uint64_t samples, uint64_t seed) {
+  uint64_t state = seed * 0x9e3779b97f4a7c15ULL + 1, bad = 0;
+  auto next = [&]() { state ^= state << 13; state ^= state >> 7; state ^= state << 17; return state; };
+  char a[80], b[80];
+  auto check = [&](double x) {
+    for(int d = 2; d <= 4; d += 2) {
+      const int n = fmt_fixed(a, x, d);
+      a[n] = 0;
+      snprintf(b, sizeof b, "%.*f", d, x);
+      bad += strcmp(a, b) != 0;
+    }
+  };
+  const double fixed[] = { 0.0, 0.125, 0.375, 2.675, 1.005, 0.005, 0.015, 0.025, 0.00005, 0.00015, 1e-13, 0.5, 1.5, 2.5, 0.045,
+                           99999.995, 12345.675, 1e10, 9.99999e10, 1e11, 3.14159, 0.999999, 0.995, 0.99995, 4.35, 4.345, 1e-300, 5e-324 };
+  for(double x : fixed) { check(x); check(-x); }
+  for(uint64_t i = 0; i < samples; ++i) {
+    double x;
+    const uint64_t r = next();
+    switch(i & 7) {
+    case 0: x = (double)(r % 2000000) / 100.0; break;
+    case 1: x = (double)(r % 200000000) / 10000.0; break;
+    case 2: x = (double)(r % 4000001) / 200.0; break;            // decimal half-way points
+    case 3: x = (double)(r % 40000001) / 20000.0; break;
+    case 4: x = std::ldexp((double)(r >> 11), -53) * 20000.0; break;
+    case 5: x = std::ldexp((double)(r >> 11), -53); break;
+    case 6: x = (double)(r % 1000000) / 1024.0; break;           // binary fractions: exact ties
+    default: x = std::ldexp((double)(r >> 11), -53 + (int)(next() % 40) - 10); break;
+    }
+    check(next() & 1 ? -x : x);
+  }
+  return bad;
+}
+
 void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
-                       const super_reads& sr, const unitigs& u, const graph_options& o, std::string& out) {
+                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out) {
   const double K = o.k_len;
   std::vector<mega_read> mrs;
   std::vector<int> sort_tiling, tiled;
   std::vector<uint32_t> path;
   std::vector<double> weights;
-  char buf[256];
+  char buf[1024];
   // ids come from super-read names, lengths from the -l/-u table: the libraries refuse a table that
   // does not cover the names (mr_align_batch, mr_graph_batch), this keeps a stray id from reading
   // past the table all the same
@@ -430,37 +525,49 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       for(int i = mr.start_unitig; i < mr.start_unitig + mr.nb_unitigs; ++i) sr_len += ulen_of(path_id(i));
       sr_len -= (mr.nb_unitigs - 1) * ((int)o.k_len - 1);
       const uint64_t qe_out = (uint64_t)(int64_t)(sr_len + mr.end_offset) - ((uint64_t)v.ql[erow] - (uint64_t)(int64_t)v.qe[erow]);
-      snprintf(buf, sizeof(buf), "%.2f %.2f %d %d %d %llu %d %.4f ", mr.imp_s, mr.imp_e, v.rs[srow], v.re[erow],
-               v.qs[srow] - mr.start_offset, (unsigned long long)qe_out, v.lpath[erow], mr.density);
-      out += buf;
-      for(size_t t = 0; t < path.size(); ++t) {             // "<id><F|R>" joined by '_': no printf per unitig
-        char nb[16];
-        int len = 0;
-        uint32_t id = path[t] >> 1;
-        nb[15 - len++] = (path[t] & 1) ? 'R' : 'F';
-        do { nb[15 - len++] = (char)('0' + id % 10); id /= 10; } while(id);
-        if(t) nb[15 - len++] = '_';
-        out.append(nb + 16 - len, (size_t)len);
+      // "%.2f %.2f %d %d %d %llu %d %.4f " (overlap_graph.cc:285-290), then "<id><F|R>" joined by '_', " sr_len"
+      char* w = buf;
+      w += fmt_fixed(w, mr.imp_s, 2); *w++ = ' ';
+      w += fmt_fixed(w, mr.imp_e, 2); *w++ = ' ';
+      w += fmt_int(w, v.rs[srow]); *w++ = ' ';
+      w += fmt_int(w, v.re[erow]); *w++ = ' ';
+      w += fmt_int(w, v.qs[srow] - mr.start_offset); *w++ = ' ';
+      w += fmt_uint(w, qe_out); *w++ = ' ';
+      w += fmt_int(w, v.lpath[erow]); *w++ = ' ';
+      w += fmt_fixed(w, mr.density, 4); *w++ = ' ';
+      for(size_t t = 0; t < path.size(); ++t) {
+        if(w - buf > (ptrdiff_t)sizeof(buf) - 32) { out.append(buf, (size_t)(w - buf)); w = buf; }
+        if(t) *w++ = '_';
+        w += fmt_uint(w, path[t] >> 1);
+        *w++ = (path[t] & 1) ? 'R' : 'F';
       }
-      snprintf(buf, sizeof(buf), " %d", sr_len);
-      out += buf;
-      if(!u.seq.empty()) {                                // super_read_name::print_sequence (super_read_name.cc:123-132)
-        out += ' ';
+      *w++ = ' ';
+      w += fmt_int(w, sr_len);
+      if(u.has_sequences()) {                             // super_read_name::print_sequence (super_read_name.cc:123-132)
+        *w++ = ' ';
+        out.append(buf, (size_t)(w - buf)); w = buf;
         const size_t pb = std::min((size_t)mr.start_unitig, path.size());
         const size_t pe = std::min((size_t)(mr.start_unitig + mr.nb_unitigs), path.size());
+        const size_t nu = u.len.size();
         for(size_t i = pb; i < pe; ++i) {
-          const std::string& s = (path[i] & 1) ? u.rc_seq.at(path[i] >> 1) : u.seq.at(path[i] >> 1);
-          const size_t skip = i == pb ? 0 : (size_t)o.k_len - 1;
-          if(skip < s.size()) out.append(s, skip, std::string::npos);
+          const uint32_t id = path[i] >> 1;
+          if(id >= nu) throw std::out_of_range("unitig id of a super-read name is not in the -u file");   // vector::at in the reference
+          if(i + 1 < pe && (path[i + 1] >> 1) < nu) {     // next piece: start fetching its first lines now
+            const char* nx = u.sequence(path[i + 1] >> 1, path[i + 1] & 1);
+            __builtin_prefetch(nx); __builtin_prefetch(nx + 64); __builtin_prefetch(nx + 128); __builtin_prefetch(nx + 192);
+          }
+          const size_t sl = (size_t)u.len[id], skip = i == pb ? 0 : (size_t)o.k_len - 1;
+          if(skip < sl) out.append(u.sequence(id, path[i] & 1) + skip, sl - skip);
         }
       }
-      out += '\n';
+      *w++ = '\n';
+      out.append(buf, (size_t)(w - buf));
     }
   }
 }
 
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
-                          const graph_options& o, unsigned threads, std::vector<std::string>& parts) {
+                          const graph_options& o, unsigned threads, std::vector<text_buf>& parts) {
   const uint32_t nreads = v.nreads;
   threads = std::max(1u, std::min(threads, nreads / 64 + 1));
   parts.resize(threads);
@@ -474,14 +581,15 @@ void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, cons
     if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
   }
   auto work = [&](unsigned t) {
-    std::string& out = parts[t];
+    text_buf& out = parts[t];
     out.clear();
     // a mega-read line carries its sequence: about 1.3 output bytes per read base on typical data;
     // reserving up front keeps the appends from reallocating (and copying) the growing buffer
     const uint64_t bases = batch.start[cut[t + 1]] - batch.start[cut[t]];
-    const size_t want = u.seq.empty() ? (size_t)(bases / 16 + 4096) : (size_t)(bases + bases / 2 + 4096);
+    const size_t want = !u.has_sequences() ? (size_t)(bases / 16 + 4096) : (size_t)(bases + bases / 2 + 4096);
     if(out.capacity() < want) out.reserve(want);
     format_mega_reads(v, batch, cut[t], cut[t + 1], sr, u, o, out);
+    out.flush();
   };
   if(threads == 1) { work(0); return; }
   // an exception in a worker must reach the caller's catch, not std::terminate
@@ -561,7 +669,7 @@ bool load_result(const std::string& path, result_dump& d) {
 
 // default ostream formatting of a double: "%g" with 6 significant digits (jf_aligner.cc:58)
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
-                   bool compact, bool zero_skip, std::string& out) {
+                   bool compact, bool zero_skip, text_buf& out) {
   char buf[512];
   for(uint32_t r = r0; r < r1; ++r) {
     const uint64_t b = v.read_coords[r], e = v.read_coords[r + 1];
@@ -589,7 +697,7 @@ void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0
   }
 }
 
-void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, std::string& out) {
+void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, text_buf& out) {
   uint64_t ng = 0, no = 0, nl = 0;
   const int64_t* groups = nullptr; const int32_t* offsets = nullptr; const uint32_t* lis = nullptr;
   if(mr_result_taps(r, &ng, &groups, &no, &offsets, &nl, &lis) != MR_OK) return;

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -35,8 +36,15 @@ struct super_reads {
 // ---- k-unitigs: read_unitigs_lengths / read_unitigs_sequences (misc.cc:11-37)
 struct unitigs {
   std::vector<int32_t>     len;
-  std::vector<std::string> seq;          // only with -u
-  std::vector<std::string> rc_seq;       // reverse complements (rev_comp_ of super_read_name.cc:106-114), built once at load
+  // only with -u: every sequence back to back in one arena, and the reverse complements
+  // (rev_comp_ of super_read_name.cc:106-114, built once at load) in a second one with the same offsets.
+  // Printing a mega-read copies ~20 unitigs of ~500 bases: with one heap string per unitig every piece cost
+  // two dependent cache misses before the copy could start; an offset table that fits the L2 and
+  // contiguous text (prefetched one piece ahead) make the copy run at memcpy speed.
+  std::string              fwd, rc;
+  std::vector<uint64_t>    off;          // len.size() + 1 offsets into fwd / rc
+  bool has_sequences() const { return !off.empty(); }
+  const char* sequence(uint32_t id, bool reversed) const { return (reversed ? rc.data() : fwd.data()) + off[id]; }
   void load_lengths(const std::string& path);
   void load_sequences(const std::string& path);
 };
@@ -69,6 +77,35 @@ public:
   bool next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads);
 };
 
+// ---- output text.  A batch of mega-read records is tens of megabytes that are written once and read
+// once (by fwrite): a growable byte buffer that never zero-fills or re-copies its storage.  (Streaming
+// stores for the unitig sequences were measured too: faster in isolation, slower here, where the
+// buffers of a batch are reused and stay in the last-level cache.)
+class text_buf {
+  char*  p_ = nullptr;
+  size_t size_ = 0, cap_ = 0;
+  void grow(size_t need);
+public:
+  text_buf() = default;
+  text_buf(const text_buf&) = delete;
+  text_buf& operator=(const text_buf&) = delete;
+  text_buf(text_buf&& o) noexcept : p_(o.p_), size_(o.size_), cap_(o.cap_) { o.p_ = nullptr; o.size_ = o.cap_ = 0; }
+  text_buf& operator=(text_buf&& o) noexcept { if(this != &o) { release(); p_ = o.p_; size_ = o.size_; cap_ = o.cap_; o.p_ = nullptr; o.size_ = o.cap_ = 0; } return *this; }
+  ~text_buf() { release(); }
+  void release();
+  const char* data() const { return p_; }
+  size_t size() const { return size_; }
+  size_t capacity() const { return cap_; }
+  bool empty() const { return size_ == 0; }
+  void clear() { size_ = 0; }
+  void reserve(size_t n) { if(n > cap_) grow(n); }
+  void append(const char* s, size_t n);
+  void flush();
+  text_buf& operator+=(char c) { if(size_ + 1 > cap_) grow(size_ + 1); p_[size_++] = c; return *this; }
+  text_buf& operator+=(const char* s) { append(s, strlen(s)); return *this; }
+  text_buf& operator+=(const std::string& s) { append(s.data(), s.size()); return *this; }
+};
+
 // ---- options shared by the two tools (Appendix B of SURVEY.md; create_mega_reads_cmdline.yaggo)
 struct graph_options {
   double   overlap_play = 1.3;
@@ -81,11 +118,11 @@ struct graph_options {
 // Text records of create_mega_reads for reads [r0, r1) of a result (overlap_graph.cc:61-299,
 // overlap_graph.hpp:198-262): best terminal node per component, tiling, one line per mega-read.
 void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
-                       const super_reads& sr, const unitigs& u, const graph_options& o, std::string& out);
+                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out);
 // same, fanned out over `threads` host threads; parts[0], parts[1], ... concatenated are the records
 // in read order (kept apart so that nobody has to copy hundreds of megabytes of text once more)
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
-                          const graph_options& o, unsigned threads, std::vector<std::string>& parts);
+                          const graph_options& o, unsigned threads, std::vector<text_buf>& parts);
 
 // Debug / profiling aid: one batch's result rows + read names on disk (MR_DUMP_BATCH=<file> in the bench's
 // host path writes the first batch), read back by pacbio_b200/tools/format_replay to time the
@@ -102,14 +139,19 @@ struct result_dump {
 bool dump_result(const std::string& path, const mr_result_view& v, const read_batch& batch);
 bool load_result(const std::string& path, result_dump& d);
 
+// self test of the fixed-point number formatter behind the mega-read lines: `samples` pseudo-random doubles
+// (decimal grids, half-way points, binary fractions, wide exponent range), "%.2f" and "%.4f", against
+// the C library; returns the number of strings that differ (must be 0)
+uint64_t selftest_fixed_format(uint64_t samples, uint64_t seed);
+
 // jf_aligner coords records (jf_aligner.cc:41-70)
 void format_coords(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr,
-                   bool compact, bool zero_skip, std::string& out);
+                   bool compact, bool zero_skip, text_buf& out);
 
 // jf_aligner --details records (jf_aligner.cc:72-108): one line per (read, super-read) pair with every
 // k-mer hit "pb:sr" in read order, the hits of the reported chain in brackets.  Needs the parity
 // taps of the result (mr_context_keep_taps).
-void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, std::string& out);
+void format_details(const mr_result* r, const read_batch& batch, const super_reads& sr, text_buf& out);
 
 // ---- compact coords files (jf_aligner --coords, format of print_coords, jf_aligner.cc:41-70),
 // read back the way longest_path_overlap_graph2 does (coords_parsing.cc:7-64): records

@@ -94,7 +94,7 @@ int main(int argc, char* argv[]) {
     uint64_t max_rows = 1u << 20;
     if(const char* e = getenv("MR_BATCH_ROWS")) max_rows = strtoull(e, nullptr, 0);
     mrh::coords_batch b;
-    std::vector<std::string> parts;
+    std::vector<mrh::text_buf> parts;
     while(in.next_batch(b, max_rows)) {
       const mr_result_view rows = b.view();
       mr_result* r = nullptr;

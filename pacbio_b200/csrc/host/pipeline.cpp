@@ -196,7 +196,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
 
   std::thread formatter([&]() {
     job j;
-    std::vector<std::string> parts;
+    std::vector<text_buf> parts;
     std::map<uint64_t, job> waiting;           // aligned out of turn (several aligner threads)
     uint64_t next_seq = 0;
     while(to_format.pop(j)) {

@@ -72,7 +72,7 @@ bool stage_batches();
 // adds per_device - 1 more contexts for every device of ds, sharing the device's index
 void add_streams(device_set& ds, unsigned per_device);
 
-typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<std::string>&)> format_fn;
+typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<text_buf>&)> format_fn;
 
 // runs the whole stream; returns the number of read bases processed
 uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,

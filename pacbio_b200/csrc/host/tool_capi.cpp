@@ -21,7 +21,7 @@ struct tool {
   uint64_t last_text_bytes = 0, last_d2h_bytes = 0, last_h2d_bytes = 0, last_coords = 0;
   uint64_t last_lookups = 0, last_hits = 0, last_groups = 0;
   double   last_align_s = 0, last_format_s = 0;       // busy time of the two pipeline stages
-  std::vector<std::string> parts;                     // text buffers, kept between runs (no re-faulting of ~1 GB)
+  std::vector<mrh::text_buf> parts;                   // text buffers, kept between runs (no re-faulting of ~1 GB)
 };
 }
 
@@ -117,7 +117,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
   bool   stop = false;
   std::string error, align_error;
   std::thread formatter([&]() {
-    std::vector<std::string>& parts = t->parts;
+    std::vector<mrh::text_buf>& parts = t->parts;
     for(size_t i = 0; i < nb; ++i) {
       mr_result* r = nullptr;
       {
@@ -211,6 +211,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
 int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   return mrh_tool_run_range(p, threads, out_path, 0, ~0ULL);
 }
+uint64_t mrh_selftest_fixed_format(uint64_t samples, uint64_t seed) { return mrh::selftest_fixed_format(samples, seed); }
 void mrh_tool_stage_seconds(void* p, double* align_s, double* format_s) {
   tool* t = (tool*)p; *align_s = t->last_align_s; *format_s = t->last_format_s;
 }

@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
     G.k_len = (uint32_t)atoi(argv[4]);
     const unsigned threads = (unsigned)atoi(argv[5]);
     const int reps = argc > 6 ? atoi(argv[6]) : 5;
-    std::vector<std::string> parts;
+    std::vector<mrh::text_buf> parts;
     double best = 1e30;
     uint64_t bytes = 0;
     for(int i = 0; i < reps; ++i) {

@@ -497,6 +497,9 @@ def ours(args, w, files):
         getattr(H, f).argtypes = [C.c_void_p]
     H.mrh_tool_batch_bases.restype = C.c_void_p
     H.mrh_tool_batch_bases.argtypes = [C.c_void_p, C.c_uint64, api.u64p]
+    for f in ("mrh_tool_batch_codes", "mrh_tool_batch_nmask"):
+        getattr(H, f).restype = api.u64p
+        getattr(H, f).argtypes = [C.c_void_p, C.c_uint64, api.u64p]
     H.mrh_tool_batch_starts.restype = api.u64p
     H.mrh_tool_batch_starts.argtypes = [C.c_void_p, C.c_uint64, api.u32p]
     H.mrh_tool_last_stats.argtypes = [C.c_void_p, api.u64p]
@@ -553,14 +556,17 @@ def ours(args, w, files):
     host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, args.gpus))
 
     # ---- device-resident copies of every batch ------------------------------------------------------
+    # (the form a batch travels and is aligned in: 2 bits per base + a non-ACGT mask, mr_pack_reads)
     dev = []
     for i in range(nbatches):
-        nb, nr = C.c_uint64(), C.c_uint32()
-        pb = H.mrh_tool_batch_bases(tool, i, C.byref(nb))
+        nc, nm, nr = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        pc = H.mrh_tool_batch_codes(tool, i, C.byref(nc))
+        pm = H.mrh_tool_batch_nmask(tool, i, C.byref(nm))
         ps = H.mrh_tool_batch_starts(tool, i, C.byref(nr))
-        hb = np.ctypeslib.as_array(C.cast(pb, api.u8p), shape=(nb.value,))
+        hc = np.ctypeslib.as_array(pc, shape=(nc.value,)).view(np.int64)
+        hm = np.ctypeslib.as_array(pm, shape=(nm.value,)).view(np.int64)
         hs = np.ctypeslib.as_array(ps, shape=(nr.value + 1,))
-        dev.append((torch.from_numpy(hb).cuda(), torch.from_numpy(hs.astype(np.int64)).cuda(), hs.copy(), nr.value))
+        dev.append((torch.from_numpy(hc).cuda(), torch.from_numpy(hm).cuda(), torch.from_numpy(hs.astype(np.int64)).cuda(), hs.copy(), nr.value))
     stream = torch.cuda.ExternalStream(L.mr_context_stream(ctx))
 
     phase = {}
@@ -574,10 +580,11 @@ def ours(args, w, files):
         lnames = (C.c_char_p * 32)(); lsecs = (C.c_double * 32)()
         ph, cn = {}, dict(lookups=0, tails=0, hits=0, groups=0, coords=0, lists=0, buckets=0)
         try:
-            for db, ds, hs, nr in dev[lane::nstreams]:
+            for dc, dm, ds, hs, nr in dev[lane::nstreams]:
                 out = C.c_void_p()
-                rc = L.mr_align_batch_device(c, idx, C.cast(params, C.POINTER(api.Params)), C.c_void_p(db.data_ptr()), C.c_void_p(ds.data_ptr()),
-                                             hs.ctypes.data_as(api.u64p), nr, C.byref(out))
+                rc = L.mr_align_batch_device_packed(c, idx, C.cast(params, C.POINTER(api.Params)), C.c_void_p(dc.data_ptr()),
+                                                    C.c_void_p(dm.data_ptr()), C.c_void_p(ds.data_ptr()),
+                                                    hs.ctypes.data_as(api.u64p), nr, C.byref(out))
                 if rc != 0:
                     raise RuntimeError(L.mr_last_error(c).decode())
                 if collect:
@@ -654,9 +661,9 @@ def ours(args, w, files):
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     # Phase timers are CUDA events recorded on the library's own stream around each phase; the
     # "seed lookup" phase is exactly one launch of seed_lookup_kernel per batch.  Algorithmic bytes
-    # (kernel table): per read base 1 B read (ASCII) + 4 B written (list size); per position
-    # that keeps a list 16 B written (lookup record); per looked-up k-mer 2 strands x 8 B (the bucket's
-    # two bounds in the prefix table); 1 B per tail entry scanned in the tail array.
+    # (kernel table): per read base 0.375 B read (2-bit code + mask bit) + 4 B written (list size);
+    # per position that keeps a list 16 B written (lookup record); per looked-up k-mer 2 strands x 8 B (the
+    # bucket's two bounds in the prefix table); 1 B per tail entry scanned in the tail array.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -669,7 +676,7 @@ def ours(args, w, files):
         T = total_bases * args.steps
         kern = "seed lookup"
         nparts = int(L.mr_index_parts(idx))           # an index of several parts: every part is probed for every k-mer
-        alg = T * 5 + counters["lists"] * 16 + counters["lookups"] * 16 * nparts + counters["tails"] * 1
+        alg = T * 4.375 + counters["lists"] * 16 + counters["lookups"] * 16 * nparts + counters["tails"] * 1
         launches_k = nbatches * args.steps * nparts
         achieved = alg / phase[kern] / 1e9 if phase.get(kern, 0) > 0 else 0.0
         traffic, hit = None, None

@@ -150,6 +150,20 @@ int  mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p,
 int  mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p,
                            const char* d_bases, const uint64_t* d_read_start, const uint64_t* h_read_start,
                            uint32_t nreads, mr_result** out);
+/* ---- packed reads.  The library keeps a batch on the device 2-bit packed (the layout of the reference's
+ *  compact_dna, src_psa/compact_dna.hpp:102-136: base g at bits 2 (g % 32) of word g / 32, A0 C1 G2 T3,
+ *  non-ACGT as 0) next to a mask with bit g % 64 of word g / 64 set where the character was not one of
+ *  ACGTacgt (those break k-mers, jf_aligner.hpp:41-52): 0.375 bytes per base over PCIe instead of one.
+ *  mr_pack_reads fills caller-owned arrays of mr_packed_code_words(n) / mr_packed_mask_words(n) words (the
+ *  counts include the padding the kernels may read); the _packed entry points take such arrays.  The
+ *  entry points that take characters pack them on the device.                                        */
+uint64_t mr_packed_code_words(uint64_t nbases);
+uint64_t mr_packed_mask_words(uint64_t nbases);
+int  mr_pack_reads(const char* bases, uint64_t nbases, uint64_t* codes, uint64_t* nmask);
+int  mr_align_batch_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* codes, const uint64_t* nmask,
+                           const uint64_t* read_start, uint32_t nreads, mr_result** out);
+int  mr_align_batch_device_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* d_codes, const uint64_t* d_nmask,
+                                  const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out);
 void mr_result_free(mr_result* r);
 
 /* Structure-of-arrays view of a result.  Coords of read r are rows
@@ -194,6 +208,8 @@ int  mr_result_get(const mr_result* r, mr_result_view* view);
  *  mr_align_staged / mr_staged_free returns.                                                     */
 typedef struct mr_staged mr_staged;
 int  mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_start, uint32_t nreads, mr_staged** out);
+int  mr_stage_batch_packed(mr_context* ctx, const uint64_t* codes, const uint64_t* nmask, const uint64_t* read_start, uint32_t nreads,
+                           mr_staged** out);
 int  mr_align_staged(mr_context* ctx, mr_index* idx, const mr_params* p, mr_staged* staged, mr_result** out);
 void mr_staged_free(mr_staged* staged);
 

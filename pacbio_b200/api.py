@@ -99,6 +99,16 @@ def lib():
                                  C.POINTER(C.c_void_p)]
     L.mr_align_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, u64p,
                                         C.c_uint32, C.POINTER(C.c_void_p)]
+    L.mr_packed_code_words.restype = C.c_uint64
+    L.mr_packed_code_words.argtypes = [C.c_uint64]
+    L.mr_packed_mask_words.restype = C.c_uint64
+    L.mr_packed_mask_words.argtypes = [C.c_uint64]
+    L.mr_pack_reads.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p]
+    L.mr_align_batch_packed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), u64p, u64p, u64p, C.c_uint32,
+                                        C.POINTER(C.c_void_p)]
+    L.mr_align_batch_device_packed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, u64p,
+                                               C.c_uint32, C.POINTER(C.c_void_p)]
+    L.mr_stage_batch_packed.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.mr_stage_batch.argtypes = [C.c_void_p, C.c_void_p, u64p, C.c_uint32, C.POINTER(C.c_void_p)]
     L.mr_align_staged.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(C.c_void_p)]
     L.mr_staged_free.argtypes = [C.c_void_p]
@@ -162,6 +172,18 @@ def load_fasta(path):
     lens = np.bincount(rec_id, weights=line_len, minlength=len(names)).astype(np.uint64)
     starts = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     return names, data[keep], starts
+
+
+def pack_reads(bases):
+    """uint8 characters -> (codes, nmask) as mr_pack_reads lays them out (padding words included)."""
+    L = lib()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    codes = np.zeros(L.mr_packed_code_words(len(bases)), dtype=np.uint64)
+    nmask = np.zeros(L.mr_packed_mask_words(len(bases)), dtype=np.uint64)
+    rc = L.mr_pack_reads(bases.ctypes.data_as(C.c_void_p), len(bases), _p(codes, u64p), _p(nmask, u64p))
+    if rc != 0:
+        raise MrError("mr_pack_reads failed (%d)" % rc)
+    return codes, nmask
 
 
 class SuperReads:
@@ -258,6 +280,16 @@ class Context:
         starts = np.ascontiguousarray(reads.starts, dtype=np.uint64)
         self.check(self.L.mr_align_batch(self.h, index.h, C.byref(params), reads.bases.ctypes.data_as(C.c_void_p),
                                          _p(starts, u64p), reads.nreads, C.byref(out)))
+        return Result(self, out)
+
+    def align_packed(self, index, reads, params):
+        """Same as align(), through the packed entry point: the batch is packed on the host (mr_pack_reads) and
+        crosses PCIe at 0.375 bytes per base."""
+        out = C.c_void_p()
+        starts = np.ascontiguousarray(reads.starts, dtype=np.uint64)
+        codes, nmask = pack_reads(reads.bases)
+        self.check(self.L.mr_align_batch_packed(self.h, index.h, C.byref(params), _p(codes, u64p), _p(nmask, u64p),
+                                                _p(starts, u64p), reads.nreads, C.byref(out)))
         return Result(self, out)
 
     def stage(self, reads):

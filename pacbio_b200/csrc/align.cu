@@ -115,18 +115,60 @@ struct tile_kmers {
   bool     cand[4];      // ... and still inside the first 17 bases of its N-free run: toggles `flag`
 };
 
+// Reads travel and live on the device 2-bit packed (compact_dna layout: base g at bits 2 (g % 32) of word
+// g / 32, A0 C1 G2 T3) next to a 1-bit mask of the non-ACGT positions: 0.375 bytes per base instead of one
+// ASCII character.  packed_reads::codes / nmask are padded by at least 4 words past the last base.
+// A tile's words (at most 37 + 19) are staged in shared memory by the TMA engine (two 1-D bulk copies
+// completing on an mbarrier) when the arrays are 16-byte aligned -- always, for the library's own
+// buffers -- and by ordinary loads otherwise.
+constexpr int kTileCodeWords = (kTile + 64 + 32) / 32 + 4;       // 39
+constexpr int kTileMaskWords = (kTile + 64 + 32) / 64 + 4;       // 21
+struct tile_stage {
+  alignas(16) uint64_t cw[kTileCodeWords + 1];
+  alignas(16) uint64_t mw[kTileMaskWords + 1];
+  alignas(8)  uint64_t bar;
+};
+static_assert(kTileCodeWords % 2 == 1 && kTileMaskWords % 2 == 1, "the + 1 keeps the arrays a multiple of 16 bytes");
+
 // Loads the tile's bases (plus look-back / look-ahead) into shared memory as codes; codes[] needs
 // kTile + 64 bytes.  Returns whether this thread loaded a non-ACGT code (positions outside the read
 // count as such).  Ends with a barrier.
-__device__ __forceinline__ bool load_tile_codes(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
-                                                uint32_t tile_pos, uint32_t k, uint8_t* codes) {
+__device__ __forceinline__ bool load_tile_codes(const packed_reads& pr, uint64_t rstart, uint32_t rlen,
+                                                uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_stage& ts) {
   const int cap = k > 18 ? (int)k : 18;        // run length is only needed up to max(k, 18)
   const int LB  = cap - (int)k;
   const int total = LB + kTile + (int)k - 1;
+  // bases [gA, gB) of the batch are inside the read and inside the window
+  const int64_t p0 = (int64_t)tile_pos - LB;
+  const uint64_t gA = rstart + (uint64_t)(p0 > 0 ? p0 : 0);
+  const int64_t pend = p0 + total;
+  const uint64_t gB = rstart + (uint64_t)(pend < (int64_t)rlen ? pend : (int64_t)rlen);
+  const uint64_t wa = (gA >> 5) & ~1ULL, ma = (gA >> 6) & ~1ULL;                       // 16-byte aligned starts
+  const uint32_t nw = (uint32_t)((((gB + 31) >> 5) - wa + 1) & ~1ULL);                 // even word counts
+  const uint32_t nm = (uint32_t)((((gB + 63) >> 6) - ma + 1) & ~1ULL);
+  if(pr.tma) {
+    if(threadIdx.x == 0) {
+      mbar_init(&ts.bar, 1);
+      mbar_expect_tx(&ts.bar, (nw + nm) * 8u);
+      bulk_copy_g2s(ts.cw, pr.codes + wa, nw * 8u, &ts.bar);
+      bulk_copy_g2s(ts.mw, pr.nmask + ma, nm * 8u, &ts.bar);
+    }
+    __syncthreads();                             // the barrier's initialisation is visible to the waiters
+    mbar_wait(&ts.bar, 0);
+  } else {
+    for(uint32_t i = threadIdx.x; i < nw; i += kSeedThreads) ts.cw[i] = __ldg(pr.codes + wa + i);
+    for(uint32_t i = threadIdx.x; i < nm; i += kSeedThreads) ts.mw[i] = __ldg(pr.nmask + ma + i);
+    __syncthreads();
+  }
   bool broke = false;
   for(int i = threadIdx.x; i < total; i += kSeedThreads) {
-    const int64_t p = (int64_t)tile_pos - LB + i;
-    const uint8_t c = (p >= 0 && p < (int64_t)rlen) ? base_code(__ldcs(bases + rstart + p)) : (uint8_t)4;
+    const int64_t p = p0 + i;
+    uint8_t c = 4;
+    if(p >= 0 && p < (int64_t)rlen) {
+      const uint64_t g = rstart + (uint64_t)p;
+      const uint64_t cw = ts.cw[(g >> 5) - wa], mw = ts.mw[(g >> 6) - ma];
+      c = (mw >> (g & 63)) & 1 ? (uint8_t)4 : (uint8_t)((cw >> (2 * (g & 31))) & 3);
+    }
     codes[i] = c;
     broke |= c == 4;
   }
@@ -165,24 +207,45 @@ __device__ __forceinline__ void tile_kmers_from_codes(uint32_t k, const uint8_t*
   }
 }
 
-__device__ __forceinline__ void enumerate_tile(const char* __restrict__ bases, uint64_t rstart, uint32_t rlen,
-                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_kmers& t, bool every_mer = false) {
-  (void)load_tile_codes(bases, rstart, rlen, tile_pos, k, codes);
+__device__ __forceinline__ void enumerate_tile(const packed_reads& bases, uint64_t rstart, uint32_t rlen,
+                                               uint32_t tile_pos, uint32_t k, uint8_t* codes, tile_stage& ts, tile_kmers& t, bool every_mer = false) {
+  (void)load_tile_codes(bases, rstart, rlen, tile_pos, k, codes, ts);
   tile_kmers_from_codes(k, codes, t, every_mer);
 }
 
+// ASCII bases on the device -> the packed form (the entry points that take characters); one thread
+// per 64 bases: one mask word and two code words.  jf_aligner.hpp:41-52 treats every character
+// outside ACGT/acgt as a break.
+__global__ void __launch_bounds__(256) pack_reads_kernel(const char* __restrict__ bases, uint64_t n, uint64_t* __restrict__ codes,
+                                                          uint64_t* __restrict__ nmask, uint64_t nmask_words) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(w >= nmask_words) return;
+  uint64_t c0 = 0, c1 = 0, m = 0;
+  const uint64_t g0 = w * 64;
+  for(int j = 0; j < 64; ++j) {
+    const uint64_t g = g0 + j;
+    const uint8_t c = g < n ? base_code(bases[g]) : (uint8_t)0;
+    const uint64_t two = c & 3;
+    if(j < 32) c0 |= two << (2 * j); else c1 |= two << (2 * (j - 32));
+    m |= (uint64_t)(c == 4) << j;
+  }
+  codes[2 * w] = c0; codes[2 * w + 1] = c1;
+  nmask[w] = m;
+}
+
 // pass 0 (only when k <= 17): number of flag-toggling k-mers per tile
-__global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ read_start,
+__global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(packed_reads bases, const uint64_t* __restrict__ read_start,
                                                                    const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                    uint32_t k, uint32_t* __restrict__ tile_cand) {
   __shared__ uint8_t codes[kTile + 64];
+  __shared__ tile_stage ts;
   __shared__ uint32_t total;
   if(threadIdx.x == 0) total = 0;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   // A k-mer toggles the flag only inside the first 17 bases of an N-free run (run <= 17): a tile whose
   // window holds no run start -- almost every tile -- has none, and skips the k-mer arithmetic.
-  const bool broke = load_tile_codes(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes);
+  const bool broke = load_tile_codes(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes, ts);
   if(!__syncthreads_or(broke)) { if(threadIdx.x == 0) tile_cand[blockIdx.x] = 0; return; }
   tile_kmers t;
   tile_kmers_from_codes(k, codes, t);
@@ -211,7 +274,7 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // kHint: the table loads carry the L2 evict_last hint (index.cuh).  kSlots: lookups start from the
 // slot table (index_view::slots) instead of the counts table.
 template<bool kMulti, bool kHint, bool kSlots>
-__global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, packed_reads bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
@@ -221,6 +284,7 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
                                                                     unsigned long long* __restrict__ n_lists,
                                                                     unsigned long long* __restrict__ n_buckets) {
   __shared__ uint8_t  codes[kTile + 64];
+  __shared__ tile_stage ts;
   __shared__ uint64_t sw[8];
   __shared__ uint32_t looked, scanned, listed, buckets;
   const uint32_t k = iv.k;
@@ -230,7 +294,7 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
   const uint32_t tpos = tile_pos[blockIdx.x];
   if(threadIdx.x == 0) { looked = 0; scanned = 0; listed = 0; buckets = 0; }
   tile_kmers t;
-  enumerate_tile(bases, rs, rlen, tpos, k, codes, t);
+  enumerate_tile(bases, rs, rlen, tpos, k, codes, ts, t);
 
   bool keep[4];
 #pragma unroll
@@ -555,19 +619,20 @@ __global__ void __launch_bounds__(256) fine_windows_kernel(uint64_t S, survivors
 }
 
 // lookups of every kk-mer of the reads: rec = {index(m), nb(m), index(rm), nb(rm)}, size = nb(m) + nb(rm)
-__global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, bool first_part, uint32_t kk, const char* __restrict__ bases,
+__global__ void __launch_bounds__(kSeedThreads) fine_seed_kernel(index_view iv, bool first_part, uint32_t kk, packed_reads bases,
                                                                   const uint64_t* __restrict__ read_start,
                                                                   const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                   const uint64_t* __restrict__ table_off,
                                                                   uint4* __restrict__ rec, uint32_t* __restrict__ size) {
   __shared__ uint8_t codes[kTile + 64];
+  __shared__ tile_stage ts;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
   const bool has_rows = table_off[r + 1] != table_off[r];        // a read without coarse rows has no window
   tile_kmers t;
-  enumerate_tile(bases, rs, rlen, tpos, kk, codes, t, true);
+  enumerate_tile(bases, rs, rlen, tpos, kk, codes, ts, t, true);
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
 #pragma unroll
   for(int j = 0; j < 4; ++j) {
@@ -948,17 +1013,47 @@ __global__ void __launch_bounds__(256) row_keys_kernel(uint64_t S, const uint32_
   k5[i] = iter[me];
 }
 template<bool kBig>
-__global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
-                                                         const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
-                                                         uint32_t warp_max, uint32_t* __restrict__ order) {
-  uint32_t r, first, step;
-  if(kBig) { r = blockIdx.x; first = threadIdx.x; step = blockDim.x; }
-  else     { r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; first = threadIdx.x & 31; step = 32; }
+__global__ void __launch_bounds__(kBig ? 512 : 128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
+                                                                     const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
+                                                                     uint32_t warp_max, uint32_t* __restrict__ order) {
+  if(kBig) {
+    // a read with many rows: 512 rows at a time are ranked against all rows of the read, which pass through
+    // shared memory in tiles of 512 (every thread reads the same tile entry: one broadcast per comparison)
+    __shared__ int4     s4[512];
+    __shared__ uint32_t s5[512];
+    const uint32_t r = blockIdx.x;
+    if(r >= nreads) return;
+    const uint64_t b = read_coords[r];
+    const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
+    if(c <= warp_max) return;
+    for(uint32_t e0 = 0; e0 < c; e0 += 512) {
+      const uint32_t e = e0 + threadIdx.x;
+      const bool mine = e < c;
+      const int4 a4 = mine ? k4[b + e] : make_int4(0, 0, 0, 0);
+      const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, mine ? k5[b + e] : 0u };
+      uint32_t rank = 0;
+      for(uint32_t f0 = 0; f0 < c; f0 += 512) {
+        __syncthreads();
+        if(f0 + threadIdx.x < c) { s4[threadIdx.x] = k4[b + f0 + threadIdx.x]; s5[threadIdx.x] = k5[b + f0 + threadIdx.x]; }
+        __syncthreads();
+        const uint32_t m = min(512u, c - f0);
+#pragma unroll 4
+        for(uint32_t f = 0; f < m; ++f) {
+          const int4 o4 = s4[f];
+          const row_key o = { o4.x, o4.y, (uint32_t)o4.z, (uint32_t)o4.w, s5[f] };
+          rank += row_key_less(o, a);
+        }
+      }
+      if(mine) order[b + rank] = slot[b + e];
+    }
+    return;
+  }
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, first = threadIdx.x & 31;
   if(r >= nreads) return;
   const uint64_t b = read_coords[r];
   const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
-  if(kBig ? c <= warp_max : c > warp_max) return;
-  for(uint32_t e = first; e < c; e += step) {
+  if(c > warp_max) return;
+  for(uint32_t e = first; e < c; e += 32) {
     const int4 a4 = k4[b + e];
     const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, k5[b + e] };
     uint32_t rank = 0;
@@ -1034,7 +1129,7 @@ static void l2_window(mr_context* ctx, cudaStream_t st, const mr_index* part, bo
 }
 
 // ================================================================================================
-static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
+static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, const packed_reads& d_bases,
                             const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads,
                             phase_timer& timer, mr_result** out) {
   cudaStream_t st = ctx->stream;
@@ -1393,7 +1488,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                                                 ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(), ws.order.as<uint32_t>());
     MR_LAUNCHED(ctx);
     if(max_rows > big_rows_threshold()) {                            // some read has that many rows
-      rank_rows_kernel<true><<<nreads, 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+      rank_rows_kernel<true><<<nreads, 512, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
                                                      ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(),
                                                      ws.order.as<uint32_t>());
       MR_LAUNCHED(ctx);
@@ -1461,11 +1556,9 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   return MR_OK;
 }
 
-extern "C" {
-
-int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
-                          const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
-  if(!ctx) return MR_EINVAL;
+// checks shared by every alignment entry point, then the batch itself on packed device arrays
+static int align_checked(mr_context* ctx, mr_index* idx, const mr_params* p, const packed_reads& d_reads,
+                         const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
   if(!idx || !p || !out || !h_read_start || !d_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
   // an index is read-only once built: any context of its device may align against it
   if(idx->ctx->device != ctx->device) return ctx->fail(MR_EINVAL, "mr_align_batch: index lives on another device");
@@ -1479,10 +1572,9 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
     return ctx->fail(MR_EINVAL, "mr_align_batch: the overlap graph needs unitig lengths (-l/-u) and -k");
   if(p->run_graph && !idx->unitig_ids_ok)
     return ctx->fail(MR_EINVAL, "mr_align_batch: a super-read name refers to a k-unitig that the unitig table (-l/-u) does not have");
-  MR_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->timers.clear();
   phase_timer timer(ctx);
-  const int rc = align_batch_impl(ctx, idx, p, d_bases, d_read_start, h_read_start, nreads, timer, out);
+  const int rc = align_batch_impl(ctx, idx, p, d_reads, d_read_start, h_read_start, nreads, timer, out);
   cudaStreamSynchronize(ctx->stream);
   if(rc == MR_OK) timer.collect();
   else {
@@ -1492,6 +1584,83 @@ int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, co
     cudaGetLastError();
   }
   return rc;
+}
+
+static bool g_no_tma() { static const bool v = getenv("MR_NO_TMA") && atoi(getenv("MR_NO_TMA")) != 0; return v; }
+static packed_reads make_packed(const uint64_t* codes, const uint64_t* nmask) {
+  packed_reads r;
+  r.codes = codes; r.nmask = nmask;
+  r.tma = !g_no_tma() && (((uintptr_t)codes | (uintptr_t)nmask) & 15) == 0;
+  return r;
+}
+
+// characters already on the device -> the context's packed buffers
+static int pack_on_device(mr_context* ctx, const char* d_bases, uint64_t T, packed_reads& out) {
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  const uint64_t mwords = mr_packed_mask_words(T), cwords = mr_packed_code_words(T);
+  MR_TRY(ws.codes.ensure(ctx, cwords * 8)); MR_TRY(ws.nmask.ensure(ctx, mwords * 8));
+  // the kernel writes whole 64-base groups; the padding words behind them stay whatever they are (never decoded)
+  const uint64_t groups = (T + 63) / 64;
+  if(groups) {
+    pack_reads_kernel<<<div_up(groups, 256), 256, 0, ctx->stream>>>(d_bases, T, ws.codes.as<uint64_t>(), ws.nmask.as<uint64_t>(), groups);
+    MR_LAUNCHED(ctx);
+  }
+  out = make_packed(ws.codes.as<uint64_t>(), ws.nmask.as<uint64_t>());
+  return MR_OK;
+}
+
+extern "C" {
+
+uint64_t mr_packed_code_words(uint64_t nbases) { return (nbases + 31) / 32 + 6; }
+uint64_t mr_packed_mask_words(uint64_t nbases) { return (nbases + 63) / 64 + 6; }
+
+// host packer: 32 characters -> one code word, 64 -> one mask word (same mapping as base_code on the device)
+int mr_pack_reads(const char* bases, uint64_t nbases, uint64_t* codes, uint64_t* nmask) {
+  if((!bases && nbases) || !codes || !nmask) return MR_EINVAL;
+  static const struct lut_t {
+    uint8_t v[256];
+    lut_t() { for(int i = 0; i < 256; ++i) v[i] = 4; v['a'] = v['A'] = 0; v['c'] = v['C'] = 1; v['g'] = v['G'] = 2; v['t'] = v['T'] = 3; }
+  } lut;
+  const uint64_t cwords = mr_packed_code_words(nbases), mwords = mr_packed_mask_words(nbases);
+  uint64_t g = 0;
+  for(uint64_t w = 0; w < mwords; ++w) {
+    uint64_t c0 = 0, c1 = 0, m = 0;
+    if(g + 64 <= nbases) {
+      const unsigned char* s = (const unsigned char*)bases + g;
+      for(int j = 0; j < 32; ++j) { const uint64_t c = lut.v[s[j]]; c0 |= (c & 3) << (2 * j); m |= (c >> 2) << j; }
+      for(int j = 0; j < 32; ++j) { const uint64_t c = lut.v[s[32 + j]]; c1 |= (c & 3) << (2 * j); m |= (c >> 2) << (32 + j); }
+      g += 64;
+    } else {
+      for(int j = 0; j < 64 && g < nbases; ++j, ++g) {
+        const uint64_t c = lut.v[(unsigned char)bases[g]];
+        if(j < 32) c0 |= (c & 3) << (2 * j); else c1 |= (c & 3) << (2 * (j - 32));
+        m |= (c >> 2) << j;
+      }
+    }
+    if(2 * w < cwords) codes[2 * w] = c0;
+    if(2 * w + 1 < cwords) codes[2 * w + 1] = c1;
+    nmask[w] = m;
+  }
+  return MR_OK;
+}
+
+int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
+                          const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!d_bases || !h_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  packed_reads pr;
+  MR_TRY(pack_on_device(ctx, d_bases, h_read_start[nreads], pr));
+  return align_checked(ctx, idx, p, pr, d_read_start, h_read_start, nreads, out);
+}
+
+int mr_align_batch_device_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* d_codes, const uint64_t* d_nmask,
+                                 const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!d_codes || !d_nmask) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  return align_checked(ctx, idx, p, make_packed(d_codes, d_nmask), d_read_start, h_read_start, nreads, out);
 }
 
 int mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p, const char* bases, const uint64_t* read_start,
@@ -1507,6 +1676,23 @@ int mr_align_batch(mr_context* ctx, mr_index* idx, const mr_params* p, const cha
   MR_CUDA(ctx, cudaMemcpyAsync(ws.bases.p, bases, T, cudaMemcpyHostToDevice, ctx->stream));
   MR_CUDA(ctx, cudaMemcpyAsync(ws.read_start.p, read_start, ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   return mr_align_batch_device(ctx, idx, p, ws.bases.as<char>(), ws.read_start.as<uint64_t>(), read_start, nreads, out);
+}
+
+int mr_align_batch_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* codes, const uint64_t* nmask,
+                          const uint64_t* read_start, uint32_t nreads, mr_result** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!codes || !nmask || !read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
+  MR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if(!ctx->ws) ctx->ws = new mr_workspace;
+  mr_workspace& ws = *ctx->ws;
+  const uint64_t T = read_start[nreads];
+  const uint64_t cwords = mr_packed_code_words(T), mwords = mr_packed_mask_words(T);
+  MR_TRY(ws.codes.ensure(ctx, cwords * 8)); MR_TRY(ws.nmask.ensure(ctx, mwords * 8));
+  MR_TRY(ws.read_start.ensure(ctx, ((size_t)nreads + 1) * 8));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.codes.p, codes, cwords * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.nmask.p, nmask, mwords * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MR_CUDA(ctx, cudaMemcpyAsync(ws.read_start.p, read_start, ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return align_checked(ctx, idx, p, make_packed(ws.codes.as<uint64_t>(), ws.nmask.as<uint64_t>()), ws.read_start.as<uint64_t>(), read_start, nreads, out);
 }
 
 // Overlap graph of coords rows that come from the caller (host memory) instead of from the aligner:
@@ -1594,9 +1780,8 @@ int mr_graph_batch(mr_context* ctx, const mr_params* p, const mr_result_view* ro
 // Staged batches: the host -> device copy of batch i + 1 runs on its own stream while the kernels
 // of batch i run.  mr_stage_batch may be called from another host thread than the one that aligns
 // (a pageable source makes the copy call block; a pinned one, mr_host_pin, returns at once).
-int mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_start, uint32_t nreads, mr_staged** out) {
-  if(!ctx) return MR_EINVAL;
-  if(!bases || !read_start || !out) return ctx->fail(MR_EINVAL, "mr_stage_batch: null argument");
+static int stage_impl(mr_context* ctx, const char* bases, const uint64_t* codes, const uint64_t* nmask, const uint64_t* read_start,
+                      uint32_t nreads, mr_staged** out) {
   *out = nullptr;
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   if(!ctx->ws) ctx->ws = new mr_workspace;
@@ -1612,15 +1797,36 @@ int mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_star
     MR_CUDA(ctx, cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
   }
   const uint64_t T = read_start[nreads];
-  MR_TRY(s->bases.ensure(ctx, T + 64));
   MR_TRY(s->read_start.ensure(ctx, ((size_t)nreads + 1) * 8));
   s->h_read_start.assign(read_start, read_start + nreads + 1);
   s->nreads = nreads;
-  MR_CUDA(ctx, cudaMemcpyAsync(s->bases.p, bases, T, cudaMemcpyHostToDevice, ctx->copy_stream));
+  s->packed = bases == nullptr;
+  if(bases) {
+    MR_TRY(s->bases.ensure(ctx, T + 64));
+    MR_CUDA(ctx, cudaMemcpyAsync(s->bases.p, bases, T, cudaMemcpyHostToDevice, ctx->copy_stream));
+  } else {
+    const uint64_t cwords = mr_packed_code_words(T), mwords = mr_packed_mask_words(T);
+    MR_TRY(s->bases.ensure(ctx, (cwords + (cwords & 1) + mwords) * 8));          // mask words start 16-byte aligned
+    MR_CUDA(ctx, cudaMemcpyAsync(s->bases.p, codes, cwords * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MR_CUDA(ctx, cudaMemcpyAsync(s->bases.as<uint64_t>() + cwords + (cwords & 1), nmask, mwords * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+  }
   MR_CUDA(ctx, cudaMemcpyAsync(s->read_start.p, s->h_read_start.data(), ((size_t)nreads + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
   MR_CUDA(ctx, cudaEventRecord(s->ready, ctx->copy_stream));
   *out = s.release();
   return MR_OK;
+}
+
+int mr_stage_batch(mr_context* ctx, const char* bases, const uint64_t* read_start, uint32_t nreads, mr_staged** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!bases || !read_start || !out) return ctx->fail(MR_EINVAL, "mr_stage_batch: null argument");
+  return stage_impl(ctx, bases, nullptr, nullptr, read_start, nreads, out);
+}
+
+int mr_stage_batch_packed(mr_context* ctx, const uint64_t* codes, const uint64_t* nmask, const uint64_t* read_start, uint32_t nreads,
+                          mr_staged** out) {
+  if(!ctx) return MR_EINVAL;
+  if(!codes || !nmask || !read_start || !out) return ctx->fail(MR_EINVAL, "mr_stage_batch: null argument");
+  return stage_impl(ctx, nullptr, codes, nmask, read_start, nreads, out);
 }
 
 void mr_staged_free(mr_staged* s) {
@@ -1640,7 +1846,12 @@ int mr_align_staged(mr_context* ctx, mr_index* idx, const mr_params* p, mr_stage
   if(!s || s->ctx != ctx) return ctx->fail(MR_EINVAL, "mr_align_staged: the batch was staged on another context");
   MR_CUDA(ctx, cudaSetDevice(ctx->device));
   MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ready, 0));
-  const int rc = mr_align_batch_device(ctx, idx, p, s->bases.as<char>(), s->read_start.as<uint64_t>(), s->h_read_start.data(), s->nreads, out);
+  int rc;
+  if(s->packed) {
+    const uint64_t cwords = mr_packed_code_words(s->h_read_start[s->nreads]);
+    rc = mr_align_batch_device_packed(ctx, idx, p, s->bases.as<uint64_t>(), s->bases.as<uint64_t>() + cwords + (cwords & 1),
+                                      s->read_start.as<uint64_t>(), s->h_read_start.data(), s->nreads, out);
+  } else rc = mr_align_batch_device(ctx, idx, p, s->bases.as<char>(), s->read_start.as<uint64_t>(), s->h_read_start.data(), s->nreads, out);
   mr_staged_free(s);
   return rc;
 }

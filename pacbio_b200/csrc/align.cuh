@@ -11,6 +11,13 @@ constexpr int      kTile        = 1024;           // read positions per CTA in t
 constexpr int      kSeedThreads = 256;
 constexpr uint32_t kNone        = 0xffffffffu;
 
+// a batch of reads on the device, 2-bit packed + non-ACGT mask (align.cu, load_tile_codes)
+struct packed_reads {
+  const uint64_t* __restrict__ codes;
+  const uint64_t* __restrict__ nmask;
+  int tma;                            // both arrays are 16-byte aligned: tiles are staged with bulk copies
+};
+
 // Final per-coords arrays on the device (structure of arrays, rows sorted per read).
 struct coords_soa {
   int32_t  *rs, *re, *qs, *qe, *nb_mers;
@@ -31,7 +38,8 @@ struct fine_buffers {
 // a batch of reads already copied (or on its way) to the device, see mr_stage_batch
 struct mr_staged {
   mr_context* ctx = nullptr;
-  dev_buf bases, read_start;
+  dev_buf bases, read_start;          // bases: characters, or with `packed` the code words followed by the mask words
+  bool packed = false;
   std::vector<uint64_t> h_read_start;
   uint32_t nreads = 0;
   cudaEvent_t ready = nullptr;
@@ -40,7 +48,7 @@ struct mr_staged {
 
 // Scratch that lives in the context and is reused from batch to batch.
 struct mr_workspace {
-  dev_buf bases, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
+  dev_buf bases, codes, nmask, read_start, read_len, tile_read, tile_pos, tile_first, tile_cand, tile_tbase;
   dev_buf size, rec, hit_off, thr, counters;
   fine_buffers fine;
   dev_buf path_ids, path_off, path_ulen;               // mr_graph_batch: the caller's unitig paths

@@ -226,13 +226,25 @@ __global__ void __launch_bounds__(256) graph_big_prepare_kernel(graph_args A) {
     A.start_node[row] = 1; A.end_node[row] = 1;
   }
   __syncthreads();
-  for(int i = tid; i < n; i += 256) {
-    const double s = imp_s[i], e = imp_e[i];
+  // node order by counting: 256 nodes at a time against all nodes, which pass through shared memory in tiles
+  __shared__ double2 tile[256];
+  for(int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + tid;
+    const bool mine = i < n;
+    const double s = mine ? imp_s[i] : 0.0, e = mine ? imp_e[i] : 0.0;
     int rk = 0;
-    for(int j = 0; j < n; ++j) {
-      const double sj = imp_s[j], ej = imp_e[j];
-      rk += (sj < s || (sj == s && ej < e)) || (sj == s && ej == e && j < i);
+    for(int j0 = 0; j0 < n; j0 += 256) {
+      __syncthreads();
+      if(j0 + tid < n) tile[tid] = make_double2(imp_s[j0 + tid], imp_e[j0 + tid]);
+      __syncthreads();
+      const int m = min(256, n - j0);
+#pragma unroll 4
+      for(int j = 0; j < m; ++j) {
+        const double2 o = tile[j];
+        rk += (o.x < s || (o.x == s && o.y < e)) || (o.x == s && o.y == e && j0 + j < i);
+      }
     }
+    if(!mine) continue;
     const uint64_t row = b + i;
     order[rk] = i;
     ord_s[rk] = s; ord_e[rk] = e; ord_err[rk] = A.c.avg_err[row];

@@ -54,8 +54,15 @@ struct read_batch {
   std::string              bases;        // concatenated
   std::vector<uint64_t>    start;        // nreads + 1
   std::vector<std::string> name;         // header up to the first white space
+  // what travels to the GPU: 2 bits per base + a mask of the non-ACGT characters (mr_pack_reads), 0.375 bytes per base
+  std::vector<uint64_t>    codes, nmask;
   uint32_t nreads() const { return (uint32_t)name.size(); }
-  void clear() { bases.clear(); start.assign(1, 0); name.clear(); }
+  void clear() { bases.clear(); start.assign(1, 0); name.clear(); codes.clear(); nmask.clear(); }
+  void pack() {
+    codes.resize(mr_packed_code_words(bases.size())); nmask.resize(mr_packed_mask_words(bases.size()));
+    mr_pack_reads(bases.data(), bases.size(), codes.data(), nmask.data());
+  }
+  bool packed() const { return !nmask.empty(); }
 };
 class read_stream {
   std::vector<std::string> paths_;

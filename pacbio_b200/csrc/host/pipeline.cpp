@@ -149,7 +149,8 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       while(to_align.pop(j)) {
         staged_job sj;
         sj.staged = nullptr;
-        if(stage_batches() && !failed && mr_stage_batch(ds.ctx[g], j.batch->bases.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
+        j.batch->pack();                        // 2 bits per base + non-ACGT mask: what crosses PCIe
+        if(stage_batches() && !failed && mr_stage_batch_packed(ds.ctx[g], j.batch->codes.data(), j.batch->nmask.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
         sj.j = std::move(j);
         staged[g]->push(std::move(sj));
@@ -171,7 +172,10 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           part pt;
           int rc;
           if(sj.staged) { rc = mr_align_staged(ds.ctx[g], ds.idx[g], &params, sj.staged, &pt.result); sj.staged = nullptr; }
-          else rc = mr_align_batch(ds.ctx[g], ds.idx[g], &params, b->bases.data(), b->start.data(), b->nreads(), &pt.result);
+          else {
+            if(!b->packed()) b->pack();         // a half of a batch that had to be split
+            rc = mr_align_batch_packed(ds.ctx[g], ds.idx[g], &params, b->codes.data(), b->nmask.data(), b->start.data(), b->nreads(), &pt.result);
+          }
           if(rc == MR_OK) { pt.batch = std::move(b); j.parts.push_back(std::move(pt)); continue; }
           if((rc == MR_ELIMIT || rc == MR_ENOMEM) && b->nreads() > 1) {
             const uint32_t half = b->nreads() / 2;

@@ -49,7 +49,7 @@ void* mrh_tool_create(const char* sr_fasta, const char* unitigs_path, int unitig
 void mrh_tool_destroy(void* p) {
   tool* t = (tool*)p;
   if(!t) return;
-  for(auto& b : t->batches) mr_host_unpin(t->DS.ctx[0], b->bases.data());
+  for(auto& b : t->batches) { mr_host_unpin(t->DS.ctx[0], b->codes.data()); mr_host_unpin(t->DS.ctx[0], b->nmask.data()); }
   delete t;
 }
 
@@ -75,7 +75,9 @@ int64_t mrh_tool_load_reads(void* p, const char* path, uint64_t batch_bases, uin
       if(!rs.next_batch(*b, batch_bases, (uint32_t)std::min<uint64_t>(left, 1u << 20))) break;
       t->total_bases += b->bases.size();
       t->total_reads += b->nreads();
-      mr_host_pin(t->DS.ctx[0], b->bases.data(), b->bases.size());
+      b->pack();                                    // the form the batch travels in (parsing + packing happen once, here)
+      mr_host_pin(t->DS.ctx[0], b->codes.data(), b->codes.size() * 8);
+      mr_host_pin(t->DS.ctx[0], b->nmask.data(), b->nmask.size() * 8);
       t->batches.push_back(std::move(b));
     }
     return (int64_t)t->total_bases;
@@ -86,6 +88,12 @@ uint64_t mrh_tool_nreads(void* p) { return ((tool*)p)->total_reads; }
 // batch accessors, so a caller can stage the same batches on the device itself
 const char* mrh_tool_batch_bases(void* p, uint64_t i, uint64_t* nbytes) {
   tool* t = (tool*)p; *nbytes = t->batches[i]->bases.size(); return t->batches[i]->bases.data();
+}
+const uint64_t* mrh_tool_batch_codes(void* p, uint64_t i, uint64_t* nwords) {
+  tool* t = (tool*)p; *nwords = t->batches[i]->codes.size(); return t->batches[i]->codes.data();
+}
+const uint64_t* mrh_tool_batch_nmask(void* p, uint64_t i, uint64_t* nwords) {
+  tool* t = (tool*)p; *nwords = t->batches[i]->nmask.size(); return t->batches[i]->nmask.data();
 }
 const uint64_t* mrh_tool_batch_starts(void* p, uint64_t i, uint32_t* nreads) {
   tool* t = (tool*)p; *nreads = t->batches[i]->nreads(); return t->batches[i]->start.data();
@@ -142,7 +150,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
           t->last_text_bytes += text.size();
         }
       } catch(std::exception& e) { error = e.what(); }
-      t->last_h2d_bytes += b->bases.size() + (b->nreads() + 1) * 8ULL;
+      t->last_h2d_bytes += (b->codes.size() + b->nmask.size() + b->nreads() + 1) * 8ULL;
       uint64_t info = 0;
       for(uint64_t c = 0; c < v.ncoords; ++c) info += v.info_len[c];
       t->last_d2h_bytes += (v.nreads + 1) * 8ULL + v.ncoords * (5 * 4 + 6 * 4 + 2 + 3 * 8 + 8 + 4 + 2 + 5 * 4) + info * 8;
@@ -173,7 +181,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
         }
         mrh::read_batch* b = t->batches[first + i].get();
         mr_staged* st = nullptr;
-        if(mrh::stage_batches() && mr_stage_batch(t->DS.ctx[s], b->bases.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
+        if(mrh::stage_batches() && mr_stage_batch_packed(t->DS.ctx[s], b->codes.data(), b->nmask.data(), b->start.data(), b->nreads(), &st) != MR_OK) {
           std::lock_guard<std::mutex> l(m);
           if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]);
           stop = true; cv.notify_all();
@@ -190,7 +198,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
         const auto a0 = std::chrono::steady_clock::now();
         mrh::read_batch* b = t->batches[first + it.i].get();
         const int rc = it.s ? mr_align_staged(t->DS.ctx[s], t->DS.idx[s], &t->P, it.s, &r)
-                            : mr_align_batch(t->DS.ctx[s], t->DS.idx[s], &t->P, b->bases.data(), b->start.data(), b->nreads(), &r);
+                            : mr_align_batch_packed(t->DS.ctx[s], t->DS.idx[s], &t->P, b->codes.data(), b->nmask.data(), b->start.data(), b->nreads(), &r);
         busy[s] += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
         std::lock_guard<std::mutex> l(m);
         if(rc != MR_OK) { if(align_error.empty()) align_error = mr_last_error(t->DS.ctx[s]); stop = true; cv.notify_all(); continue; }

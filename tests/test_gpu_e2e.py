@@ -309,6 +309,16 @@ def test_index_cache_is_used_and_checked(tmpdir_session, tmp_path):
     assert "loaded from" in go(b, other, env)
 
 
+def test_tiles_staged_without_bulk_copies_give_the_same_records(tmpdir_session, tmp_path):
+    """MR_NO_TMA=1: the read tiles reach shared memory through ordinary loads instead of the TMA engine's bulk copies."""
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_tma"), 300000, coverage=4, read_len=4000, seed=19, repeat_frac=0.1)
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-r", info["sr"], "-p", info["reads"]]
+    a, b = str(tmp_path / "tma.txt"), str(tmp_path / "plain.txt")
+    run(cmd + ["-o", a])
+    run(cmd + ["-o", b], env=dict(os.environ, MR_NO_TMA="1"))
+    assert open(a).read() == open(b).read() and len(open(a).read()) > 10000
+
+
 def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
     info = gen_synth(os.path.join(tmpdir_session, "e2e_fq"), 100000, coverage=3, read_len=3000, seed=5)
     from oracle_lib import read_fasta

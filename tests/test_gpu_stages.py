@@ -239,6 +239,19 @@ def test_align_stages_match_oracle(case, ctx, port, forward):
     port.aligner_destroy(ap)
 
 
+def test_packed_entry_point_gives_the_same_rows(case, ctx):
+    """mr_align_batch (characters, packed on the device) == mr_align_batch_packed (packed on the host by mr_pack_reads)."""
+    import pacbio_b200 as pb
+    c = case["cfg"]
+    reads = pb.Reads(case["info"]["reads"])
+    p = pb.default_params(unitigs_k=c["uk"], run_graph=1)
+    a, b = ctx.align(case["idx"], reads, p), ctx.align_packed(case["idx"], reads, p)
+    assert a.ncoords == b.ncoords > 0 and np.array_equal(a.read_coords, b.read_coords)
+    for f in ("rs", "re", "qs", "qe", "nb_mers", "sr", "use_bwd", "lpath", "lstart", "lprev", "component", "kmers_info"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.stretch.view(np.uint64), b.stretch.view(np.uint64))
+
+
 def test_staged_batches_give_the_same_rows(case, ctx):
     """mr_stage_batch + mr_align_staged (copy of the next batch under the kernels of the current one) == mr_align_batch."""
     import pacbio_b200 as pb

@@ -3,6 +3,8 @@ declares, the tools reject bad command lines like the reference's yaggo parsers 
 and the product fails loudly -- no CPU fallback -- when there is no CUDA device."""
 import ctypes
 import os
+
+import numpy as np
 import re
 import subprocess
 
@@ -219,3 +221,25 @@ def test_fixed_point_formatter_prints_what_printf_prints():
     H.mrh_selftest_fixed_format.restype = C.c_uint64
     H.mrh_selftest_fixed_format.argtypes = [C.c_uint64, C.c_uint64]
     assert H.mrh_selftest_fixed_format(2_000_000, 7) == 0
+
+
+def test_pack_reads_layout():
+    """mr_pack_reads: base g at bits 2 (g % 32) of code word g / 32 (compact_dna.hpp:102-136 layout, A0 C1 G2 T3),
+    bit g % 64 of mask word g / 64 set for every character outside ACGTacgt (they break k-mers, jf_aligner.hpp:41-52)."""
+    import pacbio_b200.api as api
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 31, 32, 33, 63, 64, 65, 1000, 4097):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtNnRY-", dtype=np.uint8), size=n)
+        codes, nmask = api.pack_reads(seq)
+        assert len(codes) >= (n + 31) // 32 + 4 and len(nmask) >= (n + 63) // 64 + 4
+        want = {ord("A"): 0, ord("a"): 0, ord("C"): 1, ord("c"): 1, ord("G"): 2, ord("g"): 2, ord("T"): 3, ord("t"): 3}
+        for g in range(n):
+            bad = int(nmask[g // 64] >> np.uint64(g % 64)) & 1
+            code = int(codes[g // 32] >> np.uint64(2 * (g % 32))) & 3
+            if int(seq[g]) in want:
+                assert bad == 0 and code == want[int(seq[g])]
+            else:
+                assert bad == 1 and code == 0
+        # nothing set past the last base
+        for g in range(n, min(len(nmask) * 64, len(codes) * 32, n + 200)):
+            assert (int(nmask[g // 64]) >> (g % 64)) & 1 == 0 and (int(codes[g // 32]) >> (2 * (g % 32))) & 3 == 0

@@ -145,6 +145,17 @@ def test_merge_coords(tmp_path):
     if os.path.exists(REF_MRG):                     # the compiled reference, when it is there
         want = subprocess.run([REF_MRG, a, b, a], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
         assert out == want
+    # gzip-compressed inputs (the reference reads its inputs through zstr, merge_coords.cc:38-43), mixed with plain ones
+    import gzip
+    bz = str(tmp_path / "b.txt.gz")
+    with gzip.open(bz, "wb") as f:
+        f.write(open(b, "rb").read())
+    az = str(tmp_path / "a.coords.gz")
+    with gzip.open(az, "wb") as f:
+        f.write(open(a, "rb").read())
+    assert subprocess.run([MRG, az, bz, a], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines() == out
+    if os.path.exists(REF_MRG):
+        assert subprocess.run([REF_MRG, az, bz, a], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines() == out
     # one input: copied; none: empty; -o writes the file
     assert subprocess.run([MRG, a], stdout=subprocess.PIPE, check=True).stdout == open(a, "rb").read()
     assert subprocess.run([MRG], stdout=subprocess.PIPE, check=True).stdout == b""

@@ -271,9 +271,9 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // kMulti (index of several parts, index.cuh): one launch per part, each with its own rec array;
 // size[g] accumulates the per-part list sizes over the launches (part_flags bit 0: first part,
 // bit 1: last part) and the max-count filter is applied to the sum by the last one.
-// kHint: the table loads carry the L2 evict_last hint (index.cuh).  kSlots: lookups start from the
-// slot table (index_view::slots) instead of the counts table.
-template<bool kMulti, bool kHint, bool kSlots>
+// kHint: the table loads carry the L2 evict_last hint (index.cuh).  kNib: bucket bounds come from the
+// nibble records (index_view::nib) instead of the counts table.
+template<bool kMulti, bool kHint, bool kNib>
 __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, packed_reads bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
@@ -315,48 +315,21 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
   const uint64_t pol = kHint ? l2_evict_last_policy() : 0;
   const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
   uint32_t c0[8], c1[8], first[8];
-  uint32_t inl[8];                        // kSlots: the bucket's tails when it is held inline in its slot
-  if(kSlots) {
-    // stage 1: ONE 8-byte read per (position, strand): bucket start, size and -- for a bucket of at
-    // most slot_cap entries -- its tails
-    uint2 sl[8];
+  // stage 1: the bucket bounds of all (position, strand) pairs of this thread, loads issued together
 #pragma unroll
-    for(int j = 0; j < 4; ++j) {
-      if(keep[j]) {
-        sl[2 * j]     = __ldg(iv.slots + (uint32_t)(t.m[j] >> iv.tail_bits));
-        sl[2 * j + 1] = __ldg(iv.slots + (uint32_t)(t.rm[j] >> iv.tail_bits));
-      }
+  for(int j = 0; j < 4; ++j) {
+    if(keep[j]) {
+      const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
+      bucket_bounds<kNib, kHint>(iv, pm, c0[2 * j], c1[2 * j], pol);
+      bucket_bounds<kNib, kHint>(iv, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
     }
-    // stage 2: larger buckets go to the tail array (size 255 = "255 or more": the exact end is in counts)
+  }
+  // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
+  // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
 #pragma unroll
-    for(int q = 0; q < 8; ++q) {
-      c0[q] = c1[q] = 0; first[q] = 0; inl[q] = 0;
-      if(keep[q >> 1]) {
-        const uint32_t n = sl[q].y & 255u;
-        c0[q] = sl[q].x; c1[q] = sl[q].x + n; inl[q] = sl[q].y >> 8;
-        if(n > iv.slot_cap) {
-          if(n == 255u) c1[q] = __ldg(iv.counts + (uint32_t)((q & 1 ? t.rm[q >> 1] : t.m[q >> 1]) >> iv.tail_bits) + 1);
-          first[q] = tail_word<false>(iv, tail_word_of(iv, c0[q]), 0);
-        }
-      }
-    }
-  } else {
-    // stage 1: prefix-table probes for all (position, strand) pairs of this thread, issued together
-#pragma unroll
-    for(int j = 0; j < 4; ++j) {
-      if(keep[j]) {
-        const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
-        load_count_pair<kHint>(iv.counts, pm, c0[2 * j], c1[2 * j], pol);
-        load_count_pair<kHint>(iv.counts, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
-      }
-    }
-    // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
-    // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
-#pragma unroll
-    for(int q = 0; q < 8; ++q) {
-      first[q] = 0;
-      if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
-    }
+  for(int q = 0; q < 8; ++q) {
+    first[q] = 0;
+    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
   }
   uint32_t nlook = 0, ntail = 0, nlist = 0, nbucket = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
@@ -375,15 +348,9 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
         if(a0 != a1) {
           const uint32_t tt = (uint32_t)mer & tmask;
           uint32_t lo, hi;
-          if(kSlots && a1 - a0 <= iv.slot_cap) {
-            uint32_t less = 0, leq = 0, pk = inl[2 * j + s];
-            for(uint32_t i = a0; i < a1; ++i, pk >>= iv.tail_bits) { const uint32_t v = pk & tmask; less += v < tt; leq += v <= tt; }
-            lo = a0 + less; hi = a0 + leq;
-          } else {
-            ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
-            ++nbucket;
-            bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
-          }
+          ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
+          ++nbucket;
+          bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
           if(hi != lo && (mer & 3) == 0)
             for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
           nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;
@@ -1012,42 +979,9 @@ __global__ void __launch_bounds__(256) row_keys_kernel(uint64_t S, const uint32_
   k4[i] = make_int4(rs[me], re[me], (int)ql[me], (int)sr[me]);
   k5[i] = iter[me];
 }
-template<bool kBig>
-__global__ void __launch_bounds__(kBig ? 512 : 128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
-                                                                     const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
-                                                                     uint32_t warp_max, uint32_t* __restrict__ order) {
-  if(kBig) {
-    // a read with many rows: 512 rows at a time are ranked against all rows of the read, which pass through
-    // shared memory in tiles of 512 (every thread reads the same tile entry: one broadcast per comparison)
-    __shared__ int4     s4[512];
-    __shared__ uint32_t s5[512];
-    const uint32_t r = blockIdx.x;
-    if(r >= nreads) return;
-    const uint64_t b = read_coords[r];
-    const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
-    if(c <= warp_max) return;
-    for(uint32_t e0 = 0; e0 < c; e0 += 512) {
-      const uint32_t e = e0 + threadIdx.x;
-      const bool mine = e < c;
-      const int4 a4 = mine ? k4[b + e] : make_int4(0, 0, 0, 0);
-      const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, mine ? k5[b + e] : 0u };
-      uint32_t rank = 0;
-      for(uint32_t f0 = 0; f0 < c; f0 += 512) {
-        __syncthreads();
-        if(f0 + threadIdx.x < c) { s4[threadIdx.x] = k4[b + f0 + threadIdx.x]; s5[threadIdx.x] = k5[b + f0 + threadIdx.x]; }
-        __syncthreads();
-        const uint32_t m = min(512u, c - f0);
-#pragma unroll 4
-        for(uint32_t f = 0; f < m; ++f) {
-          const int4 o4 = s4[f];
-          const row_key o = { o4.x, o4.y, (uint32_t)o4.z, (uint32_t)o4.w, s5[f] };
-          rank += row_key_less(o, a);
-        }
-      }
-      if(mine) order[b + rank] = slot[b + e];
-    }
-    return;
-  }
+__global__ void __launch_bounds__(128) rank_rows_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
+                                                         const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
+                                                         uint32_t warp_max, uint32_t* __restrict__ order) {
   const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, first = threadIdx.x & 31;
   if(r >= nreads) return;
   const uint64_t b = read_coords[r];
@@ -1063,6 +997,64 @@ __global__ void __launch_bounds__(kBig ? 512 : 128) rank_rows_kernel(uint32_t nr
       rank += row_key_less(o, a);
     }
     order[b + rank] = slot[b + e];
+  }
+}
+
+// A read with many rows (repeats: hundreds to thousands): one CTA.  Up to sort_cap rows the keys go to
+// shared memory and the row indices are sorted there (bitonic network; the five keys of two rows never tie
+// completely -- the super-read and the --max-match round tell them apart); above, the rows are ranked by
+// counting, 512 at a time against all rows of the read passing through shared memory in tiles of 512.
+__global__ void __launch_bounds__(512) rank_rows_big_kernel(uint32_t nreads, const uint64_t* __restrict__ read_coords, const uint32_t* __restrict__ slot,
+                                                             const int4* __restrict__ k4, const uint32_t* __restrict__ k5,
+                                                             uint32_t warp_max, uint32_t sort_cap, uint32_t* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const uint32_t r = blockIdx.x;
+  if(r >= nreads) return;
+  const uint64_t b = read_coords[r];
+  const uint32_t c = (uint32_t)(read_coords[r + 1] - b);
+  if(c <= warp_max) return;
+  if(c <= sort_cap) {
+    int4* s4 = (int4*)dyn;
+    uint32_t* s5 = (uint32_t*)(s4 + sort_cap);
+    uint32_t* idx = s5 + sort_cap;
+    uint32_t m = 1;
+    while(m < c) m <<= 1;
+    for(uint32_t i = threadIdx.x; i < m; i += 512) {
+      if(i < c) { s4[i] = k4[b + i]; s5[i] = k5[b + i]; idx[i] = i; }
+      else idx[i] = prim::kPad;
+    }
+    __syncthreads();
+    prim::bitonic_sort_idx(idx, (int)m, [&](uint32_t x, uint32_t y) {
+      const int4 x4 = s4[x], y4 = s4[y];
+      const row_key kx = { x4.x, x4.y, (uint32_t)x4.z, (uint32_t)x4.w, s5[x] }, ky = { y4.x, y4.y, (uint32_t)y4.z, (uint32_t)y4.w, s5[y] };
+      if(row_key_less(kx, ky)) return true;
+      if(row_key_less(ky, kx)) return false;
+      return x < y;
+    });
+    for(uint32_t rk = threadIdx.x; rk < c; rk += 512) order[b + rk] = slot[b + idx[rk]];
+    return;
+  }
+  int4* s4 = (int4*)dyn;                               // at least 512 entries of each (the launch sizes it)
+  uint32_t* s5 = (uint32_t*)(s4 + 512);
+  for(uint32_t e0 = 0; e0 < c; e0 += 512) {
+    const uint32_t e = e0 + threadIdx.x;
+    const bool mine = e < c;
+    const int4 a4 = mine ? k4[b + e] : make_int4(0, 0, 0, 0);
+    const row_key a = { a4.x, a4.y, (uint32_t)a4.z, (uint32_t)a4.w, mine ? k5[b + e] : 0u };
+    uint32_t rank = 0;
+    for(uint32_t f0 = 0; f0 < c; f0 += 512) {
+      __syncthreads();
+      if(f0 + threadIdx.x < c) { s4[threadIdx.x] = k4[b + f0 + threadIdx.x]; s5[threadIdx.x] = k5[b + f0 + threadIdx.x]; }
+      __syncthreads();
+      const uint32_t mm = min(512u, c - f0);
+#pragma unroll 4
+      for(uint32_t f = 0; f < mm; ++f) {
+        const int4 o4 = s4[f];
+        const row_key o = { o4.x, o4.y, (uint32_t)o4.z, (uint32_t)o4.w, s5[f] };
+        rank += row_key_less(o, a);
+      }
+    }
+    if(mine) order[b + rank] = slot[b + e];
   }
 }
 
@@ -1203,8 +1195,8 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     timer.next("seed lookup");
     if(nparts == 1) {
       l2_window(ctx, st, idx, true);
-      auto kern = iv.slots ? seed_lookup_kernel<false, false, true>
-                           : (g_l2_hint ? seed_lookup_kernel<false, true, false> : seed_lookup_kernel<false, false, false>);
+      auto kern = iv.nib ? seed_lookup_kernel<false, false, true>
+                         : (g_l2_hint ? seed_lookup_kernel<false, true, false> : seed_lookup_kernel<false, false, false>);
       kern<<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                           ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
                                           ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
@@ -1213,7 +1205,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       for(uint32_t part = 0; part < nparts; ++part) {
         l2_window(ctx, st, part ? idx->more[part - 1] : idx, true);
         const index_view& pv = idx->part_view(part);
-        auto kern = pv.slots ? seed_lookup_kernel<true, false, true> : seed_lookup_kernel<true, false, false>;
+        auto kern = pv.nib ? seed_lookup_kernel<true, false, true> : seed_lookup_kernel<true, false, false>;
         kern<<<ntiles, kSeedThreads, 0, st>>>(pv, (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
                                             d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
                                             ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
@@ -1484,13 +1476,17 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     row_keys_kernel<<<div_up(S, 256), 256, 0, st>>>(S, ws.slot.as<uint32_t>(), A.sv.rs, A.sv.re, A.sv.ql, A.sv.sr, A.sv.iter,
                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>());
     MR_LAUNCHED(ctx);
-    rank_rows_kernel<false><<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+    rank_rows_kernel<<<div_up((uint64_t)nreads * 32, 128), 128, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
                                                                                 ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(), ws.order.as<uint32_t>());
     MR_LAUNCHED(ctx);
     if(max_rows > big_rows_threshold()) {                            // some read has that many rows
-      rank_rows_kernel<true><<<nreads, 512, 0, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
-                                                     ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(),
-                                                     ws.order.as<uint32_t>());
+      uint32_t sort_cap = 512;
+      while(sort_cap < (uint32_t)std::min(max_rows, big_sort_rows_limit())) sort_cap <<= 1;
+      const size_t smem = (size_t)std::max<uint32_t>(sort_cap, 512) * 24;
+      MR_CUDA(ctx, cudaFuncSetAttribute(rank_rows_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      rank_rows_big_kernel<<<nreads, 512, smem, st>>>(nreads, ws.read_coords.as<uint64_t>(), ws.slot.as<uint32_t>(),
+                                                    ws.rowkey4.as<int4>(), ws.rowkey5.as<uint32_t>(), (uint32_t)big_rows_threshold(),
+                                                    std::min<uint32_t>(sort_cap, (uint32_t)big_sort_rows_limit()), ws.order.as<uint32_t>());
       MR_LAUNCHED(ctx);
     }
     gather_args Gt;

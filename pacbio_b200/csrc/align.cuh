@@ -155,6 +155,13 @@ inline int path_smem_rows_limit() {
   static const int v = [] { const char* e = getenv("MR_HUGE_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? std::min(x, 6144) : 6144; }();
   return v;
 }
+// rows of a read up to which the per-read orderings (coords order, graph nodes) are a bitonic sort in shared
+// memory instead of a ranking by counting; a power of two.  MR_SORT_ROWS lowers it (tests reach the fallback).
+inline int big_sort_rows_limit() {
+  static const int v = [] { const char* e = getenv("MR_SORT_ROWS"); int x = e ? atoi(e) : 0; if(x <= 0 || x > 4096) x = 4096;
+                            int p = 1; while(p * 2 <= x) p *= 2; return p; }();
+  return v;
+}
 inline int big_rows_threshold() {
   static const int v = [] { const char* e = getenv("MR_BIG_ROWS"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 96; }();
   return v;

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) graph_kernel(graph_args A) {
 //                             successor order (the slices come from an exclusive scan of the counts)
 //   graph_path_kernel         warp 0: components (union_find.cc:6-24) in edge order; warp 1: longest path
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) graph_big_prepare_kernel(graph_args A) {
+__global__ void __launch_bounds__(256) graph_big_prepare_kernel(graph_args A, int sort_cap) {
   const int tid = (int)threadIdx.x;
   const uint32_t r = blockIdx.x;
   if(r >= A.nreads) return;
@@ -226,7 +226,39 @@ __global__ void __launch_bounds__(256) graph_big_prepare_kernel(graph_args A) {
     A.start_node[row] = 1; A.end_node[row] = 1;
   }
   __syncthreads();
-  // node order by counting: 256 nodes at a time against all nodes, which pass through shared memory in tiles
+  // node order by (imp_s, imp_e), exact ties by row (the reference's std::sort is unstable there)
+  auto place = [&](int rk, int i) {
+    const uint64_t row = b + i;
+    order[rk] = i;
+    ord_s[rk] = imp_s[i]; ord_e[rk] = imp_e[i]; ord_err[rk] = A.c.avg_err[row];
+    const uint32_t sr = A.c.sr[row];
+    const uint64_t u0 = A.unitig_off ? A.unitig_off[sr] : 0;
+    const uint32_t un = A.unitig_off ? (uint32_t)(A.unitig_off[sr + 1] - u0) : 0u;
+    ord_path[rk] = make_ulonglong2(u0, (uint64_t)un | ((uint64_t)(A.c.use_bwd[row] != 0) << 32));
+  };
+  if(n <= sort_cap) {
+    // bitonic sort of the node indices with their keys in shared memory
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double* ks = (double*)dyn;
+    double* ke = ks + sort_cap;
+    uint32_t* idx = (uint32_t*)(ke + sort_cap);
+    int m = 1;
+    while(m < n) m <<= 1;
+    for(int i = tid; i < m; i += 256) {
+      if(i < n) { ks[i] = imp_s[i]; ke[i] = imp_e[i]; idx[i] = (uint32_t)i; }
+      else idx[i] = prim::kPad;
+    }
+    __syncthreads();
+    prim::bitonic_sort_idx(idx, m, [&](uint32_t x, uint32_t y) {
+      const double sx = ks[x], sy = ks[y];
+      if(sx != sy) return sx < sy;
+      const double ex = ke[x], ey = ke[y];
+      return ex != ey ? ex < ey : x < y;
+    });
+    for(int rk = tid; rk < n; rk += 256) place(rk, (int)idx[rk]);
+    return;
+  }
+  // larger reads: by counting, 256 nodes at a time against all nodes, which pass through shared memory in tiles
   __shared__ double2 tile[256];
   for(int i0 = 0; i0 < n; i0 += 256) {
     const int i = i0 + tid;
@@ -237,21 +269,14 @@ __global__ void __launch_bounds__(256) graph_big_prepare_kernel(graph_args A) {
       __syncthreads();
       if(j0 + tid < n) tile[tid] = make_double2(imp_s[j0 + tid], imp_e[j0 + tid]);
       __syncthreads();
-      const int m = min(256, n - j0);
+      const int mm = min(256, n - j0);
 #pragma unroll 4
-      for(int j = 0; j < m; ++j) {
+      for(int j = 0; j < mm; ++j) {
         const double2 o = tile[j];
         rk += (o.x < s || (o.x == s && o.y < e)) || (o.x == s && o.y == e && j0 + j < i);
       }
     }
-    if(!mine) continue;
-    const uint64_t row = b + i;
-    order[rk] = i;
-    ord_s[rk] = s; ord_e[rk] = e; ord_err[rk] = A.c.avg_err[row];
-    const uint32_t sr = A.c.sr[row];
-    const uint64_t u0 = A.unitig_off ? A.unitig_off[sr] : 0;
-    const uint32_t un = A.unitig_off ? (uint32_t)(A.unitig_off[sr + 1] - u0) : 0u;
-    ord_path[rk] = make_ulonglong2(u0, (uint64_t)un | ((uint64_t)(A.c.use_bwd[row] != 0) << 32));
+    if(mine) place(rk, i);
   }
 }
 
@@ -478,8 +503,16 @@ int launch_graph(mr_context* ctx, mr_workspace& ws, graph_args a, uint64_t S, in
   MR_TRY(ws.edge_off.ensure(ctx, (S + 2) * sizeof(uint64_t)));
   a.ord_path = ws.node_path.as<ulonglong2>(); a.edge_cnt = ws.edge_cnt.as<uint32_t>(); a.edge_off = ws.edge_off.as<uint64_t>();
   a.edges = nullptr;
-  graph_big_prepare_kernel<<<a.nreads, 256, 0, st>>>(a);
-  MR_LAUNCHED(ctx);
+  {
+    // node order: bitonic sort in shared memory (20 bytes per row, rounded up to a power of two) up to 4096 rows
+    int sort_cap = 1;
+    while(sort_cap < std::min(max_rows, big_sort_rows_limit())) sort_cap <<= 1;
+    if(sort_cap > big_sort_rows_limit()) sort_cap >>= 1;
+    const size_t smem = (size_t)sort_cap * 20;
+    MR_CUDA(ctx, cudaFuncSetAttribute(graph_big_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_big_prepare_kernel<<<a.nreads, 256, smem, st>>>(a, sort_cap);
+    MR_LAUNCHED(ctx);
+  }
   const unsigned node_blocks = div_up(S * 32, 256);
   graph_edges_kernel<false><<<node_blocks, 256, 0, st>>>(a, S);
   MR_LAUNCHED(ctx);

@@ -124,17 +124,25 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
   }
 }
 
-// slots (index_view::slots) from counts + 8-bit tails
-__global__ void __launch_bounds__(256) slots_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ tails,
-                                                    uint32_t nprefix, uint32_t tail_bits, uint32_t cap, uint2* __restrict__ slots) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nprefix; p += stride) {
-    const uint32_t a0 = counts[p], n = counts[p + 1] - a0;
-    uint32_t pack = 0;
-    if(n <= cap)
-      for(uint32_t i = 0; i < n; ++i) pack |= (uint32_t)tails[a0 + i] << (tail_bits * i);
-    slots[p] = make_uint2(a0, min(n, 255u) | (pack << 8));
+// nibble records (index_view::nib): one thread per group of 64 prefixes
+__global__ void __launch_bounds__(256) nib_kernel(const uint32_t* __restrict__ counts, uint32_t ngroups, uint4* __restrict__ nib,
+                                                  uint32_t* __restrict__ gbase, unsigned long long* __restrict__ n_overflow) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= ngroups) return;
+  const uint32_t* c = counts + (uint64_t)g * 64;
+  uint32_t w[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  bool big = false;
+  uint32_t prev = c[0];
+  for(int j = 0; j < 64; ++j) {
+    const uint32_t next = c[j + 1], sz = next - prev;
+    prev = next;
+    big |= sz >= 15;
+    w[j >> 3] |= (sz & 15u) << (4 * (j & 7));
   }
+  if(big) { w[0] |= 15u; atomicAdd(n_overflow, 1ULL); }      // marker: this group is looked up in counts[]
+  nib[2 * (uint64_t)g]     = make_uint4(w[0], w[1], w[2], w[3]);
+  nib[2 * (uint64_t)g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  gbase[g] = c[0];
 }
 
 // random-sector ceiling: every thread issues 8 independent 16-byte loads per round at hashed places
@@ -304,24 +312,28 @@ int build_slots(mr_index* idx) {
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     v.blkx = idx->blkx.as<uint4>();
   }
-  v.slots = nullptr; v.slot_cap = 0;
-  // Off unless MR_SLOTS=1.  Measured on the bench workload (mi = 12, 134 MB of slots instead of 67 MB of
-  // counts): seed lookup 30.2 -> 35.2 ms per step although only half as many tail entries are
-  // scanned; with mi = 13 (536 MB, every bucket inline, exactly one 8-byte read per lookup) 34.8 ms.
-  // The k-mers that matter are not random: a read's error-free k-mers occur once per super-read
-  // covering them, so their buckets exceed the inline capacity and still take the second read,
-  // while the table that every lookup touches doubles and loses its L2 hits.
-  const char* on = getenv("MR_SLOTS");
-  if(v.tail_bytes != 1 || v.tail_bits == 0 || !(on && atoi(on) != 0)) return MR_OK;
+  v.nib = nullptr; v.gbase = nullptr;
+  // The nibble form of the prefix counts pays while most groups of 64 buckets hold no bucket of 15 entries:
+  // a mean bucket of up to ~4 (the yeast-size index: 2.1).  MR_NIB=0 switches it off (A/B), MR_NIB=1 forces it.
   const uint32_t nprefix = 1u << (2 * v.mi);
-  if((uint64_t)v.nsa > (uint64_t)nprefix * (24 / v.tail_bits)) return MR_OK;      // mean bucket above the inline capacity: no gain
-  MR_TRY(idx->slots.ensure(ctx, (size_t)nprefix * sizeof(uint2)));
-  const uint32_t cap = 24 / v.tail_bits;
-  slots_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(idx->counts.as<uint32_t>(), idx->tails.as<uint8_t>(), nprefix, v.tail_bits, cap,
-                                                         idx->slots.as<uint2>());
+  const char* knob = getenv("MR_NIB");
+  const bool forced = knob && atoi(knob) == 1, off = knob && atoi(knob) == 0;
+  if(off || v.mi < 3 || (!forced && (uint64_t)v.nsa > (uint64_t)nprefix * 4)) return MR_OK;
+  const uint32_t ngroups = nprefix / 64;
+  MR_TRY(idx->nib.ensure(ctx, (size_t)ngroups * 2 * sizeof(uint4)));
+  MR_TRY(idx->gbase.ensure(ctx, (size_t)ngroups * sizeof(uint32_t)));
+  dev_buf ovf;
+  MR_TRY(ovf.ensure(ctx, sizeof(unsigned long long)));
+  MR_CUDA(ctx, cudaMemsetAsync(ovf.p, 0, sizeof(unsigned long long), ctx->stream));
+  nib_kernel<<<div_up(ngroups, 256), 256, 0, ctx->stream>>>(idx->counts.as<uint32_t>(), ngroups, idx->nib.as<uint4>(), idx->gbase.as<uint32_t>(),
+                                                          ovf.as<unsigned long long>());
   MR_LAUNCHED(ctx);
+  unsigned long long n_overflow = 0;
+  MR_CUDA(ctx, cudaMemcpyAsync(&n_overflow, ovf.p, sizeof n_overflow, cudaMemcpyDeviceToHost, ctx->stream));
   MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  v.slots = idx->slots.as<uint2>(); v.slot_cap = cap;
+  if(!forced && n_overflow * 4 > ngroups) { idx->nib.release(); idx->gbase.release(); return MR_OK; }    // too many groups fall back: not worth the extra read
+  v.nib = idx->nib.as<uint4>(); v.gbase = idx->gbase.as<uint32_t>();
+  idx->nib_overflow_groups = n_overflow;
   return MR_OK;
 }
 
@@ -466,8 +478,14 @@ uint64_t mr_index_sa_size(const mr_index* idx) { return idx ? idx->nsa : 0; }
 uint32_t mr_index_parts(const mr_index* idx) { return idx ? idx->nparts() : 0; }
 uint64_t mr_index_table_bytes(const mr_index* idx) {
   if(!idx) return 0;
-  uint64_t b = idx->lut_bytes;
-  for(const mr_index* p : idx->more) b += p->lut_bytes;
+  auto part_bytes = [](const mr_index* p) -> uint64_t {
+    if(!p->view.nib) return p->lut_bytes;
+    // with nibble records the prefix counts are only read for the groups that overflow
+    const uint64_t ngroups = (1ULL << (2 * p->mi)) / 64;
+    return ngroups * 36 + ((uint64_t)p->nsa + 64) * p->view.tail_bytes + p->nib_overflow_groups * 260;
+  };
+  uint64_t b = part_bytes(idx);
+  for(const mr_index* p : idx->more) b += part_bytes(p);
   return b;
 }
 

@@ -47,12 +47,15 @@ struct index_view {
   const uint4*    __restrict__ blkx;   // blkx[b] = { blk[b], sr_start[blk[b]], sr_start[blk[b] + 1], 0 }: one load locates a hit
   uint64_t n;
   uint32_t nsa, nseq, k, m, mi, tail_bits, tail_bytes, nshort;
-  // slots[p] = { counts[p], min(bucket size, 255) | tails of the bucket << 8 } for buckets of at most
-  // slot_cap = 24 / tail_bits entries: ONE 8-byte random read answers a lookup whose bucket is small
-  // (93 % of them at a mean bucket of 2) instead of a counts read plus a tails read.  Built when the
-  // tails have at most 8 bits (slot_cap >= 3); null otherwise.
-  const uint2*    __restrict__ slots;
-  uint32_t slot_cap;
+  // Compact form of `counts` for the lookups (null when the buckets are too large for it to pay):
+  // the sizes of 64 consecutive buckets as 4-bit numbers in one 32-byte record -- ONE sector -- plus the
+  // start of the group's first bucket in gbase[]; a bucket's bounds are gbase + a sum of nibbles.
+  // 8 bits per prefix instead of 32: with the 8-bit tails, what a lookup reads at random shrinks from
+  // 103 MB to 45 MB on the yeast-size index and stays in the L2 (126 MB, of which lines homed on the
+  // other die take a second copy).  A group with a bucket of 15 entries or more has nibble 0 = 15 and is
+  // looked up in `counts` as before.
+  const uint4*    __restrict__ nib;      // 2 x uint4 per group of 64 prefixes
+  const uint32_t* __restrict__ gbase;
   uint32_t own;                    // bases of the part's own super-reads (sr_start[nseq]); n - own = extension (index.cuh header)
   uint32_t sr_base;                // global index of this part's first super-read (0 for a one-part index)
   uint32_t nseq_all;               // super-reads of the whole index (== nseq for a one-part index)
@@ -69,7 +72,7 @@ struct mr_index {
   uint64_t unitig_total = 0;         // entries of unitig_ids
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;
-  dev_buf  slots;                    // uint2[4^mi]: see index_view::slots
+  dev_buf  nib, gbase;               // see index_view::nib (derived; not in index files)
   dev_buf  blkx;                     // uint4[(n>>8)+1]: see index_view::blkx (derived; not in index files)
   dev_buf  lut;                      // counts and tails live side by side in this one allocation, so that
                                      // a single L2 access-policy window covers what a lookup reads
@@ -83,6 +86,7 @@ struct mr_index {
     return MR_OK;
   }
   size_t   lut_bytes = 0;
+  uint64_t nib_overflow_groups = 0;  // groups of 64 prefixes that hold a bucket of 15 or more entries (looked up in counts)
   dev_buf  unitig_ids, unitig_off, unitig_len, sr_nunitigs;
   index_view view;
   // whole-index tables (a one-part index: the part is the index itself)
@@ -131,6 +135,32 @@ __device__ __forceinline__ void load_count_pair(const uint32_t* __restrict__ cou
   case 2: c0 = v.z; c1 = v.w; break;
   default: c0 = v.w; c1 = table_load_u32<kHint>(counts + p + 1, pol);
   }
+}
+
+// bounds [c0, c1) of the bucket of prefix p: from the nibble record when the index has one (kNib), else counts[p], counts[p + 1]
+template<bool kNib, bool kHint = false>
+__device__ __forceinline__ void bucket_bounds(const index_view& iv, uint32_t p, uint32_t& c0, uint32_t& c1, uint64_t pol = 0) {
+  if(kNib) {
+    const uint32_t g = p >> 6, j = p & 63;
+    const uint4 a = __ldg(iv.nib + 2 * g), b = __ldg(iv.nib + 2 * g + 1);
+    const uint32_t base = __ldg(iv.gbase + g);           // issued with the record, not after a look at it
+    if((a.x & 15u) != 15u) {
+      const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+      const uint32_t wj = j >> 3, sh = 4 * (j & 7);
+      uint32_t sum = base, mine = 0;
+#pragma unroll
+      for(uint32_t i = 0; i < 8; ++i) {
+        // nibbles of word i that lie before nibble j: all of them, the low ones, or none
+        const uint32_t x = i < wj ? w[i] : (i == wj ? w[i] & ((1u << sh) - 1) : 0u);
+        const uint32_t t = (x & 0x0f0f0f0fu) + ((x >> 4) & 0x0f0f0f0fu);        // byte sums, each <= 28
+        sum += (t * 0x01010101u) >> 24;
+        if(i == wj) mine = (w[i] >> sh) & 15u;
+      }
+      c0 = sum; c1 = sum + mine;
+      return;
+    }
+  }
+  load_count_pair<kHint>(iv.counts, p, c0, c1, pol);
 }
 
 template<bool kHint = false>
@@ -208,7 +238,7 @@ __device__ __forceinline__ void index_lookup(const index_view& iv, uint64_t mer,
   const uint32_t pre = (uint32_t)(mer >> iv.tail_bits);
   const uint32_t t   = (uint32_t)mer & (iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1));
   uint32_t c0, c1;
-  load_count_pair(iv.counts, pre, c0, c1);
+  if(iv.nib) bucket_bounds<true>(iv, pre, c0, c1); else load_count_pair(iv.counts, pre, c0, c1);
   index = 0; nb = 0;
   if(c0 == c1) return;
   uint32_t lo, hi;

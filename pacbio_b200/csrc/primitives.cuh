@@ -3,6 +3,7 @@
 // fully coalesced 16 KiB tiles and writes once; the roofline for them is the copy bandwidth.
 #pragma once
 #include "common.cuh"
+#include <algorithm>
 
 namespace prim {
 
@@ -32,6 +33,29 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_256(uint64_t v, uint64_
   total = tot;
   __syncthreads();
   return wprefix + inc - v;
+}
+
+// ---- CTA bitonic sort of an index array in shared memory ---------------------------------------------
+// idx[0 .. m), m a power of two; less(a, b) is a strict total order on the entries (callers break ties by the
+// entry itself, so the result does not depend on the network); entries equal to kPad sort last.  All
+// threads of the CTA must call it.  m log2(m)^2 / 4 compare-exchanges: 0.3 M for 4096 entries, where ranking
+// by counting costs 16 M comparisons.
+constexpr uint32_t kPad = 0xffffffffu;
+template<typename Less>
+__device__ __forceinline__ void bitonic_sort_idx(uint32_t* idx, int m, Less less) {
+  for(int k = 2; k <= m; k <<= 1) {
+    for(int j = k >> 1; j > 0; j >>= 1) {
+      for(int t = (int)threadIdx.x; t < (m >> 1); t += (int)blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // bit j clear
+        const int l = i | j;
+        const uint32_t a = idx[i], b = idx[l];
+        const bool b_first = b != kPad && (a == kPad || less(b, a));
+        const bool a_first = a != kPad && (b == kPad || less(a, b));
+        if((i & k) == 0 ? b_first : a_first) { idx[i] = b; idx[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // ---- exclusive scan: out[i] = sum_{j<i} in(j), in() yields uint32/uint64 ------------------------
@@ -184,33 +208,38 @@ constexpr int kSortWarps   = kSortThreads / 32;
 constexpr int kSortItems   = 16;
 constexpr int kSortTile    = kSortThreads * kSortItems;   // 4096 keys per CTA
 
-template<typename K>
+// kBits: width of the digit of this pass (at most kSortBits); a key range that is not a multiple of 8 bits is
+// cut into equal digits (14 bits: 7 + 7, 21 bits: 7 + 7 + 7) -- half as many buckets per pass means runs
+// twice as long in the scattered stores
+template<typename K, int kBits>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const K* __restrict__ keys, uint64_t n, int shift,
                                                                    uint32_t* __restrict__ table, uint32_t nblocks) {
-  __shared__ uint32_t h[kSortRadix];
-  h[threadIdx.x] = 0;
+  constexpr int kRadix = 1 << kBits;
+  __shared__ uint32_t h[kRadix];
+  if(threadIdx.x < kRadix) h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
 #pragma unroll
   for(int i = 0; i < kSortItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-    if(idx < n) atomicAdd(&h[(unsigned)(keys[idx] >> shift) & (kSortRadix - 1)], 1u);
+    if(idx < n) atomicAdd(&h[(unsigned)(keys[idx] >> shift) & (kRadix - 1)], 1u);
   }
   __syncthreads();
-  table[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // digit-major
+  if(threadIdx.x < kRadix) table[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // digit-major
 }
 
 // Each warp owns a contiguous 512-key slice of the tile and walks it 32 keys at a time, so the
 // rank of a key among equal digits is (earlier warps) + (earlier rounds of this warp) + (lower
 // lanes of this round): order preserving, hence stable.
-template<typename K, typename V>
+template<typename K, typename V, int kBits>
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __restrict__ kin, const V* __restrict__ vin,
                                                                       K* __restrict__ kout, V* __restrict__ vout,
                                                                       uint64_t n, int shift,
                                                                       const uint64_t* __restrict__ offsets, uint32_t nblocks) {
-  __shared__ uint32_t cnt[kSortWarps][kSortRadix];
-  __shared__ uint64_t wbase[kSortWarps][kSortRadix];
-  for(int i = threadIdx.x; i < kSortWarps * kSortRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  constexpr int kRadix = 1 << kBits;
+  __shared__ uint32_t cnt[kSortWarps][kRadix];
+  __shared__ uint64_t wbase[kSortWarps][kRadix];
+  for(int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
@@ -222,7 +251,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __
     const uint64_t idx = base + (uint64_t)i * 32 + lane;
     const bool valid = idx < n;
     key[i] = valid ? kin[idx] : (K)0;
-    const unsigned d = valid ? ((unsigned)(key[i] >> shift) & (kSortRadix - 1)) : (unsigned)kSortRadix;
+    const unsigned d = valid ? ((unsigned)(key[i] >> shift) & (kRadix - 1)) : (unsigned)kRadix;
     const unsigned peers  = __match_any_sync(MR_FULL_MASK, d);
     const unsigned leader = __ffs(peers) - 1;
     unsigned b = 0;
@@ -232,8 +261,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __
     __syncwarp();
   }
   __syncthreads();
-  {
-    const unsigned d = threadIdx.x;                  // kSortRadix == kSortThreads
+  if(threadIdx.x < kRadix) {                         // kRadix <= kSortThreads
+    const unsigned d = threadIdx.x;
     uint64_t run = offsets[(uint64_t)d * nblocks + blockIdx.x];
 #pragma unroll
     for(int w = 0; w < kSortWarps; ++w) { wbase[w][d] = run; run += cnt[w][d]; }
@@ -243,7 +272,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __
   for(int i = 0; i < kSortItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * 32 + lane;
     if(idx < n) {
-      const unsigned d = (unsigned)(key[i] >> shift) & (kSortRadix - 1);
+      const unsigned d = (unsigned)(key[i] >> shift) & (kRadix - 1);
       const uint64_t dst = wbase[warp][d] + rank[i];
       kout[dst] = key[i];
       vout[dst] = vin[idx];
@@ -257,29 +286,55 @@ struct sort_scratch {
   dev_buf scan;      // scan scratch
 };
 
+// one pass on the digit [shift, shift + kBits)
+template<typename K, typename V, int kBits>
+int radix_pass(mr_context* ctx, const K* kin, const V* vin, K* kout, V* vout, uint64_t n, int shift, sort_scratch& s) {
+  const uint32_t nblocks = div_up(n, kSortTile);
+  const uint64_t tsize = ((uint64_t)1 << kBits) * nblocks;
+  radix_hist_kernel<K, kBits><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, s.table.as<uint32_t>(), nblocks);
+  MR_LAUNCHED(ctx);
+  MR_TRY((exclusive_scan<ptr_in_u32, uint64_t>(ctx, ptr_in_u32{ s.table.as<uint32_t>() }, tsize, s.offsets.as<uint64_t>(), s.scan, nullptr)));
+  radix_scatter_kernel<K, V, kBits><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, s.offsets.as<uint64_t>(), nblocks);
+  MR_LAUNCHED(ctx);
+  return MR_OK;
+}
+
+// MR_SORT_EVEN_DIGITS=0: digits of 8 bits, the last one shorter (A/B switch)
+inline bool sort_even_digits() {
+  static const bool v = [] { const char* e = getenv("MR_SORT_EVEN_DIGITS"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+
 // Sorts (k0,v0) by key bits [lo_bit, hi_bit) ascending, stable.  k1/v1 are same-sized alternates.
 // On return *result_in_first tells whether the sorted data sits in (k0,v0) or (k1,v1).
 template<typename K, typename V>
 int radix_sort_pairs(mr_context* ctx, K* k0, V* v0, K* k1, V* v1, uint64_t n, int lo_bit, int hi_bit,
                      sort_scratch& s, bool* result_in_first) {
   bool first = true;
-  if(n == 0) { *result_in_first = true; return MR_OK; }
+  if(n == 0 || hi_bit <= lo_bit) { *result_in_first = true; return MR_OK; }
   const uint32_t nblocks = div_up(n, kSortTile);
   const uint64_t tsize = (uint64_t)kSortRadix * nblocks;
   MR_TRY(s.table.ensure(ctx, tsize * sizeof(uint32_t)));
   MR_TRY(s.offsets.ensure(ctx, tsize * sizeof(uint64_t)));
-  for(int shift = lo_bit; shift < hi_bit; shift += kSortBits) {
+  const int bits = hi_bit - lo_bit, passes = (bits + kSortBits - 1) / kSortBits;
+  int shift = lo_bit;
+  for(int p = 0; p < passes; ++p) {
+    // equal digits: the first (bits % passes) passes take one bit more
+    int w = sort_even_digits() ? bits / passes + (p < bits % passes ? 1 : 0) : std::min(kSortBits, hi_bit - shift);
     K* kin = first ? k0 : k1; V* vin = first ? v0 : v1;
     K* kout = first ? k1 : k0; V* vout = first ? v1 : v0;
-    radix_hist_kernel<K><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, s.table.as<uint32_t>(), nblocks);
-    MR_LAUNCHED(ctx);
-    MR_TRY((exclusive_scan<ptr_in_u32, uint64_t>(ctx, ptr_in_u32{ s.table.as<uint32_t>() }, tsize,
-                                                  s.offsets.as<uint64_t>(), s.scan, nullptr)));
-    radix_scatter_kernel<K, V><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift,
-                                                                           s.offsets.as<uint64_t>(), nblocks);
-    MR_LAUNCHED(ctx);
+    switch(w) {
+    case 8: MR_TRY((radix_pass<K, V, 8>(ctx, kin, vin, kout, vout, n, shift, s))); break;
+    case 7: MR_TRY((radix_pass<K, V, 7>(ctx, kin, vin, kout, vout, n, shift, s))); break;
+    case 6: MR_TRY((radix_pass<K, V, 6>(ctx, kin, vin, kout, vout, n, shift, s))); break;
+    case 5: MR_TRY((radix_pass<K, V, 5>(ctx, kin, vin, kout, vout, n, shift, s))); break;
+    default: MR_TRY((radix_pass<K, V, 4>(ctx, kin, vin, kout, vout, n, shift, s))); w = std::min(w, 4); break;
+    }
+    shift += w;
     first = !first;
   }
+  // digits narrower than 4 bits are rounded up to 4: the extra key bits above hi_bit are sorted too, which is
+  // harmless for every caller (they are part of the same key and equal within what the caller groups by)
   *result_in_first = first;
   return MR_OK;
 }

@@ -123,7 +123,9 @@ def test_many_row_kernels_reproduce_the_reference_fixtures(tmpdir_session, tmp_p
     meta = json.load(open(os.path.join(GOLD, name + ".json")))
     cfg = meta["config"]
     info = gen_synth(os.path.join(tmpdir_session, "e2e_" + name), **cfg["gen"])
-    env = dict(os.environ, MR_BIG_ROWS="3", MR_HUGE_ROWS="6")     # 4..6 rows: CTA of 256 threads, more: of 1024
+    # more than 3 rows: the edge-list graph kernels and the CTA ordering; up to 6 rows their sequential state lives in
+    # shared memory, above in global scratch; up to 8 rows the orderings are bitonic sorts, above rankings by counting
+    env = dict(os.environ, MR_BIG_ROWS="3", MR_HUGE_ROWS="6", MR_SORT_ROWS="8")
     common = ["-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
               "-r", info["sr"], "-p", info["reads"]]
     out_u = str(tmp_path / "cmr_u.txt")
@@ -235,7 +237,7 @@ def test_larger_input_against_oracle(tmpdir_session, tmp_path, port, tiling, tri
         cmd.append("-b")
     env = dict(os.environ, MR_BATCH_BASES="2000000")          # several batches
     if tiling == "maximal":
-        env["MR_BIG_ROWS"] = "8"                              # reads with more than 8 rows through the CTA kernels
+        env["MR_BIG_ROWS"] = "8"                              # reads with more than 8 rows through the many-row kernels
         env["MR_HUGE_ROWS"] = "20"
     run(cmd, env=env)
     want = str(tmp_path / "oracle.txt")

@@ -247,9 +247,11 @@ def test_packed_entry_point_gives_the_same_rows(case, ctx):
     p = pb.default_params(unitigs_k=c["uk"], run_graph=1)
     a, b = ctx.align(case["idx"], reads, p), ctx.align_packed(case["idx"], reads, p)
     assert a.ncoords == b.ncoords > 0 and np.array_equal(a.read_coords, b.read_coords)
-    for f in ("rs", "re", "qs", "qe", "nb_mers", "sr", "use_bwd", "lpath", "lstart", "lprev", "component", "kmers_info"):
+    for f in ("rs", "re", "qs", "qe", "nb_mers", "sr", "use_bwd", "lpath", "lstart", "lprev", "component", "info_len"):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
     assert np.array_equal(a.stretch.view(np.uint64), b.stretch.view(np.uint64))
+    for row in range(0, a.ncoords, 7):               # (a row's slice of kmers_info sits wherever its survivor slot put it)
+        assert np.array_equal(a.info(row)[0], b.info(row)[0]) and np.array_equal(a.info(row)[1], b.info(row)[1])
 
 
 def test_staged_batches_give_the_same_rows(case, ctx):

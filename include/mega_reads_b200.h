@@ -160,6 +160,9 @@ int  mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p,
 uint64_t mr_packed_code_words(uint64_t nbases);
 uint64_t mr_packed_mask_words(uint64_t nbases);
 int  mr_pack_reads(const char* bases, uint64_t nbases, uint64_t* codes, uint64_t* nmask);
+/* the same for mask words [first_word, first_word + n_words) only (and their code words): lets several host
+ * threads pack disjoint ranges of one batch */
+int  mr_pack_reads_range(const char* bases, uint64_t nbases, uint64_t first_word, uint64_t n_words, uint64_t* codes, uint64_t* nmask);
 int  mr_align_batch_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* codes, const uint64_t* nmask,
                            const uint64_t* read_start, uint32_t nreads, mr_result** out);
 int  mr_align_batch_device_packed(mr_context* ctx, mr_index* idx, const mr_params* p, const uint64_t* d_codes, const uint64_t* d_nmask,

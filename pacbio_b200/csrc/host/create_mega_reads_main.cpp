@@ -145,7 +145,7 @@ int main(int argc, char* argv[]) {
     const uint64_t nb = mrh::run_pipeline(DS, pacbio, P,
       [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<mrh::text_buf>& parts) {
         mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts);
-      }, out);
+      }, out, fthreads);
     const auto t2 = std::chrono::steady_clock::now();
     if(show_timing) std::cerr << "Starting create mega reads ... " << std::chrono::duration<double>(t2 - t1).count()
                               << " (" << nb << " bases)\n";

@@ -1,4 +1,8 @@
 #include <cerrno>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <new>
 #include <cstring>
 #include "host_common.hpp"
@@ -159,83 +163,185 @@ void unitigs::load_sequences(const std::string& path) {
 // ================================================================================================
 // long reads
 // ================================================================================================
+read_stream::read_stream(const std::vector<std::string>& paths, unsigned threads)
+  : paths_(paths), threads_(threads ? threads : std::max(1u, std::min(16u, std::thread::hardware_concurrency()))) { }
+
+void read_stream::close_current() {
+  if(map_) { munmap(map_, map_len_); map_ = nullptr; }
+  if(fd_ >= 0) { close(fd_); fd_ = -1; }
+  win_ = nullptr; win_len_ = 0; pos_ = 0; eof_ = true; open_ = false;
+  buf_.clear();
+}
+
 bool read_stream::open_next() {
-  if(f_) { fclose(f_); f_ = nullptr; }
+  close_current();
   if(next_path_ >= paths_.size()) return false;
   const std::string& p = paths_[next_path_++];
-  f_ = fopen(p.c_str(), "rb");
-  if(!f_) throw std::runtime_error("Can't open file '" + p + "'");
-  pos_ = end_ = 0; eof_ = false;
-  return true;
-}
-
-bool read_stream::fill() {
-  if(eof_ || !f_) return false;
-  end_ = fread(buf_.data(), 1, buf_.size(), f_);
-  pos_ = 0;
-  if(end_ == 0) { eof_ = true; return false; }
-  return true;
-}
-
-// next line of the current file without its terminator; false at end of file
-bool read_stream::getline(std::string& line, bool append) {
-  if(!append) line.clear();
-  bool got = false;
-  while(true) {
-    if(pos_ == end_ && !fill()) return got;
-    got = true;
-    const char* b = buf_.data() + pos_;
-    const char* nl = (const char*)memchr(b, '\n', end_ - pos_);
-    if(nl) {
-      line.append(b, nl - b);
-      pos_ += (nl - b) + 1;
-      if(!line.empty() && line.back() == '\r') line.pop_back();
+  fd_ = open(p.c_str(), O_RDONLY);
+  if(fd_ < 0) throw std::runtime_error("Can't open file '" + p + "'");
+  open_ = true; kind_ = 0;
+  struct stat st;
+  if(fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd_, 0);
+    if(m != MAP_FAILED) {
+      map_ = m; map_len_ = (size_t)st.st_size;
+      madvise(m, map_len_, MADV_SEQUENTIAL);
+      win_ = (const char*)m; win_len_ = map_len_; pos_ = 0; eof_ = true;      // everything is in the window
       return true;
     }
-    line.append(b, end_ - pos_);
-    pos_ = end_;
   }
+  eof_ = false;                              // stream mode: the window grows through refill()
+  win_ = nullptr; win_len_ = 0; pos_ = 0;
+  return true;
 }
 
-bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads) {
+bool read_stream::refill() {
+  if(eof_ || map_) return false;
+  // drop what has been consumed only when no piece of the current batch points into it (the caller resets
+  // pieces_ and pos_-relative offsets stay valid because offsets are into buf_, which is only appended to here)
+  const size_t chunk = 64u << 20;
+  const size_t old = buf_.size();
+  buf_.resize(old + chunk);
+  size_t got = 0;
+  while(got < chunk) {
+    const ssize_t r = read(fd_, buf_.data() + old + got, chunk - got);
+    if(r < 0) { if(errno == EINTR) continue; throw std::runtime_error("read error on '" + paths_[next_path_ - 1] + "'"); }
+    if(r == 0) { eof_ = true; break; }
+    got += (size_t)r;
+  }
+  buf_.resize(old + got);
+  win_ = buf_.data(); win_len_ = buf_.size();
+  return got > 0;
+}
+
+// One record at pos_.  Lines are found with memchr; nothing is copied here: the sequence lines become pieces.
+int read_stream::scan_record(read_batch& b, uint64_t& nbases) {
+  const char* w = win_;
+  const size_t end = win_len_;
+  size_t p = pos_;
+  auto line_end = [&](size_t from, size_t& nl, size_t& len) -> bool {      // false: the window ends before the line does
+    const char* q = from < end ? (const char*)memchr(w + from, '\n', end - from) : nullptr;
+    if(!q) { if(!eof_) return false; nl = end; }                            // the last line may lack its terminator
+    else nl = (size_t)(q - w);
+    len = nl - from;
+    if(len && w[from + len - 1] == '\r') --len;
+    return true;
+  };
+  size_t nl, len;
+  // header: skip empty lines
+  while(true) {
+    if(p >= end) return eof_ ? -1 : 0;
+    if(!line_end(p, nl, len)) return 0;
+    if(len) break;
+    p = std::min(end, nl + 1);
+  }
+  const char c = w[p];
+  if(c != '>' && c != '@') throw std::runtime_error("Unsupported format");
+  if(!kind_) kind_ = c;
+  const size_t hb = p + 1, he = p + len;
+  size_t ws = hb;
+  while(ws < he && !(w[ws] == ' ' || (w[ws] >= '\t' && w[ws] <= '\r'))) ++ws;
+  p = std::min(end, nl + 1);
+  const size_t first_piece = pieces_.size();
+  uint64_t rlen = 0;
+  if(c == '>') {
+    while(true) {
+      if(p >= end) { if(!eof_) { pieces_.resize(first_piece); return 0; } break; }
+      if(w[p] == '>') break;
+      if(!line_end(p, nl, len)) { pieces_.resize(first_piece); return 0; }
+      if(len) { pieces_.push_back(piece{ (uint64_t)p, (uint32_t)len, nbases + rlen }); rlen += len; }
+      p = std::min(end, nl + 1);
+    }
+  } else {
+    bool plus = false;
+    while(true) {                              // sequence lines up to the '+' line
+      if(p >= end) { if(!eof_) { pieces_.resize(first_piece); return 0; } break; }
+      if(!line_end(p, nl, len)) { pieces_.resize(first_piece); return 0; }
+      const size_t at = p;
+      p = std::min(end, nl + 1);
+      if(len && w[at] == '+') { plus = true; break; }
+      if(len) { pieces_.push_back(piece{ (uint64_t)at, (uint32_t)len, nbases + rlen }); rlen += len; }
+    }
+    uint64_t q = 0;
+    while(plus && q < rlen) {                  // quality lines: as many characters as there were bases
+      if(p >= end) { if(!eof_) { pieces_.resize(first_piece); return 0; } break; }
+      if(!line_end(p, nl, len)) { pieces_.resize(first_piece); return 0; }
+      q += len;
+      p = std::min(end, nl + 1);
+    }
+  }
+  b.name.emplace_back(w + hb, ws - hb);
+  nbases += rlen;
+  b.start.push_back(b.start.back() + rlen);
+  pos_ = p;
+  return 1;
+}
+
+bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads, bool pack) {
   if(b.start.empty()) b.start.push_back(0);
-  std::string line;
+  const uint64_t base0 = b.bases.size();
+  // ---- serial: find the records --------------------------------------------------------------------
+  // pieces of one batch may come from several files; each group is copied before its window goes away
+  uint64_t nbases = base0;
   bool any = false;
-  while(b.bases.size() - b.start[0] < max_bases && b.nreads() < max_reads) {
-    if(!have_pending_) {
-      // find the next header
-      bool found = false;
-      while(!found) {
-        if(!f_ && !open_next()) return any;
-        if(!getline(line, false)) { fclose(f_); f_ = nullptr; continue; }
-        if(line.empty()) continue;
-        if(line[0] == '>' || line[0] == '@') { pending_header_ = line.substr(1); pending_kind_ = line[0]; found = true; }
-        else throw std::runtime_error("Unsupported format");
-      }
+  auto flush_pieces = [&]() {
+    if(pieces_.empty()) { b.bases.resize(nbases); return; }
+    b.bases.resize(nbases);
+    char* dst = &b.bases[0];
+    const char* w = win_;
+    const unsigned nt = std::max(1u, std::min<unsigned>(threads_, (unsigned)(pieces_.size() / 64 + 1)));
+    auto work = [&](unsigned t) {
+      const size_t lo = pieces_.size() * t / nt, hi = pieces_.size() * (t + 1) / nt;
+      for(size_t i = lo; i < hi; ++i) memcpy(dst + pieces_[i].dst, w + pieces_[i].src, pieces_[i].len);
+    };
+    if(nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for(unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+      for(auto& x : th) x.join();
     }
-    have_pending_ = false;
-    const size_t ws = pending_header_.find_first_of(" \t\n\v\f\r");
-    b.name.push_back(pending_header_.substr(0, ws));
-    const uint64_t before = b.bases.size();
-    if(pending_kind_ == '>') {
-      while(true) {
-        if(!getline(line, false)) { fclose(f_); f_ = nullptr; break; }
-        if(!line.empty() && line[0] == '>') { pending_header_ = line.substr(1); pending_kind_ = '>'; have_pending_ = true; break; }
-        b.bases += line;
-      }
-    } else {
-      bool in_f = true;
-      while((in_f = getline(line, false))) {
-        if(!line.empty() && line[0] == '+') break;
-        b.bases += line;
-      }
-      uint64_t q = 0;
-      const uint64_t want = b.bases.size() - before;
-      while(in_f && q < want && (in_f = getline(line, false))) q += line.size();
-      if(!in_f) { fclose(f_); f_ = nullptr; }
+    pieces_.clear();
+  };
+  while(nbases - b.start[0] < max_bases && b.nreads() < max_reads) {
+    if(!open_) {
+      if(!open_next()) break;
     }
-    b.start.push_back(b.bases.size());
-    any = true;
+    if(!map_ && pieces_.empty() && pos_ > 0 && pos_ == win_len_) { buf_.clear(); win_ = nullptr; win_len_ = 0; pos_ = 0; }
+    const int rc = scan_record(b, nbases);
+    if(rc == 1) { any = true; continue; }
+    if(rc == 0) {                               // stream mode: the record continues behind the window
+      if(pieces_.empty() && pos_ > 0) {         // nothing points into the consumed part: drop it
+        buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)pos_);
+        pos_ = 0; win_ = buf_.data(); win_len_ = buf_.size();
+      }
+      refill();
+      continue;
+    }
+    flush_pieces();                             // end of this file
+    close_current();
+  }
+  flush_pieces();
+  // in stream mode the consumed prefix is dropped now that no piece points into it
+  if(open_ && !map_ && pos_ > 0) {
+    buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)pos_);
+    pos_ = 0; win_ = buf_.data(); win_len_ = buf_.size();
+  }
+  // ---- parallel: pack --------------------------------------------------------------------------------
+  if(pack && any) {
+    const uint64_t n = b.bases.size();
+    b.codes.resize(mr_packed_code_words(n)); b.nmask.resize(mr_packed_mask_words(n));
+    const uint64_t mwords = b.nmask.size();
+    const unsigned nt = std::max(1u, std::min<unsigned>(threads_, (unsigned)(mwords / 4096 + 1)));
+    auto work = [&](unsigned t) {
+      const uint64_t lo = mwords * t / nt, hi = mwords * (t + 1) / nt;
+      mr_pack_reads_range(b.bases.data(), n, lo, hi - lo, b.codes.data(), b.nmask.data());
+    };
+    if(nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for(unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+      for(auto& x : th) x.join();
+    }
   }
   return any;
 }

@@ -64,24 +64,39 @@ struct read_batch {
   }
   bool packed() const { return !nmask.empty(); }
 };
+// Reads FASTA / FASTQ files batch by batch.  A regular file is mapped and scanned in place, anything else (a FIFO,
+// a process substitution: mega_reads_assemble_cluster2.sh:472) is read in large chunks -- the stream is never
+// seeked.  A batch is cut in two steps: a serial scan that only finds the lines (memchr) and notes where each
+// record's sequence pieces lie, then `threads` workers that copy the pieces into the batch and pack it
+// (mr_pack_reads_range) -- parsing 0.6 GB of reads per step must not take longer than aligning them.
 class read_stream {
+  struct piece { uint64_t src; uint32_t len; uint64_t dst; };      // src: offset into the window
   std::vector<std::string> paths_;
   size_t next_path_ = 0;
-  FILE*  f_ = nullptr;
+  // the window: either the mapped file or the bytes read so far that are not consumed yet
+  const char* win_ = nullptr;
+  size_t win_len_ = 0, pos_ = 0;
+  void*  map_ = nullptr;
+  size_t map_len_ = 0;
+  int    fd_ = -1;
   std::vector<char> buf_;
-  size_t pos_ = 0, end_ = 0;
-  bool   eof_ = false;
-  std::string pending_header_;
-  bool   have_pending_ = false;
-  char   pending_kind_ = 0;
-  bool fill();
-  bool getline(std::string& line, bool append);
+  bool   eof_ = true, open_ = false;
+  char   kind_ = 0;                       // '>' or '@': format of the current file
+  unsigned threads_;
+  std::vector<piece> pieces_;
   bool open_next();
+  void close_current();
+  bool refill();                          // stream mode: more bytes behind the window; false at end of file
+  // scans one record starting at pos_; 1: done, 0: the window ends inside it (refill and try again), -1: end of file
+  int scan_record(read_batch& b, uint64_t& nbases);
 public:
-  explicit read_stream(const std::vector<std::string>& paths) : paths_(paths), buf_(1 << 22) { }
-  ~read_stream() { if(f_) fclose(f_); }
-  // appends reads until the batch holds >= max_bases bases or max_reads reads; false when exhausted
-  bool next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads);
+  explicit read_stream(const std::vector<std::string>& paths, unsigned threads = 0);
+  ~read_stream() { close_current(); }
+  read_stream(const read_stream&) = delete;
+  read_stream& operator=(const read_stream&) = delete;
+  // appends reads until the batch holds >= max_bases bases or max_reads reads; false when exhausted.
+  // with pack, the batch also comes out packed (read_batch::codes / nmask)
+  bool next_batch(read_batch& b, uint64_t max_bases, uint32_t max_reads, bool pack = false);
 };
 
 // ---- output text.  A batch of mega-read records is tens of megabytes that are written once and read

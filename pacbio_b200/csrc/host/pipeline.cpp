@@ -6,6 +6,9 @@
 #include <cstring>
 #include <map>
 #include <stdexcept>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cerrno>
 
 namespace mrh {
 
@@ -108,8 +111,53 @@ struct job {
 };
 }
 
+namespace {
+// Writes the text parts of one batch.  A regular file takes them through pwrite from one thread per part (each
+// call copies its part into the page cache: a single writer tops out near 2 GB/s, a fraction of what the
+// GPU produces); a pipe or terminal takes them in order through the stream.
+struct record_writer {
+  FILE* out;
+  int   fd = -1;
+  off_t at = 0;
+  explicit record_writer(FILE* f) : out(f) {
+    fflush(f);
+    struct stat st;
+    const int d = fileno(f);
+    if(d >= 0 && fstat(d, &st) == 0 && S_ISREG(st.st_mode)) {
+      const off_t cur = lseek(d, 0, SEEK_CUR);
+      if(cur >= 0) { fd = d; at = cur; }
+    }
+  }
+  bool write(const std::vector<text_buf>& parts) {
+    if(fd < 0) {
+      for(const auto& t : parts) if(!t.empty() && fwrite(t.data(), 1, t.size(), out) != t.size()) return false;
+      return true;
+    }
+    std::vector<off_t> where(parts.size());
+    for(size_t i = 0; i < parts.size(); ++i) { where[i] = at; at += (off_t)parts[i].size(); }
+    std::atomic<bool> ok(true);
+    auto put = [&](size_t i) {
+      const char* p = parts[i].data();
+      size_t left = parts[i].size();
+      off_t o = where[i];
+      while(left) {
+        const ssize_t w = pwrite(fd, p, left, o);
+        if(w < 0) { if(errno == EINTR) continue; ok = false; return; }
+        p += w; left -= (size_t)w; o += w;
+      }
+    };
+    std::vector<std::thread> th;
+    for(size_t i = 1; i < parts.size(); ++i) if(!parts[i].empty()) th.emplace_back(put, i);
+    if(!parts.empty() && !parts[0].empty()) put(0);
+    for(auto& t : th) t.join();
+    return ok;
+  }
+  void finish() { if(fd >= 0) lseek(fd, at, SEEK_SET); }       // the stream's position follows what was written
+};
+}
+
 uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,
-                      const format_fn& format, FILE* out) {
+                      const format_fn& format, FILE* out, unsigned host_threads) {
   uint64_t batch_bases = 32ULL << 20;
   if(const char* e = getenv("MR_BATCH_BASES")) batch_bases = strtoull(e, nullptr, 0);
   const uint32_t batch_reads = 1u << 20;
@@ -122,13 +170,13 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
 
   std::thread reader([&]() {
     try {
-      read_stream rs(read_paths);
+      read_stream rs(read_paths, host_threads);
       for(uint64_t seq = 0; ; ++seq) {
         job j;
         j.seq = seq;
         j.batch.reset(new read_batch);
         j.batch->clear();
-        if(!rs.next_batch(*j.batch, batch_bases, batch_reads)) break;
+        if(!rs.next_batch(*j.batch, batch_bases, batch_reads, true)) break;      // parsed and packed by the reader's workers
         total_bases += j.batch->bases.size();
         to_align.push(std::move(j));
       }
@@ -149,7 +197,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       while(to_align.pop(j)) {
         staged_job sj;
         sj.staged = nullptr;
-        j.batch->pack();                        // 2 bits per base + non-ACGT mask: what crosses PCIe
+        if(!j.batch->packed()) j.batch->pack();  // 2 bits per base + non-ACGT mask: what crosses PCIe
         if(stage_batches() && !failed && mr_stage_batch_packed(ds.ctx[g], j.batch->codes.data(), j.batch->nmask.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
         sj.j = std::move(j);
@@ -201,6 +249,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   std::thread formatter([&]() {
     job j;
     std::vector<text_buf> parts;
+    record_writer writer(out);
     std::map<uint64_t, job> waiting;           // aligned out of turn (several aligner threads)
     uint64_t next_seq = 0;
     while(to_format.pop(j)) {
@@ -211,14 +260,14 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           mr_result_get(pt.result, &v);
           for(auto& p : parts) p.clear();
           try { format(pt.result, v, *pt.batch, parts); } catch(std::exception& e) { fail(e.what()); }
-          for(const auto& text : parts)
-            if(!text.empty() && fwrite(text.data(), 1, text.size(), out) != text.size()) fail("write error on output file");
+          if(!writer.write(parts)) fail("write error on output file");
           mr_result_free(pt.result);
         }
         waiting.erase(it);
       }
     }
     for(auto& w : waiting) for(auto& pt : w.second.parts) mr_result_free(pt.result);   // only after an error
+    writer.finish();
   });
 
   reader.join();

@@ -75,7 +75,8 @@ void add_streams(device_set& ds, unsigned per_device);
 typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<text_buf>&)> format_fn;
 
 // runs the whole stream; returns the number of read bases processed
+// host_threads: workers of the reader (parsing, packing); 0 = as many as the box has, up to 16
 uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,
-                      const format_fn& format, FILE* out);
+                      const format_fn& format, FILE* out, unsigned host_threads = 0);
 
 } // namespace mrh

@@ -72,10 +72,10 @@ int64_t mrh_tool_load_reads(void* p, const char* path, uint64_t batch_bases, uin
       std::unique_ptr<mrh::read_batch> b(new mrh::read_batch);
       b->clear();
       const uint64_t left = max_reads ? max_reads - t->total_reads : (1u << 20);
-      if(!rs.next_batch(*b, batch_bases, (uint32_t)std::min<uint64_t>(left, 1u << 20))) break;
+      if(!rs.next_batch(*b, batch_bases, (uint32_t)std::min<uint64_t>(left, 1u << 20), true)) break;   // parsed and packed
       t->total_bases += b->bases.size();
       t->total_reads += b->nreads();
-      b->pack();                                    // the form the batch travels in (parsing + packing happen once, here)
+      if(!b->packed()) b->pack();                   // the form the batch travels in (parsing + packing happen once, here)
       mr_host_pin(t->DS.ctx[0], b->codes.data(), b->codes.size() * 8);
       mr_host_pin(t->DS.ctx[0], b->nmask.data(), b->nmask.size() * 8);
       t->batches.push_back(std::move(b));
@@ -218,6 +218,39 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
 }
 int64_t mrh_tool_run(void* p, unsigned threads, const char* out_path) {
   return mrh_tool_run_range(p, threads, out_path, 0, ~0ULL);
+}
+// Parses read files the way the tools do and returns what came out, for tests that have no GPU: out6 = { reads, bases,
+// FNV-1a of the bases, FNV-1a of the names (each followed by a newline), FNV-1a of the packed code words covering the
+// bases, number of non-ACGT characters according to the mask }.  Returns 0, or -1 with the message in err.
+int mrh_selftest_read_stream(const char* const* paths, unsigned npaths, uint64_t batch_bases, unsigned threads, uint64_t* out6,
+                             char* err, size_t err_cap) {
+  try {
+    std::vector<std::string> ps(paths, paths + npaths);
+    mrh::read_stream rs(ps, threads);
+    uint64_t h_bases = 1469598103934665603ULL, h_names = h_bases, h_codes = h_bases, reads = 0, bases = 0, nonacgt = 0;
+    auto fnv = [](uint64_t h, const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for(size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; } return h; };
+    while(true) {
+      mrh::read_batch b;
+      b.clear();
+      if(!rs.next_batch(b, batch_bases, 1u << 20, true)) break;
+      reads += b.nreads(); bases += b.bases.size();
+      h_bases = fnv(h_bases, b.bases.data(), b.bases.size());
+      for(const auto& n : b.name) { h_names = fnv(h_names, n.data(), n.size()); h_names = fnv(h_names, "\n", 1); }
+      for(uint64_t g = 0; g < b.bases.size(); ++g) {          // the packed form, base by base (independent of batch cuts)
+        const unsigned char code = (unsigned char)((b.codes[g >> 5] >> (2 * (g & 31))) & 3);
+        const unsigned char bad = (unsigned char)((b.nmask[g >> 6] >> (g & 63)) & 1);
+        const unsigned char both = (unsigned char)(code | (bad << 2));
+        h_codes = fnv(h_codes, &both, 1);
+        nonacgt += bad;
+      }
+      if(b.start.size() != (size_t)b.nreads() + 1 || b.start.back() != b.bases.size()) throw std::runtime_error("inconsistent batch");
+    }
+    out6[0] = reads; out6[1] = bases; out6[2] = h_bases; out6[3] = h_names; out6[4] = h_codes; out6[5] = nonacgt;
+    return 0;
+  } catch(std::exception& e) {
+    if(err && err_cap) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+    return -1;
+  }
 }
 uint64_t mrh_selftest_fixed_format(uint64_t samples, uint64_t seed) { return mrh::selftest_fixed_format(samples, seed); }
 void mrh_tool_stage_seconds(void* p, double* align_s, double* format_s) {

@@ -299,9 +299,11 @@ int radix_pass(mr_context* ctx, const K* kin, const V* vin, K* kout, V* vout, ui
   return MR_OK;
 }
 
-// MR_SORT_EVEN_DIGITS=0: digits of 8 bits, the last one shorter (A/B switch)
+// MR_SORT_EVEN_DIGITS=1: equal digits (14 bits as 7 + 7 instead of 8 + 6).  Measured on B200: group sort 13.9 -> 14.9 ms
+// per step on the yeast shape, 446 -> 462 on the human shape -- the shorter runs of 256 buckets cost less than
+// the second pass gains from having only 64 -- so the default is digits of 8 bits, the last one shorter.
 inline bool sort_even_digits() {
-  static const bool v = [] { const char* e = getenv("MR_SORT_EVEN_DIGITS"); return !(e && atoi(e) == 0); }();
+  static const bool v = [] { const char* e = getenv("MR_SORT_EVEN_DIGITS"); return e && atoi(e) == 1; }();
   return v;
 }
 

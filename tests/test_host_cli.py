@@ -254,3 +254,70 @@ def test_pack_reads_layout():
         # nothing set past the last base
         for g in range(n, min(len(nmask) * 64, len(codes) * 32, n + 200)):
             assert (int(nmask[g // 64]) >> (g % 64)) & 1 == 0 and (int(codes[g // 32]) >> (2 * (g % 32))) & 3 == 0
+
+
+def _fnv(h, data):
+    for x in data:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_read_stream_parses_fasta_fastq_files_and_pipes(tmp_path):
+    """The tools' reader (mapped files scanned in place, pipes in chunks; sequence pieces copied and packed by worker
+    threads) against a plain Python parse: FASTA single- and multi-line, FASTQ, CRLF, empty lines, a last line
+    without terminator, lower case and N, several files in one stream of batches, small and large batch sizes."""
+    import ctypes as C
+    import random
+    rnd = random.Random(5)
+    H = C.CDLL(os.path.join(ROOT, "pacbio_b200", "libmegareads_host.so"))
+    H.mrh_selftest_read_stream.argtypes = [C.POINTER(C.c_char_p), C.c_uint, C.c_uint64, C.c_uint, C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+    recs = [("r%d/x_%d some comment" % (i, i * 7), "".join(rnd.choice("ACGTACGTacgtN") for _ in range(rnd.choice([0, 1, 63, 64, 65, 500, 3000, 12001]))))
+            for i in range(60)]
+    fa1, fa2, fq = str(tmp_path / "a.fa"), str(tmp_path / "b.fa"), str(tmp_path / "c.fq")
+    with open(fa1, "w", newline="") as f:                  # one line per sequence, CRLF on some lines
+        for i, (n, s) in enumerate(recs[:20]):
+            f.write(">%s%s" % (n, "\r\n" if i % 3 == 0 else "\n"))
+            f.write(s + ("\r\n" if i % 3 == 0 else "\n"))
+    with open(fa2, "w") as f:                               # 61 columns, empty lines, no final newline
+        for n, s in recs[20:40]:
+            f.write(">%s\n" % n)
+            for i in range(0, len(s), 61):
+                f.write(s[i:i + 61] + "\n")
+            f.write("\n")
+        f.write(">last\nACGTNACGT")
+    with open(fq, "w") as f:
+        for n, s in recs[40:]:
+            f.write("@%s\n" % n)
+            half = len(s) // 2
+            f.write(s[:half] + "\n" + s[half:] + "\n+\n" + "I" * half + "\n" + "+" * (len(s) - half) + "\n")
+    all_recs = recs[:40] + [("last", "ACGTNACGT")] + recs[40:]
+    want_bases = "".join(s for _, s in all_recs).encode()
+    want_names = "".join(n.split()[0] + "\n" for n, _ in all_recs).encode()
+    code = {ord(c): v for c, v in zip("ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3])}
+    h0 = 1469598103934665603
+    want = [len(all_recs), len(want_bases), _fnv(h0, want_bases), _fnv(h0, want_names),
+            _fnv(h0, bytes(code.get(x, 4) for x in want_bases)), sum(1 for x in want_bases if x not in code)]
+
+    def parse(paths, batch, threads):
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        out = (C.c_uint64 * 6)()
+        err = C.create_string_buffer(300)
+        rc = H.mrh_selftest_read_stream(arr, len(paths), batch, threads, out, err, 300)
+        assert rc == 0, err.value
+        return list(out)
+
+    for batch, threads in ((1 << 30, 4), (5000, 3), (1, 1), (40000, 8)):
+        assert parse([fa1, fa2, fq], batch, threads) == want
+    # the same bytes through a pipe (stream mode: no mmap, no seek)
+    fifo = str(tmp_path / "pipe.fa")
+    os.mkfifo(fifo)
+    cat = subprocess.Popen("cat %s %s > %s" % (fa1, fa2, fifo), shell=True)
+    got = parse([fifo, fq], 7000, 4)
+    cat.wait()
+    # fa1 + fa2 concatenated: fa1 ends with a newline, so the records are the same
+    assert got == want
+    bad = str(tmp_path / "bad.txt")
+    open(bad, "w").write("not a sequence file\n")
+    arr = (C.c_char_p * 1)(bad.encode())
+    err = C.create_string_buffer(300)
+    assert H.mrh_selftest_read_stream(arr, 1, 1000, 1, (C.c_uint64 * 6)(), err, 300) == -1 and b"Unsupported format" in err.value

@@ -177,7 +177,7 @@ bool sr_index::locate(uint64_t x, uint32_t& sr, int32_t& off) const {
 }
 
 // ===========================================================================
-// chaining  (reference: src_lis/lis_align.hpp:139-204, window_size == 1)
+// chaining  (reference: src_lis/lis_align.hpp:139-204; the window of lis_align.hpp:17-45 as a ring per list element)
 // ===========================================================================
 // ORACLE_CHAIN_STATS=1: totals of the list walk (printed at exit), used to size the device kernels
 namespace {
@@ -192,7 +192,64 @@ struct chain_stats_t {
 } chain_stats;
 }
 
-std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, double b, double C) {
+// window > 1 (lis_align.hpp:17-45,162-163): restated literally -- every list element carries the last `window` steps
+// of its chain in a ring with a running sum; the mer predicate sees that sum plus the new step (minus the step that
+// falls out of a full ring) and is only applied when the ring will be full with the new step.
+static std::vector<uint32_t> chain_window(const std::vector<std::pair<int,int>>& X, double a, double b, double C, uint32_t W) {
+  struct ring {
+    std::vector<std::pair<double,double>> v; size_t next = 0; bool filled = false; double s1 = 0, s2 = 0;
+    explicit ring(size_t n) : v(n, std::make_pair(0.0, 0.0)) { }
+    bool will_be_filled() const { return filled || next == v.size() - 1; }
+    std::pair<double,double> test_sum(double d1, double d2) const {
+      double r1 = s1 + d1, r2 = s2 + d2;
+      if(filled || next > 0) { r1 -= v[next].first; r2 -= v[next].second; }
+      return std::make_pair(r1, r2);
+    }
+    void push(double d1, double d2) {
+      const auto t = test_sum(d1, d2);
+      s1 = t.first; s2 = t.second;
+      v[next] = std::make_pair(d1, d2);
+      next = (next + 1) % v.size();
+      filled = filled || next == 0;
+    }
+  };
+  struct elt { uint32_t idx, len; ring win; double span_pb, span_sr; };
+  const uint32_t N = X.size();
+  std::vector<elt>      L;
+  std::vector<uint32_t> P(N, N);
+  uint32_t longest = 0, best = 0;
+  for(uint32_t i = 0; i < N; ++i) {
+    elt e = { i, 1, ring(W), 0.0, 0.0 };
+    int prev = -1;
+    for(size_t p = 0; p < L.size(); ++p) {
+      const uint32_t j = L[p].idx;
+      if(X[i].second > X[j].second) {
+        const double d1 = X[i].first - X[j].first, d2 = X[i].second - X[j].second;
+        const auto ns = L[p].win.test_sum(d1, d2);
+        const double t1 = a * ns.second, t2 = a * ns.first;
+        if(!L[p].win.will_be_filled() || (ns.first <= b + t1 && ns.second <= b + t2 && ns.first <= C && ns.second <= C)) {
+          e.len = L[p].len + 1;
+          P[i]  = j;
+          e.win = L[p].win;
+          e.win.push(d1, d2);
+          e.span_pb = L[p].span_pb + d1;
+          e.span_sr = L[p].span_sr + d2;
+          break;
+        }
+      }
+      if(prev < 0 || L[p].len < L[prev].len) prev = p;
+    }
+    L.insert(L.begin() + (prev + 1), e);
+    const double s1 = a * e.span_sr, s2 = a * e.span_pb;
+    if(longest < e.len && e.span_pb <= s1 && e.span_sr <= s2) { longest = e.len; best = i; }
+  }
+  std::vector<uint32_t> res(longest);
+  for(uint32_t t = 0, cur = best; t < longest; ++t, cur = P[cur]) res[longest - 1 - t] = cur;
+  return res;
+}
+
+std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, double b, double C, uint32_t window) {
+  if(window != 1) return chain_window(X, a, b, C, window);
   struct elt { uint32_t idx, len; double span_pb, span_sr; };
   const uint32_t N = X.size();
   uint64_t st_front = 0, st_steps = 0, st_none = 0, st_none_steps = 0, st_depth = 0;
@@ -506,12 +563,12 @@ static void discard_lis(off_lis& l) {                     // pb_aligner.hpp:47-6
 void align_read(const sr_index& idx, const std::string& read, const params& p,
                 const std::vector<int>* unitigs_lengths,
                 std::vector<mer_lists>& groups, std::vector<coords>& out) {
-  if(p.window_size != 1) throw std::runtime_error("oracle port: window-size != 1 not restated");
+  if(p.window_size < 1) throw std::runtime_error("oracle port: window-size must be at least 1");
   fetch_super_reads(idx, read, p.max_count, groups);
   out.clear();
   for(auto& ml : groups) {                                // coarse_aligner.cc:42-60
-    ml.fwd.lis = chain(ml.fwd.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap);
-    ml.bwd.lis = chain(ml.bwd.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap);
+    ml.fwd.lis = chain(ml.fwd.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap, p.window_size);
+    ml.bwd.lis = chain(ml.bwd.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap, p.window_size);
     while(true) {
       coords c = compute_coords_info(idx, ml, read.size(), p, unitigs_lengths);
       if(c.nb_mers == 0) break;
@@ -524,7 +581,7 @@ void align_read(const sr_index& idx, const std::string& read, const params& p,
       if(!p.max_match) break;
       off_lis& l = ml.fwd.lis.size() > ml.bwd.lis.size() ? ml.fwd : ml.bwd;   // pb_aligner.hpp:87-92
       discard_lis(l);
-      l.lis = chain(l.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap);
+      l.lis = chain(l.offsets, p.stretch_factor, p.stretch_constant, p.stretch_cap, p.window_size);
     }
   }
   // create_mega_reads.cc:69-77 sorts (unstably) by (rs, re, ql); ties are broken here by

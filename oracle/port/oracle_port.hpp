@@ -93,7 +93,7 @@ struct coords {
 };
 
 // chaining; lis_align.hpp:139-204 (window_size == 1 only)
-std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, double b, double C);
+std::vector<uint32_t> chain(const std::vector<std::pair<int,int>>& X, double a, double b, double C, uint32_t window = 1);
 
 // coarse_aligner.cc:81-141; groups are returned in increasing super-read index
 void fetch_super_reads(const sr_index& idx, const std::string& read, int max_count, std::vector<mer_lists>& groups);

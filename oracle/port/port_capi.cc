@@ -93,10 +93,10 @@ void op_index_search(void* p, const uint64_t* mers, uint64_t q, uint64_t* index_
   for(uint64_t i = 0; i < q; ++i) idx.search(mers[i], index_out[i], nb_out[i]);
 }
 uint32_t op_lis(const int32_t* pairs, uint32_t n, double a, double b, double C, uint32_t window, uint32_t* out) {
-  if(window != 1) return UINT32_MAX;
+  if(window < 1) return UINT32_MAX;
   std::vector<std::pair<int,int>> X(n);
   for(uint32_t i = 0; i < n; ++i) X[i] = std::make_pair(pairs[2 * i], pairs[2 * i + 1]);
-  const auto res = chain(X, a, b, C);
+  const auto res = chain(X, a, b, C, window);
   for(size_t i = 0; i < res.size(); ++i) out[i] = res[i];
   return res.size();
 }

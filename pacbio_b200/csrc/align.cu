@@ -1298,6 +1298,11 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       A.cb.Lelt = (uint32_t*)(c + (H + 2) * 12);
       A.cb.pprev = (uint32_t*)alt_pay; A.cb.cstart = (uint32_t*)alt_pay + (H + 2);
     }
+    A.window = p->window_size;
+    if(p->window_size > 1) {
+      MR_TRY(ws.chainW.ensure(ctx, (H + 2) * 8));
+      A.cb.Lwpb = ws.chainW.as<int32_t>(); A.cb.Lwsr = ws.chainW.as<int32_t>() + (H + 2);
+    }
     A.a = p->stretch_factor; A.b = p->stretch_constant; A.C = p->stretch_cap;
     A.matching_mers = p->matching_mers; A.matching_bases = p->matching_bases; A.forward = p->forward;
     A.unitigs_k = idx->has_unitigs ? p->unitigs_k : 0; A.n_unitigs = idx->n_unitigs;
@@ -1430,7 +1435,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     F.a = -1.0; F.b = 0.0; F.C = -1.0;                    // lis_align::accept_all
     F.matching_mers = 0.0; F.matching_bases = 0.0; F.forward = 1; F.no_filter = 1; F.align_k = kk;
     F.group_read = fb.gread.as<uint32_t>(); F.group_sr = fb.gsr.as<uint32_t>(); F.group_iter = fb.giter.as<uint32_t>();
-    F.max_match = 0; F.removed = nullptr;
+    F.max_match = 0; F.removed = nullptr; F.window = 1;            // accept-all predicates: a window changes nothing
     F.tap_lens = nullptr; F.tap_cf = nullptr; F.tap_cb = nullptr; F.tap_sub = nullptr;
     MR_CUDA(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(uint64_t), st));
     MR_CUDA(ctx, cudaMemsetAsync(ws.read_cnt.p, 0, ((size_t)nreads + 2) * 4, st));
@@ -1558,7 +1563,7 @@ static int align_checked(mr_context* ctx, mr_index* idx, const mr_params* p, con
   if(!idx || !p || !out || !h_read_start || !d_read_start) return ctx->fail(MR_EINVAL, "mr_align_batch: null argument");
   // an index is read-only once built: any context of its device may align against it
   if(idx->ctx->device != ctx->device) return ctx->fail(MR_EINVAL, "mr_align_batch: index lives on another device");
-  if(p->window_size != 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size other than 1 is not implemented");
+  if(p->window_size < 1) return ctx->fail(MR_EINVAL, "mr_align_batch: --window-size must be at least 1");
   if(p->max_match && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with --max-match");
   if(p->fine_mer && ctx->keep_taps) return ctx->fail(MR_EINVAL, "mr_align_batch: parity taps are not available with a fine pass");
   if(p->fine_mer && (p->fine_mer < idx->m || p->fine_mer > idx->k))

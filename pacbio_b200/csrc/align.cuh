@@ -59,7 +59,7 @@ struct mr_workspace {
   dev_buf kinfo, binfo;
   dev_buf node_i32, node_u8, node_f64;
   dev_buf node_path, edge_cnt, edge_off, edges, path_i32, path_f64, path_u8;   // overlap graph of reads with many rows (graph.cu)
-  dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay, removed;
+  dev_buf tap_lens, tap_cf, tap_cb, group_lists, chain_pay, removed, chainW;
   dev_buf scan_scratch;
   prim::sort_scratch sort;
   std::vector<pinned_buf*> pinned_pool;     // result slabs are recycled: cudaMallocHost costs milliseconds
@@ -83,6 +83,7 @@ struct mr_result {
 struct chain_buffers {
   int32_t*  Lpb;  int32_t* Lsr;  uint32_t* Llen;  uint32_t* Lelt;   // indexed gs + array slot (global-memory tier)
   uint32_t* pprev; uint32_t* cstart;                                  // indexed gs + element
+  int32_t*  Lwpb; int32_t* Lwsr;                                      // --window-size > 1: the window's base per list entry
 };
 
 struct survivors {
@@ -120,6 +121,7 @@ struct chain_args {
   int no_filter;                     // every group yields a row
   const uint32_t *group_read, *group_sr, *group_iter;   // identity of group g when not taken from keys[]
   uint32_t* dbg_cycles;              // MR_TRACE: SM cycles spent chaining each group
+  uint32_t window;                   // --window-size (lis_align.hpp:17-45): 1 for every pipeline script
 };
 int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists);
 

@@ -234,10 +234,19 @@ __device__ __forceinline__ void chain_strand_smem(const uint64_t* __restrict__ p
 // ---------------------------------------------------------------------------------------------
 // global-memory strand (groups larger than the shared-memory tiers)
 // ---------------------------------------------------------------------------------------------
+// window > 1 (--window-size, lis_align.hpp:17-45,162-163): the mer predicate applies to the sum of the last `window`
+// steps of a chain and only once the chain has that many.  That sum is X[i] - X[w], w the element `window` steps
+// back from i -- the (window-1)-th ancestor of the list element the new hit would extend -- so a list entry
+// carries the coordinates of that ancestor (Lwpb / Lwsr; kNoWindow while its chain is too short to be tested)
+// next to its own, which the increasing test still uses.  The shared-memory kernels implement window 1 only;
+// with a larger window every group comes here.
+constexpr int32_t kNoWindow = (int32_t)0x80000000;
 __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N, bool neg, const chain_buffers& cb, uint64_t gs,
                                     double a, double b, double C, uint32_t& longest_out, uint32_t& best_out, uint32_t* tap_sub,
-                                    const uint8_t* removed = nullptr) {
+                                    const uint8_t* removed = nullptr, uint32_t window = 1) {
   const unsigned lane = threadIdx.x & 31;
+  const bool win = window > 1;
+  int32_t*  Lwpb = win ? cb.Lwpb + gs : nullptr; int32_t* Lwsr = win ? cb.Lwsr + gs : nullptr;
   int32_t*  Lpb  = cb.Lpb + gs;  int32_t* Lsr = cb.Lsr + gs;
   uint32_t* Llen = cb.Llen + gs; uint32_t* Lelt = cb.Lelt + gs;
   uint32_t* pprev = cb.pprev + gs; uint32_t* cstart = cb.cstart + gs;
@@ -262,7 +271,12 @@ __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N
         const uint32_t slot = cnt - 1 - p;
         int32_t lsr = 0, lpb = 0; uint32_t llen = 0, lelt = 0;
         if(in) { lsr = Lsr[slot]; lpb = Lpb[slot]; llen = Llen[slot]; lelt = Lelt[slot]; }
-        const bool feas = in && sr_i > lsr && accept_mer(pb_i, sr_i, lpb, lsr, a, b, C);
+        bool ok_mer;
+        if(win) {
+          const int32_t wsr = in ? Lwsr[slot] : kNoWindow;
+          ok_mer = wsr == kNoWindow || accept_mer(pb_i, sr_i, Lwpb[slot], wsr, a, b, C);
+        } else ok_mer = accept_mer(pb_i, sr_i, lpb, lsr, a, b, C);
+        const bool feas = in && sr_i > lsr && ok_mer;
         const unsigned ball = __ballot_sync(MR_FULL_MASK, feas);
         const unsigned limit = ball ? (unsigned)(__ffs(ball) - 1) : 32u;
         // len can exceed 27 bits only for groups of > 2^27 hits, which the batch limits exclude
@@ -284,14 +298,29 @@ __device__ void chain_strand_global(const uint64_t* __restrict__ pay, uint32_t N
         const uint32_t lo = (top - (cnt - q)) > 32 ? top - 32 : cnt - q;
         const uint32_t s = lo + lane;
         const bool has = s < top;
-        int32_t v0 = 0, v1 = 0; uint32_t v2 = 0, v3 = 0;
-        if(has) { v0 = Lpb[s]; v1 = Lsr[s]; v2 = Llen[s]; v3 = Lelt[s]; }
+        int32_t v0 = 0, v1 = 0, v4 = 0, v5 = 0; uint32_t v2 = 0, v3 = 0;
+        if(has) { v0 = Lpb[s]; v1 = Lsr[s]; v2 = Llen[s]; v3 = Lelt[s]; if(win) { v4 = Lwpb[s]; v5 = Lwsr[s]; } }
         __syncwarp();
-        if(has) { Lpb[s + 1] = v0; Lsr[s + 1] = v1; Llen[s + 1] = v2; Lelt[s + 1] = v3; }
+        if(has) { Lpb[s + 1] = v0; Lsr[s + 1] = v1; Llen[s + 1] = v2; Lelt[s + 1] = v3; if(win) { Lwpb[s + 1] = v4; Lwsr[s + 1] = v5; } }
         __syncwarp();
         top = lo;
       }
-      if(lane == 0) { const uint32_t s = cnt - q; Lpb[s] = pb_i; Lsr[s] = sr_i; Llen[s] = e_len; Lelt[s] = i; }
+      if(lane == 0) {
+        const uint32_t s = cnt - q;
+        Lpb[s] = pb_i; Lsr[s] = sr_i; Llen[s] = e_len; Lelt[s] = i;
+        if(win) {
+          // what a hit extending this element will be tested against: the element window - 1 links back, once
+          // the chain is long enough for its window to fill
+          int32_t wpb = 0, wsr = kNoWindow;
+          if(e_len >= window) {
+            uint32_t w = i;
+            for(uint32_t t = 1; t < window; ++t) w = pprev[w];
+            const uint64_t pw = pay[w];
+            wpb = (int32_t)(uint32_t)pw; wsr = (int32_t)(uint32_t)(pw >> 32);
+          }
+          Lwpb[s] = wpb; Lwsr[s] = wsr;
+        }
+      }
       ++cnt;
       __syncwarp();
       if(longest < e_len) {
@@ -527,7 +556,7 @@ constexpr uint32_t kTinyMax = 8;
 // hit 0, which this kernel records directly.
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
                                                                const uint64_t* __restrict__ pays, uint64_t* __restrict__ chain_pay,
-                                                               uint32_t* __restrict__ group_nb, bool singles_here,
+                                                               uint32_t* __restrict__ group_nb, bool singles_here, bool all_global,
                                                                uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
   // (singles_here is false with parity taps or --max-match on: then every group goes to the strand kernels)
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,7 +575,8 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
       const uint64_t p = pays[gs];
       chain_pay[gs] = p;
       group_nb[g] = 1u | ((int32_t)(uint32_t)(p >> 32) > 0 ? 0x80000000u : 0u);
-    } else if(n <= kTinyMax && singles_here) cls = kClasses;
+    } else if(all_global) cls = kSmemTiers;      // --window-size > 1: only the global-memory kernel implements it
+    else if(n <= kTinyMax && singles_here) cls = kClasses;
   }
   const unsigned lane = threadIdx.x & 31;
 #pragma unroll
@@ -676,9 +706,9 @@ __global__ void __launch_bounds__(128) chain_coords_global_kernel(chain_args A, 
     const uint64_t gs = A.group_start[g];
     const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
     uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0;
-    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub);
+    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, A.tap_sub, nullptr, A.window);
     __syncwarp();
-    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, A.tap_sub);
+    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, A.tap_sub, nullptr, A.window);
     __syncwarp();
     const bool fwd_align = len_f >= len_b;
     const uint32_t nb = fwd_align ? len_f : len_b;
@@ -844,9 +874,9 @@ __global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8
     for(uint32_t t = lane; t < N; t += 32) rem[t] = 0;
     __syncwarp();
     uint32_t len_f = 0, best_f = 0, len_b = 0, best_b = 0, used = 0;
-    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem);
+    chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem, A.window);
     __syncwarp();
-    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem);
+    chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem, A.window);
     __syncwarp();
     uint32_t* pprev = A.cb.pprev + gs;
     uint32_t* chain = A.cb.Lelt + gs;            // L is dead between chainings
@@ -871,8 +901,8 @@ __global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8
         for(uint32_t t = 0; t < dn; ++t) { rem[cur] = 1; cur = pprev[cur]; }
       }
       __syncwarp();
-      if(drop_fwd) chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem);
-      else         chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem);
+      if(drop_fwd) chain_strand_global(A.pays + gs, N, false, A.cb, gs, A.a, A.b, A.C, len_f, best_f, nullptr, rem, A.window);
+      else         chain_strand_global(A.pays + gs, N, true, A.cb, gs, A.a, A.b, A.C, len_b, best_b, nullptr, rem, A.window);
       __syncwarp();
     }
   }
@@ -946,7 +976,7 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(g_chain_trace) { cudaStreamSynchronize(ctx->stream); g_trace_t0 = trace_now(); }
   // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
   classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb,
-                                                                  A.tap_lens == nullptr && !A.max_match, cls, ctr);
+                                                                  A.tap_lens == nullptr && !A.max_match, A.window > 1, cls, ctr);
   MR_LAUNCHED(ctx);
   CHAIN_TRACE(ctx->stream, "classify");
   if(A.max_match) {

@@ -107,7 +107,7 @@ int main(int argc, char* argv[]) {
   if(!k_given) error("[-k, --k-mer=uint32] required switch");
   if(l_given && u_given) error("Switches [-u, --unitigs-sequences=path] and [-l, --unitigs-lengths=path] are mutually exclusive");
   if(argc - optind != 0) error("Requires exactly 0 argument.");
-  if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
+  if(P.window_size < 1) error("[--window-size] must be at least 1");
 
   try {
     // open the output first, for early error reporting (create_mega_reads.cc:101-107)

@@ -79,7 +79,7 @@ int main(int argc, char* argv[]) {
   if(!details_given && !coords_given) error("No output file given. Doing nothing ungracefully.");
   if(details_given && P.max_match) error("[--details] is not available together with --max-match in this build");
   if(details_given && P.fine_mer) error("[--details] is not available together with -F in this build");
-  if(P.window_size != 1) error("[--window-size] only a window of 1 is implemented in this build");
+  if(P.window_size < 1) error("[--window-size] must be at least 1");
   if((l_given || u_given) && !k_given)
     error("The mer length used for generating the k-unitigs (-k, --k-mer) is required if the unitig lengths (-l, --unitig-lengths or -u, --unitigs-sequences) is passed.");
 

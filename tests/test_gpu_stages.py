@@ -187,8 +187,10 @@ def _canon(cint, cdbl, info_off, kinfo, binfo):
     return rows
 
 
-@pytest.mark.parametrize("forward", [True, False])
-def test_align_stages_match_oracle(case, ctx, port, forward):
+@pytest.mark.parametrize("forward,window", [(True, 1), (False, 1), (True, 3), (False, 2)])
+def test_align_stages_match_oracle(case, ctx, port, forward, window):
+    """hit lists, both chains and coords rows of every (read, super-read) pair against the oracle port; window > 1 is
+    --window-size (lis_align.hpp:17-45,162-163: the mer predicate on the sum of the last `window` steps)"""
     import pacbio_b200 as pb
     c = case["cfg"]
     reads = pb.Reads(case["info"]["reads"])
@@ -206,11 +208,11 @@ def test_align_stages_match_oracle(case, ctx, port, forward):
     seqs.append(longest[:min(len(longest), 6000)])          # one chain of thousands of hits
     sub = pb.Reads(names=["r%d" % i for i in range(len(seqs))], seqs=seqs)
     uk = c["uk"] if forward else 0
-    p = pb.default_params(unitigs_k=uk, run_graph=0, forward=int(forward))
+    p = pb.default_params(unitigs_k=uk, run_graph=0, forward=int(forward), window_size=window)
     ctx.keep_taps(True)
     res = ctx.align(case["idx"], sub, p)
     ctx.keep_taps(False)
-    ap = port.aligner_create(case["hp"], unitigs_k=uk, forward=forward)
+    ap = port.aligner_create(case["hp"], unitigs_k=uk, forward=forward, window_size=window)
     total_coords = 0
     for r, s in enumerate(seqs):
         o = port.align_read(ap, s)

@@ -171,3 +171,5 @@ def test_lis_random_vs_live_reference(port, ref):
         sr = rng.integers(1, 400, size=n) if t % 3 else pb + rng.integers(-30, 30, size=n)
         pairs = np.stack([pb, sr], axis=1)
         assert port.lis(pairs).tolist() == ref.lis(pairs).tolist()
+        for window in (2, 3, 5):                        # --window-size (lis_align.hpp:17-45): the port's ring restatement
+            assert port.lis(pairs, window=window).tolist() == ref.lis(pairs, window=window).tolist(), (t, window)

@@ -37,7 +37,7 @@ int main(int argc, char* argv[]) {
   using namespace cmdline;
   bool size_given = false, mer_given = false, k_given = false, l_given = false, u_given = false;
   uint32_t mer = 0, psa_min = 13, k_mer = 0, threads = 1;
-  std::string unitigs_lengths, unitigs_sequences, output;
+  std::string unitigs_lengths, unitigs_sequences, output, dot_path;
   mr_params P;
   mr_params_default(&P);
   double bases_matching = 17.0, mers_matching = 0.0;
@@ -74,7 +74,7 @@ int main(int argc, char* argv[]) {
     case 'k': k_given = true; k_mer = to_uint32(optarg, "-k, --k-mer=uint32"); break;
     case 't': threads = to_uint32(optarg, "-t, --threads=uint32"); break;
     case 'o': output = optarg; break;
-    case O_DOT: error("[--dot] writing the overlap graph is not implemented in this build");
+    case O_DOT: dot_path = optarg; break;
     case O_SC: P.stretch_constant = (double)to_int(optarg, "--stretch-constant=int"); break;
     case O_SF: P.stretch_factor = to_double(optarg, "--stretch-factor=double"); break;
     case O_SCAP: P.stretch_cap = to_double(optarg, "--stretch-cap=double"); break;
@@ -142,10 +142,22 @@ int main(int argc, char* argv[]) {
     P.run_graph = 1;
     G.k_len = k_mer;
     const unsigned fthreads = std::max(1u, threads);
+    // --dot: the overlap graph of every read (overlap_graph.hpp:189-196); written by this one formatter thread, in read
+    // order, which is what the reference gives with -t 1
+    FILE* dot_file = nullptr;
+    if(!dot_path.empty() && !(dot_file = fopen(dot_path.c_str(), "w"))) throw std::runtime_error("Failed to open file '" + dot_path + "'");
+    mrh::dot_state dstate;
+    dstate.errors = P.errors; dstate.bases = P.bases;
+    mrh::text_buf dot_text;
     const uint64_t nb = mrh::run_pipeline(DS, pacbio, P,
       [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<mrh::text_buf>& parts) {
-        mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts);
+        if(!dot_file) { mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts); return; }
+        parts.resize(1);
+        parts[0].clear(); dot_text.clear();
+        mrh::format_mega_reads(v, b, 0, v.nreads, SR, U, G, parts[0], &dot_text, &dstate);
+        if(fwrite(dot_text.data(), 1, dot_text.size(), dot_file) != dot_text.size()) throw std::runtime_error("write error on the --dot file");
       }, out, fthreads);
+    if(dot_file && fclose(dot_file) != 0) throw std::runtime_error("write error on the --dot file");
     const auto t2 = std::chrono::steady_clock::now();
     if(show_timing) std::cerr << "Starting create mega reads ... " << std::chrono::duration<double>(t2 - t1).count()
                               << " (" << nb << " bases)\n";

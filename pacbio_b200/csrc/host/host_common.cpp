@@ -453,8 +453,83 @@ uint64_t selftest_fixed_format(uint64_t samples, uint64_t seed) {
   return bad;
 }
 
+namespace {
+// --dot, first half of a read's graph: header, node tooltips in node order, and the overlap edges in the order
+// overlap_graph::traverse finds them (overlap_graph.cc:7-59, with the edge test redone on the host)
+void dot_open_read(const mr_result_view& v, const read_batch& batch, uint32_t r, const super_reads& sr, const unitigs& u,
+                   const graph_options& o, const dot_state& ds, text_buf& dot) {
+  char buf[160];
+  const uint64_t b = v.read_coords[r];
+  const int n = (int)(v.read_coords[r + 1] - b);
+  dot += "digraph \""; dot += batch.name[r]; dot += "\" {\nnode [fontsize=\"10\"];\n";
+  if(n == 0) return;
+  const double rl = (double)(batch.start[r + 1] - batch.start[r]), K = o.k_len;
+  std::vector<double> imp_s(n), imp_e(n);
+  std::vector<int> order(n);
+  for(int i = 0; i < n; ++i) {
+    const uint64_t row = b + i;
+    imp_s[i] = v.stretch[row] + v.offset[row];
+    const double t = v.stretch[row] * (double)v.ql[row];
+    imp_e[i] = t + v.offset[row];
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return imp_s[x] < imp_s[y] || (imp_s[x] == imp_s[y] && imp_e[x] < imp_e[y]); });
+  for(int a = 0; a < n; ++a) {
+    snprintf(buf, sizeof buf, "n%d[tooltip=\"", order[a]);
+    dot += buf; dot += sr.row_name(v.sr[b + order[a]], v.use_bwd[b + order[a]]); dot += "\"];\n";
+  }
+  auto path_len = [&](uint64_t row) { return sr.path_len(v.sr[row]); };
+  auto path_at = [&](uint64_t row, uint32_t t) { return sr.path_at(v.sr[row], v.use_bwd[row], t); };
+  for(int a = 0; a < n; ++a) {
+    const int ii = order[a];
+    const uint64_t ri = b + ii;
+    if(imp_e[ii] >= rl) continue;
+    const uint32_t ln = path_len(ri);
+    for(int bb = a + 1; bb < n; ++bb) {
+      const int jj = order[bb];
+      const uint64_t rj = b + jj;
+      if(imp_s[jj] <= 1 || imp_e[ii] > imp_e[jj] + 31) continue;
+      const double position_len = imp_e[ii] - imp_s[jj];
+      const double error1 = v.avg_err[ri] + v.avg_err[rj];
+      const double error = ds.errors * error1;
+      const double ppl = position_len * o.overlap_play;
+      if(ppl + error < K) break;
+      const uint32_t rn = path_len(rj);
+      int nb_u = 0;                                       // super_read_name::overlap (super_read_name.cc:49-72)
+      if(ln >= 2 && rn >= 2) {
+        for(uint32_t i = (uint32_t)std::max<int64_t>(1, (int64_t)ln - (int64_t)rn + 1); i < ln && !nb_u; ++i) {
+          if(path_at(ri, i) != path_at(rj, 0)) continue;
+          uint32_t j = i + 1;
+          while(j < ln && path_at(ri, j) == path_at(rj, j - i)) ++j;
+          if(j == ln) nb_u = (int)(ln - i);
+        }
+      }
+      if(!nb_u) continue;
+      bool same = ln == rn;
+      for(uint32_t t = 0; same && t < ln; ++t) same = path_at(ri, t) == path_at(rj, t);
+      if(same) continue;
+      int u_len = 0, common = 0;
+      const uint32_t ilen = v.info_len[rj];
+      const int32_t* info = (ds.bases ? v.bases_info : v.kmers_info) + v.info_off[rj];
+      for(int t = 0; t < nb_u; ++t) {
+        const uint32_t id = path_at(rj, (uint32_t)t) >> 1;
+        u_len += id < u.len.size() ? u.len[id] : 0;
+        if((uint32_t)(2 * t) < ilen) common += info[2 * t];
+        if(t > 0 && (uint32_t)(2 * t - 1) < ilen) common -= info[2 * t - 1];
+      }
+      u_len -= (nb_u - 1) * ((int)o.k_len - 1);
+      const double t1 = o.overlap_play * position_len, t2 = o.overlap_play * ((double)u_len + error);
+      if((double)u_len > t1 + error || position_len > t2) continue;
+      snprintf(buf, sizeof buf, "n%d -> n%d [tooltip=\"...\", label=\"%d\"];\n", ii, jj, common);
+      dot += buf;
+    }
+  }
+}
+} // namespace
+
 void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
-                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out) {
+                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out,
+                       text_buf* dot, dot_state* ds) {
   const double K = o.k_len;
   std::vector<mega_read> mrs;
   std::vector<int> sort_tiling, tiled;
@@ -468,6 +543,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
   for(uint32_t r = r0; r < r1; ++r) {
     const uint64_t b = v.read_coords[r];
     const int n = (int)(v.read_coords[r + 1] - b);
+    if(dot) dot_open_read(v, batch, r, sr, u, o, *ds, *dot);      // (the reference opens a graph for every read, also one without rows)
     if(n == 0) continue;
     const double pb_size = (double)(batch.start[r + 1] - batch.start[r]);
     auto row_unitig_id = [&](uint64_t row, uint32_t t) -> uint32_t {
@@ -526,6 +602,17 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       }
       const double len = std::min(pb_size + 0.5, mr.tiling_end) - std::max(0.5, mr.tiling_start);
       mr.density = (double)v.lpath[row] / len;
+      if(dot) {                                            // node label (overlap_graph.cc:133-146)
+        char db[400];
+        const double node_s = v.stretch[row] + v.offset[row];
+        const double node_e = v.stretch[row] * (double)v.ql[row] + v.offset[row];
+        const int prec = ds->first_node ? 6 : 2;           // the stream's precision: 6 until the first density sets it to 2
+        ds->first_node = false;
+        snprintf(db, sizeof db, "n%d [label=\"%d L%u #%d\\nP(%d,%d) S(%d,%d)\\nI(%.*f,%.*f)\\nLP #%d L%.1f d%.2f\"%s];\n", i, i, v.ql[row],
+                 v.nb_mers[row], v.rs[row], v.re[row], v.qs[row], v.qe[row], prec, node_s, prec, node_e, v.lpath[row], len, mr.density,
+                 v.start_node[row] ? ", color=\"blue\"" : (v.end_node[row] ? ", color=\"green\"" : ""));
+        *dot += db;
+      }
       if(!v.end_node[row] || mr.density < o.density || (mr.tiling_end - mr.tiling_start) < o.min_length) continue;
       const int root = v.component[row];
       auto it = comps.find(root);
@@ -623,6 +710,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
         const size_t overlap = (size_t)v.lunitigs[irow] + sr.path_len(v.sr[jrow]) - (size_t)v.lunitigs[jrow];
         const size_t end = (size_t)sr.path_len(v.sr[irow]) - 1 - overlap;
         offset = prepend(offset, irow, 0, end);
+        if(dot) { char db[80]; snprintf(db, sizeof db, "n%d -> n%d [color=\"red\"];\n", node_i, node_j); *dot += db; }
         node_j = node_i;
         node_i = v.lprev[irow];
       }
@@ -669,6 +757,7 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       *w++ = '\n';
       out.append(buf, (size_t)(w - buf));
     }
+    if(dot) *dot += "}\n";                       // only reads with mega-reads get their graph closed (overlap_graph.hpp:258-259)
   }
 }
 

@@ -139,8 +139,15 @@ struct graph_options {
 
 // Text records of create_mega_reads for reads [r0, r1) of a result (overlap_graph.cc:61-299,
 // overlap_graph.hpp:198-262): best terminal node per component, tiling, one line per mega-read.
+// dot: when not null, also the reference's --dot text for these reads (overlap_graph.hpp:189-196, overlap_graph.cc:49-50,
+// 133-146,271): one "digraph" per read with every node, every overlap edge (recomputed here from the rows: the device
+// keeps only what the longest paths need) and the edges of the printed paths in red.  dot_state carries the one
+// piece of stream state the reference's output depends on (the first node of the stream prints its implied
+// positions with 6 decimals, every later one with 2).
+struct dot_state { bool first_node = true; double errors = 3.0; int bases = 0; };
 void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1,
-                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out);
+                       const super_reads& sr, const unitigs& u, const graph_options& o, text_buf& out,
+                       text_buf* dot = nullptr, dot_state* ds = nullptr);
 // same, fanned out over `threads` host threads; parts[0], parts[1], ... concatenated are the records
 // in read order (kept apart so that nobody has to copy hundreds of megabytes of text once more)
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,

@@ -85,8 +85,6 @@ static int download_rows(mr_context* ctx, mr_workspace& ws, mr_result* res, cons
 
 
 static const bool g_trace = getenv("MR_TRACE") != nullptr;
-// MR_L2_HINT=1: table loads of the seed kernel carry the L2 evict_last hint (A/B switch)
-static const bool g_l2_hint = getenv("MR_L2_HINT") && atoi(getenv("MR_L2_HINT")) != 0;
 #define MR_TRACE_MSG(...) do { if(g_trace) { fprintf(stderr, "[mr] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while(0)
 
 // ------------------------------------------------------------------------------------------------
@@ -233,24 +231,107 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const char* __restrict_
   nmask[w] = m;
 }
 
+// ---- k-mers straight from the packed words ---------------------------------------------------------------------
+// With the reads 2-bit packed, a k-mer is a bit field: 64 bits of the code words starting at base g hold bases
+// g .. g + 31 lowest first, so the k-mer as the reference numbers it (first base most significant,
+// mer_sa_imp.hpp:41-47) is that field with its 2-bit groups reversed, and its reverse complement is simply the
+// complemented field (base j of the k-mer lands at bits 2j, which is where the reverse complement wants the
+// complement of base j).  Whether the k bases are all ACGT, and whether a run of ACGT began within the last
+// 18 bases (the only k-mers that toggle the reference's every-other-k-mer flag, coarse_aligner.cc:89-102), are
+// two tests on an 18-bit field of the mask words.  No per-base loop, no byte array of codes.
+__device__ __forceinline__ uint64_t stage_bits(const uint64_t* w, uint64_t bit) {       // 64 bits of the array from `bit` on
+  const uint32_t wi = (uint32_t)(bit >> 6), sh = (uint32_t)bit & 63;
+  return sh ? (w[wi] >> sh) | (w[wi + 1] << (64 - sh)) : w[wi];
+}
+
+// Stages the words of the tile at (rstart, tile_pos) and returns where they start; ends with a barrier.
+struct tile_words { uint64_t wa, ma; };          // first staged code word / mask word (indices into the batch's arrays)
+__device__ __forceinline__ tile_words stage_tile_words(const packed_reads& pr, uint64_t rstart, uint32_t rlen, uint32_t tile_pos,
+                                                       uint32_t k, tile_stage& ts) {
+  const int cap = k > 18 ? (int)k : 18;
+  const int LB  = cap - (int)k;
+  const int total = LB + kTile + (int)k - 1;
+  const int64_t p0 = (int64_t)tile_pos - LB;
+  const uint64_t gA = rstart + (uint64_t)(p0 > 0 ? p0 : 0);
+  const int64_t pend = p0 + total;
+  const uint64_t gB = rstart + (uint64_t)(pend < (int64_t)rlen ? pend : (int64_t)rlen);
+  tile_words tw;
+  tw.wa = (gA >> 5) & ~1ULL; tw.ma = (gA >> 6) & ~1ULL;
+  const uint32_t nw = (uint32_t)((((gB + 31) >> 5) - tw.wa + 1) & ~1ULL);
+  const uint32_t nm = (uint32_t)((((gB + 63) >> 6) - tw.ma + 1) & ~1ULL);
+  if(pr.tma) {
+    if(threadIdx.x == 0) {
+      mbar_init(&ts.bar, 1);
+      mbar_expect_tx(&ts.bar, (nw + nm) * 8u);
+      bulk_copy_g2s(ts.cw, pr.codes + tw.wa, nw * 8u, &ts.bar);
+      bulk_copy_g2s(ts.mw, pr.nmask + tw.ma, nm * 8u, &ts.bar);
+    }
+    __syncthreads();
+    mbar_wait(&ts.bar, 0);
+  } else {
+    for(uint32_t i = threadIdx.x; i < nw; i += kSeedThreads) ts.cw[i] = __ldg(pr.codes + tw.wa + i);
+    for(uint32_t i = threadIdx.x; i < nm; i += kSeedThreads) ts.mw[i] = __ldg(pr.nmask + tw.ma + i);
+    __syncthreads();
+  }
+  return tw;
+}
+
+// k-mer and its reverse complement at read position pos (the caller knows pos + k <= rlen)
+__device__ __forceinline__ void kmer_at(const tile_stage& ts, const tile_words& tw, uint64_t g, uint32_t k, uint64_t& m, uint64_t& rm) {
+  const uint64_t win = stage_bits(ts.cw, 2 * (g - 32 * tw.wa));
+  const uint64_t mask = (1ULL << (2 * k)) - 1;
+  m  = reverse_pairs(win) >> (64 - 2 * k);
+  rm = ~win & mask;
+}
+
+// valid: k consecutive ACGT at pos, inside the read; cand: ... and a run of ACGT started within the 18 bases that end
+// with the k-mer's last one (positions before the read count as non-ACGT) -- what jf_aligner.hpp:41-52's running
+// `len <= 17` means.  Simple-sequence repeats are NOT excluded here.
+__device__ __forceinline__ void kmer_flags(const tile_stage& ts, const tile_words& tw, uint64_t rstart, uint32_t rlen, uint32_t pos,
+                                           uint32_t k, bool& valid, bool& cand) {
+  valid = false; cand = false;
+  if((uint64_t)pos + k > rlen) return;
+  const uint64_t g = rstart + pos;
+  if(k <= 18) {
+    if(pos + k >= 18) {
+      const uint64_t x = stage_bits(ts.mw, g + k - 18 - 64 * tw.ma) & 0x3ffffULL;      // bit t: base pos + k - 18 + t
+      valid = (x >> (18 - k)) == 0;
+      cand = valid && (x & ((1ULL << (18 - k)) - 1)) != 0;
+    } else {                                     // the 18-base window starts before the read does
+      const uint64_t x = stage_bits(ts.mw, g - 64 * tw.ma) & ((1ULL << k) - 1);
+      valid = x == 0;
+      cand = valid;
+    }
+  } else {
+    valid = (stage_bits(ts.mw, g - 64 * tw.ma) & ((1ULL << k) - 1)) == 0;
+  }
+}
+
 // pass 0 (only when k <= 17): number of flag-toggling k-mers per tile
 __global__ void __launch_bounds__(kSeedThreads) seed_count_kernel(packed_reads bases, const uint64_t* __restrict__ read_start,
                                                                    const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                    uint32_t k, uint32_t* __restrict__ tile_cand) {
-  __shared__ uint8_t codes[kTile + 64];
   __shared__ tile_stage ts;
   __shared__ uint32_t total;
   if(threadIdx.x == 0) total = 0;
   const uint32_t r = tile_read[blockIdx.x];
   const uint64_t rs = read_start[r];
-  // A k-mer toggles the flag only inside the first 17 bases of an N-free run (run <= 17): a tile whose
-  // window holds no run start -- almost every tile -- has none, and skips the k-mer arithmetic.
-  const bool broke = load_tile_codes(bases, rs, (uint32_t)(read_start[r + 1] - rs), tile_pos[blockIdx.x], k, codes, ts);
-  if(!__syncthreads_or(broke)) { if(threadIdx.x == 0) tile_cand[blockIdx.x] = 0; return; }
-  tile_kmers t;
-  tile_kmers_from_codes(k, codes, t);
-  const uint32_t c = (uint32_t)t.cand[0] + t.cand[1] + t.cand[2] + t.cand[3];
-  if(c) atomicAdd(&total, c);
+  const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs), tpos = tile_pos[blockIdx.x];
+  const tile_words tw = stage_tile_words(bases, rs, rlen, tpos, k, ts);
+  uint32_t c = 0;
+#pragma unroll
+  for(int j = 0; j < 4; ++j) {
+    const uint32_t pos = tpos + threadIdx.x * 4 + j;
+    bool valid, cand;
+    kmer_flags(ts, tw, rs, rlen, pos, k, valid, cand);
+    if(cand) {                                   // rare: only then is the k-mer itself needed (simple repeats do not toggle)
+      uint64_t m, rm;
+      kmer_at(ts, tw, rs + pos, k, m, rm);
+      c += !is_ssr(m, k);
+    }
+  }
+  c = __reduce_add_sync(MR_FULL_MASK, c);
+  if((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
   __syncthreads();
   if(threadIdx.x == 0) tile_cand[blockIdx.x] = total;
 }
@@ -271,10 +352,15 @@ __global__ void tile_tbase_kernel(const uint32_t* __restrict__ tile_first, uint3
 // kMulti (index of several parts, index.cuh): one launch per part, each with its own rec array;
 // size[g] accumulates the per-part list sizes over the launches (part_flags bit 0: first part,
 // bit 1: last part) and the max-count filter is applied to the sum by the last one.
-// kHint: the table loads carry the L2 evict_last hint (index.cuh).  kNib: bucket bounds come from the
-// nibble records (index_view::nib) instead of the counts table.
-template<bool kMulti, bool kHint, bool kNib>
-__global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view iv, uint32_t part_flags, packed_reads bases,
+// kNib: bucket bounds come from the nibble records (index_view::nib) instead of the counts table.
+// kBytes: the tails are one byte wide (k - mi <= 4), known at compile time.
+// A thread owns 4 consecutive positions.  It first derives their flags (bit tests on the staged words), then
+// walks them one at a time: the two strands' table reads of a position are issued together, and with 8 to 10
+// warps per scheduler in flight that is all the memory parallelism the SM can use -- the first version unrolled
+// all 8 lookups of a thread into 120 KB of code at 64 registers and stalled on instruction fetch (ncu:
+// no_instruction) once the tables had been made to stay in the L2.
+template<bool kMulti, bool kNib, bool kBytes>
+__global__ void __launch_bounds__(kSeedThreads, 5) seed_lookup_kernel(index_view iv, uint32_t part_flags, packed_reads bases,
                                                                     const uint64_t* __restrict__ read_start,
                                                                     const uint32_t* __restrict__ tile_read, const uint32_t* __restrict__ tile_pos,
                                                                     const uint32_t* __restrict__ tile_tbase, uint32_t max_count,
@@ -283,7 +369,6 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
                                                                     unsigned long long* __restrict__ n_tails,
                                                                     unsigned long long* __restrict__ n_lists,
                                                                     unsigned long long* __restrict__ n_buckets) {
-  __shared__ uint8_t  codes[kTile + 64];
   __shared__ tile_stage ts;
   __shared__ uint64_t sw[8];
   __shared__ uint32_t looked, scanned, listed, buckets;
@@ -293,97 +378,93 @@ __global__ void __launch_bounds__(kSeedThreads, 4) seed_lookup_kernel(index_view
   const uint32_t rlen = (uint32_t)(read_start[r + 1] - rs);
   const uint32_t tpos = tile_pos[blockIdx.x];
   if(threadIdx.x == 0) { looked = 0; scanned = 0; listed = 0; buckets = 0; }
-  tile_kmers t;
-  enumerate_tile(bases, rs, rlen, tpos, k, codes, ts, t);
+  const tile_words tw = stage_tile_words(bases, rs, rlen, tpos, k, ts);
 
-  bool keep[4];
+  // flags of this thread's positions: bit j of keep / cand
+  uint32_t keep = 0, candm = 0;
 #pragma unroll
-  for(int j = 0; j < 4; ++j) keep[j] = t.valid[j];
-  const uint32_t ncand = (uint32_t)t.cand[0] + t.cand[1] + t.cand[2] + t.cand[3];
+  for(int j = 0; j < 4; ++j) {
+    const uint32_t pos = tpos + threadIdx.x * 4 + j;
+    bool valid, cand;
+    kmer_flags(ts, tw, rs, rlen, pos, k, valid, cand);
+    if(valid) {
+      uint64_t m, rm;
+      kmer_at(ts, tw, rs + pos, k, m, rm);
+      if(!is_ssr(m, k)) { keep |= 1u << j; if(cand) candm |= 1u << j; }
+    }
+  }
+  const uint32_t ncand = __popc(candm);
   if(k <= 17 && __syncthreads_or(ncand != 0)) {
     uint64_t total;
     uint32_t seen = tile_tbase[blockIdx.x] + (uint32_t)prim::block_exclusive_scan_256(ncand, sw, total);
 #pragma unroll
     for(int j = 0; j < 4; ++j) {
-      if(t.cand[j]) {
-        ++seen;                              // flag starts at 1 and flips on every candidate:
-        if((seen & 1) == 0) keep[j] = false; // the 2nd, 4th, ... candidate of the read is skipped
+      if((candm >> j) & 1) {
+        ++seen;                                   // flag starts at 1 and flips on every candidate:
+        if((seen & 1) == 0) keep &= ~(1u << j);   // the 2nd, 4th, ... candidate of the read is skipped
       }
     }
   }
 
-  const uint64_t pol = kHint ? l2_evict_last_policy() : 0;
   const uint32_t tmask = iv.tail_bits >= 32 ? 0xffffffffu : ((1u << iv.tail_bits) - 1);
-  uint32_t c0[8], c1[8], first[8];
-  // stage 1: the bucket bounds of all (position, strand) pairs of this thread, loads issued together
-#pragma unroll
-  for(int j = 0; j < 4; ++j) {
-    if(keep[j]) {
-      const uint32_t pm = (uint32_t)(t.m[j] >> iv.tail_bits), pr = (uint32_t)(t.rm[j] >> iv.tail_bits);
-      bucket_bounds<kNib, kHint>(iv, pm, c0[2 * j], c1[2 * j], pol);
-      bucket_bounds<kNib, kHint>(iv, pr, c0[2 * j + 1], c1[2 * j + 1], pol);
-    }
-  }
-  // stage 2: the first tail word of every non-empty bucket, again issued together -- most buckets fit
-  // one or two words, so a thread's 8 lookups cost ~3 dependent memory round trips instead of ~16
-#pragma unroll
-  for(int q = 0; q < 8; ++q) {
-    first[q] = 0;
-    if(keep[q >> 1] && c0[q] != c1[q]) first[q] = tail_word<kHint>(iv, tail_word_of(iv, c0[q]), pol);
-  }
   uint32_t nlook = 0, ntail = 0, nlist = 0, nbucket = 0;
   const uint64_t g0 = rs + tpos + (uint64_t)threadIdx.x * 4;
-#pragma unroll
+#pragma unroll 1
   for(int j = 0; j < 4; ++j) {
+    const uint32_t pos = tpos + threadIdx.x * 4 + j;
+    if(pos >= rlen) break;
     uint4 out = make_uint4(0, 0, 0, 0);
     uint32_t sz = 0;
-    if(keep[j]) {
+    if((keep >> j) & 1) {
       ++nlook;
-      uint32_t idx[2], nb[2];
+      uint64_t mer[2];
+      kmer_at(ts, tw, rs + pos, k, mer[0], mer[1]);
+      uint32_t a0[2], a1[2], first[2], idx[2], nb[2];
+#pragma unroll
+      for(int s = 0; s < 2; ++s) bucket_bounds<kNib>(iv, (uint32_t)(mer[s] >> iv.tail_bits), a0[s], a1[s]);
+#pragma unroll
+      for(int s = 0; s < 2; ++s) first[s] = a0[s] != a1[s] ? tail_word(iv, kBytes ? a0[s] >> 2 : tail_word_of(iv, a0[s])) : 0u;
 #pragma unroll
       for(int s = 0; s < 2; ++s) {
-        const uint64_t mer = s ? t.rm[j] : t.m[j];
-        const uint32_t a0 = c0[2 * j + s], a1 = c1[2 * j + s];
         idx[s] = 0; nb[s] = 0;
-        if(a0 != a1) {
-          const uint32_t tt = (uint32_t)mer & tmask;
+        if(a0[s] != a1[s]) {
+          const uint32_t tt = (uint32_t)mer[s] & tmask;
           uint32_t lo, hi;
-          ntail += a1 - a0 <= 64 ? a1 - a0 : 2 * (32 - __clz(a1 - a0));   // entries a scan / two binary searches touch
+          ntail += a1[s] - a0[s] <= 64 ? a1[s] - a0[s] : 2 * (32 - __clz(a1[s] - a0[s]));   // entries a scan / two binary searches touch
           ++nbucket;
-          bucket_range<kHint>(iv, a0, a1, tt, first[2 * j + s], lo, hi, pol);
-          if(hi != lo && (mer & 3) == 0)
-            for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer;
+          if(kBytes) bucket_range_bytes(iv, a0[s], a1[s], tt, first[s], lo, hi);
+          else       bucket_range(iv, a0[s], a1[s], tt, first[s], lo, hi);
+          if(hi != lo && (mer[s] & 3) == 0)
+            for(uint32_t q = 0; q < iv.nshort; ++q) lo += iv.short_key[q] == mer[s];
           nb[s] = hi - lo; idx[s] = nb[s] ? lo : 0;
         }
       }
       const uint32_t total = nb[0] + nb[1];
-      if(kMulti) {
-        out = make_uint4(idx[0], nb[0], idx[1], nb[1]);
-        sz = total;
-      } else if(total != 0 && !(max_count && total >= max_count)) {
+      if(kMulti || (total != 0 && !(max_count && total >= max_count))) {
         out = make_uint4(idx[0], nb[0], idx[1], nb[1]);
         sz = total;
       }
     }
-    const uint32_t pos = tpos + threadIdx.x * 4 + j;
     // streaming stores (evict-first): the output must not push the index tables out of L2
-    if(pos < rlen) {
-      if(kMulti) {
-        if(!(part_flags & 1)) sz += size[g0 + j];
-        if((part_flags & 2) && max_count && sz >= max_count) sz = 0;
-      }
-      // expand_kernel reads rec only where size != 0 (a one-part index): positions without a list
-      // (most of them) write 4 bytes instead of 20
-      if(kMulti || sz) __stcs(rec + g0 + j, out);
-      __stcs(size + g0 + j, sz);
-      if((!kMulti || (part_flags & 2)) && sz) ++nlist;
+    if(kMulti) {
+      if(!(part_flags & 1)) sz += size[g0 + j];
+      if((part_flags & 2) && max_count && sz >= max_count) sz = 0;
     }
+    // expand_kernel reads rec only where size != 0 (a one-part index): positions without a list
+    // (most of them) write 4 bytes instead of 20
+    if(kMulti || sz) __stcs(rec + g0 + j, out);
+    __stcs(size + g0 + j, sz);
+    if((!kMulti || (part_flags & 2)) && sz) ++nlist;
   }
   if(kMulti && !(part_flags & 1)) nlook = 0;          // a k-mer is counted once, not once per part
-  if(nlook) atomicAdd(&looked, nlook);
-  if(ntail) atomicAdd(&scanned, ntail);
-  if(nlist) atomicAdd(&listed, nlist);
-  if(nbucket) atomicAdd(&buckets, nbucket);
+  nlook = __reduce_add_sync(MR_FULL_MASK, nlook); ntail = __reduce_add_sync(MR_FULL_MASK, ntail);
+  nlist = __reduce_add_sync(MR_FULL_MASK, nlist); nbucket = __reduce_add_sync(MR_FULL_MASK, nbucket);
+  if((threadIdx.x & 31) == 0) {
+    if(nlook) atomicAdd(&looked, nlook);
+    if(ntail) atomicAdd(&scanned, ntail);
+    if(nlist) atomicAdd(&listed, nlist);
+    if(nbucket) atomicAdd(&buckets, nbucket);
+  }
   __syncthreads();
   if(threadIdx.x == 0) {
     if(looked) atomicAdd(n_lookups, (unsigned long long)looked);
@@ -1193,25 +1274,23 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
       MR_LAUNCHED(ctx);
     }
     timer.next("seed lookup");
-    if(nparts == 1) {
-      l2_window(ctx, st, idx, true);
-      auto kern = iv.nib ? seed_lookup_kernel<false, false, true>
-                         : (g_l2_hint ? seed_lookup_kernel<false, true, false> : seed_lookup_kernel<false, false, false>);
-      kern<<<ntiles, kSeedThreads, 0, st>>>(iv, 3u, d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                          ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                          ws.rec.as<uint4>(), ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
+    typedef void (*seed_fn)(index_view, uint32_t, packed_reads, const uint64_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t,
+                            uint4*, uint32_t*, unsigned long long*, unsigned long long*, unsigned long long*, unsigned long long*);
+    auto pick = [](bool multi, const index_view& v) -> seed_fn {
+      const bool nibs = v.nib != nullptr, bytes = v.tail_bytes == 1;
+      if(multi) return nibs ? (bytes ? seed_lookup_kernel<true, true, true> : seed_lookup_kernel<true, true, false>)
+                            : (bytes ? seed_lookup_kernel<true, false, true> : seed_lookup_kernel<true, false, false>);
+      return nibs ? (bytes ? seed_lookup_kernel<false, true, true> : seed_lookup_kernel<false, true, false>)
+                  : (bytes ? seed_lookup_kernel<false, false, true> : seed_lookup_kernel<false, false, false>);
+    };
+    for(uint32_t part = 0; part < nparts; ++part) {
+      l2_window(ctx, st, part ? idx->more[part - 1] : idx, true);
+      const index_view& pv = idx->part_view(part);
+      pick(nparts > 1, pv)<<<ntiles, kSeedThreads, 0, st>>>(pv, nparts == 1 ? 3u : ((part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u)),
+                                                           d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
+                                                           ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
+                                                           ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
       MR_LAUNCHED(ctx);
-    } else {
-      for(uint32_t part = 0; part < nparts; ++part) {
-        l2_window(ctx, st, part ? idx->more[part - 1] : idx, true);
-        const index_view& pv = idx->part_view(part);
-        auto kern = pv.nib ? seed_lookup_kernel<true, false, true> : seed_lookup_kernel<true, false, false>;
-        kern<<<ntiles, kSeedThreads, 0, st>>>(pv, (part == 0 ? 1u : 0u) | (part + 1 == nparts ? 2u : 0u),
-                                            d_bases, d_read_start, ws.tile_read.as<uint32_t>(), ws.tile_pos.as<uint32_t>(),
-                                            ws.tile_tbase.as<uint32_t>(), p->max_count > 0 ? (uint32_t)p->max_count : 0u,
-                                            ws.rec.as<uint4>() + part * rec_stride, ws.size.as<uint32_t>(), ctr + 0, ctr + 6, ctr + 9, ctr + 10);
-        MR_LAUNCHED(ctx);
-      }
     }
     l2_window(ctx, st, idx, false);
     timer.next("count threshold");

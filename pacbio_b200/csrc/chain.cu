@@ -759,8 +759,10 @@ __global__ void __launch_bounds__(128) finish_small_groups_kernel(chain_args A, 
 // next to the chaining kernels the L1 is a few KB): the warp copies 16 pairs of every chain into a
 // shared-memory tile with coalesced cp.async, the next tile in flight while the current one is folded in.
 constexpr int kTileE = 16;
+// Groups of at most `lo` hits are left to finish_small_groups_kernel (they only appear in a class list here when
+// --window-size > 1 sends every group through the global-memory chaining kernel).
 __global__ void __launch_bounds__(128) finish_tile_kernel(chain_args A, const uint32_t* __restrict__ list,
-                                                           const uint32_t* __restrict__ list_count, uint32_t hi) {
+                                                           const uint32_t* __restrict__ list_count, uint32_t hi, uint32_t lo) {
   __shared__ uint64_t tile[4][2][32][kTileE + 1];      // + 1: lane j reads row j, 17 x 8 B apart -> no bank conflicts
   const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t total = *list_count;
@@ -775,6 +777,7 @@ __global__ void __launch_bounds__(128) finish_tile_kernel(chain_args A, const ui
       v = A.group_nb[g]; nb = v & 0x7fffffffu;
       if(nb > hi) nb = 0;
       gs = A.group_start[g];
+      if(A.group_start[g + 1] - gs <= lo) nb = 0;
     }
     const uint32_t maxnb = __reduce_max_sync(MR_FULL_MASK, nb);
     if(maxnb == 0) continue;
@@ -1014,12 +1017,15 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
     if(g_chain_trace) { snprintf(label, sizeof label, "strands, tier %d (<= %u hits)", c, c < kSmemTiers ? kTierCapHost[c] : 0u); CHAIN_TRACE(st, label); }
     snprintf(label, sizeof label, "finish %d", c); tl.open(label, st);
     if(c != 0) {
-      finish_tile_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, kThreadFinishLongMax);
+      finish_tile_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, kThreadFinishLongMax,
+                                                          c == kSmemTiers && A.window > 1 ? kTierCapHost[0] : 0u);
       MR_LAUNCHED(ctx);
       tl.close(st);
       if(g_chain_trace) { snprintf(label, sizeof label, "finish, tier %d", c); CHAIN_TRACE(st, label); }
       MR_CUDA(ctx, cudaEventRecord(ctx->ev[c], st));
     } else {
+      // (--window-size > 1: the small groups were chained by the global-memory kernel on its own stream)
+      if(A.window > 1) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[kSmemTiers], 0));
       finish_small_groups_kernel<<<div_up(G, 128), 128, 0, st>>>(A, kTierCapHost[0]);
       MR_LAUNCHED(ctx);
       tl.close(st);

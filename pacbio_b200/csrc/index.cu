@@ -124,24 +124,23 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
   }
 }
 
-// nibble records (index_view::nib): one thread per group of 64 prefixes
-__global__ void __launch_bounds__(256) nib_kernel(const uint32_t* __restrict__ counts, uint32_t ngroups, uint4* __restrict__ nib,
+// nibble records (index_view::nib): one thread per group of 32 prefixes
+__global__ void __launch_bounds__(256) nib_kernel(const uint32_t* __restrict__ counts, uint32_t ngroups, ulonglong2* __restrict__ nib,
                                                   uint32_t* __restrict__ gbase, unsigned long long* __restrict__ n_overflow) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if(g >= ngroups) return;
-  const uint32_t* c = counts + (uint64_t)g * 64;
-  uint32_t w[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  const uint32_t* c = counts + (uint64_t)g * 32;
+  uint64_t w[2] = { 0, 0 };
   bool big = false;
   uint32_t prev = c[0];
-  for(int j = 0; j < 64; ++j) {
+  for(int j = 0; j < 32; ++j) {
     const uint32_t next = c[j + 1], sz = next - prev;
     prev = next;
     big |= sz >= 15;
-    w[j >> 3] |= (sz & 15u) << (4 * (j & 7));
+    w[j >> 4] |= (uint64_t)(sz & 15u) << (4 * (j & 15));
   }
-  if(big) { w[0] |= 15u; atomicAdd(n_overflow, 1ULL); }      // marker: this group is looked up in counts[]
-  nib[2 * (uint64_t)g]     = make_uint4(w[0], w[1], w[2], w[3]);
-  nib[2 * (uint64_t)g + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  if(big) { w[0] |= 15ULL; atomicAdd(n_overflow, 1ULL); }    // marker: this group is looked up in counts[]
+  nib[g] = make_ulonglong2(w[0], w[1]);
   gbase[g] = c[0];
 }
 
@@ -319,20 +318,20 @@ int build_slots(mr_index* idx) {
   const char* knob = getenv("MR_NIB");
   const bool forced = knob && atoi(knob) == 1, off = knob && atoi(knob) == 0;
   if(off || v.mi < 3 || (!forced && (uint64_t)v.nsa > (uint64_t)nprefix * 4)) return MR_OK;
-  const uint32_t ngroups = nprefix / 64;
-  MR_TRY(idx->nib.ensure(ctx, (size_t)ngroups * 2 * sizeof(uint4)));
+  const uint32_t ngroups = nprefix / 32;
+  MR_TRY(idx->nib.ensure(ctx, (size_t)ngroups * sizeof(ulonglong2)));
   MR_TRY(idx->gbase.ensure(ctx, (size_t)ngroups * sizeof(uint32_t)));
   dev_buf ovf;
   MR_TRY(ovf.ensure(ctx, sizeof(unsigned long long)));
   MR_CUDA(ctx, cudaMemsetAsync(ovf.p, 0, sizeof(unsigned long long), ctx->stream));
-  nib_kernel<<<div_up(ngroups, 256), 256, 0, ctx->stream>>>(idx->counts.as<uint32_t>(), ngroups, idx->nib.as<uint4>(), idx->gbase.as<uint32_t>(),
+  nib_kernel<<<div_up(ngroups, 256), 256, 0, ctx->stream>>>(idx->counts.as<uint32_t>(), ngroups, idx->nib.as<ulonglong2>(), idx->gbase.as<uint32_t>(),
                                                           ovf.as<unsigned long long>());
   MR_LAUNCHED(ctx);
   unsigned long long n_overflow = 0;
   MR_CUDA(ctx, cudaMemcpyAsync(&n_overflow, ovf.p, sizeof n_overflow, cudaMemcpyDeviceToHost, ctx->stream));
   MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if(!forced && n_overflow * 4 > ngroups) { idx->nib.release(); idx->gbase.release(); return MR_OK; }    // too many groups fall back: not worth the extra read
-  v.nib = idx->nib.as<uint4>(); v.gbase = idx->gbase.as<uint32_t>();
+  v.nib = idx->nib.as<ulonglong2>(); v.gbase = idx->gbase.as<uint32_t>();
   idx->nib_overflow_groups = n_overflow;
   return MR_OK;
 }
@@ -481,8 +480,8 @@ uint64_t mr_index_table_bytes(const mr_index* idx) {
   auto part_bytes = [](const mr_index* p) -> uint64_t {
     if(!p->view.nib) return p->lut_bytes;
     // with nibble records the prefix counts are only read for the groups that overflow
-    const uint64_t ngroups = (1ULL << (2 * p->mi)) / 64;
-    return ngroups * 36 + ((uint64_t)p->nsa + 64) * p->view.tail_bytes + p->nib_overflow_groups * 260;
+    const uint64_t ngroups = (1ULL << (2 * p->mi)) / 32;
+    return ngroups * 20 + ((uint64_t)p->nsa + 64) * p->view.tail_bytes + p->nib_overflow_groups * 132;
   };
   uint64_t b = part_bytes(idx);
   for(const mr_index* p : idx->more) b += part_bytes(p);

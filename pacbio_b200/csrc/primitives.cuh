@@ -231,23 +231,27 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const K* __res
 // Each warp owns a contiguous 512-key slice of the tile and walks it 32 keys at a time, so the
 // rank of a key among equal digits is (earlier warps) + (earlier rounds of this warp) + (lower
 // lanes of this round): order preserving, hence stable.
-template<typename K, typename V, int kBits>
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __restrict__ kin, const V* __restrict__ vin,
-                                                                      K* __restrict__ kout, V* __restrict__ vout,
-                                                                      uint64_t n, int shift,
-                                                                      const uint64_t* __restrict__ offsets, uint32_t nblocks) {
-  constexpr int kRadix = 1 << kBits;
-  __shared__ uint32_t cnt[kSortWarps][kRadix];
-  __shared__ uint64_t wbase[kSortWarps][kRadix];
-  for(int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+// kThreads threads rank a tile of kSortTile keys, kSortTile / kThreads each.  256 threads x 16 keys keeps 16 keys and
+// ranks per thread in registers and leaves the SM at ~22 % occupancy with every warp waiting on its loads
+// (ncu: long_scoreboard); 512 x 8 halves the registers and doubles the warps in flight.
+template<typename K, typename V, int kBits, int kThreads>
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const K* __restrict__ kin, const V* __restrict__ vin,
+                                                                  K* __restrict__ kout, V* __restrict__ vout,
+                                                                  uint64_t n, int shift,
+                                                                  const uint64_t* __restrict__ offsets, uint32_t nblocks) {
+  constexpr int kRadix = 1 << kBits, kWarps = kThreads / 32, kItems = kSortTile / kThreads;
+  __shared__ uint32_t cnt[kWarps][kRadix];
+  __shared__ uint32_t wrel[kWarps][kRadix];       // first slot of warp w's keys with digit d, relative to dbase[d]
+  __shared__ uint64_t dbase[kRadix];              // first slot of this tile's keys with digit d
+  for(int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
+  const uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kItems);
   const unsigned lt = lanemask_lt();
-  K        key[kSortItems];
-  uint32_t rank[kSortItems];
+  K        key[kItems];
+  uint32_t rank[kItems];
 #pragma unroll
-  for(int i = 0; i < kSortItems; ++i) {
+  for(int i = 0; i < kItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * 32 + lane;
     const bool valid = idx < n;
     key[i] = valid ? kin[idx] : (K)0;
@@ -261,19 +265,19 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const K* __
     __syncwarp();
   }
   __syncthreads();
-  if(threadIdx.x < kRadix) {                         // kRadix <= kSortThreads
-    const unsigned d = threadIdx.x;
-    uint64_t run = offsets[(uint64_t)d * nblocks + blockIdx.x];
+  for(unsigned d = threadIdx.x; d < (unsigned)kRadix; d += kThreads) {
+    dbase[d] = offsets[(uint64_t)d * nblocks + blockIdx.x];
+    uint32_t run = 0;
 #pragma unroll
-    for(int w = 0; w < kSortWarps; ++w) { wbase[w][d] = run; run += cnt[w][d]; }
+    for(int w = 0; w < kWarps; ++w) { wrel[w][d] = run; run += cnt[w][d]; }
   }
   __syncthreads();
 #pragma unroll
-  for(int i = 0; i < kSortItems; ++i) {
+  for(int i = 0; i < kItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * 32 + lane;
     if(idx < n) {
       const unsigned d = (unsigned)(key[i] >> shift) & (kRadix - 1);
-      const uint64_t dst = wbase[warp][d] + rank[i];
+      const uint64_t dst = dbase[d] + wrel[warp][d] + rank[i];
       kout[dst] = key[i];
       vout[dst] = vin[idx];
     }
@@ -286,6 +290,12 @@ struct sort_scratch {
   dev_buf scan;      // scan scratch
 };
 
+// MR_SORT_THREADS=256: the scatter kernel's first shape (A/B switch); default 512 threads x 8 keys
+inline bool sort_wide_ctas() {
+  static const bool v = [] { const char* e = getenv("MR_SORT_THREADS"); return !(e && atoi(e) == 256); }();
+  return v;
+}
+
 // one pass on the digit [shift, shift + kBits)
 template<typename K, typename V, int kBits>
 int radix_pass(mr_context* ctx, const K* kin, const V* vin, K* kout, V* vout, uint64_t n, int shift, sort_scratch& s) {
@@ -294,7 +304,8 @@ int radix_pass(mr_context* ctx, const K* kin, const V* vin, K* kout, V* vout, ui
   radix_hist_kernel<K, kBits><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, n, shift, s.table.as<uint32_t>(), nblocks);
   MR_LAUNCHED(ctx);
   MR_TRY((exclusive_scan<ptr_in_u32, uint64_t>(ctx, ptr_in_u32{ s.table.as<uint32_t>() }, tsize, s.offsets.as<uint64_t>(), s.scan, nullptr)));
-  radix_scatter_kernel<K, V, kBits><<<nblocks, kSortThreads, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, s.offsets.as<uint64_t>(), nblocks);
+  if(sort_wide_ctas()) radix_scatter_kernel<K, V, kBits, 512><<<nblocks, 512, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, s.offsets.as<uint64_t>(), nblocks);
+  else                 radix_scatter_kernel<K, V, kBits, 256><<<nblocks, 256, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, s.offsets.as<uint64_t>(), nblocks);
   MR_LAUNCHED(ctx);
   return MR_OK;
 }

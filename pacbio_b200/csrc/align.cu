@@ -537,9 +537,14 @@ __global__ void __launch_bounds__(256) read_threshold_kernel(const uint64_t* __r
 __device__ __forceinline__ void emit_hit(const index_view& iv, uint32_t read, uint32_t pb_off, uint32_t sa_rank, bool minus,
                                          uint64_t slot, uint64_t* __restrict__ keys, uint64_t* __restrict__ pays,
                                          uint32_t& n_bad) {
-  const uint32_t x = __ldg(iv.sa + sa_rank);
   uint32_t sr, off;
-  if(index_locate(iv, x, sr, off)) {
+  bool inside;
+  if(iv.saloc) {
+    const uint2 l = __ldg(iv.saloc + sa_rank);
+    sr = l.x; off = l.y;
+    inside = sr != 0xffffffffu;
+  } else inside = index_locate(iv, __ldg(iv.sa + sa_rank), sr, off);
+  if(inside) {
     const int32_t soff = minus ? -(int32_t)off : (int32_t)off;
     keys[slot] = ((uint64_t)read << 32) | (iv.sr_base + sr);
     pays[slot] = (uint64_t)pb_off | ((uint64_t)(uint32_t)soff << 32);

@@ -78,7 +78,7 @@ void build_indexes(device_set& ds, const std::vector<int>& devices, const super_
 
 unsigned streams_per_device() {
   if(const char* e = getenv("MR_STREAMS")) { const int v = atoi(e); return v < 1 ? 1u : (v > 8 ? 8u : (unsigned)v); }
-  return 1;
+  return 2;
 }
 
 bool stage_batches() {

@@ -60,11 +60,12 @@ std::vector<int> choose_devices();
 void build_indexes(device_set& ds, const std::vector<int>& devices, const super_reads& sr, const unitigs& u,
                    uint32_t psa_min, uint32_t mer);
 
-// batches in flight per device: MR_STREAMS (default 1).  The kernels of one batch are a mix of
+// batches in flight per device: MR_STREAMS (default 2).  The kernels of one batch are a mix of
 // bandwidth-bound (seed lookups, sort) and latency-bound (chaining, coords) work with host round
-// trips in between; a second batch on its own stream fills some of those gaps (measured on B200,
-// configs[1]: +4 % device throughput with 2, +11 % with 3, but the aligner threads then compete
-// with the formatter threads for host cores and the end-to-end rate drops, hence the default).
+// trips in between; a second batch on its own stream fills those gaps (measured on B200, configs[1]:
+// device 85.7 -> 77.5 ms per step, end to end 90.9 -> 81.0).  In round 1 the end-to-end rate DROPPED with a
+// second stream because its aligner thread took a core from the threads that tile and print the records;
+// that stage costs half as much now (exact integer formatter, sequence arena).
 unsigned streams_per_device();
 // MR_STAGE=1: copy the next batch to the device while the current one is aligned (mr_stage_batch /
 // mr_align_staged); off by default until it has run on the target box

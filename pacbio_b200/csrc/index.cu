@@ -124,6 +124,17 @@ __global__ void __launch_bounds__(256) lookup_kernel(index_view iv, const uint64
   }
 }
 
+// located suffix-array entries (index_view::saloc)
+__global__ void __launch_bounds__(256) saloc_kernel(index_view iv, uint2* __restrict__ saloc) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < iv.nsa; i += stride) {
+    uint32_t sr, off;
+    const uint32_t x = iv.sa[i];
+    // (positions of a part's extension belong to the next part and never match here: index.cuh)
+    saloc[i] = x < iv.own && index_locate(iv, x, sr, off) ? make_uint2(sr, off) : make_uint2(0xffffffffu, 0u);
+  }
+}
+
 // nibble records (index_view::nib): one thread per group of 32 prefixes
 __global__ void __launch_bounds__(256) nib_kernel(const uint32_t* __restrict__ counts, uint32_t ngroups, ulonglong2* __restrict__ nib,
                                                   uint32_t* __restrict__ gbase, unsigned long long* __restrict__ n_overflow) {
@@ -204,7 +215,7 @@ static uint32_t choose_internal_prefix(uint64_t n, uint32_t psa_min, uint32_t k)
   }
   if(const char* e = getenv("MR_INDEX_PREFIX")) {           // tuning knob: force the internal prefix length
     const uint32_t v = (uint32_t)atoi(e);
-    if(v >= 1 && v <= psa_min) best = v;
+    if(v >= 1 && v < k && v <= 15) best = v;                // (it may exceed --psa-min: buckets are cut from the fully sorted keys)
   }
   while(k - best > (uint32_t)kMaxShort) ++best;
   return best;
@@ -310,6 +321,19 @@ int build_slots(mr_index* idx) {
     MR_LAUNCHED(ctx);
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     v.blkx = idx->blkx.as<uint4>();
+  }
+  v.saloc = nullptr;
+  {
+    // MR_SALOC=0: hits are located at expansion time through the block table, as before (A/B, and 8 bytes per
+    // text base less device memory)
+    const char* knob = getenv("MR_SALOC");
+    if(!(knob && atoi(knob) == 0)) {
+      MR_TRY(idx->saloc.ensure(ctx, (size_t)v.nsa * sizeof(uint2)));
+      saloc_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, idx->saloc.as<uint2>());
+      MR_LAUNCHED(ctx);
+      MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      v.saloc = idx->saloc.as<uint2>();
+    }
   }
   v.nib = nullptr; v.gbase = nullptr;
   // The nibble form of the prefix counts pays while most groups of 64 buckets hold no bucket of 15 entries:

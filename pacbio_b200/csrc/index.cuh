@@ -56,6 +56,11 @@ struct index_view {
   // and is looked up in `counts` as before.
   const ulonglong2* __restrict__ nib;    // one record per group of 32 prefixes
   const uint32_t*   __restrict__ gbase;
+  // saloc[i] = (super-read, 1-based offset) of suffix-array entry i for a mer of k bases, or (0xffffffff, 0) when the
+  // k-mer there crosses into the next sequence (pos_iterator, superread_parser.hpp:110-134, done once at build time):
+  // expanding a hit is one 8-byte read next to its list neighbours instead of a 4-byte read plus a dependent random
+  // 16-byte one into the block table.
+  const uint2*      __restrict__ saloc;
   uint32_t own;                    // bases of the part's own super-reads (sr_start[nseq]); n - own = extension (index.cuh header)
   uint32_t sr_base;                // global index of this part's first super-read (0 for a one-part index)
   uint32_t nseq_all;               // super-reads of the whole index (== nseq for a one-part index)
@@ -73,6 +78,7 @@ struct mr_index {
   uint64_t inputs_checksum = 0;      // mr_inputs_checksum of what the index was built from
   dev_buf  text, sa, tails, counts, sr_start, blk;
   dev_buf  nib, gbase;               // see index_view::nib (derived; not in index files)
+  dev_buf  saloc;                    // see index_view::saloc (derived; not in index files)
   dev_buf  blkx;                     // uint4[(n>>8)+1]: see index_view::blkx (derived; not in index files)
   dev_buf  lut;                      // counts and tails live side by side in this one allocation, so that
                                      // a single L2 access-policy window covers what a lookup reads

@@ -151,7 +151,7 @@ int save_part(mr_context* ctx, mr_index* idx, FILE* f, pinned_buf& stage, uint32
 int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index* idx, file_header& h, std::vector<uint32_t>& sr_len) {
   if(fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0)
     return ctx->fail(MR_EINVAL, "mr_index_load: not an index file of this library version");
-  if(!(h.m >= 1 && h.m < h.k && h.k <= 31 && h.mi >= 1 && h.mi <= h.m && h.n >= h.k && h.n < 0xfffffff0ULL && h.nseq >= 1 &&
+  if(!(h.m >= 1 && h.m < h.k && h.k <= 31 && h.mi >= 1 && h.mi < h.k && h.n >= h.k && h.n < 0xfffffff0ULL && h.nseq >= 1 &&
        h.nsa == (uint32_t)(h.n - h.m + 1) && h.tail_bits == 2 * (h.k - h.mi) && h.nshort <= (uint32_t)kMaxShort &&
        (h.tail_bytes == 1 || h.tail_bytes == 2 || h.tail_bytes == 4)))
     return ctx->fail(MR_EINVAL, "mr_index_load: inconsistent header");
@@ -205,7 +205,6 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
   v.nshort = h.nshort;
   v.sr_base = (uint32_t)h.reserved[1]; v.nseq_all = h.nseq;
   v.own = 0;                                     // set below from the loaded starts
-  MR_TRY(build_slots(idx));                      // derived from counts + tails: not part of the file
   memcpy(v.short_key, h.short_key, sizeof h.short_key);
   idx->n_all = h.n; idx->nseq_all = h.nseq;
   {                                              // super-read lengths from the starts just loaded
@@ -214,6 +213,7 @@ int load_part(mr_context* ctx, FILE* f, pinned_buf* stage, int& which, mr_index*
     for(uint32_t i = 0; i < h.nseq; ++i) sr_len.push_back(st[i + 1] - st[i]);
     v.own = st[h.nseq];
   }
+  MR_TRY(build_slots(idx));                      // tables derived from the loaded arrays: not part of the file
   return MR_OK;
 }
 

@@ -3,6 +3,7 @@
 // least-squares coords and filters, kmers_info, per-read ordering.  One kernel per CPU hot loop
 // of the reference; every kernel cites what it replaces.
 #include "align.cuh"
+#include "group.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -808,6 +809,11 @@ struct head_flag {
     return ((uint32_t)k < nseq) && (i == 0 || keys[i - 1] != k);
   }
 };
+// the per-read sort (group.cu) leaves one byte per hit
+struct head_byte {
+  const uint8_t* head;
+  __device__ uint64_t operator()(uint64_t i) const { return head[i]; }
+};
 
 
 // ------------------------------------------------------------------------------------------------
@@ -1263,7 +1269,8 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_CUDA(ctx, cudaMemsetAsync(ws.counters.p, 0, 16 * sizeof(uint64_t), st));
   unsigned long long* ctr = ws.counters.as<unsigned long long>();
   // counters: 0 lookups, 1 raw hits, 2 invalid hits, 3 groups, 4 survivors, 5 info total, 6 tails, 7 fine hits,
-  // 9 lists, 10 buckets, 11 tile overflow
+  // 9 lists, 10 buckets, 11 tile overflow, 12 most rows of a read, 13 hits of reads too large for the per-read sort,
+  // 14 groups of hits that belong to no super-read
   uint64_t h_ctr[16] = { 0 };
 
   // ---- seeds + lookups ----------------------------------------------------------------------------
@@ -1315,7 +1322,12 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_TRY((prim::exclusive_scan<prim::ptr_in_u32, uint64_t>(ctx, prim::ptr_in_u32{ ws.tile_cand.as<uint32_t>() }, ntiles, ws.hit_off.as<uint64_t>(),
                                                            ws.scan_scratch, (uint64_t*)(ctr + 1))));
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  int sr_bits = 1;
+  while((1ULL << sr_bits) <= (uint64_t)iv.nseq_all) ++sr_bits;
+  const uint32_t read_sort_cap = group_sort_capacity(sr_bits);
+  if(ntiles && read_sort_cap)
+    MR_TRY(launch_read_hits_stats(ctx, ws.hit_off.as<uint64_t>(), ws.tile_first.as<uint32_t>(), nreads, read_sort_cap, ctr + 13));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 14 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, ctx->wait(st));
   if(h_ctr[11]) return ctx->fail(MR_ELIMIT, "mr_align_batch: 2^32 or more hits in one 1024-base tile; use --max-count");
   const uint64_t H = h_ctr[1];
@@ -1347,28 +1359,51 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                          ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
     MR_LAUNCHED(ctx);
     timer.next("group sort");
-    int sr_bits = 1;
-    while((1ULL << sr_bits) <= (uint64_t)iv.nseq_all) ++sr_bits;
-    bool in_first = true;
-    MR_TRY((prim::radix_sort_pairs<uint64_t, uint64_t>(ctx, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ws.key1.as<uint64_t>(),
-                                                       ws.pay1.as<uint64_t>(), H, 0, sr_bits, ws.sort, &in_first)));
-    skeys = in_first ? ws.key0.as<uint64_t>() : ws.key1.as<uint64_t>();
-    spays = in_first ? ws.pay0.as<uint64_t>() : ws.pay1.as<uint64_t>();
-    uint64_t* alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
-    uint64_t* alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
-    // group heads -> group_start
-    MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
-    MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    // Grouping by (read, super-read).  Reads whose hits fit one SM's shared memory (nearly all of them, away from
+    // repeats) are sorted one CTA per read (group.cu): 33 bytes of HBM traffic per hit.  When reads that do not fit
+    // hold a quarter of the batch's hits or more (the human-size shape) the device-wide radix sort does it.
+    // MR_READ_SORT=0 / 1 forces one or the other.
+    static const int read_sort_env = getenv("MR_READ_SORT") ? atoi(getenv("MR_READ_SORT")) : -1;
+    const bool read_sort = read_sort_cap != 0 && (read_sort_env >= 0 ? read_sort_env != 0 : h_ctr[13] * 4 < H);
+    uint64_t *alt_key, *alt_pay;
+    if(read_sort) {
+      MR_TRY(ws.head.ensure(ctx, H + 2));
+      group_sort_args GS;
+      GS.keys_in = ws.key0.as<uint64_t>(); GS.pays_in = ws.pay0.as<uint64_t>();
+      GS.keys_out = ws.key1.as<uint64_t>(); GS.pays_out = ws.pay1.as<uint64_t>();
+      GS.head = ws.head.as<uint8_t>(); GS.hit_off = ws.hit_off.as<uint64_t>(); GS.tile_first = ws.tile_first.as<uint32_t>();
+      GS.nseq_all = iv.nseq_all; GS.sr_bits = sr_bits; GS.n_invalid_groups = ctr + 14; GS.cap = 0; GS.idx_bits = 0;
+      MR_TRY(launch_group_sort(ctx, GS, nreads));
+      skeys = GS.keys_out; spays = GS.pays_out; alt_key = GS.keys_in; alt_pay = GS.pays_in;
+      MR_TRY((prim::flag_count<head_byte>(ctx, head_byte{ GS.head }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
+    } else {
+      bool in_first = true;
+      MR_TRY((prim::radix_sort_pairs<uint64_t, uint64_t>(ctx, ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ws.key1.as<uint64_t>(),
+                                                         ws.pay1.as<uint64_t>(), H, 0, sr_bits, ws.sort, &in_first)));
+      skeys = in_first ? ws.key0.as<uint64_t>() : ws.key1.as<uint64_t>();
+      spays = in_first ? ws.pay0.as<uint64_t>() : ws.pay1.as<uint64_t>();
+      alt_key = in_first ? ws.key1.as<uint64_t>() : ws.key0.as<uint64_t>();
+      alt_pay = in_first ? ws.pay1.as<uint64_t>() : ws.pay0.as<uint64_t>();
+      // group heads -> group_start
+      MR_TRY((prim::flag_count<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, (uint64_t*)(ctr + 3))));
+    }
+    MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MR_CUDA(ctx, ctx->wait(st));
     G = h_ctr[3];
-    MR_TRACE_MSG("sorted; %llu groups", (unsigned long long)G);
+    MR_TRACE_MSG("sorted (%s); %llu groups", read_sort ? "per read" : "device-wide", (unsigned long long)G);
     const uint64_t Hvalid = H - h_ctr[2];
     res->view.n_hits = Hvalid;
-    res->view.n_groups = G;
+    res->view.n_groups = G - (read_sort ? h_ctr[14] : 0);      // (the per-read sort makes a group of a read's stray hits)
     MR_TRY(ws.group_start.ensure(ctx, (G + 2) * 8));
-    MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
-    // end of the last group; the source lives in the result object (a copy from pageable memory is staged before the call returns)
-    MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &res->view.n_hits, 8, cudaMemcpyHostToDevice, st));
+    if(read_sort) {
+      MR_TRY((prim::flag_positions<head_byte>(ctx, head_byte{ ws.head.as<uint8_t>() }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
+      // the stray hits stay inside their reads' slices: the last group ends with the last hit
+      MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, ctr + 1, 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+      MR_TRY((prim::flag_positions<head_flag>(ctx, head_flag{ skeys, iv.nseq_all }, H, ws.scan_scratch, ws.group_start.as<uint64_t>())));
+      // end of the last group; the source lives in the result object (a copy from pageable memory is staged before the call returns)
+      MR_CUDA(ctx, cudaMemcpyAsync(ws.group_start.as<uint64_t>() + G, &res->view.n_hits, 8, cudaMemcpyHostToDevice, st));
+    }
 
     // ---- chaining + coords ------------------------------------------------------------------------
     timer.next("chain coords");
@@ -1621,6 +1656,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
     std::sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) { return hk[hg[a]] < hk[hg[b]]; });
     for(uint64_t g : ord) {
       const uint64_t b = hg[g], e = hg[g + 1];
+      if((uint32_t)hk[b] == iv.nseq_all) continue;        // a read's hits that belong to no super-read
       int64_t nf = 0, nbw = 0;
       for(uint64_t i = b; i < e; ++i) ((int32_t)(uint32_t)(hp[i] >> 32) > 0 ? nf : nbw)++;
       const int64_t row[6] = { (int64_t)(hk[b] >> 32), (int64_t)(uint32_t)hk[b], nf, nbw, hl[g].x, hl[g].y };

@@ -52,7 +52,7 @@ struct mr_workspace {
   dev_buf size, rec, hit_off, thr, counters;
   fine_buffers fine;
   dev_buf path_ids, path_off, path_ulen;               // mr_graph_batch: the caller's unitig paths
-  dev_buf key0, key1, pay0, pay1, chainL, group_start;
+  dev_buf key0, key1, pay0, pay1, chainL, group_start, head;
   dev_buf sv_i32, sv_u32, sv_f64, sv_u64, sv_u8;        // survivors, unsorted
   dev_buf fin_i32, fin_u32, fin_f64, fin_u64, fin_u8;   // final rows
   dev_buf read_cnt, read_coords, read_cursor, slot, order, rowkey4, rowkey5;

@@ -554,9 +554,14 @@ constexpr uint32_t kTierWarps[kSmemTiers]   = { 8, 8, 4, 4, 2, 1, 1, 1, 1 };    
 constexpr uint32_t kTinyMax = 8;
 // Single-hit groups (most groups: spurious k-mer matches) need no chaining at all: their chain is
 // hit 0, which this kernel records directly.
+// A group whose key carries the super-read index `stray_sr` holds a read's hits that belong to no super-read (their
+// k-mer straddles two of them; the per-read sort of group.cu leaves them as the last group of the read's slice):
+// it is not chained and yields no row (group_nb = 0).  keys == nullptr: the groups are not keyed by super-read.
 __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __restrict__ group_start, uint64_t ngroups,
+                                                               const uint64_t* __restrict__ keys, uint32_t stray_sr,
                                                                const uint64_t* __restrict__ pays, uint64_t* __restrict__ chain_pay,
-                                                               uint32_t* __restrict__ group_nb, bool singles_here, bool all_global,
+                                                               uint32_t* __restrict__ group_nb, uint2* __restrict__ tap_lens,
+                                                               bool singles_here, bool all_global,
                                                                uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
   // (singles_here is false with parity taps or --max-match on: then every group goes to the strand kernels)
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -570,6 +575,10 @@ __global__ void __launch_bounds__(256) classify_groups_kernel(const uint64_t* __
     if(n == 0) {                                 // a fine-pass window without hits: no chain, a default row
       cls = -1;
       group_nb[g] = 0x80000000u;
+    } else if(keys && (uint32_t)keys[gs] == stray_sr) {
+      cls = -1;
+      group_nb[g] = 0;
+      if(tap_lens) tap_lens[g] = make_uint2(0, 0);
     } else if(n == 1 && singles_here) {
       cls = -1;
       const uint64_t p = pays[gs];
@@ -747,6 +756,7 @@ __global__ void __launch_bounds__(128) finish_small_groups_kernel(chain_args A, 
   const uint64_t gs = A.group_start[g];
   if(A.group_start[g + 1] - gs > max_group) return;
   const uint32_t v = A.group_nb[g];
+  if(v == 0) return;                             // hits that belong to no super-read (classify_groups_kernel)
   uint32_t read, sr;
   group_identity(A, g, gs, read, sr);
   const uint32_t iter = A.group_iter ? A.group_iter[g] : 0;
@@ -873,6 +883,7 @@ __global__ void __launch_bounds__(128) chain_maxmatch_kernel(chain_args A, uint8
     const uint32_t N = (uint32_t)(A.group_start[g + 1] - gs);
     const uint64_t key = A.keys[gs];
     const uint32_t read = (uint32_t)(key >> 32), sr = (uint32_t)key;
+    if(sr == A.iv.nseq_all) continue;              // hits that belong to no super-read
     uint8_t* rem = removed + gs;
     for(uint32_t t = lane; t < N; t += 32) rem[t] = 0;
     __syncwarp();
@@ -978,7 +989,8 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
   if(g_chain_trace && getenv("MR_TRACE_CYCLES")) { MR_TRY(dbg.ensure(ctx, G * 4)); cudaMemset(dbg.p, 0, G * 4); A.dbg_cycles = dbg.as<uint32_t>(); }
   if(g_chain_trace) { cudaStreamSynchronize(ctx->stream); g_trace_t0 = trace_now(); }
   // (with parity taps on, single-hit groups also go through the strand kernels so that their taps get written)
-  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.pays, A.chain_pay, A.group_nb,
+  classify_groups_kernel<<<div_up(G, 256), 256, 0, ctx->stream>>>(A.group_start, G, A.group_read ? nullptr : A.keys, A.iv.nseq_all,
+                                                                  A.pays, A.chain_pay, A.group_nb, A.tap_lens,
                                                                   A.tap_lens == nullptr && !A.max_match, A.window > 1, cls, ctr);
   MR_LAUNCHED(ctx);
   CHAIN_TRACE(ctx->stream, "classify");

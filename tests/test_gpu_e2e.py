@@ -349,6 +349,27 @@ def test_tiles_staged_without_bulk_copies_give_the_same_records(tmpdir_session, 
     assert open(a).read() == open(b).read() and len(open(a).read()) > 10000
 
 
+@pytest.mark.parametrize("env", [{"MR_READ_SORT": "0"}, {"MR_READ_SORT": "1", "MR_GSORT_CAP": "64"},
+                                 {"MR_READ_SORT": "1", "MR_GSORT_THREADS": "512"}, {"MR_READ_SORT": "1", "MR_GSORT_CAP": "1024"}])
+def test_grouping_routes_give_the_same_records(tmpdir_session, tmp_path, env):
+    """Hits are grouped by (read, super-read) one CTA per read in shared memory (default), by the same CTA out of global
+    memory when a read's hits do not fit (MR_GSORT_CAP lowers what fits), or by the device-wide radix sort
+    (MR_READ_SORT=0): the records are the same bytes, and the reference's on the fixture."""
+    meta = json.load(open(os.path.join(GOLD, "synth_g1.json")))
+    cfg = meta["config"]
+    fix = gen_synth(os.path.join(tmpdir_session, "e2e_synth_g1"), **cfg["gen"])
+    out_u = str(tmp_path / "cmr_u.txt")
+    run([CMR, "-s", "1M", "-m", str(cfg["mer"]), "--psa-min", str(cfg["psa_min"]), "-k", str(cfg["unitig_k"]),
+         "-r", fix["sr"], "-p", fix["reads"], "-u", fix["unitigs"], "-t", "2", "-o", out_u], env=dict(os.environ, **env))
+    assert sha(open(out_u, "rb").read()) == meta["cmr_with_sequences_sha256_t1"]
+    info = gen_synth(os.path.join(tmpdir_session, "e2e_group"), 300000, coverage=4, read_len=4000, seed=29, repeat_frac=0.15)
+    cmd = [CMR, "-s", "1M", "-m", "15", "-k", "41", "-u", info["unitigs"], "-r", info["sr"], "-p", info["reads"]]
+    a, b = str(tmp_path / "default.txt"), str(tmp_path / "route.txt")
+    run(cmd + ["-o", a])
+    run(cmd + ["-o", b], env=dict(os.environ, **env))
+    assert open(a).read() == open(b).read() and len(open(a).read()) > 10000
+
+
 def test_fastq_and_multiple_files(tmpdir_session, tmp_path, port):
     info = gen_synth(os.path.join(tmpdir_session, "e2e_fq"), 100000, coverage=3, read_len=3000, seed=5)
     from oracle_lib import read_fasta

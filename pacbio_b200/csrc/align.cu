@@ -1269,8 +1269,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   MR_CUDA(ctx, cudaMemsetAsync(ws.counters.p, 0, 16 * sizeof(uint64_t), st));
   unsigned long long* ctr = ws.counters.as<unsigned long long>();
   // counters: 0 lookups, 1 raw hits, 2 invalid hits, 3 groups, 4 survivors, 5 info total, 6 tails, 7 fine hits,
-  // 9 lists, 10 buckets, 11 tile overflow, 12 most rows of a read, 13 hits of reads too large for the per-read sort,
-  // 14 groups of hits that belong to no super-read
+  // 9 lists, 10 buckets, 11 tile overflow, 12 most rows of a read, 14 groups of hits that belong to no super-read
   uint64_t h_ctr[16] = { 0 };
 
   // ---- seeds + lookups ----------------------------------------------------------------------------
@@ -1324,10 +1323,7 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
   if(ntiles) MR_CUDA(ctx, cudaMemcpyAsync(ws.hit_off.as<uint64_t>() + ntiles, ctr + 1, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
   int sr_bits = 1;
   while((1ULL << sr_bits) <= (uint64_t)iv.nseq_all) ++sr_bits;
-  const uint32_t read_sort_cap = group_sort_capacity(sr_bits);
-  if(ntiles && read_sort_cap)
-    MR_TRY(launch_read_hits_stats(ctx, ws.hit_off.as<uint64_t>(), ws.tile_first.as<uint32_t>(), nreads, read_sort_cap, ctr + 13));
-  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 14 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(ctx, cudaMemcpyAsync(h_ctr, ctr, 12 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   MR_CUDA(ctx, ctx->wait(st));
   if(h_ctr[11]) return ctx->fail(MR_ELIMIT, "mr_align_batch: 2^32 or more hits in one 1024-base tile; use --max-count");
   const uint64_t H = h_ctr[1];
@@ -1359,12 +1355,11 @@ static int align_batch_impl(mr_context* ctx, mr_index* idx, const mr_params* p, 
                                                          ws.key0.as<uint64_t>(), ws.pay0.as<uint64_t>(), ctr + 2);
     MR_LAUNCHED(ctx);
     timer.next("group sort");
-    // Grouping by (read, super-read).  Reads whose hits fit one SM's shared memory (nearly all of them, away from
-    // repeats) are sorted one CTA per read (group.cu): 33 bytes of HBM traffic per hit.  When reads that do not fit
-    // hold a quarter of the batch's hits or more (the human-size shape) the device-wide radix sort does it.
-    // MR_READ_SORT=0 / 1 forces one or the other.
-    static const int read_sort_env = getenv("MR_READ_SORT") ? atoi(getenv("MR_READ_SORT")) : -1;
-    const bool read_sort = read_sort_cap != 0 && (read_sort_env >= 0 ? read_sort_env != 0 : h_ctr[13] * 4 < H);
+    // Grouping by (read, super-read): one CTA per read (group.cu), in shared memory when the read's hits fit,
+    // through one cut by the top bits of the super-read index when they do not.  An index of more than 2^25
+    // super-reads, or MR_READ_SORT=0, takes the device-wide radix sort instead.
+    static const bool read_sort_on = !(getenv("MR_READ_SORT") && atoi(getenv("MR_READ_SORT")) == 0);
+    const bool read_sort = read_sort_on && group_sort_usable(sr_bits);
     uint64_t *alt_key, *alt_pay;
     if(read_sort) {
       MR_TRY(ws.head.ensure(ctx, H + 2));

@@ -11,11 +11,12 @@ struct group_sort_args {
   uint32_t nseq_all;                          // super-read index of the hits that belong to no super-read
   int      sr_bits;                           // nseq_all < 2^sr_bits
   unsigned long long* n_invalid_groups;       // counts the reads that have such hits (each is one group)
-  uint32_t cap, idx_bits;                     // filled by launch_group_sort
+  // filled by launch_group_sort: a read of at most `cap` hits is sorted whole in shared memory as words of
+  // (super-read << idx_bits | position); larger reads are cut into buckets first, and runs of buckets of at most
+  // range_cap hits are sorted as words of (super-read - base of the run << range_idx_bits | position)
+  uint32_t cap, idx_bits, range_cap, range_idx_bits;
 };
 
-// hits one CTA sorts in shared memory for an index whose super-read numbers take sr_bits bits (0: never)
-uint32_t group_sort_capacity(int sr_bits);
-int launch_read_hits_stats(mr_context* ctx, const uint64_t* hit_off, const uint32_t* tile_first, uint32_t nreads, uint32_t cap,
-                           unsigned long long* big_hits);
+// whether the per-read sort handles an index whose super-read numbers take sr_bits bits
+bool group_sort_usable(int sr_bits);
 int launch_group_sort(mr_context* ctx, group_sort_args A, uint32_t nreads);

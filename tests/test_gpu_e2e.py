@@ -349,12 +349,14 @@ def test_tiles_staged_without_bulk_copies_give_the_same_records(tmpdir_session, 
     assert open(a).read() == open(b).read() and len(open(a).read()) > 10000
 
 
-@pytest.mark.parametrize("env", [{"MR_READ_SORT": "0"}, {"MR_READ_SORT": "1", "MR_GSORT_CAP": "64"},
-                                 {"MR_READ_SORT": "1", "MR_GSORT_THREADS": "512"}, {"MR_READ_SORT": "1", "MR_GSORT_CAP": "1024"}])
+@pytest.mark.parametrize("env", [{"MR_READ_SORT": "0"}, {"MR_GSORT_CAP": "32"}, {"MR_GSORT_CAP": "256"},
+                                 {"MR_GSORT_THREADS": "1024"}, {"MR_GSORT_THREADS": "1024", "MR_GSORT_CAP": "1024"},
+                                 {"MR_GSORT_BALLOT": "1"}, {"MR_FINISH_QUAD": "1"}])
 def test_grouping_routes_give_the_same_records(tmpdir_session, tmp_path, env):
-    """Hits are grouped by (read, super-read) one CTA per read in shared memory (default), by the same CTA out of global
-    memory when a read's hits do not fit (MR_GSORT_CAP lowers what fits), or by the device-wide radix sort
-    (MR_READ_SORT=0): the records are the same bytes, and the reference's on the fixture."""
+    """Hits are grouped by (read, super-read) one CTA per read: in shared memory when the read's hits fit (default for
+    these inputs), cut into buckets by the top bits of the super-read index first when they do not, by passes out of
+    global memory for a bucket that still does not fit (MR_GSORT_CAP lowers what fits: 32 sends whole buckets there);
+    or by the device-wide radix sort (MR_READ_SORT=0).  The records are the same bytes, and the reference's on the fixture."""
     meta = json.load(open(os.path.join(GOLD, "synth_g1.json")))
     cfg = meta["config"]
     fix = gen_synth(os.path.join(tmpdir_session, "e2e_synth_g1"), **cfg["gen"])

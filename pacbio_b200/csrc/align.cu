@@ -1728,44 +1728,7 @@ static int pack_on_device(mr_context* ctx, const char* d_bases, uint64_t T, pack
 
 extern "C" {
 
-uint64_t mr_packed_code_words(uint64_t nbases) { return (nbases + 31) / 32 + 6; }
-uint64_t mr_packed_mask_words(uint64_t nbases) { return (nbases + 63) / 64 + 6; }
-
-// host packer: 32 characters -> one code word, 64 -> one mask word (same mapping as base_code on the device).
-// mr_pack_reads_range fills mask words [first_word, first_word + n_words) and the code words that go with them,
-// so that several host threads can pack disjoint word ranges of one batch.
-int mr_pack_reads_range(const char* bases, uint64_t nbases, uint64_t first_word, uint64_t n_words, uint64_t* codes, uint64_t* nmask) {
-  if((!bases && nbases) || !codes || !nmask) return MR_EINVAL;
-  static const struct lut_t {
-    uint8_t v[256];
-    lut_t() { for(int i = 0; i < 256; ++i) v[i] = 4; v['a'] = v['A'] = 0; v['c'] = v['C'] = 1; v['g'] = v['G'] = 2; v['t'] = v['T'] = 3; }
-  } lut;
-  const uint64_t cwords = mr_packed_code_words(nbases), mwords = mr_packed_mask_words(nbases);
-  const uint64_t end_word = std::min(mwords, first_word + n_words);
-  for(uint64_t w = first_word; w < end_word; ++w) {
-    uint64_t c0 = 0, c1 = 0, m = 0;
-    const uint64_t g = w * 64;
-    if(g + 64 <= nbases) {
-      const unsigned char* s = (const unsigned char*)bases + g;
-      for(int j = 0; j < 32; ++j) { const uint64_t c = lut.v[s[j]]; c0 |= (c & 3) << (2 * j); m |= (c >> 2) << j; }
-      for(int j = 0; j < 32; ++j) { const uint64_t c = lut.v[s[32 + j]]; c1 |= (c & 3) << (2 * j); m |= (c >> 2) << (32 + j); }
-    } else if(g < nbases) {
-      for(uint64_t j = 0; j < 64 && g + j < nbases; ++j) {
-        const uint64_t c = lut.v[(unsigned char)bases[g + j]];
-        if(j < 32) c0 |= (c & 3) << (2 * j); else c1 |= (c & 3) << (2 * (j - 32));
-        m |= (c >> 2) << j;
-      }
-    }
-    if(2 * w < cwords) codes[2 * w] = c0;
-    if(2 * w + 1 < cwords) codes[2 * w + 1] = c1;
-    nmask[w] = m;
-  }
-  return MR_OK;
-}
-
-int mr_pack_reads(const char* bases, uint64_t nbases, uint64_t* codes, uint64_t* nmask) {
-  return mr_pack_reads_range(bases, nbases, 0, mr_packed_mask_words(nbases), codes, nmask);
-}
+// (mr_packed_code_words / mr_packed_mask_words / mr_pack_reads / mr_pack_reads_range: pack_host.cpp)
 
 int mr_align_batch_device(mr_context* ctx, mr_index* idx, const mr_params* p, const char* d_bases,
                           const uint64_t* d_read_start, const uint64_t* h_read_start, uint32_t nreads, mr_result** out) {

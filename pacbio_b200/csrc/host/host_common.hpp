@@ -103,6 +103,9 @@ public:
 // once (by fwrite): a growable byte buffer that never zero-fills or re-copies its storage.  (Streaming
 // stores for the unitig sequences were measured too: faster in isolation, slower here, where the
 // buffers of a batch are reused and stay in the last-level cache.)
+// lowers the calling thread's priority below the threads that feed the GPUs (host_common.cpp)
+void background_thread();
+
 class text_buf {
   char*  p_ = nullptr;
   size_t size_ = 0, cap_ = 0;

@@ -169,6 +169,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   auto fail = [&](const std::string& msg) { std::lock_guard<std::mutex> l(error_mutex); if(error.empty()) error = msg; failed = true; };
 
   std::thread reader([&]() {
+    background_thread();
     try {
       read_stream rs(read_paths, host_threads);
       for(uint64_t seq = 0; ; ++seq) {
@@ -247,6 +248,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   }
 
   std::thread formatter([&]() {
+    background_thread();                       // (and so are the threads it starts: a new thread inherits the nice value)
     job j;
     std::vector<text_buf> parts;
     record_writer writer(out);

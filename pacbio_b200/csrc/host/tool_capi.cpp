@@ -125,6 +125,7 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
   bool   stop = false;
   std::string error, align_error;
   std::thread formatter([&]() {
+    mrh::background_thread();
     std::vector<mrh::text_buf>& parts = t->parts;
     for(size_t i = 0; i < nb; ++i) {
       mr_result* r = nullptr;

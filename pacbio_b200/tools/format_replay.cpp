@@ -31,6 +31,11 @@ int main(int argc, char** argv) {
       best = std::min(best, s);
       bytes = 0;
       for(auto& p : parts) bytes += p.size();
+      if(i == 0 && getenv("MR_REPLAY_PARTS")) {          // how even the split between the threads is
+        fprintf(stderr, "bytes per part:");
+        for(auto& p : parts) fprintf(stderr, " %zu", p.size());
+        fprintf(stderr, "\n");
+      }
     }
     printf("{\"reads\": %u, \"rows\": %llu, \"text_bytes\": %llu, \"threads\": %u, \"best_s\": %.6f, \"thread_seconds\": %.6f}\n",
            d.view.nreads, (unsigned long long)d.view.ncoords, (unsigned long long)bytes, threads, best, best * threads);

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -254,6 +255,31 @@ def test_pack_reads_layout():
         # nothing set past the last base
         for g in range(n, min(len(nmask) * 64, len(codes) * 32, n + 200)):
             assert (int(nmask[g // 64]) >> (g % 64)) & 1 == 0 and (int(codes[g // 32]) >> (2 * (g % 32))) & 3 == 0
+
+
+def test_pack_reads_vector_and_portable_forms_agree():
+    """The AVX2 packer (32 characters per step) and the byte-at-a-time one (MR_PACK_SCALAR=1) give the same words,
+    also when a batch is packed in disjoint word ranges by several threads (mr_pack_reads_range)."""
+    import hashlib
+    import subprocess
+    prog = ("import numpy as np, hashlib, ctypes as C, pacbio_b200.api as api\n"
+            "rng = np.random.default_rng(11)\n"
+            "seq = rng.choice(np.frombuffer(b'ACGTACGTACGTacgtNnRY-*', dtype=np.uint8), size=1000003)\n"
+            "codes, nmask = api.pack_reads(seq)\n"
+            "L = api.lib()\n"
+            "c2, m2 = np.full(len(codes), 7, np.uint64), np.full(len(nmask), 7, np.uint64)\n"
+            "L.mr_pack_reads_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]\n"
+            "cuts = [0, 1, 17, 5000, 5001, 15000, len(nmask)]\n"
+            "for a, b in zip(cuts, cuts[1:]):\n"
+            "    assert L.mr_pack_reads_range(seq.ctypes.data, len(seq), a, b - a, c2.ctypes.data, m2.ctypes.data) == 0\n"
+            "assert np.array_equal(codes, c2) and np.array_equal(nmask, m2)\n"
+            "print(hashlib.sha256(codes.tobytes() + nmask.tobytes()).hexdigest())\n")
+    outs = []
+    for env in ({}, {"MR_PACK_SCALAR": "1"}):
+        r = subprocess.run([sys.executable, "-c", prog], env=dict(os.environ, PYTHONPATH=ROOT, **env), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 64
 
 
 def _fnv(h, data):

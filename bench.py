@@ -178,6 +178,67 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+ALL_CPUS = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+
+
+PINNED = False
+
+
+def unpin():
+    """The subprocess arms (the reference binary, the drop-in binary) get every core of the box, whatever this rank is
+    pinned to: returns the preexec_fn to give subprocess.run (None when the rank is not pinned -- a preexec_fn makes
+    Python fork() the whole CUDA process instead of spawning)."""
+    if not (PINNED and ALL_CPUS):
+        return None
+    return lambda: os.sched_setaffinity(0, ALL_CPUS)
+
+
+def pin_rank(local_rank, nranks):
+    """One process per GPU on one box: every rank keeps to its own share of the cores, on the NUMA node its GPU hangs
+    off when the box says which (pinned host buffers are then allocated there too).  Without it the 8 ranks' threads
+    migrate over all 32 cores and half of the host<->device traffic crosses the socket link.  MR_BENCH_PIN=0: off."""
+    if nranks <= 1 or not ALL_CPUS or os.environ.get("MR_BENCH_PIN", "1") == "0":
+        return None
+    node_of = {}
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=30).stdout
+        for line in out.splitlines():
+            idx, bus = [x.strip() for x in line.split(",")]
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]                                       # 00000000:1b:00.0 -> 0000:1b:00.0
+            try:
+                node_of[int(idx)] = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+            except (OSError, ValueError):
+                pass
+    except Exception:                                               # noqa: BLE001
+        pass
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = [int(x) for x in visible.split(",")] if visible and all(x.strip().isdigit() for x in visible.split(",")) else list(range(nranks))
+    nodes = [node_of.get(phys[r] if r < len(phys) else r, -1) for r in range(nranks)]
+    mine = nodes[local_rank]
+    cpus = list(ALL_CPUS)
+    peers = list(range(nranks))
+    if mine >= 0 and all(n >= 0 for n in nodes):
+        try:
+            node_cpus = []
+            for part in open("/sys/devices/system/node/node%d/cpulist" % mine).read().strip().split(","):
+                a, _, b = part.partition("-")
+                node_cpus += list(range(int(a), int(b or a) + 1))
+            node_cpus = [c for c in node_cpus if c in set(ALL_CPUS)]
+            if node_cpus:
+                cpus, peers = node_cpus, [r for r in range(nranks) if nodes[r] == mine]
+        except (OSError, ValueError):
+            pass
+    k = peers.index(local_rank)
+    share = cpus[len(cpus) * k // len(peers): len(cpus) * (k + 1) // len(peers)] or cpus
+    os.sched_setaffinity(0, share)
+    global PINNED
+    PINNED = True
+    return {"cpus": "%d-%d" % (share[0], share[-1]) if share == list(range(share[0], share[-1] + 1)) else ",".join(map(str, share)),
+            "numa_node": mine}
+
+
 def dist_setup(n):
     """One process per GPU under torchrun.  NCCL carries only the barrier and the max-over-ranks of
     the timing (MR_BENCH_BACKEND=gloo runs the same plumbing on CPU for the tests)."""
@@ -267,7 +328,7 @@ def cpu_run(w, files, nreads_sample, threads):
     if os.path.exists(ref):
         cmd = [ref] + production_flags(w, files, threads) + ["-p", sample, "-o", out]
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError("reference run failed: " + r.stderr.decode()[-500:])
@@ -417,12 +478,14 @@ def cli_run(w, files, total_bases, host_threads, gpus=1):
     best = None
     for _ in range(2):                           # second run: page cache warm, as for the reference arm
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError("create_mega_reads failed: " + r.stderr.decode()[-300:])
         ph = {}
         for line in r.stderr.decode().splitlines():
+            if line.startswith("stage busy seconds"):
+                ph["stages"] = line.split(":", 1)[1].strip()
             if line.startswith("Starting ") and "..." in line:
                 try:
                     ph[line[9:line.index("...")].strip()] = float(line.split("...")[1].split()[0])
@@ -445,7 +508,7 @@ def cli_run(w, files, total_bases, host_threads, gpus=1):
         env_n = {k: v for k, v in env.items() if k != "MR_DEVICES"}
         env_n["MR_GPUS"] = str(gpus)
         t0 = time.perf_counter()
-        r = subprocess.run(cmd_n, env=env_n, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        r = subprocess.run(cmd_n, env=env_n, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             best["multi_gpu"] = {"gpus": gpus, "error": r.stderr.decode()[-300:]}
@@ -477,6 +540,7 @@ def ours(args, w, files):
     import pacbio_b200.api as api
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned = pin_rank(local_rank, args.gpus if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 1)
     dist = dist_setup(args.gpus)
     torch.cuda.set_device(local_rank)
     L = api.lib()                                   # raises if the CUDA library is missing
@@ -553,7 +617,7 @@ def ours(args, w, files):
     if total_bases < 0:
         raise RuntimeError(H.mrh_tool_error(tool).decode())
     nbatches = int(H.mrh_tool_nbatches(tool))
-    host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, args.gpus))
+    host_threads = args.host_threads or max(1, (len(os.sched_getaffinity(0)) if pinned else (os.cpu_count() or 1) // max(1, args.gpus)))
 
     # ---- device-resident copies of every batch ------------------------------------------------------
     # (the form a batch travels and is aligned in: 2 bits per base + a non-ACGT mask, mr_pack_reads)
@@ -753,7 +817,7 @@ def ours(args, w, files):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
                 "data": "synthetic", "config": config_dict(args, w),
-                "run": {"streams_per_gpu": nstreams, "fine_mer": args.fine_mer, "shard_of_rank0": files["shard"]},
+                "run": {"streams_per_gpu": nstreams, "fine_mer": args.fine_mer, "shard_of_rank0": files["shard"], "rank0_pinned_to": pinned},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(stats[1]),
                         "d2h_bytes_per_step": int(stats[2]), "ms_per_step": 1e3 * e2e_s_max / args.steps,

@@ -150,8 +150,8 @@ int main(int argc, char* argv[]) {
     dstate.errors = P.errors; dstate.bases = P.bases;
     mrh::text_buf dot_text;
     const uint64_t nb = mrh::run_pipeline(DS, pacbio, P,
-      [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<mrh::text_buf>& parts) {
-        if(!dot_file) { mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts); return; }
+      [&](const mr_result*, const mr_result_view& v, const mrh::read_batch& b, std::vector<mrh::text_buf>& parts, const mrh::emit_fn& emit) {
+        if(!dot_file) { mrh::format_mega_reads_mt(v, b, SR, U, G, fthreads, parts, &emit); return; }
         parts.resize(1);
         parts[0].clear(); dot_text.clear();
         mrh::format_mega_reads(v, b, 0, v.nreads, SR, U, G, parts[0], &dot_text, &dstate);

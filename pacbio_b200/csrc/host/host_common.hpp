@@ -3,6 +3,7 @@
 // device's coords / graph rows into the reference's text records.  Plain C++17, no CUDA; the
 // device is reached only through include/mega_reads_b200.h.
 #pragma once
+#include <functional>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -58,8 +59,16 @@ struct read_batch {
   std::vector<uint64_t>    codes, nmask;
   uint32_t nreads() const { return (uint32_t)name.size(); }
   void clear() { bases.clear(); start.assign(1, 0); name.clear(); codes.clear(); nmask.clear(); }
+  // The pipeline page-locks the packed arrays of the batches it recycles (plain DMA instead of a staged copy);
+  // before_regrow is its hook to unlock them before a resize moves them.
+  std::function<void(read_batch&)> before_regrow;
+  const void* locked[2] = { nullptr, nullptr };
+  void size_packed(uint64_t cwords, uint64_t mwords) {
+    if((cwords > codes.capacity() || mwords > nmask.capacity()) && before_regrow) before_regrow(*this);
+    codes.resize(cwords); nmask.resize(mwords);
+  }
   void pack() {
-    codes.resize(mr_packed_code_words(bases.size())); nmask.resize(mr_packed_mask_words(bases.size()));
+    size_packed(mr_packed_code_words(bases.size()), mr_packed_mask_words(bases.size()));
     mr_pack_reads(bases.data(), bases.size(), codes.data(), nmask.data());
   }
   bool packed() const { return !nmask.empty(); }
@@ -153,8 +162,10 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
                        text_buf* dot = nullptr, dot_state* ds = nullptr);
 // same, fanned out over `threads` host threads; parts[0], parts[1], ... concatenated are the records
 // in read order (kept apart so that nobody has to copy hundreds of megabytes of text once more)
+// With `emit`: the batch is formatted slice by slice, emit(parts) consumes the text of each slice (host_common.cpp).
+typedef std::function<void(std::vector<text_buf>&)> emit_fn;
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
-                          const graph_options& o, unsigned threads, std::vector<text_buf>& parts);
+                          const graph_options& o, unsigned threads, std::vector<text_buf>& parts, const emit_fn* emit = nullptr);
 
 // Debug / profiling aid: one batch's result rows + read names on disk (MR_DUMP_BATCH=<file> in the bench's
 // host path writes the first batch), read back by pacbio_b200/tools/format_replay to time the

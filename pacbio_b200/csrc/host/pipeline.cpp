@@ -1,4 +1,5 @@
 #include "pipeline.hpp"
+#include <chrono>
 
 #include <atomic>
 #include <cstdio>
@@ -168,6 +169,36 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   std::atomic<bool> failed(false);       // what the worker threads test; the text stays under the mutex
   auto fail = [&](const std::string& msg) { std::lock_guard<std::mutex> l(error_mutex); if(error.empty()) error = msg; failed = true; };
 
+  // Batches are recycled: a fresh one costs the reader 45 MB of first-touch page faults and zero fill (a third of its
+  // time per batch); the formatter hands a batch back once its records are out.
+  std::vector<std::unique_ptr<read_batch>> pool;
+  std::mutex pool_mutex;
+  // The packed arrays of a recycled batch are page-locked once (cudaHostRegister: ~2 ms for 13 MB), so that the copy
+  // to the device is plain DMA; a copy from pageable memory is staged by the driver and, next to a reader that
+  // faults pages in all the time, took most of the 40 ms a batch spent in mr_align_batch (against 7.5 from locked memory).
+  auto unlock_batch = [&](read_batch& b) {
+    for(int i = 0; i < 2; ++i) if(b.locked[i]) { mr_host_unpin(ds.ctx[0], b.locked[i]); b.locked[i] = nullptr; }
+  };
+  auto lock_batch = [&](read_batch& b) {
+    const void* p[2] = { b.codes.data(), b.nmask.data() };
+    const size_t n[2] = { b.codes.capacity() * 8, b.nmask.capacity() * 8 };
+    for(int i = 0; i < 2; ++i) {
+      if(b.locked[i] == p[i] || !p[i]) continue;
+      if(b.locked[i]) { mr_host_unpin(ds.ctx[0], b.locked[i]); b.locked[i] = nullptr; }
+      if(mr_host_pin(ds.ctx[0], p[i], n[i]) == MR_OK) b.locked[i] = p[i];
+    }
+  };
+  auto recycle = [&](std::unique_ptr<read_batch>& b) {
+    if(!b) return;
+    std::lock_guard<std::mutex> l(pool_mutex);
+    if(pool.size() < 16) pool.push_back(std::move(b));
+    else { unlock_batch(*b); b.reset(); }
+  };
+  // MR_SHOW_TIMING: seconds every stage was busy (the stages overlap; the largest one bounds the phase)
+  static const bool stage_timing = getenv("MR_SHOW_TIMING") != nullptr;
+  std::atomic<uint64_t> busy_read_us(0), busy_upload_us(0), busy_align_us(0), busy_format_us(0), busy_write_us(0);
+  auto now_us = []() { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+
   std::thread reader([&]() {
     background_thread();
     try {
@@ -175,9 +206,16 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       for(uint64_t seq = 0; ; ++seq) {
         job j;
         j.seq = seq;
-        j.batch.reset(new read_batch);
+        {
+          std::lock_guard<std::mutex> l(pool_mutex);
+          if(!pool.empty()) { j.batch = std::move(pool.back()); pool.pop_back(); }
+        }
+        if(!j.batch) { j.batch.reset(new read_batch); j.batch->before_regrow = unlock_batch; }
         j.batch->clear();
-        if(!rs.next_batch(*j.batch, batch_bases, batch_reads, true)) break;      // parsed and packed by the reader's workers
+        const uint64_t t0 = now_us();
+        const bool more = rs.next_batch(*j.batch, batch_bases, batch_reads, true);      // parsed and packed by the reader's workers
+        busy_read_us += now_us() - t0;
+        if(!more) break;
         total_bases += j.batch->bases.size();
         to_align.push(std::move(j));
       }
@@ -198,9 +236,12 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       while(to_align.pop(j)) {
         staged_job sj;
         sj.staged = nullptr;
+        const uint64_t t0 = now_us();
         if(!j.batch->packed()) j.batch->pack();  // 2 bits per base + non-ACGT mask: what crosses PCIe
+        lock_batch(*j.batch);
         if(stage_batches() && !failed && mr_stage_batch_packed(ds.ctx[g], j.batch->codes.data(), j.batch->nmask.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
+        busy_upload_us += now_us() - t0;
         sj.j = std::move(j);
         staged[g]->push(std::move(sj));
       }
@@ -215,6 +256,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
         // in halves and retried; the halves are formatted in order, so the output does not change.
         std::deque<std::unique_ptr<read_batch>> work;
         work.push_back(std::move(j.batch));
+        const uint64_t t0 = now_us();
         while(!work.empty() && !failed) {
           std::unique_ptr<read_batch> b = std::move(work.front());
           work.pop_front();
@@ -237,10 +279,12 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
             hi->name.assign(b->name.begin() + half, b->name.end());
             work.push_front(std::move(hi));
             work.push_front(std::move(lo));
+            unlock_batch(*b);                   // (the whole batch is dropped here; its halves are plain batches)
             continue;
           }
           fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g]));
         }
+        busy_align_us += now_us() - t0;
         to_format.push(std::move(j));
       }
       if(--live == 0) to_format.close();
@@ -261,9 +305,14 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           mr_result_view v;
           mr_result_get(pt.result, &v);
           for(auto& p : parts) p.clear();
-          try { format(pt.result, v, *pt.batch, parts); } catch(std::exception& e) { fail(e.what()); }
-          if(!writer.write(parts)) fail("write error on output file");
+          uint64_t wrote_us = 0;
+          const emit_fn emit = [&](std::vector<text_buf>& ps) { const uint64_t w0 = now_us(); if(!writer.write(ps)) fail("write error on output file"); wrote_us += now_us() - w0; };
+          const uint64_t t0 = now_us();
+          try { format(pt.result, v, *pt.batch, parts, emit); } catch(std::exception& e) { fail(e.what()); }
+          emit(parts);
+          busy_format_us += now_us() - t0 - wrote_us; busy_write_us += wrote_us;
           mr_result_free(pt.result);
+          recycle(pt.batch);
         }
         waiting.erase(it);
       }
@@ -277,6 +326,10 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   for(auto& t : aligners) t.join();
   formatter.join();
   fflush(out);
+  for(auto& b : pool) unlock_batch(*b);
+  if(stage_timing)
+    fprintf(stderr, "stage busy seconds (overlapping): read+pack %.3f, upload %.3f (%zu threads), align %.3f (%zu threads), format %.3f, write %.3f\n",
+            1e-6 * busy_read_us, 1e-6 * busy_upload_us, ds.ctx.size(), 1e-6 * busy_align_us, ds.ctx.size(), 1e-6 * busy_format_us, 1e-6 * busy_write_us);
   if(!error.empty()) throw std::runtime_error(error);
   return total_bases;
 }

@@ -73,7 +73,9 @@ bool stage_batches();
 // adds per_device - 1 more contexts for every device of ds, sharing the device's index
 void add_streams(device_set& ds, unsigned per_device);
 
-typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<text_buf>&)> format_fn;
+// format(result, view, batch, parts, emit): leaves the batch's text in parts[] (written by the pipeline when it
+// returns) and / or hands it over piecewise through emit(parts) on the way (format_mega_reads_mt)
+typedef std::function<void(const mr_result*, const mr_result_view&, const read_batch&, std::vector<text_buf>&, const emit_fn&)> format_fn;
 
 // runs the whole stream; returns the number of read bases processed
 // host_threads: workers of the reader (parsing, packing); 0 = as many as the box has, up to 16

@@ -145,11 +145,13 @@ int64_t mrh_tool_run_range(void* p, unsigned threads, const char* out_path, uint
         if(*dump && !dumped.exchange(true) && !mrh::dump_result(dump, v, *b)) fprintf(stderr, "MR_DUMP_BATCH: cannot write %s\n", dump);
       }
       try {
-        mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, parts);
-        for(const auto& text : parts) {
-          if(out) fwrite(text.data(), 1, text.size(), out);
-          t->last_text_bytes += text.size();
-        }
+        const mrh::emit_fn emit = [&](std::vector<mrh::text_buf>& ps) {
+          for(const auto& text : ps) {
+            if(out) fwrite(text.data(), 1, text.size(), out);
+            t->last_text_bytes += text.size();
+          }
+        };
+        mrh::format_mega_reads_mt(v, *b, t->SR, t->U, t->G, threads, parts, &emit);
       } catch(std::exception& e) { error = e.what(); }
       t->last_h2d_bytes += (b->codes.size() + b->nmask.size() + b->nreads() + 1) * 8ULL;
       uint64_t info = 0;

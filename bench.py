@@ -784,10 +784,15 @@ def ours(args, w, files):
                 "random_access": rnd,
                 "dram_gbs_from_traffic": (traffic / (phase[kern] / launches_k) / 1e9) if traffic else None,
                 "lookup_table_bytes": int(L.mr_index_table_bytes(idx)), "index_parts": nparts,
-                "note": "random gathers into the prefix table and the tail array of the index (lookup_table_bytes over index_parts "
-                        "parts): bounded by random-access throughput (random_access), not by streaming bandwidth; with "
-                        "streams_per_gpu > 1 the launch runs next to the other stream's kernels, so avg_launch_ms is its duration "
-                        "while sharing the GPU; the chaining kernels (phase 'chain coords') are latency/issue bound, see profiles/",
+                "note": "random gathers into the bucket-bound records and the tail array of the index (lookup_table_bytes over "
+                        "index_parts parts).  When those tables fit the L2 (the yeast-size index: l2_hit_rate_ncu 0.88) the kernel "
+                        "is bound by instruction issue (ncu: 70 % of the issue slots, 20 of 32 lanes active), so neither frac "
+                        "(streaming bytes) nor random_access.frac (L2-resident random accesses) reaches 1; when they do not (the "
+                        "human-size index) by the rate of random DRAM accesses (random_access, 1 GiB-table ceiling).  traffic is "
+                        "below the algorithmic bytes because the table reads are L2 hits.  With streams_per_gpu > 1 the launch "
+                        "runs next to the other stream's kernels, so avg_launch_ms is its duration while sharing the GPU; the "
+                        "chaining kernels (phase 'chain coords') are bound by FP64 issue slots and shared-memory latency, see "
+                        "DESIGN.md section 4 and profiles/",
                 "phases_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()}}
 
     # ---- CPU baseline + parity gate (rank 0; every N) ----------------------------------------------------

@@ -93,6 +93,12 @@ class read_stream {
   char   kind_ = 0;                       // '>' or '@': format of the current file
   unsigned threads_;
   std::vector<piece> pieces_;
+  // records of a mapped FASTA file found ahead of the batches, by all threads at once (prescan)
+  struct prerec { uint64_t name_b; uint32_t name_len; uint32_t npieces; uint64_t first_piece, len, end_pos; };
+  std::vector<prerec> pre_;
+  std::vector<piece>  pre_pieces_;
+  size_t pre_next_ = 0;
+  bool prescan();
   bool open_next();
   void close_current();
   bool refill();                          // stream mode: more bytes behind the window; false at end of file
@@ -134,6 +140,7 @@ public:
   void clear() { size_ = 0; }
   void reserve(size_t n) { if(n > cap_) grow(n); }
   void append(const char* s, size_t n);
+  char* grab(size_t n) { if(size_ + n > cap_) grow(size_ + n); char* w = p_ + size_; size_ += n; return w; }   // n bytes for the caller to fill
   void flush();
   text_buf& operator+=(char c) { if(size_ + 1 > cap_) grow(size_ + 1); p_[size_++] = c; return *this; }
   text_buf& operator+=(const char* s) { append(s, strlen(s)); return *this; }

@@ -334,6 +334,24 @@ def test_read_stream_parses_fasta_fastq_files_and_pipes(tmp_path):
 
     for batch, threads in ((1 << 30, 4), (5000, 3), (1, 1), (40000, 8)):
         assert parse([fa1, fa2, fq], batch, threads) == want
+    # a mapped FASTA file of several MB: its records are found by all threads at once (read_stream::prescan), each
+    # thread starting at the first '>' that begins a line inside its share; one thread takes the serial scanner
+    big = str(tmp_path / "big.fa")
+    with open(big, "w", newline="") as f:
+        for i in range(900):
+            s = "".join(rnd.choice("ACGTN") for _ in range(rnd.choice([0, 7, 2000, 9000, 20011])))
+            f.write(">big%d with a > sign and\ttabs%s" % (i, "\r\n" if i % 5 == 0 else "\n"))
+            cols = rnd.choice([60, 70, 20011])
+            for j in range(0, len(s), cols):
+                f.write(s[j:j + cols] + ("\r\n" if i % 5 == 0 else "\n"))
+            if i % 7 == 0:
+                f.write("\n")
+    assert os.path.getsize(big) > (4 << 20)
+    serial = parse([big], 1 << 21, 1)
+    assert serial[0] == 900
+    for batch, threads in ((1 << 21, 8), (1 << 30, 5), (30000, 3)):
+        assert parse([big, fa2], batch, threads)[:2] == [serial[0] + 21, serial[1] + len("".join(s for _, s in recs[20:40])) + 9]
+        assert parse([big], batch, threads) == serial
     # the same bytes through a pipe (stream mode: no mmap, no seek)
     fifo = str(tmp_path / "pipe.fa")
     os.mkfifo(fifo)

@@ -1697,6 +1697,7 @@ static int align_checked(mr_context* ctx, mr_index* idx, const mr_params* p, con
     // a failed batch may have left kernels of the chain tiers running on the side streams: the caller
     // retries with a smaller batch, which re-sizes the very buffers they use
     for(cudaStream_t s : ctx->aux) if(s) cudaStreamSynchronize(s);
+    for(cudaStream_t s : ctx->hi) if(s) cudaStreamSynchronize(s);
     cudaGetLastError();
   }
   return rc;

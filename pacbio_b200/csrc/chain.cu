@@ -1143,13 +1143,24 @@ int launch_chain(mr_context* ctx, chain_args A, dev_buf& lists) {
       // are the scarce resource, and the quad form spends 1.75 FP64 warp instructions per hit and chain where the
       // thread form spends 0.8.
       static const bool tile_finish = !(getenv("MR_FINISH_QUAD") && atoi(getenv("MR_FINISH_QUAD")) != 0);
+      // The coords kernel runs on a stream of the highest priority: the chaining kernels of the other tiers are
+      // persistent and fill every SM, and their blocks still waiting for a slot would otherwise be served before the
+      // coords blocks of a tier that is already chained (timeline: coords of the longest tier ready at 0.16 ms, done
+      // at 1.1).  MR_FINISH_PRIORITY=0: the tier's own stream.
+      static const bool prio = !(getenv("MR_FINISH_PRIORITY") && atoi(getenv("MR_FINISH_PRIORITY")) == 0);
+      cudaStream_t fs = st;
+      if(prio && ctx->hi[c - 1]) {
+        fs = ctx->hi[c - 1];
+        MR_CUDA(ctx, cudaEventRecord(ctx->ev_hi[c - 1], st));
+        MR_CUDA(ctx, cudaStreamWaitEvent(fs, ctx->ev_hi[c - 1], 0));
+      }
       const uint32_t lo = c == kSmemTiers && A.window > 1 ? kTierCapHost[0] : 0u;
-      if(tile_finish) finish_tile_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(A, list, ctr + c, kThreadFinishLongMax, lo);
-      else            finish_quad_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(A, list, ctr + c, kThreadFinishLongMax, lo);
+      if(tile_finish) finish_tile_kernel<<<ctx->sm_count * 4, 128, 0, fs>>>(A, list, ctr + c, kThreadFinishLongMax, lo);
+      else            finish_quad_kernel<<<ctx->sm_count * 8, 128, 0, fs>>>(A, list, ctr + c, kThreadFinishLongMax, lo);
       MR_LAUNCHED(ctx);
-      tl.close(st);
-      if(g_chain_trace) { snprintf(label, sizeof label, "finish, tier %d", c); CHAIN_TRACE(st, label); }
-      MR_CUDA(ctx, cudaEventRecord(ctx->ev[c], st));
+      tl.close(fs);
+      if(g_chain_trace) { snprintf(label, sizeof label, "finish, tier %d", c); CHAIN_TRACE(fs, label); }
+      MR_CUDA(ctx, cudaEventRecord(ctx->ev[c], fs));
     } else {
       // (--window-size > 1: the small groups were chained by the global-memory kernel on its own stream)
       if(A.window > 1) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[kSmemTiers], 0));

@@ -23,7 +23,9 @@ struct mr_context {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host -> device copies of staged batches (mr_stage_batch)
   cudaStream_t aux[9] = { };   // side streams for kernels that may overlap (chain tiers)
+  cudaStream_t hi[9] = { };    // the same at the highest priority: the coords kernel that follows a tier's chaining kernel
   cudaEvent_t  ev[10] = { };
+  cudaEvent_t  ev_hi[9] = { };
   std::string  err;
   uint64_t     launches = 0;
   bool         keep_taps = false;

@@ -48,8 +48,14 @@ int mr_context_create(int device, mr_context** out) {
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if(e != cudaSuccess) { g_mr_create_error = cudaGetErrorString(e); return MR_ECUDA; }
   for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+  {
+    int least = 0, greatest = 0;
+    if(cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); greatest = 0; }
+    for(auto& a : ctx->hi) if(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); a = nullptr; }
+  }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for(auto& v : ctx->ev) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+  for(auto& v : ctx->ev_hi) cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
   {
     const char* env = getenv("MR_BLOCKING_SYNC");
     const unsigned cores = std::thread::hardware_concurrency();
@@ -67,6 +73,8 @@ void mr_context_destroy(mr_context* ctx) {
   if(ctx->stream) cudaStreamSynchronize(ctx->stream);
   if(ctx->ws) mr_workspace_free(ctx->ws);
   for(auto& a : ctx->aux) if(a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+  for(auto& a : ctx->hi) if(a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+  for(auto& v : ctx->ev_hi) if(v) cudaEventDestroy(v);
   if(ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for(auto& v : ctx->ev) if(v) cudaEventDestroy(v);
   if(ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);

@@ -6,7 +6,7 @@
 Workload (config.workload): BASELINE.json configs[1] -- synthetic yeast-size genome (12 Mbp),
 super-reads k-unitig K=41, 50x simulated 10 kbp PacBio reads at 12 % error, production flags
 (-m 15 --psa-min 13 --stretch-cap 10000 -B 17 -d 0.029 --max-count 5000, -u unitigs).  One step ==
-one pass of the whole read set through the hot path, as a sequence of 32-Mbase batches.
+one pass of the whole read set through the hot path, as a sequence of 64-Mbase batches.
 
   value : device-timed (CUDA events on the library's stream), read batches already resident in HBM,
           every kernel of mr_align_batch_device plus its result download
@@ -63,7 +63,7 @@ def parse_args():
                          "the GPUs given -- 3.1 Gbp genome with 20 %% repeats, > 2^32 super-read bases (an index of several parts), "
                          "15 kbp reads at 15 %% error, a 0.2x slice of reads per GPU unless --coverage is given")
     ap.add_argument("--host-threads", type=int, default=0)
-    ap.add_argument("--batch-bases", type=int, default=32 << 20)
+    ap.add_argument("--batch-bases", type=int, default=64 << 20)
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="mega_reads", choices=["mega_reads", "lookup"],

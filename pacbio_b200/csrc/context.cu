@@ -47,10 +47,13 @@ int mr_context_create(int device, mr_context** out) {
   }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if(e != cudaSuccess) { g_mr_create_error = cudaGetErrorString(e); return MR_ECUDA; }
-  for(auto& a : ctx->aux) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
   {
     int least = 0, greatest = 0;
     if(cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); greatest = 0; }
+    // MR_CHAIN_PRIORITY=1: the chaining kernels' streams above the main stream too (one step below the coords kernels)
+    const char* cp = getenv("MR_CHAIN_PRIORITY");
+    const int aux_prio = cp && atoi(cp) != 0 ? std::min(0, greatest + 1) : 0;
+    for(auto& a : ctx->aux) if(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, aux_prio) != cudaSuccess) { cudaGetLastError(); a = nullptr; }
     for(auto& a : ctx->hi) if(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); a = nullptr; }
   }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);

@@ -159,6 +159,12 @@ struct record_writer {
 
 uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths, const mr_params& params,
                       const format_fn& format, FILE* out, unsigned host_threads) {
+  // 32 Mbases per batch.  The library itself does better with 64 (bench.py's default: 9.8 against 9.1 Gbases/s on the
+  // yeast shape, 0.84 against 0.66 on the human one -- fewer synchronisation points, twice the groups per launch of the
+  // persistent chaining kernels), but the tools are bound by their reader (~2 Gbases/s), and page-locking the packed
+  // arrays of the recycled batches (24 MB each at 64 Mbases; cudaHostRegister also holds up the kernel launches of
+  // the aligner threads while it runs) only pays off over more batches than a short run has: create_mega_reads on
+  // 0.6 Gbases of reads took 0.34 s with 32-Mbase batches and 1.5 s with 64.  MR_BATCH_BASES overrides.
   uint64_t batch_bases = 32ULL << 20;
   if(const char* e = getenv("MR_BATCH_BASES")) batch_bases = strtoull(e, nullptr, 0);
   const uint32_t batch_reads = 1u << 20;

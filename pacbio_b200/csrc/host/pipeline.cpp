@@ -179,31 +179,50 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   // time per batch); the formatter hands a batch back once its records are out.
   std::vector<std::unique_ptr<read_batch>> pool;
   std::mutex pool_mutex;
-  // The packed arrays of a recycled batch are page-locked once (cudaHostRegister: ~2 ms for 13 MB), so that the copy
-  // to the device is plain DMA; a copy from pageable memory is staged by the driver and, next to a reader that
-  // faults pages in all the time, took most of the 40 ms a batch spent in mr_align_batch (against 7.5 from locked memory).
-  auto unlock_batch = [&](read_batch& b) {
-    for(int i = 0; i < 2; ++i) if(b.locked[i]) { mr_host_unpin(ds.ctx[0], b.locked[i]); b.locked[i] = nullptr; }
+  auto now_us = []() { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  // Host -> device copies go through page-locked staging slots, two per context, locked ONCE (cudaHostRegister costs
+  // 0.3-1.6 ms per MB depending on the host, and holds up the other threads' kernel launches while it runs): the
+  // uploader thread copies a batch's packed arrays (0.375 bytes per base) into a free slot, the aligner's copy to the
+  // device is then plain DMA.  Copying straight from the batch's pageable arrays made the driver stage the data itself,
+  // next to a reader that faults pages in all the time: 20-40 ms per 13 MB batch.  MR_STAGE_SLOTS=0: pageable copies.
+  struct pin_slot { uint64_t* codes = nullptr; uint64_t* nmask = nullptr; size_t ccap = 0, mcap = 0; };
+  static const bool use_slots = !(getenv("MR_STAGE_SLOTS") && atoi(getenv("MR_STAGE_SLOTS")) == 0);
+  std::vector<std::vector<pin_slot>> slots(ds.ctx.size(), std::vector<pin_slot>(2));
+  std::vector<std::unique_ptr<bounded_queue<int>>> free_slots;
+  for(size_t g = 0; g < ds.ctx.size(); ++g) {
+    free_slots.emplace_back(new bounded_queue<int>(2));
+    free_slots[g]->push(0); free_slots[g]->push(1);
+  }
+  auto slot_release = [&](size_t g, pin_slot& sl) {
+    if(sl.codes) { mr_host_unpin(ds.ctx[g], sl.codes); free(sl.codes); sl.codes = nullptr; }
+    if(sl.nmask) { mr_host_unpin(ds.ctx[g], sl.nmask); free(sl.nmask); sl.nmask = nullptr; }
+    sl.ccap = sl.mcap = 0;
   };
-  auto lock_batch = [&](read_batch& b) {
-    const void* p[2] = { b.codes.data(), b.nmask.data() };
-    const size_t n[2] = { b.codes.capacity() * 8, b.nmask.capacity() * 8 };
-    for(int i = 0; i < 2; ++i) {
-      if(b.locked[i] == p[i] || !p[i]) continue;
-      if(b.locked[i]) { mr_host_unpin(ds.ctx[0], b.locked[i]); b.locked[i] = nullptr; }
-      if(mr_host_pin(ds.ctx[0], p[i], n[i]) == MR_OK) b.locked[i] = p[i];
+  // copies the batch's packed arrays into the slot (grown and locked as needed); false: use the batch's own arrays
+  auto slot_fill = [&](size_t g, pin_slot& sl, const read_batch& b) -> bool {
+    const size_t cw = b.codes.size(), mw = b.nmask.size();
+    if(cw > sl.ccap || mw > sl.mcap) {
+      slot_release(g, sl);
+      const size_t cc = cw + cw / 4 + 1024, mc = mw + mw / 4 + 1024;
+      void *pc = nullptr, *pm = nullptr;
+      if(posix_memalign(&pc, 4096, cc * 8) != 0 || posix_memalign(&pm, 4096, mc * 8) != 0) { free(pc); free(pm); return false; }
+      if(mr_host_pin(ds.ctx[g], pc, cc * 8) != MR_OK) { free(pc); free(pm); return false; }
+      if(mr_host_pin(ds.ctx[g], pm, mc * 8) != MR_OK) { mr_host_unpin(ds.ctx[g], pc); free(pc); free(pm); return false; }
+      sl.codes = (uint64_t*)pc; sl.nmask = (uint64_t*)pm; sl.ccap = cc; sl.mcap = mc;
     }
+    memcpy(sl.codes, b.codes.data(), cw * 8);
+    memcpy(sl.nmask, b.nmask.data(), mw * 8);
+    return true;
   };
   auto recycle = [&](std::unique_ptr<read_batch>& b) {
     if(!b) return;
     std::lock_guard<std::mutex> l(pool_mutex);
     if(pool.size() < 16) pool.push_back(std::move(b));
-    else { unlock_batch(*b); b.reset(); }
+    else b.reset();
   };
   // MR_SHOW_TIMING: seconds every stage was busy (the stages overlap; the largest one bounds the phase)
   static const bool stage_timing = getenv("MR_SHOW_TIMING") != nullptr;
   std::atomic<uint64_t> busy_read_us(0), busy_upload_us(0), busy_align_us(0), busy_format_us(0), busy_write_us(0);
-  auto now_us = []() { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 
   std::thread reader([&]() {
     background_thread();
@@ -216,7 +235,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           std::lock_guard<std::mutex> l(pool_mutex);
           if(!pool.empty()) { j.batch = std::move(pool.back()); pool.pop_back(); }
         }
-        if(!j.batch) { j.batch.reset(new read_batch); j.batch->before_regrow = unlock_batch; }
+        if(!j.batch) j.batch.reset(new read_batch);
         j.batch->clear();
         const uint64_t t0 = now_us();
         const bool more = rs.next_batch(*j.batch, batch_bases, batch_reads, true);      // parsed and packed by the reader's workers
@@ -231,7 +250,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
 
   // per context: an uploader thread stages the next batch (host -> device copy on the context's copy
   // stream, mr_stage_batch) while the aligner thread runs the kernels of the current one
-  struct staged_job { job j; mr_staged* staged; };
+  struct staged_job { job j; mr_staged* staged; int slot = -1; };
   std::vector<std::unique_ptr<bounded_queue<staged_job>>> staged;
   for(size_t g = 0; g < ds.ctx.size(); ++g) staged.emplace_back(new bounded_queue<staged_job>(1));
   std::vector<std::thread> aligners, uploaders;
@@ -244,7 +263,11 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
         sj.staged = nullptr;
         const uint64_t t0 = now_us();
         if(!j.batch->packed()) j.batch->pack();  // 2 bits per base + non-ACGT mask: what crosses PCIe
-        lock_batch(*j.batch);
+        if(use_slots && !stage_batches()) {
+          int k = -1;
+          if(free_slots[g]->pop(k) && !slot_fill(g, slots[g][k], *j.batch)) { free_slots[g]->push(std::move(k)); k = -1; }
+          sj.slot = k;
+        }
         if(stage_batches() && !failed && mr_stage_batch_packed(ds.ctx[g], j.batch->codes.data(), j.batch->nmask.data(), j.batch->start.data(), j.batch->nreads(), &sj.staged) != MR_OK)
           sj.staged = nullptr;                  // the aligner retries through mr_align_batch and reports what is wrong
         busy_upload_us += now_us() - t0;
@@ -257,7 +280,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
       staged_job sj;
       while(staged[g]->pop(sj)) {
         job j = std::move(sj.j);
-        if(failed) { if(sj.staged) mr_staged_free(sj.staged); continue; }
+        if(failed) { if(sj.staged) mr_staged_free(sj.staged); if(sj.slot >= 0) { int k = sj.slot; free_slots[g]->push(std::move(k)); } continue; }
         // A batch whose hits exceed a device limit (very repeat-rich reads) or the free memory is cut
         // in halves and retried; the halves are formatted in order, so the output does not change.
         std::deque<std::unique_ptr<read_batch>> work;
@@ -271,7 +294,10 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
           if(sj.staged) { rc = mr_align_staged(ds.ctx[g], ds.idx[g], &params, sj.staged, &pt.result); sj.staged = nullptr; }
           else {
             if(!b->packed()) b->pack();         // a half of a batch that had to be split
-            rc = mr_align_batch_packed(ds.ctx[g], ds.idx[g], &params, b->codes.data(), b->nmask.data(), b->start.data(), b->nreads(), &pt.result);
+            const bool from_slot = sj.slot >= 0;
+            rc = mr_align_batch_packed(ds.ctx[g], ds.idx[g], &params, from_slot ? slots[g][sj.slot].codes : b->codes.data(),
+                                       from_slot ? slots[g][sj.slot].nmask : b->nmask.data(), b->start.data(), b->nreads(), &pt.result);
+            if(from_slot) { int k = sj.slot; sj.slot = -1; free_slots[g]->push(std::move(k)); }    // (a batch that is split is retried from its own arrays)
           }
           if(rc == MR_OK) { pt.batch = std::move(b); j.parts.push_back(std::move(pt)); continue; }
           if((rc == MR_ELIMIT || rc == MR_ENOMEM) && b->nreads() > 1) {
@@ -285,7 +311,6 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
             hi->name.assign(b->name.begin() + half, b->name.end());
             work.push_front(std::move(hi));
             work.push_front(std::move(lo));
-            unlock_batch(*b);                   // (the whole batch is dropped here; its halves are plain batches)
             continue;
           }
           fail(std::string("mr_align_batch: ") + mr_last_error(ds.ctx[g]));
@@ -332,7 +357,7 @@ uint64_t run_pipeline(device_set& ds, const std::vector<std::string>& read_paths
   for(auto& t : aligners) t.join();
   formatter.join();
   fflush(out);
-  for(auto& b : pool) unlock_batch(*b);
+  for(size_t g = 0; g < ds.ctx.size(); ++g) for(auto& sl : slots[g]) slot_release(g, sl);
   if(stage_timing)
     fprintf(stderr, "stage busy seconds (overlapping): read+pack %.3f, upload %.3f (%zu threads), align %.3f (%zu threads), format %.3f, write %.3f\n",
             1e-6 * busy_read_us, 1e-6 * busy_upload_us, ds.ctx.size(), 1e-6 * busy_align_us, ds.ctx.size(), 1e-6 * busy_format_us, 1e-6 * busy_write_us);

@@ -499,7 +499,8 @@ struct span { double lo, up; };
 
 // joining interval set of [lo, up) pieces: boost::icl::interval_set<double> as used by tile_greedy
 struct joined_set {
-  std::vector<span> v;
+  std::vector<span> v, nv;                     // nv: scratch of add(), kept so that a read's tiling does not allocate per piece
+  void clear() { v.clear(); }
   bool overlaps_at_least(const span& x, double limit) const {
     for(const span& y : v) {
       const double lo = std::max(y.lo, x.lo), up = std::min(y.up, x.up);
@@ -509,7 +510,7 @@ struct joined_set {
   }
   void add(span x) {
     if(!(x.lo < x.up)) return;
-    std::vector<span> nv;
+    nv.clear();
     bool placed = false;
     for(const span& y : v) {
       if(y.up < x.lo) nv.push_back(y);
@@ -639,6 +640,10 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
   std::vector<double> weights;
   struct seq_piece { const char* p; size_t n; };
   std::vector<seq_piece> pieces;
+  std::vector<int> comp_slot, comp_root;
+  std::vector<mega_read> comp_mr;
+  joined_set covered;
+  std::vector<span> placed;
   char buf[1024];
   // ids come from super-read names, lengths from the -l/-u table: the libraries refuse a table that
   // does not cover the names (mr_align_batch, mr_graph_batch), this keeps a stray id from reading
@@ -655,8 +660,11 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       return t < sr.path_len(s) ? (sr.path_at(s, v.use_bwd[row], t) >> 1) : 0x7fffffffu;
     };
 
-    // mega_reads_per_comp (overlap_graph.cc:116-161): components in increasing root order
-    std::map<int, mega_read> comps;
+    // mega_reads_per_comp (overlap_graph.cc:116-161): the best mega-read of every component, components in increasing
+    // root order (the reference keeps them in a std::map keyed by the root; a root is a node number below n, so a table
+    // of slots does the same without a tree node per component)
+    comp_slot.assign((size_t)n, -1);
+    comp_mr.clear(); comp_root.clear();
     for(int i = 0; i < n; ++i) {
       const uint64_t row = b + i;
       mega_read mr;
@@ -719,23 +727,26 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
       }
       if(!v.end_node[row] || mr.density < o.density || (mr.tiling_end - mr.tiling_start) < o.min_length) continue;
       const int root = v.component[row];
-      auto it = comps.find(root);
-      if(it == comps.end()) comps.insert(std::make_pair(root, mr));
+      if(root < 0 || root >= n) throw std::out_of_range("component root outside the read's rows");
+      const int slot = comp_slot[(size_t)root];
+      if(slot < 0) { comp_slot[(size_t)root] = (int)comp_mr.size(); comp_mr.push_back(mr); comp_root.push_back(root); }
       else {
-        const int olpath = v.lpath[b + it->second.end_node];
-        if(v.lpath[row] > olpath || (v.lpath[row] == olpath && mr.density > it->second.density)) it->second = mr;
+        mega_read& cur = comp_mr[(size_t)slot];
+        const int olpath = v.lpath[b + cur.end_node];
+        if(v.lpath[row] > olpath || (v.lpath[row] == olpath && mr.density > cur.density)) cur = mr;
       }
     }
-    if(comps.empty()) continue;
+    if(comp_mr.empty()) continue;
     mrs.clear(); sort_tiling.clear(); tiled.clear();
-    for(const auto& c : comps) { sort_tiling.push_back((int)mrs.size()); mrs.push_back(c.second); }
+    for(int root = 0; root < n; ++root)
+      if(comp_slot[(size_t)root] >= 0) { sort_tiling.push_back((int)mrs.size()); mrs.push_back(comp_mr[(size_t)comp_slot[(size_t)root]]); }
     auto lpath_of = [&](int m) { return v.lpath[b + mrs[m].end_node]; };
     auto by_pos = [&](int i, int j) {
       return mrs[i].imp_s < mrs[j].imp_s || (mrs[i].imp_s == mrs[j].imp_s && mrs[i].imp_e < mrs[j].imp_e);
     };
     auto greedy = [&]() {                                  // tile_greedy (overlap_graph.cc:165-197)
-      joined_set covered;
-      std::vector<span> placed;
+      covered.clear();
+      placed.clear();
       for(const int m : sort_tiling) {
         const span pos = { mrs[m].tiling_start, mrs[m].tiling_end };
         const double plen = pos.lo < pos.up ? pos.up - pos.lo : 0.0;

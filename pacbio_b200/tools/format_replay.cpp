@@ -19,6 +19,8 @@ int main(int argc, char** argv) {
     U.load_sequences(argv[3]);
     mrh::graph_options G;
     G.k_len = (uint32_t)atoi(argv[4]);
+    if(const char* e = getenv("MR_REPLAY_TILING")) G.tiling = atoi(e);       // 0 none, 1 greedy, 2 maximal, 3 weighted
+    if(const char* e = getenv("MR_REPLAY_TRIM")) G.trim = atoi(e);
     const unsigned threads = (unsigned)atoi(argv[5]);
     const int reps = argc > 6 ? atoi(argv[6]) : 5;
     std::vector<mrh::text_buf> parts;

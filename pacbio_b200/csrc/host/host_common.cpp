@@ -15,6 +15,9 @@
 #include <exception>
 #include <fstream>
 #include <functional>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <map>
 #include <stdexcept>
 #include <thread>
@@ -883,6 +886,63 @@ void format_mega_reads(const mr_result_view& v, const read_batch& batch, uint32_
   }
 }
 
+// Worker threads that outlive a call: a batch is formatted in a dozen slices (format_mega_reads_mt), and starting and
+// joining a set of threads for every slice costs as much as a tenth of the formatting itself when a GPU has four host
+// cores.  One pool per calling thread (the pipeline's formatter thread), created on first use, joined when that thread
+// ends.  run(n, f) calls f(0) .. f(n - 1), the caller taking its share, and returns when all of them are done.
+namespace {
+class worker_pool {
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  const std::function<void(unsigned)>* fn_ = nullptr;
+  unsigned ntasks_ = 0, next_ = 0, done_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+  void loop() {
+    background_thread();
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> l(m_);
+    while(true) {
+      cv_work_.wait(l, [&] { return stop_ || (generation_ != seen && next_ < ntasks_); });
+      if(stop_) return;
+      const uint64_t gen = generation_;
+      while(next_ < ntasks_) {
+        const unsigned t = next_++;
+        const std::function<void(unsigned)>* f = fn_;
+        l.unlock();
+        (*f)(t);
+        l.lock();
+        if(++done_ == ntasks_) cv_done_.notify_all();
+      }
+      seen = gen;
+    }
+  }
+public:
+  explicit worker_pool(unsigned workers) { for(unsigned i = 0; i < workers; ++i) th_.emplace_back([this] { loop(); }); }
+  ~worker_pool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_work_.notify_all();
+    for(auto& t : th_) t.join();
+  }
+  unsigned workers() const { return (unsigned)th_.size(); }
+  void run(unsigned ntasks, const std::function<void(unsigned)>& f) {
+    std::unique_lock<std::mutex> l(m_);
+    fn_ = &f; ntasks_ = ntasks; next_ = 0; done_ = 0; ++generation_;
+    cv_work_.notify_all();
+    while(next_ < ntasks_) {                         // the caller works too
+      const unsigned t = next_++;
+      l.unlock();
+      f(t);
+      l.lock();
+      ++done_;
+    }
+    cv_done_.wait(l, [&] { return done_ == ntasks_; });
+    fn_ = nullptr; ntasks_ = 0;                      // (a worker that wakes up late finds nothing to take)
+  }
+};
+}
+
 // Formats reads [r0, r1) on `threads` threads into parts[0 .. threads), split by coords rows so that the work is balanced.
 static void format_range_mt(const mr_result_view& v, const read_batch& batch, uint32_t r0, uint32_t r1, const super_reads& sr, const unitigs& u,
                             const graph_options& o, unsigned threads, std::vector<text_buf>& parts) {
@@ -912,10 +972,9 @@ static void format_range_mt(const mr_result_view& v, const read_batch& batch, ui
   if(threads == 1) { work(0); return; }
   // an exception in a worker must reach the caller's catch, not std::terminate
   std::vector<std::exception_ptr> errors(threads);
-  std::vector<std::thread> th;
-  for(unsigned t = 0; t < threads; ++t)
-    th.emplace_back([&, t]() { background_thread(); try { work(t); } catch(...) { errors[t] = std::current_exception(); } });
-  for(auto& x : th) x.join();
+  static thread_local std::unique_ptr<worker_pool> pool;
+  if(!pool || pool->workers() + 1 < threads) pool.reset(new worker_pool(threads - 1));
+  pool->run(threads, [&](unsigned t) { try { work(t); } catch(...) { errors[t] = std::current_exception(); } });
   for(auto& e : errors) if(e) std::rethrow_exception(e);
 }
 

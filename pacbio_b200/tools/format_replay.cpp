@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
+#include <string>
 
 #include "../csrc/host/host_common.hpp"
 
@@ -28,11 +29,17 @@ int main(int argc, char** argv) {
     uint64_t bytes = 0;
     for(int i = 0; i < reps; ++i) {
       const auto t0 = std::chrono::steady_clock::now();
-      mrh::format_mega_reads_mt(d.view, d.batch, SR, U, G, threads, parts);
+      // MR_REPLAY_SLICES=1: slice by slice through an emit callback, as the tools and bench.py's end-to-end arm do
+      std::string sliced;
+      uint64_t emitted = 0;
+      const mrh::emit_fn emit = [&](std::vector<mrh::text_buf>& ps) { for(auto& p : ps) { emitted += p.size(); if(argc > 7 && i == 0) sliced.append(p.data(), p.size()); } };
+      const bool slices = getenv("MR_REPLAY_SLICES") != nullptr;
+      mrh::format_mega_reads_mt(d.view, d.batch, SR, U, G, threads, parts, slices ? &emit : nullptr);
       const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       best = std::min(best, s);
-      bytes = 0;
+      bytes = emitted;
       for(auto& p : parts) bytes += p.size();
+      if(slices && argc > 7 && i == 0) { FILE* f = fopen(argv[7], "w"); fwrite(sliced.data(), 1, sliced.size(), f); fclose(f); }
       if(i == 0 && getenv("MR_REPLAY_PARTS")) {          // how even the split between the threads is
         fprintf(stderr, "bytes per part:");
         for(auto& p : parts) fprintf(stderr, " %zu", p.size());
@@ -41,7 +48,7 @@ int main(int argc, char** argv) {
     }
     printf("{\"reads\": %u, \"rows\": %llu, \"text_bytes\": %llu, \"threads\": %u, \"best_s\": %.6f, \"thread_seconds\": %.6f}\n",
            d.view.nreads, (unsigned long long)d.view.ncoords, (unsigned long long)bytes, threads, best, best * threads);
-    if(argc > 7) { FILE* f = fopen(argv[7], "w"); for(auto& p : parts) fwrite(p.data(), 1, p.size(), f); fclose(f); }
+    if(argc > 7 && !getenv("MR_REPLAY_SLICES")) { FILE* f = fopen(argv[7], "w"); for(auto& p : parts) fwrite(p.data(), 1, p.size(), f); fclose(f); }
   } catch(std::exception& e) { fprintf(stderr, "format_replay: %s\n", e.what()); return 1; }
   return 0;
 }

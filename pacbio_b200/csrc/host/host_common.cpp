@@ -986,7 +986,7 @@ static void format_range_mt(const mr_result_view& v, const read_batch& batch, ui
 void format_mega_reads_mt(const mr_result_view& v, const read_batch& batch, const super_reads& sr, const unitigs& u,
                           const graph_options& o, unsigned threads, std::vector<text_buf>& parts, const emit_fn* emit) {
   if(!emit || !*emit) { format_range_mt(v, batch, 0, v.nreads, sr, u, o, threads, parts); return; }
-  static const size_t kSliceBytes = [] { const char* e = getenv("MR_FORMAT_SLICE_KB"); const long x = e ? atol(e) : 0; return (size_t)(x > 0 ? x : 1536) << 10; }();
+  static const size_t kSliceBytes = [] { const char* e = getenv("MR_FORMAT_SLICE_KB"); const long x = e ? atol(e) : 0; return (size_t)(x > 0 ? x : 1024) << 10; }();
   threads = std::max(1u, threads);
   const uint64_t per_slice = std::max<uint64_t>((uint64_t)threads * kSliceBytes * 2 / 3, 1 << 16);       // read bases per slice (1.5 bytes of text each)
   uint32_t r0 = 0;

@@ -457,7 +457,22 @@ bool read_stream::next_batch(read_batch& b, uint64_t max_bases, uint32_t max_rea
 namespace {
 // ---- number formatting.  A mega-read line holds three "%.2f" / "%.4f" doubles (overlap_graph.cc:285-290);
 // glibc's printf spends ~0.4 us on each (multi-precision), a quarter of the whole formatting stage.
+// decimal digits of a 32-bit number, two at a time from a table (the unitig numbers of a mega-read line: tens of
+// thousands per batch)
+inline int fmt_u32(char* p, uint32_t v) {
+  static const char pairs[201] =
+    "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+    "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+  const int n = v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6 : v < 10000000 ? 7
+              : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
+  char* q = p + n;
+  while(v >= 100) { const uint32_t r = v % 100; v /= 100; q -= 2; q[0] = pairs[2 * r]; q[1] = pairs[2 * r + 1]; }
+  if(v >= 10) { q -= 2; q[0] = pairs[2 * v]; q[1] = pairs[2 * v + 1]; }
+  else *--q = (char)('0' + v);
+  return n;
+}
 inline int fmt_uint(char* p, uint64_t v) {
+  if(v <= 0xffffffffULL) return fmt_u32(p, (uint32_t)v);
   char t[24];
   int n = 0;
   do { t[n++] = (char)('0' + v % 10); v /= 10; } while(v);

@@ -184,13 +184,15 @@ ALL_CPUS = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") e
 PINNED = False
 
 
-def unpin():
+def unpin(cmd):
     """The subprocess arms (the reference binary, the drop-in binary) get every core of the box, whatever this rank is
-    pinned to: returns the preexec_fn to give subprocess.run (None when the rank is not pinned -- a preexec_fn makes
-    Python fork() the whole CUDA process instead of spawning)."""
+    pinned to: the command is started through taskset.  (Not a preexec_fn: that makes Python fork() this process --
+    CUDA context, NCCL threads and all -- and run Python code in the child before the exec.)"""
     if not (PINNED and ALL_CPUS):
-        return None
-    return lambda: os.sched_setaffinity(0, ALL_CPUS)
+        return cmd
+    import shutil
+    ts = shutil.which("taskset")
+    return [ts, "-c", ",".join(map(str, ALL_CPUS))] + cmd if ts else cmd
 
 
 def pin_rank(local_rank, nranks):
@@ -328,7 +330,7 @@ def cpu_run(w, files, nreads_sample, threads):
     if os.path.exists(ref):
         cmd = [ref] + production_flags(w, files, threads) + ["-p", sample, "-o", out]
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
+        r = subprocess.run(unpin(cmd), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError("reference run failed: " + r.stderr.decode()[-500:])
@@ -478,7 +480,7 @@ def cli_run(w, files, total_bases, host_threads, gpus=1):
     best = None
     for _ in range(2):                           # second run: page cache warm, as for the reference arm
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
+        r = subprocess.run(unpin(cmd), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError("create_mega_reads failed: " + r.stderr.decode()[-300:])
@@ -508,7 +510,7 @@ def cli_run(w, files, total_bases, host_threads, gpus=1):
         env_n = {k: v for k, v in env.items() if k != "MR_DEVICES"}
         env_n["MR_GPUS"] = str(gpus)
         t0 = time.perf_counter()
-        r = subprocess.run(cmd_n, env=env_n, stdout=subprocess.PIPE, stderr=subprocess.PIPE, preexec_fn=unpin())
+        r = subprocess.run(unpin(cmd_n), env=env_n, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             best["multi_gpu"] = {"gpus": gpus, "error": r.stderr.decode()[-300:]}

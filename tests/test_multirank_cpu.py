@@ -42,3 +42,26 @@ def test_reference_arm_other_ranks_do_no_work(tmp_path):
                         "--genome", "40000", "--coverage", "2", "--steps", "1", "--warmup", "0"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == b""
+
+
+def test_ranks_are_pinned_to_disjoint_cores_and_subprocess_arms_are_not():
+    """bench.pin_rank: every local rank keeps to its own share of the cores (all of them together cover the box once);
+    the subprocess arms (reference binary, drop-in binary) are started through taskset with the whole core set."""
+    code = ("import sys, os, json; sys.path.insert(0, %r); import bench\n"
+            "r, n = int(sys.argv[1]), int(sys.argv[2])\n"
+            "before = sorted(os.sched_getaffinity(0))\n"
+            "info = bench.pin_rank(r, n)\n"
+            "print(json.dumps({'before': before, 'after': sorted(os.sched_getaffinity(0)), 'info': info, 'cmd': bench.unpin(['true'])}))\n" % ROOT)
+    env = dict(os.environ)
+    env.pop("MR_BENCH_PIN", None)
+    rows = [json.loads(subprocess.run([sys.executable, "-c", code, str(r), "2"], stdout=subprocess.PIPE, check=True, env=env).stdout) for r in range(2)]
+    every = rows[0]["before"]
+    if len(every) < 2:
+        return
+    assert sorted(rows[0]["after"] + rows[1]["after"]) == every and not set(rows[0]["after"]) & set(rows[1]["after"])
+    for x in rows:
+        assert x["info"] is not None
+        cmd = x["cmd"]
+        assert cmd[-1] == "true" and (len(cmd) == 1 or (cmd[0].endswith("taskset") and cmd[2] == ",".join(map(str, every))))
+    one = json.loads(subprocess.run([sys.executable, "-c", code, "0", "1"], stdout=subprocess.PIPE, check=True, env=env).stdout)
+    assert one["info"] is None and one["after"] == one["before"] and one["cmd"] == ["true"]
